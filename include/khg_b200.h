@@ -1,0 +1,227 @@
+/* include/khg_b200.h — C ABI of libkhg_b200.so
+ *
+ * B200-native (sm_100a) implementation of ONE hot path of
+ * csukuangfj/kaldi-hmm-gmm v1.1.4: the E-step of diagonal-GMM acoustic-model
+ * training (per-frame log-likelihoods + alignment-driven sufficient
+ * statistics).  This header is the drop-in boundary: plain C types, caller-
+ * owned buffers, opaque handles.  The reference has no FFI of its own (it is
+ * C++ classes behind pybind11, python/csrc/kaldi-hmm-gmm.cc:35-68); each entry
+ * point below names the reference C++ interface whose arithmetic it replaces
+ * (paths relative to kaldi-hmm-gmm/ in the reference).  INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - Every function returns khg_status (0 = KHG_OK).  On failure
+ *    khg_last_error() returns a thread-local message; the C++/pybind layer
+ *    turns it into std::runtime_error, the reference's error convention
+ *    (csrc/log.h:46-53).
+ *  - There is NO CPU fallback: without a CUDA device every compute entry point
+ *    fails with KHG_ERR_CUDA.
+ *  - `loc` arguments say where a caller buffer lives: KHG_HOST or KHG_DEVICE.
+ *    Host buffers are copied inside the call; device buffers are used in place.
+ *  - A call whose outputs are all device-resident is asynchronous on the
+ *    handle's stream; data-dependent failures (a NaN/Inf log-likelihood, which
+ *    makes the reference throw: csrc/diag-gmm.cc:160-162, 385-387,
+ *    csrc/decodable-am-diag-gmm.cc:63-65) are latched in a device flag and
+ *    reported by the next synchronising call or by khg_model_sync().
+ *  - Handles are thread-compatible, not thread-safe, like the reference's
+ *    classes.  One process drives one GPU (khg_set_device).
+ *  - Matrices are row-major fp32 like the reference's FloatMatrix
+ *    (csrc/eigen.h:10-22); statistics are fp64 (csrc/mle-diag-gmm.h:174-181).
+ */
+#ifndef KHG_B200_H_
+#define KHG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t khg_status;
+enum {
+  KHG_OK = 0,
+  KHG_ERR_INVALID = 1,    /* bad argument (the reference KHG_ASSERTs) */
+  KHG_ERR_CUDA = 2,       /* CUDA runtime failure / no device */
+  KHG_ERR_NONFINITE = 3,  /* NaN/Inf log-likelihood or NaN gconst */
+  KHG_ERR_UNSUPPORTED = 4
+};
+
+enum { KHG_HOST = 0, KHG_DEVICE = 1 };
+
+/* Layout of an all-pdf log-likelihood block. */
+enum {
+  KHG_FRAME_MAJOR = 0, /* out[t*ld + p]: what LogLikelihoodsMatrix-style callers expect */
+  KHG_PDF_MAJOR = 1    /* out[p*ld + t]: native layout of the tensor-core kernel        */
+};
+
+/* GmmUpdateFlags, csrc/model-common.h:18-26 */
+enum {
+  KHG_GMM_MEANS = 0x001,
+  KHG_GMM_VARIANCES = 0x002,
+  KHG_GMM_WEIGHTS = 0x004,
+  KHG_GMM_TRANSITIONS = 0x008,
+  KHG_GMM_ALL = 0x00F
+};
+
+/* Which kernel computes the dense all-pdf log-likelihoods. */
+enum {
+  KHG_KERNEL_AUTO = 0,
+  KHG_KERNEL_SIMT = 1,   /* fp32 FMA kernel (any dim, any pdf size) */
+  KHG_KERNEL_TCGEN05 = 2 /* tcgen05 3xTF32 kernel, TMA-staged model tiles */
+};
+
+typedef struct khg_model khg_model; /* device-resident packed AmDiagGmm      */
+typedef struct khg_stats khg_stats; /* device-resident packed AccumAmDiagGmm */
+
+const char *khg_last_error(void);
+int32_t khg_abi_version(void);
+
+khg_status khg_device_count(int32_t *count);
+khg_status khg_set_device(int32_t device);
+/* AugmentGmmFlags, csrc/model-common.cc:72-84 */
+uint16_t khg_augment_flags(uint16_t flags);
+
+/* ---------------------------------------------------------------- model --
+ * Replaces the storage of DiagGmm (csrc/diag-gmm.h:243-257) / AmDiagGmm
+ * (csrc/am-diag-gmm.h:96): one contiguous pack of G = gauss_offsets[P]
+ * Gaussians; pdf p owns [gauss_offsets[p], gauss_offsets[p+1]). */
+khg_status khg_model_create(int32_t dim, int32_t num_pdfs,
+                            const int32_t *gauss_offsets /* host, P+1 */,
+                            khg_model **out);
+/* Uploads parameters (host pointers).  gconsts==NULL -> computed on the device
+ * from weights exactly as DiagGmm::ComputeGconsts (csrc/diag-gmm.cc:103-147):
+ * *num_bad receives the count of +-inf gconsts; a NaN gconst fails with
+ * KHG_ERR_NONFINITE.  weights may be NULL when gconsts is given. */
+khg_status khg_model_upload(khg_model *m, const float *weights /* G */,
+                            const float *means_invvars /* G x D */,
+                            const float *inv_vars /* G x D */,
+                            const float *gconsts /* G or NULL */,
+                            int32_t *num_bad /* may be NULL */);
+khg_status khg_model_get_gconsts(khg_model *m, float *gconsts /* host, G */);
+khg_status khg_model_info(const khg_model *m, int32_t *dim, int32_t *num_pdfs,
+                          int32_t *num_gauss);
+/* Chooses the dense-likelihood kernel (default KHG_KERNEL_AUTO). */
+khg_status khg_model_set_kernel(khg_model *m, int32_t kernel);
+/* Launches on this CUDA stream (a cudaStream_t; NULL = default stream). */
+khg_status khg_model_set_stream(khg_model *m, void *cuda_stream);
+/* Synchronises the stream and reports (then clears) a latched NaN/Inf. */
+khg_status khg_model_sync(khg_model *m);
+void khg_model_destroy(khg_model *m);
+
+/* Stateless DiagGmm::ComputeGconsts (csrc/diag-gmm.cc:103-147), host buffers. */
+khg_status khg_compute_gconsts(int32_t nmix, int32_t dim, const float *weights,
+                               const float *means_invvars,
+                               const float *inv_vars, float *gconsts,
+                               int32_t *num_bad);
+
+/* ---------------------------------------------------------- likelihoods --
+ * All-pdf log-likelihood block: out(t,p) = scale * LogSumExp_g(loglike(t,g)),
+ * g over pdf p.  Replaces, for every (frame, pdf) at once,
+ * DecodableAmDiagGmmUnmapped::LogLikelihoodZeroBased
+ * (csrc/decodable-am-diag-gmm.cc:29-71), DecodableAmDiagGmmScaled::
+ * LogLikelihood (csrc/decodable-am-diag-gmm.h:94-98) and AmDiagGmm::
+ * LogLikelihood (csrc/am-diag-gmm.cc:121-124).  feats is T x dim. */
+khg_status khg_loglikes_all_pdfs(khg_model *m, const float *feats, int64_t T,
+                                 int32_t feats_loc, float scale, int32_t layout,
+                                 float *out, int64_t ld_out, int32_t out_loc);
+
+/* Per-Gaussian log-likelihoods of ONE pdf: out is T x g_p (frame-major).
+ * DiagGmm::LogLikelihoods (csrc/diag-gmm.cc:167-176) for T==1,
+ * DiagGmm::LogLikelihoodsMatrix (:177-189) for T>1. */
+khg_status khg_pdf_loglikes(khg_model *m, int32_t pdf, const float *feats,
+                            int64_t T, int32_t loc, float *out);
+
+/* Posteriors of ONE pdf for T frames: post is T x g_p, loglike is T.
+ * DiagGmm::ComponentPosteriors (csrc/diag-gmm.cc:368-392) + Softmax
+ * (csrc/eigen.cc:20-32); loglike alone = DiagGmm::LogLikelihood (:150-165).
+ * post may be NULL.  NaN/Inf log-like -> KHG_ERR_NONFINITE. */
+khg_status khg_pdf_posteriors(khg_model *m, int32_t pdf, const float *feats,
+                              int64_t T, int32_t loc, float *post,
+                              float *loglike);
+
+/* ---------------------------------------------------------------- stats --
+ * Replaces AccumDiagGmm storage (csrc/mle-diag-gmm.h:174-181) for all pdfs and
+ * the totals of AccumAmDiagGmm (csrc/mle-am-diag-gmm.h:93-96).  One packed fp64
+ * device buffer: [occ G | mean G*D (if m) | var G*D (if v) | tot_like |
+ * tot_frames].  flags are augmented v=>m=>w (csrc/model-common.cc:72-84). */
+khg_status khg_stats_create(khg_model *m, uint16_t flags, khg_stats **out);
+khg_status khg_stats_zero(khg_stats *s);
+khg_status khg_stats_flags(const khg_stats *s, uint16_t *flags);
+/* Packed device buffer for the multi-GPU sum (NCCL all-reduce through
+ * torch.distributed, or AccumAmDiagGmm::Add semantics on one device). */
+khg_status khg_stats_device_buffer(khg_stats *s, double **dev_ptr,
+                                   int64_t *num_doubles);
+/* Host copies; any pointer may be NULL.  totals = {tot_like, tot_frames}. */
+khg_status khg_stats_download(khg_stats *s, double *occ, double *mean,
+                              double *var, double *totals);
+khg_status khg_stats_upload(khg_stats *s, const double *occ, const double *mean,
+                            const double *var, const double *totals);
+/* dst += scale * src : AccumAmDiagGmm::Add (csrc/mle-am-diag-gmm.cc:119-128);
+ * note the reference takes a float scale. */
+khg_status khg_stats_add(khg_stats *dst, float scale, const khg_stats *src);
+/* AccumAmDiagGmm::Scale (csrc/mle-am-diag-gmm.cc:130-138) */
+khg_status khg_stats_scale(khg_stats *s, float scale);
+void khg_stats_destroy(khg_stats *s);
+
+/* The gmm-acc-stats-ali inner loop for T frames in one call:
+ * for each frame t, AccumAmDiagGmm::AccumulateForGmm(model, feats[t],
+ * pdf_ids[t], w[t]) (csrc/mle-am-diag-gmm.cc:41-52 -> csrc/mle-diag-gmm.cc:
+ * 145-158 -> csrc/diag-gmm.cc:368-392 -> csrc/mle-diag-gmm.cc:123-143).
+ * Frames are bucketed by pdf id on the device (exact integer sort), posteriors
+ * and statistics are accumulated per pdf, totals += {sum ll*w, sum w}.
+ *   pdf_ids        int32[T]  (same loc as feats)
+ *   frame_weights  f32[T] or NULL (=1)         (same loc as feats)
+ *   per_frame_loglike f32[T] or NULL: the UNWEIGHTED per-frame log-like
+ *                  AccumulateForGmm returns              (same loc as feats)
+ *   tot_loglike    host double or NULL: this call's sum ll*w (forces a sync) */
+khg_status khg_acc_stats_ali(khg_model *m, khg_stats *s, const float *feats,
+                             int64_t T, int32_t loc, const int32_t *pdf_ids,
+                             const float *frame_weights,
+                             float *per_frame_loglike, double *tot_loglike);
+
+/* Same, from transition-ids: pdf = tid2pdf[tid]
+ * (TransitionModel::TransitionIdToPdf, csrc/transition-information.h:71-73) and
+ * trans_accs[tid] += 1 (TransitionModel::Accumulate with prob 1,
+ * csrc/transition-model.h:183-189) — the whole body of
+ * scripts/gmm_acc_stats_ali.py:46-56.  All pointers are HOST pointers.
+ *   tid2pdf int32[num_tids+1] (index 0 unused), trans_accs double[num_tids+1]
+ *   (updated in place, may be NULL). */
+khg_status khg_acc_stats_ali_tids(khg_model *m, khg_stats *s,
+                                  const float *feats, int64_t T,
+                                  const int32_t *tids, const int32_t *tid2pdf,
+                                  int32_t num_tids, double *trans_accs,
+                                  double *tot_loglike);
+
+/* AccumDiagGmm::AccumulateFromPosteriors (csrc/mle-diag-gmm.cc:123-143) for T
+ * frames of one pdf: post is T x g_p; totals[1] += sum(post)
+ * (csrc/mle-am-diag-gmm.cc:78-86).  Host or device buffers per loc. */
+khg_status khg_acc_from_posteriors(khg_model *m, khg_stats *s, int32_t pdf,
+                                   const float *feats, int64_t T, int32_t loc,
+                                   const float *post);
+
+/* Whole E-step over one batch, as BASELINE.json's north_star words it:
+ * dense all-pdf log-likelihoods (what gmm-align-compiled consumes) AND the
+ * alignment-driven statistics (what gmm-acc-stats-ali produces).
+ * loglikes_out: DEVICE buffer of at least num_pdfs * ld_out floats, pdf-major,
+ * ld_out >= chunk_frames; it is reused chunk by chunk (the consumer is on the
+ * device side of the boundary).  feats/pdf_ids/frame_weights per `loc`; with
+ * KHG_HOST the call streams chunks through pinned staging buffers, copy
+ * overlapped with compute.  chunk_frames<=0 picks a default. */
+khg_status khg_estep(khg_model *m, khg_stats *s, const float *feats, int64_t T,
+                     int32_t loc, const int32_t *pdf_ids,
+                     const float *frame_weights, float *loglikes_out,
+                     int64_t ld_out, int64_t chunk_frames,
+                     double *tot_loglike);
+
+/* Device M-step: MleAmDiagGmmUpdate without Gaussian
+ * removal is planned for a later round; not exported yet. */
+
+/* Number of kernels this library launched since load (bench.py's
+ * gpu_launches). */
+int64_t khg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KHG_B200_H_ */

@@ -1,0 +1,759 @@
+// kaldi-hmm-gmm_b200/csrc/khg_b200.cu — C ABI (include/khg_b200.h) of the B200-native
+// diag-GMM E-step.  Host-side orchestration only; the arithmetic is in
+// khg_kernels.cuh (SIMT) and khg_loglikes_tc.cu (tcgen05).  No CPU fallback:
+// every compute entry point needs a CUDA device.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "khg_internal.h"
+#include "khg_kernels.cuh"
+
+namespace khg {
+
+static thread_local std::string t_last_error;
+void set_error(const std::string &msg) { t_last_error = msg; }
+int64_t g_launch_count = 0;
+
+khg_status Buf::reserve(size_t bytes) {
+  if (bytes <= cap) return KHG_OK;
+  release();
+  size_t want = std::max(bytes, (size_t)256);
+  if (pinned)
+    KHG_CUDA_TRY(cudaMallocHost(&p, want));
+  else
+    KHG_CUDA_TRY(cudaMalloc(&p, want));
+  cap = want;
+  return KHG_OK;
+}
+void Buf::release() {
+  if (p) {
+    if (pinned) cudaFreeHost(p); else cudaFree(p);
+  }
+  p = nullptr;
+  cap = 0;
+}
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// Reads and clears the latched device error flag after synchronising.
+static khg_status sync_check(khg_model *m) {
+  KHG_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  int flag = 0;
+  KHG_CUDA_TRY(cudaMemcpy(&flag, m->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    KHG_CUDA_TRY(cudaMemset(m->d_err, 0, sizeof(int)));
+    if (flag & ERR_BAD_INDEX) {
+      set_error("index out of range (pdf id / transition id): KHG_ASSERT(gmm_index >= 0 && gmm_index < NumAccs())");
+      return KHG_ERR_INVALID;
+    }
+    set_error("Invalid answer (overflow or invalid variances/features?)");
+    return KHG_ERR_NONFINITE;
+  }
+  return KHG_OK;
+}
+
+// Returns a device pointer for a caller buffer: the buffer itself (KHG_DEVICE) or
+// a staged copy (KHG_HOST).
+template <class T>
+static khg_status stage_in(khg_model *m, Buf &buf, const T *src, size_t count, int loc, const T **dev) {
+  if (src == nullptr) { *dev = nullptr; return KHG_OK; }
+  if (loc == KHG_DEVICE) { *dev = src; return KHG_OK; }
+  KHG_TRY(buf.reserve(count * sizeof(T)));
+  KHG_CUDA_TRY(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, m->stream));
+  *dev = buf.as<T>();
+  return KHG_OK;
+}
+
+}  // namespace khg
+
+using namespace khg;
+
+extern "C" {
+
+const char *khg_last_error(void) { return t_last_error.c_str(); }
+int32_t khg_abi_version(void) { return 1; }
+int64_t khg_launch_count(void) { return g_launch_count; }
+
+khg_status khg_device_count(int32_t *count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    set_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    return KHG_ERR_CUDA;
+  }
+  *count = n;
+  return KHG_OK;
+}
+
+khg_status khg_set_device(int32_t device) {
+  KHG_CUDA_TRY(cudaSetDevice(device));
+  return KHG_OK;
+}
+
+uint16_t khg_augment_flags(uint16_t flags) {  // csrc/model-common.cc:72-84
+  flags &= KHG_GMM_ALL;
+  if (flags & KHG_GMM_VARIANCES) flags |= KHG_GMM_MEANS;
+  if (flags & KHG_GMM_MEANS) flags |= KHG_GMM_WEIGHTS;
+  if (!(flags & KHG_GMM_WEIGHTS)) flags |= KHG_GMM_WEIGHTS;
+  return flags;
+}
+
+// ------------------------------------------------------------------ model --
+khg_status khg_model_create(int32_t dim, int32_t num_pdfs, const int32_t *gauss_offsets,
+                            khg_model **out) {
+  KHG_REQUIRE(out != nullptr && gauss_offsets != nullptr, "null argument");
+  KHG_REQUIRE(dim > 0 && num_pdfs > 0, "nmix > 0 && dim > 0");
+  KHG_REQUIRE(gauss_offsets[0] == 0, "gauss_offsets[0] == 0");
+  int dev_count = 0;
+  KHG_TRY(khg_device_count(&dev_count));
+  if (dev_count <= 0) {
+    set_error("no CUDA device: libkhg_b200 has no CPU fallback");
+    return KHG_ERR_CUDA;
+  }
+  khg_model *m = new khg_model();
+  m->dim = dim;
+  m->P = num_pdfs;
+  m->h_offsets.assign(gauss_offsets, gauss_offsets + num_pdfs + 1);
+  for (int p = 0; p < num_pdfs; ++p) {
+    int ng = gauss_offsets[p + 1] - gauss_offsets[p];
+    if (ng <= 0) {
+      delete m;
+      set_error("KHG_ASSERT failed: every pdf needs at least one Gaussian (nmix > 0)");
+      return KHG_ERR_INVALID;
+    }
+    m->max_gp = std::max(m->max_gp, ng);
+  }
+  m->G = gauss_offsets[num_pdfs];
+  m->n_chunks = (m->G + kSimtChunk - 1) / kSimtChunk + 1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  auto fail = [&](cudaError_t e, const char *what) {
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    khg_model_destroy(m);
+    return KHG_ERR_CUDA;
+  };
+  cudaError_t e;
+  size_t gd = (size_t)m->G * dim;
+  if ((e = cudaMalloc(&m->d_offsets, sizeof(int32_t) * (num_pdfs + 1))) != cudaSuccess) return fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&m->d_weights, sizeof(float) * m->G)) != cudaSuccess) return fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&m->d_miv, sizeof(float) * gd)) != cudaSuccess) return fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&m->d_iv, sizeof(float) * gd)) != cudaSuccess) return fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&m->d_gconsts, sizeof(float) * m->G)) != cudaSuccess) return fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&m->d_packT, sizeof(float) * (size_t)m->n_chunks * 2 * dim * kSimtChunk)) != cudaSuccess) return fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&m->d_err, sizeof(int))) != cudaSuccess) return fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&m->d_scratch_int, sizeof(int) * 4)) != cudaSuccess) return fail(e, "cudaMalloc");
+  if ((e = cudaMemset(m->d_err, 0, sizeof(int))) != cudaSuccess) return fail(e, "cudaMemset");
+  if ((e = cudaMemcpy(m->d_offsets, gauss_offsets, sizeof(int32_t) * (num_pdfs + 1), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "cudaMemcpy");
+  // groups of 8 Gaussians per pdf for K3
+  std::vector<int32_t> grp(num_pdfs + 1, 0);
+  for (int p = 0; p < num_pdfs; ++p) grp[p + 1] = grp[p] + (gauss_offsets[p + 1] - gauss_offsets[p] + 7) / 8;
+  m->h_grp_start = grp;
+  if ((e = cudaMalloc(&m->d_grp_start, sizeof(int32_t) * (num_pdfs + 1))) != cudaSuccess) return fail(e, "cudaMalloc");
+  if ((e = cudaMemcpy(m->d_grp_start, grp.data(), sizeof(int32_t) * (num_pdfs + 1), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "cudaMemcpy");
+  if ((e = cudaMalloc(&m->d_pack8, sizeof(float) * (size_t)grp[num_pdfs] * 2 * dim * 8)) != cudaSuccess) return fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&m->d_gc8, sizeof(float) * (size_t)grp[num_pdfs] * 8)) != cudaSuccess) return fail(e, "cudaMalloc");
+  *out = m;
+  return KHG_OK;
+}
+
+khg_status khg_model_upload(khg_model *m, const float *weights, const float *means_invvars,
+                            const float *inv_vars, const float *gconsts, int32_t *num_bad) {
+  KHG_REQUIRE(m && means_invvars && inv_vars, "null argument");
+  KHG_REQUIRE(weights || gconsts, "need weights or gconsts");
+  size_t gd = (size_t)m->G * m->dim;
+  cudaStream_t st = m->stream;
+  KHG_CUDA_TRY(cudaMemcpyAsync(m->d_miv, means_invvars, sizeof(float) * gd, cudaMemcpyHostToDevice, st));
+  KHG_CUDA_TRY(cudaMemcpyAsync(m->d_iv, inv_vars, sizeof(float) * gd, cudaMemcpyHostToDevice, st));
+  if (weights) KHG_CUDA_TRY(cudaMemcpyAsync(m->d_weights, weights, sizeof(float) * m->G, cudaMemcpyHostToDevice, st));
+  if (num_bad) *num_bad = 0;
+  if (gconsts) {
+    KHG_CUDA_TRY(cudaMemcpyAsync(m->d_gconsts, gconsts, sizeof(float) * m->G, cudaMemcpyHostToDevice, st));
+  } else {
+    KHG_CUDA_TRY(cudaMemsetAsync(m->d_scratch_int, 0, sizeof(int) * 4, st));
+    gconsts_kernel<<<grid_for(m->G, 128), 128, 0, st>>>(m->G, m->dim, m->d_weights, m->d_miv, m->d_iv, m->d_gconsts, m->d_scratch_int);
+    ++g_launch_count;
+    int flags[2] = {0, 0};
+    KHG_CUDA_TRY(cudaMemcpyAsync(flags, m->d_scratch_int, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+    KHG_CUDA_TRY(cudaStreamSynchronize(st));
+    if (flags[1]) {
+      set_error("not a number in gconst computation");  // csrc/diag-gmm.cc:132-135
+      return KHG_ERR_NONFINITE;
+    }
+    if (num_bad) *num_bad = flags[0];
+  }
+  pack_simt_kernel<<<std::min(1024u, grid_for((int64_t)m->n_chunks * 2 * m->dim * kSimtChunk, 256)), 256, 0, st>>>(
+      m->G, m->dim, m->n_chunks, m->d_miv, m->d_iv, m->d_packT);
+  pack8_kernel<<<m->P, 128, 0, st>>>(m->P, m->dim, m->d_offsets, m->d_grp_start, m->d_miv, m->d_iv, m->d_gconsts, m->d_pack8, m->d_gc8);
+  g_launch_count += 2;
+  KHG_CUDA_TRY(cudaGetLastError());
+  m->uploaded = true;
+  m->tc.ready = false;
+  if (m->kernel != KHG_KERNEL_SIMT && tc_supported(m)) {
+    khg_status s = tc_pack_build(m);
+    if (s != KHG_OK && m->kernel == KHG_KERNEL_TCGEN05) return s;
+  }
+  KHG_CUDA_TRY(cudaStreamSynchronize(st));
+  return KHG_OK;
+}
+
+khg_status khg_model_get_gconsts(khg_model *m, float *gconsts) {
+  KHG_REQUIRE(m && gconsts && m->uploaded, "model not uploaded");
+  KHG_CUDA_TRY(cudaMemcpyAsync(gconsts, m->d_gconsts, sizeof(float) * m->G, cudaMemcpyDeviceToHost, m->stream));
+  KHG_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return KHG_OK;
+}
+
+khg_status khg_model_info(const khg_model *m, int32_t *dim, int32_t *num_pdfs, int32_t *num_gauss) {
+  KHG_REQUIRE(m, "null model");
+  if (dim) *dim = m->dim;
+  if (num_pdfs) *num_pdfs = m->P;
+  if (num_gauss) *num_gauss = m->G;
+  return KHG_OK;
+}
+
+khg_status khg_model_set_kernel(khg_model *m, int32_t kernel) {
+  KHG_REQUIRE(m && kernel >= KHG_KERNEL_AUTO && kernel <= KHG_KERNEL_TCGEN05, "bad kernel id");
+  if (kernel == KHG_KERNEL_TCGEN05 && !tc_supported(m)) {
+    set_error("tcgen05 kernel does not support this model shape (needs 2*dim+1 <= 96 and every pdf <= 240 Gaussians)");
+    return KHG_ERR_UNSUPPORTED;
+  }
+  m->kernel = kernel;
+  if (kernel != KHG_KERNEL_SIMT && m->uploaded && !m->tc.ready && tc_supported(m)) return tc_pack_build(m);
+  return KHG_OK;
+}
+
+khg_status khg_model_set_stream(khg_model *m, void *cuda_stream) {
+  KHG_REQUIRE(m, "null model");
+  m->stream = static_cast<cudaStream_t>(cuda_stream);
+  return KHG_OK;
+}
+
+khg_status khg_model_sync(khg_model *m) {
+  KHG_REQUIRE(m, "null model");
+  return sync_check(m);
+}
+
+void khg_model_destroy(khg_model *m) {
+  if (!m) return;
+  tc_pack_free(m);
+  cudaFree(m->d_offsets); cudaFree(m->d_weights); cudaFree(m->d_miv); cudaFree(m->d_iv);
+  cudaFree(m->d_gconsts); cudaFree(m->d_packT); cudaFree(m->d_err); cudaFree(m->d_scratch_int);
+  cudaFree(m->d_grp_start); cudaFree(m->d_pack8); cudaFree(m->d_gc8);
+  for (Buf *b : {&m->w_feats, &m->w_ids, &m->w_wts, &m->w_out, &m->w_pf, &m->w_keys, &m->w_vals_in,
+                 &m->w_vals_out, &m->w_cub, &m->w_starts, &m->w_item_start, &m->w_tot, &m->w_tid,
+                 &m->w_tid2pdf, &m->w_trans, &m->w_keys_out})
+    b->release();
+  for (int i = 0; i < 2; ++i) {
+    m->pin_feats[i].release(); m->pin_ids[i].release(); m->pin_wts[i].release();
+    m->w_efeats[i].release(); m->w_eids[i].release(); m->w_ewts[i].release();
+    if (m->ev_copy[i]) cudaEventDestroy(m->ev_copy[i]);
+    if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
+  }
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  delete m;
+}
+
+khg_status khg_compute_gconsts(int32_t nmix, int32_t dim, const float *weights,
+                               const float *means_invvars, const float *inv_vars,
+                               float *gconsts, int32_t *num_bad) {
+  KHG_REQUIRE(nmix > 0 && dim > 0 && weights && means_invvars && inv_vars && gconsts, "bad argument");
+  for (int i = 0; i < nmix; ++i) KHG_REQUIRE(weights[i] >= 0, "weights_[mix] >= 0");  // csrc/diag-gmm.cc:116
+  int32_t offs[2] = {0, nmix};
+  khg_model *m = nullptr;
+  KHG_TRY(khg_model_create(dim, 1, offs, &m));
+  m->kernel = KHG_KERNEL_SIMT;
+  khg_status s = khg_model_upload(m, weights, means_invvars, inv_vars, nullptr, num_bad);
+  if (s == KHG_OK) s = khg_model_get_gconsts(m, gconsts);
+  khg_model_destroy(m);
+  return s;
+}
+
+// ------------------------------------------------------------ likelihoods --
+static khg_status dense_device(khg_model *m, const float *d_feats, int64_t T, float scale,
+                               int layout, float *d_out, int64_t ld) {
+  const bool use_tc = m->kernel != KHG_KERNEL_SIMT && m->tc.ready;
+  if (m->kernel == KHG_KERNEL_TCGEN05 && !m->tc.ready) {
+    set_error("tcgen05 kernel requested but its model pack is not built");
+    return KHG_ERR_UNSUPPORTED;
+  }
+  if (use_tc) {
+    if (layout == KHG_PDF_MAJOR) return tc_loglikes(m, d_feats, T, scale, d_out, ld);
+    // frame-major: compute pdf-major into scratch, then transpose
+    int64_t ldt = (T + 3) & ~(int64_t)3;
+    KHG_TRY(m->w_out.reserve(sizeof(float) * (size_t)m->P * ldt));
+    KHG_TRY(tc_loglikes(m, d_feats, T, scale, m->w_out.as<float>(), ldt));
+    dim3 grid(grid_for(T, 32), grid_for(m->P, 32)), block(32, 8);
+    transpose_kernel<<<grid, block, 0, m->stream>>>(m->w_out.as<float>(), m->P, T, ldt, d_out, ld);
+    ++g_launch_count;
+    KHG_CUDA_TRY(cudaGetLastError());
+    return KHG_OK;
+  }
+  const int D = m->dim;
+  size_t smem = sizeof(float) * ((size_t)D * kDenseXP + 2 * (size_t)D * kSimtChunk);
+  if (smem > 220 * 1024) {
+    set_error("feature dimension too large for the dense SIMT kernel");
+    return KHG_ERR_UNSUPPORTED;
+  }
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(loglikes_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  });
+  int64_t n_ft = (T + kDenseFrames - 1) / kDenseFrames;
+  // enough CTAs for >= 2 waves when T is small: split the pdf range
+  int groups = (int)std::min<int64_t>(std::max<int64_t>(1, (4LL * m->sm_count + n_ft - 1) / n_ft), std::max(1, m->P / 4));
+  int ppg = (m->P + groups - 1) / groups;
+  groups = (m->P + ppg - 1) / ppg;
+  int64_t sp = layout == KHG_PDF_MAJOR ? ld : 1, stt = layout == KHG_PDF_MAJOR ? 1 : ld;
+  for (int64_t f0 = 0; f0 < n_ft; f0 += 65535 * 32) {  // gridDim.x is huge, but keep launches bounded
+    int64_t nf = std::min<int64_t>(n_ft - f0, 65535LL * 32);
+    dim3 grid((unsigned)nf, groups);
+    loglikes_simt_kernel<<<grid, 128, smem, m->stream>>>(
+        d_feats + f0 * kDenseFrames * D, T - f0 * kDenseFrames, D, m->d_packT, m->d_gconsts, m->d_offsets,
+        m->P, ppg, scale, d_out + f0 * kDenseFrames * stt, sp, stt, m->d_err);
+    ++g_launch_count;
+  }
+  KHG_CUDA_TRY(cudaGetLastError());
+  return KHG_OK;
+}
+
+khg_status khg_loglikes_all_pdfs(khg_model *m, const float *feats, int64_t T, int32_t feats_loc,
+                                 float scale, int32_t layout, float *out, int64_t ld_out,
+                                 int32_t out_loc) {
+  KHG_REQUIRE(m && m->uploaded, "model not uploaded");
+  KHG_REQUIRE(T >= 0 && (T == 0 || (feats && out)), "null buffer");
+  KHG_REQUIRE(layout == KHG_FRAME_MAJOR || layout == KHG_PDF_MAJOR, "bad layout");
+  KHG_REQUIRE(ld_out >= (layout == KHG_PDF_MAJOR ? T : m->P), "ld_out too small");
+  if (T == 0) return KHG_OK;
+  const int D = m->dim;
+  if (feats_loc == KHG_DEVICE && out_loc == KHG_DEVICE)
+    return dense_device(m, feats, T, scale, layout, out, ld_out);
+  // host buffers: stream in chunks of frames
+  const int64_t chunk = std::max<int64_t>(256, std::min<int64_t>(T, (int64_t)(256e6 / (4.0 * m->P))) & ~(int64_t)255);
+  for (int64_t t0 = 0; t0 < T; t0 += chunk) {
+    int64_t n = std::min(chunk, T - t0);
+    const float *d_f = nullptr;
+    KHG_TRY(stage_in(m, m->w_feats, feats + t0 * D, (size_t)n * D, feats_loc, &d_f));
+    float *d_o;
+    int64_t ldd;
+    if (out_loc == KHG_DEVICE) {
+      d_o = layout == KHG_PDF_MAJOR ? out + t0 : out + t0 * ld_out;
+      ldd = ld_out;
+    } else {
+      ldd = layout == KHG_PDF_MAJOR ? ((n + 3) & ~(int64_t)3) : m->P;
+      KHG_TRY(m->w_pf.reserve(sizeof(float) * (size_t)(layout == KHG_PDF_MAJOR ? m->P * ldd : n * ldd)));
+      d_o = m->w_pf.as<float>();
+    }
+    KHG_TRY(dense_device(m, d_f, n, scale, layout, d_o, ldd));
+    if (out_loc == KHG_HOST) {
+      if (layout == KHG_PDF_MAJOR)
+        KHG_CUDA_TRY(cudaMemcpy2DAsync(out + t0, sizeof(float) * ld_out, d_o, sizeof(float) * ldd, sizeof(float) * n, m->P, cudaMemcpyDeviceToHost, m->stream));
+      else
+        KHG_CUDA_TRY(cudaMemcpy2DAsync(out + t0 * ld_out, sizeof(float) * ld_out, d_o, sizeof(float) * ldd, sizeof(float) * m->P, n, cudaMemcpyDeviceToHost, m->stream));
+    }
+    KHG_TRY(sync_check(m));
+  }
+  return KHG_OK;
+}
+
+khg_status khg_pdf_loglikes(khg_model *m, int32_t pdf, const float *feats, int64_t T, int32_t loc, float *out) {
+  KHG_REQUIRE(m && m->uploaded, "model not uploaded");
+  KHG_REQUIRE(pdf >= 0 && pdf < m->P, "pdf_index out of range");
+  KHG_REQUIRE(T > 0 && feats && out, "data.rows() != 0");  // csrc/diag-gmm.cc:179
+  const int g0 = m->h_offsets[pdf], ng = m->h_offsets[pdf + 1] - g0, D = m->dim;
+  const float *d_f = nullptr;
+  KHG_TRY(stage_in(m, m->w_feats, feats, (size_t)T * D, loc, &d_f));
+  float *d_o = out;
+  if (loc == KHG_HOST) {
+    KHG_TRY(m->w_pf.reserve(sizeof(float) * (size_t)T * ng));
+    d_o = m->w_pf.as<float>();
+  }
+  pdf_loglikes_kernel<<<grid_for(T * ng, 128), 128, 0, m->stream>>>(d_f, T, D, m->d_miv + (size_t)g0 * D, m->d_iv + (size_t)g0 * D, m->d_gconsts + g0, ng, d_o);
+  ++g_launch_count;
+  KHG_CUDA_TRY(cudaGetLastError());
+  if (loc == KHG_HOST) {
+    KHG_CUDA_TRY(cudaMemcpyAsync(out, d_o, sizeof(float) * (size_t)T * ng, cudaMemcpyDeviceToHost, m->stream));
+    KHG_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  }
+  return KHG_OK;
+}
+
+khg_status khg_pdf_posteriors(khg_model *m, int32_t pdf, const float *feats, int64_t T, int32_t loc,
+                              float *post, float *loglike) {
+  KHG_REQUIRE(m && m->uploaded, "model not uploaded");
+  KHG_REQUIRE(pdf >= 0 && pdf < m->P, "pdf_index out of range");
+  KHG_REQUIRE(T > 0 && feats && (post || loglike), "null buffer");
+  const int g0 = m->h_offsets[pdf], ng = m->h_offsets[pdf + 1] - g0, D = m->dim;
+  const float *d_f = nullptr;
+  KHG_TRY(stage_in(m, m->w_feats, feats, (size_t)T * D, loc, &d_f));
+  KHG_TRY(m->w_out.reserve(sizeof(float) * (size_t)T * ng));
+  float *d_ll = m->w_out.as<float>();
+  float *d_post = post, *d_like = loglike;
+  if (loc == KHG_HOST) {
+    KHG_TRY(m->w_pf.reserve(sizeof(float) * (size_t)T));
+    d_post = post ? d_ll : nullptr;
+    d_like = loglike ? m->w_pf.as<float>() : nullptr;
+  }
+  pdf_loglikes_kernel<<<grid_for(T * ng, 128), 128, 0, m->stream>>>(d_f, T, D, m->d_miv + (size_t)g0 * D, m->d_iv + (size_t)g0 * D, m->d_gconsts + g0, ng, d_ll);
+  pdf_softmax_kernel<<<grid_for(T, 128), 128, 0, m->stream>>>(d_ll, T, ng, d_post, d_like, m->d_err);
+  g_launch_count += 2;
+  KHG_CUDA_TRY(cudaGetLastError());
+  if (loc == KHG_HOST) {
+    if (post) KHG_CUDA_TRY(cudaMemcpyAsync(post, d_post, sizeof(float) * (size_t)T * ng, cudaMemcpyDeviceToHost, m->stream));
+    if (loglike) KHG_CUDA_TRY(cudaMemcpyAsync(loglike, d_like, sizeof(float) * (size_t)T, cudaMemcpyDeviceToHost, m->stream));
+    return sync_check(m);
+  }
+  return KHG_OK;
+}
+
+// ------------------------------------------------------------------ stats --
+khg_status khg_stats_create(khg_model *m, uint16_t flags, khg_stats **out) {
+  KHG_REQUIRE(m && out, "null argument");
+  KHG_REQUIRE((flags & ~KHG_GMM_ALL) == 0, "(flags & ~kGmmAll) == 0");  // csrc/model-common.cc:73
+  khg_stats *s = new khg_stats();
+  s->model = m;
+  s->flags = khg_augment_flags(flags);
+  int64_t G = m->G, D = m->dim, n = G;
+  if (s->flags & KHG_GMM_MEANS) { s->off_mean = n; n += G * D; }
+  if (s->flags & KHG_GMM_VARIANCES) { s->off_var = n; n += G * D; }
+  s->off_tot = n;
+  n += 2;
+  s->n = n;
+  cudaError_t e = cudaMalloc(&s->buf, sizeof(double) * n);
+  if (e == cudaSuccess) e = cudaMemset(s->buf, 0, sizeof(double) * n);
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc(stats): ") + cudaGetErrorString(e));
+    delete s;
+    return KHG_ERR_CUDA;
+  }
+  *out = s;
+  return KHG_OK;
+}
+
+khg_status khg_stats_zero(khg_stats *s) {
+  KHG_REQUIRE(s, "null stats");
+  KHG_CUDA_TRY(cudaMemsetAsync(s->buf, 0, sizeof(double) * s->n, s->model->stream));
+  return KHG_OK;
+}
+
+khg_status khg_stats_flags(const khg_stats *s, uint16_t *flags) {
+  KHG_REQUIRE(s && flags, "null argument");
+  *flags = s->flags;
+  return KHG_OK;
+}
+
+khg_status khg_stats_device_buffer(khg_stats *s, double **dev_ptr, int64_t *num_doubles) {
+  KHG_REQUIRE(s && dev_ptr && num_doubles, "null argument");
+  *dev_ptr = s->buf;
+  *num_doubles = s->n;
+  return KHG_OK;
+}
+
+khg_status khg_stats_download(khg_stats *s, double *occ, double *mean, double *var, double *totals) {
+  KHG_REQUIRE(s, "null stats");
+  khg_model *m = s->model;
+  size_t G = m->G, GD = (size_t)m->G * m->dim;
+  cudaStream_t st = m->stream;
+  if (occ) KHG_CUDA_TRY(cudaMemcpyAsync(occ, s->buf, sizeof(double) * G, cudaMemcpyDeviceToHost, st));
+  if (mean && s->off_mean >= 0) KHG_CUDA_TRY(cudaMemcpyAsync(mean, s->buf + s->off_mean, sizeof(double) * GD, cudaMemcpyDeviceToHost, st));
+  if (var && s->off_var >= 0) KHG_CUDA_TRY(cudaMemcpyAsync(var, s->buf + s->off_var, sizeof(double) * GD, cudaMemcpyDeviceToHost, st));
+  if (totals) KHG_CUDA_TRY(cudaMemcpyAsync(totals, s->buf + s->off_tot, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+  return sync_check(m);
+}
+
+khg_status khg_stats_upload(khg_stats *s, const double *occ, const double *mean, const double *var, const double *totals) {
+  KHG_REQUIRE(s, "null stats");
+  khg_model *m = s->model;
+  size_t G = m->G, GD = (size_t)m->G * m->dim;
+  cudaStream_t st = m->stream;
+  if (occ) KHG_CUDA_TRY(cudaMemcpyAsync(s->buf, occ, sizeof(double) * G, cudaMemcpyHostToDevice, st));
+  if (mean && s->off_mean >= 0) KHG_CUDA_TRY(cudaMemcpyAsync(s->buf + s->off_mean, mean, sizeof(double) * GD, cudaMemcpyHostToDevice, st));
+  if (var && s->off_var >= 0) KHG_CUDA_TRY(cudaMemcpyAsync(s->buf + s->off_var, var, sizeof(double) * GD, cudaMemcpyHostToDevice, st));
+  if (totals) KHG_CUDA_TRY(cudaMemcpyAsync(s->buf + s->off_tot, totals, sizeof(double) * 2, cudaMemcpyHostToDevice, st));
+  KHG_CUDA_TRY(cudaStreamSynchronize(st));
+  return KHG_OK;
+}
+
+khg_status khg_stats_add(khg_stats *dst, float scale, const khg_stats *src) {
+  KHG_REQUIRE(dst && src, "null stats");
+  KHG_REQUIRE(dst->n == src->n && dst->flags == src->flags, "num_accs == other.NumAccs()");
+  axpy_f64_kernel<<<std::min(2048u, grid_for(dst->n, 256)), 256, 0, dst->model->stream>>>(dst->buf, src->buf, (double)scale, dst->n);
+  ++g_launch_count;
+  KHG_CUDA_TRY(cudaGetLastError());
+  return KHG_OK;
+}
+
+khg_status khg_stats_scale(khg_stats *s, float scale) {
+  KHG_REQUIRE(s, "null stats");
+  scale_f64_kernel<<<std::min(2048u, grid_for(s->n, 256)), 256, 0, s->model->stream>>>(s->buf, (double)scale, s->n);
+  ++g_launch_count;
+  KHG_CUDA_TRY(cudaGetLastError());
+  return KHG_OK;
+}
+
+void khg_stats_destroy(khg_stats *s) {
+  if (!s) return;
+  cudaFree(s->buf);
+  delete s;
+}
+
+// Bucket + accumulate for device-resident inputs; frames processed in slabs so the
+// sort workspace stays bounded.
+static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, int64_t T,
+                             const int32_t *d_ids, const float *d_w, float *d_pf, double *d_call_like) {
+  if (m->max_gp > kStatsMaxGp) {
+    set_error("a pdf has more Gaussians than the statistics kernel supports (1638)");
+    return KHG_ERR_UNSUPPORTED;
+  }
+  const int D = m->dim, P = m->P;
+  cudaStream_t st = m->stream;
+  const int64_t slab = 1 << 23;
+  int end_bit = 1;
+  while ((1 << end_bit) < P) ++end_bit;
+  int grp_batch = std::max(1, std::min(8, 20480 / (2 * D * 8 * 4)));
+  size_t smem = sizeof(float) * ((size_t)D * (kStatsFrames + 1) + kStatsLLCap + (size_t)grp_batch * 2 * D * 8 + grp_batch * 8 + 128);
+  if (smem > 220 * 1024) {
+    set_error("feature dimension too large for the statistics kernel");
+    return KHG_ERR_UNSUPPORTED;
+  }
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  });
+  for (int64_t t0 = 0; t0 < T; t0 += slab) {
+    const int64_t n = std::min(slab, T - t0);
+    KHG_TRY(m->w_keys.reserve(sizeof(int32_t) * n));
+    KHG_TRY(m->w_keys_out.reserve(sizeof(int32_t) * n));
+    KHG_TRY(m->w_vals_in.reserve(sizeof(int32_t) * n));
+    KHG_TRY(m->w_vals_out.reserve(sizeof(int32_t) * n));
+    KHG_TRY(m->w_starts.reserve(sizeof(int32_t) * (P + 1)));
+    KHG_TRY(m->w_item_start.reserve(sizeof(int32_t) * (P + 1)));
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, m->w_keys.as<int32_t>(), m->w_keys_out.as<int32_t>(),
+                                    m->w_vals_in.as<int32_t>(), m->w_vals_out.as<int32_t>(), (int)n, 0, end_bit, st);
+    KHG_TRY(m->w_cub.reserve(cub_bytes));
+    prep_keys_kernel<<<grid_for(n, 256), 256, 0, st>>>(d_ids + t0, n, P, m->w_keys.as<int32_t>(), m->w_vals_in.as<int32_t>(), m->d_err);
+    KHG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(m->w_cub.p, cub_bytes, m->w_keys.as<int32_t>(), m->w_keys_out.as<int32_t>(),
+                                                 m->w_vals_in.as<int32_t>(), m->w_vals_out.as<int32_t>(), (int)n, 0, end_bit, st));
+    bucket_starts_kernel<<<grid_for(n + 1, 256), 256, 0, st>>>(m->w_keys_out.as<int32_t>(), n, P, m->w_starts.as<int32_t>());
+    item_scan_kernel<<<1, 1024, 0, st>>>(P, m->d_offsets, m->w_starts.as<int32_t>(), m->w_item_start.as<int32_t>());
+    // upper bound on work items: every pdf wastes at most one partial item
+    int f_min = stats_frames_for(m->max_gp);
+    int64_t max_items = n / f_min + P + 1;
+    StatsArgs a;
+    a.feats = d_feats + t0 * D;
+    a.order = m->w_vals_out.as<int32_t>();
+    a.weights = d_w ? d_w + t0 : nullptr;
+    a.starts = m->w_starts.as<int32_t>();
+    a.item_start = m->w_item_start.as<int32_t>();
+    a.offsets = m->d_offsets;
+    a.grp_start = m->d_grp_start;
+    a.pack8 = m->d_pack8;
+    a.gc8 = m->d_gc8;
+    a.occ = s->buf;
+    a.mean = s->off_mean >= 0 ? s->buf + s->off_mean : nullptr;
+    a.var = s->off_var >= 0 ? s->buf + s->off_var : nullptr;
+    a.totals = s->buf + s->off_tot;
+    a.call_like = d_call_like;
+    a.per_frame = d_pf ? d_pf + t0 : nullptr;
+    a.err = m->d_err;
+    a.P = P;
+    a.D = D;
+    a.grp_batch = grp_batch;
+    stats_kernel<<<(unsigned)max_items, 128, smem, st>>>(a);
+    g_launch_count += 5 + 3;  // ours + the radix-sort passes (library)
+    KHG_CUDA_TRY(cudaGetLastError());
+  }
+  return KHG_OK;
+}
+
+khg_status khg_acc_stats_ali(khg_model *m, khg_stats *s, const float *feats, int64_t T, int32_t loc,
+                             const int32_t *pdf_ids, const float *frame_weights,
+                             float *per_frame_loglike, double *tot_loglike) {
+  KHG_REQUIRE(m && s && s->model == m && m->uploaded, "model/stats mismatch or model not uploaded");
+  KHG_REQUIRE(T >= 0, "T >= 0");
+  if (T == 0) {
+    if (tot_loglike) *tot_loglike = 0.0;
+    return KHG_OK;
+  }
+  KHG_REQUIRE(feats && pdf_ids, "null buffer");
+  const int D = m->dim;
+  const float *d_f = nullptr, *d_w = nullptr;
+  const int32_t *d_i = nullptr;
+  KHG_TRY(stage_in(m, m->w_feats, feats, (size_t)T * D, loc, &d_f));
+  KHG_TRY(stage_in(m, m->w_ids, pdf_ids, (size_t)T, loc, &d_i));
+  KHG_TRY(stage_in(m, m->w_wts, frame_weights, (size_t)T, loc, &d_w));
+  float *d_pf = per_frame_loglike;
+  if (per_frame_loglike && loc == KHG_HOST) {
+    KHG_TRY(m->w_pf.reserve(sizeof(float) * T));
+    d_pf = m->w_pf.as<float>();
+  }
+  double *d_call = nullptr;
+  if (tot_loglike) {
+    KHG_TRY(m->w_tot.reserve(sizeof(double)));
+    d_call = m->w_tot.as<double>();
+    KHG_CUDA_TRY(cudaMemsetAsync(d_call, 0, sizeof(double), m->stream));
+  }
+  KHG_TRY(acc_device(m, s, d_f, T, d_i, d_w, d_pf, d_call));
+  const bool need_sync = tot_loglike || loc == KHG_HOST;
+  if (per_frame_loglike && loc == KHG_HOST)
+    KHG_CUDA_TRY(cudaMemcpyAsync(per_frame_loglike, d_pf, sizeof(float) * T, cudaMemcpyDeviceToHost, m->stream));
+  if (tot_loglike)
+    KHG_CUDA_TRY(cudaMemcpyAsync(tot_loglike, d_call, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  if (need_sync) return sync_check(m);
+  return KHG_OK;
+}
+
+khg_status khg_acc_stats_ali_tids(khg_model *m, khg_stats *s, const float *feats, int64_t T,
+                                  const int32_t *tids, const int32_t *tid2pdf, int32_t num_tids,
+                                  double *trans_accs, double *tot_loglike) {
+  KHG_REQUIRE(m && s && s->model == m && m->uploaded, "model/stats mismatch or model not uploaded");
+  KHG_REQUIRE(T >= 0 && num_tids > 0 && tid2pdf, "bad argument");
+  if (T == 0) {
+    if (tot_loglike) *tot_loglike = 0.0;
+    return KHG_OK;
+  }
+  KHG_REQUIRE(feats && tids, "null buffer");
+  cudaStream_t st = m->stream;
+  const int D = m->dim;
+  const float *d_f = nullptr;
+  const int32_t *d_t = nullptr, *d_map = nullptr;
+  KHG_TRY(stage_in(m, m->w_feats, feats, (size_t)T * D, KHG_HOST, &d_f));
+  KHG_TRY(stage_in(m, m->w_tid, tids, (size_t)T, KHG_HOST, &d_t));
+  KHG_TRY(stage_in(m, m->w_tid2pdf, tid2pdf, (size_t)num_tids + 1, KHG_HOST, &d_map));
+  KHG_TRY(m->w_ids.reserve(sizeof(int32_t) * T));
+  unsigned long long *d_cnt = nullptr;
+  if (trans_accs) {
+    KHG_TRY(m->w_trans.reserve(sizeof(unsigned long long) * ((size_t)num_tids + 1)));
+    d_cnt = m->w_trans.as<unsigned long long>();
+    KHG_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * ((size_t)num_tids + 1), st));
+  }
+  map_tids_kernel<<<grid_for(T, 256), 256, 0, st>>>(d_t, T, d_map, num_tids, m->w_ids.as<int32_t>(), d_cnt, m->d_err);
+  ++g_launch_count;
+  double *d_call = nullptr;
+  if (tot_loglike) {
+    KHG_TRY(m->w_tot.reserve(sizeof(double)));
+    d_call = m->w_tot.as<double>();
+    KHG_CUDA_TRY(cudaMemsetAsync(d_call, 0, sizeof(double), st));
+  }
+  KHG_TRY(acc_device(m, s, d_f, T, m->w_ids.as<int32_t>(), nullptr, nullptr, d_call));
+  std::vector<unsigned long long> cnt;
+  if (trans_accs) {
+    cnt.resize((size_t)num_tids + 1);
+    KHG_CUDA_TRY(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(unsigned long long) * cnt.size(), cudaMemcpyDeviceToHost, st));
+  }
+  if (tot_loglike) KHG_CUDA_TRY(cudaMemcpyAsync(tot_loglike, d_call, sizeof(double), cudaMemcpyDeviceToHost, st));
+  KHG_TRY(sync_check(m));
+  if (trans_accs)
+    for (size_t i = 0; i < cnt.size(); ++i) trans_accs[i] += (double)cnt[i];  // integer counts: exact
+  return KHG_OK;
+}
+
+khg_status khg_acc_from_posteriors(khg_model *m, khg_stats *s, int32_t pdf, const float *feats,
+                                   int64_t T, int32_t loc, const float *post) {
+  KHG_REQUIRE(m && s && s->model == m && m->uploaded, "model/stats mismatch or model not uploaded");
+  KHG_REQUIRE(pdf >= 0 && pdf < m->P, "gmm_index >= 0 && gmm_index < NumAccs()");
+  KHG_REQUIRE(T > 0 && feats && post, "null buffer");
+  const int g0 = m->h_offsets[pdf], ng = m->h_offsets[pdf + 1] - g0, D = m->dim;
+  const float *d_f = nullptr, *d_p = nullptr;
+  KHG_TRY(stage_in(m, m->w_feats, feats, (size_t)T * D, loc, &d_f));
+  KHG_TRY(stage_in(m, m->w_wts, post, (size_t)T * ng, loc, &d_p));
+  acc_from_post_kernel<<<grid_for(ng * (D + 1), 128), 128, 0, m->stream>>>(
+      d_f, T, D, d_p, ng, g0, s->buf, s->off_mean >= 0 ? s->buf + s->off_mean : nullptr,
+      s->off_var >= 0 ? s->buf + s->off_var : nullptr, s->buf + s->off_tot);
+  ++g_launch_count;
+  KHG_CUDA_TRY(cudaGetLastError());
+  if (loc == KHG_HOST) KHG_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return KHG_OK;
+}
+
+// ------------------------------------------------------------------ E-step --
+static khg_status estep_init_streams(khg_model *m) {
+  if (m->copy_stream) return KHG_OK;
+  KHG_CUDA_TRY(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    KHG_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_copy[i], cudaEventDisableTiming));
+    KHG_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
+    m->pin_feats[i].pinned = m->pin_ids[i].pinned = m->pin_wts[i].pinned = true;
+  }
+  return KHG_OK;
+}
+
+khg_status khg_estep(khg_model *m, khg_stats *s, const float *feats, int64_t T, int32_t loc,
+                     const int32_t *pdf_ids, const float *frame_weights, float *loglikes_out,
+                     int64_t ld_out, int64_t chunk_frames, double *tot_loglike) {
+  KHG_REQUIRE(m && s && s->model == m && m->uploaded, "model/stats mismatch or model not uploaded");
+  KHG_REQUIRE(T >= 0, "T >= 0");
+  if (tot_loglike) *tot_loglike = 0.0;
+  if (T == 0) return KHG_OK;
+  KHG_REQUIRE(feats && pdf_ids && loglikes_out, "null buffer");
+  const int D = m->dim;
+  if (chunk_frames <= 0) chunk_frames = 128LL * m->sm_count * 4;
+  chunk_frames = std::min(chunk_frames, ld_out);
+  KHG_REQUIRE(chunk_frames > 0, "ld_out >= chunk_frames > 0");
+  double *d_call = nullptr;
+  if (tot_loglike) {
+    KHG_TRY(m->w_tot.reserve(sizeof(double)));
+    d_call = m->w_tot.as<double>();
+    KHG_CUDA_TRY(cudaMemsetAsync(d_call, 0, sizeof(double), m->stream));
+  }
+  if (loc == KHG_DEVICE) {
+    for (int64_t t0 = 0; t0 < T; t0 += chunk_frames) {
+      int64_t n = std::min(chunk_frames, T - t0);
+      KHG_TRY(dense_device(m, feats + t0 * D, n, 1.0f, KHG_PDF_MAJOR, loglikes_out, ld_out));
+      KHG_TRY(acc_device(m, s, feats + t0 * D, n, pdf_ids + t0, frame_weights ? frame_weights + t0 : nullptr, nullptr, d_call));
+    }
+  } else {
+    // Host inputs: double-buffered pinned staging; the H2D copy of chunk i+1 runs on
+    // copy_stream while chunk i computes on the model stream.
+    KHG_TRY(estep_init_streams(m));
+    for (int i = 0; i < 2; ++i) {
+      KHG_TRY(m->pin_feats[i].reserve(sizeof(float) * chunk_frames * D));
+      KHG_TRY(m->pin_ids[i].reserve(sizeof(int32_t) * chunk_frames));
+      KHG_TRY(m->w_efeats[i].reserve(sizeof(float) * chunk_frames * D));
+      KHG_TRY(m->w_eids[i].reserve(sizeof(int32_t) * chunk_frames));
+      if (frame_weights) {
+        KHG_TRY(m->pin_wts[i].reserve(sizeof(float) * chunk_frames));
+        KHG_TRY(m->w_ewts[i].reserve(sizeof(float) * chunk_frames));
+      }
+    }
+    int64_t n_chunks = (T + chunk_frames - 1) / chunk_frames;
+    std::vector<bool> used(2, false);
+    for (int64_t c = 0; c < n_chunks; ++c) {
+      int b = (int)(c & 1);
+      int64_t t0 = c * chunk_frames, n = std::min(chunk_frames, T - t0);
+      // the device buffers of slot b are free once the compute that read them is done
+      if (used[b]) KHG_CUDA_TRY(cudaStreamWaitEvent(m->copy_stream, m->ev_done[b], 0));
+      // pinned slot b is free once its previous H2D finished
+      if (used[b]) KHG_CUDA_TRY(cudaEventSynchronize(m->ev_copy[b]));
+      std::memcpy(m->pin_feats[b].p, feats + t0 * D, sizeof(float) * n * D);
+      std::memcpy(m->pin_ids[b].p, pdf_ids + t0, sizeof(int32_t) * n);
+      KHG_CUDA_TRY(cudaMemcpyAsync(m->w_efeats[b].p, m->pin_feats[b].p, sizeof(float) * n * D, cudaMemcpyHostToDevice, m->copy_stream));
+      KHG_CUDA_TRY(cudaMemcpyAsync(m->w_eids[b].p, m->pin_ids[b].p, sizeof(int32_t) * n, cudaMemcpyHostToDevice, m->copy_stream));
+      if (frame_weights) {
+        std::memcpy(m->pin_wts[b].p, frame_weights + t0, sizeof(float) * n);
+        KHG_CUDA_TRY(cudaMemcpyAsync(m->w_ewts[b].p, m->pin_wts[b].p, sizeof(float) * n, cudaMemcpyHostToDevice, m->copy_stream));
+      }
+      KHG_CUDA_TRY(cudaEventRecord(m->ev_copy[b], m->copy_stream));
+      KHG_CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_copy[b], 0));
+      KHG_TRY(dense_device(m, m->w_efeats[b].as<float>(), n, 1.0f, KHG_PDF_MAJOR, loglikes_out, ld_out));
+      KHG_TRY(acc_device(m, s, m->w_efeats[b].as<float>(), n, m->w_eids[b].as<int32_t>(),
+                         frame_weights ? m->w_ewts[b].as<float>() : nullptr, nullptr, d_call));
+      KHG_CUDA_TRY(cudaEventRecord(m->ev_done[b], m->stream));
+      used[b] = true;
+    }
+  }
+  if (tot_loglike) {
+    KHG_CUDA_TRY(cudaMemcpyAsync(tot_loglike, d_call, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    return sync_check(m);
+  }
+  if (loc == KHG_HOST) return sync_check(m);
+  return KHG_OK;
+}
+
+}  // extern "C"

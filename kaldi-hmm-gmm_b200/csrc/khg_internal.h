@@ -1,0 +1,135 @@
+// kaldi-hmm-gmm_b200/csrc/khg_internal.h — internals shared by the .cu files of
+// libkhg_b200.so (not part of the ABI; the ABI is include/khg_b200.h).
+#ifndef KHG_INTERNAL_H_
+#define KHG_INTERNAL_H_
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "khg_b200.h"
+
+namespace khg {
+
+void set_error(const std::string &msg);
+extern int64_t g_launch_count;
+
+#define KHG_CUDA_TRY(expr)                                                        \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      ::khg::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+      return KHG_ERR_CUDA;                                                        \
+    }                                                                             \
+  } while (0)
+
+#define KHG_TRY(expr)                \
+  do {                               \
+    khg_status _s = (expr);          \
+    if (_s != KHG_OK) return _s;     \
+  } while (0)
+
+#define KHG_REQUIRE(cond, msg)                                  \
+  do {                                                          \
+    if (!(cond)) {                                              \
+      ::khg::set_error(std::string("KHG_ASSERT failed: ") + (msg)); \
+      return KHG_ERR_INVALID;                                   \
+    }                                                           \
+  } while (0)
+
+// Device error-flag bits (latched by kernels, read by synchronising calls).
+enum : int { ERR_NONFINITE = 1, ERR_BAD_INDEX = 2 };
+
+// A growable device (or pinned host) scratch buffer.
+struct Buf {
+  void *p = nullptr;
+  size_t cap = 0;
+  bool pinned = false;
+  khg_status reserve(size_t bytes);
+  void release();
+  template <class T> T *as() { return static_cast<T *>(p); }
+};
+
+// ---- SIMT model pack ---------------------------------------------------------
+// Gaussians are grouped in chunks of 32 (global Gaussian index / 32); chunk c
+// holds [which(0=means_invvars,1=inv_vars)][d][g%32], zero padded, so a CTA can
+// stage a chunk with one contiguous copy and read 8 consecutive Gaussians of one
+// dimension with two broadcast LDS.128.
+constexpr int kSimtChunk = 32;
+
+// ---- tcgen05 model pack --------------------------------------------------------
+// B operand of the dense contraction: row g = [means_invvars(D) | -0.5*inv_vars(D)
+// | gconst | 0-pad] split into TF32 hi and lo parts (3xTF32), K padded to KP.
+struct TcPack {
+  bool ready = false;
+  int K = 0;   // 2D+1
+  int K8 = 0;  // K rounded up to 8  (UMMA_K for tf32)
+  int KP = 0;  // K rounded up to 32 (one 128-byte swizzle atom per 32 floats)
+  int rows = 0;          // padded row count of bhi/blo
+  float *bhi = nullptr;  // rows x KP
+  float *blo = nullptr;  // rows x KP
+  CUtensorMap map_hi, map_lo;
+  // N-tiles aligned to pdf boundaries: tile j covers Gaussians
+  // [tile_g0[j], tile_g0[j]+kTileN) and owns pdfs [tile_p0[j], tile_p0[j+1]).
+  int n_tiles = 0;
+  int32_t *tile_g0 = nullptr;  // device, n_tiles
+  int32_t *tile_p0 = nullptr;  // device, n_tiles+1
+  std::vector<int32_t> h_tile_g0, h_tile_p0;
+};
+
+}  // namespace khg
+
+struct khg_model {
+  int dim = 0, P = 0, G = 0, max_gp = 0;
+  std::vector<int32_t> h_offsets;
+  int32_t *d_offsets = nullptr;
+  float *d_weights = nullptr;  // G
+  float *d_miv = nullptr;      // G x D
+  float *d_iv = nullptr;       // G x D
+  float *d_gconsts = nullptr;  // G
+  float *d_packT = nullptr;    // n_chunks x 2 x D x 32
+  int n_chunks = 0;
+  std::vector<int32_t> h_grp_start;  // P+1: groups of 8 Gaussians per pdf (K3 pack)
+  int32_t *d_grp_start = nullptr;
+  float *d_pack8 = nullptr;    // n_groups x 2 x D x 8
+  float *d_gc8 = nullptr;      // n_groups x 8 (-inf padded gconsts)
+  bool uploaded = false;
+  int *d_err = nullptr;
+  int *d_scratch_int = nullptr;  // 4 ints: num_bad, has_nan, ...
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // H2D staging for khg_estep(KHG_HOST)
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  int kernel = KHG_KERNEL_AUTO;
+  int sm_count = 148;
+  khg::TcPack tc;
+  // scratch
+  khg::Buf w_feats, w_ids, w_wts, w_out, w_pf;         // device staging of host args
+  khg::Buf w_keys, w_keys_out, w_vals_in, w_vals_out, w_cub;       // bucketing (K2)
+  khg::Buf w_starts, w_item_start, w_tot;              // per-pdf starts, work items, totals
+  khg::Buf w_tid, w_tid2pdf, w_trans;                  // tid path
+  khg::Buf pin_feats[2], pin_ids[2], pin_wts[2];       // pinned staging for estep(HOST)
+  khg::Buf w_efeats[2], w_eids[2], w_ewts[2];
+};
+
+struct khg_stats {
+  khg_model *model = nullptr;
+  uint16_t flags = 0;
+  int64_t n = 0;      // doubles in buf
+  double *buf = nullptr;
+  int64_t off_mean = -1, off_var = -1, off_tot = 0;
+};
+
+namespace khg {
+// khg_loglikes_tc.cu
+khg_status tc_pack_build(khg_model *m);
+void tc_pack_free(khg_model *m);
+bool tc_supported(const khg_model *m);
+// out is pdf-major: out[p*ld + t]
+khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale,
+                       float *d_out, int64_t ld_out);
+}  // namespace khg
+
+#endif  // KHG_INTERNAL_H_

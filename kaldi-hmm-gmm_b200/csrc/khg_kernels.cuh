@@ -1,0 +1,577 @@
+// kaldi-hmm-gmm_b200/csrc/khg_kernels.cuh — SIMT (fp32 FMA) kernels of the diag-GMM
+// E-step: model pack (K4), dense all-pdf log-likelihoods (K1-simt, the any-shape
+// companion of the tcgen05 kernel in khg_loglikes_tc.cu), pdf bucketing helpers
+// (K2) and posteriors + statistics (K3).  Reference citations are relative to
+// kaldi-hmm-gmm/ in csukuangfj/kaldi-hmm-gmm v1.1.4.
+#ifndef KHG_KERNELS_CUH_
+#define KHG_KERNELS_CUH_
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "khg_internal.h"
+
+namespace khg {
+
+__device__ __forceinline__ bool finite_f(float v) { return fabsf(v) <= 3.402823466e38f; }
+
+// ---------------------------------------------------------------------------
+// K4a: DiagGmm::ComputeGconsts (csrc/diag-gmm.cc:103-147), one thread per
+// Gaussian.  The right-hand side of `gc += ...` is evaluated in double (0.5 is
+// a double literal) and gc is rounded back to float at every step, like the
+// reference.  flags[0] += #inf gconsts ("num_bad"), flags[1] |= NaN seen.
+// ---------------------------------------------------------------------------
+__global__ void gconsts_kernel(int G, int D, const float *__restrict__ w,
+                               const float *__restrict__ miv,
+                               const float *__restrict__ iv, float *__restrict__ gc_out,
+                               int *__restrict__ flags) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const double kLog2Pi = 1.8378770664093454835606594728112;  // csrc/kaldi-math.h:25
+  float offset = (float)(-0.5 * kLog2Pi * D);
+  float gc = logf(w[g]) + offset;
+  const float *m = miv + (size_t)g * D, *v = iv + (size_t)g * D;
+  for (int d = 0; d < D; ++d) {
+    double rhs = 0.5 * (double)logf(v[d]) - 0.5 * (double)m[d] * (double)m[d] / (double)v[d];
+    gc = (float)((double)gc + rhs);
+  }
+  if (isnan(gc)) atomicOr(&flags[1], 1);
+  if (isinf(gc)) {
+    atomicAdd(&flags[0], 1);
+    if (gc > 0) gc = -gc;
+  }
+  gc_out[g] = gc;
+}
+
+// K4b: SIMT chunk pack, packT[chunk][which][d][g%32] (see khg_internal.h).
+__global__ void pack_simt_kernel(int G, int D, int n_chunks, const float *__restrict__ miv,
+                                 const float *__restrict__ iv, float *__restrict__ packT) {
+  size_t total = (size_t)n_chunks * 2 * D * kSimtChunk;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    int gl = i % kSimtChunk;
+    size_t r = i / kSimtChunk;
+    int d = r % D;
+    r /= D;
+    int which = r % 2;
+    int chunk = r / 2;
+    int g = chunk * kSimtChunk + gl;
+    float v = 0.f;
+    if (g < G) v = (which ? iv : miv)[(size_t)g * D + d];
+    packT[i] = v;
+  }
+}
+
+// K4c: per-pdf groups of 8 Gaussians for K3: pack8[grp][which][d][8] and
+// gc8[grp][8] (-inf padded); grp_start[p] = first group of pdf p.
+__global__ void pack8_kernel(int P, int D, const int32_t *__restrict__ offsets,
+                             const int32_t *__restrict__ grp_start,
+                             const float *__restrict__ miv, const float *__restrict__ iv,
+                             const float *__restrict__ gconsts, float *__restrict__ pack8,
+                             float *__restrict__ gc8) {
+  int p = blockIdx.x;
+  if (p >= P) return;
+  int g0 = offsets[p], ng = offsets[p + 1] - g0;
+  int grp0 = grp_start[p], ngrp = grp_start[p + 1] - grp0;
+  int per_grp = 2 * D * 8;
+  for (int i = threadIdx.x; i < ngrp * per_grp; i += blockDim.x) {
+    int j = i % 8;
+    int r = i / 8;
+    int d = r % D;
+    r /= D;
+    int which = r % 2;
+    int grp = r / 2;
+    int gl = grp * 8 + j;
+    float v = 0.f;
+    if (gl < ng) v = (which ? iv : miv)[(size_t)(g0 + gl) * D + d];
+    pack8[(size_t)grp0 * per_grp + i] = v;
+  }
+  for (int i = threadIdx.x; i < ngrp * 8; i += blockDim.x)
+    gc8[(size_t)grp0 * 8 + i] = i < ng ? gconsts[g0 + i] : -CUDART_INF_F;
+}
+
+// ---------------------------------------------------------------------------
+// Running log-sum-exp with the reference's max-subtracted form
+// (csrc/eigen.cc:14-18) evaluated online: (M, s) with sum = s * exp(M).
+// -inf terms (zero-weight Gaussians, csrc/diag-gmm.cc:132-141) contribute 0; a
+// NaN term poisons s so the non-finite result is flagged like the reference's
+// throw (csrc/diag-gmm.cc:160-162).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void lse_push(float &M, float &s, float v) {
+  if (v > M) {
+    s = s * __expf(M - v) + 1.0f;
+    M = v;
+  } else if (!(v == -CUDART_INF_F)) {
+    s += __expf(v - M);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1-simt: all-pdf log-likelihoods, fp32 FMA.
+// Replaces DecodableAmDiagGmmUnmapped::LogLikelihoodZeroBased
+// (csrc/decodable-am-diag-gmm.cc:29-71) for a whole block of frames and pdfs:
+//   ll(t,g) = gconst_g + means_invvars_g . x_t - 0.5 * inv_vars_g . x_t^2
+//   out(t,p) = scale * LogSumExp_{g in pdf p} ll(t,g)
+// CTA = 128 threads x 2 frames = 256 frames, loops over the Gaussians of the pdf
+// range [p0, p1) of blockIdx.y.  Features are staged once, transposed, in smem
+// (xs[d][frame], pitch 257: conflict-free both ways); model chunks of 32
+// Gaussians are staged with a contiguous copy and read with broadcast LDS.128.
+// out[p*stride_p + t*stride_t].
+// ---------------------------------------------------------------------------
+constexpr int kDenseFrames = 256;
+constexpr int kDenseXP = 257;
+
+__global__ void __launch_bounds__(128)
+loglikes_simt_kernel(const float *__restrict__ feats, int64_t T, int D,
+                     const float *__restrict__ packT, const float *__restrict__ gconsts,
+                     const int32_t *__restrict__ offsets, int P, int pdfs_per_group,
+                     float scale, float *__restrict__ out, int64_t stride_p,
+                     int64_t stride_t, int *__restrict__ err) {
+  extern __shared__ float smem[];
+  float *xs = smem;                       // D x 257
+  float *ms = smem + (size_t)D * kDenseXP;  // 2 x D x 32
+  const int tid = threadIdx.x;
+  const int64_t t0 = (int64_t)blockIdx.x * kDenseFrames;
+  const int nfr = (int)min((int64_t)kDenseFrames, T - t0);
+
+  // stage features: contiguous block of nfr*D floats
+  {
+    const float *src = feats + t0 * D;
+    int total = kDenseFrames * D;
+    int valid = nfr * D;
+    for (int e = tid; e < total; e += 128) {
+      int r = e / D, d = e - r * D;
+      xs[d * kDenseXP + r] = e < valid ? src[e] : 0.f;
+    }
+  }
+  const int p0 = blockIdx.y * pdfs_per_group;
+  const int p1 = min(P, p0 + pdfs_per_group);
+  if (p0 >= p1) return;
+  const int g_begin = offsets[p0], g_end = offsets[p1];
+  int p = p0;
+  int pdf_end = offsets[p + 1];
+  float M0 = -CUDART_INF_F, s0 = 0.f, M1 = -CUDART_INF_F, s1 = 0.f;
+  const bool v0ok = tid < nfr, v1ok = tid + 128 < nfr;
+  bool bad = false;
+
+  for (int chunk = g_begin / kSimtChunk; chunk * kSimtChunk < g_end; ++chunk) {
+    __syncthreads();
+    {
+      const float4 *src = reinterpret_cast<const float4 *>(packT + (size_t)chunk * 2 * D * kSimtChunk);
+      float4 *dst = reinterpret_cast<float4 *>(ms);
+      for (int e = tid; e < 2 * D * kSimtChunk / 4; e += 128) dst[e] = src[e];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int gb = 0; gb < kSimtChunk / 8; ++gb) {
+      const int gbase = chunk * kSimtChunk + gb * 8;
+      if (gbase + 8 <= g_begin || gbase >= g_end) continue;
+      float a0[8], b0[8], a1[8], b1[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a0[j] = b0[j] = a1[j] = b1[j] = 0.f;
+      const float *mm = ms + gb * 8;
+      const float *vv = ms + D * kSimtChunk + gb * 8;
+#pragma unroll 2
+      for (int d = 0; d < D; ++d) {
+        float x0 = xs[d * kDenseXP + tid], x1 = xs[d * kDenseXP + 128 + tid];
+        float q0 = x0 * x0, q1 = x1 * x1;  // data.array().square(), csrc/diag-gmm.cc:175
+        float4 ma = *reinterpret_cast<const float4 *>(mm + d * kSimtChunk);
+        float4 mb = *reinterpret_cast<const float4 *>(mm + d * kSimtChunk + 4);
+        float4 va = *reinterpret_cast<const float4 *>(vv + d * kSimtChunk);
+        float4 vb = *reinterpret_cast<const float4 *>(vv + d * kSimtChunk + 4);
+        float mj[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+        float vj[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a0[j] = fmaf(mj[j], x0, a0[j]);
+          b0[j] = fmaf(vj[j], q0, b0[j]);
+          a1[j] = fmaf(mj[j], x1, a1[j]);
+          b1[j] = fmaf(vj[j], q1, b1[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int g = gbase + j;
+        if (g < g_begin || g >= g_end) continue;
+        const float gc = __ldg(gconsts + g);
+        lse_push(M0, s0, (gc + a0[j]) - 0.5f * b0[j]);  // csrc/diag-gmm.cc:174-175
+        lse_push(M1, s1, (gc + a1[j]) - 0.5f * b1[j]);
+        if (g + 1 == pdf_end) {
+          float r0 = M0 + logf(s0), r1 = M1 + logf(s1);  // csrc/eigen.cc:17
+          if (v0ok) {
+            if (!finite_f(r0)) bad = true;
+            out[p * stride_p + (t0 + tid) * stride_t] = scale * r0;
+          }
+          if (v1ok) {
+            if (!finite_f(r1)) bad = true;
+            out[p * stride_p + (t0 + tid + 128) * stride_t] = scale * r1;
+          }
+          ++p;
+          pdf_end = p < P ? offsets[p + 1] : 0x7fffffff;
+          M0 = M1 = -CUDART_INF_F;
+          s0 = s1 = 0.f;
+        }
+      }
+    }
+  }
+  if (bad) atomicOr(err, ERR_NONFINITE);
+}
+
+// 32x32 smem transpose: src is rows x cols (ld_src), dst is cols x rows (ld_dst).
+__global__ void transpose_kernel(const float *__restrict__ src, int64_t rows, int64_t cols,
+                                 int64_t ld_src, float *__restrict__ dst, int64_t ld_dst) {
+  __shared__ float tile[32][33];
+  int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int64_t r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = src[r * ld_src + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[c * ld_dst + r] = tile[threadIdx.x][i];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Per-pdf, per-Gaussian log-likelihoods: DiagGmm::LogLikelihoods /
+// LogLikelihoodsMatrix (csrc/diag-gmm.cc:167-189).  One thread per (t, g);
+// API-parity path for the single-frame class methods, not a throughput path.
+// ---------------------------------------------------------------------------
+__global__ void pdf_loglikes_kernel(const float *__restrict__ feats, int64_t T, int D,
+                                    const float *__restrict__ miv, const float *__restrict__ iv,
+                                    const float *__restrict__ gc, int ng, float *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * ng) return;
+  int64_t t = i / ng;
+  int g = (int)(i - t * ng);
+  const float *x = feats + t * D, *m = miv + (size_t)g * D, *v = iv + (size_t)g * D;
+  float a = 0.f, b = 0.f;
+  for (int d = 0; d < D; ++d) {
+    float xv = x[d];
+    a = fmaf(m[d], xv, a);
+    b = fmaf(v[d], xv * xv, b);
+  }
+  out[i] = (gc[g] + a) - 0.5f * b;
+}
+
+// Softmax (csrc/eigen.cc:20-32) over each row of ll (T x ng): post = exp(ll-max)/sum,
+// loglike = log(sum)+max.  One thread per frame.  post may alias ll or be NULL.
+__global__ void pdf_softmax_kernel(const float *__restrict__ ll, int64_t T, int ng,
+                                   float *__restrict__ post, float *__restrict__ loglike,
+                                   int *__restrict__ err) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float *r = ll + t * ng;
+  float mx = r[0];
+  for (int g = 1; g < ng; ++g) mx = fmaxf(mx, r[g]);
+  float s = 0.f;
+  for (int g = 0; g < ng; ++g) s += expf(r[g] - mx);
+  float lse = logf(s) + mx;
+  if (!finite_f(lse)) atomicOr(err, ERR_NONFINITE);
+  if (loglike) loglike[t] = lse;
+  if (post) {
+    float *po = post + t * ng;
+    for (int g = 0; g < ng; ++g) po[g] = expf(r[g] - mx) / s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2 helpers: exact integer bucketing of frames by pdf id.
+// ---------------------------------------------------------------------------
+__global__ void prep_keys_kernel(const int32_t *__restrict__ ids, int64_t n, int P,
+                                 int32_t *__restrict__ keys, int32_t *__restrict__ vals,
+                                 int *__restrict__ err) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t k = ids[i];
+  if (k < 0 || k >= P) {  // AccumulateForGmm asserts the range (csrc/mle-am-diag-gmm.cc:44)
+    atomicOr(err, ERR_BAD_INDEX);
+    k = 0;
+  }
+  keys[i] = k;
+  vals[i] = (int32_t)i;
+}
+
+// tid -> pdf (csrc/transition-information.h:71-73) + transition counts
+// (csrc/transition-model.h:183-189 with prob 1).
+__global__ void map_tids_kernel(const int32_t *__restrict__ tids, int64_t n,
+                                const int32_t *__restrict__ tid2pdf, int num_tids,
+                                int32_t *__restrict__ pdf_ids,
+                                unsigned long long *__restrict__ counts, int *__restrict__ err) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t tid = tids[i];
+  if (tid < 1 || tid > num_tids) {
+    atomicOr(err, ERR_BAD_INDEX);
+    pdf_ids[i] = -1;
+    return;
+  }
+  pdf_ids[i] = tid2pdf[tid];
+  if (counts) atomicAdd(&counts[tid], 1ULL);
+}
+
+// starts[p] = first position of key >= p in the sorted key array (starts[P] = n).
+__global__ void bucket_starts_kernel(const int32_t *__restrict__ sorted_keys, int64_t n, int P,
+                                     int32_t *__restrict__ starts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  int32_t kprev = i == 0 ? -1 : sorted_keys[i - 1];
+  int32_t kcur = i == n ? P : sorted_keys[i];
+  for (int32_t p = kprev + 1; p <= kcur; ++p) starts[p] = (int32_t)i;
+}
+
+constexpr int kStatsFrames = 128;   // frames per work item (upper bound)
+constexpr int kStatsLLCap = 8192;   // floats of smem for the ll/posterior tile
+constexpr int kStatsMaxGp = kStatsLLCap / 5;
+
+__host__ __device__ inline int stats_frames_for(int ng) {
+  int f = kStatsLLCap / ng - 4;
+  return f < 1 ? 1 : (f > kStatsFrames ? kStatsFrames : f);
+}
+
+// item_start[p] = exclusive scan of ceil(n_p / frames_for(g_p)); single block.
+__global__ void item_scan_kernel(int P, const int32_t *__restrict__ offsets,
+                                 const int32_t *__restrict__ starts,
+                                 int32_t *__restrict__ item_start) {
+  __shared__ int32_t carry;
+  __shared__ int32_t buf[1024];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < P; base += 1024) {
+    int p = base + threadIdx.x;
+    int32_t v = 0;
+    if (p < P) {
+      int f = stats_frames_for(offsets[p + 1] - offsets[p]);
+      v = (starts[p + 1] - starts[p] + f - 1) / f;
+    }
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      int32_t add = threadIdx.x >= off ? buf[threadIdx.x - off] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (p < P) item_start[p] = carry + buf[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += buf[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) item_start[P] = carry;
+}
+
+// ---------------------------------------------------------------------------
+// K3: posteriors + sufficient statistics for frames bucketed by pdf.
+// Replaces, per frame, AccumAmDiagGmm::AccumulateForGmm
+// (csrc/mle-am-diag-gmm.cc:41-52) -> AccumDiagGmm::AccumulateFromDiag
+// (csrc/mle-diag-gmm.cc:145-158) -> DiagGmm::ComponentPosteriors
+// (csrc/diag-gmm.cc:368-392) -> AccumulateFromPosteriors
+// (csrc/mle-diag-gmm.cc:123-143).
+// One CTA (128 threads) per work item = up to stats_frames_for(g_p) frames of one
+// pdf.  Phase A: thread = frame: log-likes of the pdf's Gaussians (groups of 8,
+// model staged in smem), max-subtracted softmax (csrc/eigen.cc:20-32), post *= w.
+// Phase B: thread = (Gaussian, dim) pair: fp32 reduction over the item's frames,
+// then ONE fp64 atomicAdd per statistic (the reference adds every frame's fp32
+// product into fp64; here <=128 products are summed in fp32 first).
+// ---------------------------------------------------------------------------
+struct StatsArgs {
+  const float *feats;       // T x D (original order)
+  const int32_t *order;     // frame indices sorted by pdf
+  const float *weights;     // T or NULL
+  const int32_t *starts;    // P+1 positions in `order`
+  const int32_t *item_start;  // P+1
+  const int32_t *offsets;   // P+1
+  const int32_t *grp_start;   // P+1
+  const float *pack8;
+  const float *gc8;
+  double *occ, *mean, *var;  // packed stats (mean/var may be NULL)
+  double *totals;            // [tot_like, tot_frames]
+  double *call_like;         // this call's sum ll*w (may be NULL)
+  float *per_frame;          // T or NULL (original order)
+  int *err;
+  int P, D, grp_batch;
+};
+
+__global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
+  extern __shared__ float smem[];
+  const int D = a.D;
+  const int XP = kStatsFrames + 1;
+  float *xs = smem;                                   // D x 129
+  float *ll = xs + (size_t)D * XP;                    // kStatsLLCap
+  float *ms = ll + kStatsLLCap;                       // grp_batch x 2 x D x 8
+  float *gcs = ms + (size_t)a.grp_batch * 2 * D * 8;  // grp_batch x 8
+  float *wsm = gcs + a.grp_batch * 8;                 // 128 weights
+  __shared__ int s_pdf;
+  __shared__ double s_red[8];
+  const int tid = threadIdx.x;
+  const int item = blockIdx.x;
+  if (item >= a.item_start[a.P]) return;
+  if (tid == 0) {  // largest p with item_start[p] <= item
+    int lo = 0, hi = a.P;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (a.item_start[mid] <= item) lo = mid; else hi = mid;
+    }
+    s_pdf = lo;
+  }
+  __syncthreads();
+  const int p = s_pdf;
+  const int g0 = a.offsets[p], ng = a.offsets[p + 1] - g0;
+  const int f = stats_frames_for(ng);
+  const int LP = f + 4;
+  const int pos0 = a.starts[p] + (item - a.item_start[p]) * f;
+  const int n = min(f, a.starts[p + 1] - pos0);
+  const int grp0 = a.grp_start[p], ngrp = a.grp_start[p + 1] - grp0;
+
+  // stage features (gathered rows), one warp per frame row
+  for (int r = tid >> 5; r < n; r += 4) {
+    const float *src = a.feats + (size_t)a.order[pos0 + r] * D;
+    for (int d = tid & 31; d < D; d += 32) xs[d * XP + r] = src[d];
+  }
+  if (tid < n) wsm[tid] = a.weights ? a.weights[a.order[pos0 + tid]] : 1.0f;
+
+  // Phase A
+  for (int gb0 = 0; gb0 < ngrp; gb0 += a.grp_batch) {
+    const int nb = min(a.grp_batch, ngrp - gb0);
+    __syncthreads();
+    {
+      const float4 *src = reinterpret_cast<const float4 *>(a.pack8 + (size_t)(grp0 + gb0) * 2 * D * 8);
+      float4 *dst = reinterpret_cast<float4 *>(ms);
+      for (int e = tid; e < nb * 2 * D * 8 / 4; e += 128) dst[e] = src[e];
+      for (int e = tid; e < nb * 8; e += 128) gcs[e] = a.gc8[(size_t)(grp0 + gb0) * 8 + e];
+    }
+    __syncthreads();
+    if (tid < n) {
+      for (int gb = 0; gb < nb; ++gb) {
+        float aa[8], bb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) aa[j] = bb[j] = 0.f;
+        const float *mm = ms + (size_t)gb * 2 * D * 8;
+        const float *vv = mm + D * 8;
+#pragma unroll 2
+        for (int d = 0; d < D; ++d) {
+          float x = xs[d * XP + tid];
+          float q = x * x;
+          float4 ma = *reinterpret_cast<const float4 *>(mm + d * 8);
+          float4 mb = *reinterpret_cast<const float4 *>(mm + d * 8 + 4);
+          float4 va = *reinterpret_cast<const float4 *>(vv + d * 8);
+          float4 vb = *reinterpret_cast<const float4 *>(vv + d * 8 + 4);
+          float mj[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+          float vj[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            aa[j] = fmaf(mj[j], x, aa[j]);
+            bb[j] = fmaf(vj[j], q, bb[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          int gl = (gb0 + gb) * 8 + j;
+          if (gl < ng) ll[gl * LP + tid] = (gcs[gb * 8 + j] + aa[j]) - 0.5f * bb[j];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // softmax over the pdf's Gaussians (csrc/eigen.cc:20-32), then post *= weight
+  // (csrc/mle-diag-gmm.cc:153); totals as csrc/mle-am-diag-gmm.cc:49-50.
+  double my_like = 0.0, my_w = 0.0;
+  if (tid < n) {
+    float mx = ll[tid];
+    for (int g = 1; g < ng; ++g) mx = fmaxf(mx, ll[g * LP + tid]);
+    float s = 0.f;
+    for (int g = 0; g < ng; ++g) {
+      float e = __expf(ll[g * LP + tid] - mx);
+      ll[g * LP + tid] = e;
+      s += e;
+    }
+    float lse = logf(s) + mx;
+    if (!finite_f(lse)) atomicOr(a.err, ERR_NONFINITE);
+    float w = wsm[tid];
+    for (int g = 0; g < ng; ++g) ll[g * LP + tid] = (ll[g * LP + tid] / s) * w;
+    if (a.per_frame) a.per_frame[a.order[pos0 + tid]] = lse;
+    my_like = (double)(lse * w);
+    my_w = (double)w;
+  }
+  // block-reduce the two totals
+  for (int off = 16; off > 0; off >>= 1) {
+    my_like += __shfl_xor_sync(0xffffffffu, my_like, off);
+    my_w += __shfl_xor_sync(0xffffffffu, my_w, off);
+  }
+  if ((tid & 31) == 0) {
+    s_red[tid >> 5] = my_like;
+    s_red[4 + (tid >> 5)] = my_w;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double L = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+    double W = s_red[4] + s_red[5] + s_red[6] + s_red[7];
+    atomicAdd(&a.totals[0], L);
+    atomicAdd(&a.totals[1], W);
+    if (a.call_like) atomicAdd(a.call_like, L);
+  }
+  // Phase B: (g, k) pairs; k in [0, D) -> mean/var stats of dim k, k == D -> occupancy
+  const int KK = D + 1;
+  for (int e = tid; e < ng * KK; e += 128) {
+    const int g = e / KK, k = e - g * KK;
+    const float *pr = ll + g * LP;
+    if (k == D) {
+      float o = 0.f;
+      for (int t = 0; t < n; ++t) o += pr[t];
+      atomicAdd(&a.occ[g0 + g], (double)o);
+    } else if (a.mean) {
+      const float *xr = xs + k * XP;
+      float sm = 0.f, sv = 0.f;
+#pragma unroll 4
+      for (int t = 0; t < n; ++t) {
+        float pv = pr[t], x = xr[t];
+        sm = fmaf(pv, x, sm);
+        sv = fmaf(pv, x * x, sv);
+      }
+      atomicAdd(&a.mean[(size_t)(g0 + g) * D + k], (double)sm);
+      if (a.var) atomicAdd(&a.var[(size_t)(g0 + g) * D + k], (double)sv);
+    }
+  }
+}
+
+// AccumDiagGmm::AccumulateFromPosteriors (csrc/mle-diag-gmm.cc:123-143) for T frames of
+// one pdf with caller-supplied posteriors (T x ng).  One thread per (g, k) pair.
+__global__ void acc_from_post_kernel(const float *__restrict__ feats, int64_t T, int D,
+                                     const float *__restrict__ post, int ng, int g0,
+                                     double *occ, double *mean, double *var, double *totals) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int KK = D + 1;
+  if (e >= ng * KK) return;
+  int g = e / KK, k = e - g * KK;
+  if (k == D) {
+    double o = 0.0;
+    for (int64_t t = 0; t < T; ++t) o += (double)post[t * ng + g];
+    occ[g0 + g] += o;
+    atomicAdd(&totals[1], o);  // csrc/mle-am-diag-gmm.cc:85: total_frames_ += posteriors.sum()
+  } else if (mean) {
+    double sm = 0.0, sv = 0.0;
+    for (int64_t t = 0; t < T; ++t) {
+      float pv = post[t * ng + g], x = feats[t * D + k];
+      sm += (double)(pv * x);          // fp32 product, then cast (csrc/mle-diag-gmm.cc:134)
+      sv += (double)(pv * (x * x));
+    }
+    mean[(size_t)(g0 + g) * D + k] += sm;
+    if (var) var[(size_t)(g0 + g) * D + k] += sv;
+  }
+}
+
+__global__ void axpy_f64_kernel(double *dst, const double *src, double scale, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] += src[i] * scale;
+}
+__global__ void scale_f64_kernel(double *dst, double scale, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] *= scale;
+}
+
+}  // namespace khg
+#endif  // KHG_KERNELS_CUH_

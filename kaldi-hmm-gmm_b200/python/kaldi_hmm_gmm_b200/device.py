@@ -1,0 +1,208 @@
+"""Handle objects over the C ABI (include/khg_b200.h): a packed AmDiagGmm on the
+device (`DeviceModel`) and its packed AccumAmDiagGmm statistics (`DeviceStats`).
+
+Buffers are numpy arrays (host; copied inside the call) or torch CUDA tensors
+(device; used in place).  All arithmetic happens in libkhg_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _cabi as A
+
+
+class DeviceModel:
+    """Packed, device-resident AmDiagGmm (reference csrc/am-diag-gmm.h:96: a vector of
+    DiagGmm*, here one contiguous pack; pdf p owns Gaussians [offsets[p], offsets[p+1]))."""
+
+    def __init__(self, dim: int, offsets):
+        self.offsets = np.ascontiguousarray(offsets, np.int32)
+        self.dim = int(dim)
+        self.num_pdfs = self.offsets.size - 1
+        self.num_gauss = int(self.offsets[-1])
+        h = C.c_void_p()
+        A.check(A.lib().khg_model_create(self.dim, self.num_pdfs, self.offsets.ctypes.data, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            A.lib().khg_model_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def upload(self, weights, means_invvars, inv_vars, gconsts=None) -> int:
+        """Returns num_bad like DiagGmm::ComputeGconsts (csrc/diag-gmm.cc:103-147) when
+        gconsts is None (computed on the device)."""
+        miv = np.ascontiguousarray(means_invvars, np.float32)
+        iv = np.ascontiguousarray(inv_vars, np.float32)
+        assert miv.shape == (self.num_gauss, self.dim) and iv.shape == miv.shape
+        w = None if weights is None else np.ascontiguousarray(weights, np.float32)
+        gc = None if gconsts is None else np.ascontiguousarray(gconsts, np.float32)
+        nb = C.c_int32(0)
+        A.check(A.lib().khg_model_upload(self._h, None if w is None else w.ctypes.data, miv.ctypes.data, iv.ctypes.data,
+                                         None if gc is None else gc.ctypes.data, C.byref(nb)))
+        return nb.value
+
+    def gconsts(self) -> np.ndarray:
+        out = np.empty(self.num_gauss, np.float32)
+        A.check(A.lib().khg_model_get_gconsts(self._h, out.ctypes.data))
+        return out
+
+    def set_kernel(self, kernel: int):
+        A.check(A.lib().khg_model_set_kernel(self._h, kernel))
+
+    def set_stream(self, cuda_stream: int):
+        A.check(A.lib().khg_model_set_stream(self._h, cuda_stream))
+
+    def sync(self):
+        A.check(A.lib().khg_model_sync(self._h))
+
+    # -- likelihoods ------------------------------------------------------
+    def loglikes_all_pdfs(self, feats, scale: float = 1.0, layout: int = A.KHG_FRAME_MAJOR, out=None):
+        """(T,P) [frame-major] or (P,T) [pdf-major] block of per-pdf log-likelihoods."""
+        fp, floc = A.ptr(feats, np.float32)
+        T = int(feats.shape[0])
+        assert feats.shape[1] == self.dim, "Dim mismatch"
+        shape = (T, self.num_pdfs) if layout == A.KHG_FRAME_MAJOR else (self.num_pdfs, T)
+        if out is None:
+            if floc == A.KHG_DEVICE:
+                import torch
+
+                out = torch.empty(shape, dtype=torch.float32, device=feats.device)
+            else:
+                out = np.empty(shape, np.float32)
+        op, oloc = A.ptr(out, np.float32)
+        ld = int(out.shape[1]) if len(out.shape) == 2 else shape[1]
+        A.check(A.lib().khg_loglikes_all_pdfs(self._h, fp, T, floc, scale, layout, op, ld, oloc))
+        return out
+
+    def pdf_loglikes(self, pdf: int, feats: np.ndarray) -> np.ndarray:
+        feats = np.ascontiguousarray(np.atleast_2d(feats), np.float32)
+        if feats.shape[1] != self.dim:
+            raise RuntimeError(f"DiagGmm::LogLikelihoods, dimension mismatch {feats.shape[1]} vs. {self.dim}")
+        ng = int(self.offsets[pdf + 1] - self.offsets[pdf])
+        out = np.empty((feats.shape[0], ng), np.float32)
+        A.check(A.lib().khg_pdf_loglikes(self._h, pdf, feats.ctypes.data, feats.shape[0], A.KHG_HOST, out.ctypes.data))
+        return out
+
+    def pdf_posteriors(self, pdf: int, feats: np.ndarray, want_post: bool = True):
+        feats = np.ascontiguousarray(np.atleast_2d(feats), np.float32)
+        if feats.shape[1] != self.dim:
+            raise RuntimeError(f"DiagGmm::LogLikelihoods, dimension mismatch {feats.shape[1]} vs. {self.dim}")
+        ng = int(self.offsets[pdf + 1] - self.offsets[pdf])
+        post = np.empty((feats.shape[0], ng), np.float32) if want_post else None
+        ll = np.empty(feats.shape[0], np.float32)
+        A.check(A.lib().khg_pdf_posteriors(self._h, pdf, feats.ctypes.data, feats.shape[0], A.KHG_HOST,
+                                           None if post is None else post.ctypes.data, ll.ctypes.data))
+        return ll, post
+
+
+class DeviceStats:
+    """Packed device AccumAmDiagGmm: [occ G | mean G*D | var G*D | tot_like, tot_frames] fp64."""
+
+    def __init__(self, model: DeviceModel, flags: int = 0xF):
+        self.model = model
+        h = C.c_void_p()
+        A.check(A.lib().khg_stats_create(model._h, flags, C.byref(h)))
+        self._h = h
+        f = C.c_uint16()
+        A.check(A.lib().khg_stats_flags(h, C.byref(f)))
+        self.flags = f.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            A.lib().khg_stats_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def zero(self):
+        A.check(A.lib().khg_stats_zero(self._h))
+
+    def device_buffer(self):
+        """(device pointer, number of doubles) of the packed stats — for the NCCL all-reduce."""
+        p, n = C.c_void_p(), C.c_int64()
+        A.check(A.lib().khg_stats_device_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def as_torch(self):
+        """Zero-copy torch.float64 CUDA view of the packed buffer."""
+        import torch
+
+        p, n = self.device_buffer()
+
+        class _Holder:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (p, False), "version": 3, "strides": None}
+
+        return torch.as_tensor(_Holder(), device="cuda")
+
+    def download(self):
+        G, D = self.model.num_gauss, self.model.dim
+        occ = np.empty(G, np.float64)
+        mean = np.empty((G, D), np.float64) if self.flags & 1 else None
+        var = np.empty((G, D), np.float64) if self.flags & 2 else None
+        tot = np.empty(2, np.float64)
+        A.check(A.lib().khg_stats_download(self._h, occ.ctypes.data, None if mean is None else mean.ctypes.data,
+                                           None if var is None else var.ctypes.data, tot.ctypes.data))
+        return dict(occ=occ, mean=mean, var=var, tot_like=float(tot[0]), tot_frames=float(tot[1]))
+
+    def upload(self, occ=None, mean=None, var=None, totals=None):
+        def p(a):
+            return None if a is None else np.ascontiguousarray(a, np.float64)
+
+        occ, mean, var, totals = p(occ), p(mean), p(var), p(totals)
+        A.check(A.lib().khg_stats_upload(self._h, *(None if a is None else a.ctypes.data for a in (occ, mean, var, totals))))
+
+    def add(self, scale: float, other: "DeviceStats"):
+        A.check(A.lib().khg_stats_add(self._h, scale, other._h))
+
+    def scale(self, scale: float):
+        A.check(A.lib().khg_stats_scale(self._h, scale))
+
+    # -- accumulation -----------------------------------------------------
+    def acc_stats_ali(self, feats, pdf_ids, frame_weights=None, per_frame=None, want_total: bool = True) -> Optional[float]:
+        """gmm-acc-stats-ali for T frames (reference scripts/gmm_acc_stats_ali.py:46-56)."""
+        fp, l0 = A.ptr(feats, np.float32)
+        ip, l1 = A.ptr(pdf_ids, np.int32)
+        wp, l2 = A.ptr(frame_weights, np.float32)
+        pp, l3 = A.ptr(per_frame, np.float32)
+        loc = A.same_loc(l0, l1, None if frame_weights is None else l2, None if per_frame is None else l3)
+        tot = C.c_double(0.0)
+        A.check(A.lib().khg_acc_stats_ali(self.model._h, self._h, fp, int(feats.shape[0]), loc, ip, wp, pp,
+                                          C.byref(tot) if want_total else None))
+        return tot.value if want_total else None
+
+    def acc_stats_ali_tids(self, feats: np.ndarray, tids, tid2pdf, trans_accs: Optional[np.ndarray] = None) -> float:
+        feats = np.ascontiguousarray(feats, np.float32)
+        tids = np.ascontiguousarray(tids, np.int32)
+        tid2pdf = np.ascontiguousarray(tid2pdf, np.int32)
+        if trans_accs is not None:
+            assert trans_accs.dtype == np.float64 and trans_accs.size == tid2pdf.size
+        tot = C.c_double(0.0)
+        A.check(A.lib().khg_acc_stats_ali_tids(self.model._h, self._h, feats.ctypes.data, feats.shape[0], tids.ctypes.data,
+                                               tid2pdf.ctypes.data, tid2pdf.size - 1,
+                                               None if trans_accs is None else trans_accs.ctypes.data, C.byref(tot)))
+        return tot.value
+
+    def acc_from_posteriors(self, pdf: int, feats: np.ndarray, post: np.ndarray):
+        feats = np.ascontiguousarray(np.atleast_2d(feats), np.float32)
+        post = np.ascontiguousarray(np.atleast_2d(post), np.float32)
+        A.check(A.lib().khg_acc_from_posteriors(self.model._h, self._h, pdf, feats.ctypes.data, feats.shape[0], A.KHG_HOST, post.ctypes.data))
+
+    def estep(self, feats, pdf_ids, loglikes_out, frame_weights=None, chunk_frames: int = 0, want_total: bool = False):
+        """Dense all-pdf log-likelihoods (into the reused device block `loglikes_out`,
+        pdf-major) + alignment statistics for one batch."""
+        fp, l0 = A.ptr(feats, np.float32)
+        ip, l1 = A.ptr(pdf_ids, np.int32)
+        wp, l2 = A.ptr(frame_weights, np.float32)
+        loc = A.same_loc(l0, l1, None if frame_weights is None else l2)
+        op, lo = A.ptr(loglikes_out, np.float32)
+        assert lo == A.KHG_DEVICE, "loglikes_out must be a device buffer"
+        tot = C.c_double(0.0)
+        A.check(A.lib().khg_estep(self.model._h, self._h, fp, int(feats.shape[0]), loc, ip, wp, op,
+                                  int(loglikes_out.shape[1]), chunk_frames, C.byref(tot) if want_total else None))
+        return tot.value if want_total else None

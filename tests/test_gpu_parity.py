@@ -1,0 +1,364 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI
+(include/khg_b200.h), against the CPU oracle on the same seeded inputs, the
+committed golden fixtures, and size-independent properties at larger sizes.
+
+Tolerances are BASELINE.json's: per-frame log-likelihoods 1e-4 relative /
+1e-3 absolute; accumulated statistics 1e-4 relative; integer work (bucketing,
+transition counts, frame counts) bit-exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import khg_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+LL_ATOL, LL_RTOL, STATS_RTOL = 1e-3, 1e-4, 1e-4
+
+
+def _assert_ll(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    err = np.abs(got - ref)
+    assert err.max() <= LL_ATOL, f"abs err {err.max()}"
+    big = np.abs(ref) > 10.0
+    if big.any():
+        assert (err[big] / np.abs(ref[big])).max() <= LL_RTOL
+
+
+def _assert_stats(got, ref, T):
+    for k in ("occ", "mean", "var"):
+        if ref[k] is None:
+            assert got[k] is None
+            continue
+        scale = np.abs(ref[k]).max() + 1e-30
+        # 1e-4 relative; entries that are tiny next to the array's scale are compared
+        # against that scale (posterior mass below fp32 resolution of the dominant term)
+        np.testing.assert_allclose(got[k], ref[k], rtol=STATS_RTOL, atol=STATS_RTOL * 1e-3 * scale)
+    assert abs(got["tot_frames"] - ref["tot_frames"]) <= 1e-9 * max(1.0, abs(ref["tot_frames"]))
+    assert abs(got["tot_like"] - ref["tot_like"]) <= STATS_RTOL * abs(ref["tot_like"]) + 1e-6
+
+
+def _device_model(model, kernel=None):
+    from kaldi_hmm_gmm_b200 import DeviceModel
+
+    dm = DeviceModel(model.dim, model.offsets)
+    if kernel is not None:
+        dm.set_kernel(kernel)
+    nbad = dm.upload(model.weights, model.means_invvars, model.inv_vars)
+    return dm, nbad
+
+
+@pytest.fixture(scope="module")
+def small(oracle):
+    model, means, vars_ = ko.make_synthetic_model(39, 13, 100, oracle=oracle)
+    feats, pdf = ko.make_synthetic_frames(model, means, vars_, 1000)
+    return model, feats, pdf
+
+
+def test_gconsts_on_device(oracle, small, golden_dir):
+    from kaldi_hmm_gmm_b200 import _cabi
+    import ctypes as C
+
+    model, _, _ = small
+    dm, nbad = _device_model(model)
+    assert nbad == 0
+    np.testing.assert_allclose(dm.gconsts(), model.gconsts, rtol=1e-5, atol=1e-4)
+    # golden closed forms (python/tests/test_diag_gmm.py:45-51)
+    for c in json.load(open(os.path.join(golden_dir, "diag_gmm_closed_form.json")))["cases"]:
+        w = np.array(c["weights"], np.float32)
+        var = np.array(c["vars"], np.float32)
+        iv = (1.0 / var).astype(np.float32)
+        miv = (np.array(c["means"], np.float32) * iv).astype(np.float32)
+        gc = np.empty(c["nmix"], np.float32)
+        nb = C.c_int32()
+        _cabi.check(_cabi.lib().khg_compute_gconsts(c["nmix"], c["dim"], w.ctypes.data, miv.ctypes.data, iv.ctypes.data, gc.ctypes.data, C.byref(nb)))
+        assert nb.value == 0
+        np.testing.assert_allclose(gc, c["gconsts"], rtol=2e-5, atol=1e-5)
+    # zero weight -> -inf counted bad; NaN -> error (csrc/diag-gmm.cc:132-141)
+    miv = np.ones((2, 3), np.float32)
+    iv = np.ones((2, 3), np.float32)
+    gc = np.empty(2, np.float32)
+    nb = C.c_int32()
+    w = np.array([0.0, 1.0], np.float32)
+    _cabi.check(_cabi.lib().khg_compute_gconsts(2, 3, w.ctypes.data, miv.ctypes.data, iv.ctypes.data, gc.ctypes.data, C.byref(nb)))
+    assert nb.value == 1 and np.isneginf(gc[0])
+    iv[1, 1] = -1.0
+    w[:] = 0.5
+    with pytest.raises(RuntimeError, match="not a number"):
+        _cabi.check(_cabi.lib().khg_compute_gconsts(2, 3, w.ctypes.data, miv.ctypes.data, iv.ctypes.data, gc.ctypes.data, C.byref(nb)))
+
+
+def test_golden_closed_form_likelihoods_and_posteriors(golden_dir):
+    """python/tests/test_diag_gmm.py:327-403, 529-553 against the CUDA path."""
+    from kaldi_hmm_gmm_b200 import DeviceModel
+
+    for c in json.load(open(os.path.join(golden_dir, "diag_gmm_closed_form.json")))["cases"]:
+        w = np.array(c["weights"], np.float32)
+        var = np.array(c["vars"], np.float32)
+        iv = (1.0 / var).astype(np.float32)
+        miv = (np.array(c["means"], np.float32) * iv).astype(np.float32)
+        x = np.array(c["x"], np.float32)
+        dm = DeviceModel(c["dim"], np.array([0, c["nmix"]], np.int32))
+        dm.upload(w, miv, iv)
+        mat = dm.pdf_loglikes(0, x)
+        assert mat.shape == (x.shape[0], c["nmix"])
+        np.testing.assert_allclose(mat, c["component_loglikes"], rtol=1e-4, atol=1e-4)
+        ll, post = dm.pdf_posteriors(0, x)
+        np.testing.assert_allclose(ll, c["loglike"], atol=1e-4)
+        np.testing.assert_allclose(post, c["posteriors"], rtol=1e-4, atol=1e-6)
+        dense = dm.loglikes_all_pdfs(x)
+        np.testing.assert_allclose(dense[:, 0], c["loglike"], atol=1e-4)
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+def test_dense_loglikes_vs_oracle(oracle, small, layout):
+    model, feats, _ = small
+    dm, _ = _device_model(model, kernel=1)
+    got = dm.loglikes_all_pdfs(feats, scale=0.7, layout=layout)
+    ref, bad = oracle.loglikes_all_pdfs(model, feats, scale=0.7, pdf_major=bool(layout))
+    assert bad == 0
+    _assert_ll(got, ref)
+
+
+@pytest.mark.parametrize("D,P,G,T", [(40, 50, 500, 2049), (5, 3, 3, 1), (13, 7, 300, 255), (80, 11, 64, 600)])
+def test_dense_loglikes_shapes(oracle, D, P, G, T):
+    import torch
+
+    model, means, vars_ = ko.make_synthetic_model(D, P, G, oracle=oracle)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, T)
+    dm, _ = _device_model(model, kernel=1)
+    ref, _ = oracle.loglikes_all_pdfs(model, feats)
+    _assert_ll(dm.loglikes_all_pdfs(feats), ref)
+    # device-resident buffers, pdf-major with padding in the leading dimension
+    dfe = torch.from_numpy(feats).cuda()
+    out = torch.full((P, T + 5), float("nan"), device="cuda")
+    dm.loglikes_all_pdfs(dfe, layout=1, out=out)
+    dm.sync()
+    _assert_ll(out[:, :T].T.cpu().numpy(), ref)
+
+
+def test_acc_stats_ali_vs_oracle(oracle, small):
+    from kaldi_hmm_gmm_b200 import DeviceStats
+
+    model, feats, pdf = small
+    dm, _ = _device_model(model)
+    fw = np.random.default_rng(3).random(feats.shape[0]).astype(np.float32)
+    for weights in (None, fw):
+        st = DeviceStats(dm)
+        pf = np.empty(feats.shape[0], np.float32)
+        tot = st.acc_stats_ali(feats, pdf, weights, pf)
+        ref = oracle.acc_stats_ali(model, feats, pdf, weights)
+        _assert_ll(pf, ref["per_frame"])
+        got = st.download()
+        _assert_stats(got, ref, feats.shape[0])
+        assert abs(tot - ref["tot_like"]) <= STATS_RTOL * abs(ref["tot_like"])
+        # occupancies of a pdf sum to the weight mass aligned to it (exact property)
+        for p in range(model.num_pdfs):
+            mass = float((np.ones_like(fw) if weights is None else fw)[pdf == p].astype(np.float64).sum())
+            assert abs(got["occ"][model.offsets[p]:model.offsets[p + 1]].sum() - mass) <= 1e-4 * max(1.0, mass)
+
+
+@pytest.mark.parametrize("flags,has_mean,has_var", [(4, False, False), (1, True, False), (2, True, True), (0, False, False)])
+def test_flags_control_buffers(oracle, small, flags, has_mean, has_var):
+    # csrc/mle-diag-gmm.cc:43-62 + csrc/model-common.cc:72-84
+    from kaldi_hmm_gmm_b200 import DeviceStats
+
+    model, feats, pdf = small
+    dm, _ = _device_model(model)
+    st = DeviceStats(dm, flags)
+    st.acc_stats_ali(feats, pdf)
+    got = st.download()
+    assert (got["mean"] is not None) == has_mean and (got["var"] is not None) == has_var
+    ref = oracle.acc_stats_ali(model, feats, pdf, flags=flags)
+    _assert_stats(got, ref, feats.shape[0])
+
+
+def test_ragged_big_pdf_and_accumulation_across_calls(oracle):
+    from kaldi_hmm_gmm_b200 import DeviceStats
+
+    rng = np.random.default_rng(11)
+    D = 20
+    sizes = np.array([1, 300, 2, 17, 64, 9, 1, 33], np.int32)  # ragged, one big pdf
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    G = int(offsets[-1])
+    means = rng.standard_normal((G, D)).astype(np.float32) * 2
+    vars_ = rng.uniform(0.5, 2, (G, D)).astype(np.float32)
+    w = np.concatenate([rng.dirichlet(np.ones(s)) for s in sizes]).astype(np.float32)
+    iv = (1 / vars_).astype(np.float32)
+    miv = (means * iv).astype(np.float32)
+    gc = np.concatenate([oracle.compute_gconsts(w[a:b], miv[a:b], iv[a:b])[0] for a, b in zip(offsets[:-1], offsets[1:])])
+    model = ko.PackedModel(offsets, w, miv, iv, gc)
+    feats, pdf = ko.make_synthetic_frames(model, means, vars_, 1500)
+    dm, _ = _device_model(model, kernel=1)
+    _assert_ll(dm.loglikes_all_pdfs(feats), oracle.loglikes_all_pdfs(model, feats)[0])
+    st = DeviceStats(dm)
+    tot = 0.0
+    for a, b in [(0, 1), (1, 700), (700, 700), (700, 1500)]:  # incl. single-frame and empty calls
+        tot += st.acc_stats_ali(feats[a:b], pdf[a:b])
+    ref = oracle.acc_stats_ali(model, feats, pdf)
+    _assert_stats(st.download(), ref, 1500)
+    assert abs(tot - ref["tot_like"]) <= STATS_RTOL * abs(ref["tot_like"])
+
+
+def test_tids_path_bit_exact_integers(oracle, small):
+    """tid->pdf mapping and transition counts are integer work: bit-exact.
+    scripts/gmm_acc_stats_ali.py:46-56; test there asserts sum(transition_accs)==frames
+    (scripts/test_gmm_acc_stats_ali.py:106)."""
+    from kaldi_hmm_gmm_b200 import DeviceStats
+
+    model, feats, _ = small
+    rng = np.random.default_rng(5)
+    num_tids = 4 * model.num_pdfs
+    tid2pdf = np.concatenate([[0], rng.integers(0, model.num_pdfs, num_tids)]).astype(np.int32)
+    tids = rng.integers(1, num_tids + 1, feats.shape[0]).astype(np.int32)
+    dm, _ = _device_model(model)
+    st = DeviceStats(dm)
+    trans = np.zeros(num_tids + 1, np.float64)
+    trans[3] = 2.0
+    tot = st.acc_stats_ali_tids(feats, tids, tid2pdf, trans)
+    expect = np.bincount(tids, minlength=num_tids + 1).astype(np.float64)
+    expect[3] += 2.0
+    assert np.array_equal(trans, expect)
+    assert trans.sum() - 2.0 == feats.shape[0]
+    ref = oracle.acc_stats_ali(model, feats, tid2pdf[tids])
+    _assert_stats(st.download(), ref, feats.shape[0])
+    assert abs(tot - ref["tot_like"]) <= STATS_RTOL * abs(ref["tot_like"])
+    bad = tids.copy()
+    bad[7] = num_tids + 1
+    with pytest.raises(RuntimeError, match="out of range"):
+        st.acc_stats_ali_tids(feats, bad, tid2pdf)
+
+
+def test_bad_pdf_id_and_nonfinite_raise(oracle, small):
+    from kaldi_hmm_gmm_b200 import DeviceStats
+
+    model, feats, pdf = small
+    dm, _ = _device_model(model, kernel=1)
+    st = DeviceStats(dm)
+    bad = pdf.copy()
+    bad[3] = model.num_pdfs
+    with pytest.raises(RuntimeError, match="out of range"):
+        st.acc_stats_ali(feats, bad)
+    f2 = feats.copy()
+    f2[5, 2] = np.nan
+    with pytest.raises(RuntimeError, match="Invalid answer"):  # csrc/diag-gmm.cc:385-387
+        DeviceStats(dm).acc_stats_ali(f2, pdf)
+    with pytest.raises(RuntimeError, match="Invalid answer"):  # csrc/decodable-am-diag-gmm.cc:63-65
+        dm.loglikes_all_pdfs(f2)
+    # a pdf whose Gaussians all have zero weight: LogSumExp is NaN -> error
+    w = model.weights.copy()
+    w[model.offsets[2]:model.offsets[3]] = 0.0
+    from kaldi_hmm_gmm_b200 import DeviceModel
+
+    dm2 = DeviceModel(model.dim, model.offsets)
+    assert dm2.upload(w, model.means_invvars, model.inv_vars) == model.offsets[3] - model.offsets[2]
+    with pytest.raises(RuntimeError, match="Invalid answer"):
+        dm2.loglikes_all_pdfs(feats[:10])
+
+
+def test_stats_add_scale_and_posteriors(oracle, small):
+    """AccumAmDiagGmm::Add/Scale (csrc/mle-am-diag-gmm.cc:119-138) and
+    AccumulateFromPosteriors (csrc/mle-diag-gmm.cc:123-143)."""
+    from kaldi_hmm_gmm_b200 import DeviceStats
+
+    model, feats, pdf = small
+    dm, _ = _device_model(model)
+    a, b = DeviceStats(dm), DeviceStats(dm)
+    a.acc_stats_ali(feats[:400], pdf[:400])
+    b.acc_stats_ali(feats[400:], pdf[400:])
+    a.add(1.0, b)
+    ref = oracle.acc_stats_ali(model, feats, pdf)
+    _assert_stats(a.download(), ref, feats.shape[0])
+    a.scale(0.5)
+    got = a.download()
+    np.testing.assert_allclose(got["occ"], 0.5 * ref["occ"], rtol=1e-4, atol=1e-7)
+    assert abs(got["tot_frames"] - 0.5 * ref["tot_frames"]) < 1e-6
+    c = DeviceStats(dm)
+    p = 4
+    ng = model.offsets[p + 1] - model.offsets[p]
+    post = np.random.default_rng(2).random((3, ng)).astype(np.float32)
+    c.acc_from_posteriors(p, feats[:3], post)
+    got = c.download()
+    occ = np.zeros(model.num_gauss)
+    mean = np.zeros((model.num_gauss, model.dim))
+    var = np.zeros_like(mean)
+    s = slice(model.offsets[p], model.offsets[p + 1])
+    for t in range(3):
+        oracle.acc_from_posteriors(ko.kGmmAll, feats[t], post[t], occ[s], mean[s], var[s])
+    np.testing.assert_allclose(got["occ"], occ, rtol=1e-6)
+    np.testing.assert_allclose(got["mean"], mean, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(got["var"], var, rtol=1e-6, atol=1e-9)
+    assert abs(got["tot_frames"] - post.sum()) < 1e-5 and got["tot_like"] == 0.0
+
+
+def test_estep_device_and_host_paths(oracle):
+    import torch
+    from kaldi_hmm_gmm_b200 import DeviceStats
+
+    model, means, vars_ = ko.make_synthetic_model(40, 64, 600, oracle=oracle)
+    T = 5000
+    feats, pdf = ko.make_synthetic_frames(model, means, vars_, T)
+    dm, _ = _device_model(model)
+    ref = oracle.acc_stats_ali(model, feats, pdf)
+    dense_ref, _ = oracle.loglikes_all_pdfs(model, feats)
+    block = torch.empty((model.num_pdfs, 2048), device="cuda")
+    # device-resident inputs
+    st = DeviceStats(dm)
+    tot = st.estep(torch.from_numpy(feats).cuda(), torch.from_numpy(pdf).cuda(), block, chunk_frames=2048, want_total=True)
+    _assert_stats(st.download(), ref, T)
+    assert abs(tot - ref["tot_like"]) <= STATS_RTOL * abs(ref["tot_like"])
+    last = T - (T // 2048) * 2048  # the block holds the last chunk
+    _assert_ll(block[:, :last].T.cpu().numpy(), dense_ref[T - last:])
+    # host inputs streamed through pinned staging
+    st2 = DeviceStats(dm)
+    tot2 = st2.estep(feats, pdf, block, chunk_frames=2048, want_total=True)
+    _assert_stats(st2.download(), ref, T)
+    assert abs(tot2 - ref["tot_like"]) <= STATS_RTOL * abs(ref["tot_like"])
+
+
+def test_large_properties(oracle):
+    """Size-independent properties at a size the oracle cannot check frame by frame:
+    (1) sum of occupancies == number of frames, per pdf, exactly the bucket sizes;
+    (2) linearity: stats(A)+stats(B) == stats(A u B); (3) permutation invariance;
+    (4) the dense block's aligned-pdf entry equals the stats path's per-frame log-like."""
+    import torch
+    from kaldi_hmm_gmm_b200 import DeviceStats
+
+    model, means, vars_ = ko.make_synthetic_model(39, 130, 1000, oracle=oracle)
+    T = 400_000
+    feats, pdf = ko.make_synthetic_frames(model, means, vars_, T)
+    dm, _ = _device_model(model)
+    dfe, dpdf = torch.from_numpy(feats).cuda(), torch.from_numpy(pdf).cuda()
+    st = DeviceStats(dm)
+    pf = torch.empty(T, device="cuda")
+    st.acc_stats_ali(dfe, dpdf, per_frame=pf, want_total=False)
+    full = st.download()
+    counts = np.bincount(pdf, minlength=model.num_pdfs)
+    pdf_occ = np.add.reduceat(full["occ"], model.offsets[:-1])
+    np.testing.assert_allclose(pdf_occ, counts, rtol=2e-6)
+    assert full["tot_frames"] == T
+    half = T // 2
+    a, b = DeviceStats(dm), DeviceStats(dm)
+    a.acc_stats_ali(dfe[:half], dpdf[:half], want_total=False)
+    b.acc_stats_ali(dfe[half:], dpdf[half:], want_total=False)
+    a.add(1.0, b)
+    got = a.download()
+    for k in ("occ", "mean", "var"):
+        np.testing.assert_allclose(got[k], full[k], rtol=1e-6, atol=1e-6 * np.abs(full[k]).max())
+    perm = torch.randperm(T, device="cuda")
+    c = DeviceStats(dm)
+    c.acc_stats_ali(dfe[perm].contiguous(), dpdf[perm].contiguous(), want_total=False)
+    got = c.download()
+    for k in ("occ", "mean", "var"):
+        np.testing.assert_allclose(got[k], full[k], rtol=1e-6, atol=1e-6 * np.abs(full[k]).max())
+    n = 20000
+    dense = dm.loglikes_all_pdfs(dfe[:n], layout=1)
+    dm.sync()
+    aligned = dense[dpdf[:n].long(), torch.arange(n, device="cuda")]
+    assert (aligned - pf[:n]).abs().max().item() < 1e-3
+    # oracle spot check on a slice
+    ref = oracle.acc_stats_ali(model, feats[:5000], pdf[:5000])
+    _assert_ll(pf[:5000].cpu().numpy(), ref["per_frame"])
