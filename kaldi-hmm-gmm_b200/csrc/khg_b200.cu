@@ -295,7 +295,7 @@ static khg_status dense_device(khg_model *m, const float *d_feats, int64_t T, fl
     return KHG_OK;
   }
   const int D = m->dim;
-  size_t smem = sizeof(float) * ((size_t)D * kDenseXP + 2 * (size_t)D * kSimtChunk);
+  size_t smem = sizeof(float) * ((size_t)D * kDenseXP + 4 + 2 * (size_t)D * kSimtChunk);
   if (smem > 220 * 1024) {
     set_error("feature dimension too large for the dense SIMT kernel");
     return KHG_ERR_UNSUPPORTED;
@@ -516,7 +516,7 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
   int end_bit = 1;
   while ((1 << end_bit) < P) ++end_bit;
   int grp_batch = std::max(1, std::min(8, 20480 / (2 * D * 8 * 4)));
-  size_t smem = sizeof(float) * ((size_t)D * (kStatsFrames + 1) + kStatsLLCap + (size_t)grp_batch * 2 * D * 8 + grp_batch * 8 + 128);
+  size_t smem = sizeof(float) * ((size_t)D * (kStatsFrames + 1) + 4 + kStatsLLCap + (size_t)grp_batch * 2 * D * 8 + grp_batch * 8 + 128);
   if (smem > 220 * 1024) {
     set_error("feature dimension too large for the statistics kernel");
     return KHG_ERR_UNSUPPORTED;

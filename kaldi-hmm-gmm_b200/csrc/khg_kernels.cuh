@@ -130,7 +130,7 @@ loglikes_simt_kernel(const float *__restrict__ feats, int64_t T, int D,
                      int64_t stride_t, int *__restrict__ err) {
   extern __shared__ float smem[];
   float *xs = smem;                       // D x 257
-  float *ms = smem + (size_t)D * kDenseXP;  // 2 x D x 32
+  float *ms = smem + (((size_t)D * kDenseXP + 3) & ~(size_t)3);  // 2 x D x 32, 16-byte aligned
   const int tid = threadIdx.x;
   const int64_t t0 = (int64_t)blockIdx.x * kDenseFrames;
   const int nfr = (int)min((int64_t)kDenseFrames, T - t0);
@@ -372,9 +372,9 @@ __global__ void item_scan_kernel(int P, const int32_t *__restrict__ offsets,
 // One CTA (128 threads) per work item = up to stats_frames_for(g_p) frames of one
 // pdf.  Phase A: thread = frame: log-likes of the pdf's Gaussians (groups of 8,
 // model staged in smem), max-subtracted softmax (csrc/eigen.cc:20-32), post *= w.
-// Phase B: thread = (Gaussian, dim) pair: fp32 reduction over the item's frames,
-// then ONE fp64 atomicAdd per statistic (the reference adds every frame's fp32
-// product into fp64; here <=128 products are summed in fp32 first).
+// Phase B: thread = (Gaussian, dim) pair: every frame's fp32 product is cast to
+// double and summed in double, like the reference; one fp64 atomicAdd per statistic
+// and work item.
 // ---------------------------------------------------------------------------
 struct StatsArgs {
   const float *feats;       // T x D (original order)
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
   const int D = a.D;
   const int XP = kStatsFrames + 1;
   float *xs = smem;                                   // D x 129
-  float *ll = xs + (size_t)D * XP;                    // kStatsLLCap
+  float *ll = xs + (((size_t)D * XP + 3) & ~(size_t)3);   // kStatsLLCap (16-byte aligned)
   float *ms = ll + kStatsLLCap;                       // grp_batch x 2 x D x 8
   float *gcs = ms + (size_t)a.grp_batch * 2 * D * 8;  // grp_batch x 8
   float *wsm = gcs + a.grp_batch * 8;                 // 128 weights
@@ -512,26 +512,28 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
     atomicAdd(&a.totals[1], W);
     if (a.call_like) atomicAdd(a.call_like, L);
   }
-  // Phase B: (g, k) pairs; k in [0, D) -> mean/var stats of dim k, k == D -> occupancy
+  // Phase B: (g, k) pairs; k in [0, D) -> mean/var stats of dim k, k == D -> occupancy.
+  // Exactly the reference's arithmetic (csrc/mle-diag-gmm.cc:131-141): each
+  // posterior-weighted product is rounded to fp32, cast to double, summed in double.
   const int KK = D + 1;
   for (int e = tid; e < ng * KK; e += 128) {
     const int g = e / KK, k = e - g * KK;
     const float *pr = ll + g * LP;
     if (k == D) {
-      float o = 0.f;
-      for (int t = 0; t < n; ++t) o += pr[t];
-      atomicAdd(&a.occ[g0 + g], (double)o);
+      double o = 0.0;
+      for (int t = 0; t < n; ++t) o += (double)pr[t];
+      atomicAdd(&a.occ[g0 + g], o);
     } else if (a.mean) {
       const float *xr = xs + k * XP;
-      float sm = 0.f, sv = 0.f;
+      double sm = 0.0, sv = 0.0;
 #pragma unroll 4
       for (int t = 0; t < n; ++t) {
-        float pv = pr[t], x = xr[t];
-        sm = fmaf(pv, x, sm);
-        sv = fmaf(pv, x * x, sv);
+        const float pv = pr[t], x = xr[t];
+        sm += (double)__fmul_rn(pv, x);
+        sv += (double)__fmul_rn(pv, __fmul_rn(x, x));
       }
-      atomicAdd(&a.mean[(size_t)(g0 + g) * D + k], (double)sm);
-      if (a.var) atomicAdd(&a.var[(size_t)(g0 + g) * D + k], (double)sv);
+      atomicAdd(&a.mean[(size_t)(g0 + g) * D + k], sm);
+      if (a.var) atomicAdd(&a.var[(size_t)(g0 + g) * D + k], sv);
     }
   }
 }

@@ -1,0 +1,110 @@
+"""tcgen05 (3xTF32, TMA, TMEM) dense log-likelihood kernel vs the CPU oracle and vs the
+fp32 SIMT kernel.  Tolerance: BASELINE.json — 1e-3 absolute / 1e-4 relative."""
+import numpy as np
+import pytest
+
+from oracle import khg_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+TC, SIMT = 2, 1
+
+
+def _models(model):
+    from kaldi_hmm_gmm_b200 import DeviceModel
+
+    out = []
+    for k in (TC, SIMT):
+        dm = DeviceModel(model.dim, model.offsets)
+        dm.set_kernel(k)
+        dm.upload(model.weights, model.means_invvars, model.inv_vars)
+        out.append(dm)
+    return out
+
+
+def _check(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    err = np.abs(got - ref)
+    assert np.isfinite(got).all()
+    assert err.max() <= 1e-3, f"abs err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"
+    big = np.abs(ref) > 10
+    assert (err[big] / np.abs(ref[big])).max() <= 1e-4
+
+
+@pytest.mark.parametrize("D,P,G,T", [
+    (40, 37, 350, 3000),     # several N tiles, T not a multiple of 128
+    (39, 13, 100, 1000),     # one N tile, K8 = 80
+    (40, 420, 4000, 700),    # many tiles, few frames -> N range split over CTAs
+    (13, 5, 17, 129),        # tiny K (one swizzle atom), single-Gaussian-ish pdfs
+    (60, 9, 200, 513),       # K = 121 -> 4 chunks
+    (5, 3, 3, 1),            # single frame
+])
+def test_tc_vs_oracle(oracle, D, P, G, T):
+    model, means, vars_ = ko.make_synthetic_model(D, P, G, oracle=oracle)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, T)
+    tc, simt = _models(model)
+    ref, bad = oracle.loglikes_all_pdfs(model, feats)
+    assert bad == 0
+    got = tc.loglikes_all_pdfs(feats)
+    _check(got, ref)
+    _check(got, simt.loglikes_all_pdfs(feats))
+    got_pm = tc.loglikes_all_pdfs(feats, scale=0.1, layout=1)
+    _check(got_pm.T * 10.0, ref)
+
+
+def test_tc_ragged_pdfs_and_zero_weight(oracle):
+    rng = np.random.default_rng(11)
+    D = 40
+    sizes = np.array([1, 240, 2, 17, 64, 9, 1, 33, 100, 139, 1, 1, 1, 230, 11], np.int32)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    G = int(offsets[-1])
+    means = rng.standard_normal((G, D)).astype(np.float32) * 2
+    vars_ = rng.uniform(0.5, 2, (G, D)).astype(np.float32)
+    w = np.concatenate([rng.dirichlet(np.ones(s)) for s in sizes]).astype(np.float32)
+    w[offsets[3] + 2] = 0.0  # zero-weight Gaussian inside a pdf: gconst = -inf, allowed
+    iv = (1 / vars_).astype(np.float32)
+    miv = (means * iv).astype(np.float32)
+    gc = np.concatenate([oracle.compute_gconsts(w[a:b], miv[a:b], iv[a:b])[0] for a, b in zip(offsets[:-1], offsets[1:])])
+    model = ko.PackedModel(offsets, w, miv, iv, gc)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, 777)
+    tc, _ = _models(model)
+    ref, bad = oracle.loglikes_all_pdfs(model, feats)
+    assert bad == 0
+    _check(tc.loglikes_all_pdfs(feats), ref)
+
+
+def test_tc_large_device_resident_vs_simt(oracle):
+    import torch
+
+    model, means, vars_ = ko.make_synthetic_model(40, 420, 4000, oracle=oracle)
+    T = 148 * 128 * 2 + 77
+    feats, pdf = ko.make_synthetic_frames(model, means, vars_, T)
+    tc, simt = _models(model)
+    dfe = torch.from_numpy(feats).cuda()
+    a = tc.loglikes_all_pdfs(dfe, layout=1)
+    b = simt.loglikes_all_pdfs(dfe, layout=1)
+    tc.sync()
+    simt.sync()
+    assert torch.isfinite(a).all()
+    assert (a - b).abs().max().item() < 1e-3
+    ref, _ = oracle.loglikes_all_pdfs(model, feats[-300:])
+    _check(a[:, -300:].T.cpu().numpy(), ref)
+
+
+def test_tc_nonfinite_and_all_zero_weight_pdf_raise(oracle):
+    from kaldi_hmm_gmm_b200 import DeviceModel
+
+    model, means, vars_ = ko.make_synthetic_model(40, 13, 100, oracle=oracle)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, 300)
+    tc, _ = _models(model)
+    f2 = feats.copy()
+    f2[5, 2] = np.nan
+    with pytest.raises(RuntimeError, match="Invalid answer"):
+        tc.loglikes_all_pdfs(f2)
+    w = model.weights.copy()
+    w[model.offsets[2]:model.offsets[3]] = 0.0
+    dm = DeviceModel(model.dim, model.offsets)
+    dm.set_kernel(TC)
+    dm.upload(w, model.means_invvars, model.inv_vars)
+    with pytest.raises(RuntimeError, match="Invalid answer"):
+        dm.loglikes_all_pdfs(feats[:10])
