@@ -250,6 +250,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     from kaldi_hmm_gmm_b200 import DeviceModel, DeviceStats, _cabi
+    from kaldi_hmm_gmm_b200 import parallel as par
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -264,14 +265,12 @@ def run_b200(args):
     D, P, G, T_total = CONFIGS[args.config]
     if args.frames:
         T_total = args.frames
-    T = T_total // world + (1 if rank < T_total % world else 0)
+    shard_a, shard_b = par.shard_frames(T_total, rank, world)
+    T = shard_b - shard_a
     K = 2 * D + 1
     hm = host_model(D, P, G)
     if world > 1:  # model parameters are broadcast once per EM iteration
-        for key in ("weights", "miv", "iv"):
-            t = torch.from_numpy(hm[key]).to(dev)
-            dist.broadcast(t, 0)
-            hm[key] = t.cpu().numpy()
+        hm.update(par.broadcast_model({k: hm[k] for k in ("weights", "miv", "iv")}, device=dev))
     dm = DeviceModel(D, hm["offsets"])
     dm.set_kernel({"auto": 0, "simt": 1, "tcgen05": 2}[args.kernel])
     dm.upload(hm["weights"], hm["miv"], hm["iv"])
@@ -296,7 +295,7 @@ def run_b200(args):
                 dense_events.append((e0, e1, b - a))
             st.acc_stats_ali(feats[a:b], pdf[a:b], want_total=False)
         if world > 1:
-            dist.all_reduce(stats_view)  # AccumAmDiagGmm::Add across ranks, NCCL over NVLink
+            par.allreduce_packed(stats_view)  # AccumAmDiagGmm::Add across ranks, NCCL over NVLink
 
     def barrier():
         if world > 1:

@@ -16,7 +16,7 @@
 // lo.lo term is ~2^-22 relative), which keeps |error| well inside BASELINE.json's
 // 1e-3 abs / 1e-4 rel bound on log-likelihoods of magnitude ~1e2.
 //
-// Structure (one persistent CTA per SM, 16 warps, warp-specialised):
+// Structure (one persistent CTA per SM, 24 warps, warp-specialised):
 //   warp 0      TMA producer: streams B tiles (240 Gaussians x 32 floats, hi and lo)
 //               through a ring of smem stages (cp.async.bulk.tensor, 128B swizzle)
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::tf32, M=128 (frames),
@@ -26,7 +26,7 @@
 //   warps 4-7   A builders: load a 128-frame feature tile, form [x, x^2, 1], split
 //               hi/lo and write it in the UMMA K-major 128B-swizzled layout.  A is
 //               stationary for all N tiles of a work item.
-//   warps 8-15  epilogue: tcgen05.ld the accumulator rows (thread = frame), per-pdf
+//   warps 8-23  epilogue: tcgen05.ld the accumulator rows (thread = frame), per-pdf
 //               max-subtracted log-sum-exp over the pdf's contiguous Gaussians,
 //               coalesced store of out[p][t] (pdf-major).
 // N tiles are aligned to pdf boundaries (tile table built on the host), so a pdf's
@@ -36,6 +36,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -50,7 +51,8 @@ constexpr int kUmmaK = 8;           // tf32
 constexpr int kAChunkBytes = kTileM * 128;   // 16384
 constexpr int kBStageBytes = kTileN * 128;   // 30720 (multiple of 1024)
 constexpr int kMaxChunks = 5;       // K <= 160
-constexpr int kTcThreads = 512;
+constexpr int kEpiGroups = 4;       // epilogue warpgroups (4 warps each, one per TMEM lane quadrant)
+constexpr int kTcThreads = 256 + 128 * kEpiGroups;
 constexpr float kNegSentinel = -1.0e30f;  // stands in for gconst = -inf (0 * inf = NaN in the split)
 
 // ---------------------------------------------------------------- PTX wrappers --
@@ -97,18 +99,26 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+// TMEM -> registers: 32 lanes x 16 consecutive fp32 columns; thread i of the warp gets
+// lane (warp%4)*32+i.  Issue and wait are separate so that the next segment's load is in
+// flight while the current one is reduced.  The wait names the destination registers as
+// in/out operands: consumers then depend on the wait, not just on the (asynchronous) load.
+struct TReg16 { uint32_t r[16]; };
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, TReg16 &t) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "=r"(t.r[0]), "=r"(t.r[1]), "=r"(t.r[2]), "=r"(t.r[3]), "=r"(t.r[4]), "=r"(t.r[5]), "=r"(t.r[6]), "=r"(t.r[7]),
+        "=r"(t.r[8]), "=r"(t.r[9]), "=r"(t.r[10]), "=r"(t.r[11]), "=r"(t.r[12]), "=r"(t.r[13]), "=r"(t.r[14]), "=r"(t.r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld16_wait(TReg16 &t) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(t.r[0]), "+r"(t.r[1]), "+r"(t.r[2]), "+r"(t.r[3]), "+r"(t.r[4]), "+r"(t.r[5]), "+r"(t.r[6]), "+r"(t.r[7]),
+                 "+r"(t.r[8]), "+r"(t.r[9]), "+r"(t.r[10]), "+r"(t.r[11]), "+r"(t.r[12]), "+r"(t.r[13]), "+r"(t.r[14]), "+r"(t.r[15])
+               :
+               : "memory");
 }
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t u;
@@ -119,6 +129,76 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// Max-subtracted log-sum-exp (csrc/eigen.cc:14-18) of the first L of 16 accumulator
+// columns held in registers; returns the max through M.  L is a compile-time constant so
+// that no issue slot is spent on masked-off columns.
+template <int L>
+__device__ __forceinline__ float seg_lse(const TReg16 &t, float &M) {
+  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+  if (L == 1) {
+    M = __uint_as_float(t.r[0]);
+    return M;
+  }
+  float m = __uint_as_float(t.r[0]);
+#pragma unroll
+  for (int i = 1; i < L; ++i) m = fmaxf(m, __uint_as_float(t.r[i]));
+  const float ml = m * kLog2e;
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i + 1 < L; i += 2) {
+    s0 += fast_exp2(fmaf(__uint_as_float(t.r[i]), kLog2e, -ml));
+    s1 += fast_exp2(fmaf(__uint_as_float(t.r[i + 1]), kLog2e, -ml));
+  }
+  if (L & 1) s0 += fast_exp2(fmaf(__uint_as_float(t.r[L - 1]), kLog2e, -ml));
+  M = m;
+  return fmaf(__log2f(s0 + s1), kLn2, m);
+}
+
+// LSE of a segment of `len` columns at TMEM address taddr whose first 16 columns are
+// already in t (len <= 16: from registers only; longer: two passes over TMEM).
+__device__ __forceinline__ float seg_lse_any(const TReg16 &t, uint32_t taddr, int len, float &M) {
+  switch (len) {
+    case 1: return seg_lse<1>(t, M);
+    case 2: return seg_lse<2>(t, M);
+    case 3: return seg_lse<3>(t, M);
+    case 4: return seg_lse<4>(t, M);
+    case 5: return seg_lse<5>(t, M);
+    case 6: return seg_lse<6>(t, M);
+    case 7: return seg_lse<7>(t, M);
+    case 8: return seg_lse<8>(t, M);
+    case 9: return seg_lse<9>(t, M);
+    case 10: return seg_lse<10>(t, M);
+    case 11: return seg_lse<11>(t, M);
+    case 12: return seg_lse<12>(t, M);
+    case 13: return seg_lse<13>(t, M);
+    case 14: return seg_lse<14>(t, M);
+    case 15: return seg_lse<15>(t, M);
+    case 16: return seg_lse<16>(t, M);
+    default: break;
+  }
+  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+  TReg16 w;
+  float m = -CUDART_INF_F;
+  for (int w0 = 0; w0 < len; w0 += 16) {
+    tc_ld16_issue(taddr + w0, w);
+    tc_ld16_wait(w);
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (w0 + i < len) m = fmaxf(m, __uint_as_float(w.r[i]));
+  }
+  const float ml = m * kLog2e;
+  float s = 0.f;
+  for (int w0 = 0; w0 < len; w0 += 16) {
+    tc_ld16_issue(taddr + w0, w);
+    tc_ld16_wait(w);
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (w0 + i < len) s += fast_exp2(fmaf(__uint_as_float(w.r[i]), kLog2e, -ml));
+  }
+  M = m;
+  return fmaf(__log2f(s), kLn2, m);
 }
 
 // UMMA shared-memory descriptor: K-major, 128B swizzle, 8-row groups 1024 B apart.
@@ -168,6 +248,7 @@ struct TcArgs {
   float *out;              // pdf-major, out[p*ld + t]
   int64_t ld;
   int *err;
+  int debug_mode;          // 0 = normal; 1 = epilogue skips the LSE (pipeline-ceiling experiment, KHG_TC_DEBUG_MODE)
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -201,7 +282,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     mbar_init(a_free, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), 8);
+      mbar_init(acc_empty(b), 4 * kEpiGroups);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
@@ -323,7 +404,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     }
   } else if (warp >= 8) {
     // ===================== epilogue =====================
-    const int wg = (warp - 8) >> 2;           // which half of the tile's pdfs
+    const int eg = (warp - 8) >> 2;           // epilogue group: handles segments eg, eg+4, ...
     const int quad = warp & 3;                // TMEM lane quadrant of this warp
     const int row = quad * 32 + lane;
     const float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
@@ -334,50 +415,63 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
       const int64_t t = (item / a.n_splits) * kTileM + row;
       const bool valid = t < a.T;
+      float *out_t = a.out + t;
       for (int j = j0; j < j1; ++j, ++acc_it) {
         const int buf = acc_it & 1;
         const int g0 = a.tile_g0[j];
         const int pa = a.tile_p0[j], pb = a.tile_p0[j + 1];
+        // segment table of the first 32 pdfs of the tile, one pdf per lane (prefetched
+        // before the accumulator is ready)
+        int o0 = __ldg(a.offsets + min(pa + lane, pb));
+        int o1 = __ldg(a.offsets + min(pa + lane + 1, pb));
         mbar_wait(acc_full(buf), (acc_it >> 1) & 1);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256;
-        for (int p = pa + wg; p < pb; p += 2) {
-          const int c0 = a.offsets[p] - g0;
-          const int len = a.offsets[p + 1] - a.offsets[p];
-          float v[16];
-          float M = -CUDART_INF_F, s = 0.f;
-          if (len <= 16) {
-            tc_ld16(trow + c0, v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < len) M = fmaxf(M, v[i]);
-            const float Ml = M * kLog2e;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < len) s += fast_exp2(fmaf(v[i], kLog2e, -Ml));
-          } else {
-            for (int w0 = 0; w0 < len; w0 += 16) {
-              tc_ld16(trow + c0 + w0, v);
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (w0 + i < len) M = fmaxf(M, v[i]);
-            }
-            const float Ml = M * kLog2e;
-            for (int w0 = 0; w0 < len; w0 += 16) {
-              tc_ld16(trow + c0 + w0, v);
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (w0 + i < len) s += fast_exp2(fmaf(v[i], kLog2e, -Ml));
-            }
+        for (int pb0 = pa; pb0 < pb && a.debug_mode != 1; pb0 += 32) {
+          if (pb0 != pa) {
+            o0 = __ldg(a.offsets + min(pb0 + lane, pb));
+            o1 = __ldg(a.offsets + min(pb0 + lane + 1, pb));
           }
-          // log(sum) + max (csrc/eigen.cc:17); a pdf whose Gaussians all carry the -inf
-          // sentinel, or a NaN, is the reference's "Invalid answer" throw.
-          float r = fmaf(__log2f(s), kLn2, M);
-          if (!(M > -1.0e29f) || !(fabsf(r) <= 3.0e38f)) {
-            r = CUDART_NAN_F;
-            if (valid) bad = true;
+          const int nseg = min(32, pb - pb0);
+          // software pipeline over this warp's segments (eg, eg+4, ...): the TMEM load
+          // of the next segment is in flight while the current one is reduced
+          auto finish = [&](const TReg16 &tr, int sidx, int c0, int len) {
+            float M;
+            float r = seg_lse_any(tr, trow + c0, len, M);
+            // a pdf whose Gaussians all carry the -inf sentinel, or a NaN, is the
+            // reference's "Invalid answer" throw (csrc/decodable-am-diag-gmm.cc:63-65)
+            if (!(M > -1.0e29f) || !(fabsf(r) <= 3.0e38f)) {
+              r = CUDART_NAN_F;
+              if (valid) bad = true;
+            }
+            if (valid) out_t[(int64_t)(pb0 + sidx) * a.ld] = a.scale * r;
+          };
+          TReg16 ta, tb;
+          int sa = eg, c0a = 0, lena = 0, c0b = 0, lenb = 0;
+          if (sa < nseg) {
+            c0a = __shfl_sync(0xffffffffu, o0, sa) - g0;
+            lena = __shfl_sync(0xffffffffu, o1, sa) - g0 - c0a;
+            tc_ld16_issue(trow + c0a, ta);
           }
-          if (valid) a.out[(int64_t)p * a.ld + t] = a.scale * r;
+          while (sa < nseg) {
+            tc_ld16_wait(ta);
+            const int sb = sa + kEpiGroups;
+            if (sb < nseg) {
+              c0b = __shfl_sync(0xffffffffu, o0, sb) - g0;
+              lenb = __shfl_sync(0xffffffffu, o1, sb) - g0 - c0b;
+              tc_ld16_issue(trow + c0b, tb);
+            }
+            finish(ta, sa, c0a, lena);
+            if (sb >= nseg) break;
+            tc_ld16_wait(tb);
+            sa = sb + kEpiGroups;
+            if (sa < nseg) {
+              c0a = __shfl_sync(0xffffffffu, o0, sa) - g0;
+              lena = __shfl_sync(0xffffffffu, o1, sa) - g0 - c0a;
+              tc_ld16_issue(trow + c0a, ta);
+            }
+            finish(tb, sb, c0b, lenb);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -523,6 +617,10 @@ khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scal
   a.out = d_out;
   a.ld = ld_out;
   a.err = m->d_err;
+  {
+    const char *dbg = getenv("KHG_TC_DEBUG_MODE");
+    a.debug_mode = dbg ? atoi(dbg) : 0;
+  }
   const size_t smem = (size_t)a_bytes + (size_t)a.stages * kBStageBytes + 256 + 1024;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;

@@ -362,3 +362,56 @@ def test_large_properties(oracle):
     # oracle spot check on a slice
     ref = oracle.acc_stats_ali(model, feats[:5000], pdf[:5000])
     _assert_ll(pf[:5000].cpu().numpy(), ref["per_frame"])
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import os
+    import sys
+
+    import torch
+    import torch.distributed as dist
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "kaldi-hmm-gmm_b200", "python")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from kaldi_hmm_gmm_b200 import DeviceModel, DeviceStats, _cabi
+    from kaldi_hmm_gmm_b200 import parallel as par
+
+    _cabi.check(_cabi.lib().khg_set_device(rank))
+    ora = ko.Oracle()
+    model, means, vars_ = ko.make_synthetic_model(40, 64, 600, oracle=ora)
+    T = 20001
+    feats, pdf = ko.make_synthetic_frames(model, means, vars_, T)
+    a, b = par.shard_frames(T, rank, world)
+    dm = DeviceModel(model.dim, model.offsets)
+    dm.upload(model.weights, model.means_invvars, model.inv_vars)
+    st = DeviceStats(dm)
+    st.acc_stats_ali(torch.from_numpy(feats[a:b]).cuda(), torch.from_numpy(pdf[a:b]).cuda(), want_total=False)
+    par.allreduce_stats(st)
+    torch.cuda.synchronize()
+    got = st.download()
+    ref = ora.acc_stats_ali(model, feats, pdf)
+    _assert_stats(got, ref, T)
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+
+
+def test_two_gpu_nccl_allreduce_of_stats(tmp_path):
+    """Frames sharded over 2 GPUs, packed stats summed by one NCCL all-reduce == oracle on all frames."""
+    import socket
+
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), f"ok{r}")) for r in range(2))
