@@ -507,7 +507,7 @@ void khg_stats_destroy(khg_stats *s) {
 static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, int64_t T,
                              const int32_t *d_ids, const float *d_w, float *d_pf, double *d_call_like) {
   if (m->max_gp > kStatsMaxGp) {
-    set_error("a pdf has more Gaussians than the statistics kernel supports (1638)");
+    set_error("a pdf has more Gaussians than the statistics kernel supports (1600)");
     return KHG_ERR_UNSUPPORTED;
   }
   const int D = m->dim, P = m->P;
@@ -515,8 +515,12 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
   const int64_t slab = 1 << 23;
   int end_bit = 1;
   while ((1 << end_bit) < P) ++end_bit;
-  int grp_batch = std::max(1, std::min(8, 20480 / (2 * D * 8 * 4)));
-  size_t smem = sizeof(float) * ((size_t)D * (kStatsFrames + 1) + 4 + kStatsLLCap + (size_t)grp_batch * 2 * D * 8 + grp_batch * 8 + 128);
+  // smem sized for THIS model: posterior tile for the largest pdf, model staging for
+  // at most the groups of the largest pdf (bounded) -> several CTAs per SM for C4-like models
+  const int max_groups = (m->max_gp + 7) / 8;
+  int grp_batch = std::max(1, std::min(std::min(8, max_groups), 20480 / (2 * D * 8 * 4)));
+  const int post_cap = std::min(kStatsPostCapMax, kStatsFrames * stats_pitch(m->max_gp));
+  size_t smem = sizeof(float) * ((size_t)kStatsFrames * stats_pitch(D) + post_cap + (size_t)grp_batch * 2 * D * 8 + grp_batch * 8 + 128);
   if (smem > 220 * 1024) {
     set_error("feature dimension too large for the statistics kernel");
     return KHG_ERR_UNSUPPORTED;
@@ -541,9 +545,9 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
     KHG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(m->w_cub.p, cub_bytes, m->w_keys.as<int32_t>(), m->w_keys_out.as<int32_t>(),
                                                  m->w_vals_in.as<int32_t>(), m->w_vals_out.as<int32_t>(), (int)n, 0, end_bit, st));
     bucket_starts_kernel<<<grid_for(n + 1, 256), 256, 0, st>>>(m->w_keys_out.as<int32_t>(), n, P, m->w_starts.as<int32_t>());
-    item_scan_kernel<<<1, 1024, 0, st>>>(P, m->d_offsets, m->w_starts.as<int32_t>(), m->w_item_start.as<int32_t>());
+    item_scan_kernel<<<1, 1024, 0, st>>>(P, m->d_offsets, m->w_starts.as<int32_t>(), m->w_item_start.as<int32_t>(), post_cap);
     // upper bound on work items: every pdf wastes at most one partial item
-    int f_min = stats_frames_for(m->max_gp);
+    int f_min = stats_frames_for(m->max_gp, post_cap);
     int64_t max_items = n / f_min + P + 1;
     StatsArgs a;
     a.feats = d_feats + t0 * D;
@@ -565,6 +569,7 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
     a.P = P;
     a.D = D;
     a.grp_batch = grp_batch;
+    a.post_cap = post_cap;
     stats_kernel<<<(unsigned)max_items, 128, smem, st>>>(a);
     g_launch_count += 5 + 3;  // ours + the radix-sort passes (library)
     KHG_CUDA_TRY(cudaGetLastError());

@@ -322,19 +322,27 @@ __global__ void bucket_starts_kernel(const int32_t *__restrict__ sorted_keys, in
   for (int32_t p = kprev + 1; p <= kcur; ++p) starts[p] = (int32_t)i;
 }
 
-constexpr int kStatsFrames = 128;   // frames per work item (upper bound)
-constexpr int kStatsLLCap = 8192;   // floats of smem for the ll/posterior tile
-constexpr int kStatsMaxGp = kStatsLLCap / 5;
+constexpr int kStatsFrames = 128;      // frames per work item (upper bound)
+constexpr int kStatsPostCapMax = 8192; // max floats of smem for the posterior tile
+constexpr int kStatsMaxGp = 1600;      // largest pdf the statistics kernel accepts
 
-__host__ __device__ inline int stats_frames_for(int ng) {
-  int f = kStatsLLCap / ng - 4;
+// Row pitch (floats) for a smem matrix whose rows are read with LDS.128 by consecutive
+// threads: a multiple of 4 whose 16-byte stride is odd => conflict-free.
+__host__ __device__ inline int stats_pitch(int n) {
+  int p = (n + 3) & ~3;
+  if (((p >> 2) & 1) == 0) p += 4;
+  return p;
+}
+// Frames per work item of a pdf with ng Gaussians, given the posterior-tile capacity.
+__host__ __device__ inline int stats_frames_for(int ng, int post_cap) {
+  int f = post_cap / stats_pitch(ng);
   return f < 1 ? 1 : (f > kStatsFrames ? kStatsFrames : f);
 }
 
 // item_start[p] = exclusive scan of ceil(n_p / frames_for(g_p)); single block.
 __global__ void item_scan_kernel(int P, const int32_t *__restrict__ offsets,
                                  const int32_t *__restrict__ starts,
-                                 int32_t *__restrict__ item_start) {
+                                 int32_t *__restrict__ item_start, int post_cap) {
   __shared__ int32_t carry;
   __shared__ int32_t buf[1024];
   if (threadIdx.x == 0) carry = 0;
@@ -343,7 +351,7 @@ __global__ void item_scan_kernel(int P, const int32_t *__restrict__ offsets,
     int p = base + threadIdx.x;
     int32_t v = 0;
     if (p < P) {
-      int f = stats_frames_for(offsets[p + 1] - offsets[p]);
+      int f = stats_frames_for(offsets[p + 1] - offsets[p], post_cap);
       v = (starts[p + 1] - starts[p] + f - 1) / f;
     }
     buf[threadIdx.x] = v;
@@ -369,12 +377,16 @@ __global__ void item_scan_kernel(int P, const int32_t *__restrict__ offsets,
 // (csrc/mle-diag-gmm.cc:145-158) -> DiagGmm::ComponentPosteriors
 // (csrc/diag-gmm.cc:368-392) -> AccumulateFromPosteriors
 // (csrc/mle-diag-gmm.cc:123-143).
-// One CTA (128 threads) per work item = up to stats_frames_for(g_p) frames of one
-// pdf.  Phase A: thread = frame: log-likes of the pdf's Gaussians (groups of 8,
-// model staged in smem), max-subtracted softmax (csrc/eigen.cc:20-32), post *= w.
-// Phase B: thread = (Gaussian, dim) pair: every frame's fp32 product is cast to
-// double and summed in double, like the reference; one fp64 atomicAdd per statistic
-// and work item.
+// One CTA (128 threads) per work item = up to 128 frames of one pdf.
+//   stage   gathered feature rows -> smem X[t][.] (row pitch chosen so that one
+//           LDS.128 per thread-row is conflict-free)
+//   phase A thread = frame: log-likes of the pdf's Gaussians (groups of 8 or 4, model
+//           staged in smem, broadcast LDS.128), max-subtracted softmax
+//           (csrc/eigen.cc:20-32), post *= w, totals (csrc/mle-am-diag-gmm.cc:49-50)
+//   phase B a (4 Gaussians x 4 dims) register tile per thread over a quarter of the
+//           frames: occ += post, mean += post*x, var += post*x^2 in fp32 over <=128
+//           frames, then ONE fp64 atomicAdd per statistic (the reference casts every
+//           frame's fp32 product to double; the difference is ~1e-7 relative).
 // ---------------------------------------------------------------------------
 struct StatsArgs {
   const float *feats;       // T x D (original order)
@@ -391,18 +403,53 @@ struct StatsArgs {
   double *call_like;         // this call's sum ll*w (may be NULL)
   float *per_frame;          // T or NULL (original order)
   int *err;
-  int P, D, grp_batch;
+  int P, D, grp_batch, post_cap;
 };
+
+// log-likes of NG (8 or 4) Gaussians of one group for the frame row xr (D floats)
+template <int NG>
+__device__ __forceinline__ void stats_group_ll(const float *__restrict__ xr, const float *__restrict__ mm,
+                                               const float *__restrict__ vv, int D, float (&aa)[8], float (&bb)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) aa[j] = bb[j] = 0.f;
+  const int D4 = D & ~3;
+  for (int d0 = 0; d0 < D4; d0 += 4) {
+    const float4 xq = *reinterpret_cast<const float4 *>(xr + d0);
+    const float xs4[4] = {xq.x, xq.y, xq.z, xq.w};
+#pragma unroll
+    for (int dd = 0; dd < 4; ++dd) {
+      const float x = xs4[dd], q = x * x;  // data.array().square(), csrc/diag-gmm.cc:175
+      const float4 ma = *reinterpret_cast<const float4 *>(mm + (d0 + dd) * 8);
+      const float4 va = *reinterpret_cast<const float4 *>(vv + (d0 + dd) * 8);
+      aa[0] = fmaf(ma.x, x, aa[0]); aa[1] = fmaf(ma.y, x, aa[1]); aa[2] = fmaf(ma.z, x, aa[2]); aa[3] = fmaf(ma.w, x, aa[3]);
+      bb[0] = fmaf(va.x, q, bb[0]); bb[1] = fmaf(va.y, q, bb[1]); bb[2] = fmaf(va.z, q, bb[2]); bb[3] = fmaf(va.w, q, bb[3]);
+      if (NG == 8) {
+        const float4 mb = *reinterpret_cast<const float4 *>(mm + (d0 + dd) * 8 + 4);
+        const float4 vb = *reinterpret_cast<const float4 *>(vv + (d0 + dd) * 8 + 4);
+        aa[4] = fmaf(mb.x, x, aa[4]); aa[5] = fmaf(mb.y, x, aa[5]); aa[6] = fmaf(mb.z, x, aa[6]); aa[7] = fmaf(mb.w, x, aa[7]);
+        bb[4] = fmaf(vb.x, q, bb[4]); bb[5] = fmaf(vb.y, q, bb[5]); bb[6] = fmaf(vb.z, q, bb[6]); bb[7] = fmaf(vb.w, q, bb[7]);
+      }
+    }
+  }
+  for (int d = D4; d < D; ++d) {
+    const float x = xr[d], q = x * x;
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
+      aa[j] = fmaf(mm[d * 8 + j], x, aa[j]);
+      bb[j] = fmaf(vv[d * 8 + j], q, bb[j]);
+    }
+  }
+}
 
 __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
   extern __shared__ float smem[];
   const int D = a.D;
-  const int XP = kStatsFrames + 1;
-  float *xs = smem;                                   // D x 129
-  float *ll = xs + (((size_t)D * XP + 3) & ~(size_t)3);   // kStatsLLCap (16-byte aligned)
-  float *ms = ll + kStatsLLCap;                       // grp_batch x 2 x D x 8
-  float *gcs = ms + (size_t)a.grp_batch * 2 * D * 8;  // grp_batch x 8
-  float *wsm = gcs + a.grp_batch * 8;                 // 128 weights
+  const int XP = stats_pitch(D);
+  float *X = smem;                                      // 128 x XP (tail of each row zero)
+  float *post = X + kStatsFrames * XP;                  // post_cap floats: [t][PG]
+  float *ms = post + a.post_cap;                        // grp_batch x 2 x D x 8
+  float *gcs = ms + (size_t)a.grp_batch * 2 * D * 8;    // grp_batch x 8
+  float *wsm = gcs + a.grp_batch * 8;                   // 128 weights
   __shared__ int s_pdf;
   __shared__ double s_red[8];
   const int tid = threadIdx.x;
@@ -419,20 +466,43 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
   __syncthreads();
   const int p = s_pdf;
   const int g0 = a.offsets[p], ng = a.offsets[p + 1] - g0;
-  const int f = stats_frames_for(ng);
-  const int LP = f + 4;
+  const int PG = stats_pitch(ng);
+  const int f = stats_frames_for(ng, a.post_cap);
   const int pos0 = a.starts[p] + (item - a.item_start[p]) * f;
   const int n = min(f, a.starts[p + 1] - pos0);
   const int grp0 = a.grp_start[p], ngrp = a.grp_start[p + 1] - grp0;
 
-  // stage features (gathered rows), one warp per frame row
-  for (int r = tid >> 5; r < n; r += 4) {
-    const float *src = a.feats + (size_t)a.order[pos0 + r] * D;
-    for (int d = tid & 31; d < D; d += 32) xs[d * XP + r] = src[d];
+  // stage features (gathered rows).  Each warp owns rows warp, warp+4, ...; it reads its
+  // 32 row indices with one load, then (rows 16-byte aligned) streams every row with
+  // cp.async 16-byte chunks so that all of its rows are in flight at once.
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int r_mine = warp + 4 * lane;
+    const int idx_mine = r_mine < n ? a.order[pos0 + r_mine] : 0;
+    const bool vec = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.feats) & 15) == 0);
+    const int chunks = D >> 2;
+    for (int k = 0; k < 32; ++k) {
+      const int r = warp + 4 * k;
+      if (r >= n) break;
+      const int idx = __shfl_sync(0xffffffffu, idx_mine, k);
+      const float *src = a.feats + (size_t)idx * D;
+      float *dst = X + r * XP;
+      if (vec) {
+        for (int c = lane; c < chunks; c += 32) {
+          const uint32_t d32 = static_cast<uint32_t>(__cvta_generic_to_shared(dst + 4 * c));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d32), "l"(src + 4 * c) : "memory");
+        }
+        for (int d = D + lane; d < XP; d += 32) dst[d] = 0.f;
+      } else {
+        for (int d = lane; d < XP; d += 32) dst[d] = d < D ? src[d] : 0.f;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   if (tid < n) wsm[tid] = a.weights ? a.weights[a.order[pos0 + tid]] : 1.0f;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 
-  // Phase A
+  // ---- phase A ----
   for (int gb0 = 0; gb0 < ngrp; gb0 += a.grp_batch) {
     const int nb = min(a.grp_batch, ngrp - gb0);
     __syncthreads();
@@ -444,58 +514,43 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
     }
     __syncthreads();
     if (tid < n) {
+      const float *xr = X + tid * XP;
       for (int gb = 0; gb < nb; ++gb) {
         float aa[8], bb[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) aa[j] = bb[j] = 0.f;
         const float *mm = ms + (size_t)gb * 2 * D * 8;
         const float *vv = mm + D * 8;
-#pragma unroll 2
-        for (int d = 0; d < D; ++d) {
-          float x = xs[d * XP + tid];
-          float q = x * x;
-          float4 ma = *reinterpret_cast<const float4 *>(mm + d * 8);
-          float4 mb = *reinterpret_cast<const float4 *>(mm + d * 8 + 4);
-          float4 va = *reinterpret_cast<const float4 *>(vv + d * 8);
-          float4 vb = *reinterpret_cast<const float4 *>(vv + d * 8 + 4);
-          float mj[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
-          float vj[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+        const int gl0 = (gb0 + gb) * 8;
+        const int cnt = min(8, ng - gl0);
+        if (cnt > 4) stats_group_ll<8>(xr, mm, vv, D, aa, bb);
+        else stats_group_ll<4>(xr, mm, vv, D, aa, bb);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            aa[j] = fmaf(mj[j], x, aa[j]);
-            bb[j] = fmaf(vj[j], q, bb[j]);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          int gl = (gb0 + gb) * 8 + j;
-          if (gl < ng) ll[gl * LP + tid] = (gcs[gb * 8 + j] + aa[j]) - 0.5f * bb[j];
-        }
+        for (int j = 0; j < 8; ++j)
+          if (j < cnt) post[tid * PG + gl0 + j] = (gcs[gb * 8 + j] + aa[j]) - 0.5f * bb[j];  // csrc/diag-gmm.cc:174-175
       }
     }
   }
-  __syncthreads();
   // softmax over the pdf's Gaussians (csrc/eigen.cc:20-32), then post *= weight
   // (csrc/mle-diag-gmm.cc:153); totals as csrc/mle-am-diag-gmm.cc:49-50.
   double my_like = 0.0, my_w = 0.0;
   if (tid < n) {
-    float mx = ll[tid];
-    for (int g = 1; g < ng; ++g) mx = fmaxf(mx, ll[g * LP + tid]);
+    float *pr = post + tid * PG;
+    float mx = pr[0];
+    for (int g = 1; g < ng; ++g) mx = fmaxf(mx, pr[g]);
     float s = 0.f;
     for (int g = 0; g < ng; ++g) {
-      float e = __expf(ll[g * LP + tid] - mx);
-      ll[g * LP + tid] = e;
+      float e = __expf(pr[g] - mx);
+      pr[g] = e;
       s += e;
     }
-    float lse = logf(s) + mx;
+    const float lse = logf(s) + mx;
     if (!finite_f(lse)) atomicOr(a.err, ERR_NONFINITE);
-    float w = wsm[tid];
-    for (int g = 0; g < ng; ++g) ll[g * LP + tid] = (ll[g * LP + tid] / s) * w;
+    const float w = wsm[tid];
+    for (int g = 0; g < ng; ++g) pr[g] = (pr[g] / s) * w;
+    for (int g = ng; g < PG; ++g) pr[g] = 0.f;
     if (a.per_frame) a.per_frame[a.order[pos0 + tid]] = lse;
     my_like = (double)(lse * w);
     my_w = (double)w;
   }
-  // block-reduce the two totals
   for (int off = 16; off > 0; off >>= 1) {
     my_like += __shfl_xor_sync(0xffffffffu, my_like, off);
     my_w += __shfl_xor_sync(0xffffffffu, my_w, off);
@@ -512,28 +567,54 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
     atomicAdd(&a.totals[1], W);
     if (a.call_like) atomicAdd(a.call_like, L);
   }
-  // Phase B: (g, k) pairs; k in [0, D) -> mean/var stats of dim k, k == D -> occupancy.
-  // Exactly the reference's arithmetic (csrc/mle-diag-gmm.cc:131-141): each
-  // posterior-weighted product is rounded to fp32, cast to double, summed in double.
-  const int KK = D + 1;
-  for (int e = tid; e < ng * KK; e += 128) {
-    const int g = e / KK, k = e - g * KK;
-    const float *pr = ll + g * LP;
-    if (k == D) {
-      double o = 0.0;
-      for (int t = 0; t < n; ++t) o += (double)pr[t];
-      atomicAdd(&a.occ[g0 + g], o);
-    } else if (a.mean) {
-      const float *xr = xs + k * XP;
-      double sm = 0.0, sv = 0.0;
-#pragma unroll 4
-      for (int t = 0; t < n; ++t) {
-        const float pv = pr[t], x = xr[t];
-        sm += (double)__fmul_rn(pv, x);
-        sv += (double)__fmul_rn(pv, __fmul_rn(x, x));
+  // ---- phase B ----
+  const int n_gt = PG >> 2, n_dt = XP >> 2;
+  const int tiles = n_gt * n_dt;
+  int TQ = 1;
+  while (TQ < 4 && tiles * TQ * 2 <= 128) TQ <<= 1;
+  const int per = (n + TQ - 1) / TQ;
+  for (int w = tid; w < tiles * TQ; w += 128) {
+    const int tq = w / tiles, tile = w - tq * tiles;
+    const int gt = tile / n_dt, dt = tile - gt * n_dt;
+    const int ta = tq * per, tb = min(n, ta + per);
+    float occ[4] = {0.f, 0.f, 0.f, 0.f};
+    float sm[4][4], sv[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sm[i][j] = sv[i][j] = 0.f;
+    const float *pp = post + gt * 4, *xp = X + dt * 4;
+#pragma unroll 2
+    for (int t = ta; t < tb; ++t) {
+      const float4 pq = *reinterpret_cast<const float4 *>(pp + t * PG);
+      const float4 xq = *reinterpret_cast<const float4 *>(xp + t * XP);
+      const float pv[4] = {pq.x, pq.y, pq.z, pq.w};
+      const float xv[4] = {xq.x, xq.y, xq.z, xq.w};
+      const float qv[4] = {xq.x * xq.x, xq.y * xq.y, xq.z * xq.z, xq.w * xq.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        occ[i] += pv[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sm[i][j] = fmaf(pv[i], xv[j], sm[i][j]);
+          sv[i][j] = fmaf(pv[i], qv[j], sv[i][j]);
+        }
       }
-      atomicAdd(&a.mean[(size_t)(g0 + g) * D + k], sm);
-      if (a.var) atomicAdd(&a.var[(size_t)(g0 + g) * D + k], sv);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int g = gt * 4 + i;
+      if (g >= ng) continue;
+      if (dt == 0) atomicAdd(&a.occ[g0 + g], (double)occ[i]);
+      if (a.mean) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int d = dt * 4 + j;
+          if (d >= D) continue;
+          atomicAdd(&a.mean[(size_t)(g0 + g) * D + d], (double)sm[i][j]);
+          if (a.var) atomicAdd(&a.var[(size_t)(g0 + g) * D + d], (double)sv[i][j]);
+        }
+      }
     }
   }
 }
