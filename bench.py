@@ -346,7 +346,8 @@ def run_b200(args):
     achieved = flops_per_frame * dense_frames / (dense_ms * 1e-3) / 1e12
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("dram_bytes_per_launch")
+        # ncu-measured DRAM bytes per frame (profiles/) x frames of an average bench launch
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["dram_bytes_per_frame"] * dense_frames / max(1, len(dense_events))
     except Exception:
         pass
     roofline = {

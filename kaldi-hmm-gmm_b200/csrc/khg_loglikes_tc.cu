@@ -145,15 +145,20 @@ __device__ __forceinline__ float seg_lse(const TReg16 &t, float &M) {
 #pragma unroll
   for (int i = 1; i < L; ++i) m = fmaxf(m, __uint_as_float(t.r[i]));
   const float ml = m * kLog2e;
-  float s0 = 0.f, s1 = 0.f;
+  // packed fp32x2 math (FFMA2 / FADD2 on sm_100): one issue slot per two columns
+  const float2 k2 = make_float2(kLog2e, kLog2e), nm2 = make_float2(-ml, -ml);
+  float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int i = 0; i + 1 < L; i += 2) {
-    s0 += fast_exp2(fmaf(__uint_as_float(t.r[i]), kLog2e, -ml));
-    s1 += fast_exp2(fmaf(__uint_as_float(t.r[i + 1]), kLog2e, -ml));
+    float2 a = __ffma2_rn(make_float2(__uint_as_float(t.r[i]), __uint_as_float(t.r[i + 1])), k2, nm2);
+    a.x = fast_exp2(a.x);
+    a.y = fast_exp2(a.y);
+    s2 = __fadd2_rn(s2, a);
   }
-  if (L & 1) s0 += fast_exp2(fmaf(__uint_as_float(t.r[L - 1]), kLog2e, -ml));
+  float s = s2.x + s2.y;
+  if (L & 1) s += fast_exp2(fmaf(__uint_as_float(t.r[L - 1]), kLog2e, -ml));
   M = m;
-  return fmaf(__log2f(s0 + s1), kLn2, m);
+  return fmaf(__log2f(s), kLn2, m);
 }
 
 // LSE of a segment of `len` columns at TMEM address taddr whose first 16 columns are

@@ -108,3 +108,35 @@ def test_tc_nonfinite_and_all_zero_weight_pdf_raise(oracle):
     dm.upload(w, model.means_invvars, model.inv_vars)
     with pytest.raises(RuntimeError, match="Invalid answer"):
         dm.loglikes_all_pdfs(feats[:10])
+
+
+@pytest.mark.parametrize("name,D,P,G,T", [
+    ("C2-monophone", 39, 130, 1000, 3000),
+    ("C3-tri1", 39, 2000, 10000, 1500),
+    ("C4-lda-mllt", 40, 4200, 40000, 1000),
+    ("C5-sat", 40, 5000, 100000, 600),
+])
+def test_baseline_config_shapes(oracle, name, D, P, G, T):
+    """The model shapes BASELINE.json names (configs[1..4]): dense block (tcgen05) and
+    alignment statistics against the oracle on a slice of frames."""
+    import os
+
+    from kaldi_hmm_gmm_b200 import DeviceStats
+
+    model, means, vars_ = ko.make_synthetic_model(D, P, G, oracle=oracle)
+    feats, pdf = ko.make_synthetic_frames(model, means, vars_, T)
+    tc, _ = _models(model)
+    ref, bad = oracle.loglikes_all_pdfs(model, feats, threads=os.cpu_count() or 1)
+    assert bad == 0
+    _check(tc.loglikes_all_pdfs(feats), ref)
+    st = DeviceStats(tc)
+    pf = np.empty(T, np.float32)
+    tot = st.acc_stats_ali(feats, pdf, per_frame=pf)
+    r = oracle.acc_stats_ali(model, feats, pdf)
+    got = st.download()
+    assert np.abs(pf - r["per_frame"]).max() < 1e-3
+    for k in ("occ", "mean", "var"):
+        np.testing.assert_allclose(got[k], r[k], rtol=1e-4, atol=1e-6 * np.abs(r[k]).max())
+    assert abs(tot - r["tot_like"]) < 1e-4 * abs(r["tot_like"])
+    # the aligned-pdf column of the dense block is the per-frame log-like of the stats path
+    assert np.abs(ref[np.arange(T), pdf] - r["per_frame"]).max() < 1e-4
