@@ -214,8 +214,33 @@ khg_status khg_estep(khg_model *m, khg_stats *s, const float *feats, int64_t T,
                      int64_t ld_out, int64_t chunk_frames,
                      double *tot_loglike);
 
-/* Device M-step: MleAmDiagGmmUpdate without Gaussian
- * removal is planned for a later round; not exported yet. */
+/* ---------------------------------------------------------------- M-step --
+ * MleAmDiagGmmUpdate (csrc/mle-am-diag-gmm.cc:153-202) = MleDiagGmmUpdate
+ * (csrc/mle-diag-gmm.cc:243-390) for every pdf, on the device, reading the packed
+ * statistics in place: weights = occ/sum(occ), mean = x/occ, var = x2/occ - mean^2
+ * floored at min_variance, Gaussians with occ <= min_gaussian_occupancy or weight <=
+ * min_gaussian_weight removed (never the last one of a pdf) with the weights
+ * renormalised, gconsts recomputed, objective change as MlObjective (:479-499).
+ * Because removal changes the number of Gaussians, the result is a NEW model handle;
+ * the old one stays valid.  update_flags is a GmmUpdateFlags subset of the stats' flags
+ * (kGmmTransitions is ignored here). */
+typedef struct {
+  float min_gaussian_weight;     /* 1e-5  (csrc/mle-diag-gmm.h:23-45) */
+  float min_gaussian_occupancy;  /* 10    */
+  double min_variance;           /* 0.001 */
+  int32_t remove_low_count_gaussians; /* 1 */
+} khg_mle_options;
+
+khg_status khg_mle_update(khg_model *m, const khg_stats *s, const khg_mle_options *opts,
+                          uint16_t update_flags, khg_model **new_model,
+                          float *obj_change, float *count,
+                          int32_t *floored_elements, int32_t *floored_gaussians,
+                          int32_t *removed_gaussians);
+
+/* Copies the packed model back to the host (any pointer may be NULL):
+ * gauss_offsets int32[P+1], weights/gconsts f32[G], means_invvars/inv_vars f32[G*D]. */
+khg_status khg_model_download(khg_model *m, int32_t *gauss_offsets, float *weights,
+                              float *means_invvars, float *inv_vars, float *gconsts);
 
 /* Number of kernels this library launched since load (bench.py's
  * gpu_launches). */

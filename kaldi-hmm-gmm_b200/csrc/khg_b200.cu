@@ -677,6 +677,148 @@ khg_status khg_acc_from_posteriors(khg_model *m, khg_stats *s, int32_t pdf, cons
   return KHG_OK;
 }
 
+// ------------------------------------------------------------------ M-step --
+khg_status khg_model_download(khg_model *m, int32_t *gauss_offsets, float *weights, float *means_invvars,
+                              float *inv_vars, float *gconsts) {
+  KHG_REQUIRE(m && m->uploaded, "model not uploaded");
+  cudaStream_t st = m->stream;
+  size_t gd = (size_t)m->G * m->dim;
+  if (gauss_offsets) std::memcpy(gauss_offsets, m->h_offsets.data(), sizeof(int32_t) * (m->P + 1));
+  if (weights) KHG_CUDA_TRY(cudaMemcpyAsync(weights, m->d_weights, sizeof(float) * m->G, cudaMemcpyDeviceToHost, st));
+  if (means_invvars) KHG_CUDA_TRY(cudaMemcpyAsync(means_invvars, m->d_miv, sizeof(float) * gd, cudaMemcpyDeviceToHost, st));
+  if (inv_vars) KHG_CUDA_TRY(cudaMemcpyAsync(inv_vars, m->d_iv, sizeof(float) * gd, cudaMemcpyDeviceToHost, st));
+  if (gconsts) KHG_CUDA_TRY(cudaMemcpyAsync(gconsts, m->d_gconsts, sizeof(float) * m->G, cudaMemcpyDeviceToHost, st));
+  KHG_CUDA_TRY(cudaStreamSynchronize(st));
+  return KHG_OK;
+}
+
+extern "C++" {
+namespace {
+struct DevTmp {  // small RAII bundle of device scratch for the M-step
+  std::vector<void *> ptrs;
+  ~DevTmp() { for (void *p : ptrs) cudaFree(p); }
+  template <class T> khg_status alloc(T **out, size_t n) {
+    void *p = nullptr;
+    KHG_CUDA_TRY(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    ptrs.push_back(p);
+    *out = static_cast<T *>(p);
+    return KHG_OK;
+  }
+};
+}  // namespace
+}  // extern "C++"
+
+khg_status khg_mle_update(khg_model *m, const khg_stats *s, const khg_mle_options *opts, uint16_t update_flags,
+                          khg_model **new_model, float *obj_change, float *count, int32_t *floored_elements,
+                          int32_t *floored_gaussians, int32_t *removed_gaussians) {
+  KHG_REQUIRE(m && s && s->model == m && m->uploaded && opts && new_model, "bad argument");
+  update_flags &= (KHG_GMM_MEANS | KHG_GMM_VARIANCES | KHG_GMM_WEIGHTS);
+  if (update_flags & ~s->flags) {
+    set_error("Flags in argument do not match the active accumulators");  // csrc/mle-diag-gmm.cc:253-255
+    return KHG_ERR_INVALID;
+  }
+  const int P = m->P, D = m->dim, G = m->G;
+  cudaStream_t st = m->stream;
+  DevTmp tmp;
+  float *w_new, *miv_new, *iv_new, *gc_old, *gc_new, *obj_old, *obj_new;
+  int32_t *remove, *counters, *flags2;
+  double *pdf_occ;
+  KHG_TRY(tmp.alloc(&w_new, G));
+  KHG_TRY(tmp.alloc(&miv_new, (size_t)G * D));
+  KHG_TRY(tmp.alloc(&iv_new, (size_t)G * D));
+  KHG_TRY(tmp.alloc(&gc_old, G));
+  KHG_TRY(tmp.alloc(&gc_new, G));
+  KHG_TRY(tmp.alloc(&obj_old, P));
+  KHG_TRY(tmp.alloc(&obj_new, P));
+  KHG_TRY(tmp.alloc(&remove, G));
+  KHG_TRY(tmp.alloc(&counters, 4));
+  KHG_TRY(tmp.alloc(&flags2, 4));
+  KHG_TRY(tmp.alloc(&pdf_occ, P));
+  KHG_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(int32_t) * 4, st));
+  KHG_CUDA_TRY(cudaMemsetAsync(flags2, 0, sizeof(int32_t) * 4, st));
+  const double *occ = s->buf;
+  const double *mean = s->off_mean >= 0 ? s->buf + s->off_mean : nullptr;
+  const double *var = s->off_var >= 0 ? s->buf + s->off_var : nullptr;
+  // gmm->ComputeGconsts(); obj_old = MlObjective(*gmm, acc)   (csrc/mle-diag-gmm.cc:266-267)
+  gconsts_kernel<<<grid_for(G, 128), 128, 0, st>>>(G, D, m->d_weights, m->d_miv, m->d_iv, gc_old, flags2);
+  mle_objective_kernel<<<P, 128, 0, st>>>(P, D, s->flags, m->d_offsets, occ, mean, var, gc_old, m->d_miv, m->d_iv, obj_old);
+  MleArgs a;
+  a.P = P; a.D = D; a.acc_flags = s->flags; a.upd_flags = update_flags;
+  a.min_w = opts->min_gaussian_weight; a.min_occ = opts->min_gaussian_occupancy; a.min_var = opts->min_variance;
+  a.remove_low = opts->remove_low_count_gaussians;
+  a.offsets = m->d_offsets; a.occ = occ; a.mean = mean; a.var = var;
+  a.w_old = m->d_weights; a.miv_old = m->d_miv; a.iv_old = m->d_iv;
+  a.w_new = w_new; a.miv_new = miv_new; a.iv_new = iv_new;
+  a.remove = remove; a.counters = counters; a.pdf_occ = pdf_occ;
+  mle_update_kernel<<<P, 128, 0, st>>>(a);
+  // gmm->ComputeGconsts(); obj_new = MlObjective(*gmm, acc)    (:365-366), before any removal
+  gconsts_kernel<<<grid_for(G, 128), 128, 0, st>>>(G, D, w_new, miv_new, iv_new, gc_new, flags2 + 2);
+  mle_objective_kernel<<<P, 128, 0, st>>>(P, D, s->flags, m->d_offsets, occ, mean, var, gc_new, miv_new, iv_new, obj_new);
+  g_launch_count += 5;
+  KHG_CUDA_TRY(cudaGetLastError());
+  std::vector<float> h_old(P), h_new(P);
+  std::vector<double> h_occ(P);
+  std::vector<int32_t> h_remove(G);
+  int32_t h_cnt[4], h_fl[4];
+  KHG_CUDA_TRY(cudaMemcpyAsync(h_old.data(), obj_old, sizeof(float) * P, cudaMemcpyDeviceToHost, st));
+  KHG_CUDA_TRY(cudaMemcpyAsync(h_new.data(), obj_new, sizeof(float) * P, cudaMemcpyDeviceToHost, st));
+  KHG_CUDA_TRY(cudaMemcpyAsync(h_occ.data(), pdf_occ, sizeof(double) * P, cudaMemcpyDeviceToHost, st));
+  KHG_CUDA_TRY(cudaMemcpyAsync(h_remove.data(), remove, sizeof(int32_t) * G, cudaMemcpyDeviceToHost, st));
+  KHG_CUDA_TRY(cudaMemcpyAsync(h_cnt, counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+  KHG_CUDA_TRY(cudaMemcpyAsync(h_fl, flags2, sizeof(h_fl), cudaMemcpyDeviceToHost, st));
+  KHG_CUDA_TRY(cudaStreamSynchronize(st));
+  if (h_fl[1] || h_fl[3]) {
+    set_error("not a number in gconst computation");
+    return KHG_ERR_NONFINITE;
+  }
+  // per-pdf float results summed in pdf order like MleAmDiagGmmUpdate (csrc/mle-am-diag-gmm.cc:177-190)
+  float tot_obj = 0.f, tot_count = 0.f;
+  for (int p = 0; p < P; ++p) {
+    tot_obj += h_new[p] - h_old[p];
+    tot_count += (float)h_occ[p];
+  }
+  if (obj_change) *obj_change = tot_obj;
+  if (count) *count = tot_count;
+  if (floored_elements) *floored_elements = h_cnt[0];
+  if (floored_gaussians) *floored_gaussians = h_cnt[1];
+  if (removed_gaussians) *removed_gaussians = h_cnt[2];
+  // new structure
+  std::vector<int32_t> new_off(P + 1, 0);
+  for (int p = 0; p < P; ++p) {
+    int kept = 0;
+    for (int g = m->h_offsets[p]; g < m->h_offsets[p + 1]; ++g) kept += h_remove[g] ? 0 : 1;
+    new_off[p + 1] = new_off[p] + kept;
+  }
+  khg_model *nm = nullptr;
+  KHG_TRY(khg_model_create(D, P, new_off.data(), &nm));
+  nm->stream = st;
+  nm->kernel = m->kernel;
+  int32_t *d_new_off = nm->d_offsets;
+  size_t shm = sizeof(float) * 2 * (size_t)m->max_gp;
+  mle_compact_kernel<<<P, 128, shm, st>>>(P, D, m->d_offsets, d_new_off, remove, w_new, miv_new, iv_new,
+                                          nm->d_weights, nm->d_miv, nm->d_iv);
+  ++g_launch_count;
+  // finish the new handle exactly like khg_model_upload(gconsts = NULL) does, from device data
+  KHG_CUDA_TRY(cudaMemsetAsync(nm->d_scratch_int, 0, sizeof(int) * 4, st));
+  gconsts_kernel<<<grid_for(nm->G, 128), 128, 0, st>>>(nm->G, D, nm->d_weights, nm->d_miv, nm->d_iv, nm->d_gconsts, nm->d_scratch_int);
+  pack_simt_kernel<<<std::min(1024u, grid_for((int64_t)nm->n_chunks * 2 * D * kSimtChunk, 256)), 256, 0, st>>>(
+      nm->G, D, nm->n_chunks, nm->d_miv, nm->d_iv, nm->d_packT);
+  pack8_kernel<<<P, 128, 0, st>>>(P, D, nm->d_offsets, nm->d_grp_start, nm->d_miv, nm->d_iv, nm->d_gconsts, nm->d_pack8, nm->d_gc8);
+  g_launch_count += 3;
+  KHG_CUDA_TRY(cudaGetLastError());
+  nm->uploaded = true;
+  if (nm->kernel != KHG_KERNEL_SIMT && tc_supported(nm)) {
+    khg_status ts = tc_pack_build(nm);
+    if (ts != KHG_OK && nm->kernel == KHG_KERNEL_TCGEN05) {
+      khg_model_destroy(nm);
+      return ts;
+    }
+  }
+  KHG_CUDA_TRY(cudaStreamSynchronize(st));
+  *new_model = nm;
+  return KHG_OK;
+}
+
 // ------------------------------------------------------------------ E-step --
 static khg_status estep_init_streams(khg_model *m) {
   if (m->copy_stream) return KHG_OK;

@@ -645,6 +645,192 @@ __global__ void acc_from_post_kernel(const float *__restrict__ feats, int64_t T,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Device M-step: MleDiagGmmUpdate (csrc/mle-diag-gmm.cc:243-390) for every pdf.
+// One CTA per pdf.  Pass 1 (mle_update_kernel): old objective, new parameters in the
+// packed layout (same Gaussian slots), removal flags, counters.  gconsts of the updated
+// (pre-removal) model come from gconsts_kernel; pass 2 (mle_objective_kernel) evaluates
+// MlObjective (csrc/mle-diag-gmm.cc:479-499) per pdf; mle_compact_kernel gathers the
+// kept Gaussians into the new model and renormalises weights like RemoveComponents
+// (csrc/diag-gmm.cc:853-937: one removal at a time, fp32).
+// ---------------------------------------------------------------------------
+struct MleArgs {
+  int P, D;
+  uint16_t acc_flags, upd_flags;
+  float min_w, min_occ;
+  double min_var;
+  int remove_low;
+  const int32_t *offsets;
+  const double *occ, *mean, *var;       // packed stats (mean/var may be NULL)
+  const float *w_old, *miv_old, *iv_old;
+  float *w_new, *miv_new, *iv_new;       // same slots as the old model
+  int32_t *remove;                       // G flags
+  int32_t *counters;                     // [0] floored elements, [1] floored gaussians, [2] removed
+  double *pdf_occ;                       // P: sum of occupancies (count)
+};
+
+__device__ __forceinline__ double block_sum_128(double v, double *red) {
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return red[0] + red[1] + red[2] + red[3];
+}
+
+__global__ void __launch_bounds__(128) mle_update_kernel(MleArgs a) {
+  __shared__ double red[4];
+  __shared__ int s_cand;
+  const int p = blockIdx.x, tid = threadIdx.x, D = a.D;
+  const int g0 = a.offsets[p], ng = a.offsets[p + 1] - g0;
+  double part = 0.0;
+  for (int g = tid; g < ng; g += 128) part += a.occ[g0 + g];
+  const double occ_sum = block_sum_128(part, red);
+  if (tid == 0) {
+    a.pdf_occ[p] = occ_sum;
+    s_cand = 0;
+  }
+  __syncthreads();
+  // candidates for removal are counted first: when every Gaussian of the pdf is a
+  // candidate the last one is kept (to_remove.size() < num_gauss - 1, :338-339)
+  int my_cand = 0;
+  for (int g = tid; g < ng; g += 128) {
+    const double occ = a.occ[g0 + g];
+    const double prob = occ_sum > 0.0 ? occ / occ_sum : 1.0 / ng;
+    if (!(occ > (double)a.min_occ && prob > (double)a.min_w)) ++my_cand;
+  }
+  if (my_cand) atomicAdd(&s_cand, my_cand);
+  __syncthreads();
+  const int n_cand = s_cand;
+  int last_cand = -1;
+  if (n_cand == ng) last_cand = ng - 1;  // all are candidates: the highest index survives
+  for (int g = tid; g < ng; g += 128) {
+    const size_t G = g0 + g;
+    const double occ = a.occ[G];
+    const double prob = occ_sum > 0.0 ? occ / occ_sum : 1.0 / ng;
+    const float *miv_o = a.miv_old + G * D, *iv_o = a.iv_old + G * D;
+    float *miv_n = a.miv_new + G * D, *iv_n = a.iv_new + G * D;
+    float w = a.w_old[G];
+    int rm = 0;
+    if (occ > (double)a.min_occ && prob > (double)a.min_w) {
+      if (a.upd_flags & KHG_GMM_WEIGHTS) w = (float)prob;
+      int floored = 0;
+      for (int d = 0; d < D; ++d) {
+        // DiagGmmNormal (csrc/diag-gmm-normal.cc:14-20): double mean / variance form
+        const double old_var = 1.0 / (double)iv_o[d];
+        const double old_mean = (double)miv_o[d] * old_var;
+        double mean = old_mean, var = old_var;
+        if (a.acc_flags & (KHG_GMM_MEANS | KHG_GMM_VARIANCES)) mean = a.mean[G * D + d] / occ;
+        if (a.acc_flags & KHG_GMM_VARIANCES) {
+          var = a.var[G * D + d] / occ - mean * mean;
+          if (!(a.upd_flags & KHG_GMM_MEANS)) {  // :300-304
+            const double dm = old_mean - mean;
+            var += dm * dm;
+          }
+          if (var < a.min_var) {
+            var = a.min_var;
+            ++floored;
+          }
+        }
+        // CopyToDiagGmm (csrc/diag-gmm-normal.cc:22-48)
+        float ivf = iv_o[d], mivf = miv_o[d];
+        if (a.upd_flags & KHG_GMM_VARIANCES) {
+          ivf = (float)(1.0 / var);
+          if (!(a.upd_flags & KHG_GMM_MEANS)) mivf = (float)old_mean * ivf;
+        }
+        if (a.upd_flags & KHG_GMM_MEANS) mivf = (float)mean * ivf;
+        iv_n[d] = ivf;
+        miv_n[d] = mivf;
+      }
+      if (floored) {
+        atomicAdd(&a.counters[0], floored);
+        atomicAdd(&a.counters[1], 1);
+      }
+    } else {
+      for (int d = 0; d < D; ++d) {
+        iv_n[d] = iv_o[d];
+        miv_n[d] = miv_o[d];
+      }
+      if (a.remove_low && g != last_cand && ng > 1) {
+        rm = 1;
+        atomicAdd(&a.counters[2], 1);
+      } else if (a.upd_flags & KHG_GMM_WEIGHTS) {
+        w = (float)fmax(prob, (double)a.min_w);  // :353-354
+      }
+    }
+    a.w_new[G] = w;
+    a.remove[G] = rm;
+  }
+}
+
+// obj[p] = MlObjective of pdf p (csrc/mle-diag-gmm.cc:479-499), reference float roundings.
+__global__ void __launch_bounds__(128)
+mle_objective_kernel(int P, int D, uint16_t acc_flags, const int32_t *__restrict__ offsets,
+                     const double *__restrict__ occ, const double *__restrict__ mean, const double *__restrict__ var,
+                     const float *__restrict__ gc, const float *__restrict__ miv, const float *__restrict__ iv,
+                     float *__restrict__ obj) {
+  __shared__ double red[4];
+  const int p = blockIdx.x, tid = threadIdx.x;
+  const int g0 = offsets[p], ng = offsets[p + 1] - g0;
+  double o = 0.0, sm = 0.0, sv = 0.0;
+  for (int g = tid; g < ng; g += 128) {
+    o += occ[g0 + g] * (double)gc[g0 + g];
+  }
+  const size_t e0 = (size_t)g0 * D, ne = (size_t)ng * D;
+  if (acc_flags & KHG_GMM_MEANS)
+    for (size_t e = tid; e < ne; e += 128) sm += mean[e0 + e] * (double)miv[e0 + e];
+  if (acc_flags & KHG_GMM_VARIANCES)
+    for (size_t e = tid; e < ne; e += 128) sv += var[e0 + e] * (double)iv[e0 + e];
+  o = block_sum_128(o, red);
+  sm = block_sum_128(sm, red);
+  sv = block_sum_128(sv, red);
+  if (tid == 0) {
+    float f = (float)o;
+    if (acc_flags & KHG_GMM_MEANS) f = (float)((double)f + sm);
+    if (acc_flags & KHG_GMM_VARIANCES) f = (float)((double)f - 0.5 * sv);
+    obj[p] = f;
+  }
+}
+
+// Gathers the kept Gaussians of pdf p into the new model; weights are renormalised the
+// way RemoveComponents does it: after each single removal, in fp32, in index order.
+__global__ void __launch_bounds__(128)
+mle_compact_kernel(int P, int D, const int32_t *__restrict__ old_off, const int32_t *__restrict__ new_off,
+                   const int32_t *__restrict__ remove, const float *__restrict__ w, const float *__restrict__ miv,
+                   const float *__restrict__ iv, float *__restrict__ w_out, float *__restrict__ miv_out,
+                   float *__restrict__ iv_out) {
+  extern __shared__ float ws[];  // ng weights + ng flags (as float)
+  const int p = blockIdx.x, tid = threadIdx.x;
+  const int g0 = old_off[p], ng = old_off[p + 1] - g0, n0 = new_off[p];
+  int *dst = reinterpret_cast<int *>(ws + ng);
+  for (int g = tid; g < ng; g += 128) ws[g] = w[g0 + g];
+  __syncthreads();
+  if (tid == 0) {
+    int k = 0, removed = 0;
+    for (int g = 0; g < ng; ++g) dst[g] = remove[g0 + g] ? -1 : k++;
+    // sequential renormalisation: one pass per removed component over the survivors
+    // that are still present at that point (components removed later are still in)
+    for (int g = 0; g < ng; ++g) {
+      if (!remove[g0 + g]) continue;
+      float s = 0.f;
+      for (int h = 0; h < ng; ++h)
+        if (h != g && !(remove[g0 + h] && h < g)) s += ws[h];
+      for (int h = 0; h < ng; ++h)
+        if (h != g && !(remove[g0 + h] && h < g)) ws[h] /= s;
+      ++removed;
+    }
+  }
+  __syncthreads();
+  for (int g = tid; g < ng; g += 128)
+    if (dst[g] >= 0) w_out[n0 + dst[g]] = ws[g];
+  for (int e = tid; e < ng * D; e += 128) {
+    const int g = e / D, d = e - g * D;
+    if (dst[g] >= 0) {
+      miv_out[(size_t)(n0 + dst[g]) * D + d] = miv[(size_t)(g0 + g) * D + d];
+      iv_out[(size_t)(n0 + dst[g]) * D + d] = iv[(size_t)(g0 + g) * D + d];
+    }
+  }
+}
+
 __global__ void axpy_f64_kernel(double *dst, const double *src, double scale, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)

@@ -54,6 +54,8 @@ SYMBOLS = [
     ("khg_acc_stats_ali_tids", _i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp, C.POINTER(C.c_double)]),
     ("khg_acc_from_posteriors", _i32, [_vp, _vp, _i32, _vp, _i64, _i32, _vp]),
     ("khg_estep", _i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _i64, C.POINTER(C.c_double)]),
+    ("khg_mle_update", _i32, [_vp, _vp, _vp, _u16, C.POINTER(_vp), C.POINTER(_f32), C.POINTER(_f32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    ("khg_model_download", _i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     ("khg_launch_count", _i64, []),
 ]
 

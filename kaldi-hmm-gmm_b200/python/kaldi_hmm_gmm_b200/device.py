@@ -52,6 +52,26 @@ class DeviceModel:
         A.check(A.lib().khg_model_get_gconsts(self._h, out.ctypes.data))
         return out
 
+    @classmethod
+    def _from_handle(cls, handle) -> "DeviceModel":
+        self = cls.__new__(cls)
+        self._h = handle
+        d, p, g = C.c_int32(), C.c_int32(), C.c_int32()
+        A.check(A.lib().khg_model_info(handle, C.byref(d), C.byref(p), C.byref(g)))
+        self.dim, self.num_pdfs, self.num_gauss = d.value, p.value, g.value
+        self.offsets = np.empty(self.num_pdfs + 1, np.int32)
+        A.check(A.lib().khg_model_download(handle, self.offsets.ctypes.data, None, None, None, None))
+        return self
+
+    def download(self):
+        """Host copies of the packed parameters: dict(offsets, weights, means_invvars, inv_vars, gconsts)."""
+        G, D = self.num_gauss, self.dim
+        w, gc = np.empty(G, np.float32), np.empty(G, np.float32)
+        miv, iv = np.empty((G, D), np.float32), np.empty((G, D), np.float32)
+        offs = np.empty(self.num_pdfs + 1, np.int32)
+        A.check(A.lib().khg_model_download(self._h, offs.ctypes.data, w.ctypes.data, miv.ctypes.data, iv.ctypes.data, gc.ctypes.data))
+        return dict(offsets=offs, weights=w, means_invvars=miv, inv_vars=iv, gconsts=gc)
+
     def set_kernel(self, kernel: int):
         A.check(A.lib().khg_model_set_kernel(self._h, kernel))
 
@@ -162,6 +182,23 @@ class DeviceStats:
 
     def scale(self, scale: float):
         A.check(A.lib().khg_stats_scale(self._h, scale))
+
+    def mle_update(self, update_flags: int = 0xF, min_gaussian_weight: float = 1e-5, min_gaussian_occupancy: float = 10.0,
+                   min_variance: float = 0.001, remove_low_count_gaussians: bool = True):
+        """Device M-step (MleAmDiagGmmUpdate, reference csrc/mle-am-diag-gmm.cc:153-202).
+        Returns (new DeviceModel, dict(obj_change, count, floored_elements, floored_gaussians, removed_gaussians))."""
+
+        class _Opts(C.Structure):
+            _fields_ = [("w", C.c_float), ("occ", C.c_float), ("var", C.c_double), ("rm", C.c_int32)]
+
+        o = _Opts(min_gaussian_weight, min_gaussian_occupancy, min_variance, int(remove_low_count_gaussians))
+        nh = C.c_void_p()
+        oc, cnt = C.c_float(), C.c_float()
+        fe, fg, rg = C.c_int32(), C.c_int32(), C.c_int32()
+        A.check(A.lib().khg_mle_update(self.model._h, self._h, C.byref(o), update_flags, C.byref(nh), C.byref(oc), C.byref(cnt),
+                                       C.byref(fe), C.byref(fg), C.byref(rg)))
+        return DeviceModel._from_handle(nh), dict(obj_change=oc.value, count=cnt.value, floored_elements=fe.value,
+                                                  floored_gaussians=fg.value, removed_gaussians=rg.value)
 
     # -- accumulation -----------------------------------------------------
     def acc_stats_ali(self, feats, pdf_ids, frame_weights=None, per_frame=None, want_total: bool = True) -> Optional[float]:
