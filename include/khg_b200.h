@@ -67,8 +67,13 @@ enum {
 /* Which kernel computes the dense all-pdf log-likelihoods. */
 enum {
   KHG_KERNEL_AUTO = 0,
-  KHG_KERNEL_SIMT = 1,   /* fp32 FMA kernel (any dim, any pdf size) */
-  KHG_KERNEL_TCGEN05 = 2 /* tcgen05 3xTF32 kernel, TMA-staged model tiles */
+  KHG_KERNEL_SIMT = 1,       /* fp32 FMA kernel (any dim, any pdf size) */
+  KHG_KERNEL_TCGEN05 = 2,    /* tcgen05 kernel, 3xTF32 split (hi/lo tf32 operands) */
+  KHG_KERNEL_TCGEN05_F16 = 3 /* tcgen05 kernel, 3xFP16 split: same 22-bit split precision at
+                                twice the tensor rate; needs model and features in fp16 range
+                                after a per-dimension power-of-two scaling.  AUTO uses it when
+                                the model fits and, decided on the device for every call, the
+                                features fit; otherwise the 3xTF32 split runs. */
 };
 
 typedef struct khg_model khg_model; /* device-resident packed AmDiagGmm      */

@@ -196,7 +196,7 @@ khg_status khg_model_upload(khg_model *m, const float *weights, const float *mea
   m->tc.ready = false;
   if (m->kernel != KHG_KERNEL_SIMT && tc_supported(m)) {
     khg_status s = tc_pack_build(m);
-    if (s != KHG_OK && m->kernel == KHG_KERNEL_TCGEN05) return s;
+    if (s != KHG_OK && (m->kernel == KHG_KERNEL_TCGEN05 || m->kernel == KHG_KERNEL_TCGEN05_F16)) return s;
   }
   KHG_CUDA_TRY(cudaStreamSynchronize(st));
   return KHG_OK;
@@ -218,8 +218,8 @@ khg_status khg_model_info(const khg_model *m, int32_t *dim, int32_t *num_pdfs, i
 }
 
 khg_status khg_model_set_kernel(khg_model *m, int32_t kernel) {
-  KHG_REQUIRE(m && kernel >= KHG_KERNEL_AUTO && kernel <= KHG_KERNEL_TCGEN05, "bad kernel id");
-  if (kernel == KHG_KERNEL_TCGEN05 && !tc_supported(m)) {
+  KHG_REQUIRE(m && kernel >= KHG_KERNEL_AUTO && kernel <= KHG_KERNEL_TCGEN05_F16, "bad kernel id");
+  if ((kernel == KHG_KERNEL_TCGEN05 || kernel == KHG_KERNEL_TCGEN05_F16) && !tc_supported(m)) {
     set_error("tcgen05 kernel does not support this model shape (needs 2*dim+1 <= 96 and every pdf <= 240 Gaussians)");
     return KHG_ERR_UNSUPPORTED;
   }
@@ -278,16 +278,17 @@ khg_status khg_compute_gconsts(int32_t nmix, int32_t dim, const float *weights,
 static khg_status dense_device(khg_model *m, const float *d_feats, int64_t T, float scale,
                                int layout, float *d_out, int64_t ld) {
   const bool use_tc = m->kernel != KHG_KERNEL_SIMT && m->tc.ready;
-  if (m->kernel == KHG_KERNEL_TCGEN05 && !m->tc.ready) {
+  const int prec = m->kernel == KHG_KERNEL_TCGEN05 ? 1 : (m->kernel == KHG_KERNEL_TCGEN05_F16 ? 2 : 0);
+  if ((m->kernel == KHG_KERNEL_TCGEN05 || m->kernel == KHG_KERNEL_TCGEN05_F16) && !m->tc.ready) {
     set_error("tcgen05 kernel requested but its model pack is not built");
     return KHG_ERR_UNSUPPORTED;
   }
   if (use_tc) {
-    if (layout == KHG_PDF_MAJOR) return tc_loglikes(m, d_feats, T, scale, d_out, ld);
+    if (layout == KHG_PDF_MAJOR) return tc_loglikes(m, d_feats, T, scale, d_out, ld, prec);
     // frame-major: compute pdf-major into scratch, then transpose
     int64_t ldt = (T + 3) & ~(int64_t)3;
     KHG_TRY(m->w_out.reserve(sizeof(float) * (size_t)m->P * ldt));
-    KHG_TRY(tc_loglikes(m, d_feats, T, scale, m->w_out.as<float>(), ldt));
+    KHG_TRY(tc_loglikes(m, d_feats, T, scale, m->w_out.as<float>(), ldt, prec));
     dim3 grid(grid_for(T, 32), grid_for(m->P, 32)), block(32, 8);
     transpose_kernel<<<grid, block, 0, m->stream>>>(m->w_out.as<float>(), m->P, T, ldt, d_out, ld);
     ++g_launch_count;
@@ -809,7 +810,7 @@ khg_status khg_mle_update(khg_model *m, const khg_stats *s, const khg_mle_option
   nm->uploaded = true;
   if (nm->kernel != KHG_KERNEL_SIMT && tc_supported(nm)) {
     khg_status ts = tc_pack_build(nm);
-    if (ts != KHG_OK && nm->kernel == KHG_KERNEL_TCGEN05) {
+    if (ts != KHG_OK && (nm->kernel == KHG_KERNEL_TCGEN05 || nm->kernel == KHG_KERNEL_TCGEN05_F16)) {
       khg_model_destroy(nm);
       return ts;
     }

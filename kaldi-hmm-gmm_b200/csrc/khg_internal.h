@@ -72,6 +72,13 @@ struct TcPack {
   float *bhi = nullptr;  // rows x KP
   float *blo = nullptr;  // rows x KP
   CUtensorMap map_hi, map_lo;
+  // fp16-split variant of the same operand (kind::f16 runs at twice the tf32 rate)
+  bool f16_ready = false;
+  int K16 = 0, KP16 = 0;        // K rounded up to 16 / to 64
+  void *hhi = nullptr, *hlo = nullptr;  // rows x KP16 __half
+  float *ascale = nullptr;      // device, 2D floats: power-of-two scale of the [x | x^2] columns
+  unsigned *gate = nullptr;     // device word: max |x*ascale| bits of the current call (auto mode)
+  CUtensorMap hmap_hi, hmap_lo;
   // N-tiles aligned to pdf boundaries: tile j covers Gaussians
   // [tile_g0[j], tile_g0[j]+kTileN) and owns pdfs [tile_p0[j], tile_p0[j+1]).
   int n_tiles = 0;
@@ -129,7 +136,7 @@ void tc_pack_free(khg_model *m);
 bool tc_supported(const khg_model *m);
 // out is pdf-major: out[p*ld + t]
 khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale,
-                       float *d_out, int64_t ld_out);
+                       float *d_out, int64_t ld_out, int precision);
 }  // namespace khg
 
 #endif  // KHG_INTERNAL_H_

@@ -32,6 +32,7 @@
 // N tiles are aligned to pdf boundaries (tile table built on the host), so a pdf's
 // Gaussians never straddle two accumulator tiles.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -46,13 +47,20 @@ namespace khg {
 
 constexpr int kTileM = 128;         // frames per CTA tile (UMMA M)
 constexpr int kTileN = 240;         // Gaussians per accumulator tile (UMMA N)
-constexpr int kChunkK = 32;         // floats per 128-byte swizzle atom
-constexpr int kUmmaK = 8;           // tf32
+// Operand element: tf32 (4 B, 32 per 128-byte swizzle atom, UMMA_K = 8) or fp16 (2 B, 64
+// per atom, UMMA_K = 16).  Either way one UMMA K-step is 32 bytes of each operand row.
+template <bool F16> struct Elem {
+  static constexpr int kBytes = F16 ? 2 : 4;
+  static constexpr int kChunkK = 128 / kBytes;  // elements per 128-byte swizzle atom
+  static constexpr int kUmmaK = 32 / kBytes;
+};
 constexpr int kAChunkBytes = kTileM * 128;   // 16384
 constexpr int kBStageBytes = kTileN * 128;   // 30720 (multiple of 1024)
-constexpr int kMaxChunks = 5;       // K <= 160
+constexpr int kMaxChunks = 5;       // 128-byte K chunks per operand row held in smem
 constexpr int kEpiGroups = 4;       // epilogue warpgroups (4 warps each, one per TMEM lane quadrant)
 constexpr int kTcThreads = 256 + 128 * kEpiGroups;
+// fp16 path: |x * 2^-k| beyond this keeps x^2 (and x) from fitting fp16 with margin
+constexpr float kF16FeatLimit = 128.0f;
 constexpr float kNegSentinel = -1.0e30f;  // stands in for gconst = -inf (0 * inf = NaN in the split)
 
 // ---------------------------------------------------------------- PTX wrappers --
@@ -91,13 +99,23 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
+template <bool F16>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (F16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  }
 }
 // TMEM -> registers: 32 lanes x 16 consecutive fp32 columns; thread i of the warp gets
 // lane (warp%4)*32+i.  Issue and wait are separate so that the next segment's load is in
@@ -210,8 +228,33 @@ __device__ __forceinline__ float seg_lse_any(const TReg16 &t, uint32_t taddr, in
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// Instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=240.
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+// Instruction descriptor: D=f32, A=B=tf32 (format 2) or f16 (format 0), both K-major, M=128, N=240.
+template <bool F16>
+__host__ __device__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+         ((uint32_t)(kTileM >> 4) << 24);
+}
+
+// Writes the hi/lo split of v at (row, col) of the A operand (UMMA K-major, 128B swizzle):
+// hi = round-to-nearest in the operand format, lo = v - hi (exact in fp32), also stored in
+// the operand format.
+template <bool F16>
+__device__ __forceinline__ void a_store_split(uint8_t *a_hi, uint32_t lo_offset, int row, int col, float v);
+template <>
+__device__ __forceinline__ void a_store_split<false>(uint8_t *a_hi, uint32_t lo_offset, int row, int col, float v) {
+  const float hi = tf32_rna(v), lo = v - hi;
+  const uint32_t off = (col >> 5) * kAChunkBytes + row * 128 + ((((col & 31) >> 2) ^ (row & 7)) << 4) + ((col & 3) << 2);
+  *reinterpret_cast<float *>(a_hi + off) = hi;
+  *reinterpret_cast<float *>(a_hi + lo_offset + off) = lo;
+}
+template <>
+__device__ __forceinline__ void a_store_split<true>(uint8_t *a_hi, uint32_t lo_offset, int row, int col, float v) {
+  const __half hi = __float2half_rn(v);
+  const __half lo = __float2half_rn(v - __half2float(hi));
+  const uint32_t off = (col >> 6) * kAChunkBytes + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4) + ((col & 7) << 1);
+  *reinterpret_cast<__half *>(a_hi + off) = hi;
+  *reinterpret_cast<__half *>(a_hi + lo_offset + off) = lo;
+}
 
 // ------------------------------------------------------------------ B pack (K4) --
 __global__ void tc_pack_kernel(int G, int D, int KP, int rows, const float *__restrict__ miv,
@@ -238,11 +281,53 @@ __global__ void tc_pack_kernel(int G, int D, int KP, int rows, const float *__re
   }
 }
 
+// fp16 variant: B scaled per dimension by powers of two (bscale[k], exact), split into fp16
+// hi and lo.  flags[0] is set when a value does not fit fp16 comfortably or a gconst is
+// -inf: the model then stays on the tf32 path.
+__global__ void tc_pack_f16_kernel(int G, int D, int KP, int rows, const float *__restrict__ miv,
+                                   const float *__restrict__ iv, const float *__restrict__ gconsts,
+                                   const float *__restrict__ bscale, __half *__restrict__ bhi,
+                                   __half *__restrict__ blo, int *__restrict__ flags) {
+  size_t total = (size_t)rows * KP;
+  bool bad = false;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int k = (int)(i % KP);
+    int g = (int)(i / KP);
+    float v = 0.f;
+    if (g < G) {
+      if (k < D) v = miv[(size_t)g * D + k] * bscale[k];
+      else if (k < 2 * D) v = -0.5f * iv[(size_t)g * D + (k - D)] * bscale[k];
+      else if (k == 2 * D) v = gconsts[g];
+    }
+    if (!(fabsf(v) <= 3.0e4f)) bad = true;  // also catches -inf gconsts and NaN
+    const __half hi = __float2half_rn(v);
+    bhi[i] = hi;
+    blo[i] = __float2half_rn(v - __half2float(hi));
+  }
+  if (bad) atomicOr(flags, 1);
+}
+
+// max over the batch of |x_d| * ascale[d] (NaN counts as huge), as float bits.
+__global__ void feat_absmax_kernel(const float *__restrict__ feats, int64_t n, int D,
+                                   const float *__restrict__ ascale, unsigned *__restrict__ out) {
+  unsigned m = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = fabsf(feats[i]) * ascale[(int)(i % D)];
+    m = max(m, __float_as_uint(v));  // non-negative floats and NaNs order like their bit patterns
+  }
+  for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
 // ------------------------------------------------------------------ the kernel --
 struct TcArgs {
   const float *feats;      // T x D
   int64_t T;
-  int D, K8, n_chunks;     // K8 = roundup(2D+1, 8); n_chunks = roundup(2D+1, 32)/32
+  int D, K8, n_chunks;     // K8 = 2D+1 rounded up to UMMA_K; n_chunks = 128-byte chunks per operand row
+  const float *ascale;     // fp16 path: per-column power-of-two scale of [x | x^2] (2D floats); NULL = none
+  const unsigned *gate;    // NULL, or device word with max |x*ascale| bits: see gate_limit
+  float gate_limit;        // fp16 kernel runs iff *gate <= limit, tf32 kernel iff *gate > limit
+  int gate_run_if_above;
   int stages;              // B ring depth
   const int32_t *offsets;  // P+1
   const int32_t *tile_g0;  // n_tiles
@@ -256,8 +341,15 @@ struct TcArgs {
   int debug_mode;          // 0 = normal; 1 = epilogue skips the LSE (pipeline-ceiling experiment, KHG_TC_DEBUG_MODE)
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
 loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, TcArgs a) {
+  constexpr int kChunkK = Elem<F16>::kChunkK, kUmmaK = Elem<F16>::kUmmaK;
+  constexpr uint32_t kIdesc = make_idesc<F16>();
+  if (a.gate != nullptr) {  // precision-path gate decided on the device (no host round trip)
+    const bool above = !(__uint_as_float(*a.gate) <= a.gate_limit);
+    if (above != (a.gate_run_if_above != 0)) return;
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -299,9 +391,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     float4 *z = reinterpret_cast<float4 *>(base_ptr);
     for (int i = b; i < 2 * NCH * kAChunkBytes / 16; i += 128) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    const int col = 2 * a.D, row = b;
-    const uint32_t off = (col >> 5) * kAChunkBytes + row * 128 + ((((col & 31) >> 2) ^ (row & 7)) << 4) + ((col & 3) << 2);
-    *reinterpret_cast<float *>(base_ptr + off) = 1.0f;
+    a_store_split<F16>(base_ptr, NCH * kAChunkBytes, b, 2 * a.D, 1.0f);
   }
   tc_fence_before();
   __syncthreads();
@@ -353,10 +443,10 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
               tc_fence_after();
               const uint64_t db = umma_desc(sB + st * kBStageBytes);
               for (int k = 0; k < nk; ++k) {
-                tc_mma_tf32(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, accum);
+                tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, accum);
                 accum = 1;
               }
-              for (int k = 0; k < nk; ++k) tc_mma_tf32(tmem_d, da_lo + 2 * k, db + 2 * k, kIdesc, 1);
+              for (int k = 0; k < nk; ++k) tc_mma<F16>(tmem_d, da_lo + 2 * k, db + 2 * k, kIdesc, 1);
               tc_commit(b_empty(st));
               ++it;
             }
@@ -365,7 +455,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
               mbar_wait(b_full(st), (it / S) & 1);
               tc_fence_after();
               const uint64_t db = umma_desc(sB + st * kBStageBytes);
-              for (int k = 0; k < nk; ++k) tc_mma_tf32(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, 1);
+              for (int k = 0; k < nk; ++k) tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, 1);
               tc_commit(b_empty(st));
               ++it;
             }
@@ -388,19 +478,13 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       for (int e = b; e < kTileM * D; e += 128) {
         const float x = e < valid ? __ldg(src + e) : 0.f;
         const int row = e / D, d = e - row * D;
-        {
-          const float hi = tf32_rna(x), lo = x - hi;
-          const uint32_t off = (d >> 5) * kAChunkBytes + row * 128 + ((((d & 31) >> 2) ^ (row & 7)) << 4) + ((d & 3) << 2);
-          *reinterpret_cast<float *>(base_ptr + off) = hi;
-          *reinterpret_cast<float *>(base_ptr + NCH * kAChunkBytes + off) = lo;
-        }
-        {
-          const float q = x * x;  // data.array().square(), csrc/decodable-am-diag-gmm.cc:57
-          const float hi = tf32_rna(q), lo = q - hi;
-          const int col = D + d;
-          const uint32_t off = (col >> 5) * kAChunkBytes + row * 128 + ((((col & 31) >> 2) ^ (row & 7)) << 4) + ((col & 3) << 2);
-          *reinterpret_cast<float *>(base_ptr + off) = hi;
-          *reinterpret_cast<float *>(base_ptr + NCH * kAChunkBytes + off) = lo;
+        const float q = x * x;  // data.array().square(), csrc/decodable-am-diag-gmm.cc:57
+        if (F16) {  // exact power-of-two column scaling keeps both operands inside fp16's range
+          a_store_split<F16>(base_ptr, NCH * kAChunkBytes, row, d, x * __ldg(a.ascale + d));
+          a_store_split<F16>(base_ptr, NCH * kAChunkBytes, row, D + d, q * __ldg(a.ascale + D + d));
+        } else {
+          a_store_split<F16>(base_ptr, NCH * kAChunkBytes, row, d, x);
+          a_store_split<F16>(base_ptr, NCH * kAChunkBytes, row, D + d, q);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -497,16 +581,20 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 // ------------------------------------------------------------------ host side --
 bool tc_supported(const khg_model *m) {
   int K = 2 * m->dim + 1;
-  int nch = (K + kChunkK - 1) / kChunkK;
+  int nch = (K + Elem<false>::kChunkK - 1) / Elem<false>::kChunkK;
   return nch <= kMaxChunks && m->max_gp <= kTileN;
 }
 
 void tc_pack_free(khg_model *m) {
   TcPack &t = m->tc;
   cudaFree(t.bhi); cudaFree(t.blo); cudaFree(t.tile_g0); cudaFree(t.tile_p0);
+  cudaFree(t.hhi); cudaFree(t.hlo); cudaFree(t.ascale); cudaFree(t.gate);
   t.bhi = t.blo = nullptr;
+  t.hhi = t.hlo = nullptr;
+  t.ascale = nullptr;
+  t.gate = nullptr;
   t.tile_g0 = t.tile_p0 = nullptr;
-  t.ready = false;
+  t.ready = t.f16_ready = false;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -526,22 +614,81 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static khg_status make_map(CUtensorMap *map, float *ptr, int KP, int rows) {
+// 2-D tensor map over a rows x KP operand matrix: box = one 128-byte K chunk x 240 rows.
+static khg_status make_map(CUtensorMap *map, void *ptr, int KP, int rows, bool f16) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return KHG_ERR_CUDA;
   }
+  const int eb = f16 ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)KP, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)KP * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)kTileN};
+  cuuint64_t strides[1] = {(cuuint64_t)KP * eb};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / eb), (cuuint32_t)kTileN};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     return KHG_ERR_CUDA;
   }
+  return KHG_OK;
+}
+
+// fp16-split operand pack.  Column d of [x | x^2] is scaled by 2^-k_d / 2^-2k_d and the
+// matching model columns by the inverse (exact), with 2^k_d ~ the rms magnitude the model
+// implies for feature d, so that both operands sit comfortably inside fp16's range.
+static khg_status tc_pack_build_f16(khg_model *m) {
+  TcPack &t = m->tc;
+  const int D = m->dim, G = m->G;
+  t.K16 = (t.K + 15) / 16 * 16;
+  t.KP16 = (t.K + 63) / 64 * 64;
+  std::vector<float> miv((size_t)G * D), iv((size_t)G * D);
+  KHG_CUDA_TRY(cudaMemcpyAsync(miv.data(), m->d_miv, sizeof(float) * miv.size(), cudaMemcpyDeviceToHost, m->stream));
+  KHG_CUDA_TRY(cudaMemcpyAsync(iv.data(), m->d_iv, sizeof(float) * iv.size(), cudaMemcpyDeviceToHost, m->stream));
+  KHG_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  std::vector<double> m2(D, 0.0);
+  for (int g = 0; g < G; ++g)
+    for (int d = 0; d < D; ++d) {
+      const double var = 1.0 / (double)iv[(size_t)g * D + d], mean = (double)miv[(size_t)g * D + d] * var;
+      m2[d] += mean * mean + var;
+    }
+  std::vector<float> ascale(2 * D), bscale(2 * D);
+  for (int d = 0; d < D; ++d) {
+    double rms = std::sqrt(m2[d] / G);
+    int k = (rms > 0.0 && std::isfinite(rms)) ? (int)std::lround(std::log2(rms)) : 0;
+    k = std::max(-20, std::min(20, k));
+    ascale[d] = std::ldexp(1.0f, -k);
+    ascale[D + d] = std::ldexp(1.0f, -2 * k);
+    bscale[d] = std::ldexp(1.0f, k);
+    bscale[D + d] = std::ldexp(1.0f, 2 * k);
+  }
+  float *d_bscale = nullptr;
+  int *d_flag = nullptr;
+  KHG_CUDA_TRY(cudaMalloc(&t.ascale, sizeof(float) * 2 * D));
+  KHG_CUDA_TRY(cudaMalloc(&t.gate, sizeof(unsigned)));
+  KHG_CUDA_TRY(cudaMalloc(&d_bscale, sizeof(float) * 2 * D));
+  KHG_CUDA_TRY(cudaMalloc(&d_flag, sizeof(int)));
+  KHG_CUDA_TRY(cudaMemcpyAsync(t.ascale, ascale.data(), sizeof(float) * 2 * D, cudaMemcpyHostToDevice, m->stream));
+  KHG_CUDA_TRY(cudaMemcpyAsync(d_bscale, bscale.data(), sizeof(float) * 2 * D, cudaMemcpyHostToDevice, m->stream));
+  KHG_CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), m->stream));
+  KHG_CUDA_TRY(cudaMalloc(&t.hhi, sizeof(__half) * (size_t)t.rows * t.KP16));
+  KHG_CUDA_TRY(cudaMalloc(&t.hlo, sizeof(__half) * (size_t)t.rows * t.KP16));
+  size_t total = (size_t)t.rows * t.KP16;
+  tc_pack_f16_kernel<<<(unsigned)std::min<size_t>(2048, (total + 255) / 256), 256, 0, m->stream>>>(
+      G, D, t.KP16, t.rows, m->d_miv, m->d_iv, m->d_gconsts, d_bscale, static_cast<__half *>(t.hhi),
+      static_cast<__half *>(t.hlo), d_flag);
+  ++g_launch_count;
+  int flag = 0;
+  KHG_CUDA_TRY(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  KHG_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  cudaFree(d_bscale);
+  cudaFree(d_flag);
+  if (flag) return KHG_OK;  // model does not fit the fp16 split: stay on tf32 (f16_ready = false)
+  KHG_TRY(make_map(&t.hmap_hi, t.hhi, t.KP16, t.rows, true));
+  KHG_TRY(make_map(&t.hmap_lo, t.hlo, t.KP16, t.rows, true));
+  t.f16_ready = true;
   return KHG_OK;
 }
 
@@ -551,7 +698,7 @@ khg_status tc_pack_build(khg_model *m) {
   const int D = m->dim, G = m->G, P = m->P;
   t.K = 2 * D + 1;
   t.K8 = (t.K + 7) / 8 * 8;
-  t.KP = (t.K + kChunkK - 1) / kChunkK * kChunkK;
+  t.KP = (t.K + 31) / 32 * 32;
   t.rows = (G + kTileN + 15) / 16 * 16;
   // pdf-aligned N tiles (greedy)
   t.h_tile_g0.clear();
@@ -581,27 +728,30 @@ khg_status tc_pack_build(khg_model *m) {
   tc_pack_kernel<<<(unsigned)std::min<size_t>(2048, (total + 255) / 256), 256, 0, m->stream>>>(G, D, t.KP, t.rows, m->d_miv, m->d_iv, m->d_gconsts, t.bhi, t.blo);
   ++g_launch_count;
   KHG_CUDA_TRY(cudaGetLastError());
-  KHG_TRY(make_map(&t.map_hi, t.bhi, t.KP, t.rows));
-  KHG_TRY(make_map(&t.map_lo, t.blo, t.KP, t.rows));
+  KHG_TRY(make_map(&t.map_hi, t.bhi, t.KP, t.rows, false));
+  KHG_TRY(make_map(&t.map_lo, t.blo, t.KP, t.rows, false));
   KHG_CUDA_TRY(cudaStreamSynchronize(m->stream));
   t.ready = true;
+  KHG_TRY(tc_pack_build_f16(m));
   return KHG_OK;
 }
 
-khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t ld_out) {
+template <bool F16>
+static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t ld_out,
+                            const unsigned *gate, int gate_run_if_above) {
   TcPack &t = m->tc;
-  if (!t.ready) {
-    set_error("tcgen05 model pack not built");
-    return KHG_ERR_UNSUPPORTED;
-  }
   TcArgs a;
   a.feats = d_feats;
   a.T = T;
   a.D = m->dim;
-  a.K8 = t.K8;
-  a.n_chunks = t.KP / kChunkK;
+  a.K8 = F16 ? t.K16 : t.K8;
+  a.n_chunks = (F16 ? t.KP16 : t.KP) / Elem<F16>::kChunkK;
+  a.ascale = F16 ? t.ascale : nullptr;
+  a.gate = gate;
+  a.gate_limit = kF16FeatLimit;
+  a.gate_run_if_above = gate_run_if_above;
   const int a_bytes = 2 * a.n_chunks * kAChunkBytes;
-  a.stages = std::min(4, (int)((225 * 1024 - a_bytes) / kBStageBytes));
+  a.stages = std::min(F16 ? 6 : 4, (int)((225 * 1024 - a_bytes) / kBStageBytes));
   if (a.stages < 2) {
     set_error("feature dimension too large for the tcgen05 kernel");
     return KHG_ERR_UNSUPPORTED;
@@ -630,14 +780,43 @@ khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scal
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(loglikes_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(loglikes_tc_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   KHG_CUDA_TRY(attr_err);
   const unsigned grid = (unsigned)std::min<int64_t>(a.n_items, m->sm_count);
-  loglikes_tc_kernel<<<grid, kTcThreads, smem, m->stream>>>(t.map_hi, t.map_lo, a);
+  if (F16)
+    loglikes_tc_kernel<F16><<<grid, kTcThreads, smem, m->stream>>>(t.hmap_hi, t.hmap_lo, a);
+  else
+    loglikes_tc_kernel<F16><<<grid, kTcThreads, smem, m->stream>>>(t.map_hi, t.map_lo, a);
   ++g_launch_count;
   KHG_CUDA_TRY(cudaGetLastError());
   return KHG_OK;
+}
+
+// precision: 0 = automatic (fp16 split when the model fits and, decided on the device per
+// call, the features fit; tf32 split otherwise), 1 = force the tf32 split, 2 = force fp16.
+khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t ld_out,
+                       int precision) {
+  TcPack &t = m->tc;
+  if (!t.ready) {
+    set_error("tcgen05 model pack not built");
+    return KHG_ERR_UNSUPPORTED;
+  }
+  if (precision == 2 && !t.f16_ready) {
+    set_error("the fp16-split tensor-core path does not fit this model (parameter range or -inf gconsts)");
+    return KHG_ERR_UNSUPPORTED;
+  }
+  if (precision == 1 || !t.f16_ready) return tc_launch<false>(m, d_feats, T, scale, d_out, ld_out, nullptr, 0);
+  if (precision == 2) return tc_launch<true>(m, d_feats, T, scale, d_out, ld_out, nullptr, 0);
+  // automatic: one pass over the features finds max |x * 2^-k|; both kernels are launched and
+  // exactly one of them runs, chosen on the device (no host round trip, stays asynchronous)
+  KHG_CUDA_TRY(cudaMemsetAsync(t.gate, 0, sizeof(unsigned), m->stream));
+  const int64_t n = T * m->dim;
+  feat_absmax_kernel<<<(unsigned)std::min<int64_t>(4 * m->sm_count, (n + 255) / 256), 256, 0, m->stream>>>(
+      d_feats, n, m->dim, t.ascale, t.gate);
+  ++g_launch_count;
+  KHG_TRY(tc_launch<true>(m, d_feats, T, scale, d_out, ld_out, t.gate, 0));
+  return tc_launch<false>(m, d_feats, T, scale, d_out, ld_out, t.gate, 1);
 }
 
 }  // namespace khg

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libkhg_b200.so")
 KHG_OK, KHG_ERR_INVALID, KHG_ERR_CUDA, KHG_ERR_NONFINITE, KHG_ERR_UNSUPPORTED = range(5)
 KHG_HOST, KHG_DEVICE = 0, 1
 KHG_FRAME_MAJOR, KHG_PDF_MAJOR = 0, 1
-KHG_KERNEL_AUTO, KHG_KERNEL_SIMT, KHG_KERNEL_TCGEN05 = 0, 1, 2
+KHG_KERNEL_AUTO, KHG_KERNEL_SIMT, KHG_KERNEL_TCGEN05, KHG_KERNEL_TCGEN05_F16 = 0, 1, 2, 3
 
 # Every symbol include/khg_b200.h declares: (name, restype, argtypes)
 _vp = C.c_void_p

@@ -7,7 +7,7 @@ from oracle import khg_oracle as ko
 
 pytestmark = pytest.mark.gpu
 
-TC, SIMT = 2, 1
+TC, SIMT, TC_F16, AUTO = 2, 1, 3, 0
 
 
 def _models(model):
@@ -140,3 +140,94 @@ def test_baseline_config_shapes(oracle, name, D, P, G, T):
     assert abs(tot - r["tot_like"]) < 1e-4 * abs(r["tot_like"])
     # the aligned-pdf column of the dense block is the per-frame log-like of the stats path
     assert np.abs(ref[np.arange(T), pdf] - r["per_frame"]).max() < 1e-4
+
+
+def _one(model, kernel):
+    from kaldi_hmm_gmm_b200 import DeviceModel
+
+    dm = DeviceModel(model.dim, model.offsets)
+    dm.set_kernel(kernel)
+    dm.upload(model.weights, model.means_invvars, model.inv_vars)
+    return dm
+
+
+@pytest.mark.parametrize("D,P,G,T", [(40, 37, 350, 3000), (39, 13, 100, 1000), (40, 420, 4000, 700), (13, 5, 17, 129),
+                                     (60, 9, 200, 513), (5, 3, 3, 1)])
+def test_tc_f16_split_vs_oracle(oracle, D, P, G, T):
+    """3xFP16 split (kind::f16, per-dimension power-of-two scaling): same tolerance as 3xTF32."""
+    model, means, vars_ = ko.make_synthetic_model(D, P, G, oracle=oracle)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, T)
+    ref, bad = oracle.loglikes_all_pdfs(model, feats)
+    assert bad == 0
+    for kernel in (TC_F16, AUTO):
+        dm = _one(model, kernel)
+        _check(dm.loglikes_all_pdfs(feats), ref)
+        _check(dm.loglikes_all_pdfs(feats, scale=0.1, layout=1).T * 10.0, ref)
+
+
+def test_tc_f16_large_magnitude_model_is_rescaled(oracle):
+    """MFCC-like raw magnitudes (means ~ +-80, variances 50..2000): the per-dimension scaling
+    keeps the fp16 operands in range; accuracy stays within the tolerance."""
+    rng = np.random.default_rng(5)
+    D, P, G, T = 39, 20, 200, 600
+    offsets = np.arange(0, G + 1, G // P).astype(np.int32)
+    means = (80.0 * rng.standard_normal((G, D))).astype(np.float32)
+    vars_ = rng.uniform(50, 2000, (G, D)).astype(np.float32)
+    w = np.full(G, P / G, np.float32)
+    iv = (1 / vars_).astype(np.float32)
+    miv = (means * iv).astype(np.float32)
+    gc = np.concatenate([oracle.compute_gconsts(w[a:b], miv[a:b], iv[a:b])[0] for a, b in zip(offsets[:-1], offsets[1:])])
+    model = ko.PackedModel(offsets, w, miv, iv, gc)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, T)
+    ref, bad = oracle.loglikes_all_pdfs(model, feats)
+    assert bad == 0
+    _check(_one(model, TC_F16).loglikes_all_pdfs(feats), ref)
+
+
+def test_tc_auto_falls_back_to_tf32_when_out_of_fp16_range(oracle):
+    import torch
+
+    model, means, vars_ = ko.make_synthetic_model(40, 37, 350, oracle=oracle)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, 500)
+    # (1) features far outside the model's range: x^2 would overflow fp16 -> the device-side
+    # gate must route the call to the tf32 kernel, results still within tolerance
+    big = feats.copy()
+    big[7] *= 300.0
+    ref, _ = oracle.loglikes_all_pdfs(model, big)
+    auto = _one(model, AUTO)
+    got = auto.loglikes_all_pdfs(big)
+    err = np.abs(got.astype(np.float64) - ref)
+    rel = err / np.maximum(np.abs(ref), 1.0)
+    assert np.isfinite(got).all() and rel.max() < 1e-4
+    tc = _one(model, TC)
+    # host buffers are processed in 256-frame calls here: the call holding frame 7 must have
+    # run the tf32 kernel (bit-identical to the forced-tf32 model), the other one the fp16 kernel
+    np.testing.assert_array_equal(got[:256], tc.loglikes_all_pdfs(big)[:256])
+    # device-resident call stays asynchronous and correct
+    out = auto.loglikes_all_pdfs(torch.from_numpy(feats).cuda(), layout=1)
+    auto.sync()
+    _check(out.T.cpu().numpy(), oracle.loglikes_all_pdfs(model, feats)[0])
+    # (2) a model whose parameters do not fit fp16 (tiny variances -> huge means*inv_vars)
+    iv = model.inv_vars * 1e5
+    miv = model.means_invvars * 1e5
+    from kaldi_hmm_gmm_b200 import DeviceModel
+
+    dm = DeviceModel(model.dim, model.offsets)
+    dm.upload(model.weights, miv, iv)  # AUTO: silently stays on tf32
+    small = (feats * 0.01).astype(np.float32)
+    gcs = dm.gconsts()
+    m2 = ko.PackedModel(model.offsets, model.weights, miv.astype(np.float32), iv.astype(np.float32), gcs)
+    ref2, _ = oracle.loglikes_all_pdfs(m2, small)
+    got2 = dm.loglikes_all_pdfs(small)
+    assert (np.abs(got2 - ref2) / np.maximum(np.abs(ref2), 1.0)).max() < 1e-4
+    dm.set_kernel(TC_F16)
+    with pytest.raises(RuntimeError, match="fp16"):
+        dm.loglikes_all_pdfs(small)
+    # (3) zero-weight Gaussians (gconst = -inf) keep the model on the tf32 path too
+    w = model.weights.copy()
+    w[model.offsets[3] + 1] = 0.0
+    dz = DeviceModel(model.dim, model.offsets)
+    dz.upload(w, model.means_invvars, model.inv_vars)
+    gz = dz.gconsts()
+    mz = ko.PackedModel(model.offsets, w, model.means_invvars, model.inv_vars, gz)
+    _check(dz.loglikes_all_pdfs(feats), oracle.loglikes_all_pdfs(mz, feats)[0])
