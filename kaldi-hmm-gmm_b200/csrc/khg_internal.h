@@ -85,6 +85,11 @@ struct TcPack {
   int32_t *tile_g0 = nullptr;  // device, n_tiles
   int32_t *tile_p0 = nullptr;  // device, n_tiles+1
   std::vector<int32_t> h_tile_g0, h_tile_p0;
+  // epilogue tables: the pdfs (segments) of a tile grouped by their number of Gaussians
+  int32_t *tile_cls0 = nullptr;  // device, n_tiles+1
+  void *cls = nullptr;           // device int4 {len, seg_begin, seg_end, 0} per class
+  uint32_t *seg = nullptr;       // device, P: column | (pdf - tile_p0) << 16, class-major
+  bool dead_pdf = false;         // some pdf has only -inf gconsts: every call must fail like the reference
 };
 
 }  // namespace khg

@@ -16,17 +16,17 @@
 // lo.lo term is ~2^-22 relative), which keeps |error| well inside BASELINE.json's
 // 1e-3 abs / 1e-4 rel bound on log-likelihoods of magnitude ~1e2.
 //
-// Structure (one persistent CTA per SM, 24 warps, warp-specialised):
+// Structure (one persistent CTA per SM, 20 warps, warp-specialised):
 //   warp 0      TMA producer: streams B tiles (240 Gaussians x 32 floats, hi and lo)
 //               through a ring of smem stages (cp.async.bulk.tensor, 128B swizzle)
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::tf32, M=128 (frames),
 //               N=240 (Gaussians), K=8 per instruction; accumulators live in TMEM
 //               (2 x 256 columns, double buffered against the epilogue)
-//   warp 2      TMEM allocator
-//   warps 4-7   A builders: load a 128-frame feature tile, form [x, x^2, 1], split
+//               (this warp also allocates / frees the TMEM columns)
+//   warps 2-3   A builders: load a 128-frame feature tile, form [x, x^2, 1], split
 //               hi/lo and write it in the UMMA K-major 128B-swizzled layout.  A is
 //               stationary for all N tiles of a work item.
-//   warps 8-23  epilogue: tcgen05.ld the accumulator rows (thread = frame), per-pdf
+//   warps 4-19  epilogue: tcgen05.ld the accumulator rows (thread = frame), per-pdf
 //               max-subtracted log-sum-exp over the pdf's contiguous Gaussians,
 //               coalesced store of out[p][t] (pdf-major).
 // N tiles are aligned to pdf boundaries (tile table built on the host), so a pdf's
@@ -37,6 +37,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -58,7 +59,8 @@ constexpr int kAChunkBytes = kTileM * 128;   // 16384
 constexpr int kBStageBytes = kTileN * 128;   // 30720 (multiple of 1024)
 constexpr int kMaxChunks = 5;       // 128-byte K chunks per operand row held in smem
 constexpr int kEpiGroups = 4;       // epilogue warpgroups (4 warps each, one per TMEM lane quadrant)
-constexpr int kTcThreads = 256 + 128 * kEpiGroups;
+constexpr int kBuilderThreads = 64;  // warps 2-3
+constexpr int kTcThreads = 128 + 128 * kEpiGroups;  // warps 0-3: TMA, MMA(+TMEM alloc), 2 A-builder warps; then the epilogue
 // fp16 path: |x * 2^-k| beyond this keeps x^2 (and x) from fitting fp16 with margin
 constexpr float kF16FeatLimit = 128.0f;
 constexpr float kNegSentinel = -1.0e30f;  // stands in for gconst = -inf (0 * inf = NaN in the split)
@@ -87,6 +89,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!ok);
+}
+// Same, for waits that are expected to last long (hundreds of microseconds): back off with
+// nanosleep so that the polling warp does not eat issue slots of the epilogue warps.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(2000);
+  }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y) {
   asm volatile(
@@ -179,28 +197,8 @@ __device__ __forceinline__ float seg_lse(const TReg16 &t, float &M) {
   return fmaf(__log2f(s), kLn2, m);
 }
 
-// LSE of a segment of `len` columns at TMEM address taddr whose first 16 columns are
-// already in t (len <= 16: from registers only; longer: two passes over TMEM).
-__device__ __forceinline__ float seg_lse_any(const TReg16 &t, uint32_t taddr, int len, float &M) {
-  switch (len) {
-    case 1: return seg_lse<1>(t, M);
-    case 2: return seg_lse<2>(t, M);
-    case 3: return seg_lse<3>(t, M);
-    case 4: return seg_lse<4>(t, M);
-    case 5: return seg_lse<5>(t, M);
-    case 6: return seg_lse<6>(t, M);
-    case 7: return seg_lse<7>(t, M);
-    case 8: return seg_lse<8>(t, M);
-    case 9: return seg_lse<9>(t, M);
-    case 10: return seg_lse<10>(t, M);
-    case 11: return seg_lse<11>(t, M);
-    case 12: return seg_lse<12>(t, M);
-    case 13: return seg_lse<13>(t, M);
-    case 14: return seg_lse<14>(t, M);
-    case 15: return seg_lse<15>(t, M);
-    case 16: return seg_lse<16>(t, M);
-    default: break;
-  }
+// Generic LSE of a segment of `len` (> 16) columns at TMEM address taddr: two passes.
+__device__ __forceinline__ float seg_lse_long(uint32_t taddr, int len) {
   constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
   TReg16 w;
   float m = -CUDART_INF_F;
@@ -220,8 +218,49 @@ __device__ __forceinline__ float seg_lse_any(const TReg16 &t, uint32_t taddr, in
     for (int i = 0; i < 16; ++i)
       if (w0 + i < len) s += fast_exp2(fmaf(__uint_as_float(w.r[i]), kLog2e, -ml));
   }
-  M = m;
   return fmaf(__log2f(s), kLn2, m);
+}
+
+// All segments [sb, se) of one length class L <= 16 of the current tile that belong to
+// this epilogue group (eg, eg+4, ...).  The class loop carries no per-segment dispatch:
+// L is a compile-time constant, the TMEM load of the next segment and the descriptor of
+// the one after it are in flight while the current segment is reduced.
+//   trow  TMEM address of this warp's lane quadrant in the current accumulator buffer
+//   seg   packed segment descriptors: column | (pdf - first pdf of tile) << 16
+//   out_p out + first_pdf_of_tile * ld + t
+// Returns true when a non-finite result was produced (the reference's "Invalid answer").
+template <int L>
+__device__ __forceinline__ bool epi_class(uint32_t trow, const uint32_t *__restrict__ seg, float *__restrict__ out_p,
+                                          int64_t ld, float scale, bool valid, int sb, int se, int eg) {
+  bool bad = false;
+  int i = sb + eg;
+  if (i >= se) return false;
+  uint32_t d = __ldg(seg + i);
+#pragma unroll 1
+  for (; i < se; i += kEpiGroups) {
+    TReg16 t;
+    tc_ld16_issue(trow + (d & 0xffffu), t);
+    const uint32_t dcur = d;
+    if (i + kEpiGroups < se) d = __ldg(seg + i + kEpiGroups);  // next descriptor, under the TMEM latency
+    tc_ld16_wait(t);
+    float M;
+    const float r = seg_lse<L>(t, M);
+    bad |= !(fabsf(r) <= 3.0e38f);
+    if (valid) out_p[(int64_t)(dcur >> 16) * ld] = scale * r;
+  }
+  return bad;
+}
+
+__device__ __forceinline__ bool epi_class_long(uint32_t trow, const uint32_t *__restrict__ seg, float *__restrict__ out_p,
+                                               int64_t ld, float scale, bool valid, int sb, int se, int eg, int len) {
+  bool bad = false;
+  for (int i = sb + eg; i < se; i += kEpiGroups) {
+    const uint32_t d = __ldg(seg + i);
+    const float r = seg_lse_long(trow + (d & 0xffffu), len);
+    bad |= !(fabsf(r) <= 3.0e38f);
+    if (valid) out_p[(int64_t)(d >> 16) * ld] = scale * r;
+  }
+  return bad;
 }
 
 // UMMA shared-memory descriptor: K-major, 128B swizzle, 8-row groups 1024 B apart.
@@ -255,6 +294,8 @@ __device__ __forceinline__ void a_store_split<true>(uint8_t *a_hi, uint32_t lo_o
   *reinterpret_cast<__half *>(a_hi + off) = hi;
   *reinterpret_cast<__half *>(a_hi + lo_offset + off) = lo;
 }
+
+__global__ void latch_error_kernel(int *err, int bits) { atomicOr(err, bits); }
 
 // ------------------------------------------------------------------ B pack (K4) --
 __global__ void tc_pack_kernel(int G, int D, int KP, int rows, const float *__restrict__ miv,
@@ -332,6 +373,9 @@ struct TcArgs {
   const int32_t *offsets;  // P+1
   const int32_t *tile_g0;  // n_tiles
   const int32_t *tile_p0;  // n_tiles+1
+  const int32_t *tile_cls0;  // n_tiles+1: range of length classes of a tile
+  const int4 *cls;           // per class: {len, seg_begin, seg_end, 0}
+  const uint32_t *seg;       // per segment: column | (pdf - tile_p0) << 16, grouped by class
   int n_tiles, n_splits, tiles_per_split;
   int64_t n_items;
   float scale;
@@ -370,28 +414,30 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(b_full(s), 1);
-      mbar_init(b_empty(s), 1);
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(b_full(s), 1);
+        mbar_init(b_empty(s), 1);
+      }
+      mbar_init(a_full, 1);
+      mbar_init(a_free, 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(acc_full(b), 1);
+        mbar_init(acc_empty(b), 4 * kEpiGroups);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    mbar_init(a_full, 1);
-    mbar_init(a_free, 1);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), 4 * kEpiGroups);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  } else if (warp == 2) {
+    __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp == 2 || warp == 3) {
     // one-time A init: zero everything, then the constant-1 column (k = 2D) of A_hi
-    const int b = threadIdx.x - 128;
+    const int b = threadIdx.x - 64;
     float4 *z = reinterpret_cast<float4 *>(base_ptr);
-    for (int i = b; i < 2 * NCH * kAChunkBytes / 16; i += 128) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    a_store_split<F16>(base_ptr, NCH * kAChunkBytes, b, 2 * a.D, 1.0f);
+    for (int i = b; i < 2 * NCH * kAChunkBytes / 16; i += kBuilderThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    for (int row = b; row < kTileM; row += kBuilderThreads) a_store_split<F16>(base_ptr, NCH * kAChunkBytes, row, 2 * a.D, 1.0f);
   }
   tc_fence_before();
   __syncthreads();
@@ -411,6 +457,10 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             for (int hl = 0; hl < 2; ++hl, ++it) {
               const int st = it % S;
               mbar_wait(b_empty(st), ((it / S) & 1) ^ 1);
+              if (a.debug_mode == 3) {  // experiment: MMA rate without operand traffic
+                mbar_arrive(b_full(st));
+                continue;
+              }
               mbar_expect_tx(b_full(st), kBStageBytes);
               tma_load_2d(sB + st * kBStageBytes, hl ? &map_lo : &map_hi, b_full(st), c * kChunkK, g0);
             }
@@ -442,11 +492,13 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
               mbar_wait(b_full(st), (it / S) & 1);
               tc_fence_after();
               const uint64_t db = umma_desc(sB + st * kBStageBytes);
-              for (int k = 0; k < nk; ++k) {
-                tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, accum);
-                accum = 1;
+              if (a.debug_mode != 2) {  // (2 = experiment: TMA rate without MMAs)
+                for (int k = 0; k < nk; ++k) {
+                  tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, accum);
+                  accum = 1;
+                }
+                for (int k = 0; k < nk; ++k) tc_mma<F16>(tmem_d, da_lo + 2 * k, db + 2 * k, kIdesc, 1);
               }
-              for (int k = 0; k < nk; ++k) tc_mma<F16>(tmem_d, da_lo + 2 * k, db + 2 * k, kIdesc, 1);
               tc_commit(b_empty(st));
               ++it;
             }
@@ -455,7 +507,8 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
               mbar_wait(b_full(st), (it / S) & 1);
               tc_fence_after();
               const uint64_t db = umma_desc(sB + st * kBStageBytes);
-              for (int k = 0; k < nk; ++k) tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, 1);
+              if (a.debug_mode != 2)
+                for (int k = 0; k < nk; ++k) tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, 1);
               tc_commit(b_empty(st));
               ++it;
             }
@@ -465,17 +518,18 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         tc_commit(a_free);
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp == 2 || warp == 3) {
     // ===================== A builders =====================
-    const int b = threadIdx.x - 128;
+    const int b = threadIdx.x - 64;
     const int D = a.D;
     uint32_t a_it = 0;
     for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x, ++a_it) {
       const int64_t t0 = (item / a.n_splits) * kTileM;
       const int64_t valid = min((int64_t)kTileM, a.T - t0) * D;
       const float *src = a.feats + t0 * D;
-      mbar_wait(a_free, (a_it & 1) ^ 1);
-      for (int e = b; e < kTileM * D; e += 128) {
+      if (b == 0) mbar_wait_sleep(a_free, (a_it & 1) ^ 1);
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+      for (int e = b; e < kTileM * D; e += kBuilderThreads) {
         const float x = e < valid ? __ldg(src + e) : 0.f;
         const int row = e / D, d = e - row * D;
         const float q = x * x;  // data.array().square(), csrc/decodable-am-diag-gmm.cc:57
@@ -488,15 +542,14 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 64;" ::: "memory");
       if (b == 0) mbar_arrive(a_full);
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int eg = (warp - 8) >> 2;           // epilogue group: handles segments eg, eg+4, ...
+    const int eg = (warp - 4) >> 2;           // epilogue group: handles segments eg, eg+4, ...
     const int quad = warp & 3;                // TMEM lane quadrant of this warp
     const int row = quad * 32 + lane;
-    const float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
     uint32_t acc_it = 0;
     bool bad = false;
     for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
@@ -507,61 +560,26 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       float *out_t = a.out + t;
       for (int j = j0; j < j1; ++j, ++acc_it) {
         const int buf = acc_it & 1;
-        const int g0 = a.tile_g0[j];
-        const int pa = a.tile_p0[j], pb = a.tile_p0[j + 1];
-        // segment table of the first 32 pdfs of the tile, one pdf per lane (prefetched
-        // before the accumulator is ready)
-        int o0 = __ldg(a.offsets + min(pa + lane, pb));
-        int o1 = __ldg(a.offsets + min(pa + lane + 1, pb));
+        const int pa = a.tile_p0[j];
+        const int cb = a.tile_cls0[j], ce = a.tile_cls0[j + 1];
+        int4 cl = __ldg(a.cls + cb);
         mbar_wait(acc_full(buf), (acc_it >> 1) & 1);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256;
-        for (int pb0 = pa; pb0 < pb && a.debug_mode != 1; pb0 += 32) {
-          if (pb0 != pa) {
-            o0 = __ldg(a.offsets + min(pb0 + lane, pb));
-            o1 = __ldg(a.offsets + min(pb0 + lane + 1, pb));
+        float *out_p = out_t + (int64_t)pa * a.ld;
+        bool tb_bad = false;
+        for (int c = cb; c < ce && a.debug_mode == 0; ++c) {
+          const int len = cl.x, sb = cl.y, se = cl.z;
+          if (c + 1 < ce) cl = __ldg(a.cls + c + 1);
+#define KHG_CASE(L) case L: tb_bad |= epi_class<L>(trow, a.seg, out_p, a.ld, a.scale, valid, sb, se, eg); break;
+          switch (len) {
+            KHG_CASE(1) KHG_CASE(2) KHG_CASE(3) KHG_CASE(4) KHG_CASE(5) KHG_CASE(6) KHG_CASE(7) KHG_CASE(8)
+            KHG_CASE(9) KHG_CASE(10) KHG_CASE(11) KHG_CASE(12) KHG_CASE(13) KHG_CASE(14) KHG_CASE(15) KHG_CASE(16)
+            default: tb_bad |= epi_class_long(trow, a.seg, out_p, a.ld, a.scale, valid, sb, se, eg, len); break;
           }
-          const int nseg = min(32, pb - pb0);
-          // software pipeline over this warp's segments (eg, eg+4, ...): the TMEM load
-          // of the next segment is in flight while the current one is reduced
-          auto finish = [&](const TReg16 &tr, int sidx, int c0, int len) {
-            float M;
-            float r = seg_lse_any(tr, trow + c0, len, M);
-            // a pdf whose Gaussians all carry the -inf sentinel, or a NaN, is the
-            // reference's "Invalid answer" throw (csrc/decodable-am-diag-gmm.cc:63-65)
-            if (!(M > -1.0e29f) || !(fabsf(r) <= 3.0e38f)) {
-              r = CUDART_NAN_F;
-              if (valid) bad = true;
-            }
-            if (valid) out_t[(int64_t)(pb0 + sidx) * a.ld] = a.scale * r;
-          };
-          TReg16 ta, tb;
-          int sa = eg, c0a = 0, lena = 0, c0b = 0, lenb = 0;
-          if (sa < nseg) {
-            c0a = __shfl_sync(0xffffffffu, o0, sa) - g0;
-            lena = __shfl_sync(0xffffffffu, o1, sa) - g0 - c0a;
-            tc_ld16_issue(trow + c0a, ta);
-          }
-          while (sa < nseg) {
-            tc_ld16_wait(ta);
-            const int sb = sa + kEpiGroups;
-            if (sb < nseg) {
-              c0b = __shfl_sync(0xffffffffu, o0, sb) - g0;
-              lenb = __shfl_sync(0xffffffffu, o1, sb) - g0 - c0b;
-              tc_ld16_issue(trow + c0b, tb);
-            }
-            finish(ta, sa, c0a, lena);
-            if (sb >= nseg) break;
-            tc_ld16_wait(tb);
-            sa = sb + kEpiGroups;
-            if (sa < nseg) {
-              c0a = __shfl_sync(0xffffffffu, o0, sa) - g0;
-              lena = __shfl_sync(0xffffffffu, o1, sa) - g0 - c0a;
-              tc_ld16_issue(trow + c0a, ta);
-            }
-            finish(tb, sb, c0b, lenb);
-          }
+#undef KHG_CASE
         }
+        if (tb_bad && valid) bad = true;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty(buf));
@@ -572,7 +590,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -589,6 +607,10 @@ void tc_pack_free(khg_model *m) {
   TcPack &t = m->tc;
   cudaFree(t.bhi); cudaFree(t.blo); cudaFree(t.tile_g0); cudaFree(t.tile_p0);
   cudaFree(t.hhi); cudaFree(t.hlo); cudaFree(t.ascale); cudaFree(t.gate);
+  cudaFree(t.tile_cls0); cudaFree(t.cls); cudaFree(t.seg);
+  t.tile_cls0 = nullptr;
+  t.cls = nullptr;
+  t.seg = nullptr;
   t.bhi = t.blo = nullptr;
   t.hhi = t.hlo = nullptr;
   t.ascale = nullptr;
@@ -718,6 +740,49 @@ khg_status tc_pack_build(khg_model *m) {
   }
   t.h_tile_p0.push_back(P);
   t.n_tiles = (int)t.h_tile_g0.size();
+  // epilogue tables: per tile, its pdfs grouped by Gaussian count (one dispatch per class)
+  {
+    std::vector<int32_t> cls0(t.n_tiles + 1, 0);
+    std::vector<int4> cls;
+    std::vector<uint32_t> seg;
+    seg.reserve(P);
+    for (int j = 0; j < t.n_tiles; ++j) {
+      const int pa = t.h_tile_p0[j], pb = t.h_tile_p0[j + 1], g0 = t.h_tile_g0[j];
+      std::vector<std::pair<int, int>> by_len;  // (len, pdf)
+      for (int q = pa; q < pb; ++q) by_len.emplace_back(m->h_offsets[q + 1] - m->h_offsets[q], q);
+      std::stable_sort(by_len.begin(), by_len.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) { return x.first < y.first; });
+      for (size_t i = 0; i < by_len.size();) {
+        size_t e = i;
+        while (e < by_len.size() && by_len[e].first == by_len[i].first) ++e;
+        int4 c;
+        c.x = by_len[i].first;
+        c.y = (int)seg.size();
+        for (size_t k = i; k < e; ++k)
+          seg.push_back((uint32_t)(m->h_offsets[by_len[k].second] - g0) | ((uint32_t)(by_len[k].second - pa) << 16));
+        c.z = (int)seg.size();
+        c.w = 0;
+        cls.push_back(c);
+        i = e;
+      }
+      cls0[j + 1] = (int32_t)cls.size();
+    }
+    KHG_CUDA_TRY(cudaMalloc(&t.tile_cls0, sizeof(int32_t) * cls0.size()));
+    KHG_CUDA_TRY(cudaMalloc(&t.cls, sizeof(int4) * cls.size()));
+    KHG_CUDA_TRY(cudaMalloc(&t.seg, sizeof(uint32_t) * seg.size()));
+    KHG_CUDA_TRY(cudaMemcpy(t.tile_cls0, cls0.data(), sizeof(int32_t) * cls0.size(), cudaMemcpyHostToDevice));
+    KHG_CUDA_TRY(cudaMemcpy(t.cls, cls.data(), sizeof(int4) * cls.size(), cudaMemcpyHostToDevice));
+    KHG_CUDA_TRY(cudaMemcpy(t.seg, seg.data(), sizeof(uint32_t) * seg.size(), cudaMemcpyHostToDevice));
+    // a pdf whose Gaussians all have gconst = -inf makes LogSumExp NaN in the reference
+    // (csrc/eigen.cc:14-18 -> throw at csrc/decodable-am-diag-gmm.cc:63-65) for every frame
+    std::vector<float> gc(G);
+    KHG_CUDA_TRY(cudaMemcpy(gc.data(), m->d_gconsts, sizeof(float) * G, cudaMemcpyDeviceToHost));
+    t.dead_pdf = false;
+    for (int q = 0; q < P && !t.dead_pdf; ++q) {
+      bool all_dead = true;
+      for (int g = m->h_offsets[q]; g < m->h_offsets[q + 1]; ++g) all_dead = all_dead && std::isinf(gc[g]) && gc[g] < 0;
+      t.dead_pdf = all_dead;
+    }
+  }
   KHG_CUDA_TRY(cudaMalloc(&t.bhi, sizeof(float) * (size_t)t.rows * t.KP));
   KHG_CUDA_TRY(cudaMalloc(&t.blo, sizeof(float) * (size_t)t.rows * t.KP));
   KHG_CUDA_TRY(cudaMalloc(&t.tile_g0, sizeof(int32_t) * t.n_tiles));
@@ -759,6 +824,9 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   a.offsets = m->d_offsets;
   a.tile_g0 = t.tile_g0;
   a.tile_p0 = t.tile_p0;
+  a.tile_cls0 = t.tile_cls0;
+  a.cls = static_cast<const int4 *>(t.cls);
+  a.seg = t.seg;
   a.n_tiles = t.n_tiles;
   const int64_t n_m = (T + kTileM - 1) / kTileM;
   // Split the N range when there are too few frame tiles to fill the SMs; keep >= 8
@@ -783,7 +851,8 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
     attr_err = cudaFuncSetAttribute(loglikes_tc_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   KHG_CUDA_TRY(attr_err);
-  const unsigned grid = (unsigned)std::min<int64_t>(a.n_items, m->sm_count);
+  unsigned grid = (unsigned)std::min<int64_t>(a.n_items, m->sm_count);
+  if (const char *mc = getenv("KHG_TC_MAX_CTAS")) grid = std::min<unsigned>(grid, (unsigned)std::max(1, atoi(mc)));  // experiments
   if (F16)
     loglikes_tc_kernel<F16><<<grid, kTcThreads, smem, m->stream>>>(t.hmap_hi, t.hmap_lo, a);
   else
@@ -801,6 +870,10 @@ khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scal
   if (!t.ready) {
     set_error("tcgen05 model pack not built");
     return KHG_ERR_UNSUPPORTED;
+  }
+  if (t.dead_pdf) {
+    latch_error_kernel<<<1, 1, 0, m->stream>>>(m->d_err, ERR_NONFINITE);
+    ++g_launch_count;
   }
   if (precision == 2 && !t.f16_ready) {
     set_error("the fp16-split tensor-core path does not fit this model (parameter range or -inf gconsts)");
