@@ -117,21 +117,28 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// The smem descriptors differ only in their low word (start address); the high word
+// (stride, version, swizzle) is a constant, so the issuing thread does 32-bit adds only.
+constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
 template <bool F16>
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t idesc, uint32_t accum) {
   if (F16) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
         : "memory");
   } else {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
         : "memory");
   }
 }
@@ -267,6 +274,8 @@ __device__ __forceinline__ bool epi_class_long(uint32_t trow, const uint32_t *__
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return (saddr >> 4) & 0x3FFF; }
+static_assert((((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61)) >> 32 == kDescHi, "descriptor high word");
 // Instruction descriptor: D=f32, A=B=tf32 (format 2) or f16 (format 0), both K-major, M=128, N=240.
 template <bool F16>
 __host__ __device__ constexpr uint32_t make_idesc() {
@@ -447,22 +456,22 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t st = 0, ph = 1;  // producer waits on "empty" with the inverted phase
       for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         const int split = (int)(item % a.n_splits);
         const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
         for (int j = j0; j < j1; ++j) {
           const int g0 = a.tile_g0[j];
           for (int c = 0; c < NCH; ++c) {
-            for (int hl = 0; hl < 2; ++hl, ++it) {
-              const int st = it % S;
-              mbar_wait(b_empty(st), ((it / S) & 1) ^ 1);
+            for (int hl = 0; hl < 2; ++hl) {
+              mbar_wait(b_empty(st), ph);
               if (a.debug_mode == 3) {  // experiment: MMA rate without operand traffic
                 mbar_arrive(b_full(st));
-                continue;
+              } else {
+                mbar_expect_tx(b_full(st), kBStageBytes);
+                tma_load_2d(sB + st * kBStageBytes, hl ? &map_lo : &map_hi, b_full(st), c * kChunkK, g0);
               }
-              mbar_expect_tx(b_full(st), kBStageBytes);
-              tma_load_2d(sB + st * kBStageBytes, hl ? &map_lo : &map_hi, b_full(st), c * kChunkK, g0);
+              if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
             }
           }
         }
@@ -470,47 +479,53 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // One thread; its instruction stream is kept as short as possible (no divisions, 32-bit
+    // descriptor arithmetic): it shares an SM sub-partition with four busy epilogue warps.
     if (lane == 0) {
-      uint32_t it = 0, acc_it = 0, a_it = 0;
+      uint32_t st = 0, ph = 0, acc_it = 0, a_it = 0;
+      const uint32_t a_hi0 = umma_desc_lo(sA_hi), a_lo0 = umma_desc_lo(sA_lo), b0 = umma_desc_lo(sB);
+      constexpr uint32_t kAChunkDesc = kAChunkBytes >> 4, kBStageDesc = kBStageBytes >> 4;
+      const int nk_last = (a.K8 - (NCH - 1) * kChunkK) / kUmmaK;
       for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x, ++a_it) {
         const int split = (int)(item % a.n_splits);
         const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
         mbar_wait(a_full, a_it & 1);
         tc_fence_after();
         for (int j = j0; j < j1; ++j, ++acc_it) {
-          const int buf = acc_it & 1;
+          const uint32_t buf = acc_it & 1;
           mbar_wait(acc_empty(buf), ((acc_it >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * 256;
           uint32_t accum = 0;
           for (int c = 0; c < NCH; ++c) {
-            const int nk = min(kChunkK / kUmmaK, (a.K8 - c * kChunkK) / kUmmaK);
-            const uint64_t da_hi = umma_desc(sA_hi + c * kAChunkBytes);
-            const uint64_t da_lo = umma_desc(sA_lo + c * kAChunkBytes);
+            const int nk = c == NCH - 1 ? nk_last : kChunkK / kUmmaK;
+            const uint32_t da_hi = a_hi0 + c * kAChunkDesc, da_lo = a_lo0 + c * kAChunkDesc;
             {  // B_hi chunk: A_hi.B_hi + A_lo.B_hi
-              const int st = it % S;
-              mbar_wait(b_full(st), (it / S) & 1);
+              mbar_wait(b_full(st), ph);
               tc_fence_after();
-              const uint64_t db = umma_desc(sB + st * kBStageBytes);
+              const uint32_t db = b0 + st * kBStageDesc;
               if (a.debug_mode != 2) {  // (2 = experiment: TMA rate without MMAs)
+#pragma unroll 4
                 for (int k = 0; k < nk; ++k) {
                   tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, accum);
                   accum = 1;
                 }
+#pragma unroll 4
                 for (int k = 0; k < nk; ++k) tc_mma<F16>(tmem_d, da_lo + 2 * k, db + 2 * k, kIdesc, 1);
               }
               tc_commit(b_empty(st));
-              ++it;
+              if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
             }
             {  // B_lo chunk: A_hi.B_lo
-              const int st = it % S;
-              mbar_wait(b_full(st), (it / S) & 1);
+              mbar_wait(b_full(st), ph);
               tc_fence_after();
-              const uint64_t db = umma_desc(sB + st * kBStageBytes);
-              if (a.debug_mode != 2)
+              const uint32_t db = b0 + st * kBStageDesc;
+              if (a.debug_mode != 2) {
+#pragma unroll 4
                 for (int k = 0; k < nk; ++k) tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, 1);
+              }
               tc_commit(b_empty(st));
-              ++it;
+              if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
             }
           }
           tc_commit(acc_full(buf));
