@@ -17,16 +17,16 @@
 // 1e-3 abs / 1e-4 rel bound on log-likelihoods of magnitude ~1e2.
 //
 // Structure (one persistent CTA per SM, 20 warps, warp-specialised):
-//   warp 0      TMA producer: streams B tiles (240 Gaussians x 32 floats, hi and lo)
+//   warp 18     TMA producer: streams B tiles (240 Gaussians x 32 floats, hi and lo)
 //               through a ring of smem stages (cp.async.bulk.tensor, 128B swizzle)
-//   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::tf32, M=128 (frames),
+//   warp 19     MMA issuer: one thread issues tcgen05.mma.kind::tf32, M=128 (frames),
 //               N=240 (Gaussians), K=8 per instruction; accumulators live in TMEM
 //               (2 x 256 columns, double buffered against the epilogue)
 //               (this warp also allocates / frees the TMEM columns)
-//   warps 2-3   A builders: load a 128-frame feature tile, form [x, x^2, 1], split
+//   warps 16-17 A builders: load a 128-frame feature tile, form [x, x^2, 1], split
 //               hi/lo and write it in the UMMA K-major 128B-swizzled layout.  A is
 //               stationary for all N tiles of a work item.
-//   warps 4-19  epilogue: tcgen05.ld the accumulator rows (thread = frame), per-pdf
+//   warps 0-15  epilogue: tcgen05.ld the accumulator rows (thread = frame), per-pdf
 //               max-subtracted log-sum-exp over the pdf's contiguous Gaussians,
 //               coalesced store of out[p][t] (pdf-major).
 // N tiles are aligned to pdf boundaries (tile table built on the host), so a pdf's
@@ -59,8 +59,13 @@ constexpr int kAChunkBytes = kTileM * 128;   // 16384
 constexpr int kBStageBytes = kTileN * 128;   // 30720 (multiple of 1024)
 constexpr int kMaxChunks = 5;       // 128-byte K chunks per operand row held in smem
 constexpr int kEpiGroups = 4;       // epilogue warpgroups (4 warps each, one per TMEM lane quadrant)
-constexpr int kBuilderThreads = 64;  // warps 2-3
-constexpr int kTcThreads = 128 + 128 * kEpiGroups;  // warps 0-3: TMA, MMA(+TMEM alloc), 2 A-builder warps; then the epilogue
+constexpr int kBuilderThreads = 64;
+constexpr int kEpiWarps = 4 * kEpiGroups;      // warps 0..15: epilogue (TMEM lane quadrant = warp % 4)
+constexpr int kBuilderWarp0 = kEpiWarps;        // warps 16-17: A builders
+constexpr int kProducerWarp = kEpiWarps + 2;    // warp 18: TMA producer
+constexpr int kMmaWarp = kEpiWarps + 3;         // warp 19: MMA issuer (+ TMEM alloc); the warp scheduler
+                                                // favours high warp ids, and this warp must never starve
+constexpr int kTcThreads = 32 * (kEpiWarps + 4);
 // fp16 path: |x * 2^-k| beyond this keeps x^2 (and x) from fitting fp16 with margin
 constexpr float kF16FeatLimit = 128.0f;
 constexpr float kNegSentinel = -1.0e30f;  // stands in for gconst = -inf (0 * inf = NaN in the split)
@@ -79,14 +84,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: the warp is parked by the hardware until the phase
+  // completes (or the hint expires) instead of polling, so waiting warps do not take issue
+  // slots (or power) from the warps that have work.
   uint32_t ok;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
   } while (!ok);
 }
@@ -314,18 +322,24 @@ __global__ void tc_pack_kernel(int G, int D, int KP, int rows, const float *__re
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int k = (int)(i % KP);
     int g = (int)(i / KP);
-    float v = 0.f;
+    float hi = 0.f, lo = 0.f;
     if (g < G) {
-      if (k < D) v = miv[(size_t)g * D + k];
-      else if (k < 2 * D) v = -0.5f * iv[(size_t)g * D + (k - D)];
-      else if (k == 2 * D) {
-        v = gconsts[g];
+      if (k < 2 * D) {
+        const float v = k < D ? miv[(size_t)g * D + k] : -0.5f * iv[(size_t)g * D + (k - D)];
+        hi = tf32_rna(v);
+        lo = v - hi;
+        if (!(fabsf(v) <= 3.0e38f)) { hi = v; lo = 0.f; }
+      } else if (k <= 2 * D + 1) {
+        // gconst rides entirely in the hi.hi product: column 2D holds its tf32 part, column
+        // 2D+1 the residual, both against a constant 1 in A_hi; the cross products then only
+        // span the 2D feature columns.
+        float v = gconsts[g];
         if (v == -CUDART_INF_F) v = kNegSentinel;  // zero-weight Gaussian (csrc/diag-gmm.cc:136-141)
+        const float vh = tf32_rna(v);
+        hi = k == 2 * D ? vh : tf32_rna(v - vh);
+        if (!(fabsf(v) <= 3.0e38f)) hi = k == 2 * D ? v : 0.f;
       }
     }
-    float hi = tf32_rna(v);
-    float lo = v - hi;
-    if (!(fabsf(v) <= 3.0e38f)) { hi = v; lo = 0.f; }
     bhi[i] = hi;
     blo[i] = lo;
   }
@@ -344,15 +358,22 @@ __global__ void tc_pack_f16_kernel(int G, int D, int KP, int rows, const float *
     int k = (int)(i % KP);
     int g = (int)(i / KP);
     float v = 0.f;
+    bool is_gc = false;
     if (g < G) {
       if (k < D) v = miv[(size_t)g * D + k] * bscale[k];
       else if (k < 2 * D) v = -0.5f * iv[(size_t)g * D + (k - D)] * bscale[k];
-      else if (k == 2 * D) v = gconsts[g];
+      else if (k <= 2 * D + 1) { v = gconsts[g]; is_gc = true; }
     }
     if (!(fabsf(v) <= 3.0e4f)) bad = true;  // also catches -inf gconsts and NaN
     const __half hi = __float2half_rn(v);
-    bhi[i] = hi;
-    blo[i] = __float2half_rn(v - __half2float(hi));
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    if (is_gc) {  // gconst: fp16 part in column 2D, residual in column 2D+1, both in B_hi
+      bhi[i] = k == 2 * D ? hi : lo;
+      blo[i] = __float2half_rn(0.f);
+    } else {
+      bhi[i] = hi;
+      blo[i] = lo;
+    }
   }
   if (bad) atomicOr(flags, 1);
 }
@@ -373,7 +394,8 @@ __global__ void feat_absmax_kernel(const float *__restrict__ feats, int64_t n, i
 struct TcArgs {
   const float *feats;      // T x D
   int64_t T;
-  int D, K8, n_chunks;     // K8 = 2D+1 rounded up to UMMA_K; n_chunks = 128-byte chunks per operand row
+  int D, K8, Kc, n_chunks; // K8 = 2D+2 rounded up to UMMA_K (hi.hi product), Kc = 2D rounded up (cross
+                           // products); n_chunks = 128-byte chunks per operand row
   const float *ascale;     // fp16 path: per-column power-of-two scale of [x | x^2] (2D floats); NULL = none
   const unsigned *gate;    // NULL, or device word with max |x*ascale| bits: see gate_limit
   float gate_limit;        // fp16 kernel runs iff *gate <= limit, tf32 kernel iff *gate > limit
@@ -423,7 +445,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         mbar_init(b_full(s), 1);
@@ -440,20 +462,23 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  } else if (warp == 2 || warp == 3) {
+  } else if (warp == kBuilderWarp0 || warp == kBuilderWarp0 + 1) {
     // one-time A init: zero everything, then the constant-1 column (k = 2D) of A_hi
-    const int b = threadIdx.x - 64;
+    const int b = threadIdx.x - 32 * kBuilderWarp0;
     float4 *z = reinterpret_cast<float4 *>(base_ptr);
     for (int i = b; i < 2 * NCH * kAChunkBytes / 16; i += kBuilderThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     asm volatile("bar.sync 1, 64;" ::: "memory");
-    for (int row = b; row < kTileM; row += kBuilderThreads) a_store_split<F16>(base_ptr, NCH * kAChunkBytes, row, 2 * a.D, 1.0f);
+    for (int row = b; row < kTileM; row += kBuilderThreads) {
+      a_store_split<F16>(base_ptr, NCH * kAChunkBytes, row, 2 * a.D, 1.0f);
+      a_store_split<F16>(base_ptr, NCH * kAChunkBytes, row, 2 * a.D + 1, 1.0f);
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t st = 0, ph = 1;  // producer waits on "empty" with the inverted phase
@@ -464,6 +489,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
           const int g0 = a.tile_g0[j];
           for (int c = 0; c < NCH; ++c) {
             for (int hl = 0; hl < 2; ++hl) {
+              if (hl == 1 && a.Kc <= c * kChunkK) continue;  // no cross-product step in this chunk
               mbar_wait(b_empty(st), ph);
               if (a.debug_mode == 3) {  // experiment: MMA rate without operand traffic
                 mbar_arrive(b_full(st));
@@ -477,7 +503,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     // One thread; its instruction stream is kept as short as possible (no divisions, 32-bit
     // descriptor arithmetic): it shares an SM sub-partition with four busy epilogue warps.
@@ -485,7 +511,6 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       uint32_t st = 0, ph = 0, acc_it = 0, a_it = 0;
       const uint32_t a_hi0 = umma_desc_lo(sA_hi), a_lo0 = umma_desc_lo(sA_lo), b0 = umma_desc_lo(sB);
       constexpr uint32_t kAChunkDesc = kAChunkBytes >> 4, kBStageDesc = kBStageBytes >> 4;
-      const int nk_last = (a.K8 - (NCH - 1) * kChunkK) / kUmmaK;
       for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x, ++a_it) {
         const int split = (int)(item % a.n_splits);
         const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
@@ -498,7 +523,8 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
           const uint32_t tmem_d = tmem_base + buf * 256;
           uint32_t accum = 0;
           for (int c = 0; c < NCH; ++c) {
-            const int nk = c == NCH - 1 ? nk_last : kChunkK / kUmmaK;
+            const int nk = min(kChunkK, a.K8 - c * kChunkK) / kUmmaK;            // hi.hi product
+            const int nkc = max(0, min(kChunkK, a.Kc - c * kChunkK)) / kUmmaK;  // cross products
             const uint32_t da_hi = a_hi0 + c * kAChunkDesc, da_lo = a_lo0 + c * kAChunkDesc;
             {  // B_hi chunk: A_hi.B_hi + A_lo.B_hi
               mbar_wait(b_full(st), ph);
@@ -511,18 +537,18 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                   accum = 1;
                 }
 #pragma unroll 4
-                for (int k = 0; k < nk; ++k) tc_mma<F16>(tmem_d, da_lo + 2 * k, db + 2 * k, kIdesc, 1);
+                for (int k = 0; k < nkc; ++k) tc_mma<F16>(tmem_d, da_lo + 2 * k, db + 2 * k, kIdesc, 1);
               }
               tc_commit(b_empty(st));
               if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
             }
-            {  // B_lo chunk: A_hi.B_lo
+            if (nkc > 0) {  // B_lo chunk: A_hi.B_lo
               mbar_wait(b_full(st), ph);
               tc_fence_after();
               const uint32_t db = b0 + st * kBStageDesc;
               if (a.debug_mode != 2) {
 #pragma unroll 4
-                for (int k = 0; k < nk; ++k) tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, 1);
+                for (int k = 0; k < nkc; ++k) tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, 1);
               }
               tc_commit(b_empty(st));
               if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
@@ -533,9 +559,9 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         tc_commit(a_free);
       }
     }
-  } else if (warp == 2 || warp == 3) {
+  } else if (warp == kBuilderWarp0 || warp == kBuilderWarp0 + 1) {
     // ===================== A builders =====================
-    const int b = threadIdx.x - 64;
+    const int b = threadIdx.x - 32 * kBuilderWarp0;
     const int D = a.D;
     uint32_t a_it = 0;
     for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x, ++a_it) {
@@ -560,9 +586,9 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       asm volatile("bar.sync 1, 64;" ::: "memory");
       if (b == 0) mbar_arrive(a_full);
     }
-  } else if (warp >= 4) {
+  } else if (warp < kEpiWarps) {
     // ===================== epilogue =====================
-    const int eg = (warp - 4) >> 2;           // epilogue group: handles segments eg, eg+4, ...
+    const int eg = warp >> 2;           // epilogue group: handles segments eg, eg+4, ...
     const int quad = warp & 3;                // TMEM lane quadrant of this warp
     const int row = quad * 32 + lane;
     uint32_t acc_it = 0;
@@ -605,7 +631,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -679,7 +705,7 @@ static khg_status make_map(CUtensorMap *map, void *ptr, int KP, int rows, bool f
 static khg_status tc_pack_build_f16(khg_model *m) {
   TcPack &t = m->tc;
   const int D = m->dim, G = m->G;
-  t.K16 = (t.K + 15) / 16 * 16;
+  t.K16 = (t.K + 1 + 15) / 16 * 16;  // hi.hi product spans 2D+2 columns (gconst + its residual)
   t.KP16 = (t.K + 63) / 64 * 64;
   std::vector<float> miv((size_t)G * D), iv((size_t)G * D);
   KHG_CUDA_TRY(cudaMemcpyAsync(miv.data(), m->d_miv, sizeof(float) * miv.size(), cudaMemcpyDeviceToHost, m->stream));
@@ -734,7 +760,7 @@ khg_status tc_pack_build(khg_model *m) {
   tc_pack_free(m);
   const int D = m->dim, G = m->G, P = m->P;
   t.K = 2 * D + 1;
-  t.K8 = (t.K + 7) / 8 * 8;
+  t.K8 = (t.K + 1 + 7) / 8 * 8;
   t.KP = (t.K + 31) / 32 * 32;
   t.rows = (G + kTileN + 15) / 16 * 16;
   // pdf-aligned N tiles (greedy)
@@ -825,6 +851,7 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   a.T = T;
   a.D = m->dim;
   a.K8 = F16 ? t.K16 : t.K8;
+  a.Kc = (2 * m->dim + Elem<F16>::kUmmaK - 1) / Elem<F16>::kUmmaK * Elem<F16>::kUmmaK;
   a.n_chunks = (F16 ? t.KP16 : t.KP) / Elem<F16>::kChunkK;
   a.ascale = F16 ? t.ascale : nullptr;
   a.gate = gate;
