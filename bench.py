@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
     ap.add_argument("--frames", type=int, default=0, help="override total frames (debug)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05", "tcgen05_f16"])
     ap.add_argument("--chunk", type=int, default=148 * 128 * 16, help="frames per dense block")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -272,7 +272,7 @@ def run_b200(args):
     if world > 1:  # model parameters are broadcast once per EM iteration
         hm.update(par.broadcast_model({k: hm[k] for k in ("weights", "miv", "iv")}, device=dev))
     dm = DeviceModel(D, hm["offsets"])
-    dm.set_kernel({"auto": 0, "simt": 1, "tcgen05": 2}[args.kernel])
+    dm.set_kernel({"auto": 0, "simt": 1, "tcgen05": 2, "tcgen05_f16": 3}[args.kernel])
     dm.upload(hm["weights"], hm["miv"], hm["iv"])
     st = DeviceStats(dm)
     stats_view = st.as_torch()
@@ -342,8 +342,21 @@ def run_b200(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    ran = dm.dense_kernel()  # 1 SIMT, 2 tcgen05 3xTF32, 3 tcgen05 3xFP16
     flops_per_frame = 2.0 * G * K
     achieved = flops_per_frame * dense_frames / (dense_ms * 1e-3) / 1e12
+    # physical tensor work per logical MAC: hi.hi over 2D+2 columns + two cross products over 2D
+    # columns, each rounded up to the instruction's K (8 for tf32, 16 for fp16)
+    uk = 16 if ran == 3 else 8
+    phys = ((2 * D + 2 + uk - 1) // uk * uk + 2 * ((2 * D + uk - 1) // uk * uk)) / K if ran != 1 else 1.0
+    if ran == 3:  # kind::f16 operands: the measured bf16 dense figure is the denominator
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
+                    else "fallback 1400 TFLOP/s sustained bf16 (B200_PROFILING.md)")
+    else:
+        peak = tf32_peak
+        peak_src = ("TF32 dense measured in this run (torch.matmul fp32 8192^3, allow_tf32, best of 10); "
+                    "MEASURED_PEAKS.json has no TF32 entry")
     traffic = None
     try:
         # ncu-measured DRAM bytes per frame (profiles/) x frames of an average bench launch
@@ -351,15 +364,16 @@ def run_b200(args):
     except Exception:
         pass
     roofline = {
-        "kernel": "loglikes_tc_kernel (tcgen05 3xTF32)" if args.kernel != "simt" else "loglikes_simt_kernel",
-        "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-        "frac": achieved / tf32_peak if tf32_peak else None, "traffic": traffic,
-        "peak_source": "TF32 dense measured in this run (torch.matmul fp32 8192^3, allow_tf32, best of 10); "
-                       "MEASURED_PEAKS.json has no TF32 entry",
-        "bf16_peak_measured": peaks.get("bf16_tflops"),
+        "kernel": {1: "loglikes_simt_kernel (fp32 FMA)", 2: "loglikes_tc_kernel<tf32> (tcgen05 3xTF32 split)",
+                   3: "loglikes_tc_kernel<f16> (tcgen05 3xFP16 split, device-gated fallback to 3xTF32)"}[ran],
+        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+        "tf32_peak_measured_in_run": tf32_peak, "bf16_peak_measured": peaks.get("bf16_tflops"),
+        "bf16_peak_sustained_measured": peaks.get("bf16_tflops_sustained"),
         "algorithmic_flops_per_frame": flops_per_frame,
-        "physical_tensor_tflops": achieved * 3.0 * (((K + 7) // 8) * 8) / K,
-        "physical_frac_of_tf32_peak": achieved * 3.0 * (((K + 7) // 8) * 8) / K / tf32_peak if tf32_peak else None,
+        "physical_per_algorithmic": phys,
+        "physical_tensor_tflops": achieved * phys,
+        "physical_frac_of_peak": achieved * phys / peak if peak else None,
         "launches_timed": len(dense_events), "avg_launch_ms": dense_ms / max(1, len(dense_events)),
         "share_of_step": dense_ms / (ms_per_step * args.steps),
         "dense_frames_per_s": dense_frames / (dense_ms * 1e-3),
@@ -368,7 +382,9 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "tf32x3 (fp32-equivalent) likelihoods, f64 stats", "data": "synthetic",
+        "vs_baseline": None,
+        "dtype": {1: "f32", 2: "tf32 (3-term hi/lo split, fp32 accumulate)", 3: "f16 (3-term hi/lo split, fp32 accumulate)"}[ran] + " likelihoods, f64 stats",
+        "data": "synthetic",
         "config": {"workload": f"{args.config}: D={D} P={P} G={G} T={T_total} E-step = dense all-pdf loglikes + "
                                f"alignment stats (+ NCCL all-reduce of {stats_view.numel() * 8} B stats at N>1)",
                    "frames_per_gpu": T, "dense_block_frames": chunk, "kernel": args.kernel,

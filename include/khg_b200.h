@@ -106,6 +106,9 @@ khg_status khg_model_upload(khg_model *m, const float *weights /* G */,
 khg_status khg_model_get_gconsts(khg_model *m, float *gconsts /* host, G */);
 khg_status khg_model_info(const khg_model *m, int32_t *dim, int32_t *num_pdfs,
                           int32_t *num_gauss);
+/* Which dense kernel an in-range call will run with the current choice: KHG_KERNEL_SIMT,
+ * KHG_KERNEL_TCGEN05 or KHG_KERNEL_TCGEN05_F16 (AUTO resolved against this model). */
+khg_status khg_model_dense_kernel(const khg_model *m, int32_t *kernel);
 /* Chooses the dense-likelihood kernel (default KHG_KERNEL_AUTO). */
 khg_status khg_model_set_kernel(khg_model *m, int32_t kernel);
 /* Launches on this CUDA stream (a cudaStream_t; NULL = default stream). */

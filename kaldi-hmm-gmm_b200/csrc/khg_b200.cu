@@ -217,6 +217,14 @@ khg_status khg_model_info(const khg_model *m, int32_t *dim, int32_t *num_pdfs, i
   return KHG_OK;
 }
 
+khg_status khg_model_dense_kernel(const khg_model *m, int32_t *kernel) {
+  KHG_REQUIRE(m && kernel, "null argument");
+  if (m->kernel == KHG_KERNEL_SIMT || !m->tc.ready) *kernel = KHG_KERNEL_SIMT;
+  else if (m->kernel == KHG_KERNEL_TCGEN05 || !m->tc.f16_ready) *kernel = KHG_KERNEL_TCGEN05;
+  else *kernel = KHG_KERNEL_TCGEN05_F16;
+  return KHG_OK;
+}
+
 khg_status khg_model_set_kernel(khg_model *m, int32_t kernel) {
   KHG_REQUIRE(m && kernel >= KHG_KERNEL_AUTO && kernel <= KHG_KERNEL_TCGEN05_F16, "bad kernel id");
   if ((kernel == KHG_KERNEL_TCGEN05 || kernel == KHG_KERNEL_TCGEN05_F16) && !tc_supported(m)) {

@@ -72,6 +72,12 @@ class DeviceModel:
         A.check(A.lib().khg_model_download(self._h, offs.ctypes.data, w.ctypes.data, miv.ctypes.data, iv.ctypes.data, gc.ctypes.data))
         return dict(offsets=offs, weights=w, means_invvars=miv, inv_vars=iv, gconsts=gc)
 
+    def dense_kernel(self) -> int:
+        """1 = SIMT, 2 = tcgen05 3xTF32, 3 = tcgen05 3xFP16 (what an in-range call runs)."""
+        k = C.c_int32()
+        A.check(A.lib().khg_model_dense_kernel(self._h, C.byref(k)))
+        return k.value
+
     def set_kernel(self, kernel: int):
         A.check(A.lib().khg_model_set_kernel(self._h, kernel))
 
