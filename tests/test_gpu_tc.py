@@ -231,3 +231,38 @@ def test_tc_auto_falls_back_to_tf32_when_out_of_fp16_range(oracle):
     gz = dz.gconsts()
     mz = ko.PackedModel(model.offsets, w, model.means_invvars, model.inv_vars, gz)
     _check(dz.loglikes_all_pdfs(feats), oracle.loglikes_all_pdfs(mz, feats)[0])
+
+
+def test_tc_length_classes_and_kernel_query(oracle):
+    """Every segment length 1..20 plus a 240-Gaussian pdf in one model: exercises each
+    compile-time length class of the epilogue, the >16 two-pass path and tile packing."""
+    from kaldi_hmm_gmm_b200 import DeviceModel
+
+    rng = np.random.default_rng(21)
+    D = 40
+    sizes = np.array(list(range(1, 21)) * 3 + [240, 1, 16, 17, 239, 2], np.int32)
+    rng.shuffle(sizes)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    G = int(offsets[-1])
+    means = rng.standard_normal((G, D)).astype(np.float32) * 2
+    vars_ = rng.uniform(0.5, 2, (G, D)).astype(np.float32)
+    w = np.concatenate([rng.dirichlet(np.ones(s)) for s in sizes]).astype(np.float32)
+    iv = (1 / vars_).astype(np.float32)
+    miv = (means * iv).astype(np.float32)
+    gc = np.concatenate([oracle.compute_gconsts(w[a:b], miv[a:b], iv[a:b])[0] for a, b in zip(offsets[:-1], offsets[1:])])
+    model = ko.PackedModel(offsets, w, miv, iv, gc)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, 300)
+    ref, bad = oracle.loglikes_all_pdfs(model, feats)
+    assert bad == 0
+    for kernel, expect in ((AUTO, 3), (TC, 2), (TC_F16, 3), (SIMT, 1)):
+        dm = _one(model, kernel)
+        assert dm.dense_kernel() == expect
+        _check(dm.loglikes_all_pdfs(feats), ref)
+    # a pdf with 241 Gaussians does not fit an accumulator tile: AUTO falls back to the SIMT kernel
+    sizes2 = np.array([241, 3], np.int32)
+    off2 = np.array([0, 241, 244], np.int32)
+    dm = DeviceModel(D, off2)
+    dm.upload(np.full(244, 1 / 122, np.float32), miv[:244], iv[:244])
+    assert dm.dense_kernel() == 1
+    with pytest.raises(RuntimeError, match="does not support"):
+        dm.set_kernel(TC)
