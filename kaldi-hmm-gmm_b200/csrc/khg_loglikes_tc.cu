@@ -98,22 +98,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
-// Same, for waits that are expected to last long (hundreds of microseconds): back off with
-// nanosleep so that the polling warp does not eat issue slots of the epilogue warps.
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  for (;;) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) break;
-    __nanosleep(2000);
-  }
-}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -568,7 +552,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       const int64_t t0 = (item / a.n_splits) * kTileM;
       const int64_t valid = min((int64_t)kTileM, a.T - t0) * D;
       const float *src = a.feats + t0 * D;
-      if (b == 0) mbar_wait_sleep(a_free, (a_it & 1) ^ 1);
+      if (b == 0) mbar_wait(a_free, (a_it & 1) ^ 1);
       asm volatile("bar.sync 1, 64;" ::: "memory");
       for (int e = b; e < kTileM * D; e += kBuilderThreads) {
         const float x = e < valid ? __ldg(src + e) : 0.f;
