@@ -160,6 +160,11 @@ __device__ __forceinline__ float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
+__device__ __forceinline__ float fast_log2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -182,18 +187,18 @@ __device__ __forceinline__ float seg_lse(const TReg16 &t, float &M) {
   const float ml = m * kLog2e;
   // packed fp32x2 math (FFMA2 / FADD2 on sm_100): one issue slot per two columns
   const float2 k2 = make_float2(kLog2e, kLog2e), nm2 = make_float2(-ml, -ml);
-  float2 s2 = make_float2(0.f, 0.f);
+  float2 s2;
 #pragma unroll
   for (int i = 0; i + 1 < L; i += 2) {
     float2 a = __ffma2_rn(make_float2(__uint_as_float(t.r[i]), __uint_as_float(t.r[i + 1])), k2, nm2);
     a.x = fast_exp2(a.x);
     a.y = fast_exp2(a.y);
-    s2 = __fadd2_rn(s2, a);
+    s2 = i == 0 ? a : __fadd2_rn(s2, a);
   }
   float s = s2.x + s2.y;
   if (L & 1) s += fast_exp2(fmaf(__uint_as_float(t.r[L - 1]), kLog2e, -ml));
   M = m;
-  return fmaf(__log2f(s), kLn2, m);
+  return fmaf(fast_log2(s), kLn2, m);
 }
 
 // Generic LSE of a segment of `len` (> 16) columns at TMEM address taddr: two passes.
@@ -217,7 +222,7 @@ __device__ __forceinline__ float seg_lse_long(uint32_t taddr, int len) {
     for (int i = 0; i < 16; ++i)
       if (w0 + i < len) s += fast_exp2(fmaf(__uint_as_float(w.r[i]), kLog2e, -ml));
   }
-  return fmaf(__log2f(s), kLn2, m);
+  return fmaf(fast_log2(s), kLn2, m);
 }
 
 // All segments [sb, se) of one length class L <= 16 of the current tile that belong to
@@ -228,12 +233,14 @@ __device__ __forceinline__ float seg_lse_long(uint32_t taddr, int len) {
 //   seg   packed segment descriptors: column | (pdf - first pdf of tile) << 16
 //   out_p out + first_pdf_of_tile * ld + t
 // Returns true when a non-finite result was produced (the reference's "Invalid answer").
+// out_b: byte address of out[first pdf of tile][t] — or of a scratch word with ld_bytes = 0
+// for rows beyond T, so that the store needs no predicate.  nan_acc collects r*0 (NaN for a
+// non-finite r): one FFMA instead of a compare/select/or per segment.
 template <int L>
-__device__ __forceinline__ bool epi_class(uint32_t trow, const uint32_t *__restrict__ seg, float *__restrict__ out_p,
-                                          int64_t ld, float scale, bool valid, int sb, int se, int eg) {
-  bool bad = false;
+__device__ __forceinline__ void epi_class(uint32_t trow, const uint32_t *__restrict__ seg, char *out_b,
+                                          uint32_t ld_bytes, float scale, float &nan_acc, int sb, int se, int eg) {
   int i = sb + eg;
-  if (i >= se) return false;
+  if (i >= se) return;
   uint32_t d = __ldg(seg + i);
 #pragma unroll 1
   for (; i < se; i += kEpiGroups) {
@@ -244,22 +251,20 @@ __device__ __forceinline__ bool epi_class(uint32_t trow, const uint32_t *__restr
     tc_ld16_wait(t);
     float M;
     const float r = seg_lse<L>(t, M);
-    bad |= !(fabsf(r) <= 3.0e38f);
-    if (valid) out_p[(int64_t)(dcur >> 16) * ld] = scale * r;
+    nan_acc = fmaf(r, 0.f, nan_acc);
+    *reinterpret_cast<float *>(out_b + (uint64_t)(dcur >> 16) * ld_bytes) = scale * r;
   }
-  return bad;
 }
 
-__device__ __forceinline__ bool epi_class_long(uint32_t trow, const uint32_t *__restrict__ seg, float *__restrict__ out_p,
-                                               int64_t ld, float scale, bool valid, int sb, int se, int eg, int len) {
-  bool bad = false;
+__device__ __forceinline__ void epi_class_long(uint32_t trow, const uint32_t *__restrict__ seg, char *out_b,
+                                               uint32_t ld_bytes, float scale, float &nan_acc, int sb, int se, int eg,
+                                               int len) {
   for (int i = sb + eg; i < se; i += kEpiGroups) {
     const uint32_t d = __ldg(seg + i);
     const float r = seg_lse_long(trow + (d & 0xffffu), len);
-    bad |= !(fabsf(r) <= 3.0e38f);
-    if (valid) out_p[(int64_t)(d >> 16) * ld] = scale * r;
+    nan_acc = fmaf(r, 0.f, nan_acc);
+    *reinterpret_cast<float *>(out_b + (uint64_t)(d >> 16) * ld_bytes) = scale * r;
   }
-  return bad;
 }
 
 // UMMA shared-memory descriptor: K-major, 128B swizzle, 8-row groups 1024 B apart.
@@ -396,6 +401,7 @@ struct TcArgs {
   float scale;
   float *out;              // pdf-major, out[p*ld + t]
   int64_t ld;
+  float *scratch;          // one device word: store target of rows beyond T
   int *err;
   int debug_mode;          // 0 = normal; 1 = epilogue skips the LSE (pipeline-ceiling experiment, KHG_TC_DEBUG_MODE)
 };
@@ -582,7 +588,10 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
       const int64_t t = (item / a.n_splits) * kTileM + row;
       const bool valid = t < a.T;
-      float *out_t = a.out + t;
+      // rows beyond T store into a scratch word (ld_bytes = 0): no predicate in the hot loop
+      char *out_t = valid ? reinterpret_cast<char *>(a.out + t) : reinterpret_cast<char *>(a.scratch);
+      const uint32_t ld_bytes = valid ? (uint32_t)(a.ld * 4) : 0u;
+      float nan_acc = 0.f;
       for (int j = j0; j < j1; ++j, ++acc_it) {
         const int buf = acc_it & 1;
         const int pa = a.tile_p0[j];
@@ -591,24 +600,23 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         mbar_wait(acc_full(buf), (acc_it >> 1) & 1);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256;
-        float *out_p = out_t + (int64_t)pa * a.ld;
-        bool tb_bad = false;
+        char *out_p = out_t + (uint64_t)pa * ld_bytes;
         for (int c = cb; c < ce && a.debug_mode == 0; ++c) {
           const int len = cl.x, sb = cl.y, se = cl.z;
           if (c + 1 < ce) cl = __ldg(a.cls + c + 1);
-#define KHG_CASE(L) case L: tb_bad |= epi_class<L>(trow, a.seg, out_p, a.ld, a.scale, valid, sb, se, eg); break;
+#define KHG_CASE(L) case L: epi_class<L>(trow, a.seg, out_p, ld_bytes, a.scale, nan_acc, sb, se, eg); break;
           switch (len) {
             KHG_CASE(1) KHG_CASE(2) KHG_CASE(3) KHG_CASE(4) KHG_CASE(5) KHG_CASE(6) KHG_CASE(7) KHG_CASE(8)
             KHG_CASE(9) KHG_CASE(10) KHG_CASE(11) KHG_CASE(12) KHG_CASE(13) KHG_CASE(14) KHG_CASE(15) KHG_CASE(16)
-            default: tb_bad |= epi_class_long(trow, a.seg, out_p, a.ld, a.scale, valid, sb, se, eg, len); break;
+            default: epi_class_long(trow, a.seg, out_p, ld_bytes, a.scale, nan_acc, sb, se, eg, len); break;
           }
 #undef KHG_CASE
         }
-        if (tb_bad && valid) bad = true;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty(buf));
       }
+      if (valid && nan_acc != nan_acc) bad = true;  // r*0 is NaN exactly for a NaN/Inf result
     }
     if (bad) atomicOr(a.err, ERR_NONFINITE);
   }
@@ -866,6 +874,11 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   a.out = d_out;
   a.ld = ld_out;
   a.err = m->d_err;
+  a.scratch = reinterpret_cast<float *>(m->d_scratch_int + 3);
+  if (ld_out * 4 >= ((int64_t)1 << 32)) {
+    set_error("ld_out too large for the tensor-core kernel (needs ld_out < 2^30)");
+    return KHG_ERR_UNSUPPORTED;
+  }
   {
     const char *dbg = getenv("KHG_TC_DEBUG_MODE");
     a.debug_mode = dbg ? atoi(dbg) : 0;
