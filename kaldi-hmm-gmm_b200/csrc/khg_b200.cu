@@ -3,6 +3,7 @@
 // khg_kernels.cuh (SIMT) and khg_loglikes_tc.cu (tcgen05).  No CPU fallback:
 // every compute entry point needs a CUDA device.
 #include <cub/device/device_radix_sort.cuh>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cmath>
@@ -36,6 +37,12 @@ void Buf::release() {
   p = nullptr;
   cap = 0;
 }
+
+// NVTX range around every batch entry point (visible in nsys / ncu --nvtx timelines).
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
@@ -164,6 +171,7 @@ khg_status khg_model_create(int32_t dim, int32_t num_pdfs, const int32_t *gauss_
 
 khg_status khg_model_upload(khg_model *m, const float *weights, const float *means_invvars,
                             const float *inv_vars, const float *gconsts, int32_t *num_bad) {
+  NvtxRange nvtx_range("khg_model_upload");
   KHG_REQUIRE(m && means_invvars && inv_vars, "null argument");
   KHG_REQUIRE(weights || gconsts, "need weights or gconsts");
   size_t gd = (size_t)m->G * m->dim;
@@ -334,6 +342,7 @@ static khg_status dense_device(khg_model *m, const float *d_feats, int64_t T, fl
 khg_status khg_loglikes_all_pdfs(khg_model *m, const float *feats, int64_t T, int32_t feats_loc,
                                  float scale, int32_t layout, float *out, int64_t ld_out,
                                  int32_t out_loc) {
+  NvtxRange nvtx_range("khg_loglikes_all_pdfs");
   KHG_REQUIRE(m && m->uploaded, "model not uploaded");
   KHG_REQUIRE(T >= 0 && (T == 0 || (feats && out)), "null buffer");
   KHG_REQUIRE(layout == KHG_FRAME_MAJOR || layout == KHG_PDF_MAJOR, "bad layout");
@@ -589,6 +598,7 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
 khg_status khg_acc_stats_ali(khg_model *m, khg_stats *s, const float *feats, int64_t T, int32_t loc,
                              const int32_t *pdf_ids, const float *frame_weights,
                              float *per_frame_loglike, double *tot_loglike) {
+  NvtxRange nvtx_range("khg_acc_stats_ali");
   KHG_REQUIRE(m && s && s->model == m && m->uploaded, "model/stats mismatch or model not uploaded");
   KHG_REQUIRE(T >= 0, "T >= 0");
   if (T == 0) {
@@ -626,6 +636,7 @@ khg_status khg_acc_stats_ali(khg_model *m, khg_stats *s, const float *feats, int
 khg_status khg_acc_stats_ali_tids(khg_model *m, khg_stats *s, const float *feats, int64_t T,
                                   const int32_t *tids, const int32_t *tid2pdf, int32_t num_tids,
                                   double *trans_accs, double *tot_loglike) {
+  NvtxRange nvtx_range("khg_acc_stats_ali_tids");
   KHG_REQUIRE(m && s && s->model == m && m->uploaded, "model/stats mismatch or model not uploaded");
   KHG_REQUIRE(T >= 0 && num_tids > 0 && tid2pdf, "bad argument");
   if (T == 0) {
@@ -720,6 +731,7 @@ struct DevTmp {  // small RAII bundle of device scratch for the M-step
 khg_status khg_mle_update(khg_model *m, const khg_stats *s, const khg_mle_options *opts, uint16_t update_flags,
                           khg_model **new_model, float *obj_change, float *count, int32_t *floored_elements,
                           int32_t *floored_gaussians, int32_t *removed_gaussians) {
+  NvtxRange nvtx_range("khg_mle_update");
   KHG_REQUIRE(m && s && s->model == m && m->uploaded && opts && new_model, "bad argument");
   update_flags &= (KHG_GMM_MEANS | KHG_GMM_VARIANCES | KHG_GMM_WEIGHTS);
   if (update_flags & ~s->flags) {
@@ -843,6 +855,7 @@ static khg_status estep_init_streams(khg_model *m) {
 khg_status khg_estep(khg_model *m, khg_stats *s, const float *feats, int64_t T, int32_t loc,
                      const int32_t *pdf_ids, const float *frame_weights, float *loglikes_out,
                      int64_t ld_out, int64_t chunk_frames, double *tot_loglike) {
+  NvtxRange nvtx_range("khg_estep");
   KHG_REQUIRE(m && s && s->model == m && m->uploaded, "model/stats mismatch or model not uploaded");
   KHG_REQUIRE(T >= 0, "T >= 0");
   if (tot_loglike) *tot_loglike = 0.0;

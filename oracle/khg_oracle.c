@@ -112,7 +112,7 @@ static void loglikes_sq(int32_t nmix, int32_t dim, const float *gconsts,
 void khg_oracle_loglikes(int32_t nmix, int32_t dim, const float *gconsts,
                          const float *means_invvars, const float *inv_vars,
                          const float *x, float *loglikes) {
-  float stack_sq[KHG_MAX_STACK_DIM];
+  float stack_sq[KHG_MAX_STACK_DIM] = {0};
   float *xsq = dim <= KHG_MAX_STACK_DIM ? stack_sq : (float *)malloc(sizeof(float) * dim);
   for (int32_t d = 0; d < dim; ++d) xsq[d] = x[d] * x[d];
   loglikes_sq(nmix, dim, gconsts, means_invvars, inv_vars, x, xsq, loglikes);
