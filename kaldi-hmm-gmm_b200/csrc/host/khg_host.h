@@ -301,6 +301,12 @@ class DecodableInterface {
 class DecodableAmDiagGmmUnmapped : public DecodableInterface {
  public:
   DecodableAmDiagGmmUnmapped(const AmDiagGmm &am, const FloatMatrix &feats, float log_sum_exp_prune = -1.0f);
+  // From a precomputed pdf-major block (num_pdfs x num_frames), e.g. one utterance's slice of a
+  // batched khg_loglikes_all_pdfs call over many utterances.
+  DecodableAmDiagGmmUnmapped(std::vector<float> block, int32_t num_pdfs, int32_t num_frames)
+      : num_frames_(num_frames), num_pdfs_(num_pdfs), log_sum_exp_prune_(-1.0f), block_(std::move(block)) {
+    KHG_HOST_ASSERT((size_t)num_pdfs * num_frames == block_.size());
+  }
   float LogLikelihood(int32_t frame, int32_t state_index) override {  // indices are one-based (:49-53)
     return LogLikelihoodZeroBased(frame, state_index - 1);
   }
@@ -325,6 +331,9 @@ class DecodableAmDiagGmmScaled : public DecodableAmDiagGmmUnmapped {
   DecodableAmDiagGmmScaled(const AmDiagGmm &am, std::vector<int32_t> tid2pdf, const FloatMatrix &feats, float scale,
                            float log_sum_exp_prune = -1.0f)
       : DecodableAmDiagGmmUnmapped(am, feats, log_sum_exp_prune), tid2pdf_(std::move(tid2pdf)), scale_(scale) {}
+  DecodableAmDiagGmmScaled(std::vector<float> block, int32_t num_pdfs, int32_t num_frames, std::vector<int32_t> tid2pdf,
+                           float scale)
+      : DecodableAmDiagGmmUnmapped(std::move(block), num_pdfs, num_frames), tid2pdf_(std::move(tid2pdf)), scale_(scale) {}
   float LogLikelihood(int32_t frame, int32_t tid) override {  // :94-98
     KHG_HOST_ASSERT(tid >= 1 && tid < (int32_t)tid2pdf_.size());
     return scale_ * LogLikelihoodZeroBased(frame, tid2pdf_[tid]);

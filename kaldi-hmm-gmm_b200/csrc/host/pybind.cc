@@ -431,5 +431,14 @@ PYBIND11_MODULE(_khg_b200, m) {
              return new DecodableAmDiagGmmScaled(am, Tid2Pdf(tm), ToMat(feats), scale, prune);
            }),
            py::arg("am"), py::arg("tm"), py::arg("feats"), py::arg("scale"), py::arg("log_sum_exp_prune") = -1.0,
-           py::keep_alive<1, 3>());
+           py::keep_alive<1, 3>())
+      // new: wrap one utterance's (num_pdfs x num_frames) slice of a batched all-pdf block
+      .def_static(
+          "from_block",
+          [](const FArr &block, const py::object &tm, float scale) {
+            if (block.ndim() != 2) throw std::runtime_error("block must be (num_pdfs, num_frames)");
+            std::vector<float> b(block.data(), block.data() + block.size());
+            return new DecodableAmDiagGmmScaled(std::move(b), (int32_t)block.shape(0), (int32_t)block.shape(1), Tid2Pdf(tm), scale);
+          },
+          py::arg("block"), py::arg("tm"), py::arg("scale"));
 }

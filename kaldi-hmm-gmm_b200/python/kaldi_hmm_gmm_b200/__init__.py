@@ -15,7 +15,7 @@ from .device import DeviceModel, DeviceStats  # noqa: F401
 try:  # the pybind11 mirror of the reference classes (built by __graft_entry__.build())
     from ._khg_b200 import *  # noqa: F401,F403
     from ._khg_b200 import __doc__ as _ext_doc  # noqa: F401
-    from .scripts import gmm_acc_stats_ali, gmm_est, make_decodable  # noqa: F401
+    from .scripts import gmm_acc_stats_ali, gmm_est, make_decodable, make_decodables  # noqa: F401
     HAVE_EXTENSION = True
 except ImportError as _e:  # pragma: no cover - reported loudly on use
     HAVE_EXTENSION = False

@@ -64,3 +64,20 @@ def make_decodable(am_gmm, transition_model, feats, acoustic_scale: float = 1.0)
     likelihood block is computed once on the GPU at construction."""
     return _ext.DecodableAmDiagGmmScaled(am=am_gmm, tm=_tid2pdf(transition_model), feats=_np(feats, np.float32),
                                          scale=acoustic_scale)
+
+
+def make_decodables(am_gmm, transition_model, feats_list, acoustic_scale: float = 1.0):
+    """Decodables for MANY utterances from ONE dense GPU call: the utterances are concatenated,
+    the (frames x pdfs) block is computed once by the tensor-core kernel and sliced per
+    utterance (the feed of a batched gmm-align-compiled)."""
+    feats_list = [_np(f, np.float32) for f in feats_list]
+    lens = [f.shape[0] for f in feats_list]
+    if not lens:
+        return []
+    block = am_gmm.log_likelihoods_all_pdfs(np.concatenate(feats_list, axis=0))  # (sum T, P)
+    t2p = _tid2pdf(transition_model)
+    out, t0 = [], 0
+    for n in lens:
+        out.append(_ext.DecodableAmDiagGmmScaled.from_block(np.ascontiguousarray(block[t0:t0 + n].T), t2p, acoustic_scale))
+        t0 += n
+    return out

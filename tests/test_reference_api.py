@@ -286,6 +286,13 @@ def test_decodables(oracle):
     with pytest.raises(RuntimeError, match="Dim mismatch"):
         khg.DecodableAmDiagGmmUnmapped(am=am, feats=np.zeros((3, 5), np.float32))
 
+    # many utterances, one dense call (batched feed of gmm-align-compiled)
+    cuts = [feats[:7], feats[7:30], feats[30:]]
+    decs = khg.make_decodables(am, tid2pdf, cuts, acoustic_scale=0.1)
+    assert [x.num_frames_ready() for x in decs] == [7, 23, 10] and decs[1].num_indices() == 5
+    assert abs(decs[1].log_likelihood(3, 3) - 0.1 * ref[10, 5]) < 1e-4
+    assert abs(decs[2].log_likelihood(9, 5) - 0.1 * ref[39, 1]) < 1e-4
+
     class Mine(khg.DecodableInterface):  # Python-overridable trampoline (python/csrc/decodable-itf.cc:16-41)
         def log_likelihood(self, frame, index):
             return -1.5
