@@ -228,15 +228,16 @@ khg_status khg_model_info(const khg_model *m, int32_t *dim, int32_t *num_pdfs, i
 khg_status khg_model_dense_kernel(const khg_model *m, int32_t *kernel) {
   KHG_REQUIRE(m && kernel, "null argument");
   if (m->kernel == KHG_KERNEL_SIMT || !m->tc.ready) *kernel = KHG_KERNEL_SIMT;
-  else if (m->kernel == KHG_KERNEL_TCGEN05 || !m->tc.f16_ready) *kernel = KHG_KERNEL_TCGEN05;
-  else *kernel = KHG_KERNEL_TCGEN05_F16;
+  else if (m->tc.f16_ready && m->kernel != KHG_KERNEL_TCGEN05) *kernel = KHG_KERNEL_TCGEN05_F16;
+  else if (m->tc.tf32_ready) *kernel = KHG_KERNEL_TCGEN05;
+  else *kernel = KHG_KERNEL_SIMT;
   return KHG_OK;
 }
 
 khg_status khg_model_set_kernel(khg_model *m, int32_t kernel) {
   KHG_REQUIRE(m && kernel >= KHG_KERNEL_AUTO && kernel <= KHG_KERNEL_TCGEN05_F16, "bad kernel id");
   if ((kernel == KHG_KERNEL_TCGEN05 || kernel == KHG_KERNEL_TCGEN05_F16) && !tc_supported(m)) {
-    set_error("tcgen05 kernel does not support this model shape (needs 2*dim+1 <= 96 and every pdf <= 240 Gaussians)");
+    set_error("tcgen05 kernel does not support this model shape (needs 2*dim+2 <= 160 for the tf32 split / <= 320 for the fp16 split, and every pdf <= 240 Gaussians)");
     return KHG_ERR_UNSUPPORTED;
   }
   m->kernel = kernel;
@@ -291,26 +292,9 @@ khg_status khg_compute_gconsts(int32_t nmix, int32_t dim, const float *weights,
 }
 
 // ------------------------------------------------------------ likelihoods --
-static khg_status dense_device(khg_model *m, const float *d_feats, int64_t T, float scale,
-                               int layout, float *d_out, int64_t ld) {
-  const bool use_tc = m->kernel != KHG_KERNEL_SIMT && m->tc.ready;
-  const int prec = m->kernel == KHG_KERNEL_TCGEN05 ? 1 : (m->kernel == KHG_KERNEL_TCGEN05_F16 ? 2 : 0);
-  if ((m->kernel == KHG_KERNEL_TCGEN05 || m->kernel == KHG_KERNEL_TCGEN05_F16) && !m->tc.ready) {
-    set_error("tcgen05 kernel requested but its model pack is not built");
-    return KHG_ERR_UNSUPPORTED;
-  }
-  if (use_tc) {
-    if (layout == KHG_PDF_MAJOR) return tc_loglikes(m, d_feats, T, scale, d_out, ld, prec);
-    // frame-major: compute pdf-major into scratch, then transpose
-    int64_t ldt = (T + 3) & ~(int64_t)3;
-    KHG_TRY(m->w_out.reserve(sizeof(float) * (size_t)m->P * ldt));
-    KHG_TRY(tc_loglikes(m, d_feats, T, scale, m->w_out.as<float>(), ldt, prec));
-    dim3 grid(grid_for(T, 32), grid_for(m->P, 32)), block(32, 8);
-    transpose_kernel<<<grid, block, 0, m->stream>>>(m->w_out.as<float>(), m->P, T, ldt, d_out, ld);
-    ++g_launch_count;
-    KHG_CUDA_TRY(cudaGetLastError());
-    return KHG_OK;
-  }
+// fp32 SIMT dense kernel; out[p*sp + t*stt].  gate (optional): see loglikes_simt_kernel.
+static khg_status simt_launch(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t sp,
+                              int64_t stt, const unsigned *gate, float gate_limit) {
   const int D = m->dim;
   size_t smem = sizeof(float) * ((size_t)D * kDenseXP + 4 + 2 * (size_t)D * kSimtChunk);
   if (smem > 220 * 1024) {
@@ -326,17 +310,51 @@ static khg_status dense_device(khg_model *m, const float *d_feats, int64_t T, fl
   int groups = (int)std::min<int64_t>(std::max<int64_t>(1, (4LL * m->sm_count + n_ft - 1) / n_ft), std::max(1, m->P / 4));
   int ppg = (m->P + groups - 1) / groups;
   groups = (m->P + ppg - 1) / ppg;
-  int64_t sp = layout == KHG_PDF_MAJOR ? ld : 1, stt = layout == KHG_PDF_MAJOR ? 1 : ld;
   for (int64_t f0 = 0; f0 < n_ft; f0 += 65535 * 32) {  // gridDim.x is huge, but keep launches bounded
     int64_t nf = std::min<int64_t>(n_ft - f0, 65535LL * 32);
     dim3 grid((unsigned)nf, groups);
     loglikes_simt_kernel<<<grid, 128, smem, m->stream>>>(
         d_feats + f0 * kDenseFrames * D, T - f0 * kDenseFrames, D, m->d_packT, m->d_gconsts, m->d_offsets,
-        m->P, ppg, scale, d_out + f0 * kDenseFrames * stt, sp, stt, m->d_err);
+        m->P, ppg, scale, d_out + f0 * kDenseFrames * stt, sp, stt, m->d_err, gate, gate_limit);
     ++g_launch_count;
   }
   KHG_CUDA_TRY(cudaGetLastError());
   return KHG_OK;
+}
+
+static khg_status dense_device(khg_model *m, const float *d_feats, int64_t T, float scale,
+                               int layout, float *d_out, int64_t ld) {
+  const bool use_tc = m->kernel != KHG_KERNEL_SIMT && m->tc.ready;
+  const int prec = m->kernel == KHG_KERNEL_TCGEN05 ? 1 : (m->kernel == KHG_KERNEL_TCGEN05_F16 ? 2 : 0);
+  if ((m->kernel == KHG_KERNEL_TCGEN05 || m->kernel == KHG_KERNEL_TCGEN05_F16) && !m->tc.ready) {
+    set_error("tcgen05 kernel requested but its model pack is not built");
+    return KHG_ERR_UNSUPPORTED;
+  }
+  if (use_tc) {
+    // the tensor-core kernel writes pdf-major; frame-major goes through scratch + transpose
+    float *dst = d_out;
+    int64_t ldt = ld;
+    if (layout != KHG_PDF_MAJOR) {
+      ldt = (T + 3) & ~(int64_t)3;
+      KHG_TRY(m->w_out.reserve(sizeof(float) * (size_t)m->P * ldt));
+      dst = m->w_out.as<float>();
+    }
+    const unsigned *gate = nullptr;
+    float gate_limit = 0.f;
+    KHG_TRY(tc_loglikes(m, d_feats, T, scale, dst, ldt, prec, &gate, &gate_limit));
+    // shapes the tf32 split cannot take (2*dim+1 > 160): the fp16 split's out-of-range
+    // fall-back is the fp32 SIMT kernel, gated on the same device word
+    if (gate != nullptr) KHG_TRY(simt_launch(m, d_feats, T, scale, dst, ldt, 1, gate, gate_limit));
+    if (layout != KHG_PDF_MAJOR) {
+      dim3 grid(grid_for(T, 32), grid_for(m->P, 32)), block(32, 8);
+      transpose_kernel<<<grid, block, 0, m->stream>>>(dst, m->P, T, ldt, d_out, ld);
+      ++g_launch_count;
+      KHG_CUDA_TRY(cudaGetLastError());
+    }
+    return KHG_OK;
+  }
+  int64_t sp = layout == KHG_PDF_MAJOR ? ld : 1, stt = layout == KHG_PDF_MAJOR ? 1 : ld;
+  return simt_launch(m, d_feats, T, scale, d_out, sp, stt, nullptr, 0.f);
 }
 
 khg_status khg_loglikes_all_pdfs(khg_model *m, const float *feats, int64_t T, int32_t feats_loc,

@@ -64,7 +64,8 @@ constexpr int kSimtChunk = 32;
 // B operand of the dense contraction: row g = [means_invvars(D) | -0.5*inv_vars(D)
 // | gconst | 0-pad] split into TF32 hi and lo parts (3xTF32), K padded to KP.
 struct TcPack {
-  bool ready = false;
+  bool ready = false;       // tile tables built and at least one operand container usable
+  bool tf32_ready = false;  // tf32 operands built (needs 2D+1 <= 160)
   int K = 0;   // 2D+1
   int K8 = 0;  // K rounded up to 8  (UMMA_K for tf32)
   int KP = 0;  // K rounded up to 32 (one 128-byte swizzle atom per 32 floats)
@@ -140,8 +141,11 @@ khg_status tc_pack_build(khg_model *m);
 void tc_pack_free(khg_model *m);
 bool tc_supported(const khg_model *m);
 // out is pdf-major: out[p*ld + t]
+// *simt_gate (out): non-NULL when the caller must also launch the fp32 SIMT kernel gated on
+// that device word (fp16-only shapes whose features may be out of range).
 khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale,
-                       float *d_out, int64_t ld_out, int precision);
+                       float *d_out, int64_t ld_out, int precision, const unsigned **simt_gate,
+                       float *gate_limit);
 }  // namespace khg
 
 #endif  // KHG_INTERNAL_H_

@@ -127,7 +127,11 @@ loglikes_simt_kernel(const float *__restrict__ feats, int64_t T, int D,
                      const float *__restrict__ packT, const float *__restrict__ gconsts,
                      const int32_t *__restrict__ offsets, int P, int pdfs_per_group,
                      float scale, float *__restrict__ out, int64_t stride_p,
-                     int64_t stride_t, int *__restrict__ err) {
+                     int64_t stride_t, int *__restrict__ err, const unsigned *__restrict__ gate,
+                     float gate_limit) {
+  // gate != NULL: this launch is the fall-back of the fp16-split tensor-core kernel and runs
+  // only when the call's features are outside fp16's range (decided on the device)
+  if (gate != nullptr && __uint_as_float(*gate) <= gate_limit) return;
   extern __shared__ float smem[];
   float *xs = smem;                       // D x 257
   float *ms = smem + (((size_t)D * kDenseXP + 3) & ~(size_t)3);  // 2 x D x 32, 16-byte aligned

@@ -630,11 +630,12 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 }
 
 // ------------------------------------------------------------------ host side --
-bool tc_supported(const khg_model *m) {
-  int K = 2 * m->dim + 1;
-  int nch = (K + Elem<false>::kChunkK - 1) / Elem<false>::kChunkK;
-  return nch <= kMaxChunks && m->max_gp <= kTileN;
+static bool tc_shape_ok(const khg_model *m, bool f16) {
+  const int K = 2 * m->dim + 2;  // feature columns + gconst + its residual
+  const int ck = f16 ? Elem<true>::kChunkK : Elem<false>::kChunkK;
+  return (K + ck - 1) / ck <= kMaxChunks && m->max_gp <= kTileN;
 }
+bool tc_supported(const khg_model *m) { return tc_shape_ok(m, false) || tc_shape_ok(m, true); }
 
 void tc_pack_free(khg_model *m) {
   TcPack &t = m->tc;
@@ -649,7 +650,7 @@ void tc_pack_free(khg_model *m) {
   t.ascale = nullptr;
   t.gate = nullptr;
   t.tile_g0 = t.tile_p0 = nullptr;
-  t.ready = t.f16_ready = false;
+  t.ready = t.f16_ready = t.tf32_ready = false;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -816,21 +817,24 @@ khg_status tc_pack_build(khg_model *m) {
       t.dead_pdf = all_dead;
     }
   }
-  KHG_CUDA_TRY(cudaMalloc(&t.bhi, sizeof(float) * (size_t)t.rows * t.KP));
-  KHG_CUDA_TRY(cudaMalloc(&t.blo, sizeof(float) * (size_t)t.rows * t.KP));
   KHG_CUDA_TRY(cudaMalloc(&t.tile_g0, sizeof(int32_t) * t.n_tiles));
   KHG_CUDA_TRY(cudaMalloc(&t.tile_p0, sizeof(int32_t) * (t.n_tiles + 1)));
   KHG_CUDA_TRY(cudaMemcpyAsync(t.tile_g0, t.h_tile_g0.data(), sizeof(int32_t) * t.n_tiles, cudaMemcpyHostToDevice, m->stream));
   KHG_CUDA_TRY(cudaMemcpyAsync(t.tile_p0, t.h_tile_p0.data(), sizeof(int32_t) * (t.n_tiles + 1), cudaMemcpyHostToDevice, m->stream));
-  size_t total = (size_t)t.rows * t.KP;
-  tc_pack_kernel<<<(unsigned)std::min<size_t>(2048, (total + 255) / 256), 256, 0, m->stream>>>(G, D, t.KP, t.rows, m->d_miv, m->d_iv, m->d_gconsts, t.bhi, t.blo);
-  ++g_launch_count;
-  KHG_CUDA_TRY(cudaGetLastError());
-  KHG_TRY(make_map(&t.map_hi, t.bhi, t.KP, t.rows, false));
-  KHG_TRY(make_map(&t.map_lo, t.blo, t.KP, t.rows, false));
+  if (tc_shape_ok(m, false)) {
+    KHG_CUDA_TRY(cudaMalloc(&t.bhi, sizeof(float) * (size_t)t.rows * t.KP));
+    KHG_CUDA_TRY(cudaMalloc(&t.blo, sizeof(float) * (size_t)t.rows * t.KP));
+    size_t total = (size_t)t.rows * t.KP;
+    tc_pack_kernel<<<(unsigned)std::min<size_t>(2048, (total + 255) / 256), 256, 0, m->stream>>>(G, D, t.KP, t.rows, m->d_miv, m->d_iv, m->d_gconsts, t.bhi, t.blo);
+    ++g_launch_count;
+    KHG_CUDA_TRY(cudaGetLastError());
+    KHG_TRY(make_map(&t.map_hi, t.bhi, t.KP, t.rows, false));
+    KHG_TRY(make_map(&t.map_lo, t.blo, t.KP, t.rows, false));
+    t.tf32_ready = true;
+  }
   KHG_CUDA_TRY(cudaStreamSynchronize(m->stream));
-  t.ready = true;
-  KHG_TRY(tc_pack_build_f16(m));
+  if (tc_shape_ok(m, true)) KHG_TRY(tc_pack_build_f16(m));
+  t.ready = t.tf32_ready || t.f16_ready;
   return KHG_OK;
 }
 
@@ -904,8 +908,10 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
 // precision: 0 = automatic (fp16 split when the model fits and, decided on the device per
 // call, the features fit; tf32 split otherwise), 1 = force the tf32 split, 2 = force fp16.
 khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t ld_out,
-                       int precision) {
+                       int precision, const unsigned **simt_gate, float *gate_limit) {
   TcPack &t = m->tc;
+  *simt_gate = nullptr;
+  *gate_limit = kF16FeatLimit;
   if (!t.ready) {
     set_error("tcgen05 model pack not built");
     return KHG_ERR_UNSUPPORTED;
@@ -918,6 +924,10 @@ khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scal
     set_error("the fp16-split tensor-core path does not fit this model (parameter range or -inf gconsts)");
     return KHG_ERR_UNSUPPORTED;
   }
+  if (precision == 1 && !t.tf32_ready) {
+    set_error("the tf32-split tensor-core path does not fit this model (2*dim+2 > 160)");
+    return KHG_ERR_UNSUPPORTED;
+  }
   if (precision == 1 || !t.f16_ready) return tc_launch<false>(m, d_feats, T, scale, d_out, ld_out, nullptr, 0);
   if (precision == 2) return tc_launch<true>(m, d_feats, T, scale, d_out, ld_out, nullptr, 0);
   // automatic: one pass over the features finds max |x * 2^-k|; both kernels are launched and
@@ -928,7 +938,9 @@ khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scal
       d_feats, n, m->dim, t.ascale, t.gate);
   ++g_launch_count;
   KHG_TRY(tc_launch<true>(m, d_feats, T, scale, d_out, ld_out, t.gate, 0));
-  return tc_launch<false>(m, d_feats, T, scale, d_out, ld_out, t.gate, 1);
+  if (t.tf32_ready) return tc_launch<false>(m, d_feats, T, scale, d_out, ld_out, t.gate, 1);
+  *simt_gate = t.gate;  // no tf32 operands for this shape: the caller launches the gated SIMT kernel
+  return KHG_OK;
 }
 
 }  // namespace khg

@@ -266,3 +266,32 @@ def test_tc_length_classes_and_kernel_query(oracle):
     assert dm.dense_kernel() == 1
     with pytest.raises(RuntimeError, match="does not support"):
         dm.set_kernel(TC)
+
+
+def test_tc_yesno_shape_dim80_fp16_only(oracle):
+    """BASELINE configs[0]: the yesno recipe feeds 80-dim fbank (reference
+    egs/yesno/local/compute_fbank_yesno.py:32) into 11 pdfs growing to ~1000 Gaussians.
+    2*80+2 columns do not fit the tf32 operand tile, they do fit the fp16 one; out-of-range
+    calls fall back to the fp32 SIMT kernel through the same device gate."""
+    model, means, vars_ = ko.make_synthetic_model(80, 11, 1000, oracle=oracle)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, 700)
+    ref, bad = oracle.loglikes_all_pdfs(model, feats)
+    assert bad == 0
+    auto = _one(model, AUTO)
+    assert auto.dense_kernel() == TC_F16
+    _check(auto.loglikes_all_pdfs(feats), ref)
+    _check(_one(model, TC_F16).loglikes_all_pdfs(feats, layout=1).T, ref)
+    from kaldi_hmm_gmm_b200 import DeviceModel
+
+    dm = DeviceModel(model.dim, model.offsets)
+    dm.upload(model.weights, model.means_invvars, model.inv_vars)
+    with pytest.raises(RuntimeError, match="tf32"):
+        dm.set_kernel(TC)
+        dm.loglikes_all_pdfs(feats[:10])
+    big = feats[:300].copy()
+    big[3] *= 500.0
+    ref_big, _ = oracle.loglikes_all_pdfs(model, big)
+    got = auto.loglikes_all_pdfs(big)
+    assert np.isfinite(got).all()
+    assert (np.abs(got - ref_big) / np.maximum(np.abs(ref_big), 1.0)).max() < 1e-4
+    np.testing.assert_array_equal(got[:256], _one(model, SIMT).loglikes_all_pdfs(big)[:256])
