@@ -264,7 +264,7 @@ void khg_model_destroy(khg_model *m) {
   cudaFree(m->d_grp_start); cudaFree(m->d_pack8); cudaFree(m->d_gc8);
   for (Buf *b : {&m->w_feats, &m->w_ids, &m->w_wts, &m->w_out, &m->w_pf, &m->w_keys, &m->w_vals_in,
                  &m->w_vals_out, &m->w_cub, &m->w_starts, &m->w_item_start, &m->w_tot, &m->w_tid,
-                 &m->w_tid2pdf, &m->w_trans, &m->w_keys_out})
+                 &m->w_tid2pdf, &m->w_trans, &m->w_keys_out, &m->w_sub, &m->w_full})
     b->release();
   for (int i = 0; i < 2; ++i) {
     m->pin_feats[i].release(); m->pin_ids[i].release(); m->pin_wts[i].release();
@@ -392,6 +392,43 @@ khg_status khg_loglikes_all_pdfs(khg_model *m, const float *feats, int64_t T, in
       else
         KHG_CUDA_TRY(cudaMemcpy2DAsync(out + t0 * ld_out, sizeof(float) * ld_out, d_o, sizeof(float) * ldd, sizeof(float) * m->P, n, cudaMemcpyDeviceToHost, m->stream));
     }
+    KHG_TRY(sync_check(m));
+  }
+  return KHG_OK;
+}
+
+khg_status khg_loglikes_pdf_subset(khg_model *m, const float *feats, int64_t T, int32_t feats_loc, const int32_t *pdf_subset,
+                                   int32_t n_subset, float scale, float *out, int64_t ld_out, int32_t out_loc) {
+  NvtxRange nvtx_range("khg_loglikes_pdf_subset");
+  KHG_REQUIRE(m && m->uploaded, "model not uploaded");
+  KHG_REQUIRE(T >= 0 && n_subset >= 0 && (T == 0 || n_subset == 0 || (feats && out && pdf_subset)), "null buffer");
+  KHG_REQUIRE(ld_out >= T, "ld_out too small");
+  if (T == 0 || n_subset == 0) return KHG_OK;
+  const int D = m->dim;
+  cudaStream_t st = m->stream;
+  KHG_TRY(m->w_sub.reserve(sizeof(int32_t) * n_subset));
+  KHG_CUDA_TRY(cudaMemcpyAsync(m->w_sub.p, pdf_subset, sizeof(int32_t) * n_subset, cudaMemcpyHostToDevice, st));
+  const int64_t chunk = std::max<int64_t>(256, std::min<int64_t>(T, (int64_t)(512e6 / (4.0 * m->P))) & ~(int64_t)255);
+  for (int64_t t0 = 0; t0 < T; t0 += chunk) {
+    const int64_t n = std::min(chunk, T - t0);
+    const float *d_f = nullptr;
+    KHG_TRY(stage_in(m, m->w_feats, feats + t0 * D, (size_t)n * D, feats_loc, &d_f));
+    const int64_t ldf = (n + 3) & ~(int64_t)3;
+    KHG_TRY(m->w_full.reserve(sizeof(float) * (size_t)m->P * ldf));
+    KHG_TRY(dense_device(m, d_f, n, scale, KHG_PDF_MAJOR, m->w_full.as<float>(), ldf));
+    float *d_o = out + t0;
+    int64_t ldo = ld_out;
+    if (out_loc == KHG_HOST) {
+      KHG_TRY(m->w_pf.reserve(sizeof(float) * (size_t)n_subset * ldf));
+      d_o = m->w_pf.as<float>();
+      ldo = ldf;
+    }
+    dim3 grid((unsigned)std::min<int64_t>(64, (n + 255) / 256), n_subset);
+    gather_rows_kernel<<<grid, 256, 0, st>>>(m->w_full.as<float>(), ldf, m->w_sub.as<int32_t>(), n_subset, n, d_o, ldo, m->P, m->d_err);
+    ++g_launch_count;
+    KHG_CUDA_TRY(cudaGetLastError());
+    if (out_loc == KHG_HOST)
+      KHG_CUDA_TRY(cudaMemcpy2DAsync(out + t0, sizeof(float) * ld_out, d_o, sizeof(float) * ldo, sizeof(float) * n, n_subset, cudaMemcpyDeviceToHost, st));
     KHG_TRY(sync_check(m));
   }
   return KHG_OK;
@@ -538,6 +575,8 @@ void khg_stats_destroy(khg_stats *s) {
   delete s;
 }
 
+constexpr int64_t kDirectMaxFrames = 2048;  // at or below this the one-launch direct kernel is used
+
 // Bucket + accumulate for device-resident inputs; frames processed in slabs so the
 // sort workspace stays bounded.
 static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, int64_t T,
@@ -548,6 +587,27 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
   }
   const int D = m->dim, P = m->P;
   cudaStream_t st = m->stream;
+  if (T <= kDirectMaxFrames && m->max_gp <= kDirectMaxGp) {
+    // small batch (one utterance): one launch, no bucketing
+    DirectArgs da;
+    da.feats = d_feats; da.ids = d_ids; da.weights = d_w; da.offsets = m->d_offsets;
+    da.miv = m->d_miv; da.iv = m->d_iv; da.gconsts = m->d_gconsts;
+    da.occ = s->buf;
+    da.mean = s->off_mean >= 0 ? s->buf + s->off_mean : nullptr;
+    da.var = s->off_var >= 0 ? s->buf + s->off_var : nullptr;
+    da.totals = s->buf + s->off_tot;
+    da.call_like = d_call_like;
+    da.per_frame = d_pf;
+    da.err = m->d_err;
+    da.T = (int)T; da.P = P; da.D = D;
+    const size_t shm = sizeof(float) * kDirectWarps * (size_t)(D + kDirectMaxGp);
+    if (shm <= 48 * 1024) {
+      stats_direct_kernel<<<grid_for(T, kDirectWarps), 32 * kDirectWarps, shm, st>>>(da);
+      ++g_launch_count;
+      KHG_CUDA_TRY(cudaGetLastError());
+      return KHG_OK;
+    }
+  }
   const int64_t slab = 1 << 23;
   int end_bit = 1;
   while ((1 << end_bit) < P) ++end_bit;

@@ -123,6 +123,7 @@ struct khg_model {
   khg::Buf w_keys, w_keys_out, w_vals_in, w_vals_out, w_cub;       // bucketing (K2)
   khg::Buf w_starts, w_item_start, w_tot;              // per-pdf starts, work items, totals
   khg::Buf w_tid, w_tid2pdf, w_trans;                  // tid path
+  khg::Buf w_sub, w_full;                              // pdf-subset gather
   khg::Buf pin_feats[2], pin_ids[2], pin_wts[2];       // pinned staging for estep(HOST)
   khg::Buf w_efeats[2], w_eids[2], w_ewts[2];
 };

@@ -623,6 +623,110 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// K3-direct: the same per-frame arithmetic for SMALL batches (one utterance): no bucketing,
+// one warp per frame, lanes over feature dimensions.  It exists for launch latency — the
+// reference's script calls gmm-acc-stats-ali once per utterance (scripts/gmm_acc_stats_ali.py)
+// — where the sort + work-item pipeline of the batched path costs ~10 launches.  Every
+// posterior-weighted product is rounded to fp32, cast to double and added with an fp64
+// atomic: exactly csrc/mle-diag-gmm.cc:131-141.
+// ---------------------------------------------------------------------------
+constexpr int kDirectMaxGp = 256;   // Gaussians per pdf this path accepts
+constexpr int kDirectWarps = 8;
+
+struct DirectArgs {
+  const float *feats;       // T x D
+  const int32_t *ids;       // T pdf ids
+  const float *weights;     // T or NULL
+  const int32_t *offsets;   // P+1
+  const float *miv, *iv, *gconsts;  // packed model, row-major
+  double *occ, *mean, *var, *totals, *call_like;
+  float *per_frame;
+  int *err;
+  int T, P, D;
+};
+
+__global__ void __launch_bounds__(32 * kDirectWarps) stats_direct_kernel(DirectArgs a) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * kDirectWarps + warp;
+  if (t >= a.T) return;
+  const int D = a.D;
+  float *xs = smem + (size_t)warp * (D + kDirectMaxGp);  // this warp's frame
+  float *ll = xs + D;                                      // and its log-likes / posteriors
+  int p = a.ids[t];
+  if (p < 0 || p >= a.P) {  // AccumulateForGmm asserts the range (csrc/mle-am-diag-gmm.cc:44)
+    if (lane == 0) atomicOr(a.err, ERR_BAD_INDEX);
+    return;
+  }
+  const int g0 = a.offsets[p], ng = a.offsets[p + 1] - g0;
+  const float w = a.weights ? a.weights[t] : 1.0f;
+  const float *x = a.feats + (size_t)t * D;
+  for (int d = lane; d < D; d += 32) xs[d] = x[d];
+  __syncwarp();
+  for (int g = 0; g < ng; ++g) {
+    const float *m = a.miv + (size_t)(g0 + g) * D, *v = a.iv + (size_t)(g0 + g) * D;
+    float sa = 0.f, sb = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float xv = xs[d];
+      sa = fmaf(m[d], xv, sa);
+      sb = fmaf(v[d], xv * xv, sb);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+      sa += __shfl_xor_sync(0xffffffffu, sa, off);
+      sb += __shfl_xor_sync(0xffffffffu, sb, off);
+    }
+    if (lane == 0) ll[g] = (a.gconsts[g0 + g] + sa) - 0.5f * sb;  // csrc/diag-gmm.cc:174-175
+  }
+  __syncwarp();
+  // Softmax (csrc/eigen.cc:20-32): lanes over Gaussians
+  float mx = -CUDART_INF_F;
+  for (int g = lane; g < ng; g += 32) mx = fmaxf(mx, ll[g]);
+  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  float s = 0.f;
+  for (int g = lane; g < ng; g += 32) {
+    const float e = expf(ll[g] - mx);
+    ll[g] = e;
+    s += e;
+  }
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  const float lse = logf(s) + mx;
+  for (int g = lane; g < ng; g += 32) ll[g] = (ll[g] / s) * w;  // post *= weight (csrc/mle-diag-gmm.cc:153)
+  __syncwarp();
+  if (lane == 0) {
+    if (!finite_f(lse)) atomicOr(a.err, ERR_NONFINITE);
+    if (a.per_frame) a.per_frame[t] = lse;
+    const double L = (double)(lse * w);  // csrc/mle-am-diag-gmm.cc:49-50
+    atomicAdd(&a.totals[0], L);
+    atomicAdd(&a.totals[1], (double)w);
+    if (a.call_like) atomicAdd(a.call_like, L);
+  }
+  for (int g = lane; g < ng; g += 32) atomicAdd(&a.occ[g0 + g], (double)ll[g]);
+  if (a.mean) {
+    for (int g = 0; g < ng; ++g) {
+      const float pg = ll[g];
+      for (int d = lane; d < D; d += 32) {
+        const float xv = xs[d];
+        atomicAdd(&a.mean[(size_t)(g0 + g) * D + d], (double)__fmul_rn(pg, xv));
+        if (a.var) atomicAdd(&a.var[(size_t)(g0 + g) * D + d], (double)__fmul_rn(pg, __fmul_rn(xv, xv)));
+      }
+    }
+  }
+}
+
+// rows of a pdf-major block: dst[i][t] = src[subset[i]][t]
+__global__ void gather_rows_kernel(const float *__restrict__ src, int64_t ld_src, const int32_t *__restrict__ subset,
+                                   int n, int64_t T, float *__restrict__ dst, int64_t ld_dst, int P, int *err) {
+  const int i = blockIdx.y;
+  const int p = subset[i];
+  if (p < 0 || p >= P) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(err, ERR_BAD_INDEX);
+    return;
+  }
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x)
+    dst[i * ld_dst + t] = src[p * ld_src + t];
+}
+
 // AccumDiagGmm::AccumulateFromPosteriors (csrc/mle-diag-gmm.cc:123-143) for T frames of
 // one pdf with caller-supplied posteriors (T x ng).  One thread per (g, k) pair.
 __global__ void acc_from_post_kernel(const float *__restrict__ feats, int64_t T, int D,

@@ -40,6 +40,7 @@ SYMBOLS = [
     ("khg_model_destroy", None, [_vp]),
     ("khg_compute_gconsts", _i32, [_i32, _i32, _vp, _vp, _vp, _vp, C.POINTER(_i32)]),
     ("khg_loglikes_all_pdfs", _i32, [_vp, _vp, _i64, _i32, _f32, _i32, _vp, _i64, _i32]),
+    ("khg_loglikes_pdf_subset", _i32, [_vp, _vp, _i64, _i32, _vp, _i32, _f32, _vp, _i64, _i32]),
     ("khg_pdf_loglikes", _i32, [_vp, _i32, _vp, _i64, _i32, _vp]),
     ("khg_pdf_posteriors", _i32, [_vp, _i32, _vp, _i64, _i32, _vp, _vp]),
     ("khg_stats_create", _i32, [_vp, _u16, C.POINTER(_vp)]),

@@ -106,6 +106,21 @@ class DeviceModel:
         A.check(A.lib().khg_loglikes_all_pdfs(self._h, fp, T, floc, scale, layout, op, ld, oloc))
         return out
 
+    def loglikes_pdf_subset(self, feats, pdf_subset, scale: float = 1.0):
+        """(len(pdf_subset), T) pdf-major block of the listed pdfs only (host or device buffers)."""
+        fp, floc = A.ptr(feats, np.float32)
+        T = int(feats.shape[0])
+        sub = np.ascontiguousarray(pdf_subset, np.int32)
+        if floc == A.KHG_DEVICE:
+            import torch
+
+            out = torch.empty((sub.size, T), dtype=torch.float32, device=feats.device)
+        else:
+            out = np.empty((sub.size, T), np.float32)
+        op, oloc = A.ptr(out, np.float32)
+        A.check(A.lib().khg_loglikes_pdf_subset(self._h, fp, T, floc, sub.ctypes.data, sub.size, scale, op, T, oloc))
+        return out
+
     def pdf_loglikes(self, pdf: int, feats: np.ndarray) -> np.ndarray:
         feats = np.ascontiguousarray(np.atleast_2d(feats), np.float32)
         if feats.shape[1] != self.dim:

@@ -415,3 +415,49 @@ def test_two_gpu_nccl_allreduce_of_stats(tmp_path):
     s.close()
     mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), f"ok{r}")) for r in range(2))
+
+
+def test_direct_small_batch_path_matches_bucketed_path(oracle):
+    """T <= 2048 takes the one-launch direct kernel, larger calls the bucketed kernels: the
+    same frames through either path give the same statistics; both match the oracle."""
+    from kaldi_hmm_gmm_b200 import DeviceStats
+
+    model, means, vars_ = ko.make_synthetic_model(40, 64, 600, oracle=oracle)
+    T = 4000
+    feats, pdf = ko.make_synthetic_frames(model, means, vars_, T)
+    fw = np.random.default_rng(9).random(T).astype(np.float32)
+    dm, _ = _device_model(model)
+    big = DeviceStats(dm)
+    pf_big = np.empty(T, np.float32)
+    tot_big = big.acc_stats_ali(feats, pdf, fw, pf_big)            # bucketed
+    small = DeviceStats(dm)
+    pf_small = np.empty(T, np.float32)
+    tot_small = 0.0
+    for a in range(0, T, 500):                                      # direct, utterance-sized calls
+        tot_small += small.acc_stats_ali(feats[a:a + 500], pdf[a:a + 500], fw[a:a + 500], pf_small[a:a + 500])
+    ref = oracle.acc_stats_ali(model, feats, pdf, fw)
+    gb, gs = big.download(), small.download()
+    _assert_stats(gb, ref, T)
+    _assert_stats(gs, ref, T)
+    _assert_ll(pf_small, ref["per_frame"])
+    np.testing.assert_allclose(pf_small, pf_big, rtol=1e-5, atol=1e-4)
+    for k in ("occ", "mean", "var"):
+        np.testing.assert_allclose(gs[k], gb[k], rtol=1e-5, atol=1e-6 * np.abs(gb[k]).max())
+    assert abs(tot_small - tot_big) <= 1e-6 * abs(tot_big)
+
+
+def test_pdf_subset_block(oracle, small):
+    """khg_loglikes_pdf_subset: only the pdfs on an utterance's graph travel to the host."""
+    import torch
+
+    model, feats, _ = small
+    dm, _ = _device_model(model)
+    ref, _ = oracle.loglikes_all_pdfs(model, feats, scale=0.5)
+    sub = np.array([7, 0, 12, 3, 3], np.int32)
+    got = dm.loglikes_pdf_subset(feats, sub, scale=0.5)
+    assert got.shape == (5, feats.shape[0])
+    _assert_ll(got, ref[:, sub].T)
+    got_d = dm.loglikes_pdf_subset(torch.from_numpy(feats).cuda(), sub, scale=0.5)
+    _assert_ll(got_d.cpu().numpy(), ref[:, sub].T)
+    with pytest.raises(RuntimeError, match="out of range"):
+        dm.loglikes_pdf_subset(feats, np.array([1, model.num_pdfs], np.int32))
