@@ -88,8 +88,9 @@ struct TcPack {
   std::vector<int32_t> h_tile_g0, h_tile_p0;
   // epilogue tables: the pdfs (segments) of a tile grouped by their number of Gaussians
   int32_t *tile_cls0 = nullptr;  // device, n_tiles+1
-  void *cls = nullptr;           // device int4 {len, seg_begin, seg_end, 0} per class
-  uint32_t *seg = nullptr;       // device, P: column | (pdf - tile_p0) << 16, class-major
+  void *cls = nullptr;           // device int4 {len, segments per epilogue group (4 x 8 bits), 0, 0} per class
+  int32_t *grp_seg0 = nullptr;   // device, 4*n_tiles+1: start in seg[] of the list of (tile, epilogue group)
+  uint32_t *seg = nullptr;       // device, P: column | (pdf - tile_p0) << 16; per (tile, group), class order
   bool dead_pdf = false;         // some pdf has only -inf gconsts: every call must fail like the reference
 };
 

@@ -58,9 +58,9 @@ template <bool F16> struct Elem {
 constexpr int kAChunkBytes = kTileM * 128;   // 16384
 constexpr int kBStageBytes = kTileN * 128;   // 30720 (multiple of 1024)
 constexpr int kMaxChunks = 5;       // 128-byte K chunks per operand row held in smem
-constexpr int kEpiGroups = 4;       // epilogue warpgroups (4 warps each, one per TMEM lane quadrant)
+constexpr int kEpiGroups = 6;       // epilogue warpgroups (4 warps each, one per TMEM lane quadrant); <= 8
 constexpr int kBuilderThreads = 64;
-constexpr int kEpiWarps = 4 * kEpiGroups;      // warps 0..15: epilogue (TMEM lane quadrant = warp % 4)
+constexpr int kEpiWarps = 4 * kEpiGroups;      // warps 0..4*kEpiGroups-1: epilogue (TMEM lane quadrant = warp % 4)
 constexpr int kBuilderWarp0 = kEpiWarps;        // warps 16-17: A builders
 constexpr int kProducerWarp = kEpiWarps + 2;    // warp 18: TMA producer
 constexpr int kMmaWarp = kEpiWarps + 3;         // warp 19: MMA issuer (+ TMEM alloc); the warp scheduler
@@ -103,6 +103,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
       : "memory");
+}
+// One lane of a converged warp.  The MMA-issuing and TMA-issuing warps run their loops with all 32
+// lanes (warp-uniform control flow: counters and descriptors then live in uniform registers and
+// UTCHMMA / UTMALDG take them directly); a loop run by `if (lane == 0)` makes the compiler wrap
+// every such instruction in a register-to-uniform "waterfall" loop (~165 cycles per MMA measured
+// with tools/mma_rate.cu, against the 120-cycle floor of a 128x240x16 MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+  return p != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -148,6 +158,18 @@ __device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, TReg16 &t) {
       : "r"(taddr)
       : "memory");
 }
+// Same load under a warp-uniform predicate (no branch: the instruction keeps its place in the
+// schedule between the two halves of the segment arithmetic).
+__device__ __forceinline__ void tc_ld16_issue_if(uint32_t taddr, TReg16 &t, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %17, 0;\n\t"
+      "@p tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t}"
+      : "=r"(t.r[0]), "=r"(t.r[1]), "=r"(t.r[2]), "=r"(t.r[3]), "=r"(t.r[4]), "=r"(t.r[5]), "=r"(t.r[6]), "=r"(t.r[7]),
+        "=r"(t.r[8]), "=r"(t.r[9]), "=r"(t.r[10]), "=r"(t.r[11]), "=r"(t.r[12]), "=r"(t.r[13]), "=r"(t.r[14]), "=r"(t.r[15])
+      : "r"(taddr), "r"((uint32_t)pred)
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld16_wait(TReg16 &t) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(t.r[0]), "+r"(t.r[1]), "+r"(t.r[2]), "+r"(t.r[3]), "+r"(t.r[4]), "+r"(t.r[5]), "+r"(t.r[6]), "+r"(t.r[7]),
@@ -172,34 +194,48 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 // Max-subtracted log-sum-exp (csrc/eigen.cc:14-18) of the first L of 16 accumulator
-// columns held in registers; returns the max through M.  L is a compile-time constant so
-// that no issue slot is spent on masked-off columns.
+// columns held in registers, in two parts so that the TMEM load of the NEXT segment can be
+// issued into the same registers between them.  L is a compile-time constant so that no
+// issue slot is spent on masked-off columns.
+//   part 1: M = max, e[i] = x[i]*log2(e) - M*log2(e)  (after it the loaded registers are dead)
+//   part 2: M + ln(sum 2^e[i])
 template <int L>
-__device__ __forceinline__ float seg_lse(const TReg16 &t, float &M) {
-  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
-  if (L == 1) {
-    M = __uint_as_float(t.r[0]);
-    return M;
-  }
-  float m = __uint_as_float(t.r[0]);
+struct SegLse {
+  static constexpr int kPairs = L / 2;
+  float2 e2[kPairs > 0 ? kPairs : 1];
+  float e1;
+  float M;
+  __device__ __forceinline__ void part1(const TReg16 &t) {
+    constexpr float kLog2e = 1.4426950408889634f;
+    float m = __uint_as_float(t.r[0]);
 #pragma unroll
-  for (int i = 1; i < L; ++i) m = fmaxf(m, __uint_as_float(t.r[i]));
-  const float ml = m * kLog2e;
-  // packed fp32x2 math (FFMA2 / FADD2 on sm_100): one issue slot per two columns
-  const float2 k2 = make_float2(kLog2e, kLog2e), nm2 = make_float2(-ml, -ml);
-  float2 s2;
+    for (int i = 1; i < L; ++i) m = fmaxf(m, __uint_as_float(t.r[i]));
+    M = m;
+    if (L == 1) return;
+    const float ml = m * kLog2e;
+    // packed fp32x2 math (FFMA2 / FADD2 on sm_100): one issue slot per two columns
+    const float2 k2 = make_float2(kLog2e, kLog2e), nm2 = make_float2(-ml, -ml);
 #pragma unroll
-  for (int i = 0; i + 1 < L; i += 2) {
-    float2 a = __ffma2_rn(make_float2(__uint_as_float(t.r[i]), __uint_as_float(t.r[i + 1])), k2, nm2);
-    a.x = fast_exp2(a.x);
-    a.y = fast_exp2(a.y);
-    s2 = i == 0 ? a : __fadd2_rn(s2, a);
+    for (int i = 0; i < kPairs; ++i)
+      e2[i] = __ffma2_rn(make_float2(__uint_as_float(t.r[2 * i]), __uint_as_float(t.r[2 * i + 1])), k2, nm2);
+    if (L & 1) e1 = fmaf(__uint_as_float(t.r[L - 1]), kLog2e, -ml);
   }
-  float s = s2.x + s2.y;
-  if (L & 1) s += fast_exp2(fmaf(__uint_as_float(t.r[L - 1]), kLog2e, -ml));
-  M = m;
-  return fmaf(fast_log2(s), kLn2, m);
-}
+  __device__ __forceinline__ float part2() {
+    constexpr float kLn2 = 0.6931471805599453f;
+    if (L == 1) return M;
+    float2 s2;
+#pragma unroll
+    for (int i = 0; i < kPairs; ++i) {
+      float2 v = e2[i];
+      v.x = fast_exp2(v.x);
+      v.y = fast_exp2(v.y);
+      s2 = i == 0 ? v : __fadd2_rn(s2, v);
+    }
+    float s = s2.x + s2.y;
+    if (L & 1) s += fast_exp2(e1);
+    return fmaf(fast_log2(s), kLn2, M);
+  }
+};
 
 // Generic LSE of a segment of `len` (> 16) columns at TMEM address taddr: two passes.
 __device__ __forceinline__ float seg_lse_long(uint32_t taddr, int len) {
@@ -225,45 +261,60 @@ __device__ __forceinline__ float seg_lse_long(uint32_t taddr, int len) {
   return fmaf(fast_log2(s), kLn2, m);
 }
 
-// All segments [sb, se) of one length class L <= 16 of the current tile that belong to
-// this epilogue group (eg, eg+4, ...).  The class loop carries no per-segment dispatch:
-// L is a compile-time constant, the TMEM load of the next segment and the descriptor of
-// the one after it are in flight while the current segment is reduced.
+// Epilogue state of one warp inside one accumulator tile.  The warp walks ITS list of
+// segments (pdfs) of the tile, seg[k] for k in [k, n_end), ordered by length class.  Invariant
+// between segments: the TMEM load of segment k (descriptor d) has been issued into t.  A
+// tcgen05.ld -> wait::ld round trip is ~170 cycles (tools/tmem_ld_rate.cu), so the load of
+// segment k+1 is issued as soon as part 1 of segment k has consumed the registers, across class
+// boundaries, and completes under part 2 (exponentials, log, store).
 //   trow  TMEM address of this warp's lane quadrant in the current accumulator buffer
 //   seg   packed segment descriptors: column | (pdf - first pdf of tile) << 16
-//   out_p out + first_pdf_of_tile * ld + t
-// Returns true when a non-finite result was produced (the reference's "Invalid answer").
-// out_b: byte address of out[first pdf of tile][t] — or of a scratch word with ld_bytes = 0
-// for rows beyond T, so that the store needs no predicate.  nan_acc collects r*0 (NaN for a
-// non-finite r): one FFMA instead of a compare/select/or per segment.
+//   out_b byte address of out[first pdf of tile][t] — or of a scratch word with ld_bytes = 0
+//         for rows beyond T, so that the store needs no predicate
+//   nan_acc collects r*0 (NaN for a non-finite r, the reference's "Invalid answer"): one FFMA
+//         instead of a compare/select/or per segment
+struct EpiState {
+  TReg16 t;
+  uint32_t d, dn;   // descriptors of segment k (load in flight) and k+1 (fetched one segment ahead)
+  int k, n_end;
+  uint32_t trow;
+  const uint32_t *seg;
+  char *out_b;
+  uint32_t ld_bytes;
+  float scale, nan_acc;
+};
+
 template <int L>
-__device__ __forceinline__ void epi_class(uint32_t trow, const uint32_t *__restrict__ seg, char *out_b,
-                                          uint32_t ld_bytes, float scale, float &nan_acc, int sb, int se, int eg) {
-  int i = sb + eg;
-  if (i >= se) return;
-  uint32_t d = __ldg(seg + i);
+__device__ __forceinline__ void epi_class(EpiState &e, int ke) {
 #pragma unroll 1
-  for (; i < se; i += kEpiGroups) {
-    TReg16 t;
-    tc_ld16_issue(trow + (d & 0xffffu), t);
-    const uint32_t dcur = d;
-    if (i + kEpiGroups < se) d = __ldg(seg + i + kEpiGroups);  // next descriptor, under the TMEM latency
-    tc_ld16_wait(t);
-    float M;
-    const float r = seg_lse<L>(t, M);
-    nan_acc = fmaf(r, 0.f, nan_acc);
-    *reinterpret_cast<float *>(out_b + (uint64_t)(dcur >> 16) * ld_bytes) = scale * r;
+  for (; e.k < ke; ++e.k) {
+    const uint32_t dcur = e.d, dnext = e.dn;
+    const bool more = e.k + 1 < e.n_end;
+    if (e.k + 2 < e.n_end) e.dn = __ldg(e.seg + e.k + 2);  // two ahead: its latency never gates the TMEM load
+    tc_ld16_wait(e.t);
+    SegLse<L> lse;
+    lse.part1(e.t);
+    // unconditional (a branch here makes ptxas sink the load below part 2): after the last
+    // segment of the tile it re-reads the current columns and the result is never used
+    tc_ld16_issue(e.trow + ((more ? dnext : dcur) & 0xffffu), e.t);
+    const float r = lse.part2();
+    e.nan_acc = fmaf(r, 0.f, e.nan_acc);
+    *reinterpret_cast<float *>(e.out_b + (uint64_t)(dcur >> 16) * e.ld_bytes) = e.scale * r;
+    e.d = dnext;
   }
 }
 
-__device__ __forceinline__ void epi_class_long(uint32_t trow, const uint32_t *__restrict__ seg, char *out_b,
-                                               uint32_t ld_bytes, float scale, float &nan_acc, int sb, int se, int eg,
-                                               int len) {
-  for (int i = sb + eg; i < se; i += kEpiGroups) {
-    const uint32_t d = __ldg(seg + i);
-    const float r = seg_lse_long(trow + (d & 0xffffu), len);
-    nan_acc = fmaf(r, 0.f, nan_acc);
-    *reinterpret_cast<float *>(out_b + (uint64_t)(d >> 16) * ld_bytes) = scale * r;
+__device__ __forceinline__ void epi_class_long(EpiState &e, int ke, int len) {
+  for (; e.k < ke; ++e.k) {
+    const uint32_t dcur = e.d, dnext = e.dn;
+    const bool more = e.k + 1 < e.n_end;
+    if (e.k + 2 < e.n_end) e.dn = __ldg(e.seg + e.k + 2);
+    tc_ld16_wait(e.t);  // the pending 16-column load is not used by the two-pass form
+    const float r = seg_lse_long(e.trow + (dcur & 0xffffu), len);
+    tc_ld16_issue(e.trow + ((more ? dnext : dcur) & 0xffffu), e.t);
+    e.nan_acc = fmaf(r, 0.f, e.nan_acc);
+    *reinterpret_cast<float *>(e.out_b + (uint64_t)(dcur >> 16) * e.ld_bytes) = e.scale * r;
+    e.d = dnext;
   }
 }
 
@@ -394,8 +445,9 @@ struct TcArgs {
   const int32_t *tile_g0;  // n_tiles
   const int32_t *tile_p0;  // n_tiles+1
   const int32_t *tile_cls0;  // n_tiles+1: range of length classes of a tile
-  const int4 *cls;           // per class: {len, seg_begin, seg_end, 0}
-  const uint32_t *seg;       // per segment: column | (pdf - tile_p0) << 16, grouped by class
+  const int4 *cls;           // per class: {len, segments per epilogue group (4 x 8 bits), 0, 0}
+  const int32_t *grp_seg0;   // kEpiGroups*n_tiles+1: start in seg[] of the list of (tile, epilogue group)
+  const uint32_t *seg;       // per segment: column | (pdf - tile_p0) << 16; per (tile, group), class order
   int n_tiles, n_splits, tiles_per_split;
   int64_t n_items;
   float scale;
@@ -433,7 +485,8 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
   const uint32_t tmem_slot = sBar + 8u * 22;
   volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + (tmem_slot - base));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
 
   if (warp == kMmaWarp) {
     if (lane == 0) {
@@ -466,27 +519,31 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       uint32_t st = 0, ph = 1;  // producer waits on "empty" with the inverted phase
       for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         const int split = (int)(item % a.n_splits);
         const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
         for (int j = j0; j < j1; ++j) {
-          const int g0 = a.tile_g0[j];
+          const int g0 = __shfl_sync(0xffffffffu, __ldg(a.tile_g0 + j), 0);
           for (int c = 0; c < NCH; ++c) {
             for (int hl = 0; hl < 2; ++hl) {
               if (hl == 1 && a.Kc <= c * kChunkK) continue;  // no cross-product step in this chunk
               mbar_wait(b_empty(st), ph);
-              if (a.debug_mode == 3) {  // experiment: MMA rate without operand traffic
-                mbar_arrive(b_full(st));
-              } else {
-                mbar_expect_tx(b_full(st), kBStageBytes);
-                tma_load_2d(sB + st * kBStageBytes, hl ? &map_lo : &map_hi, b_full(st), c * kChunkK, g0);
+              if (leader) {
+                if (a.debug_mode == 3) {  // experiment: MMA rate without operand traffic
+                  mbar_arrive(b_full(st));
+                } else {
+                  mbar_expect_tx(b_full(st), kBStageBytes);
+                  tma_load_2d(sB + st * kBStageBytes, hl ? &map_lo : &map_hi, b_full(st), c * kChunkK, g0);
+                }
               }
+              __syncwarp();
               if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
             }
           }
@@ -495,9 +552,11 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    // One thread; its instruction stream is kept as short as possible (no divisions, 32-bit
-    // descriptor arithmetic): it shares an SM sub-partition with four busy epilogue warps.
-    if (lane == 0) {
+    // All 32 lanes run the loop (uniform control flow, see elect_one); one elected lane issues.
+    // The instruction stream is kept as short as possible (no divisions, 32-bit descriptor
+    // arithmetic): this warp shares an SM sub-partition with four busy epilogue warps.
+    {
+      const bool leader = elect_one();
       uint32_t st = 0, ph = 0, acc_it = 0, a_it = 0;
       const uint32_t a_hi0 = umma_desc_lo(sA_hi), a_lo0 = umma_desc_lo(sA_lo), b0 = umma_desc_lo(sB);
       constexpr uint32_t kAChunkDesc = kAChunkBytes >> 4, kBStageDesc = kBStageBytes >> 4;
@@ -523,13 +582,14 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
               if (a.debug_mode != 2) {  // (2 = experiment: TMA rate without MMAs)
 #pragma unroll 4
                 for (int k = 0; k < nk; ++k) {
-                  tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, accum);
+                  if (leader) tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, accum);
                   accum = 1;
                 }
 #pragma unroll 4
-                for (int k = 0; k < nkc; ++k) tc_mma<F16>(tmem_d, da_lo + 2 * k, db + 2 * k, kIdesc, 1);
+                for (int k = 0; k < nkc; ++k)
+                  if (leader) tc_mma<F16>(tmem_d, da_lo + 2 * k, db + 2 * k, kIdesc, 1);
               }
-              tc_commit(b_empty(st));
+              if (leader) tc_commit(b_empty(st));
               if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
             }
             if (nkc > 0) {  // B_lo chunk: A_hi.B_lo
@@ -538,15 +598,16 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
               const uint32_t db = b0 + st * kBStageDesc;
               if (a.debug_mode != 2) {
 #pragma unroll 4
-                for (int k = 0; k < nkc; ++k) tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, 1);
+                for (int k = 0; k < nkc; ++k)
+                  if (leader) tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, 1);
               }
-              tc_commit(b_empty(st));
+              if (leader) tc_commit(b_empty(st));
               if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
             }
           }
-          tc_commit(acc_full(buf));
+          if (leader) tc_commit(acc_full(buf));
         }
-        tc_commit(a_free);
+        if (leader) tc_commit(a_free);
       }
     }
   } else if (warp == kBuilderWarp0 || warp == kBuilderWarp0 + 1) {
@@ -591,31 +652,46 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       // rows beyond T store into a scratch word (ld_bytes = 0): no predicate in the hot loop
       char *out_t = valid ? reinterpret_cast<char *>(a.out + t) : reinterpret_cast<char *>(a.scratch);
       const uint32_t ld_bytes = valid ? (uint32_t)(a.ld * 4) : 0u;
-      float nan_acc = 0.f;
+      EpiState e;
+      e.seg = a.seg;
+      e.scale = a.scale;
+      e.nan_acc = 0.f;
+      e.ld_bytes = ld_bytes;
       for (int j = j0; j < j1; ++j, ++acc_it) {
         const int buf = acc_it & 1;
         const int pa = a.tile_p0[j];
         const int cb = a.tile_cls0[j], ce = a.tile_cls0[j + 1];
+        e.k = __ldg(a.grp_seg0 + kEpiGroups * j + eg);
+        e.n_end = __ldg(a.grp_seg0 + kEpiGroups * j + eg + 1);
         int4 cl = __ldg(a.cls + cb);
+        e.d = e.dn = 0;
+        if (e.k < e.n_end) e.d = __ldg(a.seg + e.k);
+        if (e.k + 1 < e.n_end) e.dn = __ldg(a.seg + e.k + 1);
         mbar_wait(acc_full(buf), (acc_it >> 1) & 1);
         tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256;
-        char *out_p = out_t + (uint64_t)pa * ld_bytes;
-        for (int c = cb; c < ce && a.debug_mode == 0; ++c) {
-          const int len = cl.x, sb = cl.y, se = cl.z;
-          if (c + 1 < ce) cl = __ldg(a.cls + c + 1);
-#define KHG_CASE(L) case L: epi_class<L>(trow, a.seg, out_p, ld_bytes, a.scale, nan_acc, sb, se, eg); break;
-          switch (len) {
-            KHG_CASE(1) KHG_CASE(2) KHG_CASE(3) KHG_CASE(4) KHG_CASE(5) KHG_CASE(6) KHG_CASE(7) KHG_CASE(8)
-            KHG_CASE(9) KHG_CASE(10) KHG_CASE(11) KHG_CASE(12) KHG_CASE(13) KHG_CASE(14) KHG_CASE(15) KHG_CASE(16)
-            default: epi_class_long(trow, a.seg, out_p, ld_bytes, a.scale, nan_acc, sb, se, eg, len); break;
-          }
+        e.trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256;
+        e.out_b = out_t + (uint64_t)pa * ld_bytes;
+        if (a.debug_mode == 0 && e.k < e.n_end) {
+          tc_ld16_issue(e.trow + (e.d & 0xffffu), e.t);
+          for (int c = cb; c < ce; ++c) {
+            const int len = cl.x, ke = e.k + (((eg < 4 ? cl.y : cl.z) >> (8 * (eg & 3))) & 0xff);
+            if (c + 1 < ce) cl = __ldg(a.cls + c + 1);
+            if (ke == e.k) continue;
+#define KHG_CASE(L) case L: epi_class<L>(e, ke); break;
+            switch (len) {
+              KHG_CASE(1) KHG_CASE(2) KHG_CASE(3) KHG_CASE(4) KHG_CASE(5) KHG_CASE(6) KHG_CASE(7) KHG_CASE(8)
+              KHG_CASE(9) KHG_CASE(10) KHG_CASE(11) KHG_CASE(12) KHG_CASE(13) KHG_CASE(14) KHG_CASE(15) KHG_CASE(16)
+              default: epi_class_long(e, ke, len); break;
+            }
 #undef KHG_CASE
+          }
+          tc_ld16_wait(e.t);  // the (unused) load issued after the last segment
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty(buf));
       }
+      const float nan_acc = e.nan_acc;
       if (valid && nan_acc != nan_acc) bad = true;  // r*0 is NaN exactly for a NaN/Inf result
     }
     if (bad) atomicOr(a.err, ERR_NONFINITE);
@@ -641,7 +717,8 @@ void tc_pack_free(khg_model *m) {
   TcPack &t = m->tc;
   cudaFree(t.bhi); cudaFree(t.blo); cudaFree(t.tile_g0); cudaFree(t.tile_p0);
   cudaFree(t.hhi); cudaFree(t.hlo); cudaFree(t.ascale); cudaFree(t.gate);
-  cudaFree(t.tile_cls0); cudaFree(t.cls); cudaFree(t.seg);
+  cudaFree(t.tile_cls0); cudaFree(t.cls); cudaFree(t.seg); cudaFree(t.grp_seg0);
+  t.grp_seg0 = nullptr;
   t.tile_cls0 = nullptr;
   t.cls = nullptr;
   t.seg = nullptr;
@@ -776,7 +853,7 @@ khg_status tc_pack_build(khg_model *m) {
   t.n_tiles = (int)t.h_tile_g0.size();
   // epilogue tables: per tile, its pdfs grouped by Gaussian count (one dispatch per class)
   {
-    std::vector<int32_t> cls0(t.n_tiles + 1, 0);
+    std::vector<int32_t> cls0(t.n_tiles + 1, 0), grp0(kEpiGroups * (size_t)t.n_tiles + 1, 0);
     std::vector<int4> cls;
     std::vector<uint32_t> seg;
     seg.reserve(P);
@@ -785,25 +862,37 @@ khg_status tc_pack_build(khg_model *m) {
       std::vector<std::pair<int, int>> by_len;  // (len, pdf)
       for (int q = pa; q < pb; ++q) by_len.emplace_back(m->h_offsets[q + 1] - m->h_offsets[q], q);
       std::stable_sort(by_len.begin(), by_len.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) { return x.first < y.first; });
+      // segment i of the class-sorted order goes to epilogue group i % 4 (balanced over the tile)
+      std::vector<uint32_t> lists[kEpiGroups];
       for (size_t i = 0; i < by_len.size();) {
         size_t e = i;
         while (e < by_len.size() && by_len[e].first == by_len[i].first) ++e;
+        int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (size_t k = i; k < e; ++k) {
+          lists[k % kEpiGroups].push_back((uint32_t)(m->h_offsets[by_len[k].second] - g0) | ((uint32_t)(by_len[k].second - pa) << 16));
+          ++cnt[k % kEpiGroups];
+        }
         int4 c;
         c.x = by_len[i].first;
-        c.y = (int)seg.size();
-        for (size_t k = i; k < e; ++k)
-          seg.push_back((uint32_t)(m->h_offsets[by_len[k].second] - g0) | ((uint32_t)(by_len[k].second - pa) << 16));
-        c.z = (int)seg.size();
+        c.y = cnt[0] | (cnt[1] << 8) | (cnt[2] << 16) | (cnt[3] << 24);  // <= 60 segments per group (240 columns / 4)
+        c.z = cnt[4] | (cnt[5] << 8) | (cnt[6] << 16) | (cnt[7] << 24);
         c.w = 0;
         cls.push_back(c);
         i = e;
       }
+      for (int eg = 0; eg < kEpiGroups; ++eg) {
+        grp0[kEpiGroups * (size_t)j + eg] = (int32_t)seg.size();
+        seg.insert(seg.end(), lists[eg].begin(), lists[eg].end());
+      }
       cls0[j + 1] = (int32_t)cls.size();
     }
+    grp0[kEpiGroups * (size_t)t.n_tiles] = (int32_t)seg.size();
     KHG_CUDA_TRY(cudaMalloc(&t.tile_cls0, sizeof(int32_t) * cls0.size()));
+    KHG_CUDA_TRY(cudaMalloc(&t.grp_seg0, sizeof(int32_t) * grp0.size()));
     KHG_CUDA_TRY(cudaMalloc(&t.cls, sizeof(int4) * cls.size()));
     KHG_CUDA_TRY(cudaMalloc(&t.seg, sizeof(uint32_t) * seg.size()));
     KHG_CUDA_TRY(cudaMemcpy(t.tile_cls0, cls0.data(), sizeof(int32_t) * cls0.size(), cudaMemcpyHostToDevice));
+    KHG_CUDA_TRY(cudaMemcpy(t.grp_seg0, grp0.data(), sizeof(int32_t) * grp0.size(), cudaMemcpyHostToDevice));
     KHG_CUDA_TRY(cudaMemcpy(t.cls, cls.data(), sizeof(int4) * cls.size(), cudaMemcpyHostToDevice));
     KHG_CUDA_TRY(cudaMemcpy(t.seg, seg.data(), sizeof(uint32_t) * seg.size(), cudaMemcpyHostToDevice));
     // a pdf whose Gaussians all have gconst = -inf makes LogSumExp NaN in the reference
@@ -865,6 +954,7 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   a.tile_cls0 = t.tile_cls0;
   a.cls = static_cast<const int4 *>(t.cls);
   a.seg = t.seg;
+  a.grp_seg0 = t.grp_seg0;
   a.n_tiles = t.n_tiles;
   const int64_t n_m = (T + kTileM - 1) / kTileM;
   // Split the N range when there are too few frame tiles to fill the SMs; keep >= 8
