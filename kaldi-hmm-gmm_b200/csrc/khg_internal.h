@@ -63,20 +63,28 @@ constexpr int kSimtChunk = 32;
 // ---- tcgen05 model pack --------------------------------------------------------
 // B operand of the dense contraction: row g = [means_invvars(D) | -0.5*inv_vars(D)
 // | gconst | 0-pad] split into TF32 hi and lo parts (3xTF32), K padded to KP.
+// Chunks (= TMA stages) of the streamed operand of the tensor-core kernel: see khg_loglikes_tc.cu
+constexpr int kMaxStages = 12;
+struct StageTab {
+  uint32_t e[kMaxStages];  // h0 | nh << 8 | l0 << 12 | nl << 20   (units: K steps)
+  int n;
+};
 struct TcPack {
   bool ready = false;       // tile tables built and at least one operand container usable
   bool tf32_ready = false;  // tf32 operands built (needs 2D+1 <= 160)
   int K = 0;   // 2D+1
   int K8 = 0;  // K rounded up to 8  (UMMA_K for tf32)
-  int KP = 0;  // K rounded up to 32 (one 128-byte swizzle atom per 32 floats)
-  int rows = 0;          // padded row count of bhi/blo
-  float *bhi = nullptr;  // rows x KP
-  float *blo = nullptr;  // rows x KP
+  int KP = 0;  // K8 rounded up to 32 (one 128-byte swizzle atom per 32 floats): A row width
+  int KPB = 0; // width of the streamed operand rows (tab8.n chunks of 32 floats)
+  StageTab tab8, tab16;
+  int rows = 0;          // padded row count of the operand
+  float *bhi = nullptr;  // rows x KPB: B' (tf32 containers)
+  float *blo = nullptr;  // unused (hi and lo live side by side in bhi)
   CUtensorMap map_hi, map_lo;
   // fp16-split variant of the same operand (kind::f16 runs at twice the tf32 rate)
   bool f16_ready = false;
-  int K16 = 0, KP16 = 0;        // K rounded up to 16 / to 64
-  void *hhi = nullptr, *hlo = nullptr;  // rows x KP16 __half
+  int K16 = 0, KP16 = 0, KPB16 = 0;  // 2D+2 rounded up to 16; A row width (K16 -> 64); B' row width (K16 + Kc -> 64)
+  void *hhi = nullptr, *hlo = nullptr;  // hhi: rows x KPB16 __half B' = [hi | lo]; hlo unused
   float *ascale = nullptr;      // device, 2D floats: power-of-two scale of the [x | x^2] columns
   unsigned *gate = nullptr;     // device word: max |x*ascale| bits of the current call (auto mode)
   CUtensorMap hmap_hi, hmap_lo;

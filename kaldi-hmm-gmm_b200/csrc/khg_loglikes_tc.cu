@@ -355,65 +355,102 @@ __device__ __forceinline__ void a_store_split<true>(uint8_t *a_hi, uint32_t lo_o
 __global__ void latch_error_kernel(int *err, int bits) { atomicOr(err, bits); }
 
 // ------------------------------------------------------------------ B pack (K4) --
-__global__ void tc_pack_kernel(int G, int D, int KP, int rows, const float *__restrict__ miv,
+// The streamed operand B' is a sequence of 128-byte chunks (= TMA stages).  A chunk holds nh K steps
+// of the hi part starting at hi step h0, then nl K steps of the lo part starting at lo step l0
+// (a K step = 32 bytes = 16 fp16 / 8 tf32 columns).  The same table drives the pack kernels and
+// the MMA issuer.  Two layouts are built on the host:
+//   packed       [hi, Khh columns | lo, Kc columns]: fewest bytes (fp16, D=40: 3 chunks, not 4)
+//   interleaved  hi chunk 0, lo chunk 0, hi chunk 1, ...: even MMA work per stage (tf32, whose
+//                stage ring is only 4 deep and whose chunk count is the same either way)
+// logical operand column of B' column kk (-1 = padding); lo_part says which half
+template <bool F16>
+__host__ __device__ inline int stage_logical_column(const StageTab &tab, int kk, bool &lo_part) {
+  constexpr int ck = Elem<F16>::kChunkK, uk = Elem<F16>::kUmmaK;
+  const uint32_t v = tab.e[kk / ck];
+  const int h0 = v & 0xff, nh = (v >> 8) & 0xf, l0 = (v >> 12) & 0xff, nl = (v >> 20) & 0xf;
+  const int s = (kk % ck) / uk, r = kk % uk;
+  lo_part = s >= nh;
+  if (s < nh) return (h0 + s) * uk + r;
+  if (s - nh < nl) return (l0 + s - nh) * uk + r;
+  return -1;
+}
+static StageTab make_stage_tab(int Khh, int Kc, int ck, int uk, bool packed) {
+  StageTab t;
+  memset(&t, 0, sizeof(t));
+  const int hs = Khh / uk, ls = Kc / uk, spc = ck / uk;  // K steps of each part, steps per chunk
+  if (packed) {
+    for (int q = 0; q < hs + ls; q += spc, ++t.n) {
+      const int nh = std::max(0, std::min(spc, hs - q)), l0 = std::max(0, q - hs), nl = std::max(0, std::min(spc - nh, ls - l0));
+      t.e[t.n] = (uint32_t)(nh ? q : 0) | (uint32_t)nh << 8 | (uint32_t)l0 << 12 | (uint32_t)nl << 20;
+    }
+  } else {
+    for (int q = 0; q < hs; q += spc) {
+      t.e[t.n++] = (uint32_t)q | (uint32_t)std::min(spc, hs - q) << 8;
+      if (q < ls) t.e[t.n++] = (uint32_t)q << 12 | (uint32_t)std::min(spc, ls - q) << 20;
+    }
+  }
+  return t;
+}
+// One operand row per Gaussian, laid out by the stage table (KPB = 128-byte chunks * n
+// columns).  Logical columns: [means_invvars (D) |
+// -0.5*inv_vars (D) | gconst | gconst residual].  The hi part spans all 2D+2 of them rounded up
+// to the MMA K (Khh), the lo part only the 2D feature columns (Kc): the gconst rides entirely in
+// the hi.hi product (its container-rounded part and the residual, both against a constant 1 in
+// A_hi).  Storing hi and lo side by side instead of in two padded matrices cuts the bytes every
+// CTA streams per tile (192 instead of 256 fp16 columns at D = 40).
+__global__ void tc_pack_kernel(int G, int D, StageTab tab, int KPB, int rows, const float *__restrict__ miv,
                                const float *__restrict__ iv, const float *__restrict__ gconsts,
-                               float *__restrict__ bhi, float *__restrict__ blo) {
-  size_t total = (size_t)rows * KP;
+                               float *__restrict__ bp) {
+  size_t total = (size_t)rows * KPB;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int k = (int)(i % KP);
-    int g = (int)(i / KP);
-    float hi = 0.f, lo = 0.f;
-    if (g < G) {
+    const int kk = (int)(i % KPB);
+    const int g = (int)(i / KPB);
+    bool lo_part;
+    const int k = stage_logical_column<false>(tab, kk, lo_part);
+    float out = 0.f;
+    if (g < G && k >= 0) {
       if (k < 2 * D) {
         const float v = k < D ? miv[(size_t)g * D + k] : -0.5f * iv[(size_t)g * D + (k - D)];
-        hi = tf32_rna(v);
-        lo = v - hi;
+        float hi = tf32_rna(v), lo = v - hi;
         if (!(fabsf(v) <= 3.0e38f)) { hi = v; lo = 0.f; }
-      } else if (k <= 2 * D + 1) {
-        // gconst rides entirely in the hi.hi product: column 2D holds its tf32 part, column
-        // 2D+1 the residual, both against a constant 1 in A_hi; the cross products then only
-        // span the 2D feature columns.
+        out = lo_part ? lo : hi;
+      } else if (k <= 2 * D + 1 && !lo_part) {
         float v = gconsts[g];
         if (v == -CUDART_INF_F) v = kNegSentinel;  // zero-weight Gaussian (csrc/diag-gmm.cc:136-141)
         const float vh = tf32_rna(v);
-        hi = k == 2 * D ? vh : tf32_rna(v - vh);
-        if (!(fabsf(v) <= 3.0e38f)) hi = k == 2 * D ? v : 0.f;
+        out = k == 2 * D ? vh : tf32_rna(v - vh);
+        if (!(fabsf(v) <= 3.0e38f)) out = k == 2 * D ? v : 0.f;
       }
     }
-    bhi[i] = hi;
-    blo[i] = lo;
+    bp[i] = out;
   }
 }
 
 // fp16 variant: B scaled per dimension by powers of two (bscale[k], exact), split into fp16
 // hi and lo.  flags[0] is set when a value does not fit fp16 comfortably or a gconst is
 // -inf: the model then stays on the tf32 path.
-__global__ void tc_pack_f16_kernel(int G, int D, int KP, int rows, const float *__restrict__ miv,
+__global__ void tc_pack_f16_kernel(int G, int D, StageTab tab, int KPB, int rows, const float *__restrict__ miv,
                                    const float *__restrict__ iv, const float *__restrict__ gconsts,
-                                   const float *__restrict__ bscale, __half *__restrict__ bhi,
-                                   __half *__restrict__ blo, int *__restrict__ flags) {
-  size_t total = (size_t)rows * KP;
+                                   const float *__restrict__ bscale, __half *__restrict__ bp, int *__restrict__ flags) {
+  size_t total = (size_t)rows * KPB;
   bool bad = false;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int k = (int)(i % KP);
-    int g = (int)(i / KP);
+    const int kk = (int)(i % KPB);
+    const int g = (int)(i / KPB);
+    bool lo_part;
+    const int k = stage_logical_column<true>(tab, kk, lo_part);
     float v = 0.f;
     bool is_gc = false;
-    if (g < G) {
+    if (g < G && k >= 0) {
       if (k < D) v = miv[(size_t)g * D + k] * bscale[k];
       else if (k < 2 * D) v = -0.5f * iv[(size_t)g * D + (k - D)] * bscale[k];
-      else if (k <= 2 * D + 1) { v = gconsts[g]; is_gc = true; }
+      else if (k <= 2 * D + 1 && !lo_part) { v = gconsts[g]; is_gc = true; }
     }
     if (!(fabsf(v) <= 3.0e4f)) bad = true;  // also catches -inf gconsts and NaN
     const __half hi = __float2half_rn(v);
     const __half lo = __float2half_rn(v - __half2float(hi));
-    if (is_gc) {  // gconst: fp16 part in column 2D, residual in column 2D+1, both in B_hi
-      bhi[i] = k == 2 * D ? hi : lo;
-      blo[i] = __float2half_rn(0.f);
-    } else {
-      bhi[i] = hi;
-      blo[i] = lo;
-    }
+    if (is_gc) bp[i] = k == 2 * D ? hi : lo;  // gconst: fp16 part in column 2D, residual in column 2D+1
+    else bp[i] = lo_part ? lo : hi;
   }
   if (bad) atomicOr(flags, 1);
 }
@@ -435,7 +472,8 @@ struct TcArgs {
   const float *feats;      // T x D
   int64_t T;
   int D, K8, Kc, n_chunks; // K8 = 2D+2 rounded up to UMMA_K (hi.hi product), Kc = 2D rounded up (cross
-                           // products); n_chunks = 128-byte chunks per operand row
+                           // products); n_chunks = 128-byte chunks per A_hi / A_lo row held in smem
+  StageTab tab;            // chunks (= TMA stages) of the streamed operand B' and what each holds
   const float *ascale;     // fp16 path: per-column power-of-two scale of [x | x^2] (2D floats); NULL = none
   const unsigned *gate;    // NULL, or device word with max |x*ascale| bits: see gate_limit
   float gate_limit;        // fp16 kernel runs iff *gate <= limit, tf32 kernel iff *gate > limit
@@ -460,7 +498,7 @@ struct TcArgs {
 
 template <bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
-loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, TcArgs a) {
+loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
   constexpr int kChunkK = Elem<F16>::kChunkK, kUmmaK = Elem<F16>::kUmmaK;
   constexpr uint32_t kIdesc = make_idesc<F16>();
   if (a.gate != nullptr) {  // precision-path gate decided on the device (no host round trip)
@@ -531,21 +569,18 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
         for (int j = j0; j < j1; ++j) {
           const int g0 = __shfl_sync(0xffffffffu, __ldg(a.tile_g0 + j), 0);
-          for (int c = 0; c < NCH; ++c) {
-            for (int hl = 0; hl < 2; ++hl) {
-              if (hl == 1 && a.Kc <= c * kChunkK) continue;  // no cross-product step in this chunk
-              mbar_wait(b_empty(st), ph);
-              if (leader) {
-                if (a.debug_mode == 3) {  // experiment: MMA rate without operand traffic
-                  mbar_arrive(b_full(st));
-                } else {
-                  mbar_expect_tx(b_full(st), kBStageBytes);
-                  tma_load_2d(sB + st * kBStageBytes, hl ? &map_lo : &map_hi, b_full(st), c * kChunkK, g0);
-                }
+          for (int c = 0; c < a.tab.n; ++c) {
+            mbar_wait(b_empty(st), ph);
+            if (leader) {
+              if (a.debug_mode == 3) {  // experiment: MMA rate without operand traffic
+                mbar_arrive(b_full(st));
+              } else {
+                mbar_expect_tx(b_full(st), kBStageBytes);
+                tma_load_2d(sB + st * kBStageBytes, &map_b, b_full(st), c * kChunkK, g0);
               }
-              __syncwarp();
-              if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
             }
+            __syncwarp();
+            if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
           }
         }
       }
@@ -571,39 +606,33 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * 256;
           uint32_t accum = 0;
-          for (int c = 0; c < NCH; ++c) {
-            const int nk = min(kChunkK, a.K8 - c * kChunkK) / kUmmaK;            // hi.hi product
-            const int nkc = max(0, min(kChunkK, a.Kc - c * kChunkK)) / kUmmaK;  // cross products
-            const uint32_t da_hi = a_hi0 + c * kAChunkDesc, da_lo = a_lo0 + c * kAChunkDesc;
-            {  // B_hi chunk: A_hi.B_hi + A_lo.B_hi
-              mbar_wait(b_full(st), ph);
-              tc_fence_after();
-              const uint32_t db = b0 + st * kBStageDesc;
-              if (a.debug_mode != 2) {  // (2 = experiment: TMA rate without MMAs)
+          for (int c = 0; c < a.tab.n; ++c) {
+            const uint32_t e = a.tab.e[c];
+            const int h0 = e & 0xff, nh = (e >> 8) & 0xf, l0 = (e >> 12) & 0xff, nl = (e >> 20) & 0xf;
+            mbar_wait(b_full(st), ph);
+            tc_fence_after();
+            const uint32_t db = b0 + st * kBStageDesc;
+            constexpr int kSpc = kChunkK / kUmmaK;  // K steps per chunk (4)
+            if (a.debug_mode != 2) {  // (2 = experiment: TMA rate without MMAs)
+              // hi steps of B feed A_hi (hi.hi) and, inside the feature columns, A_lo (lo.hi)
 #pragma unroll 4
-                for (int k = 0; k < nk; ++k) {
-                  if (leader) tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, accum);
-                  accum = 1;
-                }
-#pragma unroll 4
-                for (int k = 0; k < nkc; ++k)
-                  if (leader) tc_mma<F16>(tmem_d, da_lo + 2 * k, db + 2 * k, kIdesc, 1);
+              for (int s = 0; s < nh; ++s) {
+                const int q = h0 + s;
+                const uint32_t ao = (uint32_t)(q / kSpc) * kAChunkDesc + (uint32_t)(q % kSpc) * 2;
+                if (leader) tc_mma<F16>(tmem_d, a_hi0 + ao, db + 2 * s, kIdesc, accum);
+                accum = 1;
+                if (q * kUmmaK < a.Kc && leader) tc_mma<F16>(tmem_d, a_lo0 + ao, db + 2 * s, kIdesc, 1);
               }
-              if (leader) tc_commit(b_empty(st));
-              if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
-            }
-            if (nkc > 0) {  // B_lo chunk: A_hi.B_lo
-              mbar_wait(b_full(st), ph);
-              tc_fence_after();
-              const uint32_t db = b0 + st * kBStageDesc;
-              if (a.debug_mode != 2) {
+              // lo steps of B feed A_hi (hi.lo)
 #pragma unroll 4
-                for (int k = 0; k < nkc; ++k)
-                  if (leader) tc_mma<F16>(tmem_d, da_hi + 2 * k, db + 2 * k, kIdesc, 1);
+              for (int s = 0; s < nl; ++s) {
+                const int q = l0 + s;
+                const uint32_t ao = (uint32_t)(q / kSpc) * kAChunkDesc + (uint32_t)(q % kSpc) * 2;
+                if (leader) tc_mma<F16>(tmem_d, a_hi0 + ao, db + 2 * (nh + s), kIdesc, 1);
               }
-              if (leader) tc_commit(b_empty(st));
-              if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
             }
+            if (leader) tc_commit(b_empty(st));
+            if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
           }
           if (leader) tc_commit(acc_full(buf));
         }
@@ -776,7 +805,10 @@ static khg_status tc_pack_build_f16(khg_model *m) {
   TcPack &t = m->tc;
   const int D = m->dim, G = m->G;
   t.K16 = (t.K + 1 + 15) / 16 * 16;  // hi.hi product spans 2D+2 columns (gconst + its residual)
-  t.KP16 = (t.K + 63) / 64 * 64;
+  t.KP16 = (t.K16 + 63) / 64 * 64;   // A_hi / A_lo row width in smem
+  const int Kc16 = (2 * D + 15) / 16 * 16;
+  t.tab16 = make_stage_tab(t.K16, Kc16, 64, 16, true);
+  t.KPB16 = t.tab16.n * 64;
   std::vector<float> miv((size_t)G * D), iv((size_t)G * D);
   KHG_CUDA_TRY(cudaMemcpyAsync(miv.data(), m->d_miv, sizeof(float) * miv.size(), cudaMemcpyDeviceToHost, m->stream));
   KHG_CUDA_TRY(cudaMemcpyAsync(iv.data(), m->d_iv, sizeof(float) * iv.size(), cudaMemcpyDeviceToHost, m->stream));
@@ -806,12 +838,10 @@ static khg_status tc_pack_build_f16(khg_model *m) {
   KHG_CUDA_TRY(cudaMemcpyAsync(t.ascale, ascale.data(), sizeof(float) * 2 * D, cudaMemcpyHostToDevice, m->stream));
   KHG_CUDA_TRY(cudaMemcpyAsync(d_bscale, bscale.data(), sizeof(float) * 2 * D, cudaMemcpyHostToDevice, m->stream));
   KHG_CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), m->stream));
-  KHG_CUDA_TRY(cudaMalloc(&t.hhi, sizeof(__half) * (size_t)t.rows * t.KP16));
-  KHG_CUDA_TRY(cudaMalloc(&t.hlo, sizeof(__half) * (size_t)t.rows * t.KP16));
-  size_t total = (size_t)t.rows * t.KP16;
+  KHG_CUDA_TRY(cudaMalloc(&t.hhi, sizeof(__half) * (size_t)t.rows * t.KPB16));
+  size_t total = (size_t)t.rows * t.KPB16;
   tc_pack_f16_kernel<<<(unsigned)std::min<size_t>(2048, (total + 255) / 256), 256, 0, m->stream>>>(
-      G, D, t.KP16, t.rows, m->d_miv, m->d_iv, m->d_gconsts, d_bscale, static_cast<__half *>(t.hhi),
-      static_cast<__half *>(t.hlo), d_flag);
+      G, D, t.tab16, t.KPB16, t.rows, m->d_miv, m->d_iv, m->d_gconsts, d_bscale, static_cast<__half *>(t.hhi), d_flag);
   ++g_launch_count;
   int flag = 0;
   KHG_CUDA_TRY(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
@@ -819,8 +849,7 @@ static khg_status tc_pack_build_f16(khg_model *m) {
   cudaFree(d_bscale);
   cudaFree(d_flag);
   if (flag) return KHG_OK;  // model does not fit the fp16 split: stay on tf32 (f16_ready = false)
-  KHG_TRY(make_map(&t.hmap_hi, t.hhi, t.KP16, t.rows, true));
-  KHG_TRY(make_map(&t.hmap_lo, t.hlo, t.KP16, t.rows, true));
+  KHG_TRY(make_map(&t.hmap_hi, t.hhi, t.KPB16, t.rows, true));
   t.f16_ready = true;
   return KHG_OK;
 }
@@ -831,7 +860,10 @@ khg_status tc_pack_build(khg_model *m) {
   const int D = m->dim, G = m->G, P = m->P;
   t.K = 2 * D + 1;
   t.K8 = (t.K + 1 + 7) / 8 * 8;
-  t.KP = (t.K + 31) / 32 * 32;
+  t.KP = (t.K8 + 31) / 32 * 32;      // A_hi / A_lo row width in smem
+  const int Kc8 = (2 * D + 7) / 8 * 8;
+  t.tab8 = make_stage_tab(t.K8, Kc8, 32, 8, false);
+  t.KPB = t.tab8.n * 32;
   t.rows = (G + kTileN + 15) / 16 * 16;
   // pdf-aligned N tiles (greedy)
   t.h_tile_g0.clear();
@@ -911,14 +943,12 @@ khg_status tc_pack_build(khg_model *m) {
   KHG_CUDA_TRY(cudaMemcpyAsync(t.tile_g0, t.h_tile_g0.data(), sizeof(int32_t) * t.n_tiles, cudaMemcpyHostToDevice, m->stream));
   KHG_CUDA_TRY(cudaMemcpyAsync(t.tile_p0, t.h_tile_p0.data(), sizeof(int32_t) * (t.n_tiles + 1), cudaMemcpyHostToDevice, m->stream));
   if (tc_shape_ok(m, false)) {
-    KHG_CUDA_TRY(cudaMalloc(&t.bhi, sizeof(float) * (size_t)t.rows * t.KP));
-    KHG_CUDA_TRY(cudaMalloc(&t.blo, sizeof(float) * (size_t)t.rows * t.KP));
-    size_t total = (size_t)t.rows * t.KP;
-    tc_pack_kernel<<<(unsigned)std::min<size_t>(2048, (total + 255) / 256), 256, 0, m->stream>>>(G, D, t.KP, t.rows, m->d_miv, m->d_iv, m->d_gconsts, t.bhi, t.blo);
+    KHG_CUDA_TRY(cudaMalloc(&t.bhi, sizeof(float) * (size_t)t.rows * t.KPB));
+    size_t total = (size_t)t.rows * t.KPB;
+    tc_pack_kernel<<<(unsigned)std::min<size_t>(2048, (total + 255) / 256), 256, 0, m->stream>>>(G, D, t.tab8, t.KPB, t.rows, m->d_miv, m->d_iv, m->d_gconsts, t.bhi);
     ++g_launch_count;
     KHG_CUDA_TRY(cudaGetLastError());
-    KHG_TRY(make_map(&t.map_hi, t.bhi, t.KP, t.rows, false));
-    KHG_TRY(make_map(&t.map_lo, t.blo, t.KP, t.rows, false));
+    KHG_TRY(make_map(&t.map_hi, t.bhi, t.KPB, t.rows, false));
     t.tf32_ready = true;
   }
   KHG_CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -938,6 +968,7 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   a.K8 = F16 ? t.K16 : t.K8;
   a.Kc = (2 * m->dim + Elem<F16>::kUmmaK - 1) / Elem<F16>::kUmmaK * Elem<F16>::kUmmaK;
   a.n_chunks = (F16 ? t.KP16 : t.KP) / Elem<F16>::kChunkK;
+  a.tab = F16 ? t.tab16 : t.tab8;
   a.ascale = F16 ? t.ascale : nullptr;
   a.gate = gate;
   a.gate_limit = kF16FeatLimit;
@@ -986,10 +1017,7 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   KHG_CUDA_TRY(attr_err);
   unsigned grid = (unsigned)std::min<int64_t>(a.n_items, m->sm_count);
   if (const char *mc = getenv("KHG_TC_MAX_CTAS")) grid = std::min<unsigned>(grid, (unsigned)std::max(1, atoi(mc)));  // experiments
-  if (F16)
-    loglikes_tc_kernel<F16><<<grid, kTcThreads, smem, m->stream>>>(t.hmap_hi, t.hmap_lo, a);
-  else
-    loglikes_tc_kernel<F16><<<grid, kTcThreads, smem, m->stream>>>(t.map_hi, t.map_lo, a);
+  loglikes_tc_kernel<F16><<<grid, kTcThreads, smem, m->stream>>>(F16 ? t.hmap_hi : t.map_hi, a);
   ++g_launch_count;
   KHG_CUDA_TRY(cudaGetLastError());
   return KHG_OK;

@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkhg_b200.so")
+# KHG_B200_LIB: development override used for same-box A/B timing of two builds (tools/ab_build.sh)
+LIB_PATH = os.environ.get("KHG_B200_LIB") or os.path.join(_HERE, "libkhg_b200.so")
 
 KHG_OK, KHG_ERR_INVALID, KHG_ERR_CUDA, KHG_ERR_NONFINITE, KHG_ERR_UNSUPPORTED = range(5)
 KHG_HOST, KHG_DEVICE = 0, 1
