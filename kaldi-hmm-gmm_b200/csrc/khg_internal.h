@@ -94,11 +94,11 @@ struct TcPack {
   int32_t *tile_g0 = nullptr;  // device, n_tiles
   int32_t *tile_p0 = nullptr;  // device, n_tiles+1
   std::vector<int32_t> h_tile_g0, h_tile_p0;
-  // epilogue tables: the pdfs (segments) of a tile grouped by their number of Gaussians
-  int32_t *tile_cls0 = nullptr;  // device, n_tiles+1
-  void *cls = nullptr;           // device int4 {len, segments per epilogue group (4 x 8 bits), 0, 0} per class
-  int32_t *grp_seg0 = nullptr;   // device, 4*n_tiles+1: start in seg[] of the list of (tile, epilogue group)
-  uint32_t *seg = nullptr;       // device, P: column | (pdf - tile_p0) << 16; per (tile, group), class order
+  // epilogue tables: per (tile, epilogue group) the list of its pdfs (segments), in runs of equal
+  // Gaussian count (khg_loglikes_tc.cu)
+  void *epi_hdr = nullptr;       // device int2 per (tile, group): {start in seg[], first run | runs << 24}
+  uint32_t *runs = nullptr;      // device: length | count << 8
+  uint32_t *seg = nullptr;       // device: column | pdf << 8, + 2 sentinels per list
   bool dead_pdf = false;         // some pdf has only -inf gconsts: every call must fail like the reference
 };
 

@@ -262,58 +262,56 @@ __device__ __forceinline__ float seg_lse_long(uint32_t taddr, int len) {
 }
 
 // Epilogue state of one warp inside one accumulator tile.  The warp walks ITS list of
-// segments (pdfs) of the tile, seg[k] for k in [k, n_end), ordered by length class.  Invariant
-// between segments: the TMEM load of segment k (descriptor d) has been issued into t.  A
-// tcgen05.ld -> wait::ld round trip is ~170 cycles (tools/tmem_ld_rate.cu), so the load of
-// segment k+1 is issued as soon as part 1 of segment k has consumed the registers, across class
-// boundaries, and completes under part 2 (exponentials, log, store).
+// segments (pdfs) of the tile, seg[k...], ordered in runs of equal length.  Invariant between
+// segments: the TMEM load of segment k (descriptor d) has been issued into t.  A tcgen05.ld ->
+// wait::ld round trip is ~170 cycles (tools/tmem_ld_rate.cu), so the load of segment k+1 is
+// issued as soon as part 1 of segment k has consumed the registers, across run boundaries, and
+// completes under part 2 (exponentials, log, store).  Every list ends with two sentinel
+// descriptors (column 0), so "the next" and "the one after" always exist: no predicates.
 //   trow  TMEM address of this warp's lane quadrant in the current accumulator buffer
-//   seg   packed segment descriptors: column | (pdf - first pdf of tile) << 16
-//   out_b byte address of out[first pdf of tile][t] — or of a scratch word with ld_bytes = 0
-//         for rows beyond T, so that the store needs no predicate
+//   sp    &seg[k]; a descriptor is  column | pdf << 8
+//   out_t byte address of out[0][t] — or of a scratch word with ld_bytes = 0 for rows beyond
+//         T, so that the store needs no predicate
 //   nan_acc collects r*0 (NaN for a non-finite r, the reference's "Invalid answer"): one FFMA
 //         instead of a compare/select/or per segment
 struct EpiState {
   TReg16 t;
-  uint32_t d, dn;   // descriptors of segment k (load in flight) and k+1 (fetched one segment ahead)
-  int k, n_end;
+  uint32_t d, dn;   // descriptors of segment k (load in flight) and k+1
+  const uint32_t *sp;
   uint32_t trow;
-  const uint32_t *seg;
-  char *out_b;
+  char *out_t;
   uint32_t ld_bytes;
   float scale, nan_acc;
 };
 
 template <int L>
-__device__ __forceinline__ void epi_class(EpiState &e, int ke) {
+__device__ __forceinline__ void epi_run(EpiState &e, int cnt) {
 #pragma unroll 1
-  for (; e.k < ke; ++e.k) {
+  for (; cnt > 0; --cnt) {
     const uint32_t dcur = e.d, dnext = e.dn;
-    const bool more = e.k + 1 < e.n_end;
-    if (e.k + 2 < e.n_end) e.dn = __ldg(e.seg + e.k + 2);  // two ahead: its latency never gates the TMEM load
+    e.dn = __ldg(e.sp + 2);  // two ahead: its latency never gates the TMEM load
+    ++e.sp;
     tc_ld16_wait(e.t);
     SegLse<L> lse;
     lse.part1(e.t);
-    // unconditional (a branch here makes ptxas sink the load below part 2): after the last
-    // segment of the tile it re-reads the current columns and the result is never used
-    tc_ld16_issue(e.trow + ((more ? dnext : dcur) & 0xffffu), e.t);
+    tc_ld16_issue(e.trow + (dnext & 0xffu), e.t);  // after the last segment: the sentinel (unused)
     const float r = lse.part2();
     e.nan_acc = fmaf(r, 0.f, e.nan_acc);
-    *reinterpret_cast<float *>(e.out_b + (uint64_t)(dcur >> 16) * e.ld_bytes) = e.scale * r;
+    *reinterpret_cast<float *>(e.out_t + (uint64_t)(dcur >> 8) * e.ld_bytes) = e.scale * r;
     e.d = dnext;
   }
 }
 
-__device__ __forceinline__ void epi_class_long(EpiState &e, int ke, int len) {
-  for (; e.k < ke; ++e.k) {
+__device__ __forceinline__ void epi_run_long(EpiState &e, int cnt, int len) {
+  for (; cnt > 0; --cnt) {
     const uint32_t dcur = e.d, dnext = e.dn;
-    const bool more = e.k + 1 < e.n_end;
-    if (e.k + 2 < e.n_end) e.dn = __ldg(e.seg + e.k + 2);
+    e.dn = __ldg(e.sp + 2);
+    ++e.sp;
     tc_ld16_wait(e.t);  // the pending 16-column load is not used by the two-pass form
-    const float r = seg_lse_long(e.trow + (dcur & 0xffffu), len);
-    tc_ld16_issue(e.trow + ((more ? dnext : dcur) & 0xffffu), e.t);
+    const float r = seg_lse_long(e.trow + (dcur & 0xffu), len);
+    tc_ld16_issue(e.trow + (dnext & 0xffu), e.t);
     e.nan_acc = fmaf(r, 0.f, e.nan_acc);
-    *reinterpret_cast<float *>(e.out_b + (uint64_t)(dcur >> 16) * e.ld_bytes) = e.scale * r;
+    *reinterpret_cast<float *>(e.out_t + (uint64_t)(dcur >> 8) * e.ld_bytes) = e.scale * r;
     e.d = dnext;
   }
 }
@@ -482,10 +480,9 @@ struct TcArgs {
   const int32_t *offsets;  // P+1
   const int32_t *tile_g0;  // n_tiles
   const int32_t *tile_p0;  // n_tiles+1
-  const int32_t *tile_cls0;  // n_tiles+1: range of length classes of a tile
-  const int4 *cls;           // per class: {len, segments per epilogue group (4 x 8 bits), 0, 0}
-  const int32_t *grp_seg0;   // kEpiGroups*n_tiles+1: start in seg[] of the list of (tile, epilogue group)
-  const uint32_t *seg;       // per segment: column | (pdf - tile_p0) << 16; per (tile, group), class order
+  const int2 *epi_hdr;       // per (tile, epilogue group): {start in seg[], first run | number of runs << 24}
+  const uint32_t *runs;      // per run of equal-length segments: length | count << 8
+  const uint32_t *seg;       // per segment: column | pdf << 8; per (tile, group) in run order, + 2 sentinels
   int n_tiles, n_splits, tiles_per_split;
   int64_t n_items;
   float scale;
@@ -682,39 +679,37 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
       char *out_t = valid ? reinterpret_cast<char *>(a.out + t) : reinterpret_cast<char *>(a.scratch);
       const uint32_t ld_bytes = valid ? (uint32_t)(a.ld * 4) : 0u;
       EpiState e;
-      e.seg = a.seg;
       e.scale = a.scale;
       e.nan_acc = 0.f;
       e.ld_bytes = ld_bytes;
-      for (int j = j0; j < j1; ++j, ++acc_it) {
+      e.out_t = out_t;
+      const int2 *hdr = a.epi_hdr + (size_t)kEpiGroups * j0 + eg;
+      for (int j = j0; j < j1; ++j, ++acc_it, hdr += kEpiGroups) {
         const int buf = acc_it & 1;
-        const int pa = a.tile_p0[j];
-        const int cb = a.tile_cls0[j], ce = a.tile_cls0[j + 1];
-        e.k = __ldg(a.grp_seg0 + kEpiGroups * j + eg);
-        e.n_end = __ldg(a.grp_seg0 + kEpiGroups * j + eg + 1);
-        int4 cl = __ldg(a.cls + cb);
-        e.d = e.dn = 0;
-        if (e.k < e.n_end) e.d = __ldg(a.seg + e.k);
-        if (e.k + 1 < e.n_end) e.dn = __ldg(a.seg + e.k + 1);
+        const int2 h = __ldg(hdr);
+        const uint32_t *rp = a.runs + (h.y & 0xffffff);
+        int nr = (int)((uint32_t)h.y >> 24);
+        e.sp = a.seg + h.x;
+        e.d = __ldg(e.sp);  // (a sentinel when the list is empty)
+        e.dn = __ldg(e.sp + 1);
+        uint32_t run = __ldg(rp);
         mbar_wait(acc_full(buf), (acc_it >> 1) & 1);
         tc_fence_after();
         e.trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256;
-        e.out_b = out_t + (uint64_t)pa * ld_bytes;
-        if (a.debug_mode == 0 && e.k < e.n_end) {
-          tc_ld16_issue(e.trow + (e.d & 0xffffu), e.t);
-          for (int c = cb; c < ce; ++c) {
-            const int len = cl.x, ke = e.k + (((eg < 4 ? cl.y : cl.z) >> (8 * (eg & 3))) & 0xff);
-            if (c + 1 < ce) cl = __ldg(a.cls + c + 1);
-            if (ke == e.k) continue;
-#define KHG_CASE(L) case L: epi_class<L>(e, ke); break;
+        if (a.debug_mode == 0 && nr > 0) {
+          tc_ld16_issue(e.trow + (e.d & 0xffu), e.t);
+          for (; nr > 0; --nr) {
+            const int len = run & 0xff, cnt = run >> 8;
+            if (nr > 1) run = __ldg(++rp);
+#define KHG_CASE(L) case L: epi_run<L>(e, cnt); break;
             switch (len) {
               KHG_CASE(1) KHG_CASE(2) KHG_CASE(3) KHG_CASE(4) KHG_CASE(5) KHG_CASE(6) KHG_CASE(7) KHG_CASE(8)
               KHG_CASE(9) KHG_CASE(10) KHG_CASE(11) KHG_CASE(12) KHG_CASE(13) KHG_CASE(14) KHG_CASE(15) KHG_CASE(16)
-              default: epi_class_long(e, ke, len); break;
+              default: epi_run_long(e, cnt, len); break;
             }
 #undef KHG_CASE
           }
-          tc_ld16_wait(e.t);  // the (unused) load issued after the last segment
+          tc_ld16_wait(e.t);  // the (unused) sentinel load issued after the last segment
         }
         tc_fence_before();
         __syncwarp();
@@ -746,10 +741,9 @@ void tc_pack_free(khg_model *m) {
   TcPack &t = m->tc;
   cudaFree(t.bhi); cudaFree(t.blo); cudaFree(t.tile_g0); cudaFree(t.tile_p0);
   cudaFree(t.hhi); cudaFree(t.hlo); cudaFree(t.ascale); cudaFree(t.gate);
-  cudaFree(t.tile_cls0); cudaFree(t.cls); cudaFree(t.seg); cudaFree(t.grp_seg0);
-  t.grp_seg0 = nullptr;
-  t.tile_cls0 = nullptr;
-  t.cls = nullptr;
+  cudaFree(t.epi_hdr); cudaFree(t.runs); cudaFree(t.seg);
+  t.epi_hdr = nullptr;
+  t.runs = nullptr;
   t.seg = nullptr;
   t.bhi = t.blo = nullptr;
   t.hhi = t.hlo = nullptr;
@@ -885,47 +879,44 @@ khg_status tc_pack_build(khg_model *m) {
   t.n_tiles = (int)t.h_tile_g0.size();
   // epilogue tables: per tile, its pdfs grouped by Gaussian count (one dispatch per class)
   {
-    std::vector<int32_t> cls0(t.n_tiles + 1, 0), grp0(kEpiGroups * (size_t)t.n_tiles + 1, 0);
-    std::vector<int4> cls;
-    std::vector<uint32_t> seg;
-    seg.reserve(P);
+    std::vector<int2> hdr((size_t)kEpiGroups * t.n_tiles);
+    std::vector<uint32_t> runs, seg;
+    seg.reserve(P + 2 * hdr.size());
     for (int j = 0; j < t.n_tiles; ++j) {
       const int pa = t.h_tile_p0[j], pb = t.h_tile_p0[j + 1], g0 = t.h_tile_g0[j];
       std::vector<std::pair<int, int>> by_len;  // (len, pdf)
       for (int q = pa; q < pb; ++q) by_len.emplace_back(m->h_offsets[q + 1] - m->h_offsets[q], q);
       std::stable_sort(by_len.begin(), by_len.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) { return x.first < y.first; });
-      // segment i of the class-sorted order goes to epilogue group i % 4 (balanced over the tile)
-      std::vector<uint32_t> lists[kEpiGroups];
-      for (size_t i = 0; i < by_len.size();) {
-        size_t e = i;
-        while (e < by_len.size() && by_len[e].first == by_len[i].first) ++e;
-        int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (size_t k = i; k < e; ++k) {
-          lists[k % kEpiGroups].push_back((uint32_t)(m->h_offsets[by_len[k].second] - g0) | ((uint32_t)(by_len[k].second - pa) << 16));
-          ++cnt[k % kEpiGroups];
-        }
-        int4 c;
-        c.x = by_len[i].first;
-        c.y = cnt[0] | (cnt[1] << 8) | (cnt[2] << 16) | (cnt[3] << 24);  // <= 60 segments per group (240 columns / 4)
-        c.z = cnt[4] | (cnt[5] << 8) | (cnt[6] << 16) | (cnt[7] << 24);
-        c.w = 0;
-        cls.push_back(c);
-        i = e;
-      }
+      // segment i of the length-sorted order goes to epilogue group i % kEpiGroups (balanced)
       for (int eg = 0; eg < kEpiGroups; ++eg) {
-        grp0[kEpiGroups * (size_t)j + eg] = (int32_t)seg.size();
-        seg.insert(seg.end(), lists[eg].begin(), lists[eg].end());
+        int2 h;
+        h.x = (int)seg.size();
+        const size_t r0 = runs.size();
+        for (size_t i = eg; i < by_len.size(); i += kEpiGroups) {
+          const int len = by_len[i].first, q = by_len[i].second;
+          // a run: equal lengths <= 255 (longer pdfs: one run each, length in the upper field)
+          if (runs.size() > r0 && (int)(runs.back() & 0xff) == std::min(len, 255) && len < 255 && (runs.back() >> 8) < 0xffffu)
+            runs.back() += 1u << 8;
+          else
+            runs.push_back((uint32_t)std::min(len, 255) | 1u << 8);
+          seg.push_back((uint32_t)(m->h_offsets[q] - g0) | (uint32_t)q << 8);
+        }
+        seg.push_back(0);  // two sentinels: the epilogue prefetches two descriptors ahead
+        seg.push_back(0);
+        h.y = (int)(r0 | (runs.size() - r0) << 24);
+        hdr[(size_t)kEpiGroups * j + eg] = h;
       }
-      cls0[j + 1] = (int32_t)cls.size();
     }
-    grp0[kEpiGroups * (size_t)t.n_tiles] = (int32_t)seg.size();
-    KHG_CUDA_TRY(cudaMalloc(&t.tile_cls0, sizeof(int32_t) * cls0.size()));
-    KHG_CUDA_TRY(cudaMalloc(&t.grp_seg0, sizeof(int32_t) * grp0.size()));
-    KHG_CUDA_TRY(cudaMalloc(&t.cls, sizeof(int4) * cls.size()));
+    runs.push_back(0);  // read (unused) by groups without segments
+    if (P >= (1 << 24) || runs.size() >= (1u << 24)) {
+      set_error("too many pdfs for the tensor-core epilogue tables");
+      return KHG_ERR_UNSUPPORTED;
+    }
+    KHG_CUDA_TRY(cudaMalloc(&t.epi_hdr, sizeof(int2) * hdr.size()));
+    KHG_CUDA_TRY(cudaMalloc(&t.runs, sizeof(uint32_t) * runs.size()));
     KHG_CUDA_TRY(cudaMalloc(&t.seg, sizeof(uint32_t) * seg.size()));
-    KHG_CUDA_TRY(cudaMemcpy(t.tile_cls0, cls0.data(), sizeof(int32_t) * cls0.size(), cudaMemcpyHostToDevice));
-    KHG_CUDA_TRY(cudaMemcpy(t.grp_seg0, grp0.data(), sizeof(int32_t) * grp0.size(), cudaMemcpyHostToDevice));
-    KHG_CUDA_TRY(cudaMemcpy(t.cls, cls.data(), sizeof(int4) * cls.size(), cudaMemcpyHostToDevice));
+    KHG_CUDA_TRY(cudaMemcpy(t.epi_hdr, hdr.data(), sizeof(int2) * hdr.size(), cudaMemcpyHostToDevice));
+    KHG_CUDA_TRY(cudaMemcpy(t.runs, runs.data(), sizeof(uint32_t) * runs.size(), cudaMemcpyHostToDevice));
     KHG_CUDA_TRY(cudaMemcpy(t.seg, seg.data(), sizeof(uint32_t) * seg.size(), cudaMemcpyHostToDevice));
     // a pdf whose Gaussians all have gconst = -inf makes LogSumExp NaN in the reference
     // (csrc/eigen.cc:14-18 -> throw at csrc/decodable-am-diag-gmm.cc:63-65) for every frame
@@ -982,10 +973,9 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   a.offsets = m->d_offsets;
   a.tile_g0 = t.tile_g0;
   a.tile_p0 = t.tile_p0;
-  a.tile_cls0 = t.tile_cls0;
-  a.cls = static_cast<const int4 *>(t.cls);
+  a.epi_hdr = static_cast<const int2 *>(t.epi_hdr);
+  a.runs = t.runs;
   a.seg = t.seg;
-  a.grp_seg0 = t.grp_seg0;
   a.n_tiles = t.n_tiles;
   const int64_t n_m = (T + kTileM - 1) / kTileM;
   // Split the N range when there are too few frame tiles to fill the SMs; keep >= 8
