@@ -58,7 +58,10 @@ template <bool F16> struct Elem {
 constexpr int kAChunkBytes = kTileM * 128;   // 16384
 constexpr int kBStageBytes = kTileN * 128;   // 30720 (multiple of 1024)
 constexpr int kMaxChunks = 5;       // 128-byte K chunks per operand row held in smem
-constexpr int kEpiGroups = 6;       // epilogue warpgroups (4 warps each, one per TMEM lane quadrant); <= 8
+#ifndef KHG_EPI_GROUPS
+#define KHG_EPI_GROUPS 6
+#endif
+constexpr int kEpiGroups = KHG_EPI_GROUPS;       // epilogue warpgroups (4 warps each, one per TMEM lane quadrant); <= 8
 constexpr int kBuilderThreads = 64;
 constexpr int kEpiWarps = 4 * kEpiGroups;      // warps 0..4*kEpiGroups-1: epilogue (TMEM lane quadrant = warp % 4)
 constexpr int kBuilderWarp0 = kEpiWarps;        // warps 16-17: A builders
