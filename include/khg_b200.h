@@ -261,6 +261,61 @@ khg_status khg_mle_update(khg_model *m, const khg_stats *s, const khg_mle_option
 khg_status khg_model_download(khg_model *m, int32_t *gauss_offsets, float *weights,
                               float *means_invvars, float *inv_vars, float *gconsts);
 
+/* ------------------------------------------------- batched forced alignment --
+ * gmm-align-compiled for a batch of utterances on the device: for every
+ * utterance, DecodableAmDiagGmmScaled (csrc/decodable-am-diag-gmm.h:81-109) over the dense
+ * all-pdf block + FasterDecoder::Decode / ReachedFinal / GetBestPath
+ * (csrc/faster-decoder.cc:125-228, 346-425) as driven by AlignUtteranceWrapper
+ * (csrc/decoder-wrappers.cc:16-108): beam, then retry_beam if no final state was reached, with
+ * the decoder options the wrapper leaves at their defaults (max_active = int max,
+ * min_active = 20, beam_delta = 0.5, csrc/faster-decoder.h:41-43).
+ *
+ * The search is the reference's frame-synchronous token passing restated as a pull-style
+ * dynamic programme (one CTA per utterance, one token per graph state, costs in double like
+ * Token::cost_): a state is expanded at frame t iff its cost < best_t + beam (or inside the
+ * min_active cutoff), exactly the reference's rule; among equal-cost predecessors the arc with
+ * the lowest index wins (the reference keeps whichever token its hash list met first, so
+ * results can differ only on exact ties).  The reference's running "next_weight_cutoff" can
+ * additionally keep tokens above the final cutoff alive for one frame; they are never expanded
+ * and can matter only when no in-beam token is final.
+ *
+ * Graphs: the compiled training graphs (fst::VectorFst<StdArc>, after AddTransitionProbs) as
+ * plain arrays, all utterances concatenated.  States and arcs use LOCAL state ids per
+ * utterance; arcs are sorted by source state.  `careful` alignment
+ * (ModifyGraphForCarefulAlignment) is a graph edit the caller applies before export. */
+typedef struct {
+  int32_t n_utts;
+  const int64_t *frame_offsets;  /* n_utts+1: rows of feats belonging to each utterance        */
+  const int32_t *state_offsets;  /* n_utts+1: utterance u owns states [state_offsets[u],
+                                    state_offsets[u+1]) of the concatenated state arrays       */
+  const int32_t *arc_offsets;    /* total_states+1: CSR over ALL states, absolute arc indices  */
+  const int32_t *arc_ilabel;     /* per arc: transition-id, 0 = epsilon                        */
+  const int32_t *arc_nextstate;  /* per arc: LOCAL state id within its utterance               */
+  const float *arc_weight;       /* per arc: tropical cost                                     */
+  const int32_t *start_state;    /* n_utts, local; -1 = empty graph (kNoStateId)               */
+  const float *final_cost;       /* per state; +inf = not final                                */
+} khg_graph_batch;
+
+enum { KHG_ALIGN_OK = 0, KHG_ALIGN_RETRIED = 1, KHG_ALIGN_FAILED = 2 };
+
+/* feats: sum of frames x dim per `feats_loc`; tid2pdf: HOST int32[n_tids] (index 0 unused,
+ * csrc/transition-information.h:71-73); graphs: HOST arrays.
+ * Outputs (HOST, any may be NULL):
+ *   alignment   int32 per frame: the transition-ids of the best path (0 for failed utterances)
+ *   utt_status  int32 per utterance: KHG_ALIGN_OK / _RETRIED / _FAILED
+ *   utt_like    float per utterance: -(graph cost + acoustic cost) / acoustic_scale
+ *   path_arcs   int32, path_offsets[n_utts+1] (int64): absolute arc ids of the best path
+ *               including epsilon arcs, for olabels ("words"); path_capacity entries
+ * pdf_ids_dev: optional DEVICE int32 per frame = tid2pdf[alignment] (0 for the frames of failed
+ * utterances; give those frames weight 0), so that khg_acc_stats_ali can consume the alignment
+ * without leaving the device. */
+khg_status khg_align_batch(khg_model *m, const khg_graph_batch *graphs, const float *feats,
+                           int32_t feats_loc, const int32_t *tid2pdf, int32_t n_tids,
+                           float acoustic_scale, float beam, float retry_beam,
+                           int32_t *alignment, int32_t *utt_status, float *utt_like,
+                           int32_t *path_arcs, int64_t *path_offsets, int64_t path_capacity,
+                           int32_t *pdf_ids_dev);
+
 /* Number of kernels this library launched since load (bench.py's
  * gpu_launches). */
 int64_t khg_launch_count(void);

@@ -1,0 +1,682 @@
+// kaldi-hmm-gmm_b200/csrc/khg_align.cu — khg_align_batch: gmm-align-compiled for a batch of
+// utterances on the device (BASELINE config C5).
+//
+// Reference behaviour restated (paths relative to kaldi-hmm-gmm/csrc/ of the reference):
+//   AlignUtteranceWrapper      decoder-wrappers.cc:16-108  (beam, retry beam, like)
+//   FasterDecoder::Decode      faster-decoder.cc:41-152    (InitDecoding, ProcessNonemitting)
+//   ::ProcessEmitting          faster-decoder.cc:154-228
+//   ::GetCutoff                faster-decoder.cc:230-320   (beam / min_active, beam_delta)
+//   ::ReachedFinal/GetBestPath faster-decoder.cc:346-425
+//   DecodableAmDiagGmmScaled   decodable-am-diag-gmm.h:94-98 (scale * loglike(frame, tid2pdf[tid]))
+//
+// Shape of the computation: the dense kernel (K1) writes the scaled all-pdf block of a chunk of
+// utterances; `viterbi_kernel` then runs ONE CTA per utterance.  The reference's hash of tokens
+// becomes one cost per graph state in shared memory (double, like Token::cost_) and the token
+// passing becomes a pull over each state's incoming arcs (the host transposes every graph
+// once), so there are no atomics and ties are broken by the lowest arc id.  Back-pointers
+// (one int32 arc id per (frame, state)) go to HBM, coalesced; thread 0 walks them back.
+#include <algorithm>
+#include <cfloat>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+#include <math_constants.h>
+
+#include "khg_internal.h"
+
+namespace khg {
+
+// one utterance of the batch, as the kernels see it
+struct UttDesc {
+  int64_t frame0;  // first row of feats / first entry of alignment
+  int64_t bp0;     // first back-pointer of the utterance inside the chunk's buffer
+  int32_t T, S, state0, start;
+  int32_t ed0, n_ed;    // states with incoming epsilon arcs: ed_state[ed0 .. ed0+n_ed)
+  int32_t pdf0, n_pdf;  // distinct pdfs on the graph: utt_pdfs[pdf0 .. pdf0+n_pdf)
+  int32_t col0;         // first column of the utterance in the chunk's likelihood block
+  int32_t pad[3];
+};
+static_assert(sizeof(UttDesc) == 64, "UttDesc layout");
+
+struct AlignDev {
+  const UttDesc *utts;
+  const int32_t *order;     // chunk-local launch order (longest first)
+  const int32_t *in_off;    // total_states+1, absolute into in_arcs
+  const int4 *in_arcs;      // {src (local), local pdf, arc id (absolute), weight bits}
+  const int32_t *ed_state;  // local state ids
+  const int32_t *ed_off;    // n_ed_total+1, absolute into e_arcs
+  const int4 *e_arcs;       // {src (local), arc id (absolute), weight bits, 0}
+  const float *final_cost;  // total_states
+  const int32_t *arc_src;   // per arc: local source state
+  const int32_t *arc_il;    // per arc: ilabel
+  const float *arc_w;       // per arc: weight
+  const int32_t *utt_pdfs;
+  const int32_t *tid2pdf;
+};
+
+struct UttOut {
+  int32_t status, best_state, path_len, pad;
+  float like;
+  int32_t pad2[3];
+};
+
+constexpr int kAlignMinActive = 20;       // faster-decoder.h:42
+constexpr float kAlignBeamDelta = 0.5f;   // faster-decoder.h:43
+constexpr int kMaxWarps = 16;
+
+struct RedScratch {
+  double v[2][kMaxWarps];
+  int n[2][kMaxWarps];
+  int s[2][kMaxWarps];
+};
+
+// (min, sum) over the CTA; one __syncthreads per call (two alternating slots).
+__device__ __forceinline__ void block_min_sum(double &v, int &n, RedScratch *rs, int &slot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    n += __shfl_xor_sync(0xffffffffu, n, o);
+  }
+  if (lane == 0) { rs->v[slot][warp] = v; rs->n[slot][warp] = n; }
+  __syncthreads();
+  double bv = rs->v[slot][0];
+  int bn = rs->n[slot][0];
+  for (int w = 1; w < nw; ++w) { bv = fmin(bv, rs->v[slot][w]); bn += rs->n[slot][w]; }
+  v = bv;
+  n = bn;
+  slot ^= 1;
+}
+
+// lexicographic min over (v, s): lowest state among equal costs
+__device__ __forceinline__ void block_argmin(double &v, int &s, RedScratch *rs, int &slot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int os = __shfl_xor_sync(0xffffffffu, s, o);
+    if (ov < v || (ov == v && os < s)) { v = ov; s = os; }
+  }
+  if (lane == 0) { rs->v[slot][warp] = v; rs->s[slot][warp] = s; }
+  __syncthreads();
+  double bv = rs->v[slot][0];
+  int bs = rs->s[slot][0];
+  for (int w = 1; w < nw; ++w) {
+    double ov = rs->v[slot][w];
+    int os = rs->s[slot][w];
+    if (ov < bv || (ov == bv && os < bs)) { bv = ov; bs = os; }
+  }
+  v = bv;
+  s = bs;
+  slot ^= 1;
+}
+
+// ProcessNonemitting (faster-decoder.cc:57-123) as a Jacobi relaxation over the states that have
+// incoming epsilon arcs: X <- min(X, min over eps arcs (X[src] + w)), a source or a result
+// above `cutoff` does not propagate.  Converges to the same least fixed point as the
+// reference's work queue; on exact ties the earlier token (then the lowest arc id) stays.
+__device__ __forceinline__ void eps_closure(double *X, double *Y, const AlignDev &g, const UttDesc &u, double cutoff,
+                                            int32_t *bp_row, int *s_flag) {
+  if (u.n_ed == 0) return;
+  for (;;) {
+    __syncthreads();  // X complete; previous round's flag consumed
+    if (threadIdx.x == 0) *s_flag = 0;
+    __syncthreads();
+    bool changed = false;
+    for (int i = threadIdx.x; i < u.n_ed; i += blockDim.x) {
+      const int d = g.ed_state[u.ed0 + i];
+      double bc = X[d];
+      int ba = -1;
+      const int k1 = g.ed_off[u.ed0 + i + 1];
+      for (int k = g.ed_off[u.ed0 + i]; k < k1; ++k) {
+        const int4 e = g.e_arcs[k];
+        const double cs = X[e.x];
+        if (!(cs > cutoff)) {
+          const double nc = cs + (double)__int_as_float(e.z);
+          if (!(nc > cutoff) && nc < bc) { bc = nc; ba = e.y; }
+        }
+      }
+      Y[d] = bc;
+      if (ba >= 0) { bp_row[d] = ba; changed = true; }
+    }
+    if (changed) *s_flag = 1;
+    __syncthreads();
+    const bool any = *s_flag != 0;
+    if (!any) break;
+    for (int i = threadIdx.x; i < u.n_ed; i += blockDim.x) {
+      const int d = g.ed_state[u.ed0 + i];
+      X[d] = Y[d];
+    }
+  }
+  __syncthreads();
+}
+
+// One CTA per utterance.  Dynamic shared memory: 3 x S_cap doubles (costs) + n_pdf_cap x FC
+// floats (the utterance's slice of the likelihood block for FC frames); FC == 0 reads the
+// block directly, use_gcost keeps the costs in global scratch (very large graphs).
+__global__ void __launch_bounds__(512) viterbi_kernel(AlignDev g, int u_base, const float *__restrict__ ll, int64_t ld,
+                                                      float beam, float retry_beam, int S_cap, int n_pdf_cap, int FC,
+                                                      double *gcost, int32_t *__restrict__ bp, int32_t *__restrict__ alignment,
+                                                      int32_t *__restrict__ pdf_ids, UttOut *__restrict__ outs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ RedScratch rs;
+  __shared__ int s_flag, s_cnt;
+  __shared__ float s_mac;
+
+  const int ui = u_base + g.order[blockIdx.x];
+  const UttDesc u = g.utts[ui];
+  const int S = u.S, T = u.T, tid = threadIdx.x, NT = blockDim.x;
+  double *cbase = gcost ? gcost + (size_t)blockIdx.x * 3 * S_cap : reinterpret_cast<double *>(smem_raw);
+  double *cur = cbase, *nxt = cbase + S_cap, *alt = cbase + 2 * S_cap;
+  float *tile = reinterpret_cast<float *>(smem_raw + (gcost ? 0 : sizeof(double) * 3 * (size_t)S_cap));
+  int32_t *ubp = bp + u.bp0;
+  const int32_t *in_off = g.in_off + u.state0;
+  const float *fin = g.final_cost + u.state0;
+  const int32_t *upd = g.utt_pdfs + u.pdf0;
+  const double kInf = CUDART_INF;
+  int slot = 0;
+  UttOut res;
+  res.status = KHG_ALIGN_FAILED;
+  res.best_state = -1;
+  res.path_len = 0;
+  res.like = 0.f;
+
+  if (u.start < 0 || S <= 0) {  // empty graph: decoder-wrappers.cc:36-42
+    if (tid == 0) outs[ui] = res;
+    return;
+  }
+
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const float cfg_beam = attempt == 0 ? beam : retry_beam;
+    if (attempt == 1 && retry_beam == 0.f) break;
+    // ---- InitDecoding: start token, then the epsilon closure with cutoff FLT_MAX
+    for (int s = tid; s < S; s += NT) {
+      cur[s] = s == u.start ? 0.0 : kInf;
+      ubp[s] = -1;
+    }
+    eps_closure(cur, alt, g, u, (double)FLT_MAX, ubp, &s_flag);
+    __syncthreads();
+    bool dead = false;
+    for (int t = 0; t < T; ++t) {
+      const int tf = FC ? t % FC : 0;
+      if (FC && tf == 0) {  // stage the next FC frames of this utterance's pdfs (ordered by the sync in the reduction)
+        const int nf = min(FC, T - t);
+        for (int i = tid; i < u.n_pdf * FC; i += NT) {
+          const int j = i / FC, f = i - j * FC;
+          if (f < nf) tile[i] = ll[(int64_t)upd[j] * ld + u.col0 + t + f];
+        }
+      }
+      // ---- GetCutoff
+      double best = kInf;
+      int ntok = 0;
+      for (int s = tid; s < S; s += NT) {
+        const double c = cur[s];
+        if (c < kInf) { best = fmin(best, c); ++ntok; }
+      }
+      block_min_sum(best, ntok, &rs, slot);
+      if (ntok == 0) { dead = true; break; }
+      const double beam_cutoff = best + (double)cfg_beam;
+      // with at most min_active tokens the reference's min_active_cutoff stays +inf, which is
+      // "looser than the beam": nothing is pruned on this frame (faster-decoder.cc:283-310)
+      double weight_cutoff = kInf;
+      float adaptive_beam = CUDART_INF_F;
+      if (ntok > kAlignMinActive) {
+        weight_cutoff = beam_cutoff;
+        adaptive_beam = cfg_beam;
+        // min_active_cutoff = tmp_array_[min_active] (costs rounded to float) exceeds the beam
+        // cutoff iff at most min_active tokens are at or below it
+        int c_le = 0;
+        double dummy = 0.0;
+        for (int s = tid; s < S; s += NT) {
+          const double c = cur[s];
+          if (c < kInf && (double)(float)c <= beam_cutoff) ++c_le;
+        }
+        block_min_sum(dummy, c_le, &rs, slot);
+        if (c_le <= kAlignMinActive) {
+          float *list = reinterpret_cast<float *>(alt);
+          if (tid == 0) s_cnt = 0;
+          __syncthreads();
+          for (int s = tid; s < S; s += NT) {
+            const double c = cur[s];
+            if (c < kInf) list[atomicAdd(&s_cnt, 1)] = (float)c;
+          }
+          __syncthreads();
+          const int n = s_cnt;
+          for (int i = tid; i < n; i += NT) {
+            const float v = list[i];
+            int r = 0;
+            for (int j = 0; j < n; ++j) {
+              const float w = list[j];
+              r += (w < v || (w == v && j < i)) ? 1 : 0;
+            }
+            if (r == kAlignMinActive) s_mac = v;
+          }
+          __syncthreads();
+          const double mac = (double)s_mac;
+          if (mac > beam_cutoff) {
+            weight_cutoff = mac;
+            adaptive_beam = (float)(mac - best + (double)kAlignBeamDelta);
+          }
+        }
+      }
+      // ---- ProcessEmitting as a pull over incoming arcs
+      int32_t *bp_row = ubp + (size_t)(t + 1) * S;
+      double lmin = kInf;
+      for (int d = tid; d < S; d += NT) {
+        double bc = kInf;
+        int ba = -1;
+        const int k1 = in_off[d + 1];
+        for (int k = in_off[d]; k < k1; ++k) {
+          const int4 e = g.in_arcs[k];
+          const double cs = cur[e.x];
+          if (cs < weight_cutoff) {
+            const float lk = FC ? tile[e.y * FC + tf] : ll[(int64_t)upd[e.y] * ld + u.col0 + t];
+            const float ac = -1.f * lk;
+            const double nw = ((double)__int_as_float(e.w) + cs) + (double)ac;
+            if (nw < bc) { bc = nw; ba = e.z; }
+          }
+        }
+        nxt[d] = bc;
+        bp_row[d] = ba;
+        lmin = fmin(lmin, bc);
+      }
+      int dummy_n = 0;
+      block_min_sum(lmin, dummy_n, &rs, slot);
+      const double next_cutoff = lmin + (double)adaptive_beam;
+      for (int d = tid; d < S; d += NT) {
+        if (!(nxt[d] < next_cutoff)) { nxt[d] = kInf; bp_row[d] = -1; }
+      }
+      eps_closure(nxt, alt, g, u, next_cutoff, bp_row, &s_flag);
+      double *tmp = cur; cur = nxt; nxt = tmp;
+    }
+    __syncthreads();
+    // ---- ReachedFinal + the best final token (faster-decoder.cc:346-388)
+    double bf = kInf;
+    int bs = 0x7fffffff;
+    if (!dead) {
+      for (int s = tid; s < S; s += NT) {
+        const double c = cur[s];
+        const float f = fin[s];
+        if (c != kInf && f != CUDART_INF_F) {
+          const double tc = c + (double)f;
+          if (tc != kInf && (tc < bf || (tc == bf && s < bs))) { bf = tc; bs = s; }
+        }
+      }
+    }
+    block_argmin(bf, bs, &rs, slot);
+    if (bs != 0x7fffffff) {
+      res.status = attempt == 0 ? KHG_ALIGN_OK : KHG_ALIGN_RETRIED;
+      res.best_state = bs;
+      break;
+    }
+    __syncthreads();
+  }
+
+  if (tid == 0) {
+    if (res.status != KHG_ALIGN_FAILED) {
+      // traceback: GetBestPath + GetLinearSymbolSequence; like = -(graph + acoustic) / scale is
+      // finished on the host (needs the scale)
+      int t = T, s = res.best_state, n = 0;
+      double graph = (double)fin[s], ac = 0.0;
+      for (;;) {
+        const int a = ubp[(size_t)t * S + s];
+        if (a < 0) break;
+        ++n;
+        const int il = g.arc_il[a];
+        graph += (double)g.arc_w[a];
+        if (il != 0) {
+          --t;
+          alignment[u.frame0 + t] = il;
+          const int pdf = g.tid2pdf[il];
+          if (pdf_ids) pdf_ids[u.frame0 + t] = pdf;
+          ac -= (double)ll[(int64_t)pdf * ld + u.col0 + t];
+        }
+        s = g.arc_src[a];
+      }
+      if (t != 0 || s != u.start) res.status = KHG_ALIGN_FAILED;  // cannot happen (KHG_ASSERT in the reference)
+      res.path_len = n;
+      res.like = (float)(graph + ac);
+    }
+    outs[ui] = res;
+  }
+}
+
+// Second walk over the back-pointers: the arcs of the best path in forward order.
+__global__ void path_kernel(AlignDev g, int u_base, int n, const int32_t *__restrict__ bp, const UttOut *__restrict__ outs,
+                            const int64_t *__restrict__ path_off, int64_t off0, int32_t *__restrict__ path) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const UttDesc u = g.utts[u_base + i];
+  const UttOut o = outs[u_base + i];
+  if (o.status == KHG_ALIGN_FAILED) return;
+  int32_t *dst = path + (path_off[u_base + i] - off0);
+  const int32_t *ubp = bp + u.bp0;
+  int t = u.T, s = o.best_state, k = o.path_len;
+  while (k > 0) {
+    const int a = ubp[(size_t)t * u.S + s];
+    if (a < 0) break;
+    dst[--k] = a;
+    if (g.arc_il[a] != 0) --t;
+    s = g.arc_src[a];
+  }
+}
+
+template <class F>
+static void parallel_for(int n, F f) {
+  int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+  if (n < 64) nt = 1;
+  if (nt == 1) {
+    for (int i = 0; i < n; ++i) f(i, 0);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int w = 0; w < nt; ++w)
+    th.emplace_back([=] {
+      for (int i = w; i < n; i += nt) f(i, w);
+    });
+  for (auto &t : th) t.join();
+}
+
+}  // namespace khg
+
+using namespace khg;
+
+extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, const float *feats, int32_t feats_loc,
+                                      const int32_t *tid2pdf, int32_t n_tids, float acoustic_scale, float beam,
+                                      float retry_beam, int32_t *alignment, int32_t *utt_status, float *utt_like,
+                                      int32_t *path_arcs, int64_t *path_offsets, int64_t path_capacity,
+                                      int32_t *pdf_ids_dev) {
+  KHG_REQUIRE(m && m->uploaded, "model not uploaded");
+  KHG_REQUIRE(gb && gb->n_utts >= 0, "null graph batch");
+  // decoder-wrappers.cc:29-33
+  if ((retry_beam != 0 && retry_beam <= beam) || beam <= 0.0f) {
+    set_error("Beams do not make sense: beam " + std::to_string(beam) + ", retry-beam " + std::to_string(retry_beam));
+    return KHG_ERR_INVALID;
+  }
+  KHG_REQUIRE(acoustic_scale != 0.f, "acoustic_scale must not be 0");
+  const int U = gb->n_utts;
+  if (path_offsets) path_offsets[0] = 0;
+  if (U == 0) return KHG_OK;
+  KHG_REQUIRE(gb->frame_offsets && gb->state_offsets && gb->arc_offsets && gb->start_state && tid2pdf && n_tids > 0,
+              "null graph array");
+  KHG_REQUIRE(!path_arcs || path_offsets, "path_arcs needs path_offsets");
+  const int64_t T_all = gb->frame_offsets[U] - gb->frame_offsets[0];
+  const int32_t S_all = gb->state_offsets[U];
+  KHG_REQUIRE(gb->state_offsets[0] == 0 && gb->arc_offsets[0] == 0, "offsets must start at 0");
+  const int32_t A_all = gb->arc_offsets[S_all];
+  KHG_REQUIRE(A_all == 0 || (gb->arc_ilabel && gb->arc_nextstate && gb->arc_weight), "null arc array");
+  KHG_REQUIRE(S_all == 0 || gb->final_cost, "null final_cost");
+  KHG_REQUIRE(T_all == 0 || feats, "null feats");
+  for (int32_t i = 0; i < n_tids; ++i)
+    KHG_REQUIRE(i == 0 || (tid2pdf[i] >= 0 && tid2pdf[i] < m->P), "tid2pdf entry out of range");
+  const int D = m->dim, P = m->P;
+  cudaStream_t st = m->stream;
+  // KHG_ALIGN_TIMING=1: host-preparation / dense-kernel / search times of the call on stderr
+  const bool timing = getenv("KHG_ALIGN_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  float ms_dense = 0.f, ms_search = 0.f;
+  if (timing)
+    for (auto &e : ev) cudaEventCreate(&e);
+
+  // ---------------- host: transpose every graph (incoming emitting arcs per state, incoming
+  // epsilon arcs per state), local pdf lists
+  std::vector<UttDesc> desc(U);
+  std::vector<int32_t> n_emit(U, 0), n_eps(U, 0), bad(U, 0);
+  std::vector<std::vector<int32_t>> updf(U);
+  std::vector<int32_t> in_off((size_t)S_all + 1, 0), arc_src(A_all), arc_lp(A_all);
+  std::vector<int32_t> eps_deg((size_t)S_all, 0);
+  const int n_workers = 16;
+  std::vector<std::vector<int32_t>> stamp(n_workers, std::vector<int32_t>(P, -1)), lidx(n_workers, std::vector<int32_t>(P, 0));
+  parallel_for(U, [&](int u, int w) {
+    const int32_t s0 = gb->state_offsets[u], s1 = gb->state_offsets[u + 1], S = s1 - s0;
+    UttDesc &d = desc[u];
+    memset(&d, 0, sizeof(d));
+    d.frame0 = gb->frame_offsets[u] - gb->frame_offsets[0];
+    d.T = (int32_t)(gb->frame_offsets[u + 1] - gb->frame_offsets[u]);
+    d.S = S;
+    d.state0 = s0;
+    d.start = gb->start_state[u];
+    if (d.T < 0 || S < 0 || d.start >= S) { bad[u] = 1; return; }
+    auto &st_ = stamp[w];
+    auto &li = lidx[w];
+    for (int32_t s = s0; s < s1; ++s) {
+      if (gb->arc_offsets[s + 1] < gb->arc_offsets[s]) { bad[u] = 1; return; }
+      for (int32_t a = gb->arc_offsets[s]; a < gb->arc_offsets[s + 1]; ++a) {
+        const int32_t ns = gb->arc_nextstate[a], il = gb->arc_ilabel[a];
+        if (ns < 0 || ns >= S || il < 0 || il >= n_tids) { bad[u] = 1; return; }
+        arc_src[a] = s - s0;
+        if (il == 0) {
+          ++n_eps[u];
+          ++eps_deg[s0 + ns];
+        } else {
+          ++n_emit[u];
+          ++in_off[(size_t)s0 + ns + 1];
+          const int32_t pdf = tid2pdf[il];
+          if (st_[pdf] != u) { st_[pdf] = u; li[pdf] = (int32_t)updf[u].size(); updf[u].push_back(pdf); }
+          arc_lp[a] = li[pdf];
+        }
+      }
+    }
+    d.n_pdf = (int32_t)updf[u].size();
+  });
+  for (int u = 0; u < U; ++u)
+    KHG_REQUIRE(!bad[u], "graph of utterance " + std::to_string(u) + ": state / label / offset out of range");
+  // prefix sums: in-arc CSR over all states; epsilon-destination lists
+  for (size_t s = 0; s < (size_t)S_all; ++s) in_off[s + 1] += in_off[s];
+  std::vector<int32_t> ed_state, ed_off(1, 0), utt_pdfs;
+  int64_t eps_total = 0;
+  int S_max = 1, n_pdf_max = 1;
+  for (int u = 0; u < U; ++u) {
+    UttDesc &d = desc[u];
+    d.ed0 = (int32_t)ed_state.size();
+    for (int32_t s = 0; s < d.S; ++s)
+      if (eps_deg[d.state0 + s]) {
+        ed_state.push_back(s);
+        eps_total += eps_deg[d.state0 + s];
+        ed_off.push_back((int32_t)eps_total);
+      }
+    d.n_ed = (int32_t)ed_state.size() - d.ed0;
+    d.pdf0 = (int32_t)utt_pdfs.size();
+    utt_pdfs.insert(utt_pdfs.end(), updf[u].begin(), updf[u].end());
+    S_max = std::max(S_max, d.S);
+    n_pdf_max = std::max(n_pdf_max, d.n_pdf);
+  }
+  const int64_t n_in = in_off[S_all];
+  std::vector<int4> in_arcs((size_t)n_in), e_arcs((size_t)eps_total);
+  parallel_for(U, [&](int u, int) {
+    const UttDesc &d = desc[u];
+    const int32_t s0 = d.state0;
+    std::vector<int32_t> fill(d.S, 0), eslot(d.S, -1), efill(d.n_ed, 0);
+    for (int i = 0; i < d.n_ed; ++i) eslot[ed_state[d.ed0 + i]] = i;
+    for (int32_t s = s0; s < s0 + d.S; ++s)
+      for (int32_t a = gb->arc_offsets[s]; a < gb->arc_offsets[s + 1]; ++a) {
+        const int32_t ns = gb->arc_nextstate[a];
+        int32_t wbits;
+        memcpy(&wbits, &gb->arc_weight[a], 4);
+        if (gb->arc_ilabel[a] != 0) {
+          in_arcs[(size_t)in_off[s0 + ns] + fill[ns]++] = make_int4(s - s0, arc_lp[a], a, wbits);
+        } else {
+          const int i = eslot[ns];
+          e_arcs[(size_t)ed_off[d.ed0 + i] + efill[i]++] = make_int4(s - s0, a, wbits, 0);
+        }
+      }
+  });
+
+  const double t_prep = now();
+  // ---------------- device copy of the graphs
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  size_t o_desc = 0, o_inoff = o_desc + al(sizeof(UttDesc) * U), o_in = o_inoff + al(4 * ((size_t)S_all + 1)),
+         o_eds = o_in + al(16 * (size_t)n_in), o_edo = o_eds + al(4 * ed_state.size()),
+         o_ea = o_edo + al(4 * ed_off.size()), o_fin = o_ea + al(16 * (size_t)eps_total),
+         o_src = o_fin + al(4 * (size_t)S_all), o_il = o_src + al(4 * (size_t)A_all), o_w = o_il + al(4 * (size_t)A_all),
+         o_pdf = o_w + al(4 * (size_t)A_all), o_t2p = o_pdf + al(4 * utt_pdfs.size()),
+         o_ord = o_t2p + al(4 * (size_t)n_tids), o_out = o_ord + al(4 * (size_t)U),
+         o_poff = o_out + al(sizeof(UttOut) * U), o_end = o_poff + al(8 * ((size_t)U + 1));
+  KHG_TRY(m->w_al_graph.reserve(o_end));
+  unsigned char *gbase = m->w_al_graph.as<unsigned char>();
+  auto up = [&](size_t off, const void *src, size_t bytes) -> cudaError_t {
+    return bytes ? cudaMemcpyAsync(gbase + off, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+  };
+
+  // ---------------- chunks of consecutive utterances: bounded likelihood block and back-pointers
+  const int64_t max_block_bytes = 6LL << 30, max_bp_bytes = 8LL << 30;
+  const int64_t max_chunk_frames = std::max<int64_t>(1024, max_block_bytes / (4LL * P));
+  std::vector<int> chunk_start(1, 0);
+  {
+    int64_t fr = 0, bpb = 0;
+    for (int u = 0; u < U; ++u) {
+      const int64_t ub = 4LL * ((int64_t)desc[u].T + 1) * desc[u].S;
+      if (u > chunk_start.back() && (fr + desc[u].T > max_chunk_frames || bpb + ub > max_bp_bytes)) {
+        chunk_start.push_back(u);
+        fr = 0;
+        bpb = 0;
+      }
+      desc[u].bp0 = bpb / 4;
+      desc[u].col0 = (int32_t)fr;
+      fr += desc[u].T;
+      bpb += ub;
+    }
+    chunk_start.push_back(U);
+  }
+  std::vector<int32_t> order(U);
+  size_t bp_bytes_max = 0;
+  int64_t chunk_frames_max = 0;
+  int max_chunk_utts = 0;
+  for (size_t c = 0; c + 1 < chunk_start.size(); ++c) {
+    const int u0 = chunk_start[c], u1 = chunk_start[c + 1];
+    for (int u = u0; u < u1; ++u) order[u] = u - u0;
+    std::stable_sort(order.begin() + u0, order.begin() + u1, [&](int a, int b) {
+      return (int64_t)desc[u0 + a].T * desc[u0 + a].S > (int64_t)desc[u0 + b].T * desc[u0 + b].S;
+    });
+    const UttDesc &l = desc[u1 - 1];
+    bp_bytes_max = std::max(bp_bytes_max, (size_t)(l.bp0 * 4 + 4LL * ((int64_t)l.T + 1) * l.S));
+    chunk_frames_max = std::max<int64_t>(chunk_frames_max, l.col0 + l.T);
+    max_chunk_utts = std::max(max_chunk_utts, u1 - u0);
+  }
+  KHG_CUDA_TRY(up(o_desc, desc.data(), sizeof(UttDesc) * U));
+  KHG_CUDA_TRY(up(o_inoff, in_off.data(), 4 * in_off.size()));
+  KHG_CUDA_TRY(up(o_in, in_arcs.data(), 16 * in_arcs.size()));
+  KHG_CUDA_TRY(up(o_eds, ed_state.data(), 4 * ed_state.size()));
+  KHG_CUDA_TRY(up(o_edo, ed_off.data(), 4 * ed_off.size()));
+  KHG_CUDA_TRY(up(o_ea, e_arcs.data(), 16 * e_arcs.size()));
+  KHG_CUDA_TRY(up(o_fin, gb->final_cost, 4 * (size_t)S_all));
+  KHG_CUDA_TRY(up(o_src, arc_src.data(), 4 * (size_t)A_all));
+  KHG_CUDA_TRY(up(o_il, gb->arc_ilabel, 4 * (size_t)A_all));
+  KHG_CUDA_TRY(up(o_w, gb->arc_weight, 4 * (size_t)A_all));
+  KHG_CUDA_TRY(up(o_pdf, utt_pdfs.data(), 4 * utt_pdfs.size()));
+  KHG_CUDA_TRY(up(o_t2p, tid2pdf, 4 * (size_t)n_tids));
+  KHG_CUDA_TRY(up(o_ord, order.data(), 4 * (size_t)U));
+  AlignDev g;
+  g.utts = reinterpret_cast<const UttDesc *>(gbase + o_desc);
+  g.in_off = reinterpret_cast<const int32_t *>(gbase + o_inoff);
+  g.in_arcs = reinterpret_cast<const int4 *>(gbase + o_in);
+  g.ed_state = reinterpret_cast<const int32_t *>(gbase + o_eds);
+  g.ed_off = reinterpret_cast<const int32_t *>(gbase + o_edo);
+  g.e_arcs = reinterpret_cast<const int4 *>(gbase + o_ea);
+  g.final_cost = reinterpret_cast<const float *>(gbase + o_fin);
+  g.arc_src = reinterpret_cast<const int32_t *>(gbase + o_src);
+  g.arc_il = reinterpret_cast<const int32_t *>(gbase + o_il);
+  g.arc_w = reinterpret_cast<const float *>(gbase + o_w);
+  g.utt_pdfs = reinterpret_cast<const int32_t *>(gbase + o_pdf);
+  g.tid2pdf = reinterpret_cast<const int32_t *>(gbase + o_t2p);
+  UttOut *d_outs = reinterpret_cast<UttOut *>(gbase + o_out);
+  int64_t *d_poff = reinterpret_cast<int64_t *>(gbase + o_poff);
+
+  // ---------------- kernel shape
+  const size_t cost_bytes = sizeof(double) * 3 * (size_t)S_max;
+  const size_t smem_budget = 200 * 1024;
+  const bool use_gcost = cost_bytes > 160 * 1024;
+  int FC = 0;
+  for (int fc : {32, 16, 8})
+    if ((use_gcost ? 0 : cost_bytes) + 4 * (size_t)fc * n_pdf_max <= smem_budget) { FC = fc; break; }
+  const size_t smem = (use_gcost ? 0 : cost_bytes) + 4 * (size_t)FC * n_pdf_max + 16;
+  static std::once_flag once;
+  std::call_once(once, [] { cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
+  const int NT = S_max <= 256 ? 128 : (S_max <= 2048 ? 256 : 512);
+  double *d_gcost = nullptr;
+  if (use_gcost) {
+    KHG_TRY(m->w_al_cost.reserve(sizeof(double) * 3 * (size_t)S_max * max_chunk_utts));
+    d_gcost = m->w_al_cost.as<double>();
+  }
+  const int64_t ld = (chunk_frames_max + 3) & ~(int64_t)3;
+  KHG_TRY(m->w_al_block.reserve(sizeof(float) * (size_t)P * std::max<int64_t>(ld, 4)));
+  KHG_TRY(m->w_al_bp.reserve(std::max<size_t>(bp_bytes_max, 256)));
+  KHG_TRY(m->w_al_ali.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(T_all, 1)));
+  int32_t *d_ali = m->w_al_ali.as<int32_t>();
+  KHG_CUDA_TRY(cudaMemsetAsync(d_ali, 0, sizeof(int32_t) * (size_t)T_all, st));
+  if (pdf_ids_dev) KHG_CUDA_TRY(cudaMemsetAsync(pdf_ids_dev, 0, sizeof(int32_t) * (size_t)T_all, st));
+  float *d_block = m->w_al_block.as<float>();
+  int32_t *d_bp = m->w_al_bp.as<int32_t>();
+  std::vector<UttOut> h_outs(U);
+  std::vector<int64_t> h_poff((size_t)U + 1, 0);
+
+  for (size_t c = 0; c + 1 < chunk_start.size(); ++c) {
+    const int u0 = chunk_start[c], u1 = chunk_start[c + 1];
+    const int64_t f0 = desc[u0].frame0, nfr = desc[u1 - 1].frame0 + desc[u1 - 1].T - f0;
+    if (timing) cudaEventRecord(ev[0], st);
+    if (nfr > 0) {
+      const float *d_f = feats + (gb->frame_offsets[0] + f0) * D;
+      if (feats_loc == KHG_HOST) {
+        KHG_TRY(m->w_feats.reserve(sizeof(float) * (size_t)nfr * D));
+        KHG_CUDA_TRY(cudaMemcpyAsync(m->w_feats.p, d_f, sizeof(float) * (size_t)nfr * D, cudaMemcpyHostToDevice, st));
+        d_f = m->w_feats.as<float>();
+      }
+      KHG_TRY(dense_block(m, d_f, nfr, acoustic_scale, KHG_PDF_MAJOR, d_block, ld));
+    }
+    if (timing) cudaEventRecord(ev[1], st);
+    g.order = reinterpret_cast<const int32_t *>(gbase + o_ord) + u0;
+    viterbi_kernel<<<u1 - u0, NT, smem, st>>>(g, u0, d_block, ld, beam, retry_beam, S_max, n_pdf_max, FC, d_gcost, d_bp,
+                                              d_ali, pdf_ids_dev, d_outs);
+    ++g_launch_count;
+    KHG_CUDA_TRY(cudaGetLastError());
+    if (timing) cudaEventRecord(ev[2], st);
+    KHG_CUDA_TRY(cudaMemcpyAsync(h_outs.data() + u0, d_outs + u0, sizeof(UttOut) * (u1 - u0), cudaMemcpyDeviceToHost, st));
+    KHG_TRY(sync_and_check(m));
+    if (timing) {
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, ev[0], ev[1]);
+      cudaEventElapsedTime(&b, ev[1], ev[2]);
+      ms_dense += a;
+      ms_search += b;
+    }
+    if (path_arcs) {
+      for (int u = u0; u < u1; ++u) h_poff[u + 1] = h_poff[u] + (h_outs[u].status == KHG_ALIGN_FAILED ? 0 : h_outs[u].path_len);
+      const int64_t n_path = h_poff[u1] - h_poff[u0];
+      KHG_REQUIRE(h_poff[u1] <= path_capacity, "path_capacity too small");
+      if (n_path > 0) {
+        KHG_TRY(m->w_al_path.reserve(sizeof(int32_t) * (size_t)n_path));
+        KHG_CUDA_TRY(cudaMemcpyAsync(d_poff + u0, h_poff.data() + u0, 8 * (size_t)(u1 - u0), cudaMemcpyHostToDevice, st));
+        path_kernel<<<(u1 - u0 + 63) / 64, 64, 0, st>>>(g, u0, u1 - u0, d_bp, d_outs, d_poff, h_poff[u0],
+                                                        m->w_al_path.as<int32_t>());
+        ++g_launch_count;
+        KHG_CUDA_TRY(cudaGetLastError());
+        KHG_CUDA_TRY(cudaMemcpyAsync(path_arcs + h_poff[u0], m->w_al_path.p, sizeof(int32_t) * (size_t)n_path,
+                                     cudaMemcpyDeviceToHost, st));
+        KHG_CUDA_TRY(cudaStreamSynchronize(st));
+      }
+    }
+  }
+  if (alignment && T_all > 0)
+    KHG_CUDA_TRY(cudaMemcpyAsync(alignment, d_ali, sizeof(int32_t) * (size_t)T_all, cudaMemcpyDeviceToHost, st));
+  KHG_CUDA_TRY(cudaStreamSynchronize(st));
+  if (timing) {
+    fprintf(stderr, "khg_align_batch: utts %d frames %lld states %d arcs %d | S_max %d n_pdf_max %d FC %d NT %d smem %zu chunks %zu | "
+            "host prep %.2f ms, dense %.2f ms, search %.2f ms, total %.2f ms\n", U, (long long)T_all, S_all, A_all, S_max, n_pdf_max,
+            FC, NT, smem, chunk_start.size() - 1, t_prep - t_begin, ms_dense, ms_search, now() - t_begin);
+    for (auto &e : ev) cudaEventDestroy(e);
+  }
+  for (int u = 0; u < U; ++u) {
+    if (utt_status) utt_status[u] = h_outs[u].status;
+    // decoder-wrappers.cc:91: like = -(graph + acoustic) / acoustic_scale
+    if (utt_like) utt_like[u] = h_outs[u].status == KHG_ALIGN_FAILED ? 0.f : -h_outs[u].like / acoustic_scale;
+    if (path_offsets) path_offsets[u + 1] = h_poff[u + 1];
+  }
+  return KHG_OK;
+}

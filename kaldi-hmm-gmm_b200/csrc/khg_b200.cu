@@ -264,7 +264,8 @@ void khg_model_destroy(khg_model *m) {
   cudaFree(m->d_grp_start); cudaFree(m->d_pack8); cudaFree(m->d_gc8);
   for (Buf *b : {&m->w_feats, &m->w_ids, &m->w_wts, &m->w_out, &m->w_pf, &m->w_keys, &m->w_vals_in,
                  &m->w_vals_out, &m->w_cub, &m->w_starts, &m->w_item_start, &m->w_tot, &m->w_tid,
-                 &m->w_tid2pdf, &m->w_trans, &m->w_keys_out, &m->w_sub, &m->w_full})
+                 &m->w_tid2pdf, &m->w_trans, &m->w_keys_out, &m->w_sub, &m->w_full, &m->w_al_graph,
+                 &m->w_al_block, &m->w_al_bp, &m->w_al_cost, &m->w_al_ali, &m->w_al_path})
     b->release();
   for (int i = 0; i < 2; ++i) {
     m->pin_feats[i].release(); m->pin_ids[i].release(); m->pin_wts[i].release();
@@ -1004,3 +1005,10 @@ khg_status khg_estep(khg_model *m, khg_stats *s, const float *feats, int64_t T, 
 }
 
 }  // extern "C"
+
+namespace khg {
+khg_status dense_block(khg_model *m, const float *d_feats, int64_t T, float scale, int layout, float *d_out, int64_t ld) {
+  return dense_device(m, d_feats, T, scale, layout, d_out, ld);
+}
+khg_status sync_and_check(khg_model *m) { return sync_check(m); }
+}  // namespace khg

@@ -133,6 +133,7 @@ struct khg_model {
   khg::Buf w_starts, w_item_start, w_tot;              // per-pdf starts, work items, totals
   khg::Buf w_tid, w_tid2pdf, w_trans;                  // tid path
   khg::Buf w_sub, w_full;                              // pdf-subset gather
+  khg::Buf w_al_graph, w_al_block, w_al_bp, w_al_cost, w_al_ali, w_al_path;  // khg_align_batch (khg_align.cu)
   khg::Buf pin_feats[2], pin_ids[2], pin_wts[2];       // pinned staging for estep(HOST)
   khg::Buf w_efeats[2], w_eids[2], w_ewts[2];
 };
@@ -156,6 +157,10 @@ bool tc_supported(const khg_model *m);
 khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale,
                        float *d_out, int64_t ld_out, int precision, const unsigned **simt_gate,
                        float *gate_limit);
+// khg_b200.cu: the dense all-pdf block of device-resident frames (kernel choice of the model),
+// and the synchronising read of the latched device error flag
+khg_status dense_block(khg_model *m, const float *d_feats, int64_t T, float scale, int layout, float *d_out, int64_t ld);
+khg_status sync_and_check(khg_model *m);
 }  // namespace khg
 
 #endif  // KHG_INTERNAL_H_

@@ -59,8 +59,16 @@ SYMBOLS = [
     ("khg_estep", _i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _i64, C.POINTER(C.c_double)]),
     ("khg_mle_update", _i32, [_vp, _vp, _vp, _u16, C.POINTER(_vp), C.POINTER(_f32), C.POINTER(_f32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     ("khg_model_download", _i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    ("khg_align_batch", _i32, [_vp, _vp, _vp, _i32, _vp, _i32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     ("khg_launch_count", _i64, []),
 ]
+KHG_ALIGN_OK, KHG_ALIGN_RETRIED, KHG_ALIGN_FAILED = 0, 1, 2
+
+
+class GraphBatch(C.Structure):
+    """khg_graph_batch of include/khg_b200.h (all HOST arrays)."""
+    _fields_ = [("n_utts", _i32), ("frame_offsets", _vp), ("state_offsets", _vp), ("arc_offsets", _vp), ("arc_ilabel", _vp),
+                ("arc_nextstate", _vp), ("arc_weight", _vp), ("start_state", _vp), ("final_cost", _vp)]
 
 _lib = None
 

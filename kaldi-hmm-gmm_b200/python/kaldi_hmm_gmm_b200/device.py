@@ -142,6 +142,78 @@ class DeviceModel:
         return ll, post
 
 
+class GraphBatch:
+    """Compiled training graphs of a batch of utterances as plain arrays (khg_graph_batch,
+    include/khg_b200.h): what a maintainer exports from `fst::VectorFst<StdArc>` after
+    AddTransitionProbs (reference scripts/gmm_align_compiled.py:36-41).
+
+    graphs: sequence of objects with arc_offsets[S+1], ilabel[A], olabel[A] (optional), weight[A],
+    nextstate[A], final[S] (inf = not final), start — arcs sorted by source state.
+    num_frames: frames of each utterance (rows of the concatenated feature matrix)."""
+
+    def __init__(self, graphs, num_frames):
+        assert len(graphs) == len(num_frames)
+        i32 = lambda x: np.ascontiguousarray(x, np.int32)  # noqa: E731
+        self.n_utts = len(graphs)
+        self.frame_offsets = np.concatenate([[0], np.cumsum(np.asarray(num_frames, np.int64))]).astype(np.int64)
+        ns = [int(np.asarray(g.arc_offsets).size) - 1 for g in graphs]
+        self.state_offsets = np.concatenate([[0], np.cumsum(ns)]).astype(np.int32)
+        offs, base = [np.zeros(1, np.int64)], 0
+        for g in graphs:
+            ao = np.asarray(g.arc_offsets, np.int64)
+            offs.append(ao[1:] + base)
+            base += int(ao[-1])
+        self.arc_offsets = i32(np.concatenate(offs))
+        cat = lambda name, dt: np.ascontiguousarray(  # noqa: E731
+            np.concatenate([np.asarray(getattr(g, name), dt) for g in graphs]) if graphs else np.zeros(0, dt), dt)
+        self.arc_ilabel, self.arc_nextstate = cat("ilabel", np.int32), cat("nextstate", np.int32)
+        self.arc_weight, self.final_cost = cat("weight", np.float32), cat("final", np.float32)
+        self.arc_olabel = cat("olabel", np.int32) if all(hasattr(g, "olabel") for g in graphs) else None
+        self.start_state = i32([g.start for g in graphs])
+
+    def c_struct(self) -> "A.GraphBatch":
+        d = lambda a: a.ctypes.data  # noqa: E731
+        return A.GraphBatch(self.n_utts, d(self.frame_offsets), d(self.state_offsets), d(self.arc_offsets), d(self.arc_ilabel),
+                            d(self.arc_nextstate), d(self.arc_weight), d(self.start_state), d(self.final_cost))
+
+
+def align_batch(model: DeviceModel, graphs: GraphBatch, feats, tid2pdf, acoustic_scale: float = 1.0, beam: float = 200.0,
+                retry_beam: float = 0.0, want_paths: bool = True, pdf_ids_out=None):
+    """gmm-align-compiled for a batch of utterances in ONE call (khg_align_batch): dense
+    log-likelihoods (K1) + per-utterance Viterbi on the device.  Returns dict(alignment int32
+    per frame, status per utterance (0 ok / 1 ok after retry / 2 failed), like per utterance,
+    path_offsets, path_arcs (absolute arc ids, epsilons included), words (if the graphs carry olabels))."""
+    fp, floc = A.ptr(feats, np.float32)
+    T = int(graphs.frame_offsets[-1])
+    assert int(feats.shape[0]) >= T and int(feats.shape[1]) == model.dim
+    t2p = np.ascontiguousarray(tid2pdf, np.int32)
+    U = graphs.n_utts
+    ali = np.zeros(T, np.int32)
+    status = np.zeros(U, np.int32)
+    like = np.zeros(U, np.float32)
+    poff = np.zeros(U + 1, np.int64)
+    cap = int(T + T // 2 + 16 * U + 1024) if want_paths else 0
+    # a path has one arc per frame plus its epsilon arcs: T + (epsilon arcs on the path); retried below if short
+    pdp, ploc = A.ptr(pdf_ids_out, np.int32)
+    assert pdf_ids_out is None or ploc == A.KHG_DEVICE
+    gs = graphs.c_struct()
+    while True:
+        paths = np.zeros(cap, np.int32) if want_paths else None
+        st = A.lib().khg_align_batch(model._h, C.byref(gs), fp, floc, t2p.ctypes.data, t2p.size, acoustic_scale, beam, retry_beam,
+                                     ali.ctypes.data, status.ctypes.data, like.ctypes.data,
+                                     None if paths is None else paths.ctypes.data, poff.ctypes.data, cap, pdp)
+        if st != A.KHG_OK and want_paths and b"path_capacity" in (A.lib().khg_last_error() or b""):
+            cap *= 4
+            continue
+        A.check(st)
+        break
+    out = dict(alignment=ali, status=status, like=like, path_offsets=poff, path_arcs=None if paths is None else paths[:poff[-1]])
+    if want_paths and graphs.arc_olabel is not None:
+        ol = graphs.arc_olabel[out["path_arcs"]]
+        out["words"] = [ol[poff[u]:poff[u + 1]][ol[poff[u]:poff[u + 1]] != 0] for u in range(U)]
+    return out
+
+
 class DeviceStats:
     """Packed device AccumAmDiagGmm: [occ G | mean G*D | var G*D | tot_like, tot_frames] fp64."""
 

@@ -1,0 +1,194 @@
+"""GPU parity of khg_align_batch (include/khg_b200.h; SURVEY.md 8f row 2, BASELINE config C5):
+the batched device aligner against the CPU restatement of FasterDecoder + AlignUtteranceWrapper
+(oracle/khg_align_oracle.py; reference csrc/faster-decoder.cc, csrc/decoder-wrappers.cc).
+
+Integer outputs (alignment, status, best-path arcs, words) must be bit-exact given the same
+likelihoods; the per-utterance log-likelihood is float (1e-5 relative)."""
+import numpy as np
+import pytest
+
+from oracle import khg_align_oracle as ao
+from oracle import khg_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(seed, n_utts, P=37, D=13, G=150, n_phones=(3, 14), noise=1.0, alt_prob=0.3):
+    rng = np.random.default_rng(seed)
+    model, means, vars_ = ko.make_synthetic_model(D, P, G)
+    graphs, feats, n_tids = [], [], 1
+    for _ in range(n_utts):
+        phones = [int(x) for x in rng.integers(0, 12, int(rng.integers(*n_phones)))]
+        g, nt = ao.make_training_graph(rng, phones, alt_prob=alt_prob)
+        graphs.append(g)
+        n_tids = max(n_tids, nt)
+    t2p = ao.make_tid2pdf(n_tids, P)
+    for g in graphs:
+        f, _ = ao.sample_utterance(rng, g, t2p, model, means, vars_, noise=noise)
+        feats.append(f)
+    return model, graphs, feats, t2p
+
+
+def _model_moments(model):
+    """(means, vars) of the packed model's Gaussians (exponential form -> moments)."""
+    vars_ = 1.0 / model.inv_vars
+    return model.means_invvars * vars_, vars_
+
+
+def _device_model(model):
+    from kaldi_hmm_gmm_b200 import DeviceModel
+
+    dm = DeviceModel(model.dim, model.offsets)
+    dm.upload(model.weights, model.means_invvars, model.inv_vars)
+    return dm
+
+
+def _run(dm, graphs, feats, t2p, scale, beam, retry, device_feats=False):
+    import torch
+    from kaldi_hmm_gmm_b200 import GraphBatch, align_batch
+    from kaldi_hmm_gmm_b200 import _cabi as A
+
+    lens = [f.shape[0] for f in feats]
+    allf = np.ascontiguousarray(np.concatenate(feats, 0), np.float32) if feats else np.zeros((0, dm.dim), np.float32)
+    gb = GraphBatch(graphs, lens)
+    pdf_ids = torch.full((max(1, allf.shape[0]),), -7, dtype=torch.int32, device="cuda")
+    out = align_batch(dm, gb, torch.from_numpy(allf).cuda() if device_feats else allf, t2p, scale, beam, retry,
+                      pdf_ids_out=pdf_ids)
+    # the likelihoods the device search saw (same kernel, same scale)
+    ll = dm.loglikes_all_pdfs(allf, scale=1.0, layout=A.KHG_PDF_MAJOR) if allf.shape[0] else np.zeros((dm.num_pdfs, 0), np.float32)
+    return out, ll, gb, pdf_ids.cpu().numpy()[: allf.shape[0]]
+
+
+def _check(out, ll, gb, graphs, t2p, scale, beam, retry, pdf_ids):
+    fo = gb.frame_offsets
+    arc0 = 0
+    for u, g in enumerate(graphs):
+        ref = ao.align_utterance(g, np.ascontiguousarray(ll[:, fo[u]:fo[u + 1]]), t2p, scale, beam=beam, retry_beam=retry, tight=True)
+        assert out["status"][u] == ref["status"], (u, out["status"][u], ref["status"])
+        got_ali = out["alignment"][fo[u]:fo[u + 1]]
+        if ref["status"] == 2:
+            assert not got_ali.any() and out["like"][u] == 0.0
+            assert out["path_offsets"][u + 1] == out["path_offsets"][u]
+            assert not pdf_ids[fo[u]:fo[u + 1]].any()
+        else:
+            assert got_ali.tolist() == ref["alignment"], u          # bit-exact
+            path = out["path_arcs"][out["path_offsets"][u]:out["path_offsets"][u + 1]] - arc0
+            assert path.tolist() == ref["path"], u                  # bit-exact, epsilons included
+            assert out["words"][u].tolist() == ref["words"], u
+            assert abs(out["like"][u] - ref["like"]) <= 1e-5 * abs(ref["like"]) + 1e-4
+            assert pdf_ids[fo[u]:fo[u + 1]].tolist() == t2p[got_ali].tolist()
+        arc0 += g.num_arcs
+
+
+@pytest.mark.parametrize("beam,retry", [(200.0, 0.0), (6.0, 40.0), (2.0, 12.0)])
+@pytest.mark.parametrize("scale", [1.0, 0.1])
+def test_align_batch_matches_oracle(beam, retry, scale):
+    model, graphs, feats, t2p = _batch(11, 24)
+    dm = _device_model(model)
+    out, ll, gb, pdf_ids = _run(dm, graphs, feats, t2p, scale, beam, retry)
+    _check(out, ll, gb, graphs, t2p, scale, beam, retry, pdf_ids)
+    assert (out["status"] == 0).sum() >= 20
+
+
+def test_align_batch_device_features_and_oracle_likelihoods():
+    """Device-resident features; and the same alignment from the ORACLE's likelihoods (the two
+    likelihood paths agree within 1e-3, far below the margins between paths on this data)."""
+    model, graphs, feats, t2p = _batch(5, 16)
+    dm = _device_model(model)
+    out, ll, gb, pdf_ids = _run(dm, graphs, feats, t2p, 1.0, 10.0, 40.0, device_feats=True)
+    _check(out, ll, gb, graphs, t2p, 1.0, 10.0, 40.0, pdf_ids)
+    ora = ko.Oracle()
+    fo = gb.frame_offsets
+    for u, g in enumerate(graphs):
+        ref_ll, _ = ora.loglikes_all_pdfs(model, feats[u])
+        ref = ao.align_utterance(g, np.ascontiguousarray(ref_ll.T), t2p, 1.0, beam=10.0, retry_beam=40.0)  # reference pruning order
+        assert out["alignment"][fo[u]:fo[u + 1]].tolist() == ref["alignment"]
+
+
+def _bushy_utt(rng, model, means, vars_, P):
+    """One short correct chain among 39 chains that are longer than the utterance; the first two
+    frames look like another chain, so a narrow beam + min_active prunes the only chain that can
+    reach a final state: first pass fails, the retry beam recovers it."""
+    g, nt = ao.make_bushy_graph(rng, [4] + [30] * 39, P)
+    t2p = ao.make_tid2pdf(nt, P)
+    st, path = 0, []
+    for _ in range(4):
+        fwd = [a for a in range(g.arc_offsets[st], g.arc_offsets[st + 1]) if g.nextstate[a] != st][0]
+        path.append(int(g.ilabel[fwd]))
+        st = int(g.nextstate[fwd])
+        loop = [a for a in range(g.arc_offsets[st], g.arc_offsets[st + 1]) if g.nextstate[a] == st][0]
+        path += [int(g.ilabel[loop])] * 2
+    pdfs = [int(t2p[t]) for t in path]
+    pdfs[0] = pdfs[1] = int(t2p[g.ilabel[g.arc_offsets[0] + 5]])
+    k = [int(model.offsets[p]) for p in pdfs]
+    feats = (means[k] + 0.3 * np.sqrt(vars_[k]) * rng.standard_normal((len(k), means.shape[1]))).astype(np.float32)
+    return g, feats, nt
+
+
+def test_align_batch_retries_and_failures():
+    """First passes that die under a narrow beam and are retried (status 1) or fail (status 2);
+    plus a too-short utterance, a zero-frame utterance and an empty graph in the same batch."""
+    P = 37
+    model, graphs, feats, t2p = _batch(23, 10, P=P, noise=3.0)
+    rng = np.random.default_rng(0)
+    n_tids = t2p.size
+    for _ in range(6):
+        g, f, nt = _bushy_utt(rng, model, *_model_moments(model), P)
+        graphs.append(g)
+        feats.append(f)
+        n_tids = max(n_tids, nt)
+    t2p = ao.make_tid2pdf(n_tids, P)
+    feats[3] = feats[3][:2]                      # cannot reach a final state
+    feats[5] = feats[5][:0]                      # no frames
+    graphs[7].start = -1                         # empty graph (fst::kNoStateId)
+    dm = _device_model(model)
+    seen = set()
+    for beam, retry in [(0.5, 0.0), (0.5, 1e4), (1e4, 0.0)]:
+        out, ll, gb, pdf_ids = _run(dm, graphs, feats, t2p, 1.0, beam, retry)
+        _check(out, ll, gb, graphs, t2p, 1.0, beam, retry, pdf_ids)
+        assert out["status"][3] == 2 and out["status"][5] == 2 and out["status"][7] == 2
+        seen |= {(retry != 0.0, int(x)) for x in out["status"][10:]}
+    assert (False, 2) in seen and (True, 1) in seen and (False, 0) in seen
+
+
+def test_align_batch_many_tokens_min_active_paths():
+    """Graphs with many parallel branches (> min_active tokens alive) under a narrow beam
+    exercise both the beam cutoff and the min_active cutoff of GetCutoff."""
+    model, graphs, feats, t2p = _batch(31, 12, n_phones=(10, 20), alt_prob=0.9, noise=2.0)
+    dm = _device_model(model)
+    for beam in (0.3, 1.5, 4.0):
+        out, ll, gb, pdf_ids = _run(dm, graphs, feats, t2p, 1.0, beam, 0.0)
+        _check(out, ll, gb, graphs, t2p, 1.0, beam, 0.0, pdf_ids)
+
+
+def test_align_batch_feeds_acc_stats_on_device():
+    """gmm-align-compiled -> gmm-acc-stats-ali without leaving the device: the pdf ids written by
+    the aligner drive khg_acc_stats_ali; stats equal the oracle's on the oracle's alignment."""
+    import torch
+    from kaldi_hmm_gmm_b200 import DeviceStats, GraphBatch, align_batch
+
+    model, graphs, feats, t2p = _batch(41, 10)
+    dm = _device_model(model)
+    allf = np.ascontiguousarray(np.concatenate(feats, 0), np.float32)
+    dfe = torch.from_numpy(allf).cuda()
+    pdf_ids = torch.zeros(allf.shape[0], dtype=torch.int32, device="cuda")
+    out = align_batch(dm, GraphBatch(graphs, [f.shape[0] for f in feats]), dfe, t2p, 1.0, 200.0, 0.0, want_paths=False,
+                      pdf_ids_out=pdf_ids)
+    assert (out["status"] == 0).all()
+    st = DeviceStats(dm)
+    st.acc_stats_ali(dfe, pdf_ids)
+    got = st.download()
+    ref = ko.Oracle().acc_stats_ali(model, allf, t2p[out["alignment"]].astype(np.int32))
+    for k in ("occ", "mean", "var"):
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-4, atol=1e-6 * np.abs(ref[k]).max())
+
+
+def test_align_batch_rejects_bad_arguments():
+    model, graphs, feats, t2p = _batch(2, 3)
+    dm = _device_model(model)
+    with pytest.raises(RuntimeError, match="Beams do not make sense"):
+        _run(dm, graphs, feats, t2p, 1.0, 10.0, 5.0)
+    graphs[1].nextstate = graphs[1].nextstate.copy()
+    graphs[1].nextstate[0] = 10 ** 6
+    with pytest.raises(RuntimeError, match="out of range"):
+        _run(dm, graphs, feats, t2p, 1.0, 10.0, 0.0)
