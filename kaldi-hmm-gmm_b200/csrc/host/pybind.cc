@@ -224,6 +224,44 @@ PYBIND11_MODULE(_khg_b200, m) {
              return out;
            },
            py::arg("feats"), py::arg("scale") = 1.0f)
+      // new, batched: gmm-align-compiled for many utterances in one call (khg_align_batch);
+      // graphs as the plain arrays of khg_graph_batch (include/khg_b200.h)
+      .def("align_batch",
+           [](const AmDiagGmm &s, const FArr &feats, const py::array_t<int64_t, py::array::c_style | py::array::forcecast> &frame_offsets,
+              const IArr &state_offsets, const IArr &arc_offsets, const IArr &arc_ilabel, const IArr &arc_nextstate,
+              const FArr &arc_weight, const IArr &start_state, const FArr &final_cost, const IArr &tid2pdf, float acoustic_scale,
+              float beam, float retry_beam, bool want_paths) {
+             if (feats.ndim() != 2 || feats.shape(1) != s.Dim()) throw std::runtime_error("feats must be (T, dim)");
+             const int32_t U = (int32_t)start_state.shape(0);
+             if (frame_offsets.shape(0) != U + 1 || state_offsets.shape(0) != U + 1)
+               throw std::runtime_error("frame_offsets / state_offsets must have n_utts + 1 entries");
+             const int64_t T = U ? frame_offsets.data()[U] : 0;
+             if (T > feats.shape(0)) throw std::runtime_error("frame_offsets exceed the feature matrix");
+             khg_graph_batch gb{U, frame_offsets.data(), state_offsets.data(), arc_offsets.data(), arc_ilabel.data(),
+                                arc_nextstate.data(), arc_weight.data(), start_state.data(), final_cost.data()};
+             py::array_t<int32_t> ali((py::ssize_t)T), status((py::ssize_t)U);
+             py::array_t<float> like((py::ssize_t)U);
+             py::array_t<int64_t> poff((py::ssize_t)U + 1);
+             int64_t cap = want_paths ? T + T / 2 + 16 * (int64_t)U + 1024 : 0;
+             py::array_t<int32_t> paths;
+             for (;;) {
+               paths = py::array_t<int32_t>((py::ssize_t)cap);
+               khg_status st = khg_align_batch(s.Device(), &gb, feats.data(), KHG_HOST, tid2pdf.data(), (int32_t)tid2pdf.shape(0),
+                                               acoustic_scale, beam, retry_beam, ali.mutable_data(), status.mutable_data(),
+                                               like.mutable_data(), want_paths ? paths.mutable_data() : nullptr,
+                                               poff.mutable_data(), cap, nullptr);
+               if (st != KHG_OK && want_paths && std::string(khg_last_error()).find("path_capacity") != std::string::npos) {
+                 cap *= 4;
+                 continue;
+               }
+               Check(st);
+               break;
+             }
+             return py::make_tuple(ali, status, like, poff, paths);
+           },
+           py::arg("feats"), py::arg("frame_offsets"), py::arg("state_offsets"), py::arg("arc_offsets"), py::arg("arc_ilabel"),
+           py::arg("arc_nextstate"), py::arg("arc_weight"), py::arg("start_state"), py::arg("final_cost"), py::arg("tid2pdf"),
+           py::arg("acoustic_scale") = 1.0f, py::arg("beam") = 200.0f, py::arg("retry_beam") = 0.0f, py::arg("want_paths") = true)
       .def(py::pickle(  // 3 arrays per pdf: python/csrc/am-diag-gmm.cc:47-71
           [](const AmDiagGmm &s) {
             py::tuple t(s.NumPdfs() * 3);
@@ -405,6 +443,18 @@ PYBIND11_MODULE(_khg_b200, m) {
         return std::make_pair(oc, c);
       },
       py::arg("config"), py::arg("amdiag_gmm_acc"), py::arg("flags"), py::arg("am_gmm"));
+
+  // ---- AlignConfig (python/csrc/decoder-wrappers.cc:15-23; csrc/decoder-wrappers.h:22-36) ----
+  struct AlignConfig {
+    float beam, retry_beam;
+    bool careful;
+  };
+  py::class_<AlignConfig>(m, "AlignConfig")
+      .def(py::init([](float beam, float retry_beam, bool careful) { return AlignConfig{beam, retry_beam, careful}; }),
+           py::arg("beam") = 200.0f, py::arg("retry_beam") = 0.0f, py::arg("careful") = false)
+      .def_readwrite("beam", &AlignConfig::beam)
+      .def_readwrite("retry_beam", &AlignConfig::retry_beam)
+      .def_readwrite("careful", &AlignConfig::careful);
 
   // ---- decodables (python/csrc/decodable-itf.cc, decodable-am-diag-gmm.cc) ----
   py::class_<DecodableInterface, PyDecodableInterface>(m, "DecodableInterface")

@@ -526,8 +526,15 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   };
 
   // ---------------- chunks of consecutive utterances: bounded likelihood block and back-pointers
-  const int64_t max_block_bytes = 6LL << 30, max_bp_bytes = 8LL << 30;
-  const int64_t max_chunk_frames = std::max<int64_t>(1024, max_block_bytes / (4LL * P));
+  // (a quarter of the free HBM each, at most 24 GB: more utterances per launch = more CTAs per SM
+  // for the latency-bound search)
+  size_t mem_free = 0, mem_total = 0;
+  KHG_CUDA_TRY(cudaMemGetInfo(&mem_free, &mem_total));
+  mem_free += m->w_al_block.cap + m->w_al_bp.cap;  // what an earlier call already holds is reusable
+  const int64_t budget = std::max<int64_t>(256LL << 20, std::min<int64_t>(24LL << 30, (int64_t)(mem_free / 4)));
+  const int64_t max_block_bytes = budget, max_bp_bytes = budget;
+  int64_t max_chunk_frames = std::max<int64_t>(1024, max_block_bytes / (4LL * P));
+  if (const char *e = getenv("KHG_ALIGN_CHUNK_FRAMES")) max_chunk_frames = std::max<int64_t>(1, atoll(e));  // tests: force several chunks
   std::vector<int> chunk_start(1, 0);
   {
     int64_t fr = 0, bpb = 0;

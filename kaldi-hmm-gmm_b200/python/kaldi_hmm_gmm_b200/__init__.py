@@ -15,7 +15,8 @@ from .device import DeviceModel, DeviceStats, GraphBatch, align_batch  # noqa: F
 try:  # the pybind11 mirror of the reference classes (built by __graft_entry__.build())
     from ._khg_b200 import *  # noqa: F401,F403
     from ._khg_b200 import __doc__ as _ext_doc  # noqa: F401
-    from .scripts import gmm_acc_stats_ali, gmm_est, make_decodable, make_decodables  # noqa: F401
+    from .scripts import (TrainingGraph, gmm_acc_stats_ali, gmm_align_compiled, gmm_align_compiled_batch, gmm_est,  # noqa: F401
+                          make_decodable, make_decodables)
     HAVE_EXTENSION = True
 except ImportError as _e:  # pragma: no cover - reported loudly on use
     HAVE_EXTENSION = False

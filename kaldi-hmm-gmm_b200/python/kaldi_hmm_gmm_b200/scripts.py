@@ -81,3 +81,118 @@ def make_decodables(am_gmm, transition_model, feats_list, acoustic_scale: float 
         out.append(_ext.DecodableAmDiagGmmScaled.from_block(np.ascontiguousarray(block[t0:t0 + n].T), t2p, acoustic_scale))
         t0 += n
     return out
+
+
+class TrainingGraph:
+    """One compiled training graph as plain arrays — what `fst::VectorFst<StdArc>` holds after
+    `add_transition_probs` (reference scripts/gmm_align_compiled.py:36-41): arcs sorted by source
+    state, `arc_offsets[s]..arc_offsets[s+1]`; `final[s]` = final cost, inf = not final."""
+
+    def __init__(self, arc_offsets, ilabel, olabel, weight, nextstate, final, start: int = 0):
+        self.arc_offsets = np.ascontiguousarray(arc_offsets, np.int32)
+        self.ilabel, self.olabel = np.ascontiguousarray(ilabel, np.int32), np.ascontiguousarray(olabel, np.int32)
+        self.weight, self.nextstate = np.ascontiguousarray(weight, np.float32), np.ascontiguousarray(nextstate, np.int32)
+        self.final, self.start = np.ascontiguousarray(final, np.float32), int(start)
+
+    @classmethod
+    def from_fst(cls, fst) -> "TrainingGraph":
+        """From anything with the OpenFst-style Python surface kaldifst.StdVectorFst exposes
+        (`start`, `num_states`, `final(s)`, and `kaldifst.ArcIterator(fst, s)` yielding arcs with
+        ilabel / olabel / weight / nextstate).  Not exercised in this repository's tests (kaldifst is
+        not installed here); the array form above is the tested boundary."""
+        import kaldifst
+
+        offs, il, ol, w, ns, fin = [0], [], [], [], [], []
+        for s in range(fst.num_states):
+            for arc in kaldifst.ArcIterator(fst, s):
+                il.append(arc.ilabel), ol.append(arc.olabel), ns.append(arc.nextstate)
+                w.append(float(getattr(arc.weight, "value", arc.weight)))
+            offs.append(len(il))
+            f = fst.final(s)
+            fin.append(float(getattr(f, "value", f)))
+        return cls(offs, il, ol, w, ns, fin, fst.start)
+
+
+def _careful(g: TrainingGraph) -> TrainingGraph:
+    """ModifyGraphForCarefulAlignment (reference csrc/decoder-wrappers.cc:111-144): Concat(fst, rhs)
+    where rhs = a copy of fst without final costs, entered through a new final pre-initial state.
+    OpenFst's Concat adds, for every final state s of the first operand, an epsilon arc with the
+    final cost to the second operand's start, and clears s's final cost."""
+    S, A = g.final.size, g.ilabel.size
+    src = np.repeat(np.arange(S, dtype=np.int32), np.diff(g.arc_offsets))
+    pre = 2 * S                                     # pre_initial of rhs, after offsetting rhs states by S
+    fin_states = np.flatnonzero(np.isfinite(g.final)).astype(np.int32)
+    a_src = np.concatenate([src, fin_states, src + S, [pre]]).astype(np.int32)
+    a_il = np.concatenate([g.ilabel, np.zeros(fin_states.size, np.int32), g.ilabel, [0]]).astype(np.int32)
+    a_ol = np.concatenate([g.olabel, np.zeros(fin_states.size, np.int32), g.olabel, [0]]).astype(np.int32)
+    a_w = np.concatenate([g.weight, g.final[fin_states], g.weight, [0.0]]).astype(np.float32)
+    a_ns = np.concatenate([g.nextstate, np.full(fin_states.size, pre, np.int32), g.nextstate + S, [g.start + S]]).astype(np.int32)
+    order = np.argsort(a_src, kind="stable")
+    offs = np.zeros(2 * S + 2, np.int32)
+    np.add.at(offs, a_src + 1, 1)
+    final = np.full(2 * S + 1, np.inf, np.float32)
+    final[pre] = 0.0
+    return TrainingGraph(np.cumsum(offs), a_il[order], a_ol[order], a_w[order], a_ns[order], final, g.start)
+
+
+def gmm_align_compiled_batch(am_gmm, transition_model, utts: List[str], fsts, feats_list, align_config,
+                             acoustic_scale: float = 1.0, num_done: int = 0, num_error: int = 0, num_retried: int = 0,
+                             tot_like: float = 0, frame_count: int = 0):
+    """gmm-align-compiled for MANY utterances in one device call (khg_align_batch): the counters,
+    `alignment` and `words` of reference scripts/gmm_align_compiled.py:10-79 per utterance.
+    `fsts`: TrainingGraph objects (or kaldifst FSTs) with the transition probabilities already
+    added (`khg.add_transition_probs`, FST-side work outside this package)."""
+    graphs = [g if isinstance(g, TrainingGraph) else TrainingGraph.from_fst(g) for g in fsts]
+    if align_config.careful:
+        graphs = [_careful(g) if g.start >= 0 and g.final.size else g for g in graphs]
+    feats_list = [_np(f, np.float32) for f in feats_list]
+    lens = np.asarray([f.shape[0] for f in feats_list], np.int64)
+    t2p = _tid2pdf(transition_model)
+    cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs) if len(xs) else np.zeros(0, dt), dt)  # noqa: E731
+    narcs = np.cumsum([0] + [g.ilabel.size for g in graphs])
+    arc_offsets = cat([np.zeros(1, np.int64)] + [g.arc_offsets[1:].astype(np.int64) + narcs[i] for i, g in enumerate(graphs)], np.int32)
+    olabel = cat([g.olabel for g in graphs], np.int32)
+    ali, status, like, poff, paths = am_gmm.align_batch(
+        feats=np.concatenate(feats_list, 0) if feats_list else np.zeros((0, am_gmm.dim), np.float32),
+        frame_offsets=np.concatenate([[0], np.cumsum(lens)]).astype(np.int64),
+        state_offsets=np.concatenate([[0], np.cumsum([g.final.size for g in graphs])]).astype(np.int32),
+        arc_offsets=arc_offsets, arc_ilabel=cat([g.ilabel for g in graphs], np.int32),
+        arc_nextstate=cat([g.nextstate for g in graphs], np.int32), arc_weight=cat([g.weight for g in graphs], np.float32),
+        start_state=np.asarray([g.start for g in graphs], np.int32), final_cost=cat([g.final for g in graphs], np.float32),
+        tid2pdf=t2p, acoustic_scale=acoustic_scale, beam=align_config.beam, retry_beam=align_config.retry_beam)
+    fo = np.concatenate([[0], np.cumsum(lens)])
+    alignments, words = [], []
+    for u in range(len(graphs)):
+        # AlignUtteranceWrapper's counters (reference csrc/decoder-wrappers.cc:36-107)
+        if graphs[u].start >= 0 and status[u] != 0 and align_config.retry_beam != 0:
+            num_retried += 1
+        if status[u] == 2:
+            num_error += 1
+            alignments.append([]), words.append([])
+            continue
+        num_done += 1
+        tot_like += float(like[u])
+        frame_count += int(lens[u])
+        alignments.append(ali[fo[u]:fo[u + 1]].tolist())
+        ol = olabel[paths[poff[u]:poff[u + 1]]]
+        words.append(ol[ol != 0].tolist())
+    return {"num_done": num_done, "num_error": num_error, "num_retried": num_retried, "tot_like": tot_like,
+            "frame_count": frame_count, "alignment": alignments, "words": words, "status": status.tolist()}
+
+
+def gmm_align_compiled(am_gmm, transition_model, utt: str, fst, feats, align_config, acoustic_scale: float = 1.0,
+                       transition_scale: float = 1.0, self_loop_scale: float = 1.0, num_done: int = 0, num_error: int = 0,
+                       num_retried: int = 0, tot_like: float = 0, frame_count: int = 0):
+    """Same contract as reference scripts/gmm_align_compiled.py:10-79 for one utterance.  When `fst`
+    is a kaldifst FST and the reference package is importable its `add_transition_probs` is applied
+    first (like the reference script); a TrainingGraph is taken as already carrying them."""
+    if not isinstance(fst, TrainingGraph):
+        import kaldi_hmm_gmm as khg  # the reference's FST-side helper (unchanged)
+
+        khg.add_transition_probs(trans_model=transition_model, transition_scale=transition_scale,
+                                 self_loop_scale=self_loop_scale, fst=fst)
+    r = gmm_align_compiled_batch(am_gmm, transition_model, [utt], [fst], [feats], align_config, acoustic_scale,
+                                 num_done, num_error, num_retried, tot_like, frame_count)
+    r["alignment"], r["words"] = r["alignment"][0], r["words"][0]
+    del r["status"]
+    return r

@@ -90,6 +90,16 @@ def test_align_batch_matches_oracle(beam, retry, scale):
     assert (out["status"] == 0).sum() >= 20
 
 
+def test_align_batch_in_several_chunks(monkeypatch):
+    """Chunks of utterances (bounded likelihood block / back-pointer memory): same results."""
+    monkeypatch.setenv("KHG_ALIGN_CHUNK_FRAMES", "150")
+    model, graphs, feats, t2p = _batch(17, 30)
+    dm = _device_model(model)
+    out, ll, gb, pdf_ids = _run(dm, graphs, feats, t2p, 1.0, 8.0, 40.0)
+    monkeypatch.delenv("KHG_ALIGN_CHUNK_FRAMES")
+    _check(out, ll, gb, graphs, t2p, 1.0, 8.0, 40.0, pdf_ids)
+
+
 def test_align_batch_device_features_and_oracle_likelihoods():
     """Device-resident features; and the same alignment from the ORACLE's likelihoods (the two
     likelihood paths agree within 1e-3, far below the margins between paths on this data)."""
@@ -192,3 +202,63 @@ def test_align_batch_rejects_bad_arguments():
     graphs[1].nextstate[0] = 10 ** 6
     with pytest.raises(RuntimeError, match="out of range"):
         _run(dm, graphs, feats, t2p, 1.0, 10.0, 0.0)
+
+
+def _am_from_packed(khg, model):
+    am = khg.AmDiagGmm()
+    for p in range(model.num_pdfs):
+        s = slice(model.offsets[p], model.offsets[p + 1])
+        g = khg.DiagGmm(nmix=s.stop - s.start, dim=model.dim)
+        g.set_weights(model.weights[s])
+        g.set_invvars_and_means(model.inv_vars[s], model.means_invvars[s] / model.inv_vars[s])
+        am.add_pdf(g)
+    assert am.compute_gconsts() == 0
+    return am
+
+
+def test_script_gmm_align_compiled_contract():
+    """The reference's script signature (scripts/gmm_align_compiled.py:10-79) over the batched
+    device call: counters, alignment, words; single-utterance and batch forms; careful graphs."""
+    import kaldi_hmm_gmm_b200 as khg
+
+    P = 37
+    model, graphs, feats, t2p = _batch(53, 8, P=P)
+    rng = np.random.default_rng(1)
+    g, f, nt = _bushy_utt(rng, model, *_model_moments(model), P)   # fails at beam 0.5, recovered by the retry
+    graphs.append(g)
+    feats.append(f)
+    t2p = ao.make_tid2pdf(max(t2p.size, nt), P)
+    graphs[2].start = -1
+    am = _am_from_packed(khg, model)
+    tgs = [khg.TrainingGraph(g.arc_offsets, g.ilabel, g.olabel, g.weight, g.nextstate, g.final, g.start) for g in graphs]
+    cfg = khg.AlignConfig(beam=0.5, retry_beam=1e4)
+    assert khg.AlignConfig().beam == 200.0 and khg.AlignConfig().retry_beam == 0.0 and not khg.AlignConfig().careful
+    r = khg.gmm_align_compiled_batch(am, t2p, [f"utt{i}" for i in range(len(tgs))], tgs, feats, cfg, acoustic_scale=0.5,
+                                     num_done=10, tot_like=-1.0)
+    ora = ko.Oracle()
+    done = err = retried = frames = 0
+    like = 0.0
+    for u, g in enumerate(graphs):
+        ll, _ = ora.loglikes_all_pdfs(model, feats[u])
+        ref = ao.align_utterance(g, np.ascontiguousarray(ll.T), t2p, 0.5, beam=0.5, retry_beam=1e4, tight=True)
+        retried += int(g.start >= 0 and ref["status"] != 0)
+        if ref["status"] == 2:
+            err += 1
+            assert r["alignment"][u] == [] and r["words"][u] == []
+            continue
+        done += 1
+        frames += feats[u].shape[0]
+        like += ref["like"]
+        assert r["alignment"][u] == ref["alignment"] and r["words"][u] == ref["words"]
+    assert (r["num_done"], r["num_error"], r["num_retried"], r["frame_count"]) == (10 + done, err, retried, frames)
+    assert retried >= 1 and err == 1
+    assert abs(r["tot_like"] - (-1.0 + like)) <= 1e-5 * abs(like)
+    # the single-utterance form with the reference's keyword names
+    one = khg.gmm_align_compiled(am_gmm=am, transition_model=t2p, utt="utt0", fst=tgs[0], feats=feats[0], align_config=cfg,
+                                 acoustic_scale=0.5)
+    assert one["alignment"] == r["alignment"][0] and one["words"] == r["words"][0] and one["num_done"] == 1
+    # careful alignment = the reference's graph edit (csrc/decoder-wrappers.cc:111-144) + the same search
+    careful = khg.AlignConfig(beam=200.0, retry_beam=0.0, careful=True)
+    rc = khg.gmm_align_compiled_batch(am, t2p, ["a", "b"], tgs[:2], feats[:2], careful)
+    plain = khg.gmm_align_compiled_batch(am, t2p, ["a", "b"], tgs[:2], feats[:2], khg.AlignConfig())
+    assert rc["alignment"] == plain["alignment"] and rc["num_done"] == 2
