@@ -39,6 +39,7 @@ CONFIGS = {
     "c2": (39, 130, 1000, 1_000_000),
     "c3": (39, 2000, 10_000, 10_000_000),
     "c4": (40, 4200, 40_000, 100_000_000),
+    "c5": (40, 5000, 100_000, 1_000_000),  # dense block feeding the batched aligner (tools/bench_align.py)
 }
 METRIC = "frames/sec (loglike+E-step stats, 1/2/4/8 B200); % tensor-core peak"
 

@@ -180,6 +180,15 @@ __device__ __forceinline__ void tc_ld16_wait(TReg16 &t) {
                :
                : "memory");
 }
+__device__ __forceinline__ void tc_ld16_wait2(TReg16 &t, TReg16 &u) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(t.r[0]), "+r"(t.r[1]), "+r"(t.r[2]), "+r"(t.r[3]), "+r"(t.r[4]), "+r"(t.r[5]), "+r"(t.r[6]), "+r"(t.r[7]),
+                 "+r"(t.r[8]), "+r"(t.r[9]), "+r"(t.r[10]), "+r"(t.r[11]), "+r"(t.r[12]), "+r"(t.r[13]), "+r"(t.r[14]), "+r"(t.r[15]),
+                 "+r"(u.r[0]), "+r"(u.r[1]), "+r"(u.r[2]), "+r"(u.r[3]), "+r"(u.r[4]), "+r"(u.r[5]), "+r"(u.r[6]), "+r"(u.r[7]),
+                 "+r"(u.r[8]), "+r"(u.r[9]), "+r"(u.r[10]), "+r"(u.r[11]), "+r"(u.r[12]), "+r"(u.r[13]), "+r"(u.r[14]), "+r"(u.r[15])
+               :
+               : "memory");
+}
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -222,6 +231,21 @@ struct SegLse {
     for (int i = 0; i < kPairs; ++i)
       e2[i] = __ffma2_rn(make_float2(__uint_as_float(t.r[2 * i]), __uint_as_float(t.r[2 * i + 1])), k2, nm2);
     if (L & 1) e1 = fmaf(__uint_as_float(t.r[L - 1]), kLog2e, -ml);
+  }
+  // sum of 2^e[i] (the caller combines two chunks of a long segment)
+  __device__ __forceinline__ float part2_sum() {
+    if (L == 1) return 1.f;
+    float2 s2;
+#pragma unroll
+    for (int i = 0; i < kPairs; ++i) {
+      float2 v = e2[i];
+      v.x = fast_exp2(v.x);
+      v.y = fast_exp2(v.y);
+      s2 = i == 0 ? v : __fadd2_rn(s2, v);
+    }
+    float s = s2.x + s2.y;
+    if (L & 1) s += fast_exp2(e1);
+    return s;
   }
   __device__ __forceinline__ float part2() {
     constexpr float kLn2 = 0.6931471805599453f;
@@ -277,8 +301,13 @@ __device__ __forceinline__ float seg_lse_long(uint32_t taddr, int len) {
 //         T, so that the store needs no predicate
 //   nan_acc collects r*0 (NaN for a non-finite r, the reference's "Invalid answer"): one FFMA
 //         instead of a compare/select/or per segment
+// A descriptor is  column | two_chunks << 8 | pdf << 9: segments of 17..32 columns are read as two
+// 16-column loads (t and t2); the flag tells whoever issues the NEXT segment's loads — possibly the
+// last segment of a run of another length — that t2 is wanted too.
+constexpr uint32_t kSegTwoChunks = 0x100u;
+constexpr int kSegPdfShift = 9;
 struct EpiState {
-  TReg16 t;
+  TReg16 t, t2;
   uint32_t d, dn;   // descriptors of segment k (load in flight) and k+1
   const uint32_t *sp;
   uint32_t trow;
@@ -287,7 +316,9 @@ struct EpiState {
   float scale, nan_acc;
 };
 
-template <int L>
+// TWO = the model has segments of 17..32 columns somewhere, i.e. the next segment may want its
+// second load issued too; models without such pdfs run the variant without that instruction.
+template <int L, bool TWO>
 __device__ __forceinline__ void epi_run(EpiState &e, int cnt) {
 #pragma unroll 1
   for (; cnt > 0; --cnt) {
@@ -298,14 +329,45 @@ __device__ __forceinline__ void epi_run(EpiState &e, int cnt) {
     SegLse<L> lse;
     lse.part1(e.t);
     tc_ld16_issue(e.trow + (dnext & 0xffu), e.t);  // after the last segment: the sentinel (unused)
+    if (TWO) tc_ld16_issue_if(e.trow + (dnext & 0xffu) + 16, e.t2, (dnext & kSegTwoChunks) != 0);
     const float r = lse.part2();
     e.nan_acc = fmaf(r, 0.f, e.nan_acc);
-    *reinterpret_cast<float *>(e.out_t + (uint64_t)(dcur >> 8) * e.ld_bytes) = e.scale * r;
+    *reinterpret_cast<float *>(e.out_t + (uint64_t)(dcur >> kSegPdfShift) * e.ld_bytes) = e.scale * r;
     e.d = dnext;
   }
 }
 
-__device__ __forceinline__ void epi_run_long(EpiState &e, int cnt, int len) {
+// Segments of 16 + LB columns (17..32 Gaussians): both 16-column loads were issued by the previous
+// segment and complete under ONE wait; chunk a is reduced, the next segment's first load goes out,
+// chunk b is reduced, the next segment's second load goes out, and the two (max, sum) pairs are
+// merged: M = max(Ma, Mb), s = sa * 2^((Ma - M) log2 e) + sb * 2^((Mb - M) log2 e).
+template <int LB>
+__device__ __forceinline__ void epi_run2(EpiState &e, int cnt) {
+  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+#pragma unroll 1
+  for (; cnt > 0; --cnt) {
+    const uint32_t dcur = e.d, dnext = e.dn;
+    e.dn = __ldg(e.sp + 2);
+    ++e.sp;
+    tc_ld16_wait2(e.t, e.t2);
+    SegLse<16> la;
+    la.part1(e.t);
+    tc_ld16_issue(e.trow + (dnext & 0xffu), e.t);
+    const float sa = la.part2_sum();
+    SegLse<LB> lb;
+    lb.part1(e.t2);
+    tc_ld16_issue_if(e.trow + (dnext & 0xffu) + 16, e.t2, (dnext & kSegTwoChunks) != 0);
+    const float sb = lb.part2_sum();
+    const float M = fmaxf(la.M, lb.M);
+    const float s = fmaf(sa, fast_exp2((la.M - M) * kLog2e), sb * fast_exp2((lb.M - M) * kLog2e));
+    const float r = fmaf(fast_log2(s), kLn2, M);
+    e.nan_acc = fmaf(r, 0.f, e.nan_acc);
+    *reinterpret_cast<float *>(e.out_t + (uint64_t)(dcur >> kSegPdfShift) * e.ld_bytes) = e.scale * r;
+    e.d = dnext;
+  }
+}
+
+__device__ __forceinline__ void epi_run_long(EpiState &e, int cnt, int len) {  // (only models with two-chunk segments set the flag)
   for (; cnt > 0; --cnt) {
     const uint32_t dcur = e.d, dnext = e.dn;
     e.dn = __ldg(e.sp + 2);
@@ -313,8 +375,9 @@ __device__ __forceinline__ void epi_run_long(EpiState &e, int cnt, int len) {
     tc_ld16_wait(e.t);  // the pending 16-column load is not used by the two-pass form
     const float r = seg_lse_long(e.trow + (dcur & 0xffu), len);
     tc_ld16_issue(e.trow + (dnext & 0xffu), e.t);
+    tc_ld16_issue_if(e.trow + (dnext & 0xffu) + 16, e.t2, (dnext & kSegTwoChunks) != 0);
     e.nan_acc = fmaf(r, 0.f, e.nan_acc);
-    *reinterpret_cast<float *>(e.out_t + (uint64_t)(dcur >> 8) * e.ld_bytes) = e.scale * r;
+    *reinterpret_cast<float *>(e.out_t + (uint64_t)(dcur >> kSegPdfShift) * e.ld_bytes) = e.scale * r;
     e.d = dnext;
   }
 }
@@ -483,6 +546,7 @@ struct TcArgs {
   const int32_t *offsets;  // P+1
   const int32_t *tile_g0;  // n_tiles
   const int32_t *tile_p0;  // n_tiles+1
+  int two_chunk_segs;        // some pdf has 17..32 Gaussians (descriptor flag kSegTwoChunks in use)
   const int2 *epi_hdr;       // per (tile, epilogue group): {start in seg[], first run | number of runs << 24}
   const uint32_t *runs;      // per run of equal-length segments: length | count << 8
   const uint32_t *seg;       // per segment: column | pdf << 8; per (tile, group) in run order, + 2 sentinels
@@ -496,7 +560,9 @@ struct TcArgs {
   int debug_mode;          // 0 = normal; 1 = epilogue skips the LSE (pipeline-ceiling experiment, KHG_TC_DEBUG_MODE)
 };
 
-template <bool F16>
+// TWO: the model has pdfs of 17..32 Gaussians (two-load segments); a separate instantiation so that
+// models without them run exactly the single-load epilogue.
+template <bool F16, bool TWO>
 __global__ void __launch_bounds__(kTcThreads, 1)
 loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
   constexpr int kChunkK = Elem<F16>::kChunkK, kUmmaK = Elem<F16>::kUmmaK;
@@ -701,18 +767,42 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
         e.trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256;
         if (a.debug_mode == 0 && nr > 0) {
           tc_ld16_issue(e.trow + (e.d & 0xffu), e.t);
-          for (; nr > 0; --nr) {
-            const int len = run & 0xff, cnt = run >> 8;
-            if (nr > 1) run = __ldg(++rp);
-#define KHG_CASE(L) case L: epi_run<L>(e, cnt); break;
-            switch (len) {
-              KHG_CASE(1) KHG_CASE(2) KHG_CASE(3) KHG_CASE(4) KHG_CASE(5) KHG_CASE(6) KHG_CASE(7) KHG_CASE(8)
-              KHG_CASE(9) KHG_CASE(10) KHG_CASE(11) KHG_CASE(12) KHG_CASE(13) KHG_CASE(14) KHG_CASE(15) KHG_CASE(16)
-              default: epi_run_long(e, cnt, len); break;
+#define KHG_CASE(L) case L: epi_run<L, KHG_TWO>(e, cnt); break;
+#define KHG_CASE2(L) case 16 + L: epi_run2<L>(e, cnt); break;
+#define KHG_CASES1 KHG_CASE(1) KHG_CASE(2) KHG_CASE(3) KHG_CASE(4) KHG_CASE(5) KHG_CASE(6) KHG_CASE(7) KHG_CASE(8) \
+                   KHG_CASE(9) KHG_CASE(10) KHG_CASE(11) KHG_CASE(12) KHG_CASE(13) KHG_CASE(14) KHG_CASE(15) KHG_CASE(16)
+#define KHG_CASES2 KHG_CASE2(1) KHG_CASE2(2) KHG_CASE2(3) KHG_CASE2(4) KHG_CASE2(5) KHG_CASE2(6) KHG_CASE2(7) KHG_CASE2(8) \
+                   KHG_CASE2(9) KHG_CASE2(10) KHG_CASE2(11) KHG_CASE2(12) KHG_CASE2(13) KHG_CASE2(14) KHG_CASE2(15) KHG_CASE2(16)
+          if constexpr (TWO) {
+            tc_ld16_issue_if(e.trow + (e.d & 0xffu) + 16, e.t2, (e.d & kSegTwoChunks) != 0);
+            for (; nr > 0; --nr) {
+              const int len = run & 0xff, cnt = run >> 8;
+              if (nr > 1) run = __ldg(++rp);
+#define KHG_TWO true
+              switch (len) {
+                KHG_CASES1 KHG_CASES2
+                default: epi_run_long(e, cnt, len); break;
+              }
+#undef KHG_TWO
             }
-#undef KHG_CASE
+            tc_ld16_wait2(e.t, e.t2);  // the (unused) sentinel load issued after the last segment
+          } else {
+            for (; nr > 0; --nr) {
+              const int len = run & 0xff, cnt = run >> 8;
+              if (nr > 1) run = __ldg(++rp);
+#define KHG_TWO false
+              switch (len) {
+                KHG_CASES1
+                default: epi_run_long(e, cnt, len); break;
+              }
+#undef KHG_TWO
+            }
+            tc_ld16_wait(e.t);  // the (unused) sentinel load issued after the last segment
           }
-          tc_ld16_wait(e.t);  // the (unused) sentinel load issued after the last segment
+#undef KHG_CASE
+#undef KHG_CASE2
+#undef KHG_CASES1
+#undef KHG_CASES2
         }
         tc_fence_before();
         __syncwarp();
@@ -885,6 +975,7 @@ khg_status tc_pack_build(khg_model *m) {
     std::vector<int2> hdr((size_t)kEpiGroups * t.n_tiles);
     std::vector<uint32_t> runs, seg;
     seg.reserve(P + 2 * hdr.size());
+    t.two_chunk_segs = false;
     for (int j = 0; j < t.n_tiles; ++j) {
       const int pa = t.h_tile_p0[j], pb = t.h_tile_p0[j + 1], g0 = t.h_tile_g0[j];
       std::vector<std::pair<int, int>> by_len;  // (len, pdf)
@@ -902,7 +993,8 @@ khg_status tc_pack_build(khg_model *m) {
             runs.back() += 1u << 8;
           else
             runs.push_back((uint32_t)std::min(len, 255) | 1u << 8);
-          seg.push_back((uint32_t)(m->h_offsets[q] - g0) | (uint32_t)q << 8);
+          if (len > 16 && len <= 32) t.two_chunk_segs = true;
+          seg.push_back((uint32_t)(m->h_offsets[q] - g0) | (len > 16 && len <= 32 ? kSegTwoChunks : 0u) | (uint32_t)q << kSegPdfShift);
         }
         seg.push_back(0);  // two sentinels: the epilogue prefetches two descriptors ahead
         seg.push_back(0);
@@ -911,7 +1003,7 @@ khg_status tc_pack_build(khg_model *m) {
       }
     }
     runs.push_back(0);  // read (unused) by groups without segments
-    if (P >= (1 << 24) || runs.size() >= (1u << 24)) {
+    if (P >= (1 << (32 - kSegPdfShift)) || runs.size() >= (1u << 24)) {
       set_error("too many pdfs for the tensor-core epilogue tables");
       return KHG_ERR_UNSUPPORTED;
     }
@@ -977,6 +1069,7 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   a.tile_g0 = t.tile_g0;
   a.tile_p0 = t.tile_p0;
   a.epi_hdr = static_cast<const int2 *>(t.epi_hdr);
+  a.two_chunk_segs = t.two_chunk_segs ? 1 : 0;
   a.runs = t.runs;
   a.seg = t.seg;
   a.n_tiles = t.n_tiles;
@@ -1005,12 +1098,17 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(loglikes_tc_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(loglikes_tc_kernel<F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(loglikes_tc_kernel<F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   KHG_CUDA_TRY(attr_err);
   unsigned grid = (unsigned)std::min<int64_t>(a.n_items, m->sm_count);
   if (const char *mc = getenv("KHG_TC_MAX_CTAS")) grid = std::min<unsigned>(grid, (unsigned)std::max(1, atoi(mc)));  // experiments
-  loglikes_tc_kernel<F16><<<grid, kTcThreads, smem, m->stream>>>(F16 ? t.hmap_hi : t.map_hi, a);
+  if (t.two_chunk_segs)
+    loglikes_tc_kernel<F16, true><<<grid, kTcThreads, smem, m->stream>>>(F16 ? t.hmap_hi : t.map_hi, a);
+  else
+    loglikes_tc_kernel<F16, false><<<grid, kTcThreads, smem, m->stream>>>(F16 ? t.hmap_hi : t.map_hi, a);
   ++g_launch_count;
   KHG_CUDA_TRY(cudaGetLastError());
   return KHG_OK;

@@ -234,13 +234,14 @@ def test_tc_auto_falls_back_to_tf32_when_out_of_fp16_range(oracle):
 
 
 def test_tc_length_classes_and_kernel_query(oracle):
-    """Every segment length 1..20 plus a 240-Gaussian pdf in one model: exercises each
-    compile-time length class of the epilogue, the >16 two-pass path and tile packing."""
+    """Every segment length 1..40 plus 240-Gaussian pdfs in one model: exercises each
+    compile-time length class of the epilogue (1..16 one load, 17..32 two loads merged as two
+    (max, sum) pairs), the >32 two-pass path, every kind of run boundary, and tile packing."""
     from kaldi_hmm_gmm_b200 import DeviceModel
 
     rng = np.random.default_rng(21)
     D = 40
-    sizes = np.array(list(range(1, 21)) * 3 + [240, 1, 16, 17, 239, 2], np.int32)
+    sizes = np.array(list(range(1, 41)) * 3 + [240, 1, 16, 17, 239, 2, 32, 33, 31], np.int32)
     rng.shuffle(sizes)
     offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
     G = int(offsets[-1])

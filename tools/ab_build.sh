@@ -8,12 +8,12 @@ rev=$1; name=$2
 tmp=$(mktemp -d)
 git -C "$ROOT" archive "$rev" kaldi-hmm-gmm_b200/csrc include | tar -x -C "$tmp"
 cd "$tmp/kaldi-hmm-gmm_b200/csrc"
-for f in khg_b200.cu khg_loglikes_tc.cu; do
+for f in *.cu; do
   /usr/local/cuda/bin/nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC \
     -I"$tmp/include" -I. --expt-relaxed-constexpr -c $f -o ${f%.cu}.o 2>/dev/null &
 done
 wait
 mkdir -p "$ROOT/tools/ab"
-/usr/local/cuda/bin/nvcc -shared -o "$ROOT/tools/ab/$name.so" khg_b200.o khg_loglikes_tc.o -cudart shared
+/usr/local/cuda/bin/nvcc -shared -o "$ROOT/tools/ab/$name.so" *.o -cudart shared
 rm -rf "$tmp"
 echo "built tools/ab/$name.so from $rev"

@@ -6,12 +6,12 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 name=$1; shift
 tmp=$(mktemp -d)
 cd "$ROOT/kaldi-hmm-gmm_b200/csrc"
-for f in khg_b200.cu khg_loglikes_tc.cu; do
+for f in *.cu; do
   /usr/local/cuda/bin/nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC \
     -I"$ROOT/include" -I. --expt-relaxed-constexpr "$@" -c $f -o $tmp/${f%.cu}.o 2>/dev/null &
 done
 wait
 mkdir -p "$ROOT/tools/ab"
-/usr/local/cuda/bin/nvcc -shared -o "$ROOT/tools/ab/$name.so" $tmp/khg_b200.o $tmp/khg_loglikes_tc.o -cudart shared
+/usr/local/cuda/bin/nvcc -shared -o "$ROOT/tools/ab/$name.so" $tmp/*.o -cudart shared
 rm -rf "$tmp"
 echo "built tools/ab/$name.so with $*"

@@ -20,7 +20,9 @@ for kv in sys.argv[3:]:
     k, v = kv.split("=", 1)
     os.environ[k] = v
 T = 148 * 128 * 16
-D, P, G, _ = bench.CONFIGS["c4"]
+if os.environ.get("K1_CONFIG") == "c5":
+    T = 148 * 128 * 8
+D, P, G, _ = bench.CONFIGS[os.environ.get("K1_CONFIG", "c4")]
 hm = bench.host_model(D, P, G)
 dm = DeviceModel(D, hm["offsets"])
 dm.set_kernel(kernel)
