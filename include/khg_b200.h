@@ -316,6 +316,22 @@ khg_status khg_align_batch(khg_model *m, const khg_graph_batch *graphs, const fl
                            int32_t *path_arcs, int64_t *path_offsets, int64_t path_capacity,
                            int32_t *pdf_ids_dev);
 
+/* -------------------------------------------------------- Gaussian selection --
+ * DiagGmm::GaussianSelection for a matrix of frames (csrc/diag-gmm.cc:241-317; the one-frame form
+ * :202-239 is T = 1) and DiagGmm::GaussianSelectionPreselect (:319-366) on pdf `pdf` of the model
+ * (a UBM is a model with one pdf): per frame the k = min(num_gselect, n) candidates with the largest
+ * log-likelihoods, best first — among equal log-likelihoods the larger index first, like the
+ * reference's std::greater on (loglike, index) pairs — and the LogAdd chain of their log-likelihoods.
+ * preselect (HOST, n_preselect entries, indices into the pdf's Gaussians, duplicates allowed)
+ * restricts the candidates; n_preselect = 0 -> all n = NumGauss() of them.
+ * Outputs (HOST): out_indices int32[T x k]; out_loglikes float[T x k] or NULL (the selected
+ * components' log-likelihoods as the device computed them); frame_loglike float[T] or NULL;
+ * *tot_loglike = sum over frames (the matrix form's return value), may be NULL. */
+khg_status khg_gaussian_selection(khg_model *m, int32_t pdf, const float *feats, int64_t T, int32_t feats_loc,
+                                  const int32_t *preselect, int32_t n_preselect, int32_t num_gselect,
+                                  int32_t *out_indices, float *out_loglikes, float *frame_loglike,
+                                  double *tot_loglike);
+
 /* Number of kernels this library launched since load (bench.py's
  * gpu_launches). */
 int64_t khg_launch_count(void);

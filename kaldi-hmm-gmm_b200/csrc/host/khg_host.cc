@@ -159,6 +159,43 @@ void DiagGmm::LogLikelihoodsPreselect(const FloatVector &data, const std::vector
   }
 }
 
+float DiagGmm::GaussianSelection(const FloatVector &data, int32_t num_gselect, std::vector<int32_t> *output) const {
+  KHG_HOST_ASSERT((int32_t)data.size() == Dim());
+  output->assign(std::max(1, std::min(num_gselect, NumGauss())), 0);
+  double tot = 0;
+  Check(khg_gaussian_selection(Device(), 0, data.data(), 1, KHG_HOST, nullptr, 0, num_gselect, output->data(), nullptr, nullptr,
+                               &tot));
+  output->resize(std::min(num_gselect, NumGauss()));
+  return (float)tot;
+}
+
+float DiagGmm::GaussianSelection(const FloatMatrix &data, int32_t num_gselect,
+                                 std::vector<std::vector<int32_t>> *output) const {
+  KHG_HOST_ASSERT(data.rows != 0);  // csrc/diag-gmm.cc:272
+  KHG_HOST_ASSERT(data.cols == Dim());
+  const int32_t k = std::min(num_gselect, NumGauss());
+  std::vector<int32_t> idx((size_t)data.rows * std::max(k, 1));
+  double tot = 0;
+  Check(khg_gaussian_selection(Device(), 0, data.data.data(), data.rows, KHG_HOST, nullptr, 0, num_gselect, idx.data(), nullptr,
+                               nullptr, &tot));
+  output->assign(data.rows, {});
+  for (int32_t t = 0; t < data.rows; ++t) (*output)[t].assign(idx.begin() + (size_t)t * k, idx.begin() + (size_t)(t + 1) * k);
+  return (float)tot;
+}
+
+float DiagGmm::GaussianSelectionPreselect(const FloatVector &data, const std::vector<int32_t> &preselect, int32_t num_gselect,
+                                          std::vector<int32_t> *output) const {
+  KHG_HOST_ASSERT((int32_t)data.size() == Dim());
+  KHG_HOST_ASSERT(!preselect.empty());  // KHG_ASSERT(!output->empty()), csrc/diag-gmm.cc:363
+  const int32_t k = std::min<int32_t>(num_gselect, (int32_t)preselect.size());
+  output->assign(std::max(k, 1), 0);
+  double tot = 0;
+  Check(khg_gaussian_selection(Device(), 0, data.data(), 1, KHG_HOST, preselect.data(), (int32_t)preselect.size(), num_gselect,
+                               output->data(), nullptr, nullptr, &tot));
+  output->resize(k);
+  return (float)tot;
+}
+
 float DiagGmm::LogLikelihood(const FloatVector &data) const {
   if (!valid_gconsts_) Throw("Must call ComputeGconsts() before computing likelihood");
   if ((int32_t)data.size() != Dim()) {

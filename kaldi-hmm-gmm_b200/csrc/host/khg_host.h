@@ -101,6 +101,12 @@ class DiagGmm {
   void LogLikelihoodsMatrix(const FloatMatrix &data, FloatMatrix *loglikes) const;   // :177-189
   void LogLikelihoodsPreselect(const FloatVector &data, const std::vector<int32_t> &indices,
                                FloatVector *loglikes) const;                         // :191-200
+  // Gaussian selection on the device (khg_gaussian_selection): top num_gselect per frame
+  float GaussianSelection(const FloatVector &data, int32_t num_gselect, std::vector<int32_t> *output) const;  // :202-239
+  float GaussianSelection(const FloatMatrix &data, int32_t num_gselect,
+                          std::vector<std::vector<int32_t>> *output) const;                                  // :241-317
+  float GaussianSelectionPreselect(const FloatVector &data, const std::vector<int32_t> &preselect, int32_t num_gselect,
+                                   std::vector<int32_t> *output) const;                                      // :319-366
   float ComponentPosteriors(const FloatVector &data, FloatVector *posterior) const;  // :368-392
   float ComponentLogLikelihood(const FloatVector &data, int32_t comp_id) const;      // :394-409
 

@@ -174,6 +174,28 @@ PYBIND11_MODULE(_khg_b200, m) {
              return FromVec(ans);
            },
            py::arg("data"), py::arg("indices"))
+      // python/csrc/diag-gmm.cc:108-136: (total log-like, indices) — selection on the device
+      .def("gaussian_selection_1d",
+           [](const DiagGmm &s, const FArr &d, int32_t num_gselect) {
+             std::vector<int32_t> out;
+             float f = s.GaussianSelection(ToVec(d), num_gselect, &out);
+             return std::make_pair(f, out);
+           },
+           py::arg("data"), py::arg("num_gselect"))
+      .def("gaussian_selection_2d",
+           [](const DiagGmm &s, const FArr &d, int32_t num_gselect) {
+             std::vector<std::vector<int32_t>> out;
+             float f = s.GaussianSelection(ToMat(d), num_gselect, &out);
+             return std::make_pair(f, out);
+           },
+           py::arg("data"), py::arg("num_gselect"))
+      .def("gaussian_selection_preselect",
+           [](const DiagGmm &s, const FArr &d, const std::vector<int32_t> &preselect, int32_t num_gselect) {
+             std::vector<int32_t> out;
+             float f = s.GaussianSelectionPreselect(ToVec(d), preselect, num_gselect, &out);
+             return std::make_pair(f, out);
+           },
+           py::arg("data"), py::arg("preselect"), py::arg("num_gselect"))
       .def("component_posteriors",
            [](const DiagGmm &s, const FArr &d) {
              FloatVector post;

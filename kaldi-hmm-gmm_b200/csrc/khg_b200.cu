@@ -174,6 +174,10 @@ khg_status khg_model_upload(khg_model *m, const float *weights, const float *mea
   NvtxRange nvtx_range("khg_model_upload");
   KHG_REQUIRE(m && means_invvars && inv_vars, "null argument");
   KHG_REQUIRE(weights || gconsts, "need weights or gconsts");
+  if (m->gsel_shadow) {  // derived from the parameters being replaced
+    khg_model_destroy(m->gsel_shadow);
+    m->gsel_shadow = nullptr;
+  }
   size_t gd = (size_t)m->G * m->dim;
   cudaStream_t st = m->stream;
   KHG_CUDA_TRY(cudaMemcpyAsync(m->d_miv, means_invvars, sizeof(float) * gd, cudaMemcpyHostToDevice, st));
@@ -258,6 +262,7 @@ khg_status khg_model_sync(khg_model *m) {
 
 void khg_model_destroy(khg_model *m) {
   if (!m) return;
+  if (m->gsel_shadow) khg_model_destroy(m->gsel_shadow);
   tc_pack_free(m);
   cudaFree(m->d_offsets); cudaFree(m->d_weights); cudaFree(m->d_miv); cudaFree(m->d_iv);
   cudaFree(m->d_gconsts); cudaFree(m->d_packT); cudaFree(m->d_err); cudaFree(m->d_scratch_int);

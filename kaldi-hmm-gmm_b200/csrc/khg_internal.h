@@ -128,6 +128,8 @@ struct khg_model {
   int kernel = KHG_KERNEL_AUTO;
   int sm_count = 148;
   khg::TcPack tc;
+  khg_model *gsel_shadow = nullptr;  // the Gaussians of pdf gsel_pdf as one-Gaussian pdfs (khg_gselect.cu)
+  int gsel_pdf = -1;
   // scratch
   khg::Buf w_feats, w_ids, w_wts, w_out, w_pf;         // device staging of host args
   khg::Buf w_keys, w_keys_out, w_vals_in, w_vals_out, w_cub;       // bucketing (K2)

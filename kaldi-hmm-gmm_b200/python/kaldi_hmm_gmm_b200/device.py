@@ -121,6 +121,25 @@ class DeviceModel:
         A.check(A.lib().khg_loglikes_pdf_subset(self._h, fp, T, floc, sub.ctypes.data, sub.size, scale, op, T, oloc))
         return out
 
+    def gaussian_selection(self, pdf: int, feats, num_gselect: int, preselect=None, want_loglikes: bool = False):
+        """DiagGmm::GaussianSelection / GaussianSelectionPreselect (reference csrc/diag-gmm.cc:202-366) of
+        pdf `pdf` for all rows of feats: (total log-like, indices int32 [T, k], per-frame log-like [T]
+        [, log-likes of the selected components [T, k]])."""
+        fp, floc = A.ptr(feats, np.float32)
+        T = int(feats.shape[0])
+        ng = int(self.offsets[pdf + 1] - self.offsets[pdf])
+        pre = None if preselect is None else np.ascontiguousarray(preselect, np.int32)
+        n = ng if pre is None else pre.size
+        k = min(int(num_gselect), n)
+        idx = np.empty((T, k), np.int32)
+        ll = np.empty((T, k), np.float32) if want_loglikes else None
+        fl = np.empty(T, np.float32)
+        tot = C.c_double(0.0)
+        A.check(A.lib().khg_gaussian_selection(self._h, pdf, fp, T, floc, None if pre is None else pre.ctypes.data,
+                                               0 if pre is None else pre.size, int(num_gselect), idx.ctypes.data,
+                                               None if ll is None else ll.ctypes.data, fl.ctypes.data, C.byref(tot)))
+        return (tot.value, idx, fl, ll) if want_loglikes else (tot.value, idx, fl)
+
     def pdf_loglikes(self, pdf: int, feats: np.ndarray) -> np.ndarray:
         feats = np.ascontiguousarray(np.atleast_2d(feats), np.float32)
         if feats.shape[1] != self.dim:

@@ -383,3 +383,37 @@ def np_loglikes_all_pdfs(model: PackedModel, feats, scale=1.0):
         m = seg.max(axis=1, keepdims=True)
         out[:, p] = (np.log(np.exp(seg - m, dtype=np.float32).sum(axis=1, dtype=np.float32), dtype=np.float32) + m[:, 0])
     return (np.float32(scale) * out).astype(np.float32)
+
+
+def np_log_add(x: np.float32, y: np.float32) -> np.float32:
+    """LogAdd(float, float), reference csrc/kaldi-math.h:60-78 (kMinLogDiffFloat = log(FLT_EPSILON))."""
+    x, y = np.float32(x), np.float32(y)
+    if x < y:
+        diff, x = np.float32(x - y), y
+    else:
+        diff = np.float32(y - x)
+    if diff >= np.float32(np.log(np.finfo(np.float32).eps)):
+        return np.float32(x + np.float32(np.log1p(np.exp(diff, dtype=np.float32), dtype=np.float32)))
+    return x
+
+
+def np_gaussian_selection(loglikes, num_gselect: int, labels=None):
+    """DiagGmm::GaussianSelection / GaussianSelectionPreselect for ONE frame given the candidates'
+    log-likelihoods (reference csrc/diag-gmm.cc:202-239, 319-366): threshold = the (n - k)-th order
+    statistic (std::nth_element), every candidate >= threshold as a (loglike, label) pair, sorted
+    with std::greater, the first k kept; tot = LogAdd chain in that order.  labels = the preselect
+    list (defaults to 0..n-1).  Returns (tot float32, list of labels)."""
+    ll = np.asarray(loglikes, np.float32)
+    n = ll.size
+    labels = np.arange(n) if labels is None else np.asarray(labels)
+    k = min(int(num_gselect), n)
+    # (the preselect form always takes the order statistic, the plain form uses -inf when k == n:
+    # the same set either way)
+    thresh = np.partition(ll, n - k)[n - k] if k < n else -np.inf
+    pairs = sorted(((float(ll[p]), int(labels[p])) for p in range(n) if ll[p] >= thresh), reverse=True)
+    tot = np.float32(-np.inf)
+    out = []
+    for v, lab in pairs[:k]:
+        out.append(lab)
+        tot = np_log_add(tot, np.float32(v))
+    return tot, out
