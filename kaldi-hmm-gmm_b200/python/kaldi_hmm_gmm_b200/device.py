@@ -72,6 +72,18 @@ class DeviceModel:
         A.check(A.lib().khg_model_download(self._h, offs.ctypes.data, w.ctypes.data, miv.ctypes.data, iv.ctypes.data, gc.ctypes.data))
         return dict(offsets=offs, weights=w, means_invvars=miv, inv_vars=iv, gconsts=gc)
 
+    # pickle / torch.save round trip of the packed model (the reference pickles
+    # (weights, inv_vars, means_invvars) per pdf, python/csrc/am-diag-gmm.cc:47-71): the state is the
+    # packed host copy, the device pack is rebuilt on load with the stored gconsts.
+    def __getstate__(self):
+        st = self.download()
+        st["dim"] = self.dim
+        return st
+
+    def __setstate__(self, st):
+        self.__init__(st["dim"], st["offsets"])
+        self.upload(st["weights"], st["means_invvars"], st["inv_vars"], st["gconsts"])
+
     def dense_kernel(self) -> int:
         """1 = SIMT, 2 = tcgen05 3xTF32, 3 = tcgen05 3xFP16 (what an in-range call runs)."""
         k = C.c_int32()

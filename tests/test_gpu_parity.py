@@ -461,3 +461,26 @@ def test_pdf_subset_block(oracle, small):
     _assert_ll(got_d.cpu().numpy(), ref[:, sub].T)
     with pytest.raises(RuntimeError, match="out of range"):
         dm.loglikes_pdf_subset(feats, np.array([1, model.num_pdfs], np.int32))
+
+
+def test_packed_model_pickle_round_trip(oracle):
+    """pickle / torch.save of the device-resident packed model: same parameters, same likelihoods."""
+    import io
+    import pickle
+
+    import torch
+
+    model, means, vars_ = ko.make_synthetic_model(13, 9, 70, oracle=oracle)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, 200)
+    dm, _ = _device_model(model)
+    ref = dm.loglikes_all_pdfs(feats)
+    dm2 = pickle.loads(pickle.dumps(dm))
+    buf = io.BytesIO()
+    torch.save(dm, buf)
+    buf.seek(0)
+    dm3 = torch.load(buf, weights_only=False)
+    for other in (dm2, dm3):
+        a, b = dm.download(), other.download()
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k])
+        np.testing.assert_array_equal(other.loglikes_all_pdfs(feats), ref)

@@ -1,0 +1,42 @@
+"""W-aligned alone: khg_acc_stats_ali = K2 bucketing + K3 statistics on device-resident
+frames of a BASELINE config; frames/s and the fraction of the HBM roof (4*D + 4 bytes per frame).
+usage: tools/bench_stats.py [config c2|c3|c4|c5] [frames]   (KHG_B200_LIB=tools/ab/x.so for A/B)"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "kaldi-hmm-gmm_b200", "python")]
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from kaldi_hmm_gmm_b200 import DeviceModel, DeviceStats  # noqa: E402
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "c4"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 8_000_000
+D, P, G, _ = bench.CONFIGS[cfg]
+hm = bench.host_model(D, P, G)
+dm = DeviceModel(D, hm["offsets"])
+dm.upload(hm["weights"], hm["miv"], hm["iv"])
+feats, pdf = bench.device_frames(hm, n, 1, torch.device("cuda"))
+st = DeviceStats(dm)
+for _ in range(2):
+    st.acc_stats_ali(feats, pdf, want_total=False)
+torch.cuda.synchronize()
+best = 1e9
+for _ in range(5):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    st.acc_stats_ali(feats, pdf, want_total=False)
+    e1.record()
+    torch.cuda.synchronize()
+    best = min(best, e0.elapsed_time(e1) / 1e3)
+peak = 6537.3
+try:
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+gbs = n * (4 * D + 4) / best / 1e9
+print(json.dumps({"workload": f"W-aligned {cfg}: D={D} P={P} G={G}, {n} frames resident in HBM", "frames_per_s": n / best,
+                  "ms": best * 1e3, "algorithmic_GBps": gbs, "hbm_peak_GBps": peak, "frac_of_hbm_roof": gbs / peak,
+                  "lib": os.environ.get("KHG_B200_LIB", "in-tree")}))
