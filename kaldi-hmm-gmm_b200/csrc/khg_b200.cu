@@ -270,7 +270,7 @@ void khg_model_destroy(khg_model *m) {
   for (Buf *b : {&m->w_feats, &m->w_ids, &m->w_wts, &m->w_out, &m->w_pf, &m->w_keys, &m->w_vals_in,
                  &m->w_vals_out, &m->w_cub, &m->w_starts, &m->w_item_start, &m->w_tot, &m->w_tid,
                  &m->w_tid2pdf, &m->w_trans, &m->w_keys_out, &m->w_sub, &m->w_full, &m->w_al_graph,
-                 &m->w_al_block, &m->w_al_bp, &m->w_al_cost, &m->w_al_ali, &m->w_al_path})
+                 &m->w_al_block, &m->w_al_bp, &m->w_al_cost, &m->w_al_ali, &m->w_al_path, &m->w_item_desc})
     b->release();
   for (int i = 0; i < 2; ++i) {
     m->pin_feats[i].release(); m->pin_ids[i].release(); m->pin_wts[i].release();
@@ -651,12 +651,16 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
     // upper bound on work items: every pdf wastes at most one partial item
     int f_min = stats_frames_for(m->max_gp, post_cap);
     int64_t max_items = n / f_min + P + 1;
+    KHG_TRY(m->w_item_desc.reserve(sizeof(int4) * (size_t)max_items));
+    item_table_kernel<<<grid_for(P, 4), 128, 0, st>>>(P, m->d_offsets, m->w_starts.as<int32_t>(), m->w_item_start.as<int32_t>(),
+                                                      post_cap, m->w_item_desc.as<int4>());
     StatsArgs a;
     a.feats = d_feats + t0 * D;
     a.order = m->w_vals_out.as<int32_t>();
     a.weights = d_w ? d_w + t0 : nullptr;
     a.starts = m->w_starts.as<int32_t>();
     a.item_start = m->w_item_start.as<int32_t>();
+    a.item_desc = m->w_item_desc.as<int4>();
     a.offsets = m->d_offsets;
     a.grp_start = m->d_grp_start;
     a.pack8 = m->d_pack8;
@@ -673,7 +677,7 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
     a.grp_batch = grp_batch;
     a.post_cap = post_cap;
     stats_kernel<<<(unsigned)max_items, 128, smem, st>>>(a);
-    g_launch_count += 5 + 3;  // ours + the radix-sort passes (library)
+    g_launch_count += 6 + 3;  // ours + the radix-sort passes (library)
     KHG_CUDA_TRY(cudaGetLastError());
   }
   return KHG_OK;

@@ -133,7 +133,7 @@ struct khg_model {
   // scratch
   khg::Buf w_feats, w_ids, w_wts, w_out, w_pf;         // device staging of host args
   khg::Buf w_keys, w_keys_out, w_vals_in, w_vals_out, w_cub;       // bucketing (K2)
-  khg::Buf w_starts, w_item_start, w_tot;              // per-pdf starts, work items, totals
+  khg::Buf w_starts, w_item_start, w_item_desc, w_tot;              // per-pdf starts, work items, totals
   khg::Buf w_tid, w_tid2pdf, w_trans;                  // tid path
   khg::Buf w_sub, w_full;                              // pdf-subset gather
   khg::Buf w_al_graph, w_al_block, w_al_bp, w_al_cost, w_al_ali, w_al_path;  // khg_align_batch (khg_align.cu)

@@ -374,6 +374,18 @@ __global__ void item_scan_kernel(int P, const int32_t *__restrict__ offsets,
   if (threadIdx.x == 0) item_start[P] = carry;
 }
 
+// item_desc[item] = {pdf, first position in `order`, frames, 0}: one warp per pdf writes the
+// descriptors of its work items, so that a statistics CTA starts from one 16-byte load instead of a
+// binary search over item_start.
+__global__ void item_table_kernel(int P, const int32_t *__restrict__ offsets, const int32_t *__restrict__ starts,
+                                  const int32_t *__restrict__ item_start, int post_cap, int4 *__restrict__ desc) {
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= P) return;
+  const int f = stats_frames_for(offsets[p + 1] - offsets[p], post_cap);
+  const int s0 = starts[p], s1 = starts[p + 1], i0 = item_start[p], ni = item_start[p + 1] - i0;
+  for (int i = threadIdx.x & 31; i < ni; i += 32) desc[i0 + i] = make_int4(p, s0 + i * f, min(f, s1 - (s0 + i * f)), 0);
+}
+
 // ---------------------------------------------------------------------------
 // K3: posteriors + sufficient statistics for frames bucketed by pdf.
 // Replaces, per frame, AccumAmDiagGmm::AccumulateForGmm
@@ -398,6 +410,7 @@ struct StatsArgs {
   const float *weights;     // T or NULL
   const int32_t *starts;    // P+1 positions in `order`
   const int32_t *item_start;  // P+1
+  const int4 *item_desc;      // per work item: {pdf, first position, frames, 0}
   const int32_t *offsets;   // P+1
   const int32_t *grp_start;   // P+1
   const float *pack8;
@@ -454,56 +467,52 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
   float *ms = post + a.post_cap;                        // grp_batch x 2 x D x 8
   float *gcs = ms + (size_t)a.grp_batch * 2 * D * 8;    // grp_batch x 8
   float *wsm = gcs + a.grp_batch * 8;                   // 128 weights
-  __shared__ int s_pdf;
+  __shared__ int s_idx[kStatsFrames];
   __shared__ double s_red[8];
   const int tid = threadIdx.x;
   const int item = blockIdx.x;
   if (item >= a.item_start[a.P]) return;
-  if (tid == 0) {  // largest p with item_start[p] <= item
-    int lo = 0, hi = a.P;
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (a.item_start[mid] <= item) lo = mid; else hi = mid;
-    }
-    s_pdf = lo;
-  }
-  __syncthreads();
-  const int p = s_pdf;
+  const int4 desc = __ldg(a.item_desc + item);
+  const int p = desc.x, pos0 = desc.y, n = desc.z;
   const int g0 = a.offsets[p], ng = a.offsets[p + 1] - g0;
   const int PG = stats_pitch(ng);
-  const int f = stats_frames_for(ng, a.post_cap);
-  const int pos0 = a.starts[p] + (item - a.item_start[p]) * f;
-  const int n = min(f, a.starts[p + 1] - pos0);
   const int grp0 = a.grp_start[p], ngrp = a.grp_start[p + 1] - grp0;
 
-  // stage features (gathered rows).  Each warp owns rows warp, warp+4, ...; it reads its
-  // 32 row indices with one load, then (rows 16-byte aligned) streams every row with
-  // cp.async 16-byte chunks so that all of its rows are in flight at once.
+  // stage features (gathered rows): the item's row indices go to shared memory first; then 16
+  // lanes per row issue the row's 16-byte chunks with cp.async (8 rows per pass, no per-row
+  // warp-wide bookkeeping); the pad columns of every row are zeroed by the row's owner thread.
   {
-    const int warp = tid >> 5, lane = tid & 31;
-    const int r_mine = warp + 4 * lane;
-    const int idx_mine = r_mine < n ? a.order[pos0 + r_mine] : 0;
+    int idx = 0;
+    if (tid < n) {
+      idx = a.order[pos0 + tid];
+      s_idx[tid] = idx;
+      wsm[tid] = a.weights ? a.weights[idx] : 1.0f;
+    }
+    for (int d = D; d < XP; ++d) X[tid * XP + d] = 0.f;
+    __syncthreads();
     const bool vec = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.feats) & 15) == 0);
-    const int chunks = D >> 2;
-    for (int k = 0; k < 32; ++k) {
-      const int r = warp + 4 * k;
-      if (r >= n) break;
-      const int idx = __shfl_sync(0xffffffffu, idx_mine, k);
-      const float *src = a.feats + (size_t)idx * D;
-      float *dst = X + r * XP;
-      if (vec) {
-        for (int c = lane; c < chunks; c += 32) {
+    if (vec) {
+      const int chunks = D >> 2, sub = tid & 15;
+      for (int r = tid >> 4; r < n; r += 8) {
+        const float *src = a.feats + (size_t)s_idx[r] * D;
+        float *dst = X + r * XP;
+        for (int c = sub; c < chunks; c += 16) {
           const uint32_t d32 = static_cast<uint32_t>(__cvta_generic_to_shared(dst + 4 * c));
           asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d32), "l"(src + 4 * c) : "memory");
         }
-        for (int d = D + lane; d < XP; d += 32) dst[d] = 0.f;
-      } else {
-        for (int d = lane; d < XP; d += 32) dst[d] = d < D ? src[d] : 0.f;
+      }
+    } else {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int r = warp; r < n; r += 4) {  // rows that are only 4-byte aligned (e.g. dim 39): 4-byte cp.async
+        const float *src = a.feats + (size_t)s_idx[r] * D;
+        for (int d = lane; d < D; d += 32) {
+          const uint32_t d32 = static_cast<uint32_t>(__cvta_generic_to_shared(X + r * XP + d));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32), "l"(src + d) : "memory");
+        }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  if (tid < n) wsm[tid] = a.weights ? a.weights[a.order[pos0 + tid]] : 1.0f;
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 
   // ---- phase A ----
@@ -572,51 +581,95 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
     if (a.call_like) atomicAdd(a.call_like, L);
   }
   // ---- phase B ----
-  const int n_gt = PG >> 2, n_dt = XP >> 2;
+  // (4 Gaussians x 4 dims) register tiles; when they fit the CTA, TQ = 128 / tiles frame slices per
+  // tile, whose partial sums are added in shared memory so that every statistic leaves the CTA as
+  // ONE fp64 atomic; pdfs with more than 128 tiles take the tiles in passes.
+  const int n_gt = PG >> 2, n_dt = (D + 3) >> 2;
   const int tiles = n_gt * n_dt;
-  int TQ = 1;
-  while (TQ < 4 && tiles * TQ * 2 <= 128) TQ <<= 1;
+  const int TQ = tiles <= 128 ? 128 / tiles : 1;
+  const int n_act = tiles * TQ;
+  const bool reduce = TQ > 1 && 36 * n_act <= kStatsFrames * XP + a.post_cap;
   const int per = (n + TQ - 1) / TQ;
-  for (int w = tid; w < tiles * TQ; w += 128) {
+  for (int w0 = 0; w0 < n_act; w0 += 128) {  // (one pass when the tiles fit the CTA)
+    const int w = w0 + tid;
+    const bool act = w < n_act;
     const int tq = w / tiles, tile = w - tq * tiles;
     const int gt = tile / n_dt, dt = tile - gt * n_dt;
-    const int ta = tq * per, tb = min(n, ta + per);
     float occ[4] = {0.f, 0.f, 0.f, 0.f};
     float sm[4][4], sv[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) sm[i][j] = sv[i][j] = 0.f;
-    const float *pp = post + gt * 4, *xp = X + dt * 4;
+    if (act) {
+      const int ta = tq * per, tb = min(n, ta + per);
+      const float *pp = post + gt * 4, *xp = X + dt * 4;
 #pragma unroll 2
-    for (int t = ta; t < tb; ++t) {
-      const float4 pq = *reinterpret_cast<const float4 *>(pp + t * PG);
-      const float4 xq = *reinterpret_cast<const float4 *>(xp + t * XP);
-      const float pv[4] = {pq.x, pq.y, pq.z, pq.w};
-      const float xv[4] = {xq.x, xq.y, xq.z, xq.w};
-      const float qv[4] = {xq.x * xq.x, xq.y * xq.y, xq.z * xq.z, xq.w * xq.w};
+      for (int t = ta; t < tb; ++t) {
+        const float4 pq = *reinterpret_cast<const float4 *>(pp + t * PG);
+        const float4 xq = *reinterpret_cast<const float4 *>(xp + t * XP);
+        const float pv[4] = {pq.x, pq.y, pq.z, pq.w};
+        const float xv[4] = {xq.x, xq.y, xq.z, xq.w};
+        const float qv[4] = {xq.x * xq.x, xq.y * xq.y, xq.z * xq.z, xq.w * xq.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        occ[i] += pv[i];
+        for (int i = 0; i < 4; ++i) {
+          occ[i] += pv[i];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          sm[i][j] = fmaf(pv[i], xv[j], sm[i][j]);
-          sv[i][j] = fmaf(pv[i], qv[j], sv[i][j]);
+          for (int j = 0; j < 4; ++j) {
+            sm[i][j] = fmaf(pv[i], xv[j], sm[i][j]);
+            sv[i][j] = fmaf(pv[i], qv[j], sv[i][j]);
+          }
         }
       }
     }
+    if (reduce) {
+      __syncthreads();  // every thread has finished reading X / post: they become the scratch
+      float *scr = smem;  // [36][n_act]
+      if (act) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int g = gt * 4 + i;
-      if (g >= ng) continue;
-      if (dt == 0) atomicAdd(&a.occ[g0 + g], (double)occ[i]);
+        for (int i = 0; i < 4; ++i) {
+          scr[i * n_act + w] = occ[i];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            scr[(4 + i * 4 + j) * n_act + w] = sm[i][j];
+            scr[(20 + i * 4 + j) * n_act + w] = sv[i][j];
+          }
+        }
+      }
+      __syncthreads();
+      for (int g = tid; g < ng; g += 128) {
+        const int tl = (g >> 2) * n_dt, k = g & 3;
+        float v = 0.f;
+        for (int q = 0; q < TQ; ++q) v += scr[k * n_act + q * tiles + tl];
+        atomicAdd(&a.occ[g0 + g], (double)v);
+      }
       if (a.mean) {
+        for (int o = tid; o < ng * D; o += 128) {
+          const int g = o / D, d = o - g * D;
+          const int tl = (g >> 2) * n_dt + (d >> 2), k = 4 + (g & 3) * 4 + (d & 3);
+          float v = 0.f, u = 0.f;
+          for (int q = 0; q < TQ; ++q) {
+            v += scr[k * n_act + q * tiles + tl];
+            u += scr[(k + 16) * n_act + q * tiles + tl];
+          }
+          atomicAdd(&a.mean[(size_t)(g0 + g) * D + d], (double)v);
+          if (a.var) atomicAdd(&a.var[(size_t)(g0 + g) * D + d], (double)u);
+        }
+      }
+    } else if (act) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int d = dt * 4 + j;
-          if (d >= D) continue;
-          atomicAdd(&a.mean[(size_t)(g0 + g) * D + d], (double)sm[i][j]);
-          if (a.var) atomicAdd(&a.var[(size_t)(g0 + g) * D + d], (double)sv[i][j]);
+      for (int i = 0; i < 4; ++i) {
+        const int g = gt * 4 + i;
+        if (g >= ng) continue;
+        if (dt == 0) atomicAdd(&a.occ[g0 + g], (double)occ[i]);
+        if (a.mean) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int d = dt * 4 + j;
+            if (d >= D) continue;
+            atomicAdd(&a.mean[(size_t)(g0 + g) * D + d], (double)sm[i][j]);
+            if (a.var) atomicAdd(&a.var[(size_t)(g0 + g) * D + d], (double)sv[i][j]);
+          }
         }
       }
     }
