@@ -423,12 +423,15 @@ struct StatsArgs {
   int P, D, grp_batch, post_cap;
 };
 
-// log-likes of NG (8 or 4) Gaussians of one group for the frame row xr (D floats)
+// log-likes of NG (8 or 4) Gaussians of one group for the frame row xr (D floats).  Packed fp32x2
+// arithmetic (FFMA2 on sm_100: two IEEE fused multiply-adds per issue slot, bitwise the same
+// results as scalar fmaf): one instruction per pair of Gaussians.
 template <int NG>
 __device__ __forceinline__ void stats_group_ll(const float *__restrict__ xr, const float *__restrict__ mm,
                                                const float *__restrict__ vv, int D, float (&aa)[8], float (&bb)[8]) {
+  float2 a2[4], b2[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) aa[j] = bb[j] = 0.f;
+  for (int j = 0; j < 4; ++j) a2[j] = b2[j] = make_float2(0.f, 0.f);
   const int D4 = D & ~3;
   for (int d0 = 0; d0 < D4; d0 += 4) {
     const float4 xq = *reinterpret_cast<const float4 *>(xr + d0);
@@ -436,17 +439,27 @@ __device__ __forceinline__ void stats_group_ll(const float *__restrict__ xr, con
 #pragma unroll
     for (int dd = 0; dd < 4; ++dd) {
       const float x = xs4[dd], q = x * x;  // data.array().square(), csrc/diag-gmm.cc:175
+      const float2 xx = make_float2(x, x), qq = make_float2(q, q);
       const float4 ma = *reinterpret_cast<const float4 *>(mm + (d0 + dd) * 8);
       const float4 va = *reinterpret_cast<const float4 *>(vv + (d0 + dd) * 8);
-      aa[0] = fmaf(ma.x, x, aa[0]); aa[1] = fmaf(ma.y, x, aa[1]); aa[2] = fmaf(ma.z, x, aa[2]); aa[3] = fmaf(ma.w, x, aa[3]);
-      bb[0] = fmaf(va.x, q, bb[0]); bb[1] = fmaf(va.y, q, bb[1]); bb[2] = fmaf(va.z, q, bb[2]); bb[3] = fmaf(va.w, q, bb[3]);
+      a2[0] = __ffma2_rn(make_float2(ma.x, ma.y), xx, a2[0]);
+      a2[1] = __ffma2_rn(make_float2(ma.z, ma.w), xx, a2[1]);
+      b2[0] = __ffma2_rn(make_float2(va.x, va.y), qq, b2[0]);
+      b2[1] = __ffma2_rn(make_float2(va.z, va.w), qq, b2[1]);
       if (NG == 8) {
         const float4 mb = *reinterpret_cast<const float4 *>(mm + (d0 + dd) * 8 + 4);
         const float4 vb = *reinterpret_cast<const float4 *>(vv + (d0 + dd) * 8 + 4);
-        aa[4] = fmaf(mb.x, x, aa[4]); aa[5] = fmaf(mb.y, x, aa[5]); aa[6] = fmaf(mb.z, x, aa[6]); aa[7] = fmaf(mb.w, x, aa[7]);
-        bb[4] = fmaf(vb.x, q, bb[4]); bb[5] = fmaf(vb.y, q, bb[5]); bb[6] = fmaf(vb.z, q, bb[6]); bb[7] = fmaf(vb.w, q, bb[7]);
+        a2[2] = __ffma2_rn(make_float2(mb.x, mb.y), xx, a2[2]);
+        a2[3] = __ffma2_rn(make_float2(mb.z, mb.w), xx, a2[3]);
+        b2[2] = __ffma2_rn(make_float2(vb.x, vb.y), qq, b2[2]);
+        b2[3] = __ffma2_rn(make_float2(vb.z, vb.w), qq, b2[3]);
       }
     }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    aa[2 * j] = a2[j].x; aa[2 * j + 1] = a2[j].y;
+    bb[2 * j] = b2[j].x; bb[2 * j + 1] = b2[j].y;
   }
   for (int d = D4; d < D; ++d) {
     const float x = xr[d], q = x * x;
@@ -558,9 +571,10 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
     const float lse = logf(s) + mx;
     if (!finite_f(lse)) atomicOr(a.err, ERR_NONFINITE);
     const float w = wsm[tid];
-    for (int g = 0; g < ng; ++g) pr[g] = (pr[g] / s) * w;
+    const float rs = __frcp_rn(s);  // exp / sum within 1 ulp of the reference's division (csrc/eigen.cc:29-31)
+    for (int g = 0; g < ng; ++g) pr[g] = (pr[g] * rs) * w;
     for (int g = ng; g < PG; ++g) pr[g] = 0.f;
-    if (a.per_frame) a.per_frame[a.order[pos0 + tid]] = lse;
+    if (a.per_frame) a.per_frame[s_idx[tid]] = lse;
     my_like = (double)(lse * w);
     my_w = (double)w;
   }
@@ -595,12 +609,11 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
     const bool act = w < n_act;
     const int tq = w / tiles, tile = w - tq * tiles;
     const int gt = tile / n_dt, dt = tile - gt * n_dt;
-    float occ[4] = {0.f, 0.f, 0.f, 0.f};
-    float sm[4][4], sv[4][4];
+    // packed fp32x2 accumulators: (dims 0,1) and (dims 2,3) of the tile per Gaussian, occupancies in pairs
+    float2 occ2[2], sm2[4][2], sv2[4][2];
+    occ2[0] = occ2[1] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) sm[i][j] = sv[i][j] = 0.f;
+    for (int i = 0; i < 4; ++i) sm2[i][0] = sm2[i][1] = sv2[i][0] = sv2[i][1] = make_float2(0.f, 0.f);
     if (act) {
       const int ta = tq * per, tb = min(n, ta + per);
       const float *pp = post + gt * 4, *xp = X + dt * 4;
@@ -608,19 +621,27 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
       for (int t = ta; t < tb; ++t) {
         const float4 pq = *reinterpret_cast<const float4 *>(pp + t * PG);
         const float4 xq = *reinterpret_cast<const float4 *>(xp + t * XP);
+        const float2 x01 = make_float2(xq.x, xq.y), x23 = make_float2(xq.z, xq.w);
+        const float2 q01 = __fmul2_rn(x01, x01), q23 = __fmul2_rn(x23, x23);
+        occ2[0] = __fadd2_rn(occ2[0], make_float2(pq.x, pq.y));
+        occ2[1] = __fadd2_rn(occ2[1], make_float2(pq.z, pq.w));
         const float pv[4] = {pq.x, pq.y, pq.z, pq.w};
-        const float xv[4] = {xq.x, xq.y, xq.z, xq.w};
-        const float qv[4] = {xq.x * xq.x, xq.y * xq.y, xq.z * xq.z, xq.w * xq.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          occ[i] += pv[i];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            sm[i][j] = fmaf(pv[i], xv[j], sm[i][j]);
-            sv[i][j] = fmaf(pv[i], qv[j], sv[i][j]);
-          }
+          const float2 p2 = make_float2(pv[i], pv[i]);
+          sm2[i][0] = __ffma2_rn(p2, x01, sm2[i][0]);
+          sm2[i][1] = __ffma2_rn(p2, x23, sm2[i][1]);
+          sv2[i][0] = __ffma2_rn(p2, q01, sv2[i][0]);
+          sv2[i][1] = __ffma2_rn(p2, q23, sv2[i][1]);
         }
       }
+    }
+    const float occ[4] = {occ2[0].x, occ2[0].y, occ2[1].x, occ2[1].y};
+    float sm[4][4], sv[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      sm[i][0] = sm2[i][0].x; sm[i][1] = sm2[i][0].y; sm[i][2] = sm2[i][1].x; sm[i][3] = sm2[i][1].y;
+      sv[i][0] = sv2[i][0].x; sv[i][1] = sv2[i][0].y; sv[i][2] = sv2[i][1].x; sv[i][3] = sv2[i][1].y;
     }
     if (reduce) {
       __syncthreads();  // every thread has finished reading X / post: they become the scratch
