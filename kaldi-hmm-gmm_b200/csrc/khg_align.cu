@@ -599,10 +599,16 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   // ---------------- kernel shape
   const size_t cost_bytes = sizeof(double) * 3 * (size_t)S_max;
   const size_t smem_budget = 200 * 1024;
-  const bool use_gcost = cost_bytes > 160 * 1024;
+  // KHG_ALIGN_FORCE_GCOST / KHG_ALIGN_FORCE_FC: tests force the large-graph paths (costs in global
+  // scratch; likelihood tile of 16 / 8 / 0 frames) on small inputs
+  const bool use_gcost = cost_bytes > 160 * 1024 || getenv("KHG_ALIGN_FORCE_GCOST") != nullptr;
   int FC = 0;
+  const char *force_fc = getenv("KHG_ALIGN_FORCE_FC");
   for (int fc : {32, 16, 8})
-    if ((use_gcost ? 0 : cost_bytes) + 4 * (size_t)fc * n_pdf_max <= smem_budget) { FC = fc; break; }
+    if ((use_gcost ? 0 : cost_bytes) + 4 * (size_t)fc * n_pdf_max <= smem_budget && (!force_fc || fc <= atoi(force_fc))) {
+      FC = fc;
+      break;
+    }
   const size_t smem = (use_gcost ? 0 : cost_bytes) + 4 * (size_t)FC * n_pdf_max + 16;
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });

@@ -29,7 +29,10 @@ class DeviceModel:
 
     def close(self):
         if getattr(self, "_h", None):
-            A.lib().khg_model_destroy(self._h)
+            try:
+                A.lib().khg_model_destroy(self._h)
+            except TypeError:  # interpreter shutdown: module globals already cleared
+                pass
             self._h = None
 
     __del__ = close
@@ -259,7 +262,10 @@ class DeviceStats:
 
     def close(self):
         if getattr(self, "_h", None):
-            A.lib().khg_stats_destroy(self._h)
+            try:
+                A.lib().khg_stats_destroy(self._h)
+            except TypeError:  # interpreter shutdown: module globals already cleared
+                pass
             self._h = None
 
     __del__ = close

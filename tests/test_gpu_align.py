@@ -100,6 +100,21 @@ def test_align_batch_in_several_chunks(monkeypatch):
     _check(out, ll, gb, graphs, t2p, 1.0, 8.0, 40.0, pdf_ids)
 
 
+@pytest.mark.parametrize("env", [{"KHG_ALIGN_FORCE_GCOST": "1"}, {"KHG_ALIGN_FORCE_FC": "0"}, {"KHG_ALIGN_FORCE_FC": "8"},
+                                 {"KHG_ALIGN_FORCE_GCOST": "1", "KHG_ALIGN_FORCE_FC": "16"}])
+def test_align_batch_large_graph_paths(monkeypatch, env):
+    """The code paths very large graphs take (state costs in global scratch instead of shared
+    memory; likelihoods read from the block directly or staged 8 / 16 frames at a time), forced on
+    small inputs: same results, narrow and wide beams, epsilon arcs and retries included."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    model, graphs, feats, t2p = _batch(29, 14)
+    dm = _device_model(model)
+    for beam, retry in [(200.0, 0.0), (3.0, 30.0)]:
+        out, ll, gb, pdf_ids = _run(dm, graphs, feats, t2p, 1.0, beam, retry)
+        _check(out, ll, gb, graphs, t2p, 1.0, beam, retry, pdf_ids)
+
+
 def test_align_batch_device_features_and_oracle_likelihoods():
     """Device-resident features; and the same alignment from the ORACLE's likelihoods (the two
     likelihood paths agree within 1e-3, far below the margins between paths on this data)."""
