@@ -316,6 +316,20 @@ khg_status khg_align_batch(khg_model *m, const khg_graph_batch *graphs, const fl
                            int32_t *path_arcs, int64_t *path_offsets, int64_t path_capacity,
                            int32_t *pdf_ids_dev);
 
+/* ------------------------------------------------------------------ mix-up --
+ * AmDiagGmm::SplitByCount (csrc/am-diag-gmm.cc:72-89) on the packed device model: the per-pdf
+ * targets of GetSplitTargets (csrc/model-common.cc:29-70; state_occs = HOST float[num_pdfs],
+ * power-law allocation with the min_count rule), then DiagGmm::Split (csrc/diag-gmm.cc:780-851) on
+ * every pdf below its target, and ComputeGconsts.  Returns a NEW handle (the Gaussian count changes);
+ * the old one stays valid.
+ * randn: HOST float[randn_rows x dim], the standard-normal vector of each split in the order the
+ * reference draws them (pdf by pdf, split by split) — pass the reference's draws to reproduce its
+ * result; NULL = drawn inside from `seed`.  *num_gauss_out = Gaussians of the new model. */
+khg_status khg_model_split_by_count(khg_model *m, const float *state_occs, int32_t target_components,
+                                    float perturb_factor, float power, float min_count, const float *randn,
+                                    int64_t randn_rows, uint64_t seed, khg_model **new_model,
+                                    int32_t *num_gauss_out);
+
 /* -------------------------------------------------------- Gaussian selection --
  * DiagGmm::GaussianSelection for a matrix of frames (csrc/diag-gmm.cc:241-317; the one-frame form
  * :202-239 is T = 1) and DiagGmm::GaussianSelectionPreselect (:319-366) on pdf `pdf` of the model

@@ -369,6 +369,33 @@ void AmDiagGmm::CopyFromAmDiagGmm(const AmDiagGmm &other) {
   for (int32_t i = 0; i < other.NumPdfs(); ++i) densities_.emplace_back(new DiagGmm(*other.densities_[i]));
 }
 
+void AmDiagGmm::SplitByCount(const FloatVector &state_occs, int32_t target_components, float perturb_factor, float power,
+                             float min_count, const FloatMatrix *randn, uint64_t seed) {
+  KHG_HOST_ASSERT((int32_t)state_occs.size() == NumPdfs());
+  static uint64_t calls = 0;  // distinct draws per call when no seed is given (the reference uses a global generator)
+  khg_model *nm = nullptr;
+  int32_t G = 0;
+  Check(khg_model_split_by_count(Device(), state_occs.data(), target_components, perturb_factor, power, min_count,
+                                 randn ? randn->data.data() : nullptr, randn ? randn->rows : 0,
+                                 seed ? seed : 0x9E3779B97F4A7C15ull + (++calls), &nm, &G));
+  ModelHandle guard;
+  guard.h = nm;
+  const int32_t P = NumPdfs(), D = Dim();
+  std::vector<int32_t> offs(P + 1);
+  std::vector<float> w(G), miv((size_t)G * D), iv((size_t)G * D), gc(G);
+  Check(khg_model_download(nm, offs.data(), w.data(), miv.data(), iv.data(), gc.data()));
+  for (int32_t p = 0; p < P; ++p) {
+    const int32_t g0 = offs[p], n = offs[p + 1] - g0;
+    if (n == densities_[p]->NumGauss()) continue;  // not split
+    FloatVector pw(w.begin() + g0, w.begin() + g0 + n);
+    FloatMatrix piv(n, D), pmiv(n, D);
+    std::copy(iv.begin() + (size_t)g0 * D, iv.begin() + (size_t)(g0 + n) * D, piv.data.begin());
+    std::copy(miv.begin() + (size_t)g0 * D, miv.begin() + (size_t)(g0 + n) * D, pmiv.data.begin());
+    densities_[p]->SetParams(&pw, &piv, &pmiv);
+    densities_[p]->ComputeGconsts();  // csrc/diag-gmm.cc:850
+  }
+}
+
 int32_t AmDiagGmm::NumGauss() const {
   int32_t ans = 0;
   for (auto &d : densities_) ans += d->NumGauss();

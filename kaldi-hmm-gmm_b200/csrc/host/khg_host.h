@@ -172,6 +172,10 @@ class AmDiagGmm {
   FloatVector GetGaussianMean(int32_t pdf_index, int32_t gauss) const;
   FloatVector GetGaussianVariance(int32_t pdf_index, int32_t gauss) const;
   void SetGaussianMean(int32_t pdf_index, int32_t gauss_index, const FloatVector &in);
+  // Mix-up on the device pack (khg_model_split_by_count), then the host pdfs are rebuilt from it.
+  // randn: optional (rows x dim) standard-normal draws in the reference's order; seed otherwise.
+  void SplitByCount(const FloatVector &state_occs, int32_t target_components, float perturb_factor, float power,
+                    float min_count, const FloatMatrix *randn = nullptr, uint64_t seed = 0);  // csrc/am-diag-gmm.cc:72-89
 
   // Device pack of the whole model (K4), rebuilt when any pdf changed.  Requires
   // valid gconsts on every pdf (csrc/decodable-am-diag-gmm.cc:49-53).

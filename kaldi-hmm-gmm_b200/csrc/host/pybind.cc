@@ -235,6 +235,19 @@ PYBIND11_MODULE(_khg_b200, m) {
       .def("set_gaussian_mean",
            [](AmDiagGmm &s, int32_t p, int32_t g, const FArr &in) { s.SetGaussianMean(p, g, ToVec(in)); },
            py::arg("pdf_index"), py::arg("gauss_index"), py::arg("in"))
+      // python/csrc/am-diag-gmm.cc:27-30 (+ optional randn / seed: reproducible perturbations)
+      .def("split_by_count",
+           [](AmDiagGmm &s, const FArr &occs, int32_t target, float perturb, float power, float min_count, py::object randn,
+              uint64_t seed) {
+             if (randn.is_none()) {
+               s.SplitByCount(ToVec(occs), target, perturb, power, min_count, nullptr, seed);
+             } else {
+               FloatMatrix r = ToMat(randn.cast<FArr>());
+               s.SplitByCount(ToVec(occs), target, perturb, power, min_count, &r, seed);
+             }
+           },
+           py::arg("state_occs"), py::arg("target_components"), py::arg("perturb_factor"), py::arg("power"),
+           py::arg("min_count"), py::arg("randn") = py::none(), py::arg("seed") = 0)
       // new, batched: (T, num_pdfs) block of per-pdf log-likelihoods computed by the dense kernel
       .def("log_likelihoods_all_pdfs",
            [](const AmDiagGmm &s, const FArr &feats, float scale) {

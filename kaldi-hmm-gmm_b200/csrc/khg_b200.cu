@@ -802,17 +802,6 @@ khg_status khg_model_download(khg_model *m, int32_t *gauss_offsets, float *weigh
 
 extern "C++" {
 namespace {
-struct DevTmp {  // small RAII bundle of device scratch for the M-step
-  std::vector<void *> ptrs;
-  ~DevTmp() { for (void *p : ptrs) cudaFree(p); }
-  template <class T> khg_status alloc(T **out, size_t n) {
-    void *p = nullptr;
-    KHG_CUDA_TRY(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-    ptrs.push_back(p);
-    *out = static_cast<T *>(p);
-    return KHG_OK;
-  }
-};
 }  // namespace
 }  // extern "C++"
 
@@ -907,23 +896,11 @@ khg_status khg_mle_update(khg_model *m, const khg_stats *s, const khg_mle_option
   mle_compact_kernel<<<P, 128, shm, st>>>(P, D, m->d_offsets, d_new_off, remove, w_new, miv_new, iv_new,
                                           nm->d_weights, nm->d_miv, nm->d_iv);
   ++g_launch_count;
-  // finish the new handle exactly like khg_model_upload(gconsts = NULL) does, from device data
-  KHG_CUDA_TRY(cudaMemsetAsync(nm->d_scratch_int, 0, sizeof(int) * 4, st));
-  gconsts_kernel<<<grid_for(nm->G, 128), 128, 0, st>>>(nm->G, D, nm->d_weights, nm->d_miv, nm->d_iv, nm->d_gconsts, nm->d_scratch_int);
-  pack_simt_kernel<<<std::min(1024u, grid_for((int64_t)nm->n_chunks * 2 * D * kSimtChunk, 256)), 256, 0, st>>>(
-      nm->G, D, nm->n_chunks, nm->d_miv, nm->d_iv, nm->d_packT);
-  pack8_kernel<<<P, 128, 0, st>>>(P, D, nm->d_offsets, nm->d_grp_start, nm->d_miv, nm->d_iv, nm->d_gconsts, nm->d_pack8, nm->d_gc8);
-  g_launch_count += 3;
-  KHG_CUDA_TRY(cudaGetLastError());
-  nm->uploaded = true;
-  if (nm->kernel != KHG_KERNEL_SIMT && tc_supported(nm)) {
-    khg_status ts = tc_pack_build(nm);
-    if (ts != KHG_OK && (nm->kernel == KHG_KERNEL_TCGEN05 || nm->kernel == KHG_KERNEL_TCGEN05_F16)) {
-      khg_model_destroy(nm);
-      return ts;
-    }
+  khg_status fs = finish_model_from_device(nm, nullptr);
+  if (fs != KHG_OK) {
+    khg_model_destroy(nm);
+    return fs;
   }
-  KHG_CUDA_TRY(cudaStreamSynchronize(st));
   *new_model = nm;
   return KHG_OK;
 }
@@ -1016,6 +993,37 @@ khg_status khg_estep(khg_model *m, khg_stats *s, const float *feats, int64_t T, 
 }  // extern "C"
 
 namespace khg {
+// Finishes a handle whose d_weights / d_miv / d_iv were written on the device, exactly like
+// khg_model_upload(gconsts = NULL) does from host data: gconsts, the derived packs, the
+// tensor-core operand.  num_bad (optional): ComputeGconsts' count of -inf gconsts.
+khg_status finish_model_from_device(khg_model *nm, int32_t *num_bad) {
+  cudaStream_t st = nm->stream;
+  const int D = nm->dim, P = nm->P;
+  KHG_CUDA_TRY(cudaMemsetAsync(nm->d_scratch_int, 0, sizeof(int) * 4, st));
+  gconsts_kernel<<<grid_for(nm->G, 128), 128, 0, st>>>(nm->G, D, nm->d_weights, nm->d_miv, nm->d_iv, nm->d_gconsts, nm->d_scratch_int);
+  pack_simt_kernel<<<std::min(1024u, grid_for((int64_t)nm->n_chunks * 2 * D * kSimtChunk, 256)), 256, 0, st>>>(
+      nm->G, D, nm->n_chunks, nm->d_miv, nm->d_iv, nm->d_packT);
+  pack8_kernel<<<P, 128, 0, st>>>(P, D, nm->d_offsets, nm->d_grp_start, nm->d_miv, nm->d_iv, nm->d_gconsts, nm->d_pack8, nm->d_gc8);
+  g_launch_count += 3;
+  KHG_CUDA_TRY(cudaGetLastError());
+  int flags[2] = {0, 0};
+  KHG_CUDA_TRY(cudaMemcpyAsync(flags, nm->d_scratch_int, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+  KHG_CUDA_TRY(cudaStreamSynchronize(st));
+  if (flags[1]) {
+    set_error("not a number in gconst computation");  // csrc/diag-gmm.cc:132-135
+    return KHG_ERR_NONFINITE;
+  }
+  if (num_bad) *num_bad = flags[0];
+  nm->uploaded = true;
+  nm->tc.ready = false;
+  if (nm->kernel != KHG_KERNEL_SIMT && tc_supported(nm)) {
+    khg_status ts = tc_pack_build(nm);
+    if (ts != KHG_OK && (nm->kernel == KHG_KERNEL_TCGEN05 || nm->kernel == KHG_KERNEL_TCGEN05_F16)) return ts;
+  }
+  KHG_CUDA_TRY(cudaStreamSynchronize(st));
+  return KHG_OK;
+}
+
 khg_status dense_block(khg_model *m, const float *d_feats, int64_t T, float scale, int layout, float *d_out, int64_t ld) {
   return dense_device(m, d_feats, T, scale, layout, d_out, ld);
 }

@@ -53,6 +53,19 @@ struct Buf {
   template <class T> T *as() { return static_cast<T *>(p); }
 };
 
+// Small RAII bundle of device scratch (M-step, mix-up).
+struct DevTmp {
+  std::vector<void *> ptrs;
+  ~DevTmp() { for (void *p : ptrs) cudaFree(p); }
+  template <class T> khg_status alloc(T **out, size_t n) {
+    void *p = nullptr;
+    KHG_CUDA_TRY(cudaMalloc(&p, (n > 0 ? n : 1) * sizeof(T)));
+    ptrs.push_back(p);
+    *out = static_cast<T *>(p);
+    return KHG_OK;
+  }
+};
+
 // ---- SIMT model pack ---------------------------------------------------------
 // Gaussians are grouped in chunks of 32 (global Gaussian index / 32); chunk c
 // holds [which(0=means_invvars,1=inv_vars)][d][g%32], zero padded, so a CTA can
@@ -164,6 +177,7 @@ khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scal
 // and the synchronising read of the latched device error flag
 khg_status dense_block(khg_model *m, const float *d_feats, int64_t T, float scale, int layout, float *d_out, int64_t ld);
 khg_status sync_and_check(khg_model *m);
+khg_status finish_model_from_device(khg_model *nm, int32_t *num_bad);
 }  // namespace khg
 
 #endif  // KHG_INTERNAL_H_

@@ -136,6 +136,20 @@ class DeviceModel:
         A.check(A.lib().khg_loglikes_pdf_subset(self._h, fp, T, floc, sub.ctypes.data, sub.size, scale, op, T, oloc))
         return out
 
+    def split_by_count(self, state_occs, target_components: int, perturb_factor: float = 0.01, power: float = 0.2,
+                       min_count: float = 20.0, randn=None, seed: int = 0) -> "DeviceModel":
+        """AmDiagGmm::SplitByCount (reference csrc/am-diag-gmm.cc:72-89; defaults of scripts/gmm_est.py) on the
+        device: a NEW DeviceModel with the mixed-up Gaussians.  randn (rows x dim): the standard-normal
+        vector of every split in the reference's order, or None to draw them from `seed`."""
+        occ = np.ascontiguousarray(state_occs, np.float32)
+        assert occ.size == self.num_pdfs
+        rn = None if randn is None else np.ascontiguousarray(randn, np.float32).reshape(-1, self.dim)
+        nh, ng = C.c_void_p(), C.c_int32()
+        A.check(A.lib().khg_model_split_by_count(self._h, occ.ctypes.data, int(target_components), perturb_factor, power,
+                                                 min_count, None if rn is None else rn.ctypes.data,
+                                                 0 if rn is None else rn.shape[0], seed, C.byref(nh), C.byref(ng)))
+        return DeviceModel._from_handle(nh)
+
     def gaussian_selection(self, pdf: int, feats, num_gselect: int, preselect=None, want_loglikes: bool = False):
         """DiagGmm::GaussianSelection / GaussianSelectionPreselect (reference csrc/diag-gmm.cc:202-366) of
         pdf `pdf` for all rows of feats: (total log-like, indices int32 [T, k], per-frame log-like [T]

@@ -417,3 +417,65 @@ def np_gaussian_selection(loglikes, num_gselect: int, labels=None):
         out.append(lab)
         tot = np_log_add(tot, np.float32(v))
     return tot, out
+
+
+def np_get_split_targets(state_occs, target_components: int, power: float, min_count: float):
+    """GetSplitTargets, reference csrc/model-common.cc:14-70: every pdf starts with one Gaussian; the pdf with
+    the largest pow(occ, power) / num_components gets the next one unless (n + 1) * min_count >= occ,
+    which retires it.  (The reference's priority queue breaks exact ties by its heap order; this
+    restatement takes the first maximum — use distinct occupancies when comparing.)"""
+    occs = np.asarray(state_occs, np.float32)
+    P = occs.size
+    occ_pow = np.power(occs.astype(np.float64), np.float64(np.float32(power))).astype(np.float32)  # float occ = pow(...)
+    n = np.ones(P, np.int64)
+    live = occ_pow.astype(np.float64).copy()
+    num_gauss = P
+    while num_gauss < target_components:
+        key = live / (n + 1.0e-10)
+        p = int(np.argmax(key))
+        if live[p] == 0:
+            break
+        if (n[p] + 1) * np.float32(min_count) >= occs[p]:
+            live[p] = 0.0
+        else:
+            n[p] += 1
+            num_gauss += 1
+    return n.astype(np.int32)
+
+
+def np_split_by_count(model: "PackedModel", state_occs, target_components: int, perturb_factor: float, power: float,
+                      min_count: float, randn):
+    """AmDiagGmm::SplitByCount (csrc/am-diag-gmm.cc:72-89) + DiagGmm::Split (csrc/diag-gmm.cc:780-851) +
+    ComputeGconsts, float32 like the reference.  randn: (rows, dim) standard-normal vectors, one per
+    split, consumed pdf by pdf.  Returns a new PackedModel."""
+    targets = np_get_split_targets(state_occs, target_components, power, min_count)
+    D = model.dim
+    randn = np.asarray(randn, np.float32).reshape(-1, D)
+    W, MIV, IV, GC, offs = [], [], [], [], [0]
+    row = 0
+    pf = np.float32(perturb_factor)
+    for p in range(model.num_pdfs):
+        s = slice(model.offsets[p], model.offsets[p + 1])
+        w, miv, iv = model.weights[s].copy(), model.means_invvars[s].copy(), model.inv_vars[s].copy()
+        tgt = int(targets[p])
+        if w.size < tgt:
+            cur = w.size
+            w = np.concatenate([w, np.zeros(tgt - cur, np.float32)])
+            miv = np.concatenate([miv, np.zeros((tgt - cur, D), np.float32)])
+            iv = np.concatenate([iv, np.zeros((tgt - cur, D), np.float32)])
+            while cur < tgt:
+                mx = int(np.argmax(w[:cur]))  # first maximum (strict > in the reference's scan)
+                w[mx] = np.float32(w[mx] / np.float32(2))
+                w[cur] = w[mx]
+                r = (randn[row] * np.sqrt(iv[mx])).astype(np.float32)
+                row += 1
+                iv[cur] = iv[mx]
+                step = (r * pf).astype(np.float32)
+                miv[cur] = miv[mx] + step
+                miv[mx] = miv[mx] - step
+                cur += 1
+        gc, _ = np_compute_gconsts(w, miv, iv)
+        W.append(w), MIV.append(miv), IV.append(iv), GC.append(gc)
+        offs.append(offs[-1] + w.size)
+    return PackedModel(np.asarray(offs, np.int32), np.concatenate(W), np.concatenate(MIV), np.concatenate(IV),
+                       np.concatenate(GC))
