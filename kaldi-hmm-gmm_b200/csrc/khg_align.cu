@@ -420,10 +420,65 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   const bool timing = getenv("KHG_ALIGN_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_begin = now();
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float ms_dense = 0.f, ms_search = 0.f;
   if (timing)
     for (auto &e : ev) cudaEventCreate(&e);
+
+  // ---------------- chunks of consecutive utterances: bounded likelihood block and back-pointers
+  // (a quarter of the free HBM each, at most 24 GB: more utterances per launch = more CTAs per SM
+  // for the latency-bound search).  Needs only the frame and state counts, so the dense kernel of
+  // the first chunk is launched BEFORE the host transposes the graphs and runs under that work.
+  std::vector<int64_t> bp0_v(U), col0_v(U);
+  std::vector<int> chunk_start(1, 0);
+  size_t bp_bytes_max = 0;
+  int64_t chunk_frames_max = 0;
+  int max_chunk_utts = 0;
+  {
+    size_t mem_free = 0, mem_total = 0;
+    KHG_CUDA_TRY(cudaMemGetInfo(&mem_free, &mem_total));
+    mem_free += m->w_al_block.cap + m->w_al_bp.cap;  // what an earlier call already holds is reusable
+    const int64_t budget = std::max<int64_t>(256LL << 20, std::min<int64_t>(24LL << 30, (int64_t)(mem_free / 4)));
+    int64_t max_chunk_frames = std::max<int64_t>(1024, budget / (4LL * P));
+    if (const char *e = getenv("KHG_ALIGN_CHUNK_FRAMES")) max_chunk_frames = std::max<int64_t>(1, atoll(e));  // tests: force several chunks
+    int64_t fr = 0, bpb = 0;
+    for (int u = 0; u < U; ++u) {
+      const int64_t Tu = gb->frame_offsets[u + 1] - gb->frame_offsets[u];
+      const int64_t Su = gb->state_offsets[u + 1] - gb->state_offsets[u];
+      KHG_REQUIRE(Tu >= 0 && Su >= 0 && Tu < (1LL << 31), "graph of utterance " + std::to_string(u) + ": frame / state offsets out of range");
+      const int64_t ub = 4LL * (Tu + 1) * Su;
+      if (u > chunk_start.back() && (fr + Tu > max_chunk_frames || bpb + ub > budget)) {
+        chunk_start.push_back(u);
+        fr = 0;
+        bpb = 0;
+      }
+      bp0_v[u] = bpb / 4;
+      col0_v[u] = fr;
+      fr += Tu;
+      bpb += ub;
+      bp_bytes_max = std::max(bp_bytes_max, (size_t)bpb);
+      chunk_frames_max = std::max(chunk_frames_max, fr);
+      max_chunk_utts = std::max(max_chunk_utts, u - chunk_start.back() + 1);
+    }
+    chunk_start.push_back(U);
+  }
+  const int64_t ld = (chunk_frames_max + 3) & ~(int64_t)3;
+  KHG_TRY(m->w_al_block.reserve(sizeof(float) * (size_t)P * std::max<int64_t>(ld, 4)));
+  float *d_block = m->w_al_block.as<float>();
+  auto launch_dense = [&](int u0, int u1) -> khg_status {
+    const int64_t f0 = gb->frame_offsets[u0] - gb->frame_offsets[0], nfr = gb->frame_offsets[u1] - gb->frame_offsets[u0];
+    if (nfr <= 0) return KHG_OK;
+    const float *d_f = feats + (gb->frame_offsets[0] + f0) * D;
+    if (feats_loc == KHG_HOST) {
+      KHG_TRY(m->w_feats.reserve(sizeof(float) * (size_t)nfr * D));
+      KHG_CUDA_TRY(cudaMemcpyAsync(m->w_feats.p, d_f, sizeof(float) * (size_t)nfr * D, cudaMemcpyHostToDevice, st));
+      d_f = m->w_feats.as<float>();
+    }
+    return dense_block(m, d_f, nfr, acoustic_scale, KHG_PDF_MAJOR, d_block, ld);
+  };
+  if (timing) cudaEventRecord(ev[0], st);
+  KHG_TRY(launch_dense(chunk_start[0], chunk_start[1]));
+  if (timing) cudaEventRecord(ev[1], st);
 
   // ---------------- host: transpose every graph (incoming emitting arcs per state, incoming
   // epsilon arcs per state), local pdf lists
@@ -443,6 +498,8 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     d.S = S;
     d.state0 = s0;
     d.start = gb->start_state[u];
+    d.bp0 = bp0_v[u];
+    d.col0 = (int32_t)col0_v[u];
     if (d.T < 0 || S < 0 || d.start >= S) { bad[u] = 1; return; }
     auto &st_ = stamp[w];
     auto &li = lidx[w];
@@ -467,7 +524,10 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     d.n_pdf = (int32_t)updf[u].size();
   });
   for (int u = 0; u < U; ++u)
-    KHG_REQUIRE(!bad[u], "graph of utterance " + std::to_string(u) + ": state / label / offset out of range");
+    if (bad[u]) {
+      cudaStreamSynchronize(st);  // the first chunk's dense kernel is already running
+      KHG_REQUIRE(false, "graph of utterance " + std::to_string(u) + ": state / label / offset out of range");
+    }
   // prefix sums: in-arc CSR over all states; epsilon-destination lists
   for (size_t s = 0; s < (size_t)S_all; ++s) in_off[s + 1] += in_off[s];
   std::vector<int32_t> ed_state, ed_off(1, 0), utt_pdfs;
@@ -525,47 +585,14 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     return bytes ? cudaMemcpyAsync(gbase + off, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
   };
 
-  // ---------------- chunks of consecutive utterances: bounded likelihood block and back-pointers
-  // (a quarter of the free HBM each, at most 24 GB: more utterances per launch = more CTAs per SM
-  // for the latency-bound search)
-  size_t mem_free = 0, mem_total = 0;
-  KHG_CUDA_TRY(cudaMemGetInfo(&mem_free, &mem_total));
-  mem_free += m->w_al_block.cap + m->w_al_bp.cap;  // what an earlier call already holds is reusable
-  const int64_t budget = std::max<int64_t>(256LL << 20, std::min<int64_t>(24LL << 30, (int64_t)(mem_free / 4)));
-  const int64_t max_block_bytes = budget, max_bp_bytes = budget;
-  int64_t max_chunk_frames = std::max<int64_t>(1024, max_block_bytes / (4LL * P));
-  if (const char *e = getenv("KHG_ALIGN_CHUNK_FRAMES")) max_chunk_frames = std::max<int64_t>(1, atoll(e));  // tests: force several chunks
-  std::vector<int> chunk_start(1, 0);
-  {
-    int64_t fr = 0, bpb = 0;
-    for (int u = 0; u < U; ++u) {
-      const int64_t ub = 4LL * ((int64_t)desc[u].T + 1) * desc[u].S;
-      if (u > chunk_start.back() && (fr + desc[u].T > max_chunk_frames || bpb + ub > max_bp_bytes)) {
-        chunk_start.push_back(u);
-        fr = 0;
-        bpb = 0;
-      }
-      desc[u].bp0 = bpb / 4;
-      desc[u].col0 = (int32_t)fr;
-      fr += desc[u].T;
-      bpb += ub;
-    }
-    chunk_start.push_back(U);
-  }
+  // launch order inside each chunk: longest search first
   std::vector<int32_t> order(U);
-  size_t bp_bytes_max = 0;
-  int64_t chunk_frames_max = 0;
-  int max_chunk_utts = 0;
   for (size_t c = 0; c + 1 < chunk_start.size(); ++c) {
     const int u0 = chunk_start[c], u1 = chunk_start[c + 1];
     for (int u = u0; u < u1; ++u) order[u] = u - u0;
     std::stable_sort(order.begin() + u0, order.begin() + u1, [&](int a, int b) {
       return (int64_t)desc[u0 + a].T * desc[u0 + a].S > (int64_t)desc[u0 + b].T * desc[u0 + b].S;
     });
-    const UttDesc &l = desc[u1 - 1];
-    bp_bytes_max = std::max(bp_bytes_max, (size_t)(l.bp0 * 4 + 4LL * ((int64_t)l.T + 1) * l.S));
-    chunk_frames_max = std::max<int64_t>(chunk_frames_max, l.col0 + l.T);
-    max_chunk_utts = std::max(max_chunk_utts, u1 - u0);
   }
   KHG_CUDA_TRY(up(o_desc, desc.data(), sizeof(UttDesc) * U));
   KHG_CUDA_TRY(up(o_inoff, in_off.data(), 4 * in_off.size()));
@@ -618,32 +645,23 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     KHG_TRY(m->w_al_cost.reserve(sizeof(double) * 3 * (size_t)S_max * max_chunk_utts));
     d_gcost = m->w_al_cost.as<double>();
   }
-  const int64_t ld = (chunk_frames_max + 3) & ~(int64_t)3;
-  KHG_TRY(m->w_al_block.reserve(sizeof(float) * (size_t)P * std::max<int64_t>(ld, 4)));
   KHG_TRY(m->w_al_bp.reserve(std::max<size_t>(bp_bytes_max, 256)));
   KHG_TRY(m->w_al_ali.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(T_all, 1)));
   int32_t *d_ali = m->w_al_ali.as<int32_t>();
   KHG_CUDA_TRY(cudaMemsetAsync(d_ali, 0, sizeof(int32_t) * (size_t)T_all, st));
   if (pdf_ids_dev) KHG_CUDA_TRY(cudaMemsetAsync(pdf_ids_dev, 0, sizeof(int32_t) * (size_t)T_all, st));
-  float *d_block = m->w_al_block.as<float>();
   int32_t *d_bp = m->w_al_bp.as<int32_t>();
   std::vector<UttOut> h_outs(U);
   std::vector<int64_t> h_poff((size_t)U + 1, 0);
 
   for (size_t c = 0; c + 1 < chunk_start.size(); ++c) {
     const int u0 = chunk_start[c], u1 = chunk_start[c + 1];
-    const int64_t f0 = desc[u0].frame0, nfr = desc[u1 - 1].frame0 + desc[u1 - 1].T - f0;
-    if (timing) cudaEventRecord(ev[0], st);
-    if (nfr > 0) {
-      const float *d_f = feats + (gb->frame_offsets[0] + f0) * D;
-      if (feats_loc == KHG_HOST) {
-        KHG_TRY(m->w_feats.reserve(sizeof(float) * (size_t)nfr * D));
-        KHG_CUDA_TRY(cudaMemcpyAsync(m->w_feats.p, d_f, sizeof(float) * (size_t)nfr * D, cudaMemcpyHostToDevice, st));
-        d_f = m->w_feats.as<float>();
-      }
-      KHG_TRY(dense_block(m, d_f, nfr, acoustic_scale, KHG_PDF_MAJOR, d_block, ld));
+    if (c > 0) {
+      if (timing) cudaEventRecord(ev[0], st);
+      KHG_TRY(launch_dense(u0, u1));
+      if (timing) cudaEventRecord(ev[1], st);
     }
-    if (timing) cudaEventRecord(ev[1], st);
+    if (timing) cudaEventRecord(ev[3], st);  // (chunk 0: ev[0] / ev[1] were recorded around the early launch)
     g.order = reinterpret_cast<const int32_t *>(gbase + o_ord) + u0;
     viterbi_kernel<<<u1 - u0, NT, smem, st>>>(g, u0, d_block, ld, beam, retry_beam, S_max, n_pdf_max, FC, d_gcost, d_bp,
                                               d_ali, pdf_ids_dev, d_outs);
@@ -655,7 +673,7 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     if (timing) {
       float a = 0.f, b = 0.f;
       cudaEventElapsedTime(&a, ev[0], ev[1]);
-      cudaEventElapsedTime(&b, ev[1], ev[2]);
+      cudaEventElapsedTime(&b, ev[3], ev[2]);
       ms_dense += a;
       ms_search += b;
     }
