@@ -330,6 +330,12 @@ khg_status khg_model_split_by_count(khg_model *m, const float *state_occs, int32
                                     int64_t randn_rows, uint64_t seed, khg_model **new_model,
                                     int32_t *num_gauss_out);
 
+/* AmDiagGmm::MergeByCount (csrc/am-diag-gmm.cc:91-108): the same targets (at least 1 per pdf), then
+ * DiagGmm::Merge (csrc/diag-gmm.cc:557-746) on every pdf ABOVE its target: greedy merging of the pair
+ * of Gaussians whose union loses the least likelihood (target 1: the global mean and variance). */
+khg_status khg_model_merge_by_count(khg_model *m, const float *state_occs, int32_t target_components, float power,
+                                    float min_count, khg_model **new_model, int32_t *num_gauss_out);
+
 /* -------------------------------------------------------- Gaussian selection --
  * DiagGmm::GaussianSelection for a matrix of frames (csrc/diag-gmm.cc:241-317; the one-frame form
  * :202-239 is T = 1) and DiagGmm::GaussianSelectionPreselect (:319-366) on pdf `pdf` of the model

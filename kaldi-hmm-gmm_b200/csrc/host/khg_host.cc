@@ -374,25 +374,37 @@ void AmDiagGmm::SplitByCount(const FloatVector &state_occs, int32_t target_compo
   KHG_HOST_ASSERT((int32_t)state_occs.size() == NumPdfs());
   static uint64_t calls = 0;  // distinct draws per call when no seed is given (the reference uses a global generator)
   khg_model *nm = nullptr;
-  int32_t G = 0;
   Check(khg_model_split_by_count(Device(), state_occs.data(), target_components, perturb_factor, power, min_count,
                                  randn ? randn->data.data() : nullptr, randn ? randn->rows : 0,
-                                 seed ? seed : 0x9E3779B97F4A7C15ull + (++calls), &nm, &G));
+                                 seed ? seed : 0x9E3779B97F4A7C15ull + (++calls), &nm, nullptr));
+  RebuildFromDevice(nm);
+}
+
+void AmDiagGmm::MergeByCount(const FloatVector &state_occs, int32_t target_components, float power, float min_count) {
+  KHG_HOST_ASSERT((int32_t)state_occs.size() == NumPdfs());
+  khg_model *nm = nullptr;
+  Check(khg_model_merge_by_count(Device(), state_occs.data(), target_components, power, min_count, &nm, nullptr));
+  RebuildFromDevice(nm);
+}
+
+// The host pdfs whose Gaussian count changed are rebuilt from the device result (takes ownership of nm).
+void AmDiagGmm::RebuildFromDevice(khg_model *nm) {
   ModelHandle guard;
   guard.h = nm;
-  const int32_t P = NumPdfs(), D = Dim();
+  int32_t D = 0, P = 0, G = 0;
+  Check(khg_model_info(nm, &D, &P, &G));
   std::vector<int32_t> offs(P + 1);
   std::vector<float> w(G), miv((size_t)G * D), iv((size_t)G * D), gc(G);
   Check(khg_model_download(nm, offs.data(), w.data(), miv.data(), iv.data(), gc.data()));
   for (int32_t p = 0; p < P; ++p) {
     const int32_t g0 = offs[p], n = offs[p + 1] - g0;
-    if (n == densities_[p]->NumGauss()) continue;  // not split
+    if (n == densities_[p]->NumGauss()) continue;  // neither split nor merged
     FloatVector pw(w.begin() + g0, w.begin() + g0 + n);
     FloatMatrix piv(n, D), pmiv(n, D);
     std::copy(iv.begin() + (size_t)g0 * D, iv.begin() + (size_t)(g0 + n) * D, piv.data.begin());
     std::copy(miv.begin() + (size_t)g0 * D, miv.begin() + (size_t)(g0 + n) * D, pmiv.data.begin());
     densities_[p]->SetParams(&pw, &piv, &pmiv);
-    densities_[p]->ComputeGconsts();  // csrc/diag-gmm.cc:850
+    densities_[p]->ComputeGconsts();  // csrc/diag-gmm.cc:745, 850
   }
 }
 

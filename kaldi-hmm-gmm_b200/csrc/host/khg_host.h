@@ -176,6 +176,10 @@ class AmDiagGmm {
   // randn: optional (rows x dim) standard-normal draws in the reference's order; seed otherwise.
   void SplitByCount(const FloatVector &state_occs, int32_t target_components, float perturb_factor, float power,
                     float min_count, const FloatMatrix *randn = nullptr, uint64_t seed = 0);  // csrc/am-diag-gmm.cc:72-89
+  void MergeByCount(const FloatVector &state_occs, int32_t target_components, float power, float min_count);  // :91-108
+ private:
+  void RebuildFromDevice(khg_model *nm);
+ public:
 
   // Device pack of the whole model (K4), rebuilt when any pdf changed.  Requires
   // valid gconsts on every pdf (csrc/decodable-am-diag-gmm.cc:49-53).

@@ -248,6 +248,11 @@ PYBIND11_MODULE(_khg_b200, m) {
            },
            py::arg("state_occs"), py::arg("target_components"), py::arg("perturb_factor"), py::arg("power"),
            py::arg("min_count"), py::arg("randn") = py::none(), py::arg("seed") = 0)
+      .def("merge_by_count",  // python/csrc/am-diag-gmm.cc:31-33
+           [](AmDiagGmm &s, const FArr &occs, int32_t target, float power, float min_count) {
+             s.MergeByCount(ToVec(occs), target, power, min_count);
+           },
+           py::arg("state_occs"), py::arg("target_components"), py::arg("power"), py::arg("min_count"))
       // new, batched: (T, num_pdfs) block of per-pdf log-likelihoods computed by the dense kernel
       .def("log_likelihoods_all_pdfs",
            [](const AmDiagGmm &s, const FArr &feats, float scale) {

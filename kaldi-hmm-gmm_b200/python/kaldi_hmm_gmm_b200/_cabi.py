@@ -62,6 +62,7 @@ SYMBOLS = [
     ("khg_align_batch", _i32, [_vp, _vp, _vp, _i32, _vp, _i32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     ("khg_gaussian_selection", _i32, [_vp, _i32, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, C.POINTER(C.c_double)]),
     ("khg_model_split_by_count", _i32, [_vp, _vp, _i32, _f32, _f32, _f32, _vp, _i64, C.c_uint64, C.POINTER(_vp), C.POINTER(_i32)]),
+    ("khg_model_merge_by_count", _i32, [_vp, _vp, _i32, _f32, _f32, C.POINTER(_vp), C.POINTER(_i32)]),
     ("khg_launch_count", _i64, []),
 ]
 KHG_ALIGN_OK, KHG_ALIGN_RETRIED, KHG_ALIGN_FAILED = 0, 1, 2

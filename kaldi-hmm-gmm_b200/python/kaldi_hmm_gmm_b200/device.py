@@ -150,6 +150,15 @@ class DeviceModel:
                                                  0 if rn is None else rn.shape[0], seed, C.byref(nh), C.byref(ng)))
         return DeviceModel._from_handle(nh)
 
+    def merge_by_count(self, state_occs, target_components: int, power: float = 0.2, min_count: float = 20.0) -> "DeviceModel":
+        """AmDiagGmm::MergeByCount (reference csrc/am-diag-gmm.cc:91-108) on the device: a NEW DeviceModel."""
+        occ = np.ascontiguousarray(state_occs, np.float32)
+        assert occ.size == self.num_pdfs
+        nh, ng = C.c_void_p(), C.c_int32()
+        A.check(A.lib().khg_model_merge_by_count(self._h, occ.ctypes.data, int(target_components), power, min_count,
+                                                 C.byref(nh), C.byref(ng)))
+        return DeviceModel._from_handle(nh)
+
     def gaussian_selection(self, pdf: int, feats, num_gselect: int, preselect=None, want_loglikes: bool = False):
         """DiagGmm::GaussianSelection / GaussianSelectionPreselect (reference csrc/diag-gmm.cc:202-366) of
         pdf `pdf` for all rows of feats: (total log-like, indices int32 [T, k], per-frame log-like [T]

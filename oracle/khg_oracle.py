@@ -479,3 +479,80 @@ def np_split_by_count(model: "PackedModel", state_occs, target_components: int, 
         offs.append(offs[-1] + w.size)
     return PackedModel(np.asarray(offs, np.int32), np.concatenate(W), np.concatenate(MIV), np.concatenate(IV),
                        np.concatenate(GC))
+
+
+def _np_merged_logdet(w1, w2, f1, f2, s1, s2):
+    """DiagGmm::MergedComponentsLogdet, reference csrc/diag-gmm.cc:748-767 (float32)."""
+    w_sum = np.float32(w1 + w2)
+    tm = (f1 + f2 * np.float32(w2 / w1)) * np.float32(w1 / w_sum)
+    tv = (s1 + s2 * np.float32(w2 / w1)) * np.float32(w1 / w_sum) - tm * tm
+    return np.float32(-0.5 * np.log(tv, dtype=np.float32).sum(dtype=np.float32))
+
+
+def np_diag_gmm_merge(w, miv, iv, target: int):
+    """DiagGmm::Merge, reference csrc/diag-gmm.cc:557-746, float32.  Returns (weights, means_invvars, inv_vars)."""
+    w, miv, iv = np.array(w, np.float32), np.array(miv, np.float32), np.array(iv, np.float32)
+    n = w.size
+    assert 0 < target <= n
+    if target == n:
+        return w, miv, iv
+    vars_ = (np.float32(1) / iv).astype(np.float32)
+    means = (miv * vars_).astype(np.float32)
+    vars_ = (vars_ + means * means).astype(np.float32)
+    if target == 1:
+        m1 = (w[None, :] @ means).astype(np.float32)[0]
+        m2 = (w[None, :] @ vars_).astype(np.float32)[0]
+        wsum = np.float32(w.sum(dtype=np.float32))
+        if not (abs(wsum - 1.0) <= 1e-6 * (abs(wsum) + 1.0)):
+            m1, m2, wsum = (m1 * wsum).astype(np.float32), (m2 * wsum).astype(np.float32), np.float32(1)
+        niv = (np.float32(1) / (m2 - m1 * m1)).astype(np.float32)
+        return np.array([wsum], np.float32), (m1 * niv)[None, :].astype(np.float32), niv[None, :]
+    disc = np.zeros(n, bool)
+    logdet = (np.float32(0.5) * np.log(iv, dtype=np.float32).sum(1, dtype=np.float32)).astype(np.float32)
+    delta = np.zeros((n, n), np.float32)
+    for i in range(n):
+        for j in range(i):
+            ml = _np_merged_logdet(w[i], w[j], means[i], means[j], vars_[i], vars_[j])
+            delta[i, j] = np.float32(np.float32(np.float32(w[i] + w[j]) * ml) - np.float32(w[i] * logdet[i])) - np.float32(w[j] * logdet[j])
+    for _ in range(n - target):
+        best, bi, bj = -np.finfo(np.float32).max, -1, -1
+        for i in range(n):
+            if disc[i]:
+                continue
+            for j in range(i):
+                if not disc[j] and delta[i, j] > best:
+                    best, bi, bj = delta[i, j], i, j
+        w1, w2 = w[bi], w[bj]
+        w_sum = np.float32(w1 + w2)
+        r21 = np.float32(w2 / w1)
+        means[bi] = ((means[bi] + r21 * means[bj]) * w1 / w_sum).astype(np.float32)
+        vars_[bi] = ((vars_[bi] + r21 * vars_[bj]) * w1 / w_sum).astype(np.float32)
+        w[bi] = w_sum
+        iv[bi] = (np.float32(1) / (vars_[bi] - means[bi] * means[bi])).astype(np.float32)
+        miv[bi] = (means[bi] * iv[bi]).astype(np.float32)
+        logdet[bi] = np.float32(0.5) * np.log(iv[bi], dtype=np.float32).sum(dtype=np.float32)
+        disc[bj] = True
+        for j in range(n):
+            if j == bi or disc[j]:
+                continue
+            ml = _np_merged_logdet(w[bi], w[j], means[bi], means[j], vars_[bi], vars_[j])
+            t = np.float32(np.float32(np.float32(w[bi] + w[j]) * ml) - np.float32(w[bi] * logdet[bi])) - np.float32(w[j] * logdet[j])
+            delta[bi, j] = delta[j, bi] = t
+    keep = ~disc
+    return w[keep], miv[keep], iv[keep]
+
+
+def np_merge_by_count(model: "PackedModel", state_occs, target_components: int, power: float, min_count: float):
+    """AmDiagGmm::MergeByCount, reference csrc/am-diag-gmm.cc:91-108."""
+    targets = np.maximum(np_get_split_targets(state_occs, target_components, power, min_count), 1)
+    W, MIV, IV, GC, offs = [], [], [], [], [0]
+    for p in range(model.num_pdfs):
+        s = slice(model.offsets[p], model.offsets[p + 1])
+        w, miv, iv = model.weights[s], model.means_invvars[s], model.inv_vars[s]
+        if w.size > targets[p]:
+            w, miv, iv = np_diag_gmm_merge(w, miv, iv, int(targets[p]))
+        gc, _ = np_compute_gconsts(w, miv, iv)
+        W.append(w), MIV.append(miv), IV.append(iv), GC.append(gc)
+        offs.append(offs[-1] + w.size)
+    return PackedModel(np.asarray(offs, np.int32), np.concatenate(W), np.concatenate(MIV), np.concatenate(IV),
+                       np.concatenate(GC))

@@ -138,3 +138,64 @@ def test_gpu_am_diag_gmm_split_by_count_method():
     assert am2.num_gauss == 43
     am.split_by_count(state_occs=occs, target_components=60, perturb_factor=0.01, power=0.2, min_count=20.0)  # internal draws
     assert am.num_gauss > 43
+    # mix-down with the reference's method name (scripts/gmm_est.py:81-87)
+    before = am.num_gauss
+    am.merge_by_count(state_occs=occs, target_components=20, power=0.2, min_count=20.0)
+    assert am.num_gauss < before and am.get_pdf(2).valid_gconsts
+    assert np.isfinite(am.log_likelihood(2, x))
+
+
+def _moments(w, miv, iv):
+    """(total weight, mixture mean, mixture second moment) of a diagonal GMM in exponential form."""
+    var = 1.0 / iv.astype(np.float64)
+    mu = miv * var
+    return w.sum(), (w[:, None] * mu).sum(0), (w[:, None] * (var + mu * mu)).sum(0)
+
+
+def test_oracle_merge_conserves_moments():
+    """Merging two Gaussians keeps the mixture's weight, mean and second moment (what
+    DiagGmm::Merge's statistics-domain arithmetic guarantees); target 1 = the global Gaussian."""
+    model, means, vars_ = ko.make_synthetic_model(13, 1, 12)
+    w, miv, iv = model.weights, model.means_invvars, model.inv_vars
+    ref = _moments(w, miv, iv)
+    for tgt in (7, 3, 1):
+        w2, miv2, iv2 = ko.np_diag_gmm_merge(w, miv, iv, tgt)
+        assert w2.size == tgt and (iv2 > 0).all()
+        got = _moments(w2, miv2, iv2)
+        assert abs(got[0] - ref[0]) < 1e-5
+        np.testing.assert_allclose(got[1], ref[1], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(got[2], ref[2], rtol=1e-4, atol=1e-4)
+    # merging the two closest of three well separated pairs: the far component survives untouched
+    w = np.array([0.3, 0.3, 0.4], np.float32)
+    mu = np.array([[0.0, 0.0], [0.1, 0.0], [9.0, 9.0]], np.float32)
+    iv = np.ones((3, 2), np.float32)
+    w2, miv2, iv2 = ko.np_diag_gmm_merge(w, mu * iv, iv, 2)
+    assert w2.tolist() == [np.float32(0.3) + np.float32(0.3), np.float32(0.4)] and miv2[1].tolist() == [9.0, 9.0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,G,target", [(6, 60, 25), (37, 400, 150), (5, 40, 5), (3, 90, 12)])
+def test_gpu_merge_by_count_matches_oracle(P, G, target):
+    from kaldi_hmm_gmm_b200 import DeviceModel
+
+    rng = np.random.default_rng(P + G)
+    model, means, vars_ = ko.make_synthetic_model(13, P, G)
+    occs = (rng.random(P) * 6000 + 100).astype(np.float32)
+    ref = ko.np_merge_by_count(model, occs, target, 0.2, 20.0)
+    dm = DeviceModel(13, model.offsets)
+    dm.upload(model.weights, model.means_invvars, model.inv_vars)
+    new = dm.merge_by_count(occs, target, 0.2, 20.0)
+    got = new.download()
+    np.testing.assert_array_equal(got["offsets"], ref.offsets)                  # allocation: exact
+    assert new.num_gauss < model.num_gauss
+    np.testing.assert_allclose(got["weights"], ref.weights, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(got["inv_vars"], ref.inv_vars, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(got["means_invvars"], ref.means_invvars, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(got["gconsts"], ref.gconsts, rtol=1e-4, atol=1e-3)
+    for p in range(P):  # mixture moments of every pdf survive the merge
+        a, b = slice(model.offsets[p], model.offsets[p + 1]), slice(got["offsets"][p], got["offsets"][p + 1])
+        m0 = _moments(model.weights[a], model.means_invvars[a], model.inv_vars[a])
+        m1 = _moments(got["weights"][b], got["means_invvars"][b], got["inv_vars"][b])
+        assert abs(m0[0] - m1[0]) < 1e-5
+        np.testing.assert_allclose(m1[1], m0[1], rtol=1e-3, atol=1e-3)
+        np.testing.assert_allclose(m1[2], m0[2], rtol=1e-3, atol=1e-3)
