@@ -41,11 +41,13 @@ def gmm_acc_stats_ali(am_gmm, gmm_accs, transition_model, feats, ali: List[int],
     return log_like, transition_accs
 
 
-def gmm_est(am_gmm, gmm_accs, transition_model=None, transition_accs=None, tcfg=None, gmm_opts=None,
+def gmm_est(am_gmm, gmm_accs, transition_model=None, transition_accs=None, tcfg=None, gmm_opts=None, mixup: int = 0,
+            mixdown: int = 0, perturb_factor: float = 0.01, power: float = 0.2, min_count: float = 20.0,
             update_flags: str = "mvwt", verbose: bool = False):
-    """GMM part of reference scripts/gmm_est.py:8-73 (the transition update is delegated to
-    transition_model.mle_update when the object provides it; mix-up/mix-down is model
-    surgery outside this package's scope). Returns (objf_impr, count, avg_like_per_frame)."""
+    """Reference scripts/gmm_est.py:8-96 with its argument names and defaults: transition update
+    (delegated to transition_model.mle_update when the object provides it), MleAmDiagGmmUpdate, then
+    mix-down (`merge_by_count`) and mix-up (`split_by_count`) by the per-pdf occupancies, both on the
+    device.  Returns (objf_impr, count, avg_like_per_frame) (the reference prints them)."""
     flags = _ext.str_to_gmm_flags(update_flags)
     if flags & int(_ext.GmmUpdateFlags.kGmmTransitions) and hasattr(transition_model, "mle_update"):
         transition_model.mle_update(transition_accs, tcfg)
@@ -56,6 +58,13 @@ def gmm_est(am_gmm, gmm_accs, transition_model=None, transition_accs=None, tcfg=
     if verbose:
         print("GMM update: Overall", objf_impr / count, "objective function improvement per frame over", count, "frames")
         print("GMM update: Overall avg like per frame =", tot_like / tot_t, "over", tot_t, "frames.")
+    if mixup != 0 or mixdown != 0:
+        pdf_occs = np.asarray([gmm_accs.get_acc(i).occupancy.sum() for i in range(gmm_accs.num_accs)], np.float32)
+        if mixdown != 0:
+            am_gmm.merge_by_count(state_occs=pdf_occs, target_components=mixdown, power=power, min_count=min_count)
+        if mixup != 0:
+            am_gmm.split_by_count(state_occs=pdf_occs, target_components=mixup, perturb_factor=perturb_factor, power=power,
+                                  min_count=min_count)
     return objf_impr, count, (tot_like / tot_t if tot_t else float("nan"))
 
 

@@ -260,6 +260,18 @@ def test_accum_am_per_frame_api_and_batched_script(oracle):
         np.testing.assert_allclose(g.weights, upd["weights"], rtol=1e-4, atol=1e-7)
         np.testing.assert_allclose(g.inv_vars, upd["inv_vars"], rtol=1e-3, atol=1e-6)
         np.testing.assert_allclose(g.means, upd["means_invvars"] / upd["inv_vars"], rtol=1e-4, atol=1e-4)
+    # the reference's mix-up arguments (scripts/gmm_est.py:14-18, 75-96): allocation by the per-pdf occupancies
+    n0 = am.num_gauss
+    accs3 = khg.AccumAmDiagGmm()
+    accs3.init(model=am, flags=khg.GmmUpdateFlags.kGmmAll)
+    khg.gmm_acc_stats_ali(am_gmm=am, gmm_accs=accs3, transition_model=tid2pdf, feats=feats, ali=ali.tolist())
+    pdf_occs = np.asarray([accs3.get_acc(i).occupancy.sum() for i in range(6)], np.float32)
+    khg.gmm_est(am_gmm=am, gmm_accs=accs3, gmm_opts=opts, mixup=n0 + 7, perturb_factor=0.01, power=0.2, min_count=2.0,
+                update_flags="mvw")
+    t = ko.np_get_split_targets(pdf_occs, n0 + 7, 0.2, 2.0)
+    # every pdf reaches its target; pdfs already above it keep their Gaussians (csrc/am-diag-gmm.cc:80-83)
+    assert n0 < t.sum() <= n0 + 7 and am.num_gauss >= t.sum()
+    assert all(am.num_gauss_in_pdf(p) >= t[p] for p in range(6))
 
 
 @pytest.mark.gpu
