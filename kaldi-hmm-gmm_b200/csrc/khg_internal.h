@@ -112,6 +112,7 @@ struct TcPack {
   void *epi_hdr = nullptr;       // device int2 per (tile, group): {start in seg[], first run | runs << 24}
   uint32_t *runs = nullptr;      // device: length | count << 8
   uint32_t *seg = nullptr;       // device: column | pdf << 8, + 2 sentinels per list
+  bool grouped_segs = false;     // some tile has a group of short pdfs read by one load (epi_run_multi)
   bool two_chunk_segs = false;   // some pdf has 17..32 Gaussians: the epilogue's two-load segment form is in use
   bool dead_pdf = false;         // some pdf has only -inf gconsts: every call must fail like the reference
 };

@@ -41,6 +41,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <utility>
 
 #include "khg_internal.h"
 
@@ -248,11 +249,13 @@ struct SegLse {
   float2 e2[kPairs > 0 ? kPairs : 1];
   float e1;
   float M;
+  // OFF: first of the L registers (several short segments can share one 16-column load)
+  template <int OFF = 0>
   __device__ __forceinline__ void part1(const TReg16 &t) {
     constexpr float kLog2e = 1.4426950408889634f;
-    float m = __uint_as_float(t.r[0]);
+    float m = __uint_as_float(t.r[OFF]);
 #pragma unroll
-    for (int i = 1; i < L; ++i) m = fmaxf(m, __uint_as_float(t.r[i]));
+    for (int i = 1; i < L; ++i) m = fmaxf(m, __uint_as_float(t.r[OFF + i]));
     M = m;
     if (L == 1) return;
     const float ml = m * kLog2e;
@@ -260,8 +263,8 @@ struct SegLse {
     const float2 k2 = make_float2(kLog2e, kLog2e), nm2 = make_float2(-ml, -ml);
 #pragma unroll
     for (int i = 0; i < kPairs; ++i)
-      e2[i] = __ffma2_rn(make_float2(__uint_as_float(t.r[2 * i]), __uint_as_float(t.r[2 * i + 1])), k2, nm2);
-    if (L & 1) e1 = fmaf(__uint_as_float(t.r[L - 1]), kLog2e, -ml);
+      e2[i] = __ffma2_rn(make_float2(__uint_as_float(t.r[OFF + 2 * i]), __uint_as_float(t.r[OFF + 2 * i + 1])), k2, nm2);
+    if (L & 1) e1 = fmaf(__uint_as_float(t.r[OFF + L - 1]), kLog2e, -ml);
   }
   // sum of 2^e[i] (the caller combines two chunks of a long segment)
   __device__ __forceinline__ float part2_sum() {
@@ -360,6 +363,38 @@ __device__ __forceinline__ void epi_run(EpiState &e, int cnt) {
     const float r = lse.part2();
     e.nan_acc = fmaf(r, 0.f, e.nan_acc);
     *reinterpret_cast<float *>(e.out_t + (uint64_t)(dcur >> kSegPdfShift) * e.ld_bytes) = e.scale * r;
+    e.d = dnext;
+  }
+}
+
+// Groups of NS = 16 / L column-adjacent segments (consecutive pdfs of L <= 8 Gaussians each) under
+// ONE 16-column load: one descriptor, one wait and one load per group instead of per segment — what
+// models with few Gaussians per pdf (a freshly initialised monophone system has one) are made of.
+// The descriptor names the group's first column and first pdf.
+template <int L, int... Ks>
+__device__ __forceinline__ void multi_part1(SegLse<L> (&s)[sizeof...(Ks)], const TReg16 &t, std::integer_sequence<int, Ks...>) {
+  (s[Ks].template part1<Ks * L>(t), ...);
+}
+template <int L, bool TWO>
+__device__ __forceinline__ void epi_run_multi(EpiState &e, int cnt) {
+  constexpr int NS = 16 / L;
+#pragma unroll 1
+  for (; cnt > 0; --cnt) {
+    const uint32_t dcur = e.d, dnext = e.dn;
+    e.dn = __ldg(e.sp + 2);
+    ++e.sp;
+    tc_ld16_wait(e.t);
+    SegLse<L> lse[NS];
+    multi_part1<L>(lse, e.t, std::make_integer_sequence<int, NS>());
+    tc_ld16_issue(e.trow + (dnext & 0xffu), e.t);
+    if (TWO) tc_ld16_issue_if(e.trow + (dnext & 0xffu) + 16, e.t2, (dnext & kSegTwoChunks) != 0);
+    char *o = e.out_t + (uint64_t)(dcur >> kSegPdfShift) * e.ld_bytes;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      const float r = lse[k].part2();
+      e.nan_acc = fmaf(r, 0.f, e.nan_acc);
+      *reinterpret_cast<float *>(o + (uint64_t)k * e.ld_bytes) = e.scale * r;
+    }
     e.d = dnext;
   }
 }
@@ -587,9 +622,10 @@ struct TcArgs {
   int debug_mode;          // 0 = normal; 1 = epilogue skips the LSE (pipeline-ceiling experiment, KHG_TC_DEBUG_MODE)
 };
 
-// TWO: the model has pdfs of 17..32 Gaussians (two-load segments); a separate instantiation so that
-// models without them run exactly the single-load epilogue.
-template <bool F16, bool TWO>
+// TWO: the model has pdfs of 17..32 Gaussians (two-load segments); GRP: it has groups of short pdfs
+// read by one load (epi_run_multi).  Separate instantiations, so that models without them run
+// exactly the plain single-load epilogue (its code layout is worth 2-4 % on the C4 shape).
+template <bool F16, bool TWO, bool GRP>
 __global__ void __launch_bounds__(kTcThreads, 1)
 loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
   constexpr int kChunkK = Elem<F16>::kChunkK, kUmmaK = Elem<F16>::kUmmaK;
@@ -796,6 +832,8 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
           tc_ld16_issue(e.trow + (e.d & 0xffu), e.t);
 #define KHG_CASE(L) case L: epi_run<L, KHG_TWO>(e, cnt); break;
 #define KHG_CASE2(L) case 16 + L: epi_run2<L>(e, cnt); break;
+#define KHG_CASEM(L) case L: epi_run_multi<L, KHG_TWO>(e, cnt); break;
+#define KHG_CASESM KHG_CASEM(1) KHG_CASEM(2) KHG_CASEM(3) KHG_CASEM(4) KHG_CASEM(5) KHG_CASEM(6) KHG_CASEM(7) KHG_CASEM(8)
 #define KHG_CASES1 KHG_CASE(1) KHG_CASE(2) KHG_CASE(3) KHG_CASE(4) KHG_CASE(5) KHG_CASE(6) KHG_CASE(7) KHG_CASE(8) \
                    KHG_CASE(9) KHG_CASE(10) KHG_CASE(11) KHG_CASE(12) KHG_CASE(13) KHG_CASE(14) KHG_CASE(15) KHG_CASE(16)
 #define KHG_CASES2 KHG_CASE2(1) KHG_CASE2(2) KHG_CASE2(3) KHG_CASE2(4) KHG_CASE2(5) KHG_CASE2(6) KHG_CASE2(7) KHG_CASE2(8) \
@@ -803,24 +841,34 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
           if constexpr (TWO) {
             tc_ld16_issue_if(e.trow + (e.d & 0xffu) + 16, e.t2, (e.d & kSegTwoChunks) != 0);
             for (; nr > 0; --nr) {
-              const int len = run & 0xff, cnt = run >> 8;
+              const int len = run & 0xff, cnt = (run >> 8) & 0x7fffff;
+              const bool grouped = GRP && (run >> 31) != 0;
               if (nr > 1) run = __ldg(++rp);
 #define KHG_TWO true
-              switch (len) {
-                KHG_CASES1 KHG_CASES2
-                default: epi_run_long(e, cnt, len); break;
+              if (GRP && grouped) {
+                switch (len) { KHG_CASESM }
+              } else {
+                switch (len) {
+                  KHG_CASES1 KHG_CASES2
+                  default: epi_run_long(e, cnt, len); break;
+                }
               }
 #undef KHG_TWO
             }
             tc_ld16_wait2(e.t, e.t2);  // the (unused) sentinel load issued after the last segment
           } else {
             for (; nr > 0; --nr) {
-              const int len = run & 0xff, cnt = run >> 8;
+              const int len = run & 0xff, cnt = (run >> 8) & 0x7fffff;
+              const bool grouped = GRP && (run >> 31) != 0;
               if (nr > 1) run = __ldg(++rp);
 #define KHG_TWO false
-              switch (len) {
-                KHG_CASES1
-                default: epi_run_long(e, cnt, len); break;
+              if (GRP && grouped) {
+                switch (len) { KHG_CASESM }
+              } else {
+                switch (len) {
+                  KHG_CASES1
+                  default: epi_run_long(e, cnt, len); break;
+                }
               }
 #undef KHG_TWO
             }
@@ -830,6 +878,8 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
 #undef KHG_CASE2
 #undef KHG_CASES1
 #undef KHG_CASES2
+#undef KHG_CASEM
+#undef KHG_CASESM
         }
         tc_fence_before();
         __syncwarp();
@@ -1003,23 +1053,36 @@ khg_status tc_pack_build(khg_model *m) {
     std::vector<uint32_t> runs, seg;
     seg.reserve(P + 2 * hdr.size());
     t.two_chunk_segs = false;
+    t.grouped_segs = false;
     for (int j = 0; j < t.n_tiles; ++j) {
       const int pa = t.h_tile_p0[j], pb = t.h_tile_p0[j + 1], g0 = t.h_tile_g0[j];
-      std::vector<std::pair<int, int>> by_len;  // (len, pdf)
-      for (int q = pa; q < pb; ++q) by_len.emplace_back(m->h_offsets[q + 1] - m->h_offsets[q], q);
+      // work items of the tile: groups of 16 / len column-adjacent pdfs of the same length <= 8 (one
+      // TMEM load per group), single pdfs otherwise; key = grouped << 8 | len
+      std::vector<std::pair<int, int>> by_len;  // (key, first pdf)
+      for (int q = pa; q < pb;) {
+        const int len = m->h_offsets[q + 1] - m->h_offsets[q];
+        const int ns = len <= 8 ? 16 / len : 1;
+        bool grp = ns > 1 && q + ns <= pb;
+        for (int k = 1; grp && k < ns; ++k) grp = m->h_offsets[q + k + 1] - m->h_offsets[q + k] == len;
+        if (grp) t.grouped_segs = true;
+        by_len.emplace_back((grp ? 256 : 0) | len, q);
+        q += grp ? ns : 1;
+      }
       std::stable_sort(by_len.begin(), by_len.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) { return x.first < y.first; });
-      // segment i of the length-sorted order goes to epilogue group i % kEpiGroups (balanced)
+      // item i of the sorted order goes to epilogue group i % kEpiGroups (balanced)
       for (int eg = 0; eg < kEpiGroups; ++eg) {
         int2 h;
         h.x = (int)seg.size();
         const size_t r0 = runs.size();
         for (size_t i = eg; i < by_len.size(); i += kEpiGroups) {
-          const int len = by_len[i].first, q = by_len[i].second;
-          // a run: equal lengths <= 255 (longer pdfs: one run each, length in the upper field)
-          if (runs.size() > r0 && (int)(runs.back() & 0xff) == std::min(len, 255) && len < 255 && (runs.back() >> 8) < 0xffffu)
+          const int key = by_len[i].first, len = key & 255, q = by_len[i].second;
+          const bool grp = key >= 256;
+          // a run: equal keys (pdfs of > 254 Gaussians: one run each); length | count << 8 | grouped << 31
+          const uint32_t tag = (uint32_t)std::min(len, 255) | (grp ? 1u << 31 : 0u);
+          if (runs.size() > r0 && (runs.back() & 0x800000ffu) == tag && len < 255 && ((runs.back() >> 8) & 0x7fffffu) < 0x7fffffu)
             runs.back() += 1u << 8;
           else
-            runs.push_back((uint32_t)std::min(len, 255) | 1u << 8);
+            runs.push_back(tag | 1u << 8);
           if (len > 16 && len <= 32) t.two_chunk_segs = true;
           seg.push_back((uint32_t)(m->h_offsets[q] - g0) | (len > 16 && len <= 32 ? kSegTwoChunks : 0u) | (uint32_t)q << kSegPdfShift);
         }
@@ -1125,17 +1188,16 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(loglikes_tc_kernel<F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(loglikes_tc_kernel<F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    for (auto fn : {loglikes_tc_kernel<F16, false, false>, loglikes_tc_kernel<F16, true, false>, loglikes_tc_kernel<F16, false, true>,
+                    loglikes_tc_kernel<F16, true, true>})
+      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   KHG_CUDA_TRY(attr_err);
   unsigned grid = (unsigned)std::min<int64_t>(a.n_items, m->sm_count);
   if (const char *mc = getenv("KHG_TC_MAX_CTAS")) grid = std::min<unsigned>(grid, (unsigned)std::max(1, atoi(mc)));  // experiments
-  if (t.two_chunk_segs)
-    loglikes_tc_kernel<F16, true><<<grid, kTcThreads, smem, m->stream>>>(F16 ? t.hmap_hi : t.map_hi, a);
-  else
-    loglikes_tc_kernel<F16, false><<<grid, kTcThreads, smem, m->stream>>>(F16 ? t.hmap_hi : t.map_hi, a);
+  auto kern = t.two_chunk_segs ? (t.grouped_segs ? loglikes_tc_kernel<F16, true, true> : loglikes_tc_kernel<F16, true, false>)
+                               : (t.grouped_segs ? loglikes_tc_kernel<F16, false, true> : loglikes_tc_kernel<F16, false, false>);
+  kern<<<grid, kTcThreads, smem, m->stream>>>(F16 ? t.hmap_hi : t.map_hi, a);
   ++g_launch_count;
   KHG_CUDA_TRY(cudaGetLastError());
   return KHG_OK;

@@ -269,6 +269,33 @@ def test_tc_length_classes_and_kernel_query(oracle):
         dm.set_kernel(TC)
 
 
+@pytest.mark.parametrize("sizes", [
+    [1] * 130,                                                       # freshly initialised monophone model: 1 Gaussian per pdf
+    [1] * 40 + [2] * 17 + [3] * 11 + [5] * 7 + [8] * 5 + [4] * 9 + [7] * 3 + [6] * 4 + [9] * 3 + [20] * 2 + [1] * 3,
+    [5] * 100 + [10] * 30 + [5] * 2 + [240] + [3] * 6,               # groups, singles, a full-tile pdf, group leftovers
+])
+def test_tc_grouped_short_segments(oracle, sizes):
+    """Runs of column-adjacent pdfs with the same small Gaussian count are read 16 / len at a time
+    by one TMEM load (epi_run_multi); leftovers and other lengths take the single-segment forms."""
+    rng = np.random.default_rng(len(sizes))
+    D = 39
+    sizes = np.asarray(sizes, np.int32)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    G = int(offsets[-1])
+    means = rng.standard_normal((G, D)).astype(np.float32) * 2
+    vars_ = rng.uniform(0.5, 2, (G, D)).astype(np.float32)
+    w = np.concatenate([rng.dirichlet(np.ones(s)) for s in sizes]).astype(np.float32)
+    iv = (1 / vars_).astype(np.float32)
+    miv = (means * iv).astype(np.float32)
+    gc = np.concatenate([oracle.compute_gconsts(w[a:b], miv[a:b], iv[a:b])[0] for a, b in zip(offsets[:-1], offsets[1:])])
+    model = ko.PackedModel(offsets, w, miv, iv, gc)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, 333)
+    ref, bad = oracle.loglikes_all_pdfs(model, feats)
+    assert bad == 0
+    for kernel in (AUTO, TC, TC_F16):
+        _check(_one(model, kernel).loglikes_all_pdfs(feats), ref)
+
+
 def test_tc_yesno_shape_dim80_fp16_only(oracle):
     """BASELINE configs[0]: the yesno recipe feeds 80-dim fbank (reference
     egs/yesno/local/compute_fbank_yesno.py:32) into 11 pdfs growing to ~1000 Gaussians.

@@ -20,7 +20,7 @@ for kv in sys.argv[3:]:
     k, v = kv.split("=", 1)
     os.environ[k] = v
 T = 148 * 128 * 16
-if os.environ.get("K1_CONFIG") == "c5":
+if os.environ.get("K1_CONFIG") in ("c5", "c3", "c2"):
     T = 148 * 128 * 8
 D, P, G, _ = bench.CONFIGS[os.environ.get("K1_CONFIG", "c4")]
 hm = bench.host_model(D, P, G)
