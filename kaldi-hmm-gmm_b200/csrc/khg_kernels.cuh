@@ -344,34 +344,42 @@ __host__ __device__ inline int stats_frames_for(int ng, int post_cap) {
 }
 
 // item_start[p] = exclusive scan of ceil(n_p / frames_for(g_p)); single block.
-__global__ void item_scan_kernel(int P, const int32_t *__restrict__ offsets,
-                                 const int32_t *__restrict__ starts,
-                                 int32_t *__restrict__ item_start, int post_cap) {
-  __shared__ int32_t carry;
-  __shared__ int32_t buf[1024];
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < P; base += 1024) {
-    int p = base + threadIdx.x;
-    int32_t v = 0;
-    if (p < P) {
-      int f = stats_frames_for(offsets[p + 1] - offsets[p], post_cap);
-      v = (starts[p + 1] - starts[p] + f - 1) / f;
-    }
-    buf[threadIdx.x] = v;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-      int32_t add = threadIdx.x >= off ? buf[threadIdx.x - off] : 0;
-      __syncthreads();
-      buf[threadIdx.x] += add;
-      __syncthreads();
-    }
-    if (p < P) item_start[p] = carry + buf[threadIdx.x] - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += buf[1023];
-    __syncthreads();
+__global__ void __launch_bounds__(1024) item_scan_kernel(int P, const int32_t *__restrict__ offsets,
+                                                         const int32_t *__restrict__ starts,
+                                                         int32_t *__restrict__ item_start, int post_cap) {
+  // every thread owns a contiguous slice of pdfs; slice sums are scanned with warp shuffles
+  __shared__ int32_t warp_tot[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (P + 1023) / 1024;
+  const int p0 = min(P, tid * per), p1 = min(P, p0 + per);
+  int32_t mine = 0;
+  for (int p = p0; p < p1; ++p) {
+    const int f = stats_frames_for(offsets[p + 1] - offsets[p], post_cap);
+    mine += (starts[p + 1] - starts[p] + f - 1) / f;
   }
-  if (threadIdx.x == 0) item_start[P] = carry;
+  int32_t incl = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int32_t w = warp_tot[lane], wi = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    warp_tot[lane] = wi - w;  // exclusive
+  }
+  __syncthreads();
+  int32_t run = warp_tot[warp] + incl - mine;
+  for (int p = p0; p < p1; ++p) {
+    item_start[p] = run;
+    const int f = stats_frames_for(offsets[p + 1] - offsets[p], post_cap);
+    run += (starts[p + 1] - starts[p] + f - 1) / f;
+  }
+  if (tid == 1023) item_start[P] = run;  // (threads past the last pdf carry the total)
 }
 
 // item_desc[item] = {pdf, first position in `order`, frames, 0}: one warp per pdf writes the
