@@ -108,6 +108,27 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
+// Cluster (CTA pair) forms: the pair streams ONE copy of the operand B' out of L2 — each CTA loads half
+// of every stage and multicasts it into both CTAs' shared memory (same offsets, each CTA's own "full"
+// barrier gets the bytes), and a stage is free again once BOTH CTAs' MMAs have read it.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 // One lane of a converged warp.  The MMA-issuing and TMA-issuing warps run their loops with all 32
 // lanes (warp-uniform control flow: counters and descriptors then live in uniform registers and
 // UTCHMMA / UTMALDG take them directly); a loop run by `if (lane == 0)` makes the compiler wrap
@@ -620,6 +641,8 @@ struct TcArgs {
   float *scratch;          // one device word: store target of rows beyond T
   int *err;
   int debug_mode;          // 0 = normal; 1 = epilogue skips the LSE (pipeline-ceiling experiment, KHG_TC_DEBUG_MODE)
+  int cluster;             // 1 = plain launch; 2 = CTA pairs sharing the streamed operand by TMA multicast
+                           // (n_splits == 1: CTA rank r of pair k works on frame tile 2k + r)
 };
 
 // TWO: the model has pdfs of 17..32 Gaussians (two-load segments); GRP: it has groups of short pdfs
@@ -627,7 +650,7 @@ struct TcArgs {
 // exactly the plain single-load epilogue (its code layout is worth 2-4 % on the C4 shape).
 template <bool F16, bool TWO, bool GRP>
 __global__ void __launch_bounds__(kTcThreads, 1)
-loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
+loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_b_half, TcArgs a) {
   constexpr int kChunkK = Elem<F16>::kChunkK, kUmmaK = Elem<F16>::kUmmaK;
   constexpr uint32_t kIdesc = make_idesc<F16>();
   if (a.gate != nullptr) {  // precision-path gate decided on the device (no host round trip)
@@ -654,12 +677,19 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
+  // work items of this CTA: item(k) for k = k_first, k_first + k_stride, ... < k_end
+  const bool clu = a.cluster == 2;
+  const uint32_t crank = clu ? cluster_ctarank() : 0u;
+  const int64_t k_first = clu ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+  const int64_t k_stride = clu ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+  const int64_t k_end = clu ? (a.n_items + 1) / 2 : a.n_items;  // (a phantom tile beyond T pads an odd count)
+  auto item_of = [&](int64_t k) -> int64_t { return clu ? 2 * k + crank : k; };
 
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         mbar_init(b_full(s), 1);
-        mbar_init(b_empty(s), 1);
+        mbar_init(b_empty(s), clu ? 2 : 1);  // pair: the MMA warps of both CTAs release a stage
       }
       mbar_init(a_full, 1);
       mbar_init(a_free, 1);
@@ -686,6 +716,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (clu) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
 
   if (warp == kProducerWarp) {
@@ -693,7 +724,8 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
     {
       const bool leader = elect_one();
       uint32_t st = 0, ph = 1;  // producer waits on "empty" with the inverted phase
-      for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      for (int64_t k = k_first; k < k_end; k += k_stride) {
+        const int64_t item = item_of(k);
         const int split = (int)(item % a.n_splits);
         const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
         for (int j = j0; j < j1; ++j) {
@@ -701,8 +733,15 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
           for (int c = 0; c < a.tab.n; ++c) {
             mbar_wait(b_empty(st), ph);
             if (leader) {
-              if (a.debug_mode == 3) {  // experiment: MMA rate without operand traffic
+              // experiments (timing only, results are garbage): 3 = MMA rate without operand traffic,
+              // 4 / 5 = only the first / all but the second chunk of every tile is loaded (1/3, 2/3 of the traffic)
+              if (a.debug_mode == 3 || (a.debug_mode == 4 && c != 0) || (a.debug_mode == 5 && c == 1)) {
                 mbar_arrive(b_full(st));
+              } else if (clu) {
+                // this CTA's half of the stage's rows, into both CTAs; the other half arrives from the peer
+                mbar_expect_tx(b_full(st), kBStageBytes);
+                tma_load_2d_mc(sB + st * kBStageBytes + crank * (kBStageBytes / 2), &map_b_half, b_full(st), c * kChunkK,
+                               g0 + (int)crank * (kTileN / 2), (uint16_t)3);
               } else {
                 mbar_expect_tx(b_full(st), kBStageBytes);
                 tma_load_2d(sB + st * kBStageBytes, &map_b, b_full(st), c * kChunkK, g0);
@@ -724,7 +763,8 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
       uint32_t st = 0, ph = 0, acc_it = 0, a_it = 0;
       const uint32_t a_hi0 = umma_desc_lo(sA_hi), a_lo0 = umma_desc_lo(sA_lo), b0 = umma_desc_lo(sB);
       constexpr uint32_t kAChunkDesc = kAChunkBytes >> 4, kBStageDesc = kBStageBytes >> 4;
-      for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x, ++a_it) {
+      for (int64_t k = k_first; k < k_end; k += k_stride, ++a_it) {
+        const int64_t item = item_of(k);
         const int split = (int)(item % a.n_splits);
         const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
         mbar_wait(a_full, a_it & 1);
@@ -760,7 +800,9 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
                 if (leader) tc_mma<F16>(tmem_d, a_hi0 + ao, db + 2 * (nh + s), kIdesc, 1);
               }
             }
-            if (leader) tc_commit(b_empty(st));
+            if (leader) {
+              if (clu) tc_commit_mc(b_empty(st), (uint16_t)3); else tc_commit(b_empty(st));
+            }
             if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
           }
           if (leader) tc_commit(acc_full(buf));
@@ -773,9 +815,10 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
     const int b = threadIdx.x - 32 * kBuilderWarp0;
     const int D = a.D;
     uint32_t a_it = 0;
-    for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x, ++a_it) {
+    for (int64_t k = k_first; k < k_end; k += k_stride, ++a_it) {
+      const int64_t item = item_of(k);
       const int64_t t0 = (item / a.n_splits) * kTileM;
-      const int64_t valid = min((int64_t)kTileM, a.T - t0) * D;
+      const int64_t valid = max((int64_t)0, min((int64_t)kTileM, a.T - t0)) * D;  // (0 for the pair's phantom tile)
       const float *src = a.feats + t0 * D;
       if (b == 0) mbar_wait(a_free, (a_it & 1) ^ 1);
       asm volatile("bar.sync 1, 64;" ::: "memory");
@@ -802,7 +845,8 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
     const int row = quad * 32 + lane;
     uint32_t acc_it = 0;
     bool bad = false;
-    for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    for (int64_t k = k_first; k < k_end; k += k_stride) {
+      const int64_t item = item_of(k);
       const int split = (int)(item % a.n_splits);
       const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
       const int64_t t = (item / a.n_splits) * kTileM + row;
@@ -893,6 +937,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, TcArgs a) {
 
   tc_fence_before();
   __syncthreads();
+  if (clu) cluster_sync_all();  // no CTA leaves while its peer can still multicast into it
   if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -941,7 +986,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D tensor map over a rows x KP operand matrix: box = one 128-byte K chunk x 240 rows.
-static khg_status make_map(CUtensorMap *map, void *ptr, int KP, int rows, bool f16) {
+static khg_status make_map(CUtensorMap *map, void *ptr, int KP, int rows, bool f16, int box_rows = kTileN) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -950,7 +995,7 @@ static khg_status make_map(CUtensorMap *map, void *ptr, int KP, int rows, bool f
   const int eb = f16 ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)KP, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)KP * eb};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / eb), (cuuint32_t)kTileN};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / eb), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1014,6 +1059,7 @@ static khg_status tc_pack_build_f16(khg_model *m) {
   cudaFree(d_flag);
   if (flag) return KHG_OK;  // model does not fit the fp16 split: stay on tf32 (f16_ready = false)
   KHG_TRY(make_map(&t.hmap_hi, t.hhi, t.KPB16, t.rows, true));
+  KHG_TRY(make_map(&t.hmap_lo, t.hhi, t.KPB16, t.rows, true, kTileN / 2));  // half-stage box of the CTA-pair form
   t.f16_ready = true;
   return KHG_OK;
 }
@@ -1125,6 +1171,7 @@ khg_status tc_pack_build(khg_model *m) {
     ++g_launch_count;
     KHG_CUDA_TRY(cudaGetLastError());
     KHG_TRY(make_map(&t.map_hi, t.bhi, t.KPB, t.rows, false));
+    KHG_TRY(make_map(&t.map_lo, t.bhi, t.KPB, t.rows, false, kTileN / 2));  // half-stage box of the CTA-pair form
     t.tf32_ready = true;
   }
   KHG_CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -1151,6 +1198,7 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   a.gate_run_if_above = gate_run_if_above;
   const int a_bytes = 2 * a.n_chunks * kAChunkBytes;
   a.stages = std::min(F16 ? 6 : 4, (int)((225 * 1024 - a_bytes) / kBStageBytes));
+  if (const char *e = getenv("KHG_TC_STAGES")) a.stages = std::max(2, std::min(a.stages, atoi(e)));  // experiments: ring depth
   if (a.stages < 2) {
     set_error("feature dimension too large for the tcgen05 kernel");
     return KHG_ERR_UNSUPPORTED;
@@ -1197,7 +1245,32 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   if (const char *mc = getenv("KHG_TC_MAX_CTAS")) grid = std::min<unsigned>(grid, (unsigned)std::max(1, atoi(mc)));  // experiments
   auto kern = t.two_chunk_segs ? (t.grouped_segs ? loglikes_tc_kernel<F16, true, true> : loglikes_tc_kernel<F16, true, false>)
                                : (t.grouped_segs ? loglikes_tc_kernel<F16, false, true> : loglikes_tc_kernel<F16, false, false>);
-  kern<<<grid, kTcThreads, smem, m->stream>>>(F16 ? t.hmap_hi : t.map_hi, a);
+  // CTA pairs (clusters of 2) share the streamed operand through TMA multicast when every CTA has
+  // whole frame tiles to itself and there are enough of them (KHG_TC_CLUSTER=0 forces the plain form)
+  const char *cl = getenv("KHG_TC_CLUSTER");
+  a.cluster = (a.n_splits == 1 && n_m >= 2LL * m->sm_count && grid >= 2 && !(cl && atoi(cl) == 0)) ? 2 : 1;
+  if (a.cluster == 2) {
+    grid &= ~1u;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = m->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, F16 ? t.hmap_hi : t.map_hi, F16 ? t.hmap_lo : t.map_lo, a) != cudaSuccess) {
+      (void)cudaGetLastError();  // pairs cannot be scheduled here (e.g. a partitioned GPU): the plain form
+      a.cluster = 1;
+      kern<<<grid, kTcThreads, smem, m->stream>>>(F16 ? t.hmap_hi : t.map_hi, F16 ? t.hmap_lo : t.map_lo, a);
+    }
+  } else {
+    kern<<<grid, kTcThreads, smem, m->stream>>>(F16 ? t.hmap_hi : t.map_hi, F16 ? t.hmap_lo : t.map_lo, a);
+  }
   ++g_launch_count;
   KHG_CUDA_TRY(cudaGetLastError());
   return KHG_OK;

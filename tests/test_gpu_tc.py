@@ -323,3 +323,28 @@ def test_tc_yesno_shape_dim80_fp16_only(oracle):
     assert np.isfinite(got).all()
     assert (np.abs(got - ref_big) / np.maximum(np.abs(ref_big), 1.0)).max() < 1e-4
     np.testing.assert_array_equal(got[:256], _one(model, SIMT).loglikes_all_pdfs(big)[:256])
+
+
+@pytest.mark.parametrize("T", [128 * 300, 128 * 301 + 77])
+def test_tc_cta_pair_multicast_path(oracle, T, monkeypatch):
+    """Enough frame tiles (>= 2 per SM) switch the tensor-core kernel to CTA pairs that share the
+    streamed operand by TMA multicast (even and odd tile counts: the odd one has a phantom tile).
+    Same results as the plain launch (KHG_TC_CLUSTER=0) bit for bit, and as the oracle within tolerance."""
+    import torch
+
+    model, means, vars_ = ko.make_synthetic_model(40, 300, 2900, oracle=oracle)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, T)
+    dfe = torch.from_numpy(feats).cuda()
+    for kernel in (TC_F16, TC):
+        dm = _one(model, kernel)
+        pair = dm.loglikes_all_pdfs(dfe, layout=1)
+        dm.sync()
+        monkeypatch.setenv("KHG_TC_CLUSTER", "0")
+        plain = dm.loglikes_all_pdfs(dfe, layout=1)
+        dm.sync()
+        monkeypatch.delenv("KHG_TC_CLUSTER")
+        assert torch.equal(pair, plain)
+        n = 3000
+        for sl in (slice(0, n), slice(T - n, T)):
+            ref, _ = oracle.loglikes_all_pdfs(model, feats[sl])
+            _check(pair[:, sl].T.cpu().numpy(), ref)
