@@ -102,6 +102,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+// Waits of the MMA issuer and the TMA producer.  -DKHG_SPIN_WAIT=1 makes them pure spins
+// (mbarrier.test_wait, never suspends) — measured: no difference (profiles/r1u_*), so the
+// suspending wait stays.
+#ifndef KHG_SPIN_WAIT
+#define KHG_SPIN_WAIT 0
+#endif
+__device__ __forceinline__ void mbar_wait_crit(uint32_t bar, uint32_t parity) {
+#if KHG_SPIN_WAIT
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -119,6 +141,27 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *
 }
 __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+// --- cta_group::2 forms (mode 3): ONE MMA of M = 256 per instruction spans the CTA pair — each CTA keeps
+// its own 128 frame rows of A and only HALF of the streamed operand's rows in shared memory (the
+// tensor cores of both SMs read both halves), so the bytes TMA writes into each SM halve.
+__device__ __forceinline__ uint32_t mapa_cta(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -165,6 +208,28 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint32_t adesc_lo, uint3
         "mov.b64 db, {%2, %5};\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
+        : "memory");
+  }
+}
+template <bool F16>
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t idesc, uint32_t accum) {
+  if (F16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
         : "memory");
   }
@@ -472,10 +537,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return (saddr >> 4) & 0x3FFF; }
 static_assert((((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61)) >> 32 == kDescHi, "descriptor high word");
 // Instruction descriptor: D=f32, A=B=tf32 (format 2) or f16 (format 0), both K-major, M=128, N=240.
-template <bool F16>
+template <bool F16, int M = kTileM>
 __host__ __device__ constexpr uint32_t make_idesc() {
   return (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((uint32_t)(kTileN >> 3) << 17) |
-         ((uint32_t)(kTileM >> 4) << 24);
+         ((uint32_t)(M >> 4) << 24);
 }
 
 // Writes the hi/lo split of v at (row, col) of the A operand (UMMA K-major, 128B swizzle):
@@ -648,7 +713,7 @@ struct TcArgs {
 // TWO: the model has pdfs of 17..32 Gaussians (two-load segments); GRP: it has groups of short pdfs
 // read by one load (epi_run_multi).  Separate instantiations, so that models without them run
 // exactly the plain single-load epilogue (its code layout is worth 2-4 % on the C4 shape).
-template <bool F16, bool TWO, bool GRP>
+template <bool F16, bool TWO, bool GRP, bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_b_half, TcArgs a) {
   constexpr int kChunkK = Elem<F16>::kChunkK, kUmmaK = Elem<F16>::kUmmaK;
@@ -678,8 +743,13 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   // work items of this CTA: item(k) for k = k_first, k_first + k_stride, ... < k_end
-  const bool clu = a.cluster == 2;
+  const bool clu = a.cluster >= 2;        // launched as CTA pairs
+  const bool mcast = a.cluster == 2;      // each CTA runs its own MMAs; the operand stages are multicast
+  // one cta_group::2 MMA stream issued by the pair's rank-0 CTA; its own instantiation (PAIR): a kernel
+  // that contains cta_group::2 instructions can only be launched as clusters
+  const bool pairmma = PAIR && a.cluster == 3;
   const uint32_t crank = clu ? cluster_ctarank() : 0u;
+  constexpr uint32_t kIdescPair = make_idesc<F16, 2 * kTileM>();
   const int64_t k_first = clu ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
   const int64_t k_stride = clu ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
   const int64_t k_end = clu ? (a.n_items + 1) / 2 : a.n_items;  // (a phantom tile beyond T pads an odd count)
@@ -689,19 +759,25 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         mbar_init(b_full(s), 1);
-        mbar_init(b_empty(s), clu ? 2 : 1);  // pair: the MMA warps of both CTAs release a stage
+        mbar_init(b_empty(s), mcast ? 2 : 1);  // multicast pair: the MMA warps of both CTAs release a stage
       }
-      mbar_init(a_full, 1);
+      // pair MMA: the rank-0 CTA's barriers also count the peer's A builder and epilogue warps
+      mbar_init(a_full, pairmma ? 2 : 1);
       mbar_init(a_free, 1);
       for (int b = 0; b < 2; ++b) {
         mbar_init(acc_full(b), 1);
-        mbar_init(acc_empty(b), 4 * kEpiGroups);
+        mbar_init(acc_empty(b), (pairmma ? 2 : 1) * 4 * kEpiGroups);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   } else if (warp == kBuilderWarp0 || warp == kBuilderWarp0 + 1) {
     // one-time A init: zero everything, then the constant-1 column (k = 2D) of A_hi
     const int b = threadIdx.x - 32 * kBuilderWarp0;
@@ -731,13 +807,19 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
         for (int j = j0; j < j1; ++j) {
           const int g0 = __shfl_sync(0xffffffffu, __ldg(a.tile_g0 + j), 0);
           for (int c = 0; c < a.tab.n; ++c) {
-            mbar_wait(b_empty(st), ph);
+            mbar_wait_crit(b_empty(st), ph);
             if (leader) {
               // experiments (timing only, results are garbage): 3 = MMA rate without operand traffic,
               // 4 / 5 = only the first / all but the second chunk of every tile is loaded (1/3, 2/3 of the traffic)
               if (a.debug_mode == 3 || (a.debug_mode == 4 && c != 0) || (a.debug_mode == 5 && c == 1)) {
                 mbar_arrive(b_full(st));
-              } else if (clu) {
+              } else if (PAIR) {
+                // this CTA keeps only ITS half of the stage's rows; the bytes of both halves are counted
+                // by the rank-0 CTA's barrier, where the MMAs are issued
+                if (crank == 0) mbar_expect_tx(b_full(st), kBStageBytes);
+                tma_load_2d_pair(sB + st * kBStageBytes, &map_b_half, mapa_cta(b_full(st), 0), c * kChunkK,
+                                 g0 + (int)crank * (kTileN / 2));
+              } else if (mcast) {
                 // this CTA's half of the stage's rows, into both CTAs; the other half arrives from the peer
                 mbar_expect_tx(b_full(st), kBStageBytes);
                 tma_load_2d_mc(sB + st * kBStageBytes + crank * (kBStageBytes / 2), &map_b_half, b_full(st), c * kChunkK,
@@ -758,7 +840,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
     // All 32 lanes run the loop (uniform control flow, see elect_one); one elected lane issues.
     // The instruction stream is kept as short as possible (no divisions, 32-bit descriptor
     // arithmetic): this warp shares an SM sub-partition with four busy epilogue warps.
-    {
+    if (!pairmma || crank == 0) {
       const bool leader = elect_one();
       uint32_t st = 0, ph = 0, acc_it = 0, a_it = 0;
       const uint32_t a_hi0 = umma_desc_lo(sA_hi), a_lo0 = umma_desc_lo(sA_lo), b0 = umma_desc_lo(sB);
@@ -767,18 +849,18 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
         const int64_t item = item_of(k);
         const int split = (int)(item % a.n_splits);
         const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
-        mbar_wait(a_full, a_it & 1);
+        mbar_wait_crit(a_full, a_it & 1);
         tc_fence_after();
         for (int j = j0; j < j1; ++j, ++acc_it) {
           const uint32_t buf = acc_it & 1;
-          mbar_wait(acc_empty(buf), ((acc_it >> 1) & 1) ^ 1);
+          mbar_wait_crit(acc_empty(buf), ((acc_it >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * 256;
           uint32_t accum = 0;
           for (int c = 0; c < a.tab.n; ++c) {
             const uint32_t e = a.tab.e[c];
             const int h0 = e & 0xff, nh = (e >> 8) & 0xf, l0 = (e >> 12) & 0xff, nl = (e >> 20) & 0xf;
-            mbar_wait(b_full(st), ph);
+            mbar_wait_crit(b_full(st), ph);
             tc_fence_after();
             const uint32_t db = b0 + st * kBStageDesc;
             constexpr int kSpc = kChunkK / kUmmaK;  // K steps per chunk (4)
@@ -788,26 +870,41 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
               for (int s = 0; s < nh; ++s) {
                 const int q = h0 + s;
                 const uint32_t ao = (uint32_t)(q / kSpc) * kAChunkDesc + (uint32_t)(q % kSpc) * 2;
-                if (leader) tc_mma<F16>(tmem_d, a_hi0 + ao, db + 2 * s, kIdesc, accum);
-                accum = 1;
-                if (q * kUmmaK < a.Kc && leader) tc_mma<F16>(tmem_d, a_lo0 + ao, db + 2 * s, kIdesc, 1);
+                if constexpr (PAIR) {
+                  if (leader) tc_mma_pair<F16>(tmem_d, a_hi0 + ao, db + 2 * s, kIdescPair, accum);
+                  accum = 1;
+                  if (q * kUmmaK < a.Kc && leader) tc_mma_pair<F16>(tmem_d, a_lo0 + ao, db + 2 * s, kIdescPair, 1);
+                } else {
+                  if (leader) tc_mma<F16>(tmem_d, a_hi0 + ao, db + 2 * s, kIdesc, accum);
+                  accum = 1;
+                  if (q * kUmmaK < a.Kc && leader) tc_mma<F16>(tmem_d, a_lo0 + ao, db + 2 * s, kIdesc, 1);
+                }
               }
               // lo steps of B feed A_hi (hi.lo)
 #pragma unroll 4
               for (int s = 0; s < nl; ++s) {
                 const int q = l0 + s;
                 const uint32_t ao = (uint32_t)(q / kSpc) * kAChunkDesc + (uint32_t)(q % kSpc) * 2;
-                if (leader) tc_mma<F16>(tmem_d, a_hi0 + ao, db + 2 * (nh + s), kIdesc, 1);
+                if (leader) {
+                  if constexpr (PAIR) tc_mma_pair<F16>(tmem_d, a_hi0 + ao, db + 2 * (nh + s), kIdescPair, 1);
+                  else tc_mma<F16>(tmem_d, a_hi0 + ao, db + 2 * (nh + s), kIdesc, 1);
+                }
               }
             }
             if (leader) {
-              if (clu) tc_commit_mc(b_empty(st), (uint16_t)3); else tc_commit(b_empty(st));
+              if constexpr (PAIR) tc_commit_pair(b_empty(st), (uint16_t)3);
+              else if (mcast) tc_commit_mc(b_empty(st), (uint16_t)3);
+              else tc_commit(b_empty(st));
             }
             if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
           }
-          if (leader) tc_commit(acc_full(buf));
+          if (leader) {
+            if constexpr (PAIR) tc_commit_pair(acc_full(buf), (uint16_t)3); else tc_commit(acc_full(buf));
+          }
         }
-        if (leader) tc_commit(a_free);
+        if (leader) {
+          if constexpr (PAIR) tc_commit_pair(a_free, (uint16_t)3); else tc_commit(a_free);
+        }
       }
     }
   } else if (warp == kBuilderWarp0 || warp == kBuilderWarp0 + 1) {
@@ -836,7 +933,9 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 64;" ::: "memory");
-      if (b == 0) mbar_arrive(a_full);
+      if (b == 0) {
+        if (pairmma) mbar_arrive_cluster(mapa_cta(a_full, 0)); else mbar_arrive(a_full);
+      }
     }
   } else if (warp < kEpiWarps) {
     // ===================== epilogue =====================
@@ -927,7 +1026,9 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty(buf));
+        if (lane == 0) {
+          if (pairmma) mbar_arrive_cluster(mapa_cta(acc_empty(buf), 0)); else mbar_arrive(acc_empty(buf));
+        }
       }
       const float nan_acc = e.nan_acc;
       if (valid && nan_acc != nan_acc) bad = true;  // r*0 is NaN exactly for a NaN/Inf result
@@ -940,7 +1041,10 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
   if (clu) cluster_sync_all();  // no CTA leaves while its peer can still multicast into it
   if (warp == kMmaWarp) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -1236,20 +1340,25 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    for (auto fn : {loglikes_tc_kernel<F16, false, false>, loglikes_tc_kernel<F16, true, false>, loglikes_tc_kernel<F16, false, true>,
-                    loglikes_tc_kernel<F16, true, true>})
+    for (auto fn : {loglikes_tc_kernel<F16, false, false, false>, loglikes_tc_kernel<F16, true, false, false>,
+                    loglikes_tc_kernel<F16, false, true, false>, loglikes_tc_kernel<F16, true, true, false>,
+                    loglikes_tc_kernel<F16, false, false, true>, loglikes_tc_kernel<F16, true, false, true>})
       if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   KHG_CUDA_TRY(attr_err);
   unsigned grid = (unsigned)std::min<int64_t>(a.n_items, m->sm_count);
   if (const char *mc = getenv("KHG_TC_MAX_CTAS")) grid = std::min<unsigned>(grid, (unsigned)std::max(1, atoi(mc)));  // experiments
-  auto kern = t.two_chunk_segs ? (t.grouped_segs ? loglikes_tc_kernel<F16, true, true> : loglikes_tc_kernel<F16, true, false>)
-                               : (t.grouped_segs ? loglikes_tc_kernel<F16, false, true> : loglikes_tc_kernel<F16, false, false>);
+  auto kern = t.two_chunk_segs ? (t.grouped_segs ? loglikes_tc_kernel<F16, true, true, false> : loglikes_tc_kernel<F16, true, false, false>)
+                               : (t.grouped_segs ? loglikes_tc_kernel<F16, false, true, false> : loglikes_tc_kernel<F16, false, false, false>);
   // CTA pairs (clusters of 2) share the streamed operand through TMA multicast when every CTA has
   // whole frame tiles to itself and there are enough of them (KHG_TC_CLUSTER=0 forces the plain form)
   const char *cl = getenv("KHG_TC_CLUSTER");
   a.cluster = (a.n_splits == 1 && n_m >= 2LL * m->sm_count && grid >= 2 && !(cl && atoi(cl) == 0)) ? 2 : 1;
-  if (a.cluster == 2) {
+  if (a.cluster == 2 && cl && atoi(cl) == 3 && !t.grouped_segs) {  // cta_group::2 MMAs across the pair
+    a.cluster = 3;
+    kern = t.two_chunk_segs ? loglikes_tc_kernel<F16, true, false, true> : loglikes_tc_kernel<F16, false, false, true>;
+  }
+  if (a.cluster >= 2) {
     grid &= ~1u;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -1266,6 +1375,8 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
     if (cudaLaunchKernelEx(&cfg, kern, F16 ? t.hmap_hi : t.map_hi, F16 ? t.hmap_lo : t.map_lo, a) != cudaSuccess) {
       (void)cudaGetLastError();  // pairs cannot be scheduled here (e.g. a partitioned GPU): the plain form
       a.cluster = 1;
+      kern = t.two_chunk_segs ? (t.grouped_segs ? loglikes_tc_kernel<F16, true, true, false> : loglikes_tc_kernel<F16, true, false, false>)
+                              : (t.grouped_segs ? loglikes_tc_kernel<F16, false, true, false> : loglikes_tc_kernel<F16, false, false, false>);
       kern<<<grid, kTcThreads, smem, m->stream>>>(F16 ? t.hmap_hi : t.map_hi, F16 ? t.hmap_lo : t.map_lo, a);
     }
   } else {
