@@ -824,6 +824,12 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
                 mbar_expect_tx(b_full(st), kBStageBytes);
                 tma_load_2d_mc(sB + st * kBStageBytes + crank * (kBStageBytes / 2), &map_b_half, b_full(st), c * kChunkK,
                                g0 + (int)crank * (kTileN / 2), (uint16_t)3);
+              } else if (a.debug_mode == 6 || a.debug_mode == 7) {
+                // experiments: the 2nd chunk (6) / every chunk (7) is always the SAME box of the operand:
+                // full shared-memory write volume, (almost) no L2 footprint
+                const bool same = a.debug_mode == 7 || c == 1;
+                mbar_expect_tx(b_full(st), kBStageBytes);
+                tma_load_2d(sB + st * kBStageBytes, &map_b, b_full(st), same ? 0 : c * kChunkK, same ? 0 : g0);
               } else {
                 mbar_expect_tx(b_full(st), kBStageBytes);
                 tma_load_2d(sB + st * kBStageBytes, &map_b, b_full(st), c * kChunkK, g0);
