@@ -326,6 +326,14 @@ __global__ void bucket_starts_kernel(const int32_t *__restrict__ sorted_keys, in
   for (int32_t p = kprev + 1; p <= kcur; ++p) starts[p] = (int32_t)i;
 }
 
+#ifndef KHG_STATS_UNROLL_A
+#define KHG_STATS_UNROLL_A 1
+#endif
+#ifndef KHG_STATS_UNROLL_B
+#define KHG_STATS_UNROLL_B 2
+#endif
+constexpr int kStatsUnrollA = KHG_STATS_UNROLL_A;  // unroll factors of the two hot loops of stats_kernel
+constexpr int kStatsUnrollB = KHG_STATS_UNROLL_B;
 constexpr int kStatsFrames = 128;      // frames per work item (upper bound)
 constexpr int kStatsPostCapMax = 8192; // max floats of smem for the posterior tile
 constexpr int kStatsMaxGp = 1600;      // largest pdf the statistics kernel accepts
@@ -441,6 +449,7 @@ __device__ __forceinline__ void stats_group_ll(const float *__restrict__ xr, con
 #pragma unroll
   for (int j = 0; j < 4; ++j) a2[j] = b2[j] = make_float2(0.f, 0.f);
   const int D4 = D & ~3;
+#pragma unroll(kStatsUnrollA)
   for (int d0 = 0; d0 < D4; d0 += 4) {
     const float4 xq = *reinterpret_cast<const float4 *>(xr + d0);
     const float xs4[4] = {xq.x, xq.y, xq.z, xq.w};
@@ -625,7 +634,7 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
     if (act) {
       const int ta = tq * per, tb = min(n, ta + per);
       const float *pp = post + gt * 4, *xp = X + dt * 4;
-#pragma unroll 2
+#pragma unroll(kStatsUnrollB)
       for (int t = ta; t < tb; ++t) {
         const float4 pq = *reinterpret_cast<const float4 *>(pp + t * PG);
         const float4 xq = *reinterpret_cast<const float4 *>(xp + t * XP);

@@ -8,7 +8,7 @@ tmp=$(mktemp -d)
 cd "$ROOT/kaldi-hmm-gmm_b200/csrc"
 for f in *.cu; do
   /usr/local/cuda/bin/nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC \
-    -I"$ROOT/include" -I. --expt-relaxed-constexpr "$@" -c $f -o $tmp/${f%.cu}.o 2>/dev/null &
+    -I"$ROOT/include" -I. --expt-relaxed-constexpr "$@" -c $f -o $tmp/${f%.cu}.o 2>/dev/null || echo "COMPILE FAILED: $f" &
 done
 wait
 mkdir -p "$ROOT/tools/ab"
