@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -159,7 +160,8 @@ extern "C" khg_status khg_gaussian_selection(khg_model *m, int32_t pdf, const fl
     KHG_CUDA_TRY(cudaMemcpyAsync(m->w_sub.p, preselect, sizeof(int32_t) * n_preselect, cudaMemcpyHostToDevice, st));
     d_pre = m->w_sub.as<int32_t>();
   }
-  const int64_t chunk = std::max<int64_t>(256, std::min<int64_t>(T, (int64_t)(512e6 / (4.0 * ng))) & ~(int64_t)255);
+  int64_t chunk = std::max<int64_t>(256, std::min<int64_t>(T, (int64_t)(512e6 / (4.0 * ng))) & ~(int64_t)255);
+  if (const char *e = getenv("KHG_GSEL_CHUNK_FRAMES")) chunk = std::max<int64_t>(1, atoll(e));  // tests: force several chunks
   double tot = 0.0;
   std::vector<float> h_like;
   for (int64_t t0 = 0; t0 < T; t0 += chunk) {

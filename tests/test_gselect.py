@@ -110,6 +110,23 @@ def test_gpu_gaussian_selection_matches_oracle(ng, D, k):
 
 
 @pytest.mark.gpu
+def test_gpu_gaussian_selection_in_several_chunks(monkeypatch):
+    """Frames are processed in chunks (bounded per-Gaussian block): same result as one chunk."""
+    from kaldi_hmm_gmm_b200 import DeviceModel
+
+    model, feats = _ubm(9, 64, 13)
+    dm = DeviceModel(13, model.offsets)
+    dm.upload(model.weights, model.means_invvars, model.inv_vars)
+    one = dm.gaussian_selection(0, feats, 7, want_loglikes=True)
+    monkeypatch.setenv("KHG_GSEL_CHUNK_FRAMES", "77")
+    many = dm.gaussian_selection(0, feats, 7, want_loglikes=True)
+    monkeypatch.delenv("KHG_GSEL_CHUNK_FRAMES")
+    assert abs(one[0] - many[0]) <= 1e-9 * abs(one[0])
+    for a, b in zip(one[1:], many[1:]):
+        np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.gpu
 def test_gpu_gaussian_selection_ties_preselect_and_device_feats():
     import torch
     from kaldi_hmm_gmm_b200 import DeviceModel
