@@ -38,10 +38,12 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <utility>
+#include <vector>
 
 #include "khg_internal.h"
 
@@ -691,6 +693,7 @@ struct TcArgs {
   float gate_limit;        // fp16 kernel runs iff *gate <= limit, tf32 kernel iff *gate > limit
   int gate_run_if_above;
   int stages;              // B ring depth
+  int a_slots;             // 1 or 2 A buffers (2: the next item's A is built under the current item's MMAs)
   const int32_t *offsets;  // P+1
   const int32_t *tile_g0;  // n_tiles
   const int32_t *tile_p0;  // n_tiles+1
@@ -706,6 +709,7 @@ struct TcArgs {
   float *scratch;          // one device word: store target of rows beyond T
   int *err;
   int debug_mode;          // 0 = normal; 1 = epilogue skips the LSE (pipeline-ceiling experiment, KHG_TC_DEBUG_MODE)
+  unsigned long long *timing;  // NULL, or per-CTA {builder wait for a_free, A build, MMA wait for a_full, items} in ns (KHG_TC_TIMING)
   int cluster;             // 1 = plain launch; 2 = CTA pairs sharing the streamed operand by TMA multicast
                            // (n_splits == 1: CTA rank r of pair k works on frame tile 2k + r)
 };
@@ -727,14 +731,18 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *base_ptr = smem_raw + (base - raw);
   const int NCH = a.n_chunks, S = a.stages;
+  const uint32_t kASlotBytes = 2u * NCH * kAChunkBytes;  // one A buffer: hi chunks, then lo chunks
   const uint32_t sA_hi = base;
   const uint32_t sA_lo = base + NCH * kAChunkBytes;
-  const uint32_t sB = base + 2 * NCH * kAChunkBytes;
+  const uint32_t sB = base + (uint32_t)a.a_slots * kASlotBytes;
   const uint32_t sBar = sB + S * kBStageBytes;
   // barrier slots (8 B each)
   auto b_full = [&](int s) { return sBar + 8u * s; };
   auto b_empty = [&](int s) { return sBar + 8u * (8 + s); };
-  const uint32_t a_full = sBar + 8u * 16, a_free = sBar + 8u * 17;
+  // A slot s (item it uses slot it % a_slots, phase (it / a_slots) & 1)
+  auto a_full = [&](uint32_t sl) { return sBar + 8u * (sl == 0 ? 16 : 23); };
+  auto a_free = [&](uint32_t sl) { return sBar + 8u * (sl == 0 ? 17 : 24); };
+  const uint32_t a_two = a.a_slots == 2 ? 1u : 0u;
   auto acc_full = [&](int b) { return sBar + 8u * (18 + b); };
   auto acc_empty = [&](int b) { return sBar + 8u * (20 + b); };
   const uint32_t tmem_slot = sBar + 8u * 22;
@@ -762,8 +770,10 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
         mbar_init(b_empty(s), mcast ? 2 : 1);  // multicast pair: the MMA warps of both CTAs release a stage
       }
       // pair MMA: the rank-0 CTA's barriers also count the peer's A builder and epilogue warps
-      mbar_init(a_full, pairmma ? 2 : 1);
-      mbar_init(a_free, 1);
+      for (uint32_t sl = 0; sl < 2; ++sl) {
+        mbar_init(a_full(sl), pairmma ? 2 : 1);
+        mbar_init(a_free(sl), 1);
+      }
       for (int b = 0; b < 2; ++b) {
         mbar_init(acc_full(b), 1);
         mbar_init(acc_empty(b), (pairmma ? 2 : 1) * 4 * kEpiGroups);
@@ -782,12 +792,13 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
     // one-time A init: zero everything, then the constant-1 column (k = 2D) of A_hi
     const int b = threadIdx.x - 32 * kBuilderWarp0;
     float4 *z = reinterpret_cast<float4 *>(base_ptr);
-    for (int i = b; i < 2 * NCH * kAChunkBytes / 16; i += kBuilderThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = b; i < a.a_slots * 2 * NCH * kAChunkBytes / 16; i += kBuilderThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     asm volatile("bar.sync 1, 64;" ::: "memory");
-    for (int row = b; row < kTileM; row += kBuilderThreads) {
-      a_store_split<F16>(base_ptr, NCH * kAChunkBytes, row, 2 * a.D, 1.0f);
-      a_store_split<F16>(base_ptr, NCH * kAChunkBytes, row, 2 * a.D + 1, 1.0f);
-    }
+    for (int sl = 0; sl < a.a_slots; ++sl)
+      for (int row = b; row < kTileM; row += kBuilderThreads) {
+        a_store_split<F16>(base_ptr + sl * kASlotBytes, NCH * kAChunkBytes, row, 2 * a.D, 1.0f);
+        a_store_split<F16>(base_ptr + sl * kASlotBytes, NCH * kAChunkBytes, row, 2 * a.D + 1, 1.0f);
+      }
   }
   tc_fence_before();
   __syncthreads();
@@ -849,13 +860,23 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
     if (!pairmma || crank == 0) {
       const bool leader = elect_one();
       uint32_t st = 0, ph = 0, acc_it = 0, a_it = 0;
-      const uint32_t a_hi0 = umma_desc_lo(sA_hi), a_lo0 = umma_desc_lo(sA_lo), b0 = umma_desc_lo(sB);
+      const uint32_t a_hi_base = umma_desc_lo(sA_hi), a_lo_base = umma_desc_lo(sA_lo), b0 = umma_desc_lo(sB);
+      const uint32_t a_slot_desc = kASlotBytes >> 4;
       constexpr uint32_t kAChunkDesc = kAChunkBytes >> 4, kBStageDesc = kBStageBytes >> 4;
       for (int64_t k = k_first; k < k_end; k += k_stride, ++a_it) {
         const int64_t item = item_of(k);
         const int split = (int)(item % a.n_splits);
         const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
-        mbar_wait_crit(a_full, a_it & 1);
+        unsigned long long tm0 = 0;
+        if (a.timing && leader) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm0));
+        const uint32_t asl = a_it & a_two, aph = (a_two ? a_it >> 1 : a_it) & 1;
+        const uint32_t a_hi0 = a_hi_base + asl * a_slot_desc, a_lo0 = a_lo_base + asl * a_slot_desc;
+        mbar_wait_crit(a_full(asl), aph);
+        if (a.timing && leader) {
+          unsigned long long tm1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm1));
+          a.timing[4 * blockIdx.x + 2] += tm1 - tm0;
+        }
         tc_fence_after();
         for (int j = j0; j < j1; ++j, ++acc_it) {
           const uint32_t buf = acc_it & 1;
@@ -909,7 +930,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
           }
         }
         if (leader) {
-          if constexpr (PAIR) tc_commit_pair(a_free, (uint16_t)3); else tc_commit(a_free);
+          if constexpr (PAIR) tc_commit_pair(a_free(asl), (uint16_t)3); else tc_commit(a_free(asl));
         }
       }
     }
@@ -923,24 +944,65 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
       const int64_t t0 = (item / a.n_splits) * kTileM;
       const int64_t valid = max((int64_t)0, min((int64_t)kTileM, a.T - t0)) * D;  // (0 for the pair's phantom tile)
       const float *src = a.feats + t0 * D;
-      if (b == 0) mbar_wait(a_free, (a_it & 1) ^ 1);
-      asm volatile("bar.sync 1, 64;" ::: "memory");
-      for (int e = b; e < kTileM * D; e += kBuilderThreads) {
-        const float x = e < valid ? __ldg(src + e) : 0.f;
-        const int row = e / D, d = e - row * D;
-        const float q = x * x;  // data.array().square(), csrc/decodable-am-diag-gmm.cc:57
-        if (F16) {  // exact power-of-two column scaling keeps both operands inside fp16's range
-          a_store_split<F16>(base_ptr, NCH * kAChunkBytes, row, d, x * __ldg(a.ascale + d));
-          a_store_split<F16>(base_ptr, NCH * kAChunkBytes, row, D + d, q * __ldg(a.ascale + D + d));
-        } else {
-          a_store_split<F16>(base_ptr, NCH * kAChunkBytes, row, d, x);
-          a_store_split<F16>(base_ptr, NCH * kAChunkBytes, row, D + d, q);
+      // The tile's features come straight from HBM (every frame is read once per E-step), so the loads
+      // are issued kABatch at a time per thread — a one-load-per-iteration loop pays the full DRAM
+      // latency ~80 times in a row, during which the tensor pipe waits for A — and the first batch is
+      // already in registers when the MMAs of the previous item release the A buffer.
+      constexpr int kABatch = 16;
+      const int n_el = (a.debug_mode == 8 && a_it > 0) ? 0 : kTileM * D;  // (8, timing only: A built once)
+      const uint32_t asl = a_it & a_two, aph = (a_two ? a_it >> 1 : a_it) & 1;
+      uint8_t *a_ptr = base_ptr + asl * kASlotBytes;
+      float xs[kABatch], ys[kABatch];
+      auto load_batch = [&](float (&v)[kABatch], int e0) {
+#pragma unroll
+        for (int j = 0; j < kABatch; ++j) {
+          const int e = e0 + j * kBuilderThreads;
+          v[j] = e < valid ? __ldg(src + e) : 0.f;
         }
+      };
+      auto store_batch = [&](const float (&v)[kABatch], int e0) {
+#pragma unroll
+        for (int j = 0; j < kABatch; ++j) {
+          const int e = e0 + j * kBuilderThreads;
+          if (e < n_el) {
+            const float x = v[j];
+            const int row = e / D, d = e - row * D;
+            const float q = x * x;  // data.array().square(), csrc/decodable-am-diag-gmm.cc:57
+            if (F16) {  // exact power-of-two column scaling keeps both operands inside fp16's range
+              a_store_split<F16>(a_ptr, NCH * kAChunkBytes, row, d, x * __ldg(a.ascale + d));
+              a_store_split<F16>(a_ptr, NCH * kAChunkBytes, row, D + d, q * __ldg(a.ascale + D + d));
+            } else {
+              a_store_split<F16>(a_ptr, NCH * kAChunkBytes, row, d, x);
+              a_store_split<F16>(a_ptr, NCH * kAChunkBytes, row, D + d, q);
+            }
+          }
+        }
+      };
+      constexpr int kStep = kBuilderThreads * kABatch;
+      load_batch(xs, b);
+      unsigned long long tt0 = 0, tt1 = 0;
+      if (a.timing && b == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt0));
+      if (b == 0) mbar_wait(a_free(asl), aph ^ 1);
+      if (a.timing && b == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt1));
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+      for (int e0 = b; e0 < n_el; e0 += 2 * kStep) {  // the next batch's loads are in flight under the stores
+        const int e1 = e0 + kStep, e2 = e1 + kStep;
+        if (e1 < n_el) load_batch(ys, e1);
+        store_batch(xs, e0);
+        if (e2 < n_el) load_batch(xs, e2);
+        if (e1 < n_el) store_batch(ys, e1);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 64;" ::: "memory");
       if (b == 0) {
-        if (pairmma) mbar_arrive_cluster(mapa_cta(a_full, 0)); else mbar_arrive(a_full);
+        if (pairmma) mbar_arrive_cluster(mapa_cta(a_full(asl), 0)); else mbar_arrive(a_full(asl));
+        if (a.timing) {
+          unsigned long long tt2;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt2));
+          a.timing[4 * blockIdx.x + 0] += tt1 - tt0;
+          a.timing[4 * blockIdx.x + 1] += tt2 - tt1;
+          a.timing[4 * blockIdx.x + 3] += 1;
+        }
       }
     }
   } else if (warp < kEpiWarps) {
@@ -1307,7 +1369,11 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   a.gate_limit = kF16FeatLimit;
   a.gate_run_if_above = gate_run_if_above;
   const int a_bytes = 2 * a.n_chunks * kAChunkBytes;
-  a.stages = std::min(F16 ? 6 : 4, (int)((225 * 1024 - a_bytes) / kBStageBytes));
+  // two A buffers when they leave room for >= 3 operand stages (3, 4 and 5 stages run at the same
+  // rate, profiles/r1u_*): the A build of the next item then overlaps the MMAs of the current one
+  a.a_slots = (225 * 1024 - 2 * a_bytes) / kBStageBytes >= 3 ? 2 : 1;
+  if (const char *e = getenv("KHG_TC_A_SLOTS")) a.a_slots = std::max(1, std::min(a.a_slots, atoi(e)));  // experiments
+  a.stages = std::min(F16 ? 6 : 4, (int)((225 * 1024 - a.a_slots * a_bytes) / kBStageBytes));
   if (const char *e = getenv("KHG_TC_STAGES")) a.stages = std::max(2, std::min(a.stages, atoi(e)));  // experiments: ring depth
   if (a.stages < 2) {
     set_error("feature dimension too large for the tcgen05 kernel");
@@ -1342,7 +1408,7 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
     const char *dbg = getenv("KHG_TC_DEBUG_MODE");
     a.debug_mode = dbg ? atoi(dbg) : 0;
   }
-  const size_t smem = (size_t)a_bytes + (size_t)a.stages * kBStageBytes + 256 + 1024;
+  const size_t smem = (size_t)a.a_slots * a_bytes + (size_t)a.stages * kBStageBytes + 256 + 1024;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -1356,6 +1422,14 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   if (const char *mc = getenv("KHG_TC_MAX_CTAS")) grid = std::min<unsigned>(grid, (unsigned)std::max(1, atoi(mc)));  // experiments
   auto kern = t.two_chunk_segs ? (t.grouped_segs ? loglikes_tc_kernel<F16, true, true, false> : loglikes_tc_kernel<F16, true, false, false>)
                                : (t.grouped_segs ? loglikes_tc_kernel<F16, false, true, false> : loglikes_tc_kernel<F16, false, false, false>);
+  a.timing = nullptr;
+  static unsigned long long *d_timing = nullptr;
+  const bool want_timing = getenv("KHG_TC_TIMING") != nullptr;
+  if (want_timing) {
+    if (!d_timing) cudaMalloc(&d_timing, sizeof(unsigned long long) * 4 * 1024);
+    cudaMemsetAsync(d_timing, 0, sizeof(unsigned long long) * 4 * 1024, m->stream);
+    a.timing = d_timing;
+  }
   // CTA pairs (clusters of 2) share the streamed operand through TMA multicast when every CTA has
   // whole frame tiles to itself and there are enough of them (KHG_TC_CLUSTER=0 forces the plain form)
   const char *cl = getenv("KHG_TC_CLUSTER");
@@ -1390,6 +1464,16 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   }
   ++g_launch_count;
   KHG_CUDA_TRY(cudaGetLastError());
+  if (want_timing) {  // diagnostics: per-item averages over the CTAs of this launch
+    std::vector<unsigned long long> h(4 * grid);
+    cudaStreamSynchronize(m->stream);
+    cudaMemcpy(h.data(), d_timing, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost);
+    double w = 0, bld = 0, mw = 0, items = 0;
+    for (unsigned i = 0; i < grid; ++i) { w += h[4 * i]; bld += h[4 * i + 1]; mw += h[4 * i + 2]; items += h[4 * i + 3]; }
+    if (items > 0)
+      fprintf(stderr, "K1 timing (f16=%d): per item: builder waits a_free %.1f us, builds A %.1f us; MMA warp waits a_full %.1f us (%g items)\n",
+              (int)F16, w / items / 1e3, bld / items / 1e3, mw / items / 1e3, items);
+  }
   return KHG_OK;
 }
 
