@@ -943,7 +943,8 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
       const int64_t item = item_of(k);
       const int64_t t0 = (item / a.n_splits) * kTileM;
       const int64_t valid = max((int64_t)0, min((int64_t)kTileM, a.T - t0)) * D;  // (0 for the pair's phantom tile)
-      const float *src = a.feats + t0 * D;
+      // (debug mode 9, timing only: every item re-reads the CTA's first tile — the full A build on repeating data)
+      const float *src = a.feats + (a.debug_mode == 9 ? item_of(k_first) / a.n_splits * kTileM : t0) * D;
       // The tile's features come straight from HBM (every frame is read once per E-step), so the loads
       // are issued kABatch at a time per thread — a one-load-per-iteration loop pays the full DRAM
       // latency ~80 times in a row, during which the tensor pipe waits for A — and the first batch is
