@@ -11,24 +11,27 @@
 // B = [means_invvars, -0.5*inv_vars, gconst]  (G x K), followed by a fused per-pdf
 // log-sum-exp epilogue.
 //
-// Precision: 3xTF32.  Both operands are split  v = hi + lo  with hi = rna_tf32(v); the
-// tensor core accumulates  A_hi.B_hi + A_lo.B_hi + A_hi.B_lo  in fp32 (the dropped
-// lo.lo term is ~2^-22 relative), which keeps |error| well inside BASELINE.json's
-// 1e-3 abs / 1e-4 rel bound on log-likelihoods of magnitude ~1e2.
+// Precision: a 3-term split.  Both operands are split  v = hi + lo  with hi = the value rounded to
+// the operand container — tf32 (kind::tf32) or fp16 with exact per-column power-of-two scaling
+// (kind::f16, twice the tensor rate) — and the tensor core accumulates
+// A_hi.B_hi + A_lo.B_hi + A_hi.B_lo  in fp32 (the dropped lo.lo term is ~2^-22 relative), which
+// keeps |error| well inside BASELINE.json's 1e-3 abs / 1e-4 rel bound on log-likelihoods of
+// magnitude ~1e2.
 //
-// Structure (one persistent CTA per SM, 20 warps, warp-specialised):
-//   warp 18     TMA producer: streams B tiles (240 Gaussians x 32 floats, hi and lo)
-//               through a ring of smem stages (cp.async.bulk.tensor, 128B swizzle)
-//   warp 19     MMA issuer: one thread issues tcgen05.mma.kind::tf32, M=128 (frames),
-//               N=240 (Gaussians), K=8 per instruction; accumulators live in TMEM
-//               (2 x 256 columns, double buffered against the epilogue)
-//               (this warp also allocates / frees the TMEM columns)
-//   warps 16-17 A builders: load a 128-frame feature tile, form [x, x^2, 1], split
-//               hi/lo and write it in the UMMA K-major 128B-swizzled layout.  A is
-//               stationary for all N tiles of a work item.
-//   warps 0-15  epilogue: tcgen05.ld the accumulator rows (thread = frame), per-pdf
-//               max-subtracted log-sum-exp over the pdf's contiguous Gaussians,
-//               coalesced store of out[p][t] (pdf-major).
+// Structure (one persistent CTA per SM, 28 warps, warp-specialised; CTAs run in pairs that share
+// the streamed operand by TMA multicast when there are enough frame tiles):
+//   warps 0-23  epilogue (6 groups x 4 TMEM lane quadrants): tcgen05.ld the accumulator rows
+//               (thread = frame), per-pdf max-subtracted log-sum-exp over the pdf's contiguous
+//               Gaussians driven by host-built run tables, coalesced store of out[p][t] (pdf-major)
+//   warps 24-25 A builders: load a 128-frame feature tile (16 loads in flight per thread), form
+//               [x, x^2, 1, 1], split hi/lo and write it in the UMMA K-major 128B-swizzled layout
+//               into one of TWO A buffers, one item ahead of the MMAs; A is stationary for all N
+//               tiles of a work item
+//   warp 26     TMA producer: streams the operand B' (240 Gaussians x one 128-byte K chunk per
+//               stage) through a ring of smem stages (cp.async.bulk.tensor, 128B swizzle)
+//   warp 27     MMA issuer: one elected lane issues tcgen05.mma, M=128 (frames), N=240
+//               (Gaussians); accumulators live in TMEM (2 x 256 columns, double buffered against
+//               the epilogue); this warp also allocates / frees the TMEM columns
 // N tiles are aligned to pdf boundaries (tile table built on the host), so a pdf's
 // Gaussians never straddle two accumulator tiles.
 #include <cuda.h>
