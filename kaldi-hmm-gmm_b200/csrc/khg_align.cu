@@ -75,15 +75,24 @@ struct RedScratch {
   int s[2][kMaxWarps];
 };
 
-// (min, sum) over the CTA; one __syncthreads per call (two alternating slots).
+// Order-preserving map double -> uint64 (so that a min over costs is two 32-bit redux.sync).
+__device__ __forceinline__ unsigned long long cost_key(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_cost(unsigned long long k) {
+  return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+// (min, sum) over the CTA; one __syncthreads per call (two alternating slots).  Warp stage: the
+// minimum of the 64-bit keys as redux.sync.min over the high words, then over the low words of the
+// lanes that hold the minimal high word; the count as redux.sync.add.
 __device__ __forceinline__ void block_min_sum(double &v, int &n, RedScratch *rs, int &slot) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    n += __shfl_xor_sync(0xffffffffu, n, o);
-  }
-  if (lane == 0) { rs->v[slot][warp] = v; rs->n[slot][warp] = n; }
+  const unsigned long long k = cost_key(v);
+  const unsigned hi = (unsigned)(k >> 32), mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? (unsigned)k : 0xffffffffu);
+  n = __reduce_add_sync(0xffffffffu, n);
+  if (lane == 0) { rs->v[slot][warp] = key_cost(((unsigned long long)mhi << 32) | mlo); rs->n[slot][warp] = n; }
   __syncthreads();
   double bv = rs->v[slot][0];
   int bn = rs->n[slot][0];
@@ -203,11 +212,12 @@ __global__ void __launch_bounds__(512) viterbi_kernel(AlignDev g, int u_base, co
     __syncthreads();
     bool dead = false;
     for (int t = 0; t < T; ++t) {
-      const int tf = FC ? t % FC : 0;
+      const int tf = FC ? (t & (FC - 1)) : 0;  // FC is 32, 16, 8 or 0
       if (FC && tf == 0) {  // stage the next FC frames of this utterance's pdfs (ordered by the sync in the reduction)
         const int nf = min(FC, T - t);
+        const int fsh = 31 - __clz(FC);
         for (int i = tid; i < u.n_pdf * FC; i += NT) {
-          const int j = i / FC, f = i - j * FC;
+          const int j = i >> fsh, f = i & (FC - 1);
           if (f < nf) tile[i] = ll[(int64_t)upd[j] * ld + u.col0 + t + f];
         }
       }
