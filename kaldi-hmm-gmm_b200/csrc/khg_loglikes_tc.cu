@@ -52,6 +52,10 @@
 
 namespace khg {
 
+#ifndef KHG_FEAT_LOAD
+#define KHG_FEAT_LOAD __ldcg
+#endif
+
 constexpr int kTileM = 128;         // frames per CTA tile (UMMA M)
 constexpr int kTileN = 240;         // Gaussians per accumulator tile (UMMA N)
 // Operand element: tf32 (4 B, 32 per 128-byte swizzle atom, UMMA_K = 8) or fp16 (2 B, 64
@@ -961,7 +965,9 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
 #pragma unroll
         for (int j = 0; j < kABatch; ++j) {
           const int e = e0 + j * kBuilderThreads;
-          v[j] = e < valid ? __ldg(src + e) : 0.f;
+          // L2-only load (ld.global.cg): every frame is read once, nothing to keep in L1 (measured: no
+          // difference to ld.global.nc or .cs)
+          v[j] = e < valid ? KHG_FEAT_LOAD(src + e) : 0.f;
         }
       };
       auto store_batch = [&](const float (&v)[kABatch], int e0) {
