@@ -222,7 +222,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": "reference's Eigen build is unbuildable here (Eigen 3.4.0 is network-fetched); this is the oracle port of its algorithm",
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ------------------------------------------------------------------ GPU arm --
@@ -450,13 +450,30 @@ def run_b200(args):
                                               f"-O3 AVX2, {threads} OpenMP threads"}
         except Exception as ex:
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": threads, "kind": "port", "error": repr(ex)[:200]}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit_line(line):
+    """The ONE JSON line goes to the process's original stdout; everything libraries print to fd 1
+    during the run (NCCL's "NCCL version ..." banner at N>1) was routed to stderr in __main__."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)
