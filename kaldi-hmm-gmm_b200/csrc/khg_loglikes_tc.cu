@@ -1029,8 +1029,11 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
       const int64_t t = (item / a.n_splits) * kTileM + row;
       const bool valid = t < a.T;
       // rows beyond T store into a scratch word (ld_bytes = 0): no predicate in the hot loop
-      char *out_t = valid ? reinterpret_cast<char *>(a.out + t) : reinterpret_cast<char *>(a.scratch);
-      const uint32_t ld_bytes = valid ? (uint32_t)(a.ld * 4) : 0u;
+      // (experiments, timing only: 10 = every tile stores into the block's first 128 frames — an L2-resident
+      // window, no DRAM write stream; 11 = every store goes to the scratch word — no store traffic at all)
+      const bool to_scratch = !valid || a.debug_mode == 11;
+      char *out_t = to_scratch ? reinterpret_cast<char *>(a.scratch) : reinterpret_cast<char *>(a.out + (a.debug_mode == 10 ? (int64_t)row : t));
+      const uint32_t ld_bytes = to_scratch ? 0u : (uint32_t)(a.ld * 4);
       EpiState e;
       e.scale = a.scale;
       e.nan_acc = 0.f;

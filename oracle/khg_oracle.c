@@ -378,6 +378,128 @@ int64_t khg_oracle_loglikes_all_pdfs(int32_t dim, int32_t num_pdfs,
   return bad;
 }
 
+/* ---- csrc/diag-gmm.cc:177-189 (LogLikelihoodsMatrix) for every pdf ------
+ * The matrix form of the same arithmetic: a block of FB frames at a time,
+ *   loglikes(FB x nmix) = data * means_invvars^T - 0.5 * data^2 * inv_vars^T + gconsts,
+ * i.e. the frame-blocked GEMM the reference executes when it is handed a feature
+ * matrix, so that the model streams through the cache once per FB frames instead
+ * of once per frame.  This is the CPU *baseline* form (bench.py); the per-frame
+ * function above stays the parity form.  The exponentials are a vectorisable
+ * Cephes-style expf (what Eigen's packet exp is), the sums run over frames so the
+ * compiler keeps them in SIMD registers.  */
+#define KHG_FB 64
+typedef float khg_v8 __attribute__((vector_size(32), aligned(32)));
+typedef int32_t khg_i8 __attribute__((vector_size(32), aligned(32)));
+#define KHG_V8(c) ((khg_v8){c, c, c, c, c, c, c, c})
+static inline khg_v8 khg_max_v8(khg_v8 a, khg_v8 b) {
+  khg_i8 m = a > b, ai, bi;
+  memcpy(&ai, &a, sizeof(ai));
+  memcpy(&bi, &b, sizeof(bi));
+  khg_i8 r = (ai & m) | (bi & ~m);
+  khg_v8 out;
+  memcpy(&out, &r, sizeof(out));
+  return out;
+}
+static inline khg_v8 khg_exp_v8(khg_v8 x) {
+  /* exp(x) for x <= 0 (max-subtracted): x = n ln2 + r, degree-5 polynomial, 2^n by exponent bits */
+  khg_v8 lo = KHG_V8(-87.0f);
+  x = khg_max_v8(x, lo);
+  khg_v8 t = x * KHG_V8(1.44269504088896341f) - KHG_V8(0.5f);
+  khg_i8 n = __builtin_convertvector(t, khg_i8); /* truncation: round to nearest for non-positive arguments */
+  khg_v8 fn = __builtin_convertvector(n, khg_v8);
+  khg_v8 r = x - fn * KHG_V8(0.693359375f);
+  r = r + fn * KHG_V8(2.12194440e-4f);
+  khg_v8 p = KHG_V8(1.9875691500e-4f);
+  p = p * r + KHG_V8(1.3981999507e-3f);
+  p = p * r + KHG_V8(8.3334519073e-3f);
+  p = p * r + KHG_V8(4.1665795894e-2f);
+  p = p * r + KHG_V8(1.6666665459e-1f);
+  p = p * r + KHG_V8(5.0000001201e-1f);
+  p = p * r * r + r + KHG_V8(1.0f);
+  khg_i8 e = (n + 127) << 23;
+  khg_v8 scale;
+  memcpy(&scale, &e, sizeof(scale));
+  return p * scale;
+}
+
+int64_t khg_oracle_loglikes_all_pdfs_blocked(int32_t dim, int32_t num_pdfs,
+                                             const int32_t *offsets,
+                                             const float *gconsts,
+                                             const float *means_invvars,
+                                             const float *inv_vars,
+                                             const float *feats, int64_t T,
+                                             float scale, int32_t pdf_major,
+                                             float *out, int32_t threads) {
+  int32_t mg = max_gauss(num_pdfs, offsets);
+  int64_t bad = 0;
+  if (threads < 1) threads = 1;
+  int64_t n_blocks = (T + KHG_FB - 1) / KHG_FB;
+#pragma omp parallel num_threads(threads) reduction(+ : bad)
+  {
+    float *xt = (float *)aligned_alloc(64, sizeof(float) * (size_t)dim * KHG_FB);
+    float *xs = (float *)aligned_alloc(64, sizeof(float) * (size_t)dim * KHG_FB);
+    float *ll = (float *)aligned_alloc(64, sizeof(float) * (size_t)(mg > 0 ? mg : 1) * KHG_FB);
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t b = 0; b < n_blocks; ++b) {
+      int64_t t0 = b * KHG_FB;
+      int32_t nf = (int32_t)(T - t0 < KHG_FB ? T - t0 : KHG_FB);
+      for (int32_t d = 0; d < dim; ++d)
+        for (int32_t f = 0; f < KHG_FB; ++f) {
+          float x = f < nf ? feats[(size_t)(t0 + f) * dim + d] : 0.0f;
+          xt[d * KHG_FB + f] = x;
+          xs[d * KHG_FB + f] = x * x;
+        }
+      for (int32_t p = 0; p < num_pdfs; ++p) {
+        int32_t g0 = offsets[p], ng = offsets[p + 1] - g0;
+        for (int32_t g = 0; g < ng; ++g) {
+          const float *mv = means_invvars + (size_t)(g0 + g) * dim;
+          const float *iv = inv_vars + (size_t)(g0 + g) * dim;
+          /* 8 packet accumulators (64 frames) stay in registers across the D loop */
+          khg_v8 acc[KHG_FB / 8];
+          float gc = gconsts[g0 + g];
+          for (int32_t i = 0; i < KHG_FB / 8; ++i) acc[i] = (khg_v8){gc, gc, gc, gc, gc, gc, gc, gc};
+          for (int32_t d = 0; d < dim; ++d) {
+            float a1 = mv[d], h1 = -0.5f * iv[d];
+            khg_v8 a = {a1, a1, a1, a1, a1, a1, a1, a1}, h = {h1, h1, h1, h1, h1, h1, h1, h1};
+            const khg_v8 *xr = (const khg_v8 *)(xt + d * KHG_FB), *sr = (const khg_v8 *)(xs + d * KHG_FB);
+            for (int32_t i = 0; i < KHG_FB / 8; ++i) {
+              acc[i] += a * xr[i];
+              acc[i] += h * sr[i];
+            }
+          }
+          for (int32_t i = 0; i < KHG_FB / 8; ++i) ((khg_v8 *)ll)[g * (KHG_FB / 8) + i] = acc[i];
+        }
+        /* LogSumExp over the pdf's Gaussians, csrc/eigen.cc:14-18, for FB frames at once */
+        khg_v8 mxv[KHG_FB / 8], smv[KHG_FB / 8];
+        const khg_v8 *lv = (const khg_v8 *)ll;
+        for (int32_t i = 0; i < KHG_FB / 8; ++i) mxv[i] = lv[i];
+        for (int32_t g = 1; g < ng; ++g)
+          for (int32_t i = 0; i < KHG_FB / 8; ++i) {
+            khg_v8 l = lv[g * (KHG_FB / 8) + i];
+            mxv[i] = khg_max_v8(l, mxv[i]);
+          }
+        for (int32_t i = 0; i < KHG_FB / 8; ++i) smv[i] = KHG_V8(0.0f);
+        for (int32_t g = 0; g < ng; ++g)
+          for (int32_t i = 0; i < KHG_FB / 8; ++i) smv[i] += khg_exp_v8(lv[g * (KHG_FB / 8) + i] - mxv[i]);
+        const float *mx = (const float *)mxv, *sm = (const float *)smv;
+        for (int32_t f = 0; f < nf; ++f) {
+          float s = logf(sm[f]) + mx[f];
+          if (isnan(s) || isinf(s)) bad++;
+          s = scale * s;
+          if (pdf_major)
+            out[(size_t)p * T + t0 + f] = s;
+          else
+            out[(size_t)(t0 + f) * num_pdfs + p] = s;
+        }
+      }
+    }
+    free(xt);
+    free(xs);
+    free(ll);
+  }
+  return bad;
+}
+
 /* ---- csrc/mle-diag-gmm.cc:479-499 ------------------------------------- */
 float khg_oracle_ml_objective(int32_t nmix, int32_t dim, uint16_t acc_flags,
                               const float *gconsts, const float *means_invvars,

@@ -150,6 +150,16 @@ int64_t khg_oracle_loglikes_all_pdfs(int32_t dim, int32_t num_pdfs,
                                      const float *inv_vars, const float *feats,
                                      int64_t T, float scale, int32_t pdf_major,
                                      float *out, int32_t threads);
+/* The same block in the frame-blocked matrix form of csrc/diag-gmm.cc:177-189
+ * (LogLikelihoodsMatrix): the CPU baseline bench.py times; agrees with the per-frame
+ * form to fp32 rounding (tests/test_oracle.py). */
+int64_t khg_oracle_loglikes_all_pdfs_blocked(int32_t dim, int32_t num_pdfs,
+                                     const int32_t *offsets,
+                                     const float *gconsts,
+                                     const float *means_invvars,
+                                     const float *inv_vars, const float *feats,
+                                     int64_t T, float scale, int32_t pdf_major,
+                                     float *out, int32_t threads);
 
 /* csrc/mle-diag-gmm.cc:479-499 */
 float khg_oracle_ml_objective(int32_t nmix, int32_t dim, uint16_t acc_flags,

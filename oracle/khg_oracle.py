@@ -88,6 +88,8 @@ class Oracle:
         L.khg_oracle_acc_stats_ali_mt.argtypes = [C.c_int32, C.c_int32, _i32p, _f32p, _f32p, _f32p, C.c_uint16, _f32p, C.c_int64, _i32p, _f32p, _f64p, _f64p, _f64p, _f64p, C.c_int32]
         L.khg_oracle_loglikes_all_pdfs.restype = C.c_int64
         L.khg_oracle_loglikes_all_pdfs.argtypes = [C.c_int32, C.c_int32, _i32p, _f32p, _f32p, _f32p, _f32p, C.c_int64, C.c_float, C.c_int32, _f32p, C.c_int32]
+        L.khg_oracle_loglikes_all_pdfs_blocked.restype = C.c_int64
+        L.khg_oracle_loglikes_all_pdfs_blocked.argtypes = L.khg_oracle_loglikes_all_pdfs.argtypes
         L.khg_oracle_ml_objective.restype = C.c_float
         L.khg_oracle_ml_objective.argtypes = [C.c_int32, C.c_int32, C.c_uint16, _f32p, _f32p, _f32p, _f64p, _f64p, _f64p]
         L.khg_oracle_mle_update.restype = C.c_int32
@@ -190,12 +192,14 @@ class Oracle:
             bad = self.lib.khg_oracle_acc_stats_ali_mt(D, m.num_pdfs, _fp(m.offsets, _i32p), _fp(m.gconsts), _fp(m.means_invvars), _fp(m.inv_vars), flags, _fp(feats), T, _fp(pdf_ids, _i32p), _fp(fw), _fp(occ, _f64p), _fp(mean, _f64p), _fp(var, _f64p), _fp(totals, _f64p), threads)
         return dict(occ=occ, mean=mean, var=var, tot_like=float(totals[0]), tot_frames=float(totals[1]), per_frame=pf, bad=int(bad))
 
-    def loglikes_all_pdfs(self, model: "PackedModel", feats, scale=1.0, pdf_major=False, threads=1):
+    def loglikes_all_pdfs(self, model: "PackedModel", feats, scale=1.0, pdf_major=False, threads=1, blocked=False):
+        """blocked=True: the frame-blocked matrix form (csrc/diag-gmm.cc:177-189), the CPU baseline."""
         m = model
         feats = np.ascontiguousarray(feats, np.float32)
         T = feats.shape[0]
         out = np.empty((m.num_pdfs, T) if pdf_major else (T, m.num_pdfs), np.float32)
-        bad = self.lib.khg_oracle_loglikes_all_pdfs(m.dim, m.num_pdfs, _fp(m.offsets, _i32p), _fp(m.gconsts), _fp(m.means_invvars), _fp(m.inv_vars), _fp(feats), T, scale, int(pdf_major), _fp(out), threads)
+        fn = self.lib.khg_oracle_loglikes_all_pdfs_blocked if blocked else self.lib.khg_oracle_loglikes_all_pdfs
+        bad = fn(m.dim, m.num_pdfs, _fp(m.offsets, _i32p), _fp(m.gconsts), _fp(m.means_invvars), _fp(m.inv_vars), _fp(feats), T, scale, int(pdf_major), _fp(out), threads)
         return out, int(bad)
 
     def ml_objective(self, acc_flags, gc, miv, iv, occ, mean, var):

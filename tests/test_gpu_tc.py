@@ -22,6 +22,15 @@ def _models(model):
     return out
 
 
+def _one(model, kernel):
+    from kaldi_hmm_gmm_b200 import DeviceModel
+
+    dm = DeviceModel(model.dim, model.offsets)
+    dm.set_kernel(kernel)
+    dm.upload(model.weights, model.means_invvars, model.inv_vars)
+    return dm
+
+
 def _check(got, ref):
     got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
     err = np.abs(got - ref)
@@ -110,14 +119,16 @@ def test_tc_nonfinite_and_all_zero_weight_pdf_raise(oracle):
         dm.loglikes_all_pdfs(feats[:10])
 
 
+@pytest.mark.parametrize("kernel", [TC, TC_F16, AUTO], ids=["tf32", "f16", "auto"])
 @pytest.mark.parametrize("name,D,P,G,T", [
     ("C2-monophone", 39, 130, 1000, 3000),
     ("C3-tri1", 39, 2000, 10000, 1500),
     ("C4-lda-mllt", 40, 4200, 40000, 1000),
     ("C5-sat", 40, 5000, 100000, 600),
 ])
-def test_baseline_config_shapes(oracle, name, D, P, G, T):
-    """The model shapes BASELINE.json names (configs[1..4]): dense block (tcgen05) and
+def test_baseline_config_shapes(oracle, name, D, P, G, T, kernel):
+    """The model shapes BASELINE.json names (configs[1..4]) on EVERY tensor-core kernel choice — the
+    3xTF32 split, the 3xFP16 split and the device-gated AUTO that bench.py runs: dense block and
     alignment statistics against the oracle on a slice of frames."""
     import os
 
@@ -125,7 +136,8 @@ def test_baseline_config_shapes(oracle, name, D, P, G, T):
 
     model, means, vars_ = ko.make_synthetic_model(D, P, G, oracle=oracle)
     feats, pdf = ko.make_synthetic_frames(model, means, vars_, T)
-    tc, _ = _models(model)
+    tc = _one(model, kernel)
+    assert tc.dense_kernel() == (TC if kernel == TC else TC_F16)  # AUTO resolves to the fp16 split on these models
     ref, bad = oracle.loglikes_all_pdfs(model, feats, threads=os.cpu_count() or 1)
     assert bad == 0
     _check(tc.loglikes_all_pdfs(feats), ref)
@@ -142,13 +154,28 @@ def test_baseline_config_shapes(oracle, name, D, P, G, T):
     assert np.abs(ref[np.arange(T), pdf] - r["per_frame"]).max() < 1e-4
 
 
-def _one(model, kernel):
-    from kaldi_hmm_gmm_b200 import DeviceModel
+@pytest.mark.parametrize("kernel", [TC_F16, AUTO, TC], ids=["f16", "auto", "tf32"])
+@pytest.mark.parametrize("name,D,P,G", [("C4-lda-mllt", 40, 4200, 40000), ("C5-sat", 40, 5000, 100000)])
+def test_baseline_config_shapes_many_frame_tiles(oracle, name, D, P, G, kernel):
+    """C4 / C5 with more than two frame tiles per SM and a ragged tail, device-resident like bench.py and
+    khg_align_batch feed them: the launch form used at full size (every N tile of the model, every
+    CTA working through many frame tiles).  Oracle on the first and last frames; every entry finite."""
+    import os
 
-    dm = DeviceModel(model.dim, model.offsets)
-    dm.set_kernel(kernel)
-    dm.upload(model.weights, model.means_invvars, model.inv_vars)
-    return dm
+    import torch
+
+    model, means, vars_ = ko.make_synthetic_model(D, P, G, oracle=oracle)
+    T = 2 * 148 * 128 + 128 * 5 + 77
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, T)
+    dm = _one(model, kernel)
+    out = dm.loglikes_all_pdfs(torch.from_numpy(feats).cuda(), layout=1)
+    dm.sync()
+    assert out.shape == (P, T) and bool(torch.isfinite(out).all())
+    n = 250
+    for sl in (slice(0, n), slice(T - n, T), slice(148 * 128 - n // 2, 148 * 128 + n // 2)):
+        ref, bad = oracle.loglikes_all_pdfs(model, feats[sl], threads=os.cpu_count() or 1)
+        assert bad == 0
+        _check(out[:, sl].T.cpu().numpy(), ref)
 
 
 @pytest.mark.parametrize("D,P,G,T", [(40, 37, 350, 3000), (39, 13, 100, 1000), (40, 420, 4000, 700), (13, 5, 17, 129),

@@ -193,3 +193,20 @@ def test_mle_update_removes_low_count_gaussian(oracle):
     np.testing.assert_allclose(upd["weights"].sum(), 1.0, rtol=1e-6)
     np.testing.assert_allclose(upd["weights"], np.array([100, 50]) / 150.0, rtol=1e-5)
     np.testing.assert_allclose(1.0 / upd["inv_vars"], 1.0, rtol=1e-5)
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_blocked_matrix_form_agrees_with_per_frame_form(fast):
+    """The frame-blocked LogLikelihoodsMatrix form (csrc/diag-gmm.cc:177-189; bench.py's CPU baseline)
+    against the per-frame parity form (csrc/decodable-am-diag-gmm.cc:29-71): same numbers to fp32
+    rounding, both layouts, ragged tail block, several threads."""
+    ora = ko.Oracle(fast=fast)
+    model, means, vars_ = ko.make_synthetic_model(39, 57, 500, oracle=ora)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, 64 * 3 + 17)
+    a, bad_a = ora.loglikes_all_pdfs(model, feats, scale=0.5)
+    for threads in (1, 3):
+        b, bad_b = ora.loglikes_all_pdfs(model, feats, scale=0.5, blocked=True, threads=threads)
+        assert bad_a == bad_b == 0
+        assert np.abs(a - b).max() < 1e-3 and (np.abs(a - b) / np.maximum(np.abs(a), 10.0)).max() < 1e-4
+        c, _ = ora.loglikes_all_pdfs(model, feats, scale=0.5, blocked=True, threads=threads, pdf_major=True)
+        np.testing.assert_array_equal(c.T, b)
