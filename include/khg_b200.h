@@ -181,6 +181,10 @@ khg_status khg_stats_upload(khg_stats *s, const double *occ, const double *mean,
 khg_status khg_stats_add(khg_stats *dst, float scale, const khg_stats *src);
 /* AccumAmDiagGmm::Scale (csrc/mle-am-diag-gmm.cc:130-138) */
 khg_status khg_stats_scale(khg_stats *s, float scale);
+/* Lifetime: a khg_stats keeps a pointer to the model it was created on (its stream,
+ * its Gaussian layout).  Destroy the statistics BEFORE their model; a model handle
+ * returned by khg_mle_update / split / merge is a different model and needs its own
+ * khg_stats.  Views of the device buffer (khg_stats_device_buffer) die with the handle. */
 void khg_stats_destroy(khg_stats *s);
 
 /* The gmm-acc-stats-ali inner loop for T frames in one call:
@@ -193,7 +197,13 @@ void khg_stats_destroy(khg_stats *s);
  *   frame_weights  f32[T] or NULL (=1)         (same loc as feats)
  *   per_frame_loglike f32[T] or NULL: the UNWEIGHTED per-frame log-like
  *                  AccumulateForGmm returns              (same loc as feats)
- *   tot_loglike    host double or NULL: this call's sum ll*w (forces a sync) */
+ *   tot_loglike    host double or NULL: this call's sum ll*w (forces a sync)
+ * A pdf id outside [0, num_pdfs) is the reference's KHG_ASSERT
+ * (csrc/mle-am-diag-gmm.cc:44): the call — or, for asynchronous device-buffer
+ * calls, the next synchronising call on the model — returns KHG_ERR_INVALID.
+ * Such frames contribute NOTHING to the statistics (on every internal path); the
+ * other frames of the call have been accumulated, so treat the stats handle as
+ * poisoned after this error (zero it or destroy it), as the reference's abort does. */
 khg_status khg_acc_stats_ali(khg_model *m, khg_stats *s, const float *feats,
                              int64_t T, int32_t loc, const int32_t *pdf_ids,
                              const float *frame_weights,

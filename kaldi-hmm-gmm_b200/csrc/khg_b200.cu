@@ -616,7 +616,7 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
   }
   const int64_t slab = 1 << 23;
   int end_bit = 1;
-  while ((1 << end_bit) < P) ++end_bit;
+  while ((1 << end_bit) <= P) ++end_bit;  // keys 0..P: P is the sentinel bucket of out-of-range ids
   // smem sized for THIS model: posterior tile for the largest pdf, model staging for
   // at most the groups of the largest pdf (bounded) -> several CTAs per SM for C4-like models
   const int max_groups = (m->max_gp + 7) / 8;
@@ -946,13 +946,25 @@ khg_status khg_estep(khg_model *m, khg_stats *s, const float *feats, int64_t T, 
     // Host inputs: double-buffered pinned staging; the H2D copy of chunk i+1 runs on
     // copy_stream while chunk i computes on the model stream.
     KHG_TRY(estep_init_streams(m));
+    // Caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory)
+    // are copied from directly: no staging memcpy on the calling thread, which is what limits several
+    // ranks feeding their GPUs from one host.
+    auto is_pinned = [](const void *p) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+      }
+      return at.type == cudaMemoryTypeHost;
+    };
+    const bool direct_f = is_pinned(feats), direct_i = is_pinned(pdf_ids), direct_w = frame_weights && is_pinned(frame_weights);
     for (int i = 0; i < 2; ++i) {
-      KHG_TRY(m->pin_feats[i].reserve(sizeof(float) * chunk_frames * D));
-      KHG_TRY(m->pin_ids[i].reserve(sizeof(int32_t) * chunk_frames));
+      if (!direct_f) KHG_TRY(m->pin_feats[i].reserve(sizeof(float) * chunk_frames * D));
+      if (!direct_i) KHG_TRY(m->pin_ids[i].reserve(sizeof(int32_t) * chunk_frames));
       KHG_TRY(m->w_efeats[i].reserve(sizeof(float) * chunk_frames * D));
       KHG_TRY(m->w_eids[i].reserve(sizeof(int32_t) * chunk_frames));
       if (frame_weights) {
-        KHG_TRY(m->pin_wts[i].reserve(sizeof(float) * chunk_frames));
+        if (!direct_w) KHG_TRY(m->pin_wts[i].reserve(sizeof(float) * chunk_frames));
         KHG_TRY(m->w_ewts[i].reserve(sizeof(float) * chunk_frames));
       }
     }
@@ -965,13 +977,15 @@ khg_status khg_estep(khg_model *m, khg_stats *s, const float *feats, int64_t T, 
       if (used[b]) KHG_CUDA_TRY(cudaStreamWaitEvent(m->copy_stream, m->ev_done[b], 0));
       // pinned slot b is free once its previous H2D finished
       if (used[b]) KHG_CUDA_TRY(cudaEventSynchronize(m->ev_copy[b]));
-      std::memcpy(m->pin_feats[b].p, feats + t0 * D, sizeof(float) * n * D);
-      std::memcpy(m->pin_ids[b].p, pdf_ids + t0, sizeof(int32_t) * n);
-      KHG_CUDA_TRY(cudaMemcpyAsync(m->w_efeats[b].p, m->pin_feats[b].p, sizeof(float) * n * D, cudaMemcpyHostToDevice, m->copy_stream));
-      KHG_CUDA_TRY(cudaMemcpyAsync(m->w_eids[b].p, m->pin_ids[b].p, sizeof(int32_t) * n, cudaMemcpyHostToDevice, m->copy_stream));
+      const void *src_f = feats + t0 * D, *src_i = pdf_ids + t0;
+      if (!direct_f) src_f = std::memcpy(m->pin_feats[b].p, src_f, sizeof(float) * n * D);
+      if (!direct_i) src_i = std::memcpy(m->pin_ids[b].p, src_i, sizeof(int32_t) * n);
+      KHG_CUDA_TRY(cudaMemcpyAsync(m->w_efeats[b].p, src_f, sizeof(float) * n * D, cudaMemcpyHostToDevice, m->copy_stream));
+      KHG_CUDA_TRY(cudaMemcpyAsync(m->w_eids[b].p, src_i, sizeof(int32_t) * n, cudaMemcpyHostToDevice, m->copy_stream));
       if (frame_weights) {
-        std::memcpy(m->pin_wts[b].p, frame_weights + t0, sizeof(float) * n);
-        KHG_CUDA_TRY(cudaMemcpyAsync(m->w_ewts[b].p, m->pin_wts[b].p, sizeof(float) * n, cudaMemcpyHostToDevice, m->copy_stream));
+        const void *src_w = frame_weights + t0;
+        if (!direct_w) src_w = std::memcpy(m->pin_wts[b].p, src_w, sizeof(float) * n);
+        KHG_CUDA_TRY(cudaMemcpyAsync(m->w_ewts[b].p, src_w, sizeof(float) * n, cudaMemcpyHostToDevice, m->copy_stream));
       }
       KHG_CUDA_TRY(cudaEventRecord(m->ev_copy[b], m->copy_stream));
       KHG_CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_copy[b], 0));

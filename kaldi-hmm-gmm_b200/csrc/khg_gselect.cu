@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(32 * kGselWarps) gselect_kernel(const float *_
 }
 
 khg_status gsel_shadow(khg_model *m, int32_t pdf, khg_model **out) {
-  if (m->gsel_shadow && m->gsel_pdf == pdf) { *out = m->gsel_shadow; return KHG_OK; }
+  // the shadow shares the parent's scratch buffers, so it always works on the parent's CURRENT stream
+  if (m->gsel_shadow && m->gsel_pdf == pdf) { m->gsel_shadow->stream = m->stream; *out = m->gsel_shadow; return KHG_OK; }
   if (m->gsel_shadow) { khg_model_destroy(m->gsel_shadow); m->gsel_shadow = nullptr; }
   const int g0 = m->h_offsets[pdf], ng = m->h_offsets[pdf + 1] - g0, D = m->dim;
   std::vector<float> miv((size_t)ng * D), iv((size_t)ng * D), gc(ng), w(ng, 1.0f);
@@ -118,7 +119,7 @@ khg_status gsel_shadow(khg_model *m, int32_t pdf, khg_model **out) {
   // a zero-weight Gaussian (gconst = -inf) is a legitimate, never-selected candidate here, not
   // the "all components dead" pdf that makes LogLikelihood throw
   s->tc.dead_pdf = false;
-  if (m->stream) s->stream = m->stream;
+  s->stream = m->stream;
   m->gsel_shadow = s;
   m->gsel_pdf = pdf;
   *out = s;

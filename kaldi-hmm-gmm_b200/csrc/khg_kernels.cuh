@@ -292,7 +292,7 @@ __global__ void prep_keys_kernel(const int32_t *__restrict__ ids, int64_t n, int
   int32_t k = ids[i];
   if (k < 0 || k >= P) {  // AccumulateForGmm asserts the range (csrc/mle-am-diag-gmm.cc:44)
     atomicOr(err, ERR_BAD_INDEX);
-    k = 0;
+    k = P;  // sentinel bucket that no work item covers: the frame contributes nothing, as in stats_direct_kernel
   }
   keys[i] = k;
   vals[i] = (int32_t)i;
