@@ -115,6 +115,11 @@ struct TcPack {
   bool grouped_segs = false;     // some tile has a group of short pdfs read by one load (epi_run_multi)
   bool two_chunk_segs = false;   // some pdf has 17..32 Gaussians: the epilogue's two-load segment form is in use
   bool dead_pdf = false;         // some pdf has only -inf gconsts: every call must fail like the reference
+  // Gaussian-stationary kernel (khg_loglikes_gs.cu): the split feature operand A' of the current block
+  // of frames, a_rows x KPB16 fp16, and its TMA map (box 64 columns x 128 rows)
+  Buf a_scr;
+  int64_t a_rows = 0;
+  CUtensorMap amap;
 };
 
 }  // namespace khg
@@ -174,6 +179,12 @@ bool tc_supported(const khg_model *m);
 khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale,
                        float *d_out, int64_t ld_out, int precision, const unsigned **simt_gate,
                        float *gate_limit);
+// khg_loglikes_gs.cu: the Gaussian-stationary form of the fp16-split kernel (model tile resident in shared
+// memory, pre-split feature operand streamed); `fallback` is launched behind every gated sub-block
+bool gs_supported(const khg_model *m);
+void gs_free(khg_model *m);
+khg_status gs_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t ld_out, bool gated,
+                       khg_status (*fallback)(khg_model *, const float *, int64_t, float, float *, int64_t, const unsigned *));
 // khg_b200.cu: the dense all-pdf block of device-resident frames (kernel choice of the model),
 // and the synchronising read of the latched device error flag
 khg_status dense_block(khg_model *m, const float *d_feats, int64_t T, float scale, int layout, float *d_out, int64_t ld);
