@@ -59,58 +59,157 @@ class _Token:
         self.arc, self.prev, self.cost = arc, prev, cost
 
 
+class _Elem:
+    __slots__ = ("key", "val", "tail")
+
+    def __init__(self, key, val):
+        self.key, self.val, self.tail = key, val, None
+
+
+class _HashList:
+    """csrc/hash-list-inl.h restated: the token container of FasterDecoder.  What matters for parity
+    is the ORDER in which ProcessEmitting / ProcessNonemitting / GetCutoff walk the tokens — the
+    running `next_weight_cutoff` of ProcessEmitting (faster-decoder.cc:196-216) makes the set of
+    surviving tokens depend on it.  The list is the concatenation of the occupied buckets in the
+    order they were first occupied; inside a bucket, elements are in insertion order (:128-170).
+    bucket = key % hash_size (:133); the size only ever grows (faster-decoder.cc:322-329,
+    PossiblyResizeHash) from the constructor's 1000 (:29)."""
+
+    def __init__(self):
+        self.hash_size = 0
+        self.head = None
+        self.bucket_tail = -1
+        self.buckets = {}  # index -> [prev_bucket, last_elem]; only occupied buckets are present
+
+    def set_size(self, size: int):  # :26-35
+        assert self.head is None and self.bucket_tail == -1
+        self.hash_size = size
+
+    def size(self) -> int:
+        return self.hash_size
+
+    def clear(self):  # :37-51: hands the list to the caller
+        self.buckets = {}
+        self.bucket_tail = -1
+        head, self.head = self.head, None
+        out = []
+        while head is not None:
+            out.append(head)
+            head = head.tail
+        return out
+
+    def elems(self):  # GetList()
+        e = self.head
+        while e is not None:
+            yield e
+            e = e.tail
+
+    def _bucket_range(self, b):
+        prev_bucket, last = b
+        head = self.head if prev_bucket == -1 else self.buckets[prev_bucket][1].tail
+        return head, last.tail
+
+    def find(self, key):  # :62-82
+        b = self.buckets.get(key % self.hash_size)
+        if b is None:
+            return None
+        e, stop = self._bucket_range(b)
+        while e is not stop:
+            if e.key == key:
+                return e
+            e = e.tail
+        return None
+
+    def insert(self, key, val):  # :128-170: returns the existing element or the new one
+        index = key % self.hash_size
+        b = self.buckets.get(index)
+        if b is not None:
+            e, stop = self._bucket_range(b)
+            while e is not stop:
+                if e.key == key:
+                    return e
+                e = e.tail
+        elem = _Elem(key, val)
+        if b is None:  # unoccupied bucket: appended to the chain of buckets = to the end of the list
+            if self.bucket_tail == -1:
+                self.head = elem
+            else:
+                self.buckets[self.bucket_tail][1].tail = elem
+            elem.tail = None
+            self.buckets[index] = [self.bucket_tail, elem]
+            self.bucket_tail = index
+        else:  # occupied bucket: after its last element, i.e. possibly in the MIDDLE of the list
+            elem.tail = b[1].tail
+            b[1].tail = elem
+            b[1] = elem
+        return elem
+
+
 class FasterDecoderOracle:
     """faster-decoder.cc with the option defaults AlignUtteranceWrapper leaves in place
-    (faster-decoder.h:41-43): max_active = int max, min_active = 20, beam_delta = 0.5."""
+    (faster-decoder.h:41-43): max_active = int max, min_active = 20, beam_delta = 0.5, hash_ratio = 2."""
 
-    def __init__(self, g: Graph, beam: float, min_active: int = 20, beam_delta: float = 0.5, tight: bool = False):
-        """tight=False: the reference's order-dependent running `next_weight_cutoff` (tokens are visited
-        in dict insertion order, standing in for the HashList order, which is not specified either).
-        tight=True: the order-independent rule the device kernel implements — a new token survives
-        iff its cost < (lowest new cost of the frame) + adaptive_beam, i.e. the FINAL value of
-        next_weight_cutoff; tokens are visited by state id so that ties go to the lowest arc id.  The
-        reference keeps a superset of these tokens for one frame; the extra ones are above the next
-        frame's beam cutoff."""
+    def __init__(self, g: Graph, beam: float, min_active: int = 20, beam_delta: float = 0.5, tight: bool = False,
+                 hash_ratio: float = 2.0):
+        """tight=False: the reference's rule exactly — the order-dependent running `next_weight_cutoff`, tokens
+        visited in the HashList's order (restated above), the hash size growing as PossiblyResizeHash does.
+        tight=True: the order-independent rule of the device kernel's fast path — a new token survives iff its
+        cost < (lowest new cost of the frame) + adaptive_beam, i.e. the FINAL value of next_weight_cutoff;
+        tokens are visited by state id so that ties go to the lowest arc id.  The reference keeps a superset
+        of these tokens for one frame; the extra ones are above the next frame's beam cutoff."""
         self.g, self.beam, self.min_active, self.beam_delta = g, float(F32(beam)), min_active, float(F32(beam_delta))
         self.tight = tight
-        self.toks = {}  # state -> token, insertion ordered like the hash list
+        self.hash_ratio = float(F32(hash_ratio))
+        self.hl = _HashList()
+        self.hl.set_size(1000)  # faster-decoder.cc:29
         self.frames = 0
+        self.max_extra = 0      # diagnostics: most tokens kept above the final cutoff in one frame (tight=False)
+
+    def set_beam(self, beam: float):  # SetOptions, decoder-wrappers.cc:61-63
+        self.beam = float(F32(beam))
+
+    @property
+    def toks(self):
+        """state -> token in the container's order."""
+        return {e.key: e.val for e in self.hl.elems()}
 
     # --- faster-decoder.cc:36-49
     def init_decoding(self):
-        self.toks = {self.g.start: _Token(-1, None, 0.0)}
+        self.hl.clear()
+        self.hl.insert(self.g.start, _Token(-1, None, 0.0))
         self._process_nonemitting(float(np.finfo(np.float32).max))
         self.frames = 0
 
     # --- faster-decoder.cc:51-123
     def _process_nonemitting(self, cutoff: float):
         g = self.g
-        queue = list(self.toks.keys())
+        queue = list(self.hl.elems())
         while queue:
-            state = queue.pop()
-            tok = self.toks[state]
+            e = queue.pop()
+            state, tok = e.key, e.val
             if tok.cost > cutoff:
                 continue
             for a in range(g.arc_offsets[state], g.arc_offsets[state + 1]):
                 if g.ilabel[a] != 0:
                     continue
-                cost = tok.cost + float(g.weight[a])  # faster-decoder.h:128-137
-                if cost > cutoff:
+                new = _Token(a, tok, tok.cost + float(g.weight[a]))  # faster-decoder.h:128-137
+                if new.cost > cutoff:
                     continue
-                ns = int(g.nextstate[a])
-                old = self.toks.get(ns)
-                if old is None or old.cost > cost:  # *(e_found->val) < *new_tok
-                    self.toks[ns] = _Token(a, tok, cost)
-                    queue.append(ns)
+                found = self.hl.insert(int(g.nextstate[a]), new)
+                if found.val is new:
+                    queue.append(found)
+                elif found.val.cost > new.cost:  # *(e_found->val) < *new_tok
+                    found.val = new
+                    queue.append(found)
 
     # --- faster-decoder.cc:230-335 (max_active = int max)
-    def _get_cutoff(self, toks) -> Tuple[float, float, Optional[int]]:
-        best, best_state = INF, None
+    def _get_cutoff(self, elems) -> Tuple[float, float, Optional[_Elem]]:
+        best, best_elem = INF, None
         costs = []
-        for s, t in toks.items():
-            costs.append(t.cost)
-            if t.cost < best:
-                best, best_state = t.cost, s
+        for e in elems:
+            costs.append(e.val.cost)
+            if e.val.cost < best:
+                best, best_elem = e.val.cost, e
         beam_cutoff = best + self.beam
         min_active_cutoff = INF
         if len(costs) > self.min_active:
@@ -121,65 +220,61 @@ class FasterDecoderOracle:
                 arr = np.sort(np.asarray(costs, dtype=np.float32))
                 min_active_cutoff = float(arr[self.min_active])
         if min_active_cutoff > beam_cutoff:
-            return min_active_cutoff, float(F32(min_active_cutoff - best + self.beam_delta)), best_state
-        return beam_cutoff, self.beam, best_state
+            return min_active_cutoff, float(F32(min_active_cutoff - best + self.beam_delta)), best_elem
+        return beam_cutoff, self.beam, best_elem
 
     # --- faster-decoder.cc:154-228
     def _process_emitting(self, loglike) -> float:
         g = self.g
         frame = self.frames
-        last = self.toks
-        self.toks = {}
-        weight_cutoff, adaptive_beam, best_state = self._get_cutoff(last)
+        last = self.hl.clear()
+        weight_cutoff, adaptive_beam, best_elem = self._get_cutoff(last)
+        new_sz = int(F32(F32(len(last)) * F32(self.hash_ratio)))  # PossiblyResizeHash, :322-329
+        if new_sz > self.hl.size():
+            self.hl.set_size(new_sz)
         next_cutoff = INF
-        if self.tight:
-            for state in sorted(last):
-                tok = last[state]
-                if tok.cost < weight_cutoff:
-                    for a in range(g.arc_offsets[state], g.arc_offsets[state + 1]):
-                        if g.ilabel[a] != 0:
-                            ac = float(F32(-1) * F32(loglike(frame, int(g.ilabel[a]))))
-                            nw = float(g.weight[a]) + tok.cost + ac
-                            next_cutoff = min(next_cutoff, nw + adaptive_beam)
-            for state in sorted(last):
-                tok = last[state]
-                if tok.cost < weight_cutoff:
-                    for a in range(g.arc_offsets[state], g.arc_offsets[state + 1]):
-                        if g.ilabel[a] == 0:
-                            continue
-                        ac = float(F32(-1) * F32(loglike(frame, int(g.ilabel[a]))))
-                        nw = float(g.weight[a]) + tok.cost + ac
-                        if nw < next_cutoff:
-                            ns = int(g.nextstate[a])
-                            old = self.toks.get(ns)
-                            if old is None or old.cost > nw:
-                                self.toks[ns] = _Token(a, tok, nw)
-            self.frames += 1
-            return next_cutoff
-        if best_state is not None:
-            tok = last[best_state]
-            for a in range(g.arc_offsets[best_state], g.arc_offsets[best_state + 1]):
+
+        def arcs_of(state):
+            for a in range(g.arc_offsets[state], g.arc_offsets[state + 1]):
                 if g.ilabel[a] != 0:
                     ac = float(F32(-1) * F32(loglike(frame, int(g.ilabel[a]))))
-                    nw = float(g.weight[a]) + tok.cost + ac
-                    if nw + adaptive_beam < next_cutoff:
-                        next_cutoff = nw + adaptive_beam
-        for state, tok in last.items():
+                    yield a, ac
+
+        if self.tight:
+            for e in last:
+                if e.val.cost < weight_cutoff:
+                    for a, ac in arcs_of(e.key):
+                        next_cutoff = min(next_cutoff, float(g.weight[a]) + e.val.cost + ac + adaptive_beam)
+            for e in sorted(last, key=lambda x: x.key):
+                tok = e.val
+                if tok.cost < weight_cutoff:
+                    for a, ac in arcs_of(e.key):
+                        nw = float(g.weight[a]) + tok.cost + ac
+                        if nw < next_cutoff:
+                            found = self.hl.insert(int(g.nextstate[a]), None)
+                            if found.val is None or found.val.cost > nw:
+                                found.val = _Token(a, tok, nw)
+            self.frames += 1
+            return next_cutoff
+        if best_elem is not None:  # :177-190: the best token first, for a tight bound
+            for a, ac in arcs_of(best_elem.key):
+                nw = float(g.weight[a]) + best_elem.val.cost + ac
+                if nw + adaptive_beam < next_cutoff:
+                    next_cutoff = nw + adaptive_beam
+        for e in last:  # :197-225
+            tok = e.val
             if tok.cost < weight_cutoff:
-                for a in range(g.arc_offsets[state], g.arc_offsets[state + 1]):
-                    if g.ilabel[a] == 0:
-                        continue
-                    ac = float(F32(-1) * F32(loglike(frame, int(g.ilabel[a]))))
+                for a, ac in arcs_of(e.key):
                     nw = float(g.weight[a]) + tok.cost + ac
                     if nw < next_cutoff:
                         # Token(arc, ac_cost, prev): cost_ = prev->cost_ + weight + ac_cost
                         new = _Token(a, tok, tok.cost + float(g.weight[a]) + ac)
+                        found = self.hl.insert(int(g.nextstate[a]), new)
                         if nw + adaptive_beam < next_cutoff:
                             next_cutoff = nw + adaptive_beam
-                        ns = int(g.nextstate[a])
-                        old = self.toks.get(ns)
-                        if old is None or old.cost > new.cost:
-                            self.toks[ns] = new
+                        if found.val is not new and found.val.cost > new.cost:
+                            found.val = new
+        self.max_extra = max(self.max_extra, sum(1 for e in self.hl.elems() if e.val.cost >= next_cutoff))
         self.frames += 1
         return next_cutoff
 
@@ -191,7 +286,7 @@ class FasterDecoderOracle:
 
     # --- faster-decoder.cc:346-354
     def reached_final(self) -> bool:
-        return any(t.cost != INF and self.g.final[s] != INF for s, t in self.toks.items())
+        return any(e.val.cost != INF and self.g.final[e.key] != INF for e in self.hl.elems())
 
     # --- faster-decoder.cc:356-425
     def best_path(self):
@@ -200,15 +295,15 @@ class FasterDecoderOracle:
         best_tok, best_state = None, None
         is_final = self.reached_final()
         if not is_final:
-            for s, t in self.toks.items():
-                if best_tok is None or best_tok.cost > t.cost:
-                    best_tok, best_state = t, s
+            for e in self.hl.elems():
+                if best_tok is None or best_tok.cost > e.val.cost:
+                    best_tok, best_state = e.val, e.key
         else:
             best = INF
-            for s, t in self.toks.items():
-                c = t.cost + float(g.final[s])
+            for e in self.hl.elems():
+                c = e.val.cost + float(g.final[e.key])
                 if c < best and c != INF:
-                    best, best_tok, best_state = c, t, s
+                    best, best_tok, best_state = c, e.val, e.key
         if best_tok is None:
             return None
         arcs, graph, ac = [], F32(0), F32(0)
@@ -246,7 +341,7 @@ def align_utterance(g: Graph, loglikes_pdf_major: np.ndarray, tid2pdf: np.ndarra
     ok = dec.reached_final()
     if not ok and retry_beam != 0:
         status = 1
-        dec = FasterDecoderOracle(g, retry_beam, tight=tight)
+        dec.set_beam(retry_beam)  # the same decoder object: its hash keeps the size it grew to
         dec.decode(T, loglike)
         ok = dec.reached_final()
     if not ok:
@@ -255,7 +350,7 @@ def align_utterance(g: Graph, loglikes_pdf_major: np.ndarray, tid2pdf: np.ndarra
     ali = [int(g.ilabel[a]) for a in arcs if g.ilabel[a] != 0]
     words = [int(g.olabel[a]) for a in arcs if g.olabel[a] != 0]
     like = -(graph + ac) / float(acoustic_scale)
-    return dict(status=status, alignment=ali, words=words, like=like, path=arcs)
+    return dict(status=status, alignment=ali, words=words, like=like, path=arcs, max_extra=dec.max_extra)
 
 
 def brute_force_best(g: Graph, loglikes_pdf_major: np.ndarray, tid2pdf: np.ndarray, acoustic_scale: float):
