@@ -326,6 +326,23 @@ khg_status khg_align_batch(khg_model *m, const khg_graph_batch *graphs, const fl
                            int32_t *path_arcs, int64_t *path_offsets, int64_t path_capacity,
                            int32_t *pdf_ids_dev);
 
+/* The reference's FasterDecoder + AlignUtteranceWrapper on the HOST for ONE utterance of a graph batch,
+ * consuming a block of log-likelihoods computed elsewhere (the GPU): csrc/faster-decoder.cc:36-425 with
+ * its token container's visiting order (csrc/hash-list-inl.h:26-170: buckets in order of first use,
+ * key % hash_size, the hash growing as PossiblyResizeHash does), i.e. including the order-dependent
+ * running next_weight_cutoff of ProcessEmitting (:196-216) — the exact reference rule.  khg_align_batch
+ * uses it for the utterances whose device search cannot be proven equal to it; no GPU is needed.
+ *   loglikes  HOST float, rows x ld: SCALED log-likelihoods, row tid2row[tid] = the row of tid's pdf,
+ *             column t = frame t of this utterance (what DecodableAmDiagGmmScaled::LogLikelihood(t, tid)
+ *             returns, csrc/decodable-am-diag-gmm.h:94-98)
+ *   tid2row   HOST int32[n_tids] (index 0 unused)
+ * Outputs (HOST): alignment int32[T]; *status KHG_ALIGN_*; *like = -(graph + acoustic cost) /
+ * acoustic_scale; path_arcs (absolute arc ids incl. epsilons, path_capacity entries) / *path_len may be NULL. */
+khg_status khg_align_utterance_host(const khg_graph_batch *graphs, int32_t utt, const float *loglikes, int64_t ld,
+                                    const int32_t *tid2row, int32_t n_tids, float acoustic_scale, float beam,
+                                    float retry_beam, int32_t *alignment, int32_t *status, float *like,
+                                    int32_t *path_arcs, int32_t path_capacity, int32_t *path_len);
+
 /* ------------------------------------------------------------------ mix-up --
  * AmDiagGmm::SplitByCount (csrc/am-diag-gmm.cc:72-89) on the packed device model: the per-pdf
  * targets of GetSplitTargets (csrc/model-common.cc:29-70; state_occs = HOST float[num_pdfs],

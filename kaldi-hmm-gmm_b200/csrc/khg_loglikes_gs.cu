@@ -101,6 +101,7 @@ struct GsArgs {
   int64_t ld;
   float *scratch;          // one device word: store target of rows beyond T
   int *err;
+  int rotate;              // 1: the epilogue groups swap their pdf lists from frame tile to frame tile (load balance)
   int debug_mode;          // experiments (KHG_EXPERIMENTS builds only)
 };
 
@@ -158,6 +159,10 @@ loglikes_gs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   auto acc_empty = [&](uint32_t b) { return sBar + 8u * (2 * kGsMaxStages + 4 + b); };
   const uint32_t tmem_slot = sBar + 8u * (2 * kGsMaxStages + 6);
   volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + (tmem_slot - base));
+  // per segment: the kEpiGroups pdf lists of the model tile {seg start, first run, runs, first two descriptors,
+  // first run word}, so that a frame tile starts from one shared-memory read instead of three dependent global loads
+  struct EpiRole { uint32_t seg0, run0, nr, d0, d1, runw, pad0, pad1; };
+  EpiRole *roles = reinterpret_cast<EpiRole *>(base_ptr + (sBar + 8u * (2 * kGsMaxStages + 8) - base));
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -285,9 +290,22 @@ loglikes_gs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     GsSegIter it(a.n_tiles, a.n_ft);
     int j, f0, f1;
     while (it.next(j, f0, f1)) {
-      const int2 h = __ldg(a.epi_hdr + (size_t)kEpiGroups * j + eg);
-      const uint32_t *rp0 = a.runs + (h.y & 0xffffff);
-      const int nr0 = (int)((uint32_t)h.y >> 24);
+      // (re)build the role table of this model tile: all epilogue warps have left the previous segment
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      if (threadIdx.x < kEpiGroups) {
+        const int2 h = __ldg(a.epi_hdr + (size_t)kEpiGroups * j + threadIdx.x);
+        EpiRole r;
+        r.seg0 = (uint32_t)h.x;
+        r.run0 = (uint32_t)h.y & 0xffffffu;
+        r.nr = (uint32_t)h.y >> 24;
+        r.d0 = __ldg(a.seg + r.seg0);  // (a sentinel when the list is empty)
+        r.d1 = __ldg(a.seg + r.seg0 + 1);
+        r.runw = __ldg(a.runs + r.run0);
+        r.pad0 = r.pad1 = 0;
+        roles[threadIdx.x] = r;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      uint32_t role = a.rotate ? (uint32_t)(eg + f0) % kEpiGroups : (uint32_t)eg;
       for (int f = f0; f < f1; ++f, ++acc_it) {
         const int buf = acc_it & 1;
         const int64_t t = (int64_t)f * kTileM + row;
@@ -303,12 +321,14 @@ loglikes_gs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         e.ld_bytes = valid ? (uint32_t)(a.ld * 4) : 0u;
 #endif
         e.nan_acc = 0.f;
-        const uint32_t *rp = rp0;
-        int nr = nr0;
-        e.sp = a.seg + h.x;
-        e.d = __ldg(e.sp);  // (a sentinel when the list is empty)
-        e.dn = __ldg(e.sp + 1);
-        uint32_t run = __ldg(rp);
+        const EpiRole r = roles[role];
+        if (a.rotate && ++role == (uint32_t)kEpiGroups) role = 0;
+        const uint32_t *rp = a.runs + r.run0;
+        int nr = (int)r.nr;
+        e.sp = a.seg + r.seg0;
+        e.d = r.d0;
+        e.dn = r.d1;
+        uint32_t run = r.runw;
         mbar_wait(acc_full(buf), (acc_it >> 1) & 1);
         tc_fence_after();
         e.trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256;
@@ -466,6 +486,8 @@ static khg_status gs_launch(khg_model *m, const float *d_feats, int64_t T, float
   a.ld = ld_out;
   a.scratch = reinterpret_cast<float *>(m->d_scratch_int + 3);
   a.err = m->d_err;
+  a.rotate = 1;
+  if (const char *e = getenv("KHG_GS_ROTATE")) a.rotate = atoi(e) != 0;  // experiments
   a.debug_mode = 0;
 #ifdef KHG_EXPERIMENTS
   if (const char *dbg = getenv("KHG_TC_DEBUG_MODE")) a.debug_mode = atoi(dbg);
@@ -474,7 +496,7 @@ static khg_status gs_launch(khg_model *m, const float *d_feats, int64_t T, float
     set_error("ld_out too large for the tensor-core kernel (needs ld_out < 2^30)");
     return KHG_ERR_UNSUPPORTED;
   }
-  const size_t smem = (size_t)b_bytes + (size_t)a.stages * kAChunkBytes + 512 + 1024;
+  const size_t smem = (size_t)b_bytes + (size_t)a.stages * kAChunkBytes + 512 + 1024;  // (512: barriers + the role table)
   auto kern = t.two_chunk_segs ? (t.grouped_segs ? loglikes_gs_kernel<true, true> : loglikes_gs_kernel<true, false>)
                                : (t.grouped_segs ? loglikes_gs_kernel<false, true> : loglikes_gs_kernel<false, false>);
   KHG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  // (per device; cheap)

@@ -10,7 +10,7 @@ Layers (bottom up):
 There is no CPU fallback anywhere in this package.
 """
 from . import _cabi  # noqa: F401
-from .device import DeviceModel, DeviceStats, GraphBatch, align_batch  # noqa: F401
+from .device import DeviceModel, DeviceStats, GraphBatch, align_batch, align_utterance_host  # noqa: F401
 
 try:  # the pybind11 mirror of the reference classes (built by __graft_entry__.build())
     from ._khg_b200 import *  # noqa: F401,F403

@@ -271,6 +271,26 @@ def align_batch(model: DeviceModel, graphs: GraphBatch, feats, tid2pdf, acoustic
     return out
 
 
+def align_utterance_host(graphs: GraphBatch, utt: int, loglikes, tid2row, acoustic_scale: float = 1.0, beam: float = 200.0,
+                         retry_beam: float = 0.0):
+    """The reference's FasterDecoder + AlignUtteranceWrapper on the host for utterance `utt`, on a (rows, T) block
+    of SCALED log-likelihoods (khg_align_utterance_host; needs no GPU).  Returns dict(status, alignment, like, path)."""
+    ll = np.ascontiguousarray(loglikes, np.float32)
+    t2r = np.ascontiguousarray(tid2row, np.int32)
+    T = int(graphs.frame_offsets[utt + 1] - graphs.frame_offsets[utt])
+    assert ll.ndim == 2 and ll.shape[1] >= T
+    ali = np.zeros(T, np.int32)
+    n_arcs_u = int(graphs.arc_offsets[graphs.state_offsets[utt + 1]] - graphs.arc_offsets[graphs.state_offsets[utt]])
+    cap = T + n_arcs_u + 16
+    path = np.zeros(cap, np.int32)
+    status, like, plen = C.c_int32(), C.c_float(), C.c_int32()
+    gs = graphs.c_struct()
+    A.check(A.lib().khg_align_utterance_host(C.byref(gs), utt, ll.ctypes.data, ll.shape[1], t2r.ctypes.data, t2r.size, acoustic_scale,
+                                             beam, retry_beam, ali.ctypes.data, C.byref(status), C.byref(like), path.ctypes.data, cap,
+                                             C.byref(plen)))
+    return dict(status=status.value, alignment=ali, like=like.value, path=path[:plen.value])
+
+
 class DeviceStats:
     """Packed device AccumAmDiagGmm: [occ G | mean G*D | var G*D | tot_like, tot_frames] fp64."""
 

@@ -98,3 +98,67 @@ def test_zero_frames_and_empty_graph():
     assert r["status"] == 2  # start is not final in these graphs
     g.start = -1
     assert ao.align_utterance(g, ll, t2p, 1.0)["status"] == 2
+
+
+# ---------------------------------------------------------------------------------------------
+# The C++ restatement of the same decoder inside libkhg_b200.so (khg_align_utterance_host: the
+# exact host path of khg_align_batch) against the Python oracle with the reference's rule
+# (tight=False).  Host code only: runs without a GPU.
+def _host_align(g, ll, t2p, scale, beam, retry):
+    from kaldi_hmm_gmm_b200 import GraphBatch, align_utterance_host
+
+    gb = GraphBatch([g], [ll.shape[1]])
+    scaled = (np.float32(scale) * ll).astype(np.float32)  # decodable-am-diag-gmm.h:94-98, fp32 product
+    return align_utterance_host(gb, 0, scaled, t2p, scale, beam, retry)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_host_exact_decoder_equals_reference_rule_oracle(seed):
+    """Recipe beams (egs/yesno/train.py:165-167: 6 / 40, and 10 / 40) on data with a dominant path, plus
+    flat random likelihoods where many tokens compete: alignment, status and best path bit-exact, like
+    to float rounding — including the utterances where the reference keeps tokens above the final cutoff."""
+    if seed % 2 == 0:
+        g, t2p, ll = _realistic_case(300 + seed, n_phones=12)
+    else:
+        g, t2p, ll = _case(400 + seed, n_phones=9, T_extra=15)
+    for scale, beam, retry in ((1.0, 6.0, 40.0), (0.7, 10.0, 40.0), (1.0, 2.0, 0.0), (1.0, 1e4, 0.0)):
+        ref = ao.align_utterance(g, ll, t2p, scale, beam=beam, retry_beam=retry, tight=False)
+        got = _host_align(g, ll, t2p, scale, beam, retry)
+        assert got["status"] == ref["status"], (seed, beam)
+        if ref["status"] == 2:
+            assert not got["alignment"].any() and got["like"] == 0.0 and got["path"].size == 0
+        else:
+            assert got["alignment"].tolist() == ref["alignment"], (seed, beam)
+            assert got["path"].tolist() == ref["path"], (seed, beam)
+            assert abs(got["like"] - ref["like"]) <= 1e-5 * abs(ref["like"]) + 1e-4
+
+
+def test_host_exact_decoder_hash_collisions_change_the_visiting_order():
+    """More than 1000 states: state ids collide modulo the initial hash size (faster-decoder.cc:29), so the
+    token list is no longer in insertion order (hash-list-inl.h:160-168).  Still bit-exact with the oracle's
+    restatement of the container — and the container order is exercised (some bucket holds two states)."""
+    rng = np.random.default_rng(77)
+    phones = [int(x) for x in rng.integers(1, 9, 360)]  # ~1100+ states, no silence skips
+    g, n_tids = ao.make_training_graph(rng, phones, alt_prob=0.1)
+    assert g.num_states > 1100
+    P = 23
+    t2p = ao.make_tid2pdf(n_tids, P)
+    T = 5 * len(phones)
+    ll = (-6.0 * rng.random((P, T)) - 1.0).astype(np.float32)
+    statuses = []
+    for beam, retry in ((4.0, 60.0), (12.0, 400.0), (30.0, 0.0)):
+        ref = ao.align_utterance(g, ll, t2p, 1.0, beam=beam, retry_beam=retry, tight=False)
+        got = _host_align(g, ll, t2p, 1.0, beam, retry)
+        assert got["status"] == ref["status"]
+        statuses.append(ref["status"])
+        if ref["status"] != 2:
+            assert got["alignment"].tolist() == ref["alignment"] and got["path"].tolist() == ref["path"]
+    assert min(statuses) < 2, statuses
+
+
+def test_host_exact_decoder_errors():
+    g, t2p, ll = _case(3)
+    with pytest.raises(RuntimeError, match="Beams do not make sense"):
+        _host_align(g, ll, t2p, 1.0, 10.0, 5.0)
+    g.start = -1
+    assert _host_align(g, ll, t2p, 1.0, 10.0, 40.0)["status"] == 2
