@@ -69,11 +69,16 @@ enum {
   KHG_KERNEL_AUTO = 0,
   KHG_KERNEL_SIMT = 1,       /* fp32 FMA kernel (any dim, any pdf size) */
   KHG_KERNEL_TCGEN05 = 2,    /* tcgen05 kernel, 3xTF32 split (hi/lo tf32 operands) */
-  KHG_KERNEL_TCGEN05_F16 = 3 /* tcgen05 kernel, 3xFP16 split: same 22-bit split precision at
+  KHG_KERNEL_TCGEN05_F16 = 3, /* tcgen05 kernel, 3xFP16 split: same 22-bit split precision at
                                 twice the tensor rate; needs model and features in fp16 range
                                 after a per-dimension power-of-two scaling.  AUTO uses it when
                                 the model fits and, decided on the device for every call, the
                                 features fit; otherwise the 3xTF32 split runs. */
+  KHG_KERNEL_TCGEN05_F16_GS = 4 /* the same 3xFP16 arithmetic, Gaussian-stationary form: a 240-Gaussian model
+                                tile stays in shared memory and the pre-split feature operand is streamed
+                                (half the operand bytes per MMA; needs 2*dim+2 <= 128).  Same results; not
+                                faster than 3 on B200, where the path is power-bound in the tensor pipe
+                                 — kept selectable, never chosen by AUTO. */
 };
 
 typedef struct khg_model khg_model; /* device-resident packed AmDiagGmm      */
@@ -107,7 +112,7 @@ khg_status khg_model_get_gconsts(khg_model *m, float *gconsts /* host, G */);
 khg_status khg_model_info(const khg_model *m, int32_t *dim, int32_t *num_pdfs,
                           int32_t *num_gauss);
 /* Which dense kernel an in-range call will run with the current choice: KHG_KERNEL_SIMT,
- * KHG_KERNEL_TCGEN05 or KHG_KERNEL_TCGEN05_F16 (AUTO resolved against this model). */
+ * KHG_KERNEL_TCGEN05, KHG_KERNEL_TCGEN05_F16 or KHG_KERNEL_TCGEN05_F16_GS (AUTO resolved against this model). */
 khg_status khg_model_dense_kernel(const khg_model *m, int32_t *kernel);
 /* Chooses the dense-likelihood kernel (default KHG_KERNEL_AUTO). */
 khg_status khg_model_set_kernel(khg_model *m, int32_t kernel);
@@ -280,14 +285,18 @@ khg_status khg_model_download(khg_model *m, int32_t *gauss_offsets, float *weigh
  * the decoder options the wrapper leaves at their defaults (max_active = int max,
  * min_active = 20, beam_delta = 0.5, csrc/faster-decoder.h:41-43).
  *
- * The search is the reference's frame-synchronous token passing restated as a pull-style
+ * The device search is the reference's frame-synchronous token passing restated as a pull-style
  * dynamic programme (one CTA per utterance, one token per graph state, costs in double like
  * Token::cost_): a state is expanded at frame t iff its cost < best_t + beam (or inside the
- * min_active cutoff), exactly the reference's rule; among equal-cost predecessors the arc with
- * the lowest index wins (the reference keeps whichever token its hash list met first, so
- * results can differ only on exact ties).  The reference's running "next_weight_cutoff" can
- * additionally keep tokens above the final cutoff alive for one frame; they are never expanded
- * and can matter only when no in-beam token is final.
+ * min_active cutoff), exactly the reference's rule.  Two things in the reference depend on the ORDER
+ * of its token list (csrc/hash-list-inl.h): which token survives an exact cost tie, and — through the
+ * running next_weight_cutoff of ProcessEmitting (csrc/faster-decoder.cc:196-216) — which tokens above
+ * the frame's final cutoff are kept alive for one more frame.  The device search checks, frame by
+ * frame, a certificate that neither can have influenced the result (khg_align.cu); the utterances for
+ * which it cannot are re-aligned inside the same call by khg_align_utterance_host below, the exact
+ * restatement of the reference's decoder, on the same likelihood block.  So every returned alignment
+ * is the reference's, given the likelihoods.  KHG_ALIGN_EXACT=all / none (environment) sends every /
+ * no utterance through the host decoder.
  *
  * Graphs: the compiled training graphs (fst::VectorFst<StdArc>, after AddTransitionProbs) as
  * plain arrays, all utterances concatenated.  States and arcs use LOCAL state ids per
@@ -325,6 +334,10 @@ khg_status khg_align_batch(khg_model *m, const khg_graph_batch *graphs, const fl
                            int32_t *alignment, int32_t *utt_status, float *utt_like,
                            int32_t *path_arcs, int64_t *path_offsets, int64_t path_capacity,
                            int32_t *pdf_ids_dev);
+
+/* Utterances of the most recent khg_align_batch call (this process) that were re-aligned by the exact
+ * host decoder below because the device search could not certify its result (diagnostics). */
+int64_t khg_align_last_exact_count(void);
 
 /* The reference's FasterDecoder + AlignUtteranceWrapper on the HOST for ONE utterance of a graph batch,
  * consuming a block of log-likelihoods computed elsewhere (the GPU): csrc/faster-decoder.cc:36-425 with

@@ -15,6 +15,22 @@
 // passing becomes a pull over each state's incoming arcs (the host transposes every graph
 // once), so there are no atomics and ties are broken by the lowest arc id.  Back-pointers
 // (one int32 arc id per (frame, state)) go to HBM, coalesced; thread 0 walks them back.
+//
+// Exactness.  The reference prunes new tokens against a RUNNING next_weight_cutoff while it walks its
+// token list (faster-decoder.cc:196-216), so for one frame it can keep tokens above the frame's final
+// cutoff — which ones depends on the list order (hash-list-inl.h).  The device search applies the final
+// cutoff (order-independent) and, per frame, checks a certificate that those extra tokens cannot exist
+// or cannot matter:
+//   * a token can only be "extra" if its cost lies in [final cutoff, c0), c0 = the bound the reference
+//     gets from expanding its best token first (:177-190); x_min = the cheapest such candidate;
+//   * extras are never cheaper than any kept token, so with more than min_active kept tokens GetCutoff
+//     (:230-320) returns the same cutoffs; they are expanded on the next frame only if x_min < that
+//     frame's weight_cutoff; with <= min_active kept tokens they could change the token count or be
+//     expanded (the cutoff is +inf then), and on the last frame they could be the best final token.
+// An utterance for which any of these cannot be ruled out — or that has an exact cost tie between
+// competing predecessors / final states (the reference then keeps whichever its list order met first), or
+// a negative epsilon weight — is FLAGGED and re-aligned by the exact host restatement of the reference
+// (khg_align_exact.cu) on the same likelihood block.  Everything else is provably the reference's result.
 #include <algorithm>
 #include <cfloat>
 #include <chrono>
@@ -65,12 +81,14 @@ struct UttOut {
   int32_t pad2[3];
 };
 
+int64_t g_align_exact_utts = 0;           // utterances of the last khg_align_batch call that took the exact host pass
 constexpr int kAlignMinActive = 20;       // faster-decoder.h:42
 constexpr float kAlignBeamDelta = 0.5f;   // faster-decoder.h:43
 constexpr int kMaxWarps = 16;
 
 struct RedScratch {
   double v[2][kMaxWarps];
+  double v2[2][kMaxWarps];
   int n[2][kMaxWarps];
   int s[2][kMaxWarps];
 };
@@ -83,23 +101,32 @@ __device__ __forceinline__ unsigned long long cost_key(double v) {
 __device__ __forceinline__ double key_cost(unsigned long long k) {
   return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
 }
-// (min, sum) over the CTA; one __syncthreads per call (two alternating slots).  Warp stage: the
+// (min, min, sum) over the CTA; one __syncthreads per call (two alternating slots).  Warp stage: the
 // minimum of the 64-bit keys as redux.sync.min over the high words, then over the low words of the
 // lanes that hold the minimal high word; the count as redux.sync.add.
-__device__ __forceinline__ void block_min_sum(double &v, int &n, RedScratch *rs, int &slot) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+__device__ __forceinline__ double warp_min_f64(double v) {
   const unsigned long long k = cost_key(v);
   const unsigned hi = (unsigned)(k >> 32), mhi = __reduce_min_sync(0xffffffffu, hi);
   const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? (unsigned)k : 0xffffffffu);
+  return key_cost(((unsigned long long)mhi << 32) | mlo);
+}
+__device__ __forceinline__ void block_min2_sum(double &v, double &v2, int &n, RedScratch *rs, int &slot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const double wv = warp_min_f64(v), wv2 = warp_min_f64(v2);
   n = __reduce_add_sync(0xffffffffu, n);
-  if (lane == 0) { rs->v[slot][warp] = key_cost(((unsigned long long)mhi << 32) | mlo); rs->n[slot][warp] = n; }
+  if (lane == 0) { rs->v[slot][warp] = wv; rs->v2[slot][warp] = wv2; rs->n[slot][warp] = n; }
   __syncthreads();
-  double bv = rs->v[slot][0];
+  double bv = rs->v[slot][0], bv2 = rs->v2[slot][0];
   int bn = rs->n[slot][0];
-  for (int w = 1; w < nw; ++w) { bv = fmin(bv, rs->v[slot][w]); bn += rs->n[slot][w]; }
+  for (int w = 1; w < nw; ++w) { bv = fmin(bv, rs->v[slot][w]); bv2 = fmin(bv2, rs->v2[slot][w]); bn += rs->n[slot][w]; }
   v = bv;
+  v2 = bv2;
   n = bn;
   slot ^= 1;
+}
+__device__ __forceinline__ void block_min_sum(double &v, int &n, RedScratch *rs, int &slot) {
+  double dummy = CUDART_INF;
+  block_min2_sum(v, dummy, n, rs, slot);
 }
 
 // lexicographic min over (v, s): lowest state among equal costs
@@ -130,7 +157,7 @@ __device__ __forceinline__ void block_argmin(double &v, int &s, RedScratch *rs, 
 // above `cutoff` does not propagate.  Converges to the same least fixed point as the
 // reference's work queue; on exact ties the earlier token (then the lowest arc id) stays.
 __device__ __forceinline__ void eps_closure(double *X, double *Y, const AlignDev &g, const UttDesc &u, double cutoff,
-                                            int32_t *bp_row, int *s_flag) {
+                                            int32_t *bp_row, int *s_flag, bool &tie) {
   if (u.n_ed == 0) return;
   for (;;) {
     __syncthreads();  // X complete; previous round's flag consumed
@@ -147,7 +174,15 @@ __device__ __forceinline__ void eps_closure(double *X, double *Y, const AlignDev
         const double cs = X[e.x];
         if (!(cs > cutoff)) {
           const double nc = cs + (double)__int_as_float(e.z);
-          if (!(nc > cutoff) && nc < bc) { bc = nc; ba = e.y; }
+          if (!(nc > cutoff)) {
+            if (nc < bc) { bc = nc; ba = e.y; }
+            else if (nc == bc) {
+              // two epsilon arrivals at the same cost: the reference's queue order decides which one stays
+              // (an emitting token of the same cost always stays, in both: faster-decoder.cc:105-115)
+              const int prev = ba >= 0 ? ba : bp_row[d];
+              if (prev >= 0 && prev != e.y && g.arc_il[prev] == 0) tie = true;
+            }
+          }
         }
       }
       Y[d] = bc;
@@ -194,6 +229,8 @@ __global__ void __launch_bounds__(512) viterbi_kernel(AlignDev g, int u_base, co
   res.best_state = -1;
   res.path_len = 0;
   res.like = 0.f;
+  bool flagged = false;  // block-uniform: the reference's order-dependent pruning could have mattered
+  bool tie = false;      // per thread: an exact cost tie between competing predecessors
 
   if (u.start < 0 || S <= 0) {  // empty graph: decoder-wrappers.cc:36-42
     if (tid == 0) outs[ui] = res;
@@ -208,9 +245,10 @@ __global__ void __launch_bounds__(512) viterbi_kernel(AlignDev g, int u_base, co
       cur[s] = s == u.start ? 0.0 : kInf;
       ubp[s] = -1;
     }
-    eps_closure(cur, alt, g, u, (double)FLT_MAX, ubp, &s_flag);
+    eps_closure(cur, alt, g, u, (double)FLT_MAX, ubp, &s_flag, tie);
     __syncthreads();
     bool dead = false;
+    double x_local = kInf;  // cheapest candidate of the previous frame that the reference may have kept above the cutoff
     for (int t = 0; t < T; ++t) {
       const int tf = FC ? (t & (FC - 1)) : 0;  // FC is 32, 16, 8 or 0
       if (FC && tf == 0) {  // stage the next FC frames of this utterance's pdfs (ordered by the sync in the reduction)
@@ -228,7 +266,12 @@ __global__ void __launch_bounds__(512) viterbi_kernel(AlignDev g, int u_base, co
         const double c = cur[s];
         if (c < kInf) { best = fmin(best, c); ++ntok; }
       }
-      block_min_sum(best, ntok, &rs, slot);
+      double x_min = x_local;
+      block_min2_sum(best, x_min, ntok, &rs, slot);
+      x_local = kInf;
+      // extras of the previous frame exist at best at cost x_min: with <= min_active kept tokens they can change
+      // the token count GetCutoff sees, or be expanded under its +inf cutoff
+      if (x_min < kInf && ntok <= kAlignMinActive) flagged = true;
       if (ntok == 0) { dead = true; break; }
       const double beam_cutoff = best + (double)cfg_beam;
       // with at most min_active tokens the reference's min_active_cutoff stays +inf, which is
@@ -274,12 +317,16 @@ __global__ void __launch_bounds__(512) viterbi_kernel(AlignDev g, int u_base, co
           }
         }
       }
+      // kept extras would be expanded on this frame iff they are below its cutoff
+      if (x_min < weight_cutoff) flagged = true;
       // ---- ProcessEmitting as a pull over incoming arcs
       int32_t *bp_row = ubp + (size_t)(t + 1) * S;
-      double lmin = kInf;
+      double lmin = kInf, lmin0 = kInf;  // lowest new cost; lowest new cost out of the best token (the reference's first bound)
+      int n_best = 0;
       for (int d = tid; d < S; d += NT) {
         double bc = kInf;
-        int ba = -1;
+        int ba = -1, bsrc = -1;
+        n_best += cur[d] == best ? 1 : 0;
         const int k1 = in_off[d + 1];
         for (int k = in_off[d]; k < k1; ++k) {
           const int4 e = g.in_arcs[k];
@@ -288,20 +335,29 @@ __global__ void __launch_bounds__(512) viterbi_kernel(AlignDev g, int u_base, co
             const float lk = FC ? tile[e.y * FC + tf] : ll[(int64_t)upd[e.y] * ld + u.col0 + t];
             const float ac = -1.f * lk;
             const double nw = ((double)__int_as_float(e.w) + cs) + (double)ac;
-            if (nw < bc) { bc = nw; ba = e.z; }
+            if (cs == best) lmin0 = fmin(lmin0, nw);
+            if (nw < bc) { bc = nw; ba = e.z; bsrc = e.x; }
+            else if (nw == bc && e.x != bsrc) tie = true;  // equal cost from two source tokens: list order decides in the reference
           }
         }
         nxt[d] = bc;
         bp_row[d] = ba;
         lmin = fmin(lmin, bc);
       }
-      int dummy_n = 0;
-      block_min_sum(lmin, dummy_n, &rs, slot);
+      block_min2_sum(lmin, lmin0, n_best, &rs, slot);
       const double next_cutoff = lmin + (double)adaptive_beam;
+      // the reference's bound after expanding its best token first (faster-decoder.cc:177-190); with several
+      // equally good best tokens it is whichever comes first in its list: unknown here, so no bound
+      const double c0 = n_best > 1 ? kInf : lmin0 + (double)adaptive_beam;
       for (int d = tid; d < S; d += NT) {
-        if (!(nxt[d] < next_cutoff)) { nxt[d] = kInf; bp_row[d] = -1; }
+        const double c = nxt[d];
+        if (!(c < next_cutoff)) {
+          if (c < c0) x_local = fmin(x_local, c);  // the running cutoff may have let this one in
+          nxt[d] = kInf;
+          bp_row[d] = -1;
+        }
       }
-      eps_closure(nxt, alt, g, u, next_cutoff, bp_row, &s_flag);
+      eps_closure(nxt, alt, g, u, next_cutoff, bp_row, &s_flag, tie);
       double *tmp = cur; cur = nxt; nxt = tmp;
     }
     __syncthreads();
@@ -319,6 +375,17 @@ __global__ void __launch_bounds__(512) viterbi_kernel(AlignDev g, int u_base, co
       }
     }
     block_argmin(bf, bs, &rs, slot);
+    {
+      // extras of the LAST frame could be final tokens; two final states at exactly the best total cost are
+      // resolved by list order in the reference (faster-decoder.cc:377-384)
+      double xl = x_local, dummy = kInf;
+      int n_tie = 0;
+      if (!dead && bs != 0x7fffffff)
+        for (int s = tid; s < S; s += NT)
+          if (cur[s] != kInf && fin[s] != CUDART_INF_F && cur[s] + (double)fin[s] == bf) ++n_tie;
+      block_min2_sum(xl, dummy, n_tie, &rs, slot);
+      if (xl < kInf || n_tie > 1) flagged = true;
+    }
     if (bs != 0x7fffffff) {
       res.status = attempt == 0 ? KHG_ALIGN_OK : KHG_ALIGN_RETRIED;
       res.best_state = bs;
@@ -327,6 +394,7 @@ __global__ void __launch_bounds__(512) viterbi_kernel(AlignDev g, int u_base, co
     __syncthreads();
   }
 
+  res.pad = (flagged || __syncthreads_or(tie ? 1 : 0)) ? 1 : 0;
   if (tid == 0) {
     if (res.status != KHG_ALIGN_FAILED) {
       // traceback: GetBestPath + GetLinearSymbolSequence; like = -(graph + acoustic) / scale is
@@ -363,7 +431,7 @@ __global__ void path_kernel(AlignDev g, int u_base, int n, const int32_t *__rest
   if (i >= n) return;
   const UttDesc u = g.utts[u_base + i];
   const UttOut o = outs[u_base + i];
-  if (o.status == KHG_ALIGN_FAILED) return;
+  if (o.status == KHG_ALIGN_FAILED || path_off[u_base + i] < 0) return;  // (< 0: re-aligned on the host)
   int32_t *dst = path + (path_off[u_base + i] - off0);
   const int32_t *ubp = bp + u.bp0;
   int t = u.T, s = o.best_state, k = o.path_len;
@@ -376,10 +444,24 @@ __global__ void path_kernel(AlignDev g, int u_base, int n, const int32_t *__rest
   }
 }
 
+// The likelihood rows of flagged utterances, compacted for the host: entry i = (utterance, first float of its
+// n_pdf x T block in dst).
+__global__ void gather_ll_kernel(AlignDev g, const int2 *__restrict__ list, const int64_t *__restrict__ dst_off,
+                                 const float *__restrict__ ll, int64_t ld, float *__restrict__ dst) {
+  const UttDesc u = g.utts[list[blockIdx.x].x];
+  const int32_t *upd = g.utt_pdfs + u.pdf0;
+  float *o = dst + dst_off[blockIdx.x];
+  for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < (int64_t)u.n_pdf * u.T; i += (int64_t)gridDim.y * blockDim.x) {
+    const int j = (int)(i / u.T), t = (int)(i - (int64_t)j * u.T);
+    o[i] = ll[(int64_t)upd[j] * ld + u.col0 + t];
+  }
+}
+
 template <class F>
-static void parallel_for(int n, F f) {
+static void parallel_for(int n, F f, int min_parallel = 64) {
   int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
-  if (n < 64) nt = 1;
+  nt = std::min(nt, std::max(1, n));
+  if (n < min_parallel) nt = 1;
   if (nt == 1) {
     for (int i = 0; i < n; ++i) f(i, 0);
     return;
@@ -493,7 +575,7 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   // ---------------- host: transpose every graph (incoming emitting arcs per state, incoming
   // epsilon arcs per state), local pdf lists
   std::vector<UttDesc> desc(U);
-  std::vector<int32_t> n_emit(U, 0), n_eps(U, 0), bad(U, 0);
+  std::vector<int32_t> n_emit(U, 0), n_eps(U, 0), bad(U, 0), neg_eps(U, 0);
   std::vector<std::vector<int32_t>> updf(U);
   std::vector<int32_t> in_off((size_t)S_all + 1, 0), arc_src(A_all), arc_lp(A_all);
   std::vector<int32_t> eps_deg((size_t)S_all, 0);
@@ -520,6 +602,7 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
         if (ns < 0 || ns >= S || il < 0 || il >= n_tids) { bad[u] = 1; return; }
         arc_src[a] = s - s0;
         if (il == 0) {
+          if (gb->arc_weight[a] < 0.f) neg_eps[u] = 1;  // the exactness certificate assumes epsilon costs >= 0
           ++n_eps[u];
           ++eps_deg[s0 + ns];
         } else {
@@ -663,6 +746,11 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   int32_t *d_bp = m->w_al_bp.as<int32_t>();
   std::vector<UttOut> h_outs(U);
   std::vector<int64_t> h_poff((size_t)U + 1, 0);
+  std::vector<std::vector<int32_t>> x_ali(U), x_path(U), x_pdf(U);  // results of the exact host pass
+  std::vector<char> is_exact(U, 0);
+  int exact_mode = 1, n_redo_total = 0;  // 1 = flagged utterances only
+  if (const char *e = getenv("KHG_ALIGN_EXACT")) exact_mode = !strcmp(e, "none") ? 0 : (!strcmp(e, "all") ? 2 : 1);
+  double ms_exact = 0.0;
 
   for (size_t c = 0; c + 1 < chunk_start.size(); ++c) {
     const int u0 = chunk_start[c], u1 = chunk_start[c + 1];
@@ -687,13 +775,70 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
       ms_dense += a;
       ms_search += b;
     }
+    // ---- utterances the device search could not certify: the reference's decoder on the host, on the same
+    // likelihood block (KHG_ALIGN_EXACT=all / none forces every / no utterance through it: tests, timing)
+    std::vector<int> redo;
+    for (int u = u0; u < u1; ++u)
+      if (exact_mode != 0 && desc[u].start >= 0 && desc[u].S > 0 && (exact_mode == 2 || h_outs[u].pad != 0 || neg_eps[u])) redo.push_back(u);
+    n_redo_total += (int)redo.size();
+    if (!redo.empty()) {
+      const double t_x0 = now();
+      std::vector<int2> list(redo.size());
+      std::vector<int64_t> off(redo.size() + 1, 0);
+      for (size_t i = 0; i < redo.size(); ++i) {
+        list[i] = make_int2(redo[i], 0);
+        off[i + 1] = off[i] + (int64_t)desc[redo[i]].n_pdf * desc[redo[i]].T;
+      }
+      KHG_TRY(m->w_al_xlist.reserve(sizeof(int2) * list.size() + 8 * off.size()));
+      KHG_TRY(m->w_al_xll.reserve(sizeof(float) * (size_t)std::max<int64_t>(off.back(), 1)));
+      int2 *d_list = m->w_al_xlist.as<int2>();
+      int64_t *d_off = reinterpret_cast<int64_t *>(d_list + list.size());
+      KHG_CUDA_TRY(cudaMemcpyAsync(d_list, list.data(), sizeof(int2) * list.size(), cudaMemcpyHostToDevice, st));
+      KHG_CUDA_TRY(cudaMemcpyAsync(d_off, off.data(), 8 * off.size(), cudaMemcpyHostToDevice, st));
+      gather_ll_kernel<<<dim3((unsigned)redo.size(), 8), 256, 0, st>>>(g, d_list, d_off, d_block, ld, m->w_al_xll.as<float>());
+      ++g_launch_count;
+      KHG_CUDA_TRY(cudaGetLastError());
+      std::vector<float> xll((size_t)off.back());
+      if (off.back() > 0)
+        KHG_CUDA_TRY(cudaMemcpyAsync(xll.data(), m->w_al_xll.p, sizeof(float) * xll.size(), cudaMemcpyDeviceToHost, st));
+      KHG_CUDA_TRY(cudaStreamSynchronize(st));
+      std::vector<khg_status> rst(redo.size(), KHG_OK);
+      parallel_for((int)redo.size(), [&](int i, int) {
+        const int u = redo[i];
+        x_ali[u].assign((size_t)desc[u].T, 0);
+        int32_t status = KHG_ALIGN_FAILED;
+        float cost = 0.f;
+        rst[i] = align_exact_host(gb, u, xll.data() + off[i], desc[u].T, nullptr, arc_lp.data(), beam, retry_beam,
+                                  x_ali[u].data(), &status, &cost, &x_path[u]);
+        h_outs[u].status = status;
+        h_outs[u].path_len = (int32_t)x_path[u].size();
+        h_outs[u].like = cost;
+        is_exact[u] = 1;
+      }, 1);
+      for (khg_status r : rst) KHG_TRY(r);
+      // the per-frame pdf ids the statistics pass consumes, and the device copy of the alignment
+      for (int u : redo) {
+        if (desc[u].T == 0) continue;
+        KHG_CUDA_TRY(cudaMemcpyAsync(d_ali + desc[u].frame0, x_ali[u].data(), sizeof(int32_t) * desc[u].T, cudaMemcpyHostToDevice, st));
+        if (pdf_ids_dev) {
+          x_pdf[u].resize(desc[u].T);
+          for (int t = 0; t < desc[u].T; ++t) x_pdf[u][t] = x_ali[u][t] > 0 ? tid2pdf[x_ali[u][t]] : 0;
+          KHG_CUDA_TRY(cudaMemcpyAsync(pdf_ids_dev + desc[u].frame0, x_pdf[u].data(), sizeof(int32_t) * desc[u].T, cudaMemcpyHostToDevice, st));
+        }
+      }
+      KHG_CUDA_TRY(cudaStreamSynchronize(st));
+      ms_exact += now() - t_x0;
+    }
     if (path_arcs) {
       for (int u = u0; u < u1; ++u) h_poff[u + 1] = h_poff[u] + (h_outs[u].status == KHG_ALIGN_FAILED ? 0 : h_outs[u].path_len);
       const int64_t n_path = h_poff[u1] - h_poff[u0];
       KHG_REQUIRE(h_poff[u1] <= path_capacity, "path_capacity too small");
       if (n_path > 0) {
         KHG_TRY(m->w_al_path.reserve(sizeof(int32_t) * (size_t)n_path));
-        KHG_CUDA_TRY(cudaMemcpyAsync(d_poff + u0, h_poff.data() + u0, 8 * (size_t)(u1 - u0), cudaMemcpyHostToDevice, st));
+        std::vector<int64_t> poff_dev(h_poff.begin() + u0, h_poff.begin() + u1);
+        for (int u = u0; u < u1; ++u)
+          if (is_exact[u]) poff_dev[u - u0] = -1;  // path_kernel skips them
+        KHG_CUDA_TRY(cudaMemcpyAsync(d_poff + u0, poff_dev.data(), 8 * (size_t)(u1 - u0), cudaMemcpyHostToDevice, st));
         path_kernel<<<(u1 - u0 + 63) / 64, 64, 0, st>>>(g, u0, u1 - u0, d_bp, d_outs, d_poff, h_poff[u0],
                                                         m->w_al_path.as<int32_t>());
         ++g_launch_count;
@@ -701,6 +846,8 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
         KHG_CUDA_TRY(cudaMemcpyAsync(path_arcs + h_poff[u0], m->w_al_path.p, sizeof(int32_t) * (size_t)n_path,
                                      cudaMemcpyDeviceToHost, st));
         KHG_CUDA_TRY(cudaStreamSynchronize(st));
+        for (int u = u0; u < u1; ++u)
+          if (is_exact[u] && !x_path[u].empty()) std::copy(x_path[u].begin(), x_path[u].end(), path_arcs + h_poff[u]);
       }
     }
   }
@@ -709,10 +856,12 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   KHG_CUDA_TRY(cudaStreamSynchronize(st));
   if (timing) {
     fprintf(stderr, "khg_align_batch: utts %d frames %lld states %d arcs %d | S_max %d n_pdf_max %d FC %d NT %d smem %zu chunks %zu | "
-            "host prep %.2f ms, dense %.2f ms, search %.2f ms, total %.2f ms\n", U, (long long)T_all, S_all, A_all, S_max, n_pdf_max,
-            FC, NT, smem, chunk_start.size() - 1, t_prep - t_begin, ms_dense, ms_search, now() - t_begin);
+            "host prep %.2f ms, dense %.2f ms, search %.2f ms, exact host pass %.2f ms (%d utterances), total %.2f ms\n", U,
+            (long long)T_all, S_all, A_all, S_max, n_pdf_max, FC, NT, smem, chunk_start.size() - 1, t_prep - t_begin, ms_dense,
+            ms_search, ms_exact, n_redo_total, now() - t_begin);
     for (auto &e : ev) cudaEventDestroy(e);
   }
+  g_align_exact_utts = n_redo_total;
   for (int u = 0; u < U; ++u) {
     if (utt_status) utt_status[u] = h_outs[u].status;
     // decoder-wrappers.cc:91: like = -(graph + acoustic) / acoustic_scale
@@ -721,3 +870,5 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   }
   return KHG_OK;
 }
+
+extern "C" int64_t khg_align_last_exact_count(void) { return g_align_exact_utts; }

@@ -95,8 +95,8 @@ struct Graph {  // one utterance of a khg_graph_batch
 
 class ExactDecoder {
  public:
-  ExactDecoder(const Graph &g, const float *ll, int64_t ld, const int32_t *row_of_tid, int32_t T)
-      : g_(g), ll_(ll), ld_(ld), row_(row_of_tid), T_(T) {
+  ExactDecoder(const Graph &g, const float *ll, int64_t ld, const int32_t *row_of_tid, const int32_t *row_of_arc, int32_t T)
+      : g_(g), ll_(ll), ld_(ld), row_(row_of_tid), arow_(row_of_arc), T_(T) {
     toks_.SetSize(1000);  // faster-decoder.cc:29
   }
 
@@ -149,7 +149,7 @@ class ExactDecoder {
   static constexpr int kMinActive = 20;
   static constexpr float kBeamDelta = 0.5f, kHashRatio = 2.0f;
 
-  float AcCost(int32_t t, int32_t tid) const { return -1.f * ll_[(int64_t)row_[tid] * ld_ + t]; }
+  float AcCost(int32_t t, int32_t arc) const { return -1.f * ll_[(int64_t)(arow_ ? arow_[arc] : row_[g_.il[arc]]) * ld_ + t]; }
 
   void ProcessNonemitting(double cutoff) {
     queue_.clear();
@@ -215,7 +215,7 @@ class ExactDecoder {
       const double tc = arena_[last_[best_elem].second].cost;
       for (int32_t a = g_.arc_off[state]; a < g_.arc_off[state + 1]; ++a)
         if (g_.il[a] != 0) {
-          const float ac_cost = AcCost(frame, g_.il[a]);
+          const float ac_cost = AcCost(frame, a);
           const double new_weight = (double)g_.w[a] + tc + (double)ac_cost;
           if (new_weight + (double)adaptive_beam < next_weight_cutoff) next_weight_cutoff = new_weight + (double)adaptive_beam;
         }
@@ -226,7 +226,7 @@ class ExactDecoder {
       if (!(tc < weight_cutoff)) continue;
       for (int32_t a = g_.arc_off[state]; a < g_.arc_off[state + 1]; ++a) {
         if (g_.il[a] == 0) continue;
-        const float ac_cost = AcCost(frame, g_.il[a]);
+        const float ac_cost = AcCost(frame, a);
         const double new_weight = (double)g_.w[a] + tc + (double)ac_cost;
         if (new_weight < next_weight_cutoff) {
           // Token(arc, ac_cost, prev): cost_ = prev->cost_ + arc.weight + ac_cost  (faster-decoder.h:117-126)
@@ -248,7 +248,7 @@ class ExactDecoder {
   const Graph &g_;
   const float *ll_;
   int64_t ld_;
-  const int32_t *row_;
+  const int32_t *row_, *arow_;
   int32_t T_;
   float beam_ = 0.f;
   HashList toks_;
@@ -260,11 +260,12 @@ class ExactDecoder {
 
 }  // namespace
 
-// One utterance.  ll: rows x ld floats, SCALED log-likelihoods (DecodableAmDiagGmmScaled::LogLikelihood),
-// row_of_tid[tid] = row of tid's pdf.  path: absolute arc ids of the best path, epsilons included.
+// One utterance.  ll: rows x ld floats, SCALED log-likelihoods (DecodableAmDiagGmmScaled::LogLikelihood);
+// the row of an emitting arc is row_of_arc[absolute arc id] if given, else row_of_tid[its transition-id].
+// path: absolute arc ids of the best path, epsilons included; *cost = graph + acoustic cost.
 khg_status align_exact_host(const khg_graph_batch *gb, int32_t utt, const float *ll, int64_t ld, const int32_t *row_of_tid,
-                            float beam, float retry_beam, int32_t *alignment, int32_t *status, float *cost,
-                            std::vector<int32_t> *path) {
+                            const int32_t *row_of_arc, float beam, float retry_beam, int32_t *alignment, int32_t *status,
+                            float *cost, std::vector<int32_t> *path) {
   const int32_t s0 = gb->state_offsets[utt];
   Graph g;
   g.S = gb->state_offsets[utt + 1] - s0;
@@ -280,7 +281,7 @@ khg_status align_exact_host(const khg_graph_batch *gb, int32_t utt, const float 
   path->clear();
   for (int32_t t = 0; t < T; ++t) alignment[t] = 0;
   if (g.start < 0 || g.S <= 0) return KHG_OK;  // decoder-wrappers.cc:36-42
-  ExactDecoder dec(g, ll, ld, row_of_tid, T);
+  ExactDecoder dec(g, ll, ld, row_of_tid, row_of_arc, T);
   dec.Decode(beam);
   bool ans = dec.ReachedFinal();
   int32_t st = KHG_ALIGN_OK;
@@ -320,7 +321,7 @@ extern "C" khg_status khg_align_utterance_host(const khg_graph_batch *gb, int32_
                 "graph: label / state out of range");
   std::vector<int32_t> path;
   float cost = 0.f;
-  KHG_TRY(align_exact_host(gb, utt, loglikes, ld, tid2row, beam, retry_beam, alignment, status, &cost, &path));
+  KHG_TRY(align_exact_host(gb, utt, loglikes, ld, tid2row, nullptr, beam, retry_beam, alignment, status, &cost, &path));
   if (like) *like = *status == KHG_ALIGN_FAILED ? 0.f : -cost / acoustic_scale;  // decoder-wrappers.cc:91
   if (path_len) *path_len = (int32_t)path.size();
   if (path_arcs) {

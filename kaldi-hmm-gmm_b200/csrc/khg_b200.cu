@@ -208,7 +208,7 @@ khg_status khg_model_upload(khg_model *m, const float *weights, const float *mea
   m->tc.ready = false;
   if (m->kernel != KHG_KERNEL_SIMT && tc_supported(m)) {
     khg_status s = tc_pack_build(m);
-    if (s != KHG_OK && (m->kernel == KHG_KERNEL_TCGEN05 || m->kernel == KHG_KERNEL_TCGEN05_F16)) return s;
+    if (s != KHG_OK && m->kernel >= KHG_KERNEL_TCGEN05) return s;
   }
   KHG_CUDA_TRY(cudaStreamSynchronize(st));
   return KHG_OK;
@@ -232,6 +232,7 @@ khg_status khg_model_info(const khg_model *m, int32_t *dim, int32_t *num_pdfs, i
 khg_status khg_model_dense_kernel(const khg_model *m, int32_t *kernel) {
   KHG_REQUIRE(m && kernel, "null argument");
   if (m->kernel == KHG_KERNEL_SIMT || !m->tc.ready) *kernel = KHG_KERNEL_SIMT;
+  else if (m->kernel == KHG_KERNEL_TCGEN05_F16_GS && gs_supported(m)) *kernel = KHG_KERNEL_TCGEN05_F16_GS;
   else if (m->tc.f16_ready && m->kernel != KHG_KERNEL_TCGEN05) *kernel = KHG_KERNEL_TCGEN05_F16;
   else if (m->tc.tf32_ready) *kernel = KHG_KERNEL_TCGEN05;
   else *kernel = KHG_KERNEL_SIMT;
@@ -239,8 +240,8 @@ khg_status khg_model_dense_kernel(const khg_model *m, int32_t *kernel) {
 }
 
 khg_status khg_model_set_kernel(khg_model *m, int32_t kernel) {
-  KHG_REQUIRE(m && kernel >= KHG_KERNEL_AUTO && kernel <= KHG_KERNEL_TCGEN05_F16, "bad kernel id");
-  if ((kernel == KHG_KERNEL_TCGEN05 || kernel == KHG_KERNEL_TCGEN05_F16) && !tc_supported(m)) {
+  KHG_REQUIRE(m && kernel >= KHG_KERNEL_AUTO && kernel <= KHG_KERNEL_TCGEN05_F16_GS, "bad kernel id");
+  if (kernel >= KHG_KERNEL_TCGEN05 && !tc_supported(m)) {
     set_error("tcgen05 kernel does not support this model shape (needs 2*dim+2 <= 160 for the tf32 split / <= 320 for the fp16 split, and every pdf <= 240 Gaussians)");
     return KHG_ERR_UNSUPPORTED;
   }
@@ -270,7 +271,7 @@ void khg_model_destroy(khg_model *m) {
   for (Buf *b : {&m->w_feats, &m->w_ids, &m->w_wts, &m->w_out, &m->w_pf, &m->w_keys, &m->w_vals_in,
                  &m->w_vals_out, &m->w_cub, &m->w_starts, &m->w_item_start, &m->w_tot, &m->w_tid,
                  &m->w_tid2pdf, &m->w_trans, &m->w_keys_out, &m->w_sub, &m->w_full, &m->w_al_graph,
-                 &m->w_al_block, &m->w_al_bp, &m->w_al_cost, &m->w_al_ali, &m->w_al_path, &m->w_item_desc})
+                 &m->w_al_block, &m->w_al_bp, &m->w_al_cost, &m->w_al_ali, &m->w_al_path, &m->w_al_xlist, &m->w_al_xll, &m->w_item_desc})
     b->release();
   for (int i = 0; i < 2; ++i) {
     m->pin_feats[i].release(); m->pin_ids[i].release(); m->pin_wts[i].release();
@@ -331,8 +332,8 @@ static khg_status simt_launch(khg_model *m, const float *d_feats, int64_t T, flo
 static khg_status dense_device(khg_model *m, const float *d_feats, int64_t T, float scale,
                                int layout, float *d_out, int64_t ld) {
   const bool use_tc = m->kernel != KHG_KERNEL_SIMT && m->tc.ready;
-  const int prec = m->kernel == KHG_KERNEL_TCGEN05 ? 1 : (m->kernel == KHG_KERNEL_TCGEN05_F16 ? 2 : 0);
-  if ((m->kernel == KHG_KERNEL_TCGEN05 || m->kernel == KHG_KERNEL_TCGEN05_F16) && !m->tc.ready) {
+  const int prec = m->kernel == KHG_KERNEL_TCGEN05 ? 1 : (m->kernel == KHG_KERNEL_TCGEN05_F16 ? 2 : (m->kernel == KHG_KERNEL_TCGEN05_F16_GS ? 3 : 0));
+  if (m->kernel >= KHG_KERNEL_TCGEN05 && !m->tc.ready) {
     set_error("tcgen05 kernel requested but its model pack is not built");
     return KHG_ERR_UNSUPPORTED;
   }
@@ -1032,7 +1033,7 @@ khg_status finish_model_from_device(khg_model *nm, int32_t *num_bad) {
   nm->tc.ready = false;
   if (nm->kernel != KHG_KERNEL_SIMT && tc_supported(nm)) {
     khg_status ts = tc_pack_build(nm);
-    if (ts != KHG_OK && (nm->kernel == KHG_KERNEL_TCGEN05 || nm->kernel == KHG_KERNEL_TCGEN05_F16)) return ts;
+    if (ts != KHG_OK && nm->kernel >= KHG_KERNEL_TCGEN05) return ts;
   }
   KHG_CUDA_TRY(cudaStreamSynchronize(st));
   return KHG_OK;

@@ -156,6 +156,7 @@ struct khg_model {
   khg::Buf w_tid, w_tid2pdf, w_trans;                  // tid path
   khg::Buf w_sub, w_full;                              // pdf-subset gather
   khg::Buf w_al_graph, w_al_block, w_al_bp, w_al_cost, w_al_ali, w_al_path;  // khg_align_batch (khg_align.cu)
+  khg::Buf w_al_xlist, w_al_xll;                                             // ... its exact host pass: flagged list, likelihood rows
   khg::Buf pin_feats[2], pin_ids[2], pin_wts[2];       // pinned staging for estep(HOST)
   khg::Buf w_efeats[2], w_eids[2], w_ewts[2];
 };
@@ -180,11 +181,14 @@ khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scal
                        float *d_out, int64_t ld_out, int precision, const unsigned **simt_gate,
                        float *gate_limit);
 // khg_loglikes_gs.cu: the Gaussian-stationary form of the fp16-split kernel (model tile resident in shared
-// memory, pre-split feature operand streamed); `fallback` is launched behind every gated sub-block
+// memory, pre-split feature operand streamed)
 bool gs_supported(const khg_model *m);
 void gs_free(khg_model *m);
-khg_status gs_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t ld_out, bool gated,
-                       khg_status (*fallback)(khg_model *, const float *, int64_t, float, float *, int64_t, const unsigned *));
+khg_status gs_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t ld_out);
+// khg_align_exact.cu: the reference's FasterDecoder on the host for one utterance of a graph batch
+khg_status align_exact_host(const khg_graph_batch *gb, int32_t utt, const float *ll, int64_t ld, const int32_t *row_of_tid,
+                            const int32_t *row_of_arc, float beam, float retry_beam, int32_t *alignment, int32_t *status,
+                            float *cost, std::vector<int32_t> *path);
 // khg_b200.cu: the dense all-pdf block of device-resident frames (kernel choice of the model),
 // and the synchronising read of the latched device error flag
 khg_status dense_block(khg_model *m, const float *d_feats, int64_t T, float scale, int layout, float *d_out, int64_t ld);

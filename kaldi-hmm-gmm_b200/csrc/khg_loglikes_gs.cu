@@ -46,12 +46,11 @@ constexpr int kGsMaxBChunks = 4;              // B' tile = up to 4 x 30 KB
 // Row t of A' = the packed K steps [hi steps | lo steps] of [x*s, x^2*s^2, 1, 1] (hi = fp16 round-to-
 // nearest, lo = fp16 of the exact fp32 residual; s = the per-dimension power-of-two scale of the fp16
 // model pack), laid out by the same stage table as B'.  One thread = 8 consecutive fp16 (16 bytes).
-// Rows [T, rows_padded) are zero.  Also the gate of the automatic precision choice: max |x * s|.
+// Rows [T, rows_padded) are zero.
 __global__ void gs_build_a_kernel(const float *__restrict__ feats, int64_t T, int64_t rows_padded, int D, StageTab tab, int KPA,
-                                  const float *__restrict__ ascale, __half *__restrict__ ap, unsigned *__restrict__ gate) {
+                                  const float *__restrict__ ascale, __half *__restrict__ ap) {
   const int gpr = KPA >> 3;  // 16-byte groups per row
   const int64_t total = rows_padded * gpr;
-  unsigned mx = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / gpr;
     const int grp = (int)(i - row * gpr);
@@ -65,7 +64,6 @@ __global__ void gs_build_a_kernel(const float *__restrict__ feats, int64_t T, in
         if (k < 2 * D) {
           const float x = __ldg(feats + row * D + (k < D ? k : k - D));
           v = (k < D ? x : x * x) * __ldg(ascale + k);  // data.array().square(), csrc/decodable-am-diag-gmm.cc:57
-          if (k < D && !lo_part) mx = max(mx, __float_as_uint(fabsf(v)));  // (NaN orders above every finite value)
         } else if (k <= 2 * D + 1 && !lo_part) {
           v = 1.f;  // the two columns the gconst and its residual ride on
         }
@@ -74,10 +72,6 @@ __global__ void gs_build_a_kernel(const float *__restrict__ feats, int64_t T, in
       o[e] = lo_part ? __float2half_rn(v - __half2float(hi)) : hi;
     }
     *reinterpret_cast<uint4 *>(ap + i * 8) = *reinterpret_cast<const uint4 *>(o);
-  }
-  if (gate != nullptr) {
-    for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    if ((threadIdx.x & 31) == 0 && mx) atomicMax(gate, mx);
   }
 }
 
@@ -89,9 +83,6 @@ struct GsArgs {
   StageTab tab;            // chunks of a packed operand row (same for A' and B') and the K steps each holds
   int hs, ls;              // K steps of the hi part (2D+2 columns) and of the lo part (2D columns)
   int stages;              // A' ring depth
-  const unsigned *gate;    // NULL, or device word with max |x*s| bits
-  float gate_limit;
-  int gate_run_if_above;
   const int32_t *tile_g0;  // first Gaussian (operand row) of every model tile
   const int2 *epi_hdr;     // epilogue tables (khg_loglikes_tc.cu)
   const uint32_t *runs;
@@ -101,7 +92,6 @@ struct GsArgs {
   int64_t ld;
   float *scratch;          // one device word: store target of rows beyond T
   int *err;
-  int rotate;              // 1: the epilogue groups swap their pdf lists from frame tile to frame tile (load balance)
   int debug_mode;          // experiments (KHG_EXPERIMENTS builds only)
 };
 
@@ -140,10 +130,6 @@ template <bool TWO, bool GRP>
 __global__ void __launch_bounds__(kTcThreads, 1)
 loglikes_gs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GsArgs a) {
   constexpr uint32_t kIdesc = make_idesc<true>();
-  if (a.gate != nullptr) {  // precision-path gate decided on the device (no host round trip)
-    const bool above = !(__uint_as_float(*a.gate) <= a.gate_limit);
-    if (above != (a.gate_run_if_above != 0)) return;
-  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -305,7 +291,6 @@ loglikes_gs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         roles[threadIdx.x] = r;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-      uint32_t role = a.rotate ? (uint32_t)(eg + f0) % kEpiGroups : (uint32_t)eg;
       for (int f = f0; f < f1; ++f, ++acc_it) {
         const int buf = acc_it & 1;
         const int64_t t = (int64_t)f * kTileM + row;
@@ -321,8 +306,7 @@ loglikes_gs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         e.ld_bytes = valid ? (uint32_t)(a.ld * 4) : 0u;
 #endif
         e.nan_acc = 0.f;
-        const EpiRole r = roles[role];
-        if (a.rotate && ++role == (uint32_t)kEpiGroups) role = 0;
+        const EpiRole r = roles[eg];
         const uint32_t *rp = a.runs + r.run0;
         int nr = (int)r.nr;
         e.sp = a.seg + r.seg0;
@@ -402,9 +386,7 @@ static int64_t gs_chunk_frames(const khg_model *m) {
 
 bool gs_supported(const khg_model *m) {
   const TcPack &t = m->tc;
-  if (!t.f16_ready || t.tab16.n > kGsMaxBChunks) return false;
-  if (const char *e = getenv("KHG_GS")) return atoi(e) != 0;
-  return true;
+  return t.f16_ready && t.tab16.n <= kGsMaxBChunks;
 }
 
 void gs_free(khg_model *m) {
@@ -445,10 +427,8 @@ static khg_status gs_reserve_a(khg_model *m, int64_t rows) {
   return KHG_OK;
 }
 
-// One K0 + K1g pair over frames [0, T) (T <= the A' capacity).  gate: NULL (forced fp16), or the
-// device word K0 fills; K1g then runs iff *gate <= limit.
-static khg_status gs_launch(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t ld_out,
-                            unsigned *gate) {
+// One K0 + K1g pair over frames [0, T) (T <= the A' capacity).
+static khg_status gs_launch(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t ld_out) {
   TcPack &t = m->tc;
   const int D = m->dim;
   const int64_t rows = (T + kTileM - 1) / kTileM * kTileM;
@@ -456,7 +436,7 @@ static khg_status gs_launch(khg_model *m, const float *d_feats, int64_t T, float
   {
     const int64_t total = rows * (t.KPB16 / 8);
     const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, 16LL * m->sm_count);
-    gs_build_a_kernel<<<grid, 256, 0, m->stream>>>(d_feats, T, rows, D, t.tab16, t.KPB16, t.ascale, t.a_scr.as<__half>(), gate);
+    gs_build_a_kernel<<<grid, 256, 0, m->stream>>>(d_feats, T, rows, D, t.tab16, t.KPB16, t.ascale, t.a_scr.as<__half>());
     ++g_launch_count;
     KHG_CUDA_TRY(cudaGetLastError());
   }
@@ -474,9 +454,6 @@ static khg_status gs_launch(khg_model *m, const float *d_feats, int64_t T, float
     set_error("feature dimension too large for the Gaussian-stationary tcgen05 kernel");
     return KHG_ERR_UNSUPPORTED;
   }
-  a.gate = gate;
-  a.gate_limit = kF16FeatLimit;
-  a.gate_run_if_above = 0;
   a.tile_g0 = t.tile_g0;
   a.epi_hdr = static_cast<const int2 *>(t.epi_hdr);
   a.runs = t.runs;
@@ -486,8 +463,6 @@ static khg_status gs_launch(khg_model *m, const float *d_feats, int64_t T, float
   a.ld = ld_out;
   a.scratch = reinterpret_cast<float *>(m->d_scratch_int + 3);
   a.err = m->d_err;
-  a.rotate = 1;
-  if (const char *e = getenv("KHG_GS_ROTATE")) a.rotate = atoi(e) != 0;  // experiments
   a.debug_mode = 0;
 #ifdef KHG_EXPERIMENTS
   if (const char *dbg = getenv("KHG_TC_DEBUG_MODE")) a.debug_mode = atoi(dbg);
@@ -508,18 +483,13 @@ static khg_status gs_launch(khg_model *m, const float *d_feats, int64_t T, float
   return KHG_OK;
 }
 
-// The fp16-split dense block of frames [0, T) in sub-blocks of gs_chunk_frames().  gated: the
-// automatic precision choice — per sub-block K0 measures max |x * s|, K1g runs iff it is in range, and
-// `fallback` (the tf32-split kernel, gated the other way) is launched right behind it.
-khg_status gs_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t ld_out, bool gated,
-                       khg_status (*fallback)(khg_model *, const float *, int64_t, float, float *, int64_t, const unsigned *)) {
-  TcPack &t = m->tc;
+// The fp16-split dense block of frames [0, T) in sub-blocks of gs_chunk_frames() (forced precision: the
+// caller chose this kernel; out-of-range features give non-finite results, which are reported).
+khg_status gs_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t ld_out) {
   const int64_t chunk = gs_chunk_frames(m);
   for (int64_t t0 = 0; t0 < T; t0 += chunk) {
     const int64_t n = std::min(chunk, T - t0);
-    if (gated) KHG_CUDA_TRY(cudaMemsetAsync(t.gate, 0, sizeof(unsigned), m->stream));
-    KHG_TRY(gs_launch(m, d_feats + t0 * m->dim, n, scale, d_out + t0, ld_out, gated ? t.gate : nullptr));
-    if (gated && fallback) KHG_TRY(fallback(m, d_feats + t0 * m->dim, n, scale, d_out + t0, ld_out, t.gate));
+    KHG_TRY(gs_launch(m, d_feats + t0 * m->dim, n, scale, d_out + t0, ld_out));
   }
   return KHG_OK;
 }

@@ -158,8 +158,7 @@ struct TcArgs {
   int64_t ld;
   float *scratch;          // one device word: store target of rows beyond T
   int *err;
-  int debug_mode;          // 0 = normal; 1 = epilogue skips the LSE (pipeline-ceiling experiment, KHG_TC_DEBUG_MODE)
-  unsigned long long *timing;  // NULL, or per-CTA {builder wait for a_free, A build, MMA wait for a_full, items} in ns (KHG_TC_TIMING)
+  int debug_mode;          // 0 = normal; others: timing experiments, compiled in with -DKHG_EXPERIMENTS only (KHG_TC_DEBUG_MODE)
   int cluster;             // 1 = plain launch; 2 = CTA pairs sharing the streamed operand by TMA multicast
                            // (n_splits == 1: CTA rank r of pair k works on frame tile 2k + r)
 };
@@ -167,7 +166,7 @@ struct TcArgs {
 // TWO: the model has pdfs of 17..32 Gaussians (two-load segments); GRP: it has groups of short pdfs
 // read by one load (epi_run_multi).  Separate instantiations, so that models without them run
 // exactly the plain single-load epilogue (its code layout is worth 2-4 % on the C4 shape).
-template <bool F16, bool TWO, bool GRP, bool PAIR>
+template <bool F16, bool TWO, bool GRP>
 __global__ void __launch_bounds__(kTcThreads, 1)
 loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_b_half, TcArgs a) {
   constexpr int kChunkK = Elem<F16>::kChunkK, kUmmaK = Elem<F16>::kUmmaK;
@@ -203,11 +202,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
   // work items of this CTA: item(k) for k = k_first, k_first + k_stride, ... < k_end
   const bool clu = a.cluster >= 2;        // launched as CTA pairs
   const bool mcast = a.cluster == 2;      // each CTA runs its own MMAs; the operand stages are multicast
-  // one cta_group::2 MMA stream issued by the pair's rank-0 CTA; its own instantiation (PAIR): a kernel
-  // that contains cta_group::2 instructions can only be launched as clusters
-  const bool pairmma = PAIR && a.cluster == 3;
   const uint32_t crank = clu ? cluster_ctarank() : 0u;
-  constexpr uint32_t kIdescPair = make_idesc<F16, 2 * kTileM>();
   const int64_t k_first = clu ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
   const int64_t k_stride = clu ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
   const int64_t k_end = clu ? (a.n_items + 1) / 2 : a.n_items;  // (a phantom tile beyond T pads an odd count)
@@ -219,25 +214,19 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
         mbar_init(b_full(s), 1);
         mbar_init(b_empty(s), mcast ? 2 : 1);  // multicast pair: the MMA warps of both CTAs release a stage
       }
-      // pair MMA: the rank-0 CTA's barriers also count the peer's A builder and epilogue warps
       for (uint32_t sl = 0; sl < 2; ++sl) {
-        mbar_init(a_full(sl), pairmma ? 2 : 1);
+        mbar_init(a_full(sl), 1);
         mbar_init(a_free(sl), 1);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(acc_full(b), 1);
-        mbar_init(acc_empty(b), (pairmma ? 2 : 1) * 4 * kEpiGroups);
+        mbar_init(acc_empty(b), 4 * kEpiGroups);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    if constexpr (PAIR) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   } else if (warp == kBuilderWarp0 || warp == kBuilderWarp0 + 1) {
     // one-time A init: zero everything, then the constant-1 column (k = 2D) of A_hi
     const int b = threadIdx.x - 32 * kBuilderWarp0;
@@ -268,29 +257,25 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
         for (int j = j0; j < j1; ++j) {
           const int g0 = __shfl_sync(0xffffffffu, __ldg(a.tile_g0 + j), 0);
           for (int c = 0; c < a.tab.n; ++c) {
-            mbar_wait_crit(b_empty(st), ph);
+            mbar_wait(b_empty(st), ph);
             if (leader) {
-              // experiments (timing only, results are garbage): 3 = MMA rate without operand traffic,
-              // 4 / 5 = only the first / all but the second chunk of every tile is loaded (1/3, 2/3 of the traffic)
+#ifdef KHG_EXPERIMENTS
+              // (timing only, results are garbage) 3 = MMA rate without operand traffic, 4 / 5 = only the first /
+              // all but the second chunk of every tile is loaded, 6 / 7 = the 2nd / every chunk is always the SAME
+              // box of the operand (full shared-memory write volume, no L2 footprint); plain launches only
               if (a.debug_mode == 3 || (a.debug_mode == 4 && c != 0) || (a.debug_mode == 5 && c == 1)) {
                 mbar_arrive(b_full(st));
-              } else if (PAIR) {
-                // this CTA keeps only ITS half of the stage's rows; the bytes of both halves are counted
-                // by the rank-0 CTA's barrier, where the MMAs are issued
-                if (crank == 0) mbar_expect_tx(b_full(st), kBStageBytes);
-                tma_load_2d_pair(sB + st * kBStageBytes, &map_b_half, mapa_cta(b_full(st), 0), c * kChunkK,
-                                 g0 + (int)crank * (kTileN / 2));
-              } else if (mcast) {
+              } else if (!mcast && (a.debug_mode == 6 || a.debug_mode == 7)) {
+                const bool same = a.debug_mode == 7 || c == 1;
+                mbar_expect_tx(b_full(st), kBStageBytes);
+                tma_load_2d(sB + st * kBStageBytes, &map_b, b_full(st), same ? 0 : c * kChunkK, same ? 0 : g0);
+              } else
+#endif
+              if (mcast) {
                 // this CTA's half of the stage's rows, into both CTAs; the other half arrives from the peer
                 mbar_expect_tx(b_full(st), kBStageBytes);
                 tma_load_2d_mc(sB + st * kBStageBytes + crank * (kBStageBytes / 2), &map_b_half, b_full(st), c * kChunkK,
                                g0 + (int)crank * (kTileN / 2), (uint16_t)3);
-              } else if (a.debug_mode == 6 || a.debug_mode == 7) {
-                // experiments: the 2nd chunk (6) / every chunk (7) is always the SAME box of the operand:
-                // full shared-memory write volume, (almost) no L2 footprint
-                const bool same = a.debug_mode == 7 || c == 1;
-                mbar_expect_tx(b_full(st), kBStageBytes);
-                tma_load_2d(sB + st * kBStageBytes, &map_b, b_full(st), same ? 0 : c * kChunkK, same ? 0 : g0);
               } else {
                 mbar_expect_tx(b_full(st), kBStageBytes);
                 tma_load_2d(sB + st * kBStageBytes, &map_b, b_full(st), c * kChunkK, g0);
@@ -307,7 +292,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
     // All 32 lanes run the loop (uniform control flow, see elect_one); one elected lane issues.
     // The instruction stream is kept as short as possible (no divisions, 32-bit descriptor
     // arithmetic): this warp shares an SM sub-partition with four busy epilogue warps.
-    if (!pairmma || crank == 0) {
+    {
       const bool leader = elect_one();
       uint32_t st = 0, ph = 0, acc_it = 0, a_it = 0;
       const uint32_t a_hi_base = umma_desc_lo(sA_hi), a_lo_base = umma_desc_lo(sA_lo), b0 = umma_desc_lo(sB);
@@ -317,71 +302,53 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
         const int64_t item = item_of(k);
         const int split = (int)(item % a.n_splits);
         const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
-        unsigned long long tm0 = 0;
-        if (a.timing && leader) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm0));
         const uint32_t asl = a_it & a_two, aph = (a_two ? a_it >> 1 : a_it) & 1;
         const uint32_t a_hi0 = a_hi_base + asl * a_slot_desc, a_lo0 = a_lo_base + asl * a_slot_desc;
-        mbar_wait_crit(a_full(asl), aph);
-        if (a.timing && leader) {
-          unsigned long long tm1;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm1));
-          a.timing[4 * blockIdx.x + 2] += tm1 - tm0;
-        }
+        mbar_wait(a_full(asl), aph);
         tc_fence_after();
         for (int j = j0; j < j1; ++j, ++acc_it) {
           const uint32_t buf = acc_it & 1;
-          mbar_wait_crit(acc_empty(buf), ((acc_it >> 1) & 1) ^ 1);
+          mbar_wait(acc_empty(buf), ((acc_it >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * 256;
           uint32_t accum = 0;
           for (int c = 0; c < a.tab.n; ++c) {
             const uint32_t e = a.tab.e[c];
             const int h0 = e & 0xff, nh = (e >> 8) & 0xf, l0 = (e >> 12) & 0xff, nl = (e >> 20) & 0xf;
-            mbar_wait_crit(b_full(st), ph);
+            mbar_wait(b_full(st), ph);
             tc_fence_after();
             const uint32_t db = b0 + st * kBStageDesc;
             constexpr int kSpc = kChunkK / kUmmaK;  // K steps per chunk (4)
-            if (a.debug_mode != 2) {  // (2 = experiment: TMA rate without MMAs)
+#ifdef KHG_EXPERIMENTS
+            if (a.debug_mode != 2)  // (2 = TMA rate without MMAs)
+#endif
+            {
               // hi steps of B feed A_hi (hi.hi) and, inside the feature columns, A_lo (lo.hi)
 #pragma unroll 4
               for (int s = 0; s < nh; ++s) {
                 const int q = h0 + s;
                 const uint32_t ao = (uint32_t)(q / kSpc) * kAChunkDesc + (uint32_t)(q % kSpc) * 2;
-                if constexpr (PAIR) {
-                  if (leader) tc_mma_pair<F16>(tmem_d, a_hi0 + ao, db + 2 * s, kIdescPair, accum);
-                  accum = 1;
-                  if (q * kUmmaK < a.Kc && leader) tc_mma_pair<F16>(tmem_d, a_lo0 + ao, db + 2 * s, kIdescPair, 1);
-                } else {
-                  if (leader) tc_mma<F16>(tmem_d, a_hi0 + ao, db + 2 * s, kIdesc, accum);
-                  accum = 1;
-                  if (q * kUmmaK < a.Kc && leader) tc_mma<F16>(tmem_d, a_lo0 + ao, db + 2 * s, kIdesc, 1);
-                }
+                if (leader) tc_mma<F16>(tmem_d, a_hi0 + ao, db + 2 * s, kIdesc, accum);
+                accum = 1;
+                if (q * kUmmaK < a.Kc && leader) tc_mma<F16>(tmem_d, a_lo0 + ao, db + 2 * s, kIdesc, 1);
               }
               // lo steps of B feed A_hi (hi.lo)
 #pragma unroll 4
               for (int s = 0; s < nl; ++s) {
                 const int q = l0 + s;
                 const uint32_t ao = (uint32_t)(q / kSpc) * kAChunkDesc + (uint32_t)(q % kSpc) * 2;
-                if (leader) {
-                  if constexpr (PAIR) tc_mma_pair<F16>(tmem_d, a_hi0 + ao, db + 2 * (nh + s), kIdescPair, 1);
-                  else tc_mma<F16>(tmem_d, a_hi0 + ao, db + 2 * (nh + s), kIdesc, 1);
-                }
+                if (leader) tc_mma<F16>(tmem_d, a_hi0 + ao, db + 2 * (nh + s), kIdesc, 1);
               }
             }
             if (leader) {
-              if constexpr (PAIR) tc_commit_pair(b_empty(st), (uint16_t)3);
-              else if (mcast) tc_commit_mc(b_empty(st), (uint16_t)3);
+              if (mcast) tc_commit_mc(b_empty(st), (uint16_t)3);
               else tc_commit(b_empty(st));
             }
             if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
           }
-          if (leader) {
-            if constexpr (PAIR) tc_commit_pair(acc_full(buf), (uint16_t)3); else tc_commit(acc_full(buf));
-          }
+          if (leader) tc_commit(acc_full(buf));
         }
-        if (leader) {
-          if constexpr (PAIR) tc_commit_pair(a_free(asl), (uint16_t)3); else tc_commit(a_free(asl));
-        }
+        if (leader) tc_commit(a_free(asl));
       }
     }
   } else if (warp == kBuilderWarp0 || warp == kBuilderWarp0 + 1) {
@@ -393,14 +360,22 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
       const int64_t item = item_of(k);
       const int64_t t0 = (item / a.n_splits) * kTileM;
       const int64_t valid = max((int64_t)0, min((int64_t)kTileM, a.T - t0)) * D;  // (0 for the pair's phantom tile)
-      // (debug mode 9, timing only: every item re-reads the CTA's first tile — the full A build on repeating data)
+#ifdef KHG_EXPERIMENTS
+      // (9, timing only: every item re-reads the CTA's first tile — the full A build on repeating data)
       const float *src = a.feats + (a.debug_mode == 9 ? item_of(k_first) / a.n_splits * kTileM : t0) * D;
+#else
+      const float *src = a.feats + t0 * D;
+#endif
       // The tile's features come straight from HBM (every frame is read once per E-step), so the loads
       // are issued kABatch at a time per thread — a one-load-per-iteration loop pays the full DRAM
       // latency ~80 times in a row, during which the tensor pipe waits for A — and the first batch is
       // already in registers when the MMAs of the previous item release the A buffer.
       constexpr int kABatch = 16;
+#ifdef KHG_EXPERIMENTS
       const int n_el = (a.debug_mode == 8 && a_it > 0) ? 0 : kTileM * D;  // (8, timing only: A built once)
+#else
+      const int n_el = kTileM * D;
+#endif
       const uint32_t asl = a_it & a_two, aph = (a_two ? a_it >> 1 : a_it) & 1;
       uint8_t *a_ptr = base_ptr + asl * kASlotBytes;
       float xs[kABatch], ys[kABatch];
@@ -433,10 +408,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
       };
       constexpr int kStep = kBuilderThreads * kABatch;
       load_batch(xs, b);
-      unsigned long long tt0 = 0, tt1 = 0;
-      if (a.timing && b == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt0));
       if (b == 0) mbar_wait(a_free(asl), aph ^ 1);
-      if (a.timing && b == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt1));
       asm volatile("bar.sync 1, 64;" ::: "memory");
       for (int e0 = b; e0 < n_el; e0 += 2 * kStep) {  // the next batch's loads are in flight under the stores
         const int e1 = e0 + kStep, e2 = e1 + kStep;
@@ -447,16 +419,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 64;" ::: "memory");
-      if (b == 0) {
-        if (pairmma) mbar_arrive_cluster(mapa_cta(a_full(asl), 0)); else mbar_arrive(a_full(asl));
-        if (a.timing) {
-          unsigned long long tt2;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt2));
-          a.timing[4 * blockIdx.x + 0] += tt1 - tt0;
-          a.timing[4 * blockIdx.x + 1] += tt2 - tt1;
-          a.timing[4 * blockIdx.x + 3] += 1;
-        }
-      }
+      if (b == 0) mbar_arrive(a_full(asl));
     }
   } else if (warp < kEpiWarps) {
     // ===================== epilogue =====================
@@ -472,11 +435,17 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
       const int64_t t = (item / a.n_splits) * kTileM + row;
       const bool valid = t < a.T;
       // rows beyond T store into a scratch word (ld_bytes = 0): no predicate in the hot loop
-      // (experiments, timing only: 10 = every tile stores into the block's first 128 frames — an L2-resident
-      // window, no DRAM write stream; 11 = every store goes to the scratch word — no store traffic at all)
+#ifdef KHG_EXPERIMENTS
+      // (timing only: 10 = every tile stores into the block's first 128 frames — an L2-resident window, no DRAM
+      // write stream; 11 = every store goes to the scratch word)
       const bool to_scratch = !valid || a.debug_mode == 11;
       char *out_t = to_scratch ? reinterpret_cast<char *>(a.scratch) : reinterpret_cast<char *>(a.out + (a.debug_mode == 10 ? (int64_t)row : t));
       const uint32_t ld_bytes = to_scratch ? 0u : (uint32_t)(a.ld * 4);
+#else
+      // rows beyond T store into a scratch word (ld_bytes = 0): no predicate in the hot loop
+      char *out_t = valid ? reinterpret_cast<char *>(a.out + t) : reinterpret_cast<char *>(a.scratch);
+      const uint32_t ld_bytes = valid ? (uint32_t)(a.ld * 4) : 0u;
+#endif
       EpiState e;
       e.scale = a.scale;
       e.nan_acc = 0.f;
@@ -495,7 +464,10 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
         mbar_wait(acc_full(buf), (acc_it >> 1) & 1);
         tc_fence_after();
         e.trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256;
-        if (a.debug_mode == 0 && nr > 0) {
+#ifdef KHG_EXPERIMENTS
+        if (a.debug_mode == 1) nr = 0;  // (1 = the epilogue skips the LSE: pipeline ceiling)
+#endif
+        if (nr > 0) {
           tc_ld16_issue(e.trow + (e.d & 0xffu), e.t);
 #define KHG_CASE(L) case L: epi_run<L, KHG_TWO>(e, cnt); break;
 #define KHG_CASE2(L) case 16 + L: epi_run2<L>(e, cnt); break;
@@ -550,9 +522,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          if (pairmma) mbar_arrive_cluster(mapa_cta(acc_empty(buf), 0)); else mbar_arrive(acc_empty(buf));
-        }
+        if (lane == 0) mbar_arrive(acc_empty(buf));
       }
       const float nan_acc = e.nan_acc;
       if (valid && nan_acc != nan_acc) bad = true;  // r*0 is NaN exactly for a NaN/Inf result
@@ -565,10 +535,7 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
   if (clu) cluster_sync_all();  // no CTA leaves while its peer can still multicast into it
   if (warp == kMmaWarp) {
     tc_fence_after();
-    if constexpr (PAIR)
-      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-    else
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -861,40 +828,24 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
     set_error("ld_out too large for the tensor-core kernel (needs ld_out < 2^30)");
     return KHG_ERR_UNSUPPORTED;
   }
-  {
-    const char *dbg = getenv("KHG_TC_DEBUG_MODE");
-    a.debug_mode = dbg ? atoi(dbg) : 0;
-  }
+  a.debug_mode = 0;
+#ifdef KHG_EXPERIMENTS
+  if (const char *dbg = getenv("KHG_TC_DEBUG_MODE")) a.debug_mode = atoi(dbg);
+#endif
   const size_t smem = (size_t)a.a_slots * a_bytes + (size_t)a.stages * kBStageBytes + 256 + 1024;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    for (auto fn : {loglikes_tc_kernel<F16, false, false, false>, loglikes_tc_kernel<F16, true, false, false>,
-                    loglikes_tc_kernel<F16, false, true, false>, loglikes_tc_kernel<F16, true, true, false>,
-                    loglikes_tc_kernel<F16, false, false, true>, loglikes_tc_kernel<F16, true, false, true>})
-      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  KHG_CUDA_TRY(attr_err);
+  auto kern = t.two_chunk_segs ? (t.grouped_segs ? loglikes_tc_kernel<F16, true, true> : loglikes_tc_kernel<F16, true, false>)
+                               : (t.grouped_segs ? loglikes_tc_kernel<F16, false, true> : loglikes_tc_kernel<F16, false, false>);
+  // (an attribute of the function on the CURRENT device: set on every launch, so that khg_set_device works)
+  KHG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   unsigned grid = (unsigned)std::min<int64_t>(a.n_items, m->sm_count);
   if (const char *mc = getenv("KHG_TC_MAX_CTAS")) grid = std::min<unsigned>(grid, (unsigned)std::max(1, atoi(mc)));  // experiments
-  auto kern = t.two_chunk_segs ? (t.grouped_segs ? loglikes_tc_kernel<F16, true, true, false> : loglikes_tc_kernel<F16, true, false, false>)
-                               : (t.grouped_segs ? loglikes_tc_kernel<F16, false, true, false> : loglikes_tc_kernel<F16, false, false, false>);
-  a.timing = nullptr;
-  static unsigned long long *d_timing = nullptr;
-  const bool want_timing = getenv("KHG_TC_TIMING") != nullptr;
-  if (want_timing) {
-    if (!d_timing) cudaMalloc(&d_timing, sizeof(unsigned long long) * 4 * 1024);
-    cudaMemsetAsync(d_timing, 0, sizeof(unsigned long long) * 4 * 1024, m->stream);
-    a.timing = d_timing;
-  }
   // CTA pairs (clusters of 2) share the streamed operand through TMA multicast when every CTA has
   // whole frame tiles to itself and there are enough of them (KHG_TC_CLUSTER=0 forces the plain form)
   const char *cl = getenv("KHG_TC_CLUSTER");
   a.cluster = (a.n_splits == 1 && n_m >= 2LL * m->sm_count && grid >= 2 && !(cl && atoi(cl) == 0)) ? 2 : 1;
-  if (a.cluster == 2 && cl && atoi(cl) == 3 && !t.grouped_segs) {  // cta_group::2 MMAs across the pair
-    a.cluster = 3;
-    kern = t.two_chunk_segs ? loglikes_tc_kernel<F16, true, false, true> : loglikes_tc_kernel<F16, false, false, true>;
-  }
+#ifdef KHG_EXPERIMENTS
+  if (a.debug_mode == 6 || a.debug_mode == 7) a.cluster = 1;
+#endif
   if (a.cluster >= 2) {
     grid &= ~1u;
     cudaLaunchConfig_t cfg = {};
@@ -912,8 +863,6 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
     if (cudaLaunchKernelEx(&cfg, kern, F16 ? t.hmap_hi : t.map_hi, F16 ? t.hmap_lo : t.map_lo, a) != cudaSuccess) {
       (void)cudaGetLastError();  // pairs cannot be scheduled here (e.g. a partitioned GPU): the plain form
       a.cluster = 1;
-      kern = t.two_chunk_segs ? (t.grouped_segs ? loglikes_tc_kernel<F16, true, true, false> : loglikes_tc_kernel<F16, true, false, false>)
-                              : (t.grouped_segs ? loglikes_tc_kernel<F16, false, true, false> : loglikes_tc_kernel<F16, false, false, false>);
       kern<<<grid, kTcThreads, smem, m->stream>>>(F16 ? t.hmap_hi : t.map_hi, F16 ? t.hmap_lo : t.map_lo, a);
     }
   } else {
@@ -921,21 +870,12 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   }
   ++g_launch_count;
   KHG_CUDA_TRY(cudaGetLastError());
-  if (want_timing) {  // diagnostics: per-item averages over the CTAs of this launch
-    std::vector<unsigned long long> h(4 * grid);
-    cudaStreamSynchronize(m->stream);
-    cudaMemcpy(h.data(), d_timing, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost);
-    double w = 0, bld = 0, mw = 0, items = 0;
-    for (unsigned i = 0; i < grid; ++i) { w += h[4 * i]; bld += h[4 * i + 1]; mw += h[4 * i + 2]; items += h[4 * i + 3]; }
-    if (items > 0)
-      fprintf(stderr, "K1 timing (f16=%d): per item: builder waits a_free %.1f us, builds A %.1f us; MMA warp waits a_full %.1f us (%g items)\n",
-              (int)F16, w / items / 1e3, bld / items / 1e3, mw / items / 1e3, items);
-  }
   return KHG_OK;
 }
 
 // precision: 0 = automatic (fp16 split when the model fits and, decided on the device per
-// call, the features fit; tf32 split otherwise), 1 = force the tf32 split, 2 = force fp16.
+// call, the features fit; tf32 split otherwise), 1 = force the tf32 split, 2 = force fp16,
+// 3 = force fp16 in the Gaussian-stationary form.
 khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t ld_out,
                        int precision, const unsigned **simt_gate, float *gate_limit) {
   TcPack &t = m->tc;
@@ -949,7 +889,7 @@ khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scal
     latch_error_kernel<<<1, 1, 0, m->stream>>>(m->d_err, ERR_NONFINITE);
     ++g_launch_count;
   }
-  if (precision == 2 && !t.f16_ready) {
+  if (precision >= 2 && !t.f16_ready) {
     set_error("the fp16-split tensor-core path does not fit this model (parameter range or -inf gconsts)");
     return KHG_ERR_UNSUPPORTED;
   }
@@ -958,14 +898,12 @@ khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scal
     return KHG_ERR_UNSUPPORTED;
   }
   if (precision == 1 || !t.f16_ready) return tc_launch<false>(m, d_feats, T, scale, d_out, ld_out, nullptr, 0);
-  // fp16 split: the Gaussian-stationary kernel whenever the model tile fits shared memory next to its
-  // feature ring (2D+2 <= 128 columns); the frame-stationary kernel below for the rest (e.g. 80-dim fbank)
-  if (gs_supported(m)) {
-    if (precision == 2) return gs_loglikes(m, d_feats, T, scale, d_out, ld_out, false, nullptr);
-    return gs_loglikes(m, d_feats, T, scale, d_out, ld_out, true,
-                       t.tf32_ready ? [](khg_model *mm, const float *f, int64_t n, float sc, float *o, int64_t ld, const unsigned *gate) {
-                         return tc_launch<false>(mm, f, n, sc, o, ld, gate, 1);
-                       } : (khg_status(*)(khg_model *, const float *, int64_t, float, float *, int64_t, const unsigned *)) nullptr);
+  if (precision == 3) {  // the Gaussian-stationary form of the fp16 split (khg_loglikes_gs.cu), forced
+    if (!gs_supported(m)) {
+      set_error("the Gaussian-stationary fp16 kernel does not fit this model (fp16 range, or 2*dim+2 > 128)");
+      return KHG_ERR_UNSUPPORTED;
+    }
+    return gs_loglikes(m, d_feats, T, scale, d_out, ld_out);
   }
   if (precision == 2) return tc_launch<true>(m, d_feats, T, scale, d_out, ld_out, nullptr, 0);
   // automatic: one pass over the features finds max |x * 2^-k|; both kernels are launched and

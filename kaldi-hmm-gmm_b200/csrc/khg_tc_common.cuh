@@ -77,28 +77,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
-// Waits of the MMA issuer and the TMA producer.  -DKHG_SPIN_WAIT=1 makes them pure spins
-// (mbarrier.test_wait, never suspends) — measured: no difference (profiles/r1u_*), so the
-// suspending wait stays.
-#ifndef KHG_SPIN_WAIT
-#define KHG_SPIN_WAIT 0
-#endif
-__device__ __forceinline__ void mbar_wait_crit(uint32_t bar, uint32_t parity) {
-#if KHG_SPIN_WAIT
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-#else
-  mbar_wait(bar, parity);
-#endif
-}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -116,27 +94,6 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *
 }
 __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
-}
-// --- cta_group::2 forms (mode 3): ONE MMA of M = 256 per instruction spans the CTA pair — each CTA keeps
-// its own 128 frame rows of A and only HALF of the streamed operand's rows in shared memory (the
-// tensor cores of both SMs read both halves), so the bytes TMA writes into each SM halve.
-__device__ __forceinline__ uint32_t mapa_cta(uint32_t addr, uint32_t cta) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int x, int y) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(x), "r"(y)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -183,28 +140,6 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint32_t adesc_lo, uint3
         "mov.b64 db, {%2, %5};\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
-        : "memory");
-  }
-}
-template <bool F16>
-__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t idesc, uint32_t accum) {
-  if (F16) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %5};\n\t"
-        "mov.b64 db, {%2, %5};\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %5};\n\t"
-        "mov.b64 db, {%2, %5};\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
         : "memory");
   }
@@ -267,37 +202,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// 2^e for a pair of non-positive arguments on the FMA pipe instead of the MUFU (which the LSE of
-// G Gaussians per frame keeps busiest): round-to-nearest split e = n + f by the 1.5*2^23 trick,
-// degree-4 polynomial for 2^f on [-0.5, 0.5] (max relative error 2.6e-6, ~2^-18.5: below the
-// split-precision error of the accumulators), n added to the exponent field.  Packed fp32x2
-// arithmetic: 7 FFMA2/FADD2 + 2 FMNMX + 2 LEA per pair against 2 MUFU.EX2.
-// KHG_EXP_POLY_EVERY = k > 0: every k-th pair of a segment takes this path.
-#ifndef KHG_EXP_POLY_EVERY
-#define KHG_EXP_POLY_EVERY 0
-#endif
-__device__ __forceinline__ float2 exp2_poly2(float2 e) {
-  e.x = fmaxf(e.x, -120.f);
-  e.y = fmaxf(e.y, -120.f);
-  const float2 t = __fadd2_rn(e, make_float2(12582912.f, 12582912.f));
-  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
-  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), e);
-  float2 p = __ffma2_rn(f, make_float2(0.009570101276040077f, 0.009570101276040077f), make_float2(0.05591785907745361f, 0.05591785907745361f));
-  p = __ffma2_rn(p, f, make_float2(0.240247443318367f, 0.240247443318367f));
-  p = __ffma2_rn(p, f, make_float2(0.6931217908859253f, 0.6931217908859253f));
-  p = __ffma2_rn(p, f, make_float2(0.9999992847442627f, 0.9999992847442627f));
-  float2 r;
-  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
-  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
-  return r;
-}
-__device__ __forceinline__ float2 seg_exp2_pair(float2 v, int i) {
-  if (KHG_EXP_POLY_EVERY > 0 && (i % (KHG_EXP_POLY_EVERY > 0 ? KHG_EXP_POLY_EVERY : 1)) == KHG_EXP_POLY_EVERY - 1) return exp2_poly2(v);
-  v.x = fast_exp2(v.x);
-  v.y = fast_exp2(v.y);
-  return v;
-}
-
 // Max-subtracted log-sum-exp (csrc/eigen.cc:14-18) of the first L of 16 accumulator
 // columns held in registers, in two parts so that the TMEM load of the NEXT segment can be
 // issued into the same registers between them.  L is a compile-time constant so that no
@@ -333,7 +237,7 @@ struct SegLse {
     float2 s2;
 #pragma unroll
     for (int i = 0; i < kPairs; ++i) {
-      const float2 v = seg_exp2_pair(e2[i], i);
+      const float2 v = make_float2(fast_exp2(e2[i].x), fast_exp2(e2[i].y));
       s2 = i == 0 ? v : __fadd2_rn(s2, v);
     }
     float s = s2.x + s2.y;
@@ -346,7 +250,7 @@ struct SegLse {
     float2 s2;
 #pragma unroll
     for (int i = 0; i < kPairs; ++i) {
-      const float2 v = seg_exp2_pair(e2[i], i);
+      const float2 v = make_float2(fast_exp2(e2[i].x), fast_exp2(e2[i].y));
       s2 = i == 0 ? v : __fadd2_rn(s2, v);
     }
     float s = s2.x + s2.y;

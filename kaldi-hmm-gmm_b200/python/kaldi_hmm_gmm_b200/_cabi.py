@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("KHG_B200_LIB") or os.path.join(_HERE, "libkhg_b200.so
 KHG_OK, KHG_ERR_INVALID, KHG_ERR_CUDA, KHG_ERR_NONFINITE, KHG_ERR_UNSUPPORTED = range(5)
 KHG_HOST, KHG_DEVICE = 0, 1
 KHG_FRAME_MAJOR, KHG_PDF_MAJOR = 0, 1
-KHG_KERNEL_AUTO, KHG_KERNEL_SIMT, KHG_KERNEL_TCGEN05, KHG_KERNEL_TCGEN05_F16 = 0, 1, 2, 3
+KHG_KERNEL_AUTO, KHG_KERNEL_SIMT, KHG_KERNEL_TCGEN05, KHG_KERNEL_TCGEN05_F16, KHG_KERNEL_TCGEN05_F16_GS = 0, 1, 2, 3, 4
 
 # Every symbol include/khg_b200.h declares: (name, restype, argtypes)
 _vp = C.c_void_p
@@ -60,6 +60,7 @@ SYMBOLS = [
     ("khg_mle_update", _i32, [_vp, _vp, _vp, _u16, C.POINTER(_vp), C.POINTER(_f32), C.POINTER(_f32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     ("khg_model_download", _i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     ("khg_align_batch", _i32, [_vp, _vp, _vp, _i32, _vp, _i32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    ("khg_align_last_exact_count", _i64, []),
     ("khg_align_utterance_host", _i32, [_vp, _i32, _vp, _i64, _vp, _i32, _f32, _f32, _f32, _vp, C.POINTER(_i32), C.POINTER(_f32), _vp, _i32, C.POINTER(_i32)]),
     ("khg_gaussian_selection", _i32, [_vp, _i32, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, C.POINTER(C.c_double)]),
     ("khg_model_split_by_count", _i32, [_vp, _vp, _i32, _f32, _f32, _f32, _vp, _i64, C.c_uint64, C.POINTER(_vp), C.POINTER(_i32)]),

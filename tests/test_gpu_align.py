@@ -12,6 +12,28 @@ from oracle import khg_oracle as ko
 
 pytestmark = pytest.mark.gpu
 
+# khg_align_batch must return the REFERENCE's alignment (its order-dependent running cutoff included,
+# oracle tight=False) however the work is split between the certified device search and the exact
+# host decoder: "flagged" = the default (host pass only for utterances the device cannot certify),
+# "all" = every utterance through the host decoder, "none" = device search only, which is compared with
+# the order-independent rule it implements (oracle tight=True).
+_EXACT = {"mode": "flagged"}
+
+
+@pytest.fixture(autouse=True, params=["flagged", "all", "none"])
+def exact_mode(request, monkeypatch):
+    if request.param == "flagged":
+        monkeypatch.delenv("KHG_ALIGN_EXACT", raising=False)
+    else:
+        monkeypatch.setenv("KHG_ALIGN_EXACT", request.param)
+    _EXACT["mode"] = request.param
+    yield request.param
+    _EXACT["mode"] = "flagged"
+
+
+def _tight():
+    return _EXACT["mode"] == "none"
+
 
 def _batch(seed, n_utts, P=37, D=13, G=150, n_phones=(3, 14), noise=1.0, alt_prob=0.3):
     rng = np.random.default_rng(seed)
@@ -63,7 +85,7 @@ def _check(out, ll, gb, graphs, t2p, scale, beam, retry, pdf_ids):
     fo = gb.frame_offsets
     arc0 = 0
     for u, g in enumerate(graphs):
-        ref = ao.align_utterance(g, np.ascontiguousarray(ll[:, fo[u]:fo[u + 1]]), t2p, scale, beam=beam, retry_beam=retry, tight=True)
+        ref = ao.align_utterance(g, np.ascontiguousarray(ll[:, fo[u]:fo[u + 1]]), t2p, scale, beam=beam, retry_beam=retry, tight=_tight())
         assert out["status"][u] == ref["status"], (u, out["status"][u], ref["status"])
         got_ali = out["alignment"][fo[u]:fo[u + 1]]
         if ref["status"] == 2:
@@ -186,6 +208,28 @@ def test_align_batch_many_tokens_min_active_paths():
         _check(out, ll, gb, graphs, t2p, 1.0, beam, 0.0, pdf_ids)
 
 
+def test_recipe_beams_reference_rule_many_utterances(exact_mode):
+    """VERDICT r1 #1c: the reference's own pruning rule (oracle tight=False: running next_weight_cutoff in
+    HashList order) at the recipe's beams (egs/yesno/train.py:165-167: 6 / 40; 10 / 40) over 200 short
+    utterances and 16 C5-like ones (48 phones, ~500 frames): the batch call returns the reference's
+    alignment for every utterance, and most utterances are certified on the device (no host pass)."""
+    from kaldi_hmm_gmm_b200 import _cabi as A
+
+    if exact_mode != "flagged":
+        pytest.skip("default mode only")
+    total = flagged = 0
+    for seed, n_utts, n_phones, noise in ((71, 200, (4, 14), 1.5), (72, 16, (46, 50), 1.0)):
+        model, graphs, feats, t2p = _batch(seed, n_utts, n_phones=n_phones, noise=noise)
+        dm = _device_model(model)
+        for beam, retry in ((6.0, 40.0), (10.0, 40.0)):
+            out, ll, gb, pdf_ids = _run(dm, graphs, feats, t2p, 1.0, beam, retry)
+            flagged += A.lib().khg_align_last_exact_count()
+            total += n_utts
+            _check(out, ll, gb, graphs, t2p, 1.0, beam, retry, pdf_ids)
+    print(f"exact host pass: {flagged} of {total} utterances")
+    assert flagged < 0.6 * total
+
+
 def test_align_batch_feeds_acc_stats_on_device():
     """gmm-align-compiled -> gmm-acc-stats-ali without leaving the device: the pdf ids written by
     the aligner drive khg_acc_stats_ali; stats equal the oracle's on the oracle's alignment."""
@@ -255,7 +299,7 @@ def test_script_gmm_align_compiled_contract():
     like = 0.0
     for u, g in enumerate(graphs):
         ll, _ = ora.loglikes_all_pdfs(model, feats[u])
-        ref = ao.align_utterance(g, np.ascontiguousarray(ll.T), t2p, 0.5, beam=0.5, retry_beam=1e4, tight=True)
+        ref = ao.align_utterance(g, np.ascontiguousarray(ll.T), t2p, 0.5, beam=0.5, retry_beam=1e4, tight=_tight())
         retried += int(g.start >= 0 and ref["status"] != 0)
         if ref["status"] == 2:
             err += 1

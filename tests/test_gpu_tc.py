@@ -7,7 +7,7 @@ from oracle import khg_oracle as ko
 
 pytestmark = pytest.mark.gpu
 
-TC, SIMT, TC_F16, AUTO = 2, 1, 3, 0
+TC, SIMT, TC_F16, AUTO, TC_F16_GS = 2, 1, 3, 0, 4
 
 
 def _models(model):
@@ -375,3 +375,62 @@ def test_tc_cta_pair_multicast_path(oracle, T, monkeypatch):
         for sl in (slice(0, n), slice(T - n, T)):
             ref, _ = oracle.loglikes_all_pdfs(model, feats[sl])
             _check(pair[:, sl].T.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("D,P,G,T", [(40, 37, 350, 3000), (39, 13, 100, 1000), (40, 420, 4000, 700), (13, 5, 17, 129),
+                                     (60, 9, 200, 513), (5, 3, 3, 1), (39, 130, 1000, 40000)])
+def test_gaussian_stationary_f16_kernel_vs_oracle(oracle, D, P, G, T):
+    """KHG_KERNEL_TCGEN05_F16_GS (khg_loglikes_gs.cu): the model tile stays in shared memory, the pre-split
+    feature operand A' is streamed; same 3xFP16 arithmetic, same tolerance.  Work splits: whole rounds of model
+    tiles in lock step, leftover tiles dealt out by frame range, fewer units than SMs."""
+    model, means, vars_ = ko.make_synthetic_model(D, P, G, oracle=oracle)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, T)
+    dm = _one(model, TC_F16_GS)
+    assert dm.dense_kernel() == TC_F16_GS
+    sl = slice(0, T) if T <= 3000 else slice(T - 1500, T)
+    ref, bad = oracle.loglikes_all_pdfs(model, feats[sl])
+    assert bad == 0
+    _check(dm.loglikes_all_pdfs(feats)[sl], ref)
+    _check(dm.loglikes_all_pdfs(feats, scale=0.1, layout=1).T[sl] * 10.0, ref)
+
+
+@pytest.mark.parametrize("name,D,P,G", [("C4-lda-mllt", 40, 4200, 40000), ("C5-sat", 40, 5000, 100000)])
+def test_gaussian_stationary_baseline_shapes_and_length_classes(oracle, name, D, P, G):
+    """C4 (167 model tiles: one whole round + 19 leftover tiles) and C5 (two-load segments) device-resident with a
+    ragged tail and more frames than one A' sub-block; bit-identical to nothing, but within tolerance of the oracle and
+    of the frame-stationary kernel everywhere."""
+    import os
+
+    import torch
+
+    model, means, vars_ = ko.make_synthetic_model(D, P, G, oracle=oracle)
+    T = 148 * 128 * 8 + 128 * 3 + 5
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, T)
+    dfe = torch.from_numpy(feats).cuda()
+    gs, fs = _one(model, TC_F16_GS), _one(model, TC_F16)
+    a = gs.loglikes_all_pdfs(dfe, layout=1)
+    b = fs.loglikes_all_pdfs(dfe, layout=1)
+    gs.sync()
+    fs.sync()
+    assert bool(torch.isfinite(a).all()) and (a - b).abs().max().item() < 1e-3
+    for sl in (slice(0, 200), slice(T - 200, T), slice(148 * 128 * 8 - 100, 148 * 128 * 8 + 100)):
+        ref, bad = oracle.loglikes_all_pdfs(model, feats[sl], threads=os.cpu_count() or 1)
+        assert bad == 0
+        _check(a[:, sl].T.cpu().numpy(), ref)
+
+
+def test_gaussian_stationary_rejects_wide_features_and_raises_on_nonfinite(oracle):
+    from kaldi_hmm_gmm_b200 import DeviceModel
+
+    model, means, vars_ = ko.make_synthetic_model(80, 11, 100, oracle=oracle)
+    dm = DeviceModel(model.dim, model.offsets)
+    dm.upload(model.weights, model.means_invvars, model.inv_vars)
+    dm.set_kernel(TC_F16_GS)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, 50)
+    with pytest.raises(RuntimeError, match="Gaussian-stationary"):
+        dm.loglikes_all_pdfs(feats)
+    model, means, vars_ = ko.make_synthetic_model(40, 13, 100, oracle=oracle)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, 300)
+    feats[5, 2] = np.nan
+    with pytest.raises(RuntimeError, match="Invalid answer"):
+        _one(model, TC_F16_GS).loglikes_all_pdfs(feats)

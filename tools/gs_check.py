@@ -18,7 +18,7 @@ for D, P, G, T in [(40, 37, 350, 3000), (13, 5, 17, 129), (5, 3, 3, 1), (60, 9, 
                    (40, 420, 4000, 700), (40, 4200, 40000, 148 * 128 * 3 + 77), (40, 5000, 100000, 148 * 128 + 5)]:
     hm = host_model(D, P, G)
     outs = []
-    for k in (3, 1):
+    for k in (4, 1):
         dm = DeviceModel(D, hm["offsets"])
         dm.set_kernel(k)
         dm.upload(hm["weights"], hm["miv"], hm["iv"])
