@@ -343,6 +343,18 @@ void DiagGmm::RemoveComponents(const std::vector<int32_t> &gauss_in, bool renorm
   }
 }
 
+void DiagGmm::SetAllFromDevice(const float *w, const float *inv_vars, const float *means_invvars, const float *gconsts,
+                               int32_t nmix, int32_t dim) {
+  weights_.assign(w, w + nmix);
+  gconsts_.assign(gconsts, gconsts + nmix);
+  inv_vars_ = FloatMatrix(nmix, dim);
+  means_invvars_ = FloatMatrix(nmix, dim);
+  std::copy(inv_vars, inv_vars + (size_t)nmix * dim, inv_vars_.data.begin());
+  std::copy(means_invvars, means_invvars + (size_t)nmix * dim, means_invvars_.data.begin());
+  Bump();
+  valid_gconsts_ = true;
+}
+
 void DiagGmm::SetParams(const FloatVector *w, const FloatMatrix *inv_vars, const FloatMatrix *means_invvars) {
   if (w) weights_ = *w;
   if (inv_vars) inv_vars_ = *inv_vars;
@@ -377,35 +389,33 @@ void AmDiagGmm::SplitByCount(const FloatVector &state_occs, int32_t target_compo
   Check(khg_model_split_by_count(Device(), state_occs.data(), target_components, perturb_factor, power, min_count,
                                  randn ? randn->data.data() : nullptr, randn ? randn->rows : 0,
                                  seed ? seed : 0x9E3779B97F4A7C15ull + (++calls), &nm, nullptr));
-  RebuildFromDevice(nm);
+  AdoptDevice(nm, false);
 }
 
 void AmDiagGmm::MergeByCount(const FloatVector &state_occs, int32_t target_components, float power, float min_count) {
   KHG_HOST_ASSERT((int32_t)state_occs.size() == NumPdfs());
   khg_model *nm = nullptr;
   Check(khg_model_merge_by_count(Device(), state_occs.data(), target_components, power, min_count, &nm, nullptr));
-  RebuildFromDevice(nm);
+  AdoptDevice(nm, false);
 }
 
-// The host pdfs whose Gaussian count changed are rebuilt from the device result (takes ownership of nm).
-void AmDiagGmm::RebuildFromDevice(khg_model *nm) {
-  ModelHandle guard;
-  guard.h = nm;
+void AmDiagGmm::AdoptDevice(khg_model *nm, bool all_pdfs) {
+  auto h = std::make_shared<ModelHandle>();
+  h->h = nm;
   int32_t D = 0, P = 0, G = 0;
   Check(khg_model_info(nm, &D, &P, &G));
+  KHG_HOST_ASSERT(P == NumPdfs());
   std::vector<int32_t> offs(P + 1);
   std::vector<float> w(G), miv((size_t)G * D), iv((size_t)G * D), gc(G);
   Check(khg_model_download(nm, offs.data(), w.data(), miv.data(), iv.data(), gc.data()));
   for (int32_t p = 0; p < P; ++p) {
     const int32_t g0 = offs[p], n = offs[p + 1] - g0;
-    if (n == densities_[p]->NumGauss()) continue;  // neither split nor merged
-    FloatVector pw(w.begin() + g0, w.begin() + g0 + n);
-    FloatMatrix piv(n, D), pmiv(n, D);
-    std::copy(iv.begin() + (size_t)g0 * D, iv.begin() + (size_t)(g0 + n) * D, piv.data.begin());
-    std::copy(miv.begin() + (size_t)g0 * D, miv.begin() + (size_t)(g0 + n) * D, pmiv.data.begin());
-    densities_[p]->SetParams(&pw, &piv, &pmiv);
-    densities_[p]->ComputeGconsts();  // csrc/diag-gmm.cc:745, 850
+    if (!all_pdfs && n == densities_[p]->NumGauss()) continue;  // neither split nor merged
+    densities_[p]->SetAllFromDevice(w.data() + g0, iv.data() + (size_t)g0 * D, miv.data() + (size_t)g0 * D, gc.data() + g0, n, D);
   }
+  dev_ = h;
+  dev_sig_.clear();
+  for (auto &d : densities_) dev_sig_.emplace_back(d.get(), d->version());
 }
 
 int32_t AmDiagGmm::NumGauss() const {
@@ -731,6 +741,7 @@ void AccumAmDiagGmm::Init(const AmDiagGmm &model, GmmFlagsType flags) {
   dev_model_keep_.reset();
   dev_model_ = nullptr;
   dirty_ = false;
+  host_stats_ = false;
   total_frames_ = total_log_like_ = 0.0;  // fresh object semantics (members start at 0, .h:93-96)
   flags_ = AugmentGmmFlags(flags);
   for (int32_t i = 0; i < model.NumPdfs(); ++i) {
@@ -746,6 +757,7 @@ void AccumAmDiagGmm::Init(const AmDiagGmm &model, int32_t dim, GmmFlagsType flag
   dev_model_keep_.reset();
   dev_model_ = nullptr;
   dirty_ = false;
+  host_stats_ = false;
   total_frames_ = total_log_like_ = 0.0;
   flags_ = AugmentGmmFlags(flags);
   for (int32_t i = 0; i < model.NumPdfs(); ++i) {
@@ -803,6 +815,32 @@ void AccumAmDiagGmm::Flush() const {
   total_frames_ += tot[1];
   Check(khg_stats_zero(dev_->h));
   dirty_ = false;
+  host_stats_ = true;
+}
+
+void AccumAmDiagGmm::DeviceTotals(double tot[2]) const {
+  tot[0] = tot[1] = 0.0;
+  if (dev_ && dirty_) Check(khg_stats_download(dev_->h, nullptr, nullptr, nullptr, tot));
+}
+
+FloatVector AccumAmDiagGmm::PdfOccupancies() const {
+  FloatVector out(gmm_accumulators_.size(), 0.f);
+  DoubleVector occ;
+  if (dev_ && dirty_) {
+    int32_t dim = 0, P = 0, G = 0;
+    Check(khg_model_info(dev_model_, &dim, &P, &G));
+    occ.resize(G);
+    Check(khg_stats_download(dev_->h, occ.data(), nullptr, nullptr, nullptr));
+  }
+  size_t g0 = 0;
+  for (size_t p = 0; p < gmm_accumulators_.size(); ++p) {
+    double s = 0.0;
+    const size_t ng = gmm_accumulators_[p]->NumGauss();
+    for (size_t i = 0; i < ng; ++i) s += gmm_accumulators_[p]->occupancy()[i] + (occ.empty() ? 0.0 : occ[g0 + i]);
+    out[p] = (float)s;
+    g0 += ng;
+  }
+  return out;
 }
 
 float AccumAmDiagGmm::AccumulateForGmm(const AmDiagGmm &model, const FloatVector &data, int32_t gmm_index, float weight) {
@@ -848,6 +886,7 @@ void AccumAmDiagGmm::AccumulateForGaussian(const AmDiagGmm &am, const FloatVecto
                                            int32_t gauss_index, float weight) {
   KHG_HOST_ASSERT(gmm_index >= 0 && gmm_index < NumAccs());
   KHG_HOST_ASSERT(gauss_index >= 0 && gauss_index < am.GetPdf(gmm_index).NumGauss());
+  host_stats_ = true;
   gmm_accumulators_[gmm_index]->AccumulateForComponent(data, gauss_index, weight);
 }
 
@@ -867,12 +906,14 @@ const AccumDiagGmm &AccumAmDiagGmm::GetAcc(int32_t index) const {
 AccumDiagGmm &AccumAmDiagGmm::GetAcc(int32_t index) {
   KHG_HOST_ASSERT(index >= 0 && index < NumAccs());
   Flush();
+  host_stats_ = true;  // a mutable view: the caller may edit it
   return *gmm_accumulators_[index];
 }
 
 void AccumAmDiagGmm::Add(float scale, const AccumAmDiagGmm &other) {
   Flush();
   other.Flush();
+  host_stats_ = true;
   total_frames_ += scale * other.total_frames_;
   total_log_like_ += scale * other.total_log_like_;
   KHG_HOST_ASSERT(NumAccs() == other.NumAccs());
@@ -910,6 +951,25 @@ double AccumAmDiagGmm::AccumulateAlignment(const AmDiagGmm &model, const std::ve
 void MleAmDiagGmmUpdate(const MleDiagGmmOptions &config, const AccumAmDiagGmm &acc, GmmFlagsType flags,
                         AmDiagGmm *am_gmm, float *obj_change_out, float *count_out) {
   KHG_HOST_ASSERT(am_gmm != nullptr);
+  // Device M-step (khg_mle_update): when every statistic of this accumulator is still on the
+  // device and was gathered under the model's CURRENT pack, the update runs there — the 26 MB of statistics never
+  // leave the GPU — and the host pdfs are rebuilt from the new pack.  Anything else (statistics folded into or
+  // edited on the host, a model changed since the E-step) takes the host path below.
+  if (acc.dev_ && acc.dirty_ && !acc.host_stats_ && acc.NumAccs() == am_gmm->NumPdfs() && acc.Dim() == am_gmm->Dim() &&
+      acc.dev_model_ == am_gmm->Device()) {
+    khg_mle_options o;
+    o.min_gaussian_weight = config.min_gaussian_weight;
+    o.min_gaussian_occupancy = config.min_gaussian_occupancy;
+    o.min_variance = config.min_variance;
+    o.remove_low_count_gaussians = config.remove_low_count_gaussians ? 1 : 0;
+    khg_model *nm = nullptr;
+    float obj = 0.f, cnt = 0.f;
+    Check(khg_mle_update(acc.dev_model_, acc.dev_->h, &o, flags, &nm, &obj, &cnt, nullptr, nullptr, nullptr));
+    am_gmm->AdoptDevice(nm, true);
+    if (obj_change_out) *obj_change_out = obj;
+    if (count_out) *count_out = cnt;
+    return;
+  }
   acc.Flush();
   if (acc.Dim() != am_gmm->Dim()) Throw("Dimensions of accumulator and gmm do not match");
   KHG_HOST_ASSERT(acc.NumAccs() == am_gmm->NumPdfs());

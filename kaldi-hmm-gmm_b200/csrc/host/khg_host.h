@@ -139,6 +139,9 @@ class DiagGmm {
   uint64_t version() const { return version_; }
   // direct parameter replacement used by the M-step (DiagGmmNormal::CopyToDiagGmm)
   void SetParams(const FloatVector *w, const FloatMatrix *inv_vars, const FloatMatrix *means_invvars);
+  // all parameters INCLUDING the gconsts the device computed for them (device M-step / mix-up results)
+  void SetAllFromDevice(const float *w, const float *inv_vars, const float *means_invvars, const float *gconsts, int32_t nmix,
+                        int32_t dim);
 
  private:
   khg_model *Device() const;  // 1-pdf device pack of this GMM, rebuilt when stale
@@ -177,9 +180,10 @@ class AmDiagGmm {
   void SplitByCount(const FloatVector &state_occs, int32_t target_components, float perturb_factor, float power,
                     float min_count, const FloatMatrix *randn = nullptr, uint64_t seed = 0);  // csrc/am-diag-gmm.cc:72-89
   void MergeByCount(const FloatVector &state_occs, int32_t target_components, float power, float min_count);  // :91-108
- private:
-  void RebuildFromDevice(khg_model *nm);
- public:
+  // Takes ownership of a device model produced FROM this model's pack (M-step, split, merge): the host
+  // pdfs are rebuilt from it (all of them, or only those whose Gaussian count changed) and it becomes
+  // the current device pack, so the next E-step neither re-uploads nor re-packs anything.
+  void AdoptDevice(khg_model *nm, bool all_pdfs);
 
   // Device pack of the whole model (K4), rebuilt when any pdf changed.  Requires
   // valid gconsts on every pdf (csrc/decodable-am-diag-gmm.cc:49-53).
@@ -257,8 +261,13 @@ class AccumAmDiagGmm {
                              int32_t gauss_index, float weight);                                             // :88-97
   int32_t NumAccs() const { return (int32_t)gmm_accumulators_.size(); }
   float TotStatsCount() const;                                          // :99-106
-  float TotCount() const { Flush(); return (float)total_frames_; }     // csrc/mle-am-diag-gmm.h:72-76 (float!)
-  float TotLogLike() const { Flush(); return (float)total_log_like_; }
+  // csrc/mle-am-diag-gmm.h:72-76 (float!); the device part is read without moving the statistics
+  float TotCount() const { double t[2]; DeviceTotals(t); return (float)(total_frames_ + t[1]); }
+  float TotLogLike() const { double t[2]; DeviceTotals(t); return (float)(total_log_like_ + t[0]); }
+  // per-pdf occupancy (sum over the pdf's Gaussians): what gmm-est hands to SplitByCount / MergeByCount
+  // (scripts/gmm_est.py:66-73); only the occupancy vector leaves the device
+  FloatVector PdfOccupancies() const;
+  bool StatsOnDevice() const { return dev_ && dirty_ && !host_stats_; }
   const AccumDiagGmm &GetAcc(int32_t index) const;                      // :108-117
   AccumDiagGmm &GetAcc(int32_t index);
   void Add(float scale, const AccumAmDiagGmm &other);                   // :119-128
@@ -280,6 +289,7 @@ class AccumAmDiagGmm {
 
  private:
   void EnsureDevice(const AmDiagGmm &model) const;
+  void DeviceTotals(double tot[2]) const;  // {tot_like, tot_frames} still on the device (0 when clean)
   std::vector<std::unique_ptr<AccumDiagGmm>> gmm_accumulators_;
   mutable double total_frames_ = 0.0, total_log_like_ = 0.0;
   GmmFlagsType flags_ = 0;
@@ -287,6 +297,9 @@ class AccumAmDiagGmm {
   mutable khg_model *dev_model_ = nullptr;
   mutable std::shared_ptr<ModelHandle> dev_model_keep_;
   mutable bool dirty_ = false;
+  // the HOST accumulators may hold statistics (folded in by Flush, accumulated or edited on the host): the
+  // device M-step then cannot consume the device buffer alone
+  mutable bool host_stats_ = false;
   friend void MleAmDiagGmmUpdate(const MleDiagGmmOptions &, const AccumAmDiagGmm &, GmmFlagsType, AmDiagGmm *,
                                  float *, float *);
 };

@@ -258,9 +258,19 @@ PYBIND11_MODULE(_khg_b200, m) {
            [](const AmDiagGmm &s, const FArr &feats, float scale) {
              if (feats.ndim() != 2 || feats.shape(1) != s.Dim()) throw std::runtime_error("feats must be (T, dim)");
              py::array_t<float> out({(py::ssize_t)feats.shape(0), (py::ssize_t)s.NumPdfs()});
-             if (feats.shape(0) > 0)
-               Check(khg_loglikes_all_pdfs(s.Device(), feats.data(), feats.shape(0), KHG_HOST, scale, KHG_FRAME_MAJOR,
-                                           out.mutable_data(), s.NumPdfs(), KHG_HOST));
+             if (feats.shape(0) > 0) {
+               khg_model *dev = s.Device();
+               const float *fp = feats.data();
+               float *op = out.mutable_data();
+               const int64_t T = feats.shape(0);
+               const int32_t P = s.NumPdfs();
+               khg_status st;
+               {
+                 py::gil_scoped_release nogil;
+                 st = khg_loglikes_all_pdfs(dev, fp, T, KHG_HOST, scale, KHG_FRAME_MAJOR, op, P, KHG_HOST);
+               }
+               Check(st);
+             }
              return out;
            },
            py::arg("feats"), py::arg("scale") = 1.0f)
@@ -284,12 +294,21 @@ PYBIND11_MODULE(_khg_b200, m) {
              py::array_t<int64_t> poff((py::ssize_t)U + 1);
              int64_t cap = want_paths ? T + T / 2 + 16 * (int64_t)U + 1024 : 0;
              py::array_t<int32_t> paths;
+             khg_model *dev = s.Device();
              for (;;) {
                paths = py::array_t<int32_t>((py::ssize_t)cap);
-               khg_status st = khg_align_batch(s.Device(), &gb, feats.data(), KHG_HOST, tid2pdf.data(), (int32_t)tid2pdf.shape(0),
-                                               acoustic_scale, beam, retry_beam, ali.mutable_data(), status.mutable_data(),
-                                               like.mutable_data(), want_paths ? paths.mutable_data() : nullptr,
-                                               poff.mutable_data(), cap, nullptr);
+               int32_t *pa = want_paths ? paths.mutable_data() : nullptr, *al = ali.mutable_data(), *stp = status.mutable_data();
+               float *lk = like.mutable_data();
+               int64_t *po = poff.mutable_data();
+               const float *fp = feats.data();
+               const int32_t *t2p = tid2pdf.data();
+               const int32_t n_tids = (int32_t)tid2pdf.shape(0);
+               khg_status st;
+               {
+                 py::gil_scoped_release nogil;
+                 st = khg_align_batch(dev, &gb, fp, KHG_HOST, t2p, n_tids, acoustic_scale, beam, retry_beam, al, stp, lk, pa, po, cap,
+                                      nullptr);
+               }
                if (st != KHG_OK && want_paths && std::string(khg_last_error()).find("path_capacity") != std::string::npos) {
                  cap *= 4;
                  continue;
@@ -453,7 +472,11 @@ PYBIND11_MODULE(_khg_b200, m) {
                if (!w || w.ndim() != 1 || w.shape(0) != feats.shape(0)) throw std::runtime_error("len(weights) != num frames");
                wp = w.data();
              }
-             return s.AccumulateFrames(model, feats.data(), feats.shape(0), pdf_ids.data(), wp);
+             const float *fp = feats.data();
+             const int32_t *ip = pdf_ids.data();
+             const int64_t T = feats.shape(0);
+             py::gil_scoped_release nogil;  // a host thread pool can feed several GPUs / streams from Python
+             return s.AccumulateFrames(model, fp, T, ip, wp);
            },
            py::arg("model"), py::arg("feats"), py::arg("pdf_ids"), py::arg("weights") = py::none())
       .def("accumulate_alignment",
@@ -469,17 +492,34 @@ PYBIND11_MODULE(_khg_b200, m) {
                  throw std::runtime_error("transition_accs must be a writeable float64 array of size num_transition_ids+1");
                tp = ta.mutable_data();
              }
-             return s.AccumulateAlignment(model, t2p, feats.data(), feats.shape(0), ali.data(), tp);
+             const float *fp = feats.data();
+             const int32_t *ap = ali.data();
+             const int64_t T = feats.shape(0);
+             py::gil_scoped_release nogil;
+             return s.AccumulateAlignment(model, t2p, fp, T, ap, tp);
            },
            py::arg("model"), py::arg("transition_model"), py::arg("feats"), py::arg("ali"),
            py::arg("transition_accs") = py::none())
-      .def("flush", &AccumAmDiagGmm::Flush);
+      .def("flush", &AccumAmDiagGmm::Flush)
+      // diagnostics: True while every accumulated statistic is still on the device and none was folded into the host
+      // accumulators — the condition under which mle_am_diag_gmm_update runs the device M-step
+      .def_property_readonly("stats_on_device", &AccumAmDiagGmm::StatsOnDevice)
+      // per-pdf occupancies for mix-up / mix-down without moving the mean / variance statistics
+      .def("pdf_occupancies", [](const AccumAmDiagGmm &s) {
+        FloatVector v = s.PdfOccupancies();
+        py::array_t<float> out((py::ssize_t)v.size());
+        std::copy(v.begin(), v.end(), out.mutable_data());
+        return out;
+      });
 
   m.def(
       "mle_am_diag_gmm_update",
       [](const MleDiagGmmOptions &config, const AccumAmDiagGmm &acc, GmmFlagsType flags, AmDiagGmm *am_gmm) {
         float oc, c;
-        MleAmDiagGmmUpdate(config, acc, flags, am_gmm, &oc, &c);
+        {
+          py::gil_scoped_release nogil;
+          MleAmDiagGmmUpdate(config, acc, flags, am_gmm, &oc, &c);
+        }
         return std::make_pair(oc, c);
       },
       py::arg("config"), py::arg("amdiag_gmm_acc"), py::arg("flags"), py::arg("am_gmm"));
@@ -516,19 +556,32 @@ PYBIND11_MODULE(_khg_b200, m) {
                      d.NumFramesReady(), self, false);
       });
 
+  // the object handed in as `tm` is kept and returned by .transition_model, like the reference's
+  // TransModel() (python/csrc/decodable-am-diag-gmm.cc:26, csrc/decodable-am-diag-gmm.h:104)
+  struct ScaledWithTm : DecodableAmDiagGmmScaled {
+    using DecodableAmDiagGmmScaled::DecodableAmDiagGmmScaled;
+    py::object tm;
+  };
   py::class_<DecodableAmDiagGmmScaled, DecodableAmDiagGmmUnmapped>(m, "DecodableAmDiagGmmScaled")
       .def(py::init([](const AmDiagGmm &am, const py::object &tm, const FArr &feats, float scale, float prune) {
-             return new DecodableAmDiagGmmScaled(am, Tid2Pdf(tm), ToMat(feats), scale, prune);
+             auto *d = new ScaledWithTm(am, Tid2Pdf(tm), ToMat(feats), scale, prune);
+             d->tm = tm;
+             return static_cast<DecodableAmDiagGmmScaled *>(d);
            }),
-           py::arg("am"), py::arg("tm"), py::arg("feats"), py::arg("scale"), py::arg("log_sum_exp_prune") = -1.0,
-           py::keep_alive<1, 3>())
+           py::arg("am"), py::arg("tm"), py::arg("feats"), py::arg("scale"), py::arg("log_sum_exp_prune") = -1.0)
+      .def_property_readonly("transition_model", [](DecodableAmDiagGmmScaled &self) -> py::object {
+        auto *d = dynamic_cast<ScaledWithTm *>(&self);
+        return d ? d->tm : py::none();
+      })
       // new: wrap one utterance's (num_pdfs x num_frames) slice of a batched all-pdf block
       .def_static(
           "from_block",
           [](const FArr &block, const py::object &tm, float scale) {
             if (block.ndim() != 2) throw std::runtime_error("block must be (num_pdfs, num_frames)");
             std::vector<float> b(block.data(), block.data() + block.size());
-            return new DecodableAmDiagGmmScaled(std::move(b), (int32_t)block.shape(0), (int32_t)block.shape(1), Tid2Pdf(tm), scale);
+            auto *d = new ScaledWithTm(std::move(b), (int32_t)block.shape(0), (int32_t)block.shape(1), Tid2Pdf(tm), scale);
+            d->tm = tm;
+            return static_cast<DecodableAmDiagGmmScaled *>(d);
           },
           py::arg("block"), py::arg("tm"), py::arg("scale"));
 }

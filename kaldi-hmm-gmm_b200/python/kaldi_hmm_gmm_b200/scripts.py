@@ -31,23 +31,40 @@ def gmm_acc_stats_ali(am_gmm, gmm_accs, transition_model, feats, ali: List[int],
     assert feats.ndim == 2, feats.shape
     assert len(ali) == feats.shape[0], (len(ali), feats.shape[0])
     t2p = _tid2pdf(transition_model)
+    given = transition_accs
     if transition_accs is None:
         # TransitionModel::InitStats: zeros(num_transition_ids + 1), csrc/transition-model.h:176-180
         transition_accs = np.zeros(t2p.size, np.float64)
+    elif hasattr(transition_accs, "detach"):
+        # a torch tensor: a float64 CPU tensor is updated IN PLACE through its numpy view (shared memory); anything
+        # else is accumulated in a float64 copy and written back into the caller's tensor below
+        t = transition_accs.detach()
+        if t.device.type == "cpu" and t.dtype.is_floating_point and t.element_size() == 8 and t.is_contiguous():
+            transition_accs = t.numpy()
+        else:
+            transition_accs = np.ascontiguousarray(t.cpu().numpy(), np.float64)
     else:
         transition_accs = _np(transition_accs, np.float64)
     log_like = gmm_accs.accumulate_alignment(model=am_gmm, transition_model=t2p, feats=feats,
                                              ali=_np(ali, np.int32), transition_accs=transition_accs)
+    if hasattr(given, "detach"):
+        if not np.shares_memory(transition_accs, given.detach().cpu().numpy() if given.device.type != "cpu" else given.detach().numpy()):
+            import torch
+
+            given.detach().copy_(torch.from_numpy(transition_accs).to(given.dtype))
+        return log_like, given
     return log_like, transition_accs
 
 
 def gmm_est(am_gmm, gmm_accs, transition_model=None, transition_accs=None, tcfg=None, gmm_opts=None, mixup: int = 0,
             mixdown: int = 0, perturb_factor: float = 0.01, power: float = 0.2, min_count: float = 20.0,
-            update_flags: str = "mvwt", verbose: bool = False):
+            update_flags: str = "mvwt", verbose: bool = False, randn=None, seed: int = 0):
     """Reference scripts/gmm_est.py:8-96 with its argument names and defaults: transition update
     (delegated to transition_model.mle_update when the object provides it), MleAmDiagGmmUpdate, then
     mix-down (`merge_by_count`) and mix-up (`split_by_count`) by the per-pdf occupancies, both on the
-    device.  Returns (objf_impr, count, avg_like_per_frame) (the reference prints them)."""
+    device.  Returns (objf_impr, count, avg_like_per_frame) (the reference prints them).
+    randn / seed (not in the reference, whose Split draws from a global generator): the standard-normal
+    vectors of the mix-up splits, (rows, dim) in the reference's order, or the seed they are drawn from."""
     flags = _ext.str_to_gmm_flags(update_flags)
     if flags & int(_ext.GmmUpdateFlags.kGmmTransitions) and hasattr(transition_model, "mle_update"):
         transition_model.mle_update(transition_accs, tcfg)
@@ -59,12 +76,14 @@ def gmm_est(am_gmm, gmm_accs, transition_model=None, transition_accs=None, tcfg=
         print("GMM update: Overall", objf_impr / count, "objective function improvement per frame over", count, "frames")
         print("GMM update: Overall avg like per frame =", tot_like / tot_t, "over", tot_t, "frames.")
     if mixup != 0 or mixdown != 0:
-        pdf_occs = np.asarray([gmm_accs.get_acc(i).occupancy.sum() for i in range(gmm_accs.num_accs)], np.float32)
+        # the reference sums get_acc(i).occupancy per pdf (scripts/gmm_est.py:66-69); here only the occupancy vector
+        # leaves the device
+        pdf_occs = np.asarray(gmm_accs.pdf_occupancies(), np.float32)
         if mixdown != 0:
             am_gmm.merge_by_count(state_occs=pdf_occs, target_components=mixdown, power=power, min_count=min_count)
         if mixup != 0:
             am_gmm.split_by_count(state_occs=pdf_occs, target_components=mixup, perturb_factor=perturb_factor, power=power,
-                                  min_count=min_count)
+                                  min_count=min_count, randn=randn, seed=seed)
     return objf_impr, count, (tot_like / tot_t if tot_t else float("nan"))
 
 

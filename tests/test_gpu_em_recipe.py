@@ -1,0 +1,203 @@
+"""BASELINE.json configs[0] as a system: the yesno monophone recipe's EM loop (reference
+egs/yesno/train.py:152-222) on synthetic data of its shape — 80-dim features
+(egs/yesno/local/compute_fbank_yesno.py:32), 11 pdfs (SIL 5 states, YES / NO 3 each: scripts/prepare_lang.py
+generate_hmm_topo defaults), equal-alignment start, realignment at scheduled iterations (beam 6 / retry 40,
+acoustic scale 0.1), mix-up towards a growing Gaussian target — driven ONLY through the reference-signature
+functions of this package (gmm_align_compiled_batch -> gmm_acc_stats_ali -> gmm_est), against the same loop
+driven by the CPU oracle (oracle/khg_oracle*.py, oracle/khg_align_oracle.py).
+
+Per iteration: alignments identical, average log-likelihood per frame within 1e-4 relative, Gaussian counts per
+pdf equal; at the end the re-estimated parameters within 1e-4 relative.  Also asserted: the statistics never
+leave the device (the class API's M-step runs khg_mle_update) and the model pack produced by the M-step / mix-up
+is adopted as the next iteration's device pack."""
+import numpy as np
+import pytest
+
+from oracle import khg_align_oracle as ao
+from oracle import khg_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+D = 80
+STATES = {0: 5, 1: 3, 2: 3}                      # phone -> HMM states: SIL, YES, NO
+FIRST = {0: 0, 1: 5, 2: 8}                       # first pdf (= HMM state) of each phone
+P = 11
+
+
+def _graph(rng, words):
+    """SIL? (w SIL?)*: a left-to-right chain with self loops; every silence is optional (epsilon skip).
+    transition-ids of HMM state k: 2k+1 self loop, 2k+2 forward.  Returns (graph, HMM-state chain of the
+    path that takes every silence)."""
+    arcs, n_states, cur, chain = [], 1, 0, []
+
+    def phone(src, ph, word):
+        nonlocal n_states
+        s = src
+        for k in range(STATES[ph]):
+            hs = FIRST[ph] + k
+            nxt = n_states
+            n_states += 1
+            arcs.append((s, 2 * hs + 2, word if k == 0 else 0, float(rng.uniform(0.2, 1.2)), nxt))
+            arcs.append((nxt, 2 * hs + 1, 0, float(rng.uniform(0.2, 1.2)), nxt))
+            chain.append(hs)
+            s = nxt
+        return s
+
+    def opt_sil(src):
+        end = phone(src, 0, 0)
+        arcs.append((src, 0, 0, float(rng.uniform(0.3, 0.9)), end))
+        return end
+
+    cur = opt_sil(cur)
+    for i, w in enumerate(words):
+        cur = phone(cur, w, i + 1)
+        cur = opt_sil(cur)
+    arcs.sort(key=lambda a: a[0])
+    src = np.array([a[0] for a in arcs], np.int32)
+    offs = np.zeros(n_states + 1, np.int32)
+    np.add.at(offs, src + 1, 1)
+    final = np.full(n_states, np.inf, np.float32)
+    final[cur] = 0.0
+    g = ao.Graph(np.cumsum(offs).astype(np.int32), np.array([a[1] for a in arcs], np.int32), np.array([a[2] for a in arcs], np.int32),
+                 np.array([a[3] for a in arcs], np.float32), np.array([a[4] for a in arcs], np.int32), final, 0)
+    return g, chain
+
+
+def _data(seed=2023, n_utts=30):
+    rng = np.random.default_rng(seed)
+    gen_means = (1.6 * rng.standard_normal((P, 2, D))).astype(np.float32)   # two modes per HMM state
+    gen_std = rng.uniform(0.7, 1.3, (P, 2, D)).astype(np.float32)
+    graphs, feats, chains = [], [], []
+    for _ in range(n_utts):
+        words = [int(x) for x in rng.integers(1, 3, int(rng.integers(3, 7)))]
+        g, chain = _graph(rng, words)
+        dur = rng.integers(2, 7, len(chain))
+        hs = np.repeat(np.asarray(chain), dur)
+        mode = rng.integers(0, 2, hs.size)
+        x = gen_means[hs, mode] + gen_std[hs, mode] * rng.standard_normal((hs.size, D)).astype(np.float32)
+        graphs.append(g)
+        feats.append(x.astype(np.float32))
+        chains.append(chain)
+    return graphs, feats, chains
+
+
+def _equal_alignment(chain, T):
+    """align-equal-compiled's outcome on a linear graph: the frames split evenly over the chain's states."""
+    n = len(chain)
+    bounds = np.linspace(0, T, n + 1).round().astype(int)
+    ali = []
+    for k, hs in enumerate(chain):
+        ln = bounds[k + 1] - bounds[k]
+        assert ln >= 1
+        ali += [2 * hs + 2] + [2 * hs + 1] * (ln - 1)
+    return ali
+
+
+def _packed_init(allf):
+    """gmm-init-mono: one Gaussian per pdf at the global mean / variance of the data."""
+    mean = allf.mean(0).astype(np.float32)
+    var = allf.var(0).astype(np.float32)
+    iv = np.tile((1.0 / var).astype(np.float32), (P, 1))
+    miv = np.tile((mean / var).astype(np.float32), (P, 1))
+    w = np.ones(P, np.float32)
+    gc = np.concatenate([ko.np_compute_gconsts(w[p:p + 1], miv[p:p + 1], iv[p:p + 1])[0] for p in range(P)])
+    return ko.PackedModel(np.arange(P + 1, dtype=np.int32), w, miv, iv, gc)
+
+
+def _am_from_packed(khg, model):
+    am = khg.AmDiagGmm()
+    for p in range(model.num_pdfs):
+        s = slice(model.offsets[p], model.offsets[p + 1])
+        g = khg.DiagGmm(nmix=s.stop - s.start, dim=model.dim)
+        g.set_weights(model.weights[s])
+        g.set_invvars_and_means(model.inv_vars[s], model.means_invvars[s] / model.inv_vars[s])
+        am.add_pdf(g)
+    assert am.compute_gconsts() == 0
+    return am
+
+
+def _oracle_mstep(ora, model, st, min_occ):
+    W, MIV, IV, GC, offs = [], [], [], [], [0]
+    for p in range(model.num_pdfs):
+        s = slice(model.offsets[p], model.offsets[p + 1])
+        r = ora.mle_update(model.weights[s], model.means_invvars[s], model.inv_vars[s], st["occ"][s], st["mean"][s], st["var"][s],
+                           min_gaussian_occupancy=min_occ)
+        W.append(r["weights"]), MIV.append(r["means_invvars"]), IV.append(r["inv_vars"]), GC.append(r["gconsts"])
+        offs.append(offs[-1] + r["weights"].size)
+    return ko.PackedModel(np.asarray(offs, np.int32), np.concatenate(W), np.concatenate(MIV), np.concatenate(IV), np.concatenate(GC))
+
+
+def test_yesno_shaped_em_loop_through_the_reference_signatures():
+    import kaldi_hmm_gmm_b200 as khg
+
+    graphs, feats, chains = _data()
+    allf = np.concatenate(feats, 0)
+    n_frames = allf.shape[0]
+    t2p = np.concatenate([[0], np.repeat(np.arange(P), 2)]).astype(np.int32)  # tid -> pdf, index 0 unused
+    ora = ko.Oracle()
+    ref_model = _packed_init(allf)
+    am = _am_from_packed(khg, ref_model)
+    tgs = [khg.TrainingGraph(g.arc_offsets, g.ilabel, g.olabel, g.weight, g.nextstate, g.final, g.start) for g in graphs]
+    cfg = khg.AlignConfig(beam=6.0, retry_beam=40.0)
+    ali = [_equal_alignment(c, f.shape[0]) for c, f in zip(chains, feats)]
+    ref_ali = [list(a) for a in ali]
+    rng = np.random.default_rng(7)
+    num_gauss, inc_gauss, realign = 11, 21, {1, 2, 3, 5, 8}
+    packs_seen = set()
+    for it in range(12):
+        if it in realign:
+            r = khg.gmm_align_compiled_batch(am, t2p, [f"u{i}" for i in range(len(tgs))], tgs, feats, cfg, acoustic_scale=0.1)
+            assert r["num_error"] == 0
+            ali = r["alignment"]
+            for u, g in enumerate(graphs):
+                ll = ora.loglikes_all_pdfs(ref_model, feats[u])[0]
+                a = ao.align_utterance(g, np.ascontiguousarray(ll.T), t2p, 0.1, beam=6.0, retry_beam=40.0, tight=False)
+                assert a["status"] != 2
+                ref_ali[u] = a["alignment"]
+            assert ali == ref_ali, f"iteration {it}: alignments differ"
+        # ---- E-step through the reference's script signature, one utterance at a time like the recipe
+        accs = khg.AccumAmDiagGmm()
+        accs.init(model=am, flags=khg.GmmUpdateFlags.kGmmAll)
+        tacc, tot = None, 0.0
+        for u in range(len(feats)):
+            ll, tacc = khg.gmm_acc_stats_ali(am_gmm=am, gmm_accs=accs, transition_model=t2p, feats=feats[u], ali=ali[u],
+                                             transition_accs=tacc)
+            tot += ll
+        assert accs.stats_on_device
+        assert tacc.sum() == n_frames and tacc[0] == 0
+        pdf_all = t2p[np.concatenate([np.asarray(a, np.int32) for a in ref_ali])]
+        st = ora.acc_stats_ali(ref_model, allf, pdf_all)
+        assert abs(tot - st["tot_like"]) <= 1e-4 * abs(st["tot_like"]), (it, tot / n_frames, st["tot_like"] / n_frames)
+        assert abs(accs.tot_log_like / accs.tot_count - st["tot_like"] / n_frames) <= 1e-4 * abs(st["tot_like"] / n_frames)
+        assert accs.stats_on_device, "reading the totals must not move the statistics"
+        # ---- M-step + mix-up through gmm_est
+        opts = khg.MleDiagGmmOptions()
+        opts.min_gaussian_occupancy = 3.0
+        randn = rng.standard_normal((num_gauss + 8, D)).astype(np.float32)
+        objf, count, avg = khg.gmm_est(am_gmm=am, gmm_accs=accs, transition_model=t2p, transition_accs=tacc, gmm_opts=opts,
+                                       mixup=num_gauss, perturb_factor=0.01, power=0.2, min_count=20.0, update_flags="mvw",
+                                       randn=randn)
+        assert accs.stats_on_device, "the class API's M-step and the occupancies for mix-up must run on the device buffer"
+        assert abs(count - n_frames) < 1e-2 * n_frames
+        ref_model = _oracle_mstep(ora, ref_model, st, 3.0)
+        ref_model, counts = _oracle_mixup(ref_model, st, pdf_all, num_gauss, randn)
+        got_counts = [am.num_gauss_in_pdf(p) for p in range(P)]
+        assert got_counts == counts, (it, got_counts, counts)
+        packs_seen.add(am.num_gauss)
+        if it < 9:
+            num_gauss += inc_gauss
+    assert am.num_gauss > 100 and len(packs_seen) >= 5
+    # re-estimated parameters after 12 iterations of E-step / M-step / mix-up / realignment
+    for p in range(P):
+        s = slice(ref_model.offsets[p], ref_model.offsets[p + 1])
+        g = am.get_pdf(p)
+        np.testing.assert_allclose(np.asarray(g.weights), ref_model.weights[s], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(np.asarray(g.means_invvars), ref_model.means_invvars[s], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(np.asarray(g.inv_vars), ref_model.inv_vars[s], rtol=1e-4, atol=1e-5)
+
+
+def _oracle_mixup(model, st, pdf_all, target, randn):
+    """scripts/gmm_est.py:66-73: per-pdf occupancies of the accumulators, then SplitByCount."""
+    pdf_occ = np.bincount(pdf_all, minlength=model.num_pdfs).astype(np.float32)  # weights are 1: occupancy = frame count
+    new = ko.np_split_by_count(model, pdf_occ, target, 0.01, 0.2, 20.0, randn)
+    return new, [int(new.offsets[p + 1] - new.offsets[p]) for p in range(new.num_pdfs)]

@@ -317,3 +317,77 @@ def test_decodables(oracle):
 
     m = Mine()
     assert m.log_likelihood(0, 1) == -1.5 and m.num_indices() == 3 and m.is_last_frame(0)
+
+
+def test_training_graph_from_fst_with_a_kaldifst_shaped_object(monkeypatch):
+    """TrainingGraph.from_fst walks an FST through the surface kaldifst.StdVectorFst exposes (`start`,
+    `num_states`, `final(s)`, `kaldifst.ArcIterator(fst, s)` with ilabel / olabel / weight / nextstate,
+    weights as objects with `.value` like kaldifst's TropicalWeight, or plain floats).  kaldifst is not
+    installed here, so a stand-in module with that surface is put in its place; the reference's own use is
+    scripts/gmm_align_compiled.py:36-41 / egs/yesno/train.py:176-186.  Host-only."""
+    import sys
+    import types
+    from collections import namedtuple
+
+    import kaldi_hmm_gmm_b200 as khg
+
+    Arc = namedtuple("Arc", "ilabel olabel weight nextstate")
+    W = namedtuple("W", "value")
+
+    class FakeFst:
+        start = 0
+        num_states = 4
+        _arcs = {0: [Arc(2, 7, W(0.5), 1), Arc(0, 0, W(0.25), 2)], 1: [Arc(1, 0, 0.75, 1), Arc(4, 0, W(1.5), 2)],
+                 2: [Arc(3, 0, W(0.125), 2), Arc(6, 9, W(2.0), 3)], 3: []}
+        _final = {3: W(0.375)}
+
+        def final(self, s):
+            return self._final.get(s, W(float("inf")))
+
+    fake = types.ModuleType("kaldifst")
+    fake.ArcIterator = lambda fst, s: iter(fst._arcs[s])
+    monkeypatch.setitem(sys.modules, "kaldifst", fake)
+    g = khg.TrainingGraph.from_fst(FakeFst())
+    assert g.start == 0 and g.arc_offsets.tolist() == [0, 2, 4, 6, 6]
+    assert g.ilabel.tolist() == [2, 0, 1, 4, 3, 6] and g.olabel.tolist() == [7, 0, 0, 0, 0, 9]
+    assert g.nextstate.tolist() == [1, 2, 1, 2, 2, 3]
+    np.testing.assert_array_equal(g.weight, np.asarray([0.5, 0.25, 0.75, 1.5, 0.125, 2.0], np.float32))
+    assert np.isinf(g.final[:3]).all() and g.final[3] == np.float32(0.375)
+    assert g.ilabel.dtype == np.int32 and g.weight.dtype == np.float32
+
+
+def test_decodable_scaled_keeps_its_transition_model_object():
+    """DecodableAmDiagGmmScaled.transition_model (reference python/csrc/decodable-am-diag-gmm.cc:26): the object
+    handed in as `tm`.  from_block needs no device, so this runs on the CPU."""
+    import kaldi_hmm_gmm_b200 as khg
+
+    class Tm:
+        id2pdf_id = np.asarray([0, 0, 1, 1], np.int32)
+
+    tm = Tm()
+    d = khg.DecodableAmDiagGmmScaled.from_block(np.zeros((2, 3), np.float32), tm, 0.5)
+    assert d.transition_model is tm and d.num_indices() == 3 and d.num_frames_ready() == 3
+
+
+def test_gmm_acc_stats_ali_updates_a_torch_transition_accs_in_place():
+    """scripts.gmm_acc_stats_ali: a float64 CPU torch tensor handed in as transition_accs is updated in place
+    (and returned); other dtypes are written back into the caller's tensor.  Uses a stand-in accumulator
+    (the batched call's contract: accumulate_alignment adds one count per frame), host-only."""
+    import torch
+
+    import kaldi_hmm_gmm_b200 as khg
+
+    class FakeAccs:
+        def accumulate_alignment(self, model, transition_model, feats, ali, transition_accs):
+            np.add.at(transition_accs, ali, 1.0)
+            return -1.5 * len(ali)
+
+    t2p = np.asarray([0, 0, 0, 1, 1], np.int32)
+    feats = np.zeros((4, 3), np.float32)
+    for dtype in (torch.float64, torch.float32):
+        acc = torch.zeros(5, dtype=dtype)
+        ll, out = khg.gmm_acc_stats_ali(am_gmm=None, gmm_accs=FakeAccs(), transition_model=t2p, feats=feats, ali=[1, 1, 3, 4],
+                                        transition_accs=acc)
+        assert out is acc and acc.tolist() == [0, 2, 0, 1, 1] and ll == -6.0
+    ll, out = khg.gmm_acc_stats_ali(am_gmm=None, gmm_accs=FakeAccs(), transition_model=t2p, feats=feats, ali=[2, 2, 2, 2])
+    assert out.dtype == np.float64 and out.tolist() == [0, 0, 4, 0, 0]
