@@ -155,6 +155,7 @@ def test_yesno_shaped_em_loop_through_the_reference_signatures():
                 assert a["status"] != 2
                 ref_ali[u] = a["alignment"]
             assert ali == ref_ali, f"iteration {it}: alignments differ"
+        start_model, num_gauss_now = _packed_from_am(am), num_gauss
         # ---- E-step through the reference's script signature, one utterance at a time like the recipe
         accs = khg.AccumAmDiagGmm()
         accs.init(model=am, flags=khg.GmmUpdateFlags.kGmmAll)
@@ -183,17 +184,38 @@ def test_yesno_shaped_em_loop_through_the_reference_signatures():
         ref_model, counts = _oracle_mixup(ref_model, st, pdf_all, num_gauss, randn)
         got_counts = [am.num_gauss_in_pdf(p) for p in range(P)]
         assert got_counts == counts, (it, got_counts, counts)
+        # one EM step from the SAME starting model (the device's model before this iteration, the same alignment):
+        # re-estimated parameters within 1e-4 relative (BASELINE.json); the free-running oracle loop above drifts by
+        # more than that over a dozen iterations, which is what iterating a map does, and is checked loosely at the end
+        st1 = ora.acc_stats_ali(start_model, allf, pdf_all)
+        one, _ = _oracle_mixup(_oracle_mstep(ora, start_model, st1, 3.0), st1, pdf_all, num_gauss_now, randn)
+        _assert_model_close(am, one, 1e-4, it)
         packs_seen.add(am.num_gauss)
         if it < 9:
             num_gauss += inc_gauss
     assert am.num_gauss > 100 and len(packs_seen) >= 5
-    # re-estimated parameters after 12 iterations of E-step / M-step / mix-up / realignment
-    for p in range(P):
-        s = slice(ref_model.offsets[p], ref_model.offsets[p + 1])
+    # after 12 iterations of E-step / M-step / mix-up / realignment the two free-running trajectories are still together
+    _assert_model_close(am, ref_model, 5e-3, "end")
+
+
+def _packed_from_am(am):
+    W, MIV, IV, GC, offs = [], [], [], [], [0]
+    for p in range(am.num_pdfs):
         g = am.get_pdf(p)
-        np.testing.assert_allclose(np.asarray(g.weights), ref_model.weights[s], rtol=1e-4, atol=1e-6)
-        np.testing.assert_allclose(np.asarray(g.means_invvars), ref_model.means_invvars[s], rtol=1e-4, atol=1e-4)
-        np.testing.assert_allclose(np.asarray(g.inv_vars), ref_model.inv_vars[s], rtol=1e-4, atol=1e-5)
+        W.append(np.array(g.weights, np.float32)), MIV.append(np.array(g.means_invvars, np.float32))
+        IV.append(np.array(g.inv_vars, np.float32)), GC.append(np.array(g.gconsts, np.float32))
+        offs.append(offs[-1] + W[-1].size)
+    return ko.PackedModel(np.asarray(offs, np.int32), np.concatenate(W), np.concatenate(MIV), np.concatenate(IV), np.concatenate(GC))
+
+
+def _assert_model_close(am, ref, rtol, where):
+    got = _packed_from_am(am)
+    assert got.offsets.tolist() == ref.offsets.tolist(), where
+    np.testing.assert_allclose(got.weights, ref.weights, rtol=rtol, atol=1e-6, err_msg=str(where))
+    np.testing.assert_allclose(got.inv_vars, ref.inv_vars, rtol=rtol, atol=rtol * np.abs(ref.inv_vars).max(), err_msg=str(where))
+    # means_invvars = mean / var changes sign: entries near zero are compared against the scale of their column
+    np.testing.assert_allclose(got.means_invvars, ref.means_invvars, rtol=rtol, atol=rtol * np.abs(ref.means_invvars).max(), err_msg=str(where))
+    np.testing.assert_allclose(got.gconsts, ref.gconsts, rtol=rtol, atol=1e-3, err_msg=str(where))
 
 
 def _oracle_mixup(model, st, pdf_all, target, randn):
