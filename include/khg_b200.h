@@ -85,7 +85,7 @@ typedef struct khg_model khg_model; /* device-resident packed AmDiagGmm      */
 typedef struct khg_stats khg_stats; /* device-resident packed AccumAmDiagGmm */
 
 const char *khg_last_error(void);
-int32_t khg_abi_version(void); /* 2 (1 + batched alignment, Gaussian selection, mix-up / mix-down) */
+int32_t khg_abi_version(void); /* 3 (2 + khg_align_utterance_host, khg_align_last_exact_count, KHG_KERNEL_TCGEN05_F16_GS) */
 
 khg_status khg_device_count(int32_t *count);
 khg_status khg_set_device(int32_t device);

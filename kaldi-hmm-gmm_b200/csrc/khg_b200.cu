@@ -82,7 +82,7 @@ using namespace khg;
 extern "C" {
 
 const char *khg_last_error(void) { return t_last_error.c_str(); }
-int32_t khg_abi_version(void) { return 2; }  // 2: + khg_align_batch, khg_gaussian_selection, khg_model_split/merge_by_count
+int32_t khg_abi_version(void) { return 3; }  // 3: + khg_align_utterance_host, khg_align_last_exact_count, KHG_KERNEL_TCGEN05_F16_GS
 int64_t khg_launch_count(void) { return g_launch_count; }
 
 khg_status khg_device_count(int32_t *count) {

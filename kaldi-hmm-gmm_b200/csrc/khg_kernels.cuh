@@ -488,6 +488,59 @@ __device__ __forceinline__ void stats_group_ll(const float *__restrict__ xr, con
   }
 }
 
+// The same for TWO frames per thread: every broadcast load of the model feeds both, which halves the
+// shared-memory wavefronts of phase A (the kernel's bound: 40 of them per frame before, ncu r2f).
+template <int NG>
+__device__ __forceinline__ void stats_group_ll2(const float *__restrict__ xr0, const float *__restrict__ xr1,
+                                                const float *__restrict__ mm, const float *__restrict__ vv, int D,
+                                                float (&aa0)[8], float (&bb0)[8], float (&aa1)[8], float (&bb1)[8]) {
+  float2 a0[4], b0[4], a1[4], b1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a0[j] = b0[j] = a1[j] = b1[j] = make_float2(0.f, 0.f);
+  const int D4 = D & ~3;
+#pragma unroll(kStatsUnrollA)
+  for (int d0 = 0; d0 < D4; d0 += 4) {
+    const float4 xq0 = *reinterpret_cast<const float4 *>(xr0 + d0);
+    const float4 xq1 = *reinterpret_cast<const float4 *>(xr1 + d0);
+    const float xs0[4] = {xq0.x, xq0.y, xq0.z, xq0.w}, xs1[4] = {xq1.x, xq1.y, xq1.z, xq1.w};
+#pragma unroll
+    for (int dd = 0; dd < 4; ++dd) {
+      const float x0 = xs0[dd], q0 = x0 * x0, x1 = xs1[dd], q1 = x1 * x1;  // data.array().square(), csrc/diag-gmm.cc:175
+      const float2 xx0 = make_float2(x0, x0), qq0 = make_float2(q0, q0), xx1 = make_float2(x1, x1), qq1 = make_float2(q1, q1);
+      const float4 ma = *reinterpret_cast<const float4 *>(mm + (d0 + dd) * 8);
+      const float4 va = *reinterpret_cast<const float4 *>(vv + (d0 + dd) * 8);
+      const float2 m01 = make_float2(ma.x, ma.y), m23 = make_float2(ma.z, ma.w), v01 = make_float2(va.x, va.y), v23 = make_float2(va.z, va.w);
+      a0[0] = __ffma2_rn(m01, xx0, a0[0]); a0[1] = __ffma2_rn(m23, xx0, a0[1]);
+      b0[0] = __ffma2_rn(v01, qq0, b0[0]); b0[1] = __ffma2_rn(v23, qq0, b0[1]);
+      a1[0] = __ffma2_rn(m01, xx1, a1[0]); a1[1] = __ffma2_rn(m23, xx1, a1[1]);
+      b1[0] = __ffma2_rn(v01, qq1, b1[0]); b1[1] = __ffma2_rn(v23, qq1, b1[1]);
+      if (NG == 8) {
+        const float4 mb = *reinterpret_cast<const float4 *>(mm + (d0 + dd) * 8 + 4);
+        const float4 vb = *reinterpret_cast<const float4 *>(vv + (d0 + dd) * 8 + 4);
+        const float2 m45 = make_float2(mb.x, mb.y), m67 = make_float2(mb.z, mb.w), v45 = make_float2(vb.x, vb.y), v67 = make_float2(vb.z, vb.w);
+        a0[2] = __ffma2_rn(m45, xx0, a0[2]); a0[3] = __ffma2_rn(m67, xx0, a0[3]);
+        b0[2] = __ffma2_rn(v45, qq0, b0[2]); b0[3] = __ffma2_rn(v67, qq0, b0[3]);
+        a1[2] = __ffma2_rn(m45, xx1, a1[2]); a1[3] = __ffma2_rn(m67, xx1, a1[3]);
+        b1[2] = __ffma2_rn(v45, qq1, b1[2]); b1[3] = __ffma2_rn(v67, qq1, b1[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    aa0[2 * j] = a0[j].x; aa0[2 * j + 1] = a0[j].y; bb0[2 * j] = b0[j].x; bb0[2 * j + 1] = b0[j].y;
+    aa1[2 * j] = a1[j].x; aa1[2 * j + 1] = a1[j].y; bb1[2 * j] = b1[j].x; bb1[2 * j + 1] = b1[j].y;
+  }
+  for (int d = D4; d < D; ++d) {
+    const float x0 = xr0[d], q0 = x0 * x0, x1 = xr1[d], q1 = x1 * x1;
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
+      const float mv = mm[d * 8 + j], vvv = vv[d * 8 + j];
+      aa0[j] = fmaf(mv, x0, aa0[j]); bb0[j] = fmaf(vvv, q0, bb0[j]);
+      aa1[j] = fmaf(mv, x1, aa1[j]); bb1[j] = fmaf(vvv, q1, bb1[j]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
   extern __shared__ float smem[];
   const int D = a.D;
@@ -522,14 +575,16 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
     __syncthreads();
     const bool vec = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.feats) & 15) == 0);
     if (vec) {
-      const int chunks = D >> 2, sub = tid & 15;
-      for (int r = tid >> 4; r < n; r += 8) {
-        const float *src = a.feats + (size_t)s_idx[r] * D;
-        float *dst = X + r * XP;
-        for (int c = sub; c < chunks; c += 16) {
-          const uint32_t d32 = static_cast<uint32_t>(__cvta_generic_to_shared(dst + 4 * c));
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d32), "l"(src + 4 * c) : "memory");
-        }
+      // one thread per gathered row: its 16-byte chunks back to back (16 lanes per row cost 15 warp instructions per
+      // frame in address arithmetic and loop control, ncu r2f; the rows are scattered, so nothing is lost in coalescing,
+      // and consecutive rows land conflict-free in shared memory thanks to the row pitch)
+      if (tid < n) {
+        const float *src = a.feats + (size_t)idx * D;
+        const uint32_t d32 = static_cast<uint32_t>(__cvta_generic_to_shared(X + tid * XP));
+        const int chunks = D >> 2;
+#pragma unroll 4
+        for (int c = 0; c < chunks; ++c)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d32 + 16 * c), "l"(src + 4 * c) : "memory");
       }
     } else {
       const int warp = tid >> 5, lane = tid & 31;
@@ -556,7 +611,30 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
       for (int e = tid; e < nb * 8; e += 128) gcs[e] = a.gc8[(size_t)(grp0 + gb0) * 8 + e];
     }
     __syncthreads();
-    if (tid < n) {
+    if (nb >= 2) {
+      // warp pair k = warps (2k, 2k+1) takes groups k, k+2, ...; lane l of the pair's warp h handles frames
+      // f = 32 h + l and f + 64
+      const int pair = tid >> 6, f0 = tid & 63, f1 = f0 + 64;
+      if (f0 < n) {
+        const float *xr0 = X + f0 * XP, *xr1 = X + min(f1, n - 1) * XP;
+        for (int gb = pair; gb < nb; gb += 2) {
+          float aa0[8], bb0[8], aa1[8], bb1[8];
+          const float *mm = ms + (size_t)gb * 2 * D * 8;
+          const float *vv = mm + D * 8;
+          const int gl0 = (gb0 + gb) * 8;
+          const int cnt = min(8, ng - gl0);
+          if (cnt > 4) stats_group_ll2<8>(xr0, xr1, mm, vv, D, aa0, bb0, aa1, bb1);
+          else stats_group_ll2<4>(xr0, xr1, mm, vv, D, aa0, bb0, aa1, bb1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < cnt) {
+              const float gc = gcs[gb * 8 + j];
+              post[f0 * PG + gl0 + j] = (gc + aa0[j]) - 0.5f * bb0[j];  // csrc/diag-gmm.cc:174-175
+              if (f1 < n) post[f1 * PG + gl0 + j] = (gc + aa1[j]) - 0.5f * bb1[j];
+            }
+        }
+      }
+    } else if (tid < n) {
       const float *xr = X + tid * XP;
       for (int gb = 0; gb < nb; ++gb) {
         float aa[8], bb[8];
@@ -575,22 +653,57 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
   // softmax over the pdf's Gaussians (csrc/eigen.cc:20-32), then post *= weight
   // (csrc/mle-diag-gmm.cc:153); totals as csrc/mle-am-diag-gmm.cc:49-50.
   double my_like = 0.0, my_w = 0.0;
+  __syncthreads();  // a frame's log-likes may have been written by several warps (one per Gaussian group)
   if (tid < n) {
     float *pr = post + tid * PG;
-    float mx = pr[0];
-    for (int g = 1; g < ng; ++g) mx = fmaxf(mx, pr[g]);
-    float s = 0.f;
-    for (int g = 0; g < ng; ++g) {
-      float e = __expf(pr[g] - mx);
-      pr[g] = e;
-      s += e;
-    }
-    const float lse = logf(s) + mx;
-    if (!finite_f(lse)) atomicOr(a.err, ERR_NONFINITE);
     const float w = wsm[tid];
-    const float rs = __frcp_rn(s);  // exp / sum within 1 ulp of the reference's division (csrc/eigen.cc:29-31)
-    for (int g = 0; g < ng; ++g) pr[g] = (pr[g] * rs) * w;
-    for (int g = ng; g < PG; ++g) pr[g] = 0.f;
+    float lse;
+    if (PG <= 20) {
+      // up to 16 Gaussians (+ pad): the row goes through registers with 128-bit accesses — the scalar walk below
+      // costs four conflicted passes over shared memory
+      float v[20];
+#pragma unroll
+      for (int q = 0; q < 5; ++q)
+        if (4 * q < PG) {
+          const float4 t4 = *reinterpret_cast<const float4 *>(pr + 4 * q);
+          v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+        }
+      float mx = v[0];
+#pragma unroll
+      for (int g = 1; g < 20; ++g)
+        if (g < ng) mx = fmaxf(mx, v[g]);
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < 20; ++g) {
+        if (g < ng) {
+          v[g] = __expf(v[g] - mx);
+          s += v[g];
+        } else {
+          v[g] = 0.f;
+        }
+      }
+      lse = logf(s) + mx;
+      const float rs = __frcp_rn(s);  // exp / sum within 1 ulp of the reference's division (csrc/eigen.cc:29-31)
+#pragma unroll
+      for (int q = 0; q < 5; ++q)
+        if (4 * q < PG)
+          *reinterpret_cast<float4 *>(pr + 4 * q) = make_float4((v[4 * q] * rs) * w, (v[4 * q + 1] * rs) * w, (v[4 * q + 2] * rs) * w,
+                                                                (v[4 * q + 3] * rs) * w);
+    } else {
+      float mx = pr[0];
+      for (int g = 1; g < ng; ++g) mx = fmaxf(mx, pr[g]);
+      float s = 0.f;
+      for (int g = 0; g < ng; ++g) {
+        float e = __expf(pr[g] - mx);
+        pr[g] = e;
+        s += e;
+      }
+      lse = logf(s) + mx;
+      const float rs = __frcp_rn(s);
+      for (int g = 0; g < ng; ++g) pr[g] = (pr[g] * rs) * w;
+      for (int g = ng; g < PG; ++g) pr[g] = 0.f;
+    }
+    if (!finite_f(lse)) atomicOr(a.err, ERR_NONFINITE);
     if (a.per_frame) a.per_frame[s_idx[tid]] = lse;
     my_like = (double)(lse * w);
     my_w = (double)w;
