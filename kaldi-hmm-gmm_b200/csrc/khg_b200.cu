@@ -623,18 +623,12 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
   const int max_groups = (m->max_gp + 7) / 8;
   int grp_batch = std::max(1, std::min(std::min(8, max_groups), 20480 / (2 * D * 8 * 4)));
   const int post_cap = std::min(kStatsPostCapMax, kStatsFrames * stats_pitch(m->max_gp));
-  // two row tiles (the next item's gather runs under the current item's compute), the posterior tile, the model block
-  size_t smem = sizeof(float) * (2 * (size_t)kStatsFrames * stats_pitch(D) + post_cap + (size_t)grp_batch * 2 * D * 8 + grp_batch * 8 + 2 * kStatsFrames);
+  size_t smem = sizeof(float) * ((size_t)kStatsFrames * stats_pitch(D) + post_cap + (size_t)grp_batch * 2 * D * 8 + grp_batch * 8 + 128);
   if (smem > 220 * 1024) {
     set_error("feature dimension too large for the statistics kernel");
     return KHG_ERR_UNSUPPORTED;
   }
   KHG_CUDA_TRY(cudaFuncSetAttribute(stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));  // (per device)
-  // persistent CTAs, each with a contiguous range of work items: as many as fit an SM (shared memory, registers)
-  int stats_ctas_per_sm = 1;
-  KHG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&stats_ctas_per_sm, stats_kernel, 128, smem));
-  stats_ctas_per_sm = std::max(1, stats_ctas_per_sm);
-  if (const char *e = getenv("KHG_STATS_CTAS_PER_SM")) stats_ctas_per_sm = std::max(1, std::min(stats_ctas_per_sm, atoi(e)));  // experiments
   for (int64_t t0 = 0; t0 < T; t0 += slab) {
     const int64_t n = std::min(slab, T - t0);
     KHG_TRY(m->w_keys.reserve(sizeof(int32_t) * n));
@@ -680,7 +674,7 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
     a.D = D;
     a.grp_batch = grp_batch;
     a.post_cap = post_cap;
-    stats_kernel<<<(unsigned)std::min<int64_t>(max_items, (int64_t)m->sm_count * stats_ctas_per_sm), 128, smem, st>>>(a);
+    stats_kernel<<<(unsigned)max_items, 128, smem, st>>>(a);
     g_launch_count += 6 + 3;  // ours + the radix-sort passes (library)
     KHG_CUDA_TRY(cudaGetLastError());
   }

@@ -409,9 +409,9 @@ __global__ void item_table_kernel(int P, const int32_t *__restrict__ offsets, co
 // (csrc/mle-diag-gmm.cc:145-158) -> DiagGmm::ComponentPosteriors
 // (csrc/diag-gmm.cc:368-392) -> AccumulateFromPosteriors
 // (csrc/mle-diag-gmm.cc:123-143).
-// Work item = up to 128 frames of one pdf; a CTA (128 threads) owns a contiguous range of items.
+// One CTA (128 threads) per work item = up to 128 frames of one pdf.
 //   stage   gathered feature rows -> smem X[t][.] (row pitch chosen so that one
-//           LDS.128 per thread-row is conflict-free), one item ahead of the compute
+//           LDS.128 per thread-row is conflict-free)
 //   phase A thread = frame: log-likes of the pdf's Gaussians (groups of 8 or 4, model
 //           staged in smem, broadcast LDS.128), max-subtracted softmax
 //           (csrc/eigen.cc:20-32), post *= w, totals (csrc/mle-am-diag-gmm.cc:49-50)
@@ -488,327 +488,226 @@ __device__ __forceinline__ void stats_group_ll(const float *__restrict__ xr, con
   }
 }
 
-// One CTA (128 threads) works through a CONTIGUOUS range of work items (items are ordered by pdf):
-//   * the gathered feature rows of item i+1 are fetched (cp.async, one thread per row) while item i is computed,
-//     into the second of two row tiles: the HBM latency of the gather — a quarter of the kernel's time when every
-//     item was its own CTA (ncu r2g) — is off the critical path;
-//   * the pdf's model block stays in shared memory while the pdf does not change, and the statistics of a pdf stay
-//     in registers across its items: they leave the CTA as ONE fp64 atomic per statistic per (pdf, CTA) instead of
-//     per 128 frames; the two totals once per CTA.
-// Per item: phase A, thread = frame: the pdf's log-likes (groups of 8 / 4 Gaussians, broadcast LDS.128, packed
-// FFMA2), softmax through registers (csrc/eigen.cc:20-32), post *= weight (csrc/mle-diag-gmm.cc:153); phase B:
-// (4 Gaussians x 4 dims) register tiles x 128 / tiles frame slices accumulate post*x, post*x^2 in fp32
-// (the reference casts every frame's fp32 product to double, csrc/mle-diag-gmm.cc:131-141: ~1e-7 relative).
-// pdfs whose tiles do not fit one pass (> 128 tiles) flush per item, in passes, as before.
-struct StatsSmem {
-  float *X[2];     // 128 x XP each (tail of each row zero)
-  float *post;     // post_cap floats: [t][PG]
-  float *ms;       // grp_batch x 2 x D x 8
-  float *gcs;      // grp_batch x 8
-  float *wsm[2];   // 128 frame weights each
-};
+// The same for TWO frames per thread: every broadcast load of the model feeds both, which halves the
+// shared-memory wavefronts of phase A (the kernel's bound: 40 of them per frame before, ncu r2f).
+template <int NG>
+__device__ __forceinline__ void stats_group_ll2(const float *__restrict__ xr0, const float *__restrict__ xr1,
+                                                const float *__restrict__ mm, const float *__restrict__ vv, int D,
+                                                float (&aa0)[8], float (&bb0)[8], float (&aa1)[8], float (&bb1)[8]) {
+  float2 a0[4], b0[4], a1[4], b1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a0[j] = b0[j] = a1[j] = b1[j] = make_float2(0.f, 0.f);
+  const int D4 = D & ~3;
+#pragma unroll(kStatsUnrollA)
+  for (int d0 = 0; d0 < D4; d0 += 4) {
+    const float4 xq0 = *reinterpret_cast<const float4 *>(xr0 + d0);
+    const float4 xq1 = *reinterpret_cast<const float4 *>(xr1 + d0);
+    const float xs0[4] = {xq0.x, xq0.y, xq0.z, xq0.w}, xs1[4] = {xq1.x, xq1.y, xq1.z, xq1.w};
+#pragma unroll
+    for (int dd = 0; dd < 4; ++dd) {
+      const float x0 = xs0[dd], q0 = x0 * x0, x1 = xs1[dd], q1 = x1 * x1;  // data.array().square(), csrc/diag-gmm.cc:175
+      const float2 xx0 = make_float2(x0, x0), qq0 = make_float2(q0, q0), xx1 = make_float2(x1, x1), qq1 = make_float2(q1, q1);
+      const float4 ma = *reinterpret_cast<const float4 *>(mm + (d0 + dd) * 8);
+      const float4 va = *reinterpret_cast<const float4 *>(vv + (d0 + dd) * 8);
+      const float2 m01 = make_float2(ma.x, ma.y), m23 = make_float2(ma.z, ma.w), v01 = make_float2(va.x, va.y), v23 = make_float2(va.z, va.w);
+      a0[0] = __ffma2_rn(m01, xx0, a0[0]); a0[1] = __ffma2_rn(m23, xx0, a0[1]);
+      b0[0] = __ffma2_rn(v01, qq0, b0[0]); b0[1] = __ffma2_rn(v23, qq0, b0[1]);
+      a1[0] = __ffma2_rn(m01, xx1, a1[0]); a1[1] = __ffma2_rn(m23, xx1, a1[1]);
+      b1[0] = __ffma2_rn(v01, qq1, b1[0]); b1[1] = __ffma2_rn(v23, qq1, b1[1]);
+      if (NG == 8) {
+        const float4 mb = *reinterpret_cast<const float4 *>(mm + (d0 + dd) * 8 + 4);
+        const float4 vb = *reinterpret_cast<const float4 *>(vv + (d0 + dd) * 8 + 4);
+        const float2 m45 = make_float2(mb.x, mb.y), m67 = make_float2(mb.z, mb.w), v45 = make_float2(vb.x, vb.y), v67 = make_float2(vb.z, vb.w);
+        a0[2] = __ffma2_rn(m45, xx0, a0[2]); a0[3] = __ffma2_rn(m67, xx0, a0[3]);
+        b0[2] = __ffma2_rn(v45, qq0, b0[2]); b0[3] = __ffma2_rn(v67, qq0, b0[3]);
+        a1[2] = __ffma2_rn(m45, xx1, a1[2]); a1[3] = __ffma2_rn(m67, xx1, a1[3]);
+        b1[2] = __ffma2_rn(v45, qq1, b1[2]); b1[3] = __ffma2_rn(v67, qq1, b1[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    aa0[2 * j] = a0[j].x; aa0[2 * j + 1] = a0[j].y; bb0[2 * j] = b0[j].x; bb0[2 * j + 1] = b0[j].y;
+    aa1[2 * j] = a1[j].x; aa1[2 * j + 1] = a1[j].y; bb1[2 * j] = b1[j].x; bb1[2 * j + 1] = b1[j].y;
+  }
+  for (int d = D4; d < D; ++d) {
+    const float x0 = xr0[d], q0 = x0 * x0, x1 = xr1[d], q1 = x1 * x1;
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
+      const float mv = mm[d * 8 + j], vvv = vv[d * 8 + j];
+      aa0[j] = fmaf(mv, x0, aa0[j]); bb0[j] = fmaf(vvv, q0, bb0[j]);
+      aa1[j] = fmaf(mv, x1, aa1[j]); bb1[j] = fmaf(vvv, q1, bb1[j]);
+    }
+  }
+}
 
 __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
   extern __shared__ float smem[];
   const int D = a.D;
   const int XP = stats_pitch(D);
-  StatsSmem sh;
-  sh.X[0] = smem;
-  sh.X[1] = smem + kStatsFrames * XP;
-  sh.post = sh.X[1] + kStatsFrames * XP;
-  sh.ms = sh.post + a.post_cap;
-  sh.gcs = sh.ms + (size_t)a.grp_batch * 2 * D * 8;
-  sh.wsm[0] = sh.gcs + a.grp_batch * 8;
-  sh.wsm[1] = sh.wsm[0] + kStatsFrames;
-  __shared__ int s_idx[2][kStatsFrames];
+  float *X = smem;                                      // 128 x XP (tail of each row zero)
+  float *post = X + kStatsFrames * XP;                  // post_cap floats: [t][PG]
+  float *ms = post + a.post_cap;                        // grp_batch x 2 x D x 8
+  float *gcs = ms + (size_t)a.grp_batch * 2 * D * 8;    // grp_batch x 8
+  float *wsm = gcs + a.grp_batch * 8;                   // 128 weights
+  __shared__ int s_idx[kStatsFrames];
   __shared__ double s_red[8];
   const int tid = threadIdx.x;
-  const int n_items = a.item_start[a.P];
-  const int i0 = (int)((int64_t)n_items * blockIdx.x / gridDim.x), i1 = (int)((int64_t)n_items * (blockIdx.x + 1) / gridDim.x);
-  if (i0 >= i1) return;
-  const bool vec = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.feats) & 15) == 0);
+  const int item = blockIdx.x;
+  if (item >= a.item_start[a.P]) return;
+  const int4 desc = __ldg(a.item_desc + item);
+  const int p = desc.x, pos0 = desc.y, n = desc.z;
+  const int g0 = a.offsets[p], ng = a.offsets[p + 1] - g0;
+  const int PG = stats_pitch(ng);
+  const int grp0 = a.grp_start[p], ngrp = a.grp_start[p + 1] - grp0;
 
-  // the pad columns of every row of both tiles are zero for the whole launch (cp.async only writes D columns)
-  for (int b = 0; b < 2; ++b)
-    for (int d = D; d < XP; ++d) sh.X[b][tid * XP + d] = 0.f;
-
-  // issues the gather of item `it` into tile b (one thread per row) and commits the group
-  auto prefetch = [&](int it, int b) {
-    const int4 desc = __ldg(a.item_desc + it);
-    if (tid < desc.z) {
-      const int idx = a.order[desc.y + tid];
-      s_idx[b][tid] = idx;
-      sh.wsm[b][tid] = a.weights ? a.weights[idx] : 1.0f;
-      const float *src = a.feats + (size_t)idx * D;
-      const uint32_t d32 = static_cast<uint32_t>(__cvta_generic_to_shared(sh.X[b] + tid * XP));
-      if (vec) {
+  // stage features (gathered rows): the item's row indices go to shared memory first; then 16
+  // lanes per row issue the row's 16-byte chunks with cp.async (8 rows per pass, no per-row
+  // warp-wide bookkeeping); the pad columns of every row are zeroed by the row's owner thread.
+  {
+    int idx = 0;
+    if (tid < n) {
+      idx = a.order[pos0 + tid];
+      s_idx[tid] = idx;
+      wsm[tid] = a.weights ? a.weights[idx] : 1.0f;
+    }
+    for (int d = D; d < XP; ++d) X[tid * XP + d] = 0.f;
+    __syncthreads();
+    const bool vec = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.feats) & 15) == 0);
+    if (vec) {
+      // one thread per gathered row: its 16-byte chunks back to back (16 lanes per row cost 15 warp instructions per
+      // frame in address arithmetic and loop control, ncu r2f; the rows are scattered, so nothing is lost in coalescing,
+      // and consecutive rows land conflict-free in shared memory thanks to the row pitch)
+      if (tid < n) {
+        const float *src = a.feats + (size_t)idx * D;
+        const uint32_t d32 = static_cast<uint32_t>(__cvta_generic_to_shared(X + tid * XP));
         const int chunks = D >> 2;
 #pragma unroll 4
         for (int c = 0; c < chunks; ++c)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d32 + 16 * c), "l"(src + 4 * c) : "memory");
-      } else {  // rows that are only 4-byte aligned (e.g. dim 39)
-        for (int d = 0; d < D; ++d)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32 + 4 * d), "l"(src + d) : "memory");
+      }
+    } else {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int r = warp; r < n; r += 4) {  // rows that are only 4-byte aligned (e.g. dim 39): 4-byte cp.async
+        const float *src = a.feats + (size_t)s_idx[r] * D;
+        for (int d = lane; d < D; d += 32) {
+          const uint32_t d32 = static_cast<uint32_t>(__cvta_generic_to_shared(X + r * XP + d));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32), "l"(src + d) : "memory");
+        }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-  };
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 
-  // statistics of the current pdf, resident in registers (the thread's tile and frame slice)
-  float2 occ2[2], sm2[4][2], sv2[4][2];
-  auto zero_acc = [&]() {
-    occ2[0] = occ2[1] = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sm2[i][0] = sm2[i][1] = sv2[i][0] = sv2[i][1] = make_float2(0.f, 0.f);
-  };
-  zero_acc();
-  double my_like = 0.0, my_w = 0.0;
-
-  int cur_p = -1, g0 = 0, ng = 0, PG = 4, grp0 = 0, ngrp = 0, n_gt = 1, tiles = 1, TQ = 1, n_act = 1;
-  const int n_dt = (D + 3) >> 2;
-  bool resident = false, model_cached = false;
-
-  // adds the thread-level partial statistics of pdf (g0, ng) to the global accumulators: the frame slices are summed
-  // in shared memory (scr, >= 36 * n_act floats) so that every statistic is ONE fp64 atomic
-  auto flush = [&](float *scr, int w, bool act) {
-    const float occ[4] = {occ2[0].x, occ2[0].y, occ2[1].x, occ2[1].y};
-    if (act) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        scr[i * n_act + w] = occ[i];
-        scr[(4 + i * 4 + 0) * n_act + w] = sm2[i][0].x; scr[(4 + i * 4 + 1) * n_act + w] = sm2[i][0].y;
-        scr[(4 + i * 4 + 2) * n_act + w] = sm2[i][1].x; scr[(4 + i * 4 + 3) * n_act + w] = sm2[i][1].y;
-        scr[(20 + i * 4 + 0) * n_act + w] = sv2[i][0].x; scr[(20 + i * 4 + 1) * n_act + w] = sv2[i][0].y;
-        scr[(20 + i * 4 + 2) * n_act + w] = sv2[i][1].x; scr[(20 + i * 4 + 3) * n_act + w] = sv2[i][1].y;
-      }
+  // ---- phase A ----
+  for (int gb0 = 0; gb0 < ngrp; gb0 += a.grp_batch) {
+    const int nb = min(a.grp_batch, ngrp - gb0);
+    __syncthreads();
+    {
+      const float4 *src = reinterpret_cast<const float4 *>(a.pack8 + (size_t)(grp0 + gb0) * 2 * D * 8);
+      float4 *dst = reinterpret_cast<float4 *>(ms);
+      for (int e = tid; e < nb * 2 * D * 8 / 4; e += 128) dst[e] = src[e];
+      for (int e = tid; e < nb * 8; e += 128) gcs[e] = a.gc8[(size_t)(grp0 + gb0) * 8 + e];
     }
     __syncthreads();
-    for (int g = tid; g < ng; g += 128) {
-      const int tl = (g >> 2) * n_dt, k = g & 3;
-      float v = 0.f;
-      for (int q = 0; q < TQ; ++q) v += scr[k * n_act + q * tiles + tl];
-      atomicAdd(&a.occ[g0 + g], (double)v);
-    }
-    if (a.mean) {
-      for (int o = tid; o < ng * D; o += 128) {
-        const int g = o / D, d = o - g * D;
-        const int tl = (g >> 2) * n_dt + (d >> 2), k = 4 + (g & 3) * 4 + (d & 3);
-        float v = 0.f, u = 0.f;
-        for (int q = 0; q < TQ; ++q) {
-          v += scr[k * n_act + q * tiles + tl];
-          u += scr[(k + 16) * n_act + q * tiles + tl];
-        }
-        atomicAdd(&a.mean[(size_t)(g0 + g) * D + d], (double)v);
-        if (a.var) atomicAdd(&a.var[(size_t)(g0 + g) * D + d], (double)u);
-      }
-    }
-    __syncthreads();
-    for (int d = D; d < XP; ++d) scr[tid * XP + d] = 0.f;  // scr is a row tile: its pad columns are zero again
-  };
-
-  prefetch(i0, 0);
-  for (int it = i0; it < i1; ++it) {
-    const int b = (it - i0) & 1;
-    const int4 desc = __ldg(a.item_desc + it);
-    const int p = desc.x, n = desc.z;
-    float *X = sh.X[b], *post = sh.post;
-    if (p != cur_p) {
-      // ---- a new pdf: the previous one's statistics leave the registers; geometry of the new one
-      if (cur_p >= 0 && resident) {
-        const int w = tid;
-        flush(sh.X[b ^ 1], w, w < n_act);  // (tile b^1 is free: item it-1 is done, item it+1 not yet requested)
-        zero_acc();
-      }
-      cur_p = p;
-      g0 = a.offsets[p];
-      ng = a.offsets[p + 1] - g0;
-      PG = stats_pitch(ng);
-      grp0 = a.grp_start[p];
-      ngrp = a.grp_start[p + 1] - grp0;
-      n_gt = PG >> 2;
-      tiles = n_gt * n_dt;
-      TQ = tiles <= 128 ? 128 / tiles : 1;
-      n_act = tiles * TQ;
-      resident = tiles <= 128 && 36 * n_act <= kStatsFrames * XP;  // (the slice sums go through one row tile)
-      if (!resident) {
-        TQ = 1;
-        n_act = tiles;
-      }
-      model_cached = false;
-    }
-    if (it + 1 < i1) prefetch(it + 1, b ^ 1);
-    else asm volatile("cp.async.commit_group;" ::: "memory");  // (an empty group keeps the wait count uniform)
-    asm volatile("cp.async.wait_group 1;" ::: "memory");  // item `it`'s rows have landed (this thread's)
-
-    // ---- phase A ----
-    for (int gb0 = 0; gb0 < ngrp; gb0 += a.grp_batch) {
-      const int nb = min(a.grp_batch, ngrp - gb0);
-      __syncthreads();  // rows of every thread visible; previous users of ms / post are done
-      if (!(model_cached && ngrp <= a.grp_batch)) {
-        const float4 *src = reinterpret_cast<const float4 *>(a.pack8 + (size_t)(grp0 + gb0) * 2 * D * 8);
-        float4 *dst = reinterpret_cast<float4 *>(sh.ms);
-        for (int e = tid; e < nb * 2 * D * 8 / 4; e += 128) dst[e] = __ldg(src + e);
-        for (int e = tid; e < nb * 8; e += 128) sh.gcs[e] = a.gc8[(size_t)(grp0 + gb0) * 8 + e];
-        __syncthreads();
-      }
-      if (tid < n) {
-        const float *xr = X + tid * XP;
-        for (int gb = 0; gb < nb; ++gb) {
-          float aa[8], bb[8];
-          const float *mm = sh.ms + (size_t)gb * 2 * D * 8;
+    if (nb >= 2) {
+      // warp pair k = warps (2k, 2k+1) takes groups k, k+2, ...; lane l of the pair's warp h handles frames
+      // f = 32 h + l and f + 64
+      const int pair = tid >> 6, f0 = tid & 63, f1 = f0 + 64;
+      if (f0 < n) {
+        const float *xr0 = X + f0 * XP, *xr1 = X + min(f1, n - 1) * XP;
+        for (int gb = pair; gb < nb; gb += 2) {
+          float aa0[8], bb0[8], aa1[8], bb1[8];
+          const float *mm = ms + (size_t)gb * 2 * D * 8;
           const float *vv = mm + D * 8;
           const int gl0 = (gb0 + gb) * 8;
           const int cnt = min(8, ng - gl0);
-          if (cnt > 4) stats_group_ll<8>(xr, mm, vv, D, aa, bb);
-          else stats_group_ll<4>(xr, mm, vv, D, aa, bb);
+          if (cnt > 4) stats_group_ll2<8>(xr0, xr1, mm, vv, D, aa0, bb0, aa1, bb1);
+          else stats_group_ll2<4>(xr0, xr1, mm, vv, D, aa0, bb0, aa1, bb1);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (j < cnt) post[tid * PG + gl0 + j] = (sh.gcs[gb * 8 + j] + aa[j]) - 0.5f * bb[j];  // csrc/diag-gmm.cc:174-175
-        }
-      }
-    }
-    model_cached = true;  // (only honoured when the whole pdf fits one batch)
-    // softmax over the pdf's Gaussians (csrc/eigen.cc:20-32), then post *= weight
-    // (csrc/mle-diag-gmm.cc:153); totals as csrc/mle-am-diag-gmm.cc:49-50.  Same thread as phase A: no barrier.
-    if (tid < n) {
-      float *pr = post + tid * PG;
-      const float w = sh.wsm[b][tid];
-      float lse;
-      if (PG <= 20) {
-        // up to 16 Gaussians (+ pad): the row goes through registers with 128-bit accesses — a scalar walk costs
-        // four bank-conflicted passes over shared memory
-        float v[20];
-#pragma unroll
-        for (int q = 0; q < 5; ++q)
-          if (4 * q < PG) {
-            const float4 t4 = *reinterpret_cast<const float4 *>(pr + 4 * q);
-            v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
-          }
-        float mx = v[0];
-#pragma unroll
-        for (int g = 1; g < 20; ++g)
-          if (g < ng) mx = fmaxf(mx, v[g]);
-        float s = 0.f;
-#pragma unroll
-        for (int g = 0; g < 20; ++g) {
-          if (g < ng) {
-            v[g] = __expf(v[g] - mx);
-            s += v[g];
-          } else {
-            v[g] = 0.f;
-          }
-        }
-        lse = logf(s) + mx;
-        const float rs = __frcp_rn(s);  // exp / sum within 1 ulp of the reference's division (csrc/eigen.cc:29-31)
-#pragma unroll
-        for (int q = 0; q < 5; ++q)
-          if (4 * q < PG)
-            *reinterpret_cast<float4 *>(pr + 4 * q) = make_float4((v[4 * q] * rs) * w, (v[4 * q + 1] * rs) * w, (v[4 * q + 2] * rs) * w,
-                                                                  (v[4 * q + 3] * rs) * w);
-      } else {
-        float mx = pr[0];
-        for (int g = 1; g < ng; ++g) mx = fmaxf(mx, pr[g]);
-        float s = 0.f;
-        for (int g = 0; g < ng; ++g) {
-          float e = __expf(pr[g] - mx);
-          pr[g] = e;
-          s += e;
-        }
-        lse = logf(s) + mx;
-        const float rs = __frcp_rn(s);
-        for (int g = 0; g < ng; ++g) pr[g] = (pr[g] * rs) * w;
-        for (int g = ng; g < PG; ++g) pr[g] = 0.f;
-      }
-      if (!finite_f(lse)) atomicOr(a.err, ERR_NONFINITE);
-      if (a.per_frame) a.per_frame[s_idx[b][tid]] = lse;
-      my_like += (double)(lse * w);
-      my_w += (double)w;
-    }
-    __syncthreads();  // posteriors of every frame visible
-
-    // ---- phase B ----
-    const int per = (n + TQ - 1) / TQ;
-    if (resident) {
-      const int w = tid;
-      if (w < n_act) {
-        const int tq = w / tiles, tile = w - tq * tiles;
-        const int gt = tile / n_dt, dt = tile - gt * n_dt;
-        const int ta = tq * per, tb = min(n, ta + per);
-        const float *pp = post + gt * 4, *xp = X + dt * 4;
-#pragma unroll(kStatsUnrollB)
-        for (int t = ta; t < tb; ++t) {
-          const float4 pq = *reinterpret_cast<const float4 *>(pp + t * PG);
-          const float4 xq = *reinterpret_cast<const float4 *>(xp + t * XP);
-          const float2 x01 = make_float2(xq.x, xq.y), x23 = make_float2(xq.z, xq.w);
-          const float2 q01 = __fmul2_rn(x01, x01), q23 = __fmul2_rn(x23, x23);
-          occ2[0] = __fadd2_rn(occ2[0], make_float2(pq.x, pq.y));
-          occ2[1] = __fadd2_rn(occ2[1], make_float2(pq.z, pq.w));
-          const float pv[4] = {pq.x, pq.y, pq.z, pq.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 p2 = make_float2(pv[i], pv[i]);
-            sm2[i][0] = __ffma2_rn(p2, x01, sm2[i][0]);
-            sm2[i][1] = __ffma2_rn(p2, x23, sm2[i][1]);
-            sv2[i][0] = __ffma2_rn(p2, q01, sv2[i][0]);
-            sv2[i][1] = __ffma2_rn(p2, q23, sv2[i][1]);
-          }
-        }
-      }
-    } else {
-      // pdfs with more than 128 register tiles: the tiles in passes, one atomic per statistic per item and pass
-      for (int w0 = 0; w0 < n_act; w0 += 128) {
-        const int w = w0 + tid;
-        const bool act = w < n_act;
-        zero_acc();
-        const int tile = w;  // TQ == 1
-        const int gt = tile / n_dt, dt = tile - gt * n_dt;
-        if (act) {
-          const float *pp = post + gt * 4, *xp = X + dt * 4;
-          for (int t = 0; t < n; ++t) {
-            const float4 pq = *reinterpret_cast<const float4 *>(pp + t * PG);
-            const float4 xq = *reinterpret_cast<const float4 *>(xp + t * XP);
-            const float2 x01 = make_float2(xq.x, xq.y), x23 = make_float2(xq.z, xq.w);
-            const float2 q01 = __fmul2_rn(x01, x01), q23 = __fmul2_rn(x23, x23);
-            occ2[0] = __fadd2_rn(occ2[0], make_float2(pq.x, pq.y));
-            occ2[1] = __fadd2_rn(occ2[1], make_float2(pq.z, pq.w));
-            const float pv[4] = {pq.x, pq.y, pq.z, pq.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 p2 = make_float2(pv[i], pv[i]);
-              sm2[i][0] = __ffma2_rn(p2, x01, sm2[i][0]);
-              sm2[i][1] = __ffma2_rn(p2, x23, sm2[i][1]);
-              sv2[i][0] = __ffma2_rn(p2, q01, sv2[i][0]);
-              sv2[i][1] = __ffma2_rn(p2, q23, sv2[i][1]);
+            if (j < cnt) {
+              const float gc = gcs[gb * 8 + j];
+              post[f0 * PG + gl0 + j] = (gc + aa0[j]) - 0.5f * bb0[j];  // csrc/diag-gmm.cc:174-175
+              if (f1 < n) post[f1 * PG + gl0 + j] = (gc + aa1[j]) - 0.5f * bb1[j];
             }
-          }
-          const float occ[4] = {occ2[0].x, occ2[0].y, occ2[1].x, occ2[1].y};
-          const float sm[4][4] = {{sm2[0][0].x, sm2[0][0].y, sm2[0][1].x, sm2[0][1].y}, {sm2[1][0].x, sm2[1][0].y, sm2[1][1].x, sm2[1][1].y},
-                                  {sm2[2][0].x, sm2[2][0].y, sm2[2][1].x, sm2[2][1].y}, {sm2[3][0].x, sm2[3][0].y, sm2[3][1].x, sm2[3][1].y}};
-          const float sv[4][4] = {{sv2[0][0].x, sv2[0][0].y, sv2[0][1].x, sv2[0][1].y}, {sv2[1][0].x, sv2[1][0].y, sv2[1][1].x, sv2[1][1].y},
-                                  {sv2[2][0].x, sv2[2][0].y, sv2[2][1].x, sv2[2][1].y}, {sv2[3][0].x, sv2[3][0].y, sv2[3][1].x, sv2[3][1].y}};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int g = gt * 4 + i;
-            if (g >= ng) continue;
-            if (dt == 0) atomicAdd(&a.occ[g0 + g], (double)occ[i]);
-            if (a.mean) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int d = dt * 4 + j;
-                if (d >= D) continue;
-                atomicAdd(&a.mean[(size_t)(g0 + g) * D + d], (double)sm[i][j]);
-                if (a.var) atomicAdd(&a.var[(size_t)(g0 + g) * D + d], (double)sv[i][j]);
-              }
-            }
-          }
         }
       }
-      zero_acc();
+    } else if (tid < n) {
+      const float *xr = X + tid * XP;
+      for (int gb = 0; gb < nb; ++gb) {
+        float aa[8], bb[8];
+        const float *mm = ms + (size_t)gb * 2 * D * 8;
+        const float *vv = mm + D * 8;
+        const int gl0 = (gb0 + gb) * 8;
+        const int cnt = min(8, ng - gl0);
+        if (cnt > 4) stats_group_ll<8>(xr, mm, vv, D, aa, bb);
+        else stats_group_ll<4>(xr, mm, vv, D, aa, bb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < cnt) post[tid * PG + gl0 + j] = (gcs[gb * 8 + j] + aa[j]) - 0.5f * bb[j];  // csrc/diag-gmm.cc:174-175
+      }
     }
-    __syncthreads();  // tile b and the posterior tile are free for the next items
   }
-  if (resident) flush(sh.X[0], tid, tid < n_act);
-  // totals: once per CTA
+  // softmax over the pdf's Gaussians (csrc/eigen.cc:20-32), then post *= weight
+  // (csrc/mle-diag-gmm.cc:153); totals as csrc/mle-am-diag-gmm.cc:49-50.
+  double my_like = 0.0, my_w = 0.0;
+  __syncthreads();  // a frame's log-likes may have been written by several warps (one per Gaussian group)
+  if (tid < n) {
+    float *pr = post + tid * PG;
+    const float w = wsm[tid];
+    float lse;
+    if (PG <= 20) {
+      // up to 16 Gaussians (+ pad): the row goes through registers with 128-bit accesses — the scalar walk below
+      // costs four conflicted passes over shared memory
+      float v[20];
+#pragma unroll
+      for (int q = 0; q < 5; ++q)
+        if (4 * q < PG) {
+          const float4 t4 = *reinterpret_cast<const float4 *>(pr + 4 * q);
+          v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+        }
+      float mx = v[0];
+#pragma unroll
+      for (int g = 1; g < 20; ++g)
+        if (g < ng) mx = fmaxf(mx, v[g]);
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < 20; ++g) {
+        if (g < ng) {
+          v[g] = __expf(v[g] - mx);
+          s += v[g];
+        } else {
+          v[g] = 0.f;
+        }
+      }
+      lse = logf(s) + mx;
+      const float rs = __frcp_rn(s);  // exp / sum within 1 ulp of the reference's division (csrc/eigen.cc:29-31)
+#pragma unroll
+      for (int q = 0; q < 5; ++q)
+        if (4 * q < PG)
+          *reinterpret_cast<float4 *>(pr + 4 * q) = make_float4((v[4 * q] * rs) * w, (v[4 * q + 1] * rs) * w, (v[4 * q + 2] * rs) * w,
+                                                                (v[4 * q + 3] * rs) * w);
+    } else {
+      float mx = pr[0];
+      for (int g = 1; g < ng; ++g) mx = fmaxf(mx, pr[g]);
+      float s = 0.f;
+      for (int g = 0; g < ng; ++g) {
+        float e = __expf(pr[g] - mx);
+        pr[g] = e;
+        s += e;
+      }
+      lse = logf(s) + mx;
+      const float rs = __frcp_rn(s);
+      for (int g = 0; g < ng; ++g) pr[g] = (pr[g] * rs) * w;
+      for (int g = ng; g < PG; ++g) pr[g] = 0.f;
+    }
+    if (!finite_f(lse)) atomicOr(a.err, ERR_NONFINITE);
+    if (a.per_frame) a.per_frame[s_idx[tid]] = lse;
+    my_like = (double)(lse * w);
+    my_w = (double)w;
+  }
   for (int off = 16; off > 0; off >>= 1) {
     my_like += __shfl_xor_sync(0xffffffffu, my_like, off);
     my_w += __shfl_xor_sync(0xffffffffu, my_w, off);
@@ -825,8 +724,108 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
     atomicAdd(&a.totals[1], W);
     if (a.call_like) atomicAdd(a.call_like, L);
   }
+  // ---- phase B ----
+  // (4 Gaussians x 4 dims) register tiles; when they fit the CTA, TQ = 128 / tiles frame slices per
+  // tile, whose partial sums are added in shared memory so that every statistic leaves the CTA as
+  // ONE fp64 atomic; pdfs with more than 128 tiles take the tiles in passes.
+  const int n_gt = PG >> 2, n_dt = (D + 3) >> 2;
+  const int tiles = n_gt * n_dt;
+  const int TQ = tiles <= 128 ? 128 / tiles : 1;
+  const int n_act = tiles * TQ;
+  const bool reduce = TQ > 1 && 36 * n_act <= kStatsFrames * XP + a.post_cap;
+  const int per = (n + TQ - 1) / TQ;
+  for (int w0 = 0; w0 < n_act; w0 += 128) {  // (one pass when the tiles fit the CTA)
+    const int w = w0 + tid;
+    const bool act = w < n_act;
+    const int tq = w / tiles, tile = w - tq * tiles;
+    const int gt = tile / n_dt, dt = tile - gt * n_dt;
+    // packed fp32x2 accumulators: (dims 0,1) and (dims 2,3) of the tile per Gaussian, occupancies in pairs
+    float2 occ2[2], sm2[4][2], sv2[4][2];
+    occ2[0] = occ2[1] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sm2[i][0] = sm2[i][1] = sv2[i][0] = sv2[i][1] = make_float2(0.f, 0.f);
+    if (act) {
+      const int ta = tq * per, tb = min(n, ta + per);
+      const float *pp = post + gt * 4, *xp = X + dt * 4;
+#pragma unroll(kStatsUnrollB)
+      for (int t = ta; t < tb; ++t) {
+        const float4 pq = *reinterpret_cast<const float4 *>(pp + t * PG);
+        const float4 xq = *reinterpret_cast<const float4 *>(xp + t * XP);
+        const float2 x01 = make_float2(xq.x, xq.y), x23 = make_float2(xq.z, xq.w);
+        const float2 q01 = __fmul2_rn(x01, x01), q23 = __fmul2_rn(x23, x23);
+        occ2[0] = __fadd2_rn(occ2[0], make_float2(pq.x, pq.y));
+        occ2[1] = __fadd2_rn(occ2[1], make_float2(pq.z, pq.w));
+        const float pv[4] = {pq.x, pq.y, pq.z, pq.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 p2 = make_float2(pv[i], pv[i]);
+          sm2[i][0] = __ffma2_rn(p2, x01, sm2[i][0]);
+          sm2[i][1] = __ffma2_rn(p2, x23, sm2[i][1]);
+          sv2[i][0] = __ffma2_rn(p2, q01, sv2[i][0]);
+          sv2[i][1] = __ffma2_rn(p2, q23, sv2[i][1]);
+        }
+      }
+    }
+    const float occ[4] = {occ2[0].x, occ2[0].y, occ2[1].x, occ2[1].y};
+    float sm[4][4], sv[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      sm[i][0] = sm2[i][0].x; sm[i][1] = sm2[i][0].y; sm[i][2] = sm2[i][1].x; sm[i][3] = sm2[i][1].y;
+      sv[i][0] = sv2[i][0].x; sv[i][1] = sv2[i][0].y; sv[i][2] = sv2[i][1].x; sv[i][3] = sv2[i][1].y;
+    }
+    if (reduce) {
+      __syncthreads();  // every thread has finished reading X / post: they become the scratch
+      float *scr = smem;  // [36][n_act]
+      if (act) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          scr[i * n_act + w] = occ[i];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            scr[(4 + i * 4 + j) * n_act + w] = sm[i][j];
+            scr[(20 + i * 4 + j) * n_act + w] = sv[i][j];
+          }
+        }
+      }
+      __syncthreads();
+      for (int g = tid; g < ng; g += 128) {
+        const int tl = (g >> 2) * n_dt, k = g & 3;
+        float v = 0.f;
+        for (int q = 0; q < TQ; ++q) v += scr[k * n_act + q * tiles + tl];
+        atomicAdd(&a.occ[g0 + g], (double)v);
+      }
+      if (a.mean) {
+        for (int o = tid; o < ng * D; o += 128) {
+          const int g = o / D, d = o - g * D;
+          const int tl = (g >> 2) * n_dt + (d >> 2), k = 4 + (g & 3) * 4 + (d & 3);
+          float v = 0.f, u = 0.f;
+          for (int q = 0; q < TQ; ++q) {
+            v += scr[k * n_act + q * tiles + tl];
+            u += scr[(k + 16) * n_act + q * tiles + tl];
+          }
+          atomicAdd(&a.mean[(size_t)(g0 + g) * D + d], (double)v);
+          if (a.var) atomicAdd(&a.var[(size_t)(g0 + g) * D + d], (double)u);
+        }
+      }
+    } else if (act) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int g = gt * 4 + i;
+        if (g >= ng) continue;
+        if (dt == 0) atomicAdd(&a.occ[g0 + g], (double)occ[i]);
+        if (a.mean) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int d = dt * 4 + j;
+            if (d >= D) continue;
+            atomicAdd(&a.mean[(size_t)(g0 + g) * D + d], (double)sm[i][j]);
+            if (a.var) atomicAdd(&a.var[(size_t)(g0 + g) * D + d], (double)sv[i][j]);
+          }
+        }
+      }
+    }
+  }
 }
-
 
 // ---------------------------------------------------------------------------
 // K3-direct: the same per-frame arithmetic for SMALL batches (one utterance): no bucketing,
