@@ -206,6 +206,7 @@ khg_status khg_model_upload(khg_model *m, const float *weights, const float *mea
   KHG_CUDA_TRY(cudaGetLastError());
   m->uploaded = true;
   m->tc.ready = false;
+  stats_tc_free(m);
   if (m->kernel != KHG_KERNEL_SIMT && tc_supported(m)) {
     khg_status s = tc_pack_build(m);
     if (s != KHG_OK && m->kernel >= KHG_KERNEL_TCGEN05) return s;
@@ -265,13 +266,14 @@ void khg_model_destroy(khg_model *m) {
   if (!m) return;
   if (m->gsel_shadow) khg_model_destroy(m->gsel_shadow);
   tc_pack_free(m);
+  stats_tc_free(m);
   cudaFree(m->d_offsets); cudaFree(m->d_weights); cudaFree(m->d_miv); cudaFree(m->d_iv);
   cudaFree(m->d_gconsts); cudaFree(m->d_packT); cudaFree(m->d_err); cudaFree(m->d_scratch_int);
   cudaFree(m->d_grp_start); cudaFree(m->d_pack8); cudaFree(m->d_gc8);
   for (Buf *b : {&m->w_feats, &m->w_ids, &m->w_wts, &m->w_out, &m->w_pf, &m->w_keys, &m->w_vals_in,
                  &m->w_vals_out, &m->w_cub, &m->w_starts, &m->w_item_start, &m->w_tot, &m->w_tid,
                  &m->w_tid2pdf, &m->w_trans, &m->w_keys_out, &m->w_sub, &m->w_full, &m->w_al_graph,
-                 &m->w_al_block, &m->w_al_bp, &m->w_al_cost, &m->w_al_ali, &m->w_al_path, &m->w_al_xlist, &m->w_al_xll, &m->w_item_desc})
+                 &m->w_al_block, &m->w_al_bp, &m->w_al_cost, &m->w_al_ali, &m->w_al_path, &m->w_al_xlist, &m->w_al_xll, &m->w_item_desc, &m->w_fb_items})
     b->release();
   for (int i = 0; i < 2; ++i) {
     m->pin_feats[i].release(); m->pin_ids[i].release(); m->pin_wts[i].release();
@@ -629,6 +631,15 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
     return KHG_ERR_UNSUPPORTED;
   }
   KHG_CUDA_TRY(cudaFuncSetAttribute(stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));  // (per device)
+  // pdfs of <= 32 Gaussians, dim <= 56, operands inside fp16's range: the tensor-core kernel (khg_stats_tc.cu)
+  bool use_tc = false;
+  {
+    const char *e = getenv("KHG_STATS_KERNEL");  // "simt" / "tc" (default: tc when the model fits)
+    if (!(e && !strcmp(e, "simt"))) {
+      KHG_TRY(stats_tc_build(m));
+      use_tc = m->stk.ready;
+    }
+  }
   for (int64_t t0 = 0; t0 < T; t0 += slab) {
     const int64_t n = std::min(slab, T - t0);
     KHG_TRY(m->w_keys.reserve(sizeof(int32_t) * n));
@@ -674,7 +685,24 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
     a.D = D;
     a.grp_batch = grp_batch;
     a.post_cap = post_cap;
-    stats_kernel<<<(unsigned)max_items, 128, smem, st>>>(a);
+    a.item_list = nullptr;
+    a.item_list_n = nullptr;
+    if (use_tc) {
+      // tensor-core kernel over all items; the items it declines (values outside fp16's range after scaling) go to
+      // the fp32 kernel through a device-side list — normally empty, then the second launch is a few idle CTAs
+      KHG_TRY(m->w_fb_items.reserve(sizeof(int32_t) * (size_t)max_items));
+      StatsTcArgs ta;
+      ta.feats = a.feats; ta.order = a.order; ta.weights = a.weights; ta.item_start = a.item_start; ta.item_desc = a.item_desc;
+      ta.offsets = a.offsets; ta.occ = a.occ; ta.mean = a.mean; ta.var = a.var; ta.totals = a.totals; ta.call_like = a.call_like;
+      ta.per_frame = a.per_frame; ta.err = a.err; ta.fb_items = m->w_fb_items.as<int32_t>(); ta.P = P; ta.D = D; ta.n_frames = (int)n;
+      ta.img = nullptr; ta.img_off = nullptr; ta.ascale = nullptr; ta.unscale = nullptr; ta.fb_count = nullptr;
+      KHG_TRY(stats_tc_launch(m, ta, st));
+      a.item_list = m->w_fb_items.as<int32_t>();
+      a.item_list_n = m->stk.fb_count;
+      stats_kernel<<<(unsigned)std::min<int64_t>(max_items, 2 * (int64_t)m->sm_count), 128, smem, st>>>(a);
+    } else {
+      stats_kernel<<<(unsigned)max_items, 128, smem, st>>>(a);
+    }
     g_launch_count += 6 + 3;  // ours + the radix-sort passes (library)
     KHG_CUDA_TRY(cudaGetLastError());
   }
@@ -1028,6 +1056,7 @@ khg_status finish_model_from_device(khg_model *nm, int32_t *num_bad) {
   if (num_bad) *num_bad = flags[0];
   nm->uploaded = true;
   nm->tc.ready = false;
+  stats_tc_free(nm);
   if (nm->kernel != KHG_KERNEL_SIMT && tc_supported(nm)) {
     khg_status ts = tc_pack_build(nm);
     if (ts != KHG_OK && nm->kernel >= KHG_KERNEL_TCGEN05) return ts;

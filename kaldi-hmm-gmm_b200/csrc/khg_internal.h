@@ -122,6 +122,42 @@ struct TcPack {
   CUtensorMap amap;
 };
 
+
+// ---- tensor-core statistics kernel (khg_stats_tc.cu) ---------------------------
+// Per-pdf operand images (fp16 hi / lo rows of [means_invvars | -inv_vars/2 | gconst], 128-byte swizzle, ready for
+// one bulk copy into shared memory) and the per-dimension power-of-two scaling they were built with.
+struct StatsTcPack {
+  bool tried = false;      // build attempted for the current parameters
+  bool ready = false;      // shape and value range fit (dim <= 40, pdfs <= 32 Gaussians, |operand| <= 3e4)
+  int DP = 0;              // dim rounded up to 8
+  uint8_t *img = nullptr;
+  int32_t *img_off = nullptr;  // P+1, 1024-byte units
+  float *ascale = nullptr;     // 64 floats: 2^-k_d
+  float *unscale = nullptr;    // 128 floats: multiplier of each row of the statistics tile
+  int *fb_count = nullptr;     // [0]: items left to the fp32 kernel by the current launch; [1]: pack flag
+};
+struct StatsTcArgs {
+  const float *feats;
+  const int32_t *order;
+  const float *weights;
+  const int32_t *item_start;  // P+1 (item_start[P] = number of items)
+  const int4 *item_desc;
+  const int32_t *offsets;
+  const uint8_t *img;         // per-pdf model images
+  const int32_t *img_off;     // P+1, in 1024-byte units
+  const float *ascale;        // DP floats: 2^-k_d
+  const float *unscale;       // 128 floats: what a row of S is multiplied by
+  const float *miv, *iv, *gconsts;  // the fp32 parameters (exact re-evaluation of the Gaussians that matter)
+  int np_max;                 // 16 or 32: operand rows of the model's largest pdf
+  int n_frames;               // entries of `order`
+  double *occ, *mean, *var, *totals, *call_like;
+  float *per_frame;
+  int *err;
+  int32_t *fb_items;          // items left to the fp32 kernel
+  int *fb_count;
+  int P, D;
+};
+
 }  // namespace khg
 
 struct khg_model {
@@ -147,12 +183,13 @@ struct khg_model {
   int kernel = KHG_KERNEL_AUTO;
   int sm_count = 148;
   khg::TcPack tc;
+  khg::StatsTcPack stk;
   khg_model *gsel_shadow = nullptr;  // the Gaussians of pdf gsel_pdf as one-Gaussian pdfs (khg_gselect.cu)
   int gsel_pdf = -1;
   // scratch
   khg::Buf w_feats, w_ids, w_wts, w_out, w_pf;         // device staging of host args
   khg::Buf w_keys, w_keys_out, w_vals_in, w_vals_out, w_cub;       // bucketing (K2)
-  khg::Buf w_starts, w_item_start, w_item_desc, w_tot;              // per-pdf starts, work items, totals
+  khg::Buf w_starts, w_item_start, w_item_desc, w_tot, w_fb_items;              // per-pdf starts, work items, totals
   khg::Buf w_tid, w_tid2pdf, w_trans;                  // tid path
   khg::Buf w_sub, w_full;                              // pdf-subset gather
   khg::Buf w_al_graph, w_al_block, w_al_bp, w_al_cost, w_al_ali, w_al_path;  // khg_align_batch (khg_align.cu)
@@ -180,6 +217,10 @@ bool tc_supported(const khg_model *m);
 khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale,
                        float *d_out, int64_t ld_out, int precision, const unsigned **simt_gate,
                        float *gate_limit);
+// khg_stats_tc.cu: posteriors + statistics of bucketed frames on the tensor cores (lazy pack; launch fills the pack fields of `a`)
+khg_status stats_tc_build(khg_model *m);
+void stats_tc_free(khg_model *m);
+khg_status stats_tc_launch(khg_model *m, StatsTcArgs a, cudaStream_t st);
 // khg_loglikes_gs.cu: the Gaussian-stationary form of the fp16-split kernel (model tile resident in shared
 // memory, pre-split feature operand streamed)
 bool gs_supported(const khg_model *m);

@@ -437,6 +437,10 @@ struct StatsArgs {
   float *per_frame;          // T or NULL (original order)
   int *err;
   int P, D, grp_batch, post_cap;
+  // optional: process only the items item_list[0 .. *item_list_n) — what the tensor-core kernel (khg_stats_tc.cu)
+  // left to this one — grid-strided, the count read on the device
+  const int32_t *item_list;
+  const int *item_list_n;
 };
 
 // log-likes of NG (8 or 4) Gaussians of one group for the frame row xr (D floats).  Packed fp32x2
@@ -553,8 +557,10 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
   __shared__ int s_idx[kStatsFrames];
   __shared__ double s_red[8];
   const int tid = threadIdx.x;
-  const int item = blockIdx.x;
-  if (item >= a.item_start[a.P]) return;
+  const int n_work = a.item_list ? *a.item_list_n : a.item_start[a.P];
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+  if (work != (int)blockIdx.x) __syncthreads();  // (the previous item's shared memory is done with)
+  const int item = a.item_list ? a.item_list[work] : work;
   const int4 desc = __ldg(a.item_desc + item);
   const int p = desc.x, pos0 = desc.y, n = desc.z;
   const int g0 = a.offsets[p], ng = a.offsets[p + 1] - g0;
@@ -825,6 +831,7 @@ __global__ void __launch_bounds__(128) stats_kernel(StatsArgs a) {
       }
     }
   }
+  }  // work items of this CTA
 }
 
 // ---------------------------------------------------------------------------
