@@ -85,7 +85,7 @@ typedef struct khg_model khg_model; /* device-resident packed AmDiagGmm      */
 typedef struct khg_stats khg_stats; /* device-resident packed AccumAmDiagGmm */
 
 const char *khg_last_error(void);
-int32_t khg_abi_version(void); /* 3 (2 + khg_align_utterance_host, khg_align_last_exact_count, KHG_KERNEL_TCGEN05_F16_GS) */
+int32_t khg_abi_version(void); /* 4 (3 + khg_model_stats_kernel) */
 
 khg_status khg_device_count(int32_t *count);
 khg_status khg_set_device(int32_t device);
@@ -114,6 +114,13 @@ khg_status khg_model_info(const khg_model *m, int32_t *dim, int32_t *num_pdfs,
 /* Which dense kernel an in-range call will run with the current choice: KHG_KERNEL_SIMT,
  * KHG_KERNEL_TCGEN05, KHG_KERNEL_TCGEN05_F16 or KHG_KERNEL_TCGEN05_F16_GS (AUTO resolved against this model). */
 khg_status khg_model_dense_kernel(const khg_model *m, int32_t *kernel);
+/* Which kernel the bucketed statistics pass of khg_acc_stats_ali / khg_acc_stats_ali_tids / khg_estep (the per-frame
+ * AccumAmDiagGmm::AccumulateForGmm, csrc/mle-am-diag-gmm.cc:41-52, of more than 2048 frames) runs for this model:
+ * KHG_KERNEL_TCGEN05_F16 = the tensor-core kernel (dim <= 40, every pdf <= 32 Gaussians, parameters inside fp16's
+ * range after a per-dimension power-of-two scaling; work items whose features or frame weights leave that range
+ * are handed, on the device, to the fp32 kernel), KHG_KERNEL_SIMT = the fp32 kernel for everything.  Same
+ * statistics either way (tests/test_gpu_stats_tc.py).  Builds the tensor-core operand pack on first use. */
+khg_status khg_model_stats_kernel(khg_model *m, int32_t *kernel);
 /* Chooses the dense-likelihood kernel (default KHG_KERNEL_AUTO). */
 khg_status khg_model_set_kernel(khg_model *m, int32_t kernel);
 /* Launches on this CUDA stream (a cudaStream_t; NULL = default stream). */

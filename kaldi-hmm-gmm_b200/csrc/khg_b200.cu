@@ -82,7 +82,7 @@ using namespace khg;
 extern "C" {
 
 const char *khg_last_error(void) { return t_last_error.c_str(); }
-int32_t khg_abi_version(void) { return 3; }  // 3: + khg_align_utterance_host, khg_align_last_exact_count, KHG_KERNEL_TCGEN05_F16_GS
+int32_t khg_abi_version(void) { return 4; }  // 4: + khg_model_stats_kernel
 int64_t khg_launch_count(void) { return g_launch_count; }
 
 khg_status khg_device_count(int32_t *count) {
@@ -237,6 +237,24 @@ khg_status khg_model_dense_kernel(const khg_model *m, int32_t *kernel) {
   else if (m->tc.f16_ready && m->kernel != KHG_KERNEL_TCGEN05) *kernel = KHG_KERNEL_TCGEN05_F16;
   else if (m->tc.tf32_ready) *kernel = KHG_KERNEL_TCGEN05;
   else *kernel = KHG_KERNEL_SIMT;
+  return KHG_OK;
+}
+
+// the choice acc_device makes (KHG_STATS_KERNEL=simt forces the fp32 kernel: experiments / A-B runs)
+static khg_status stats_use_tc(khg_model *m, bool *use_tc) {
+  *use_tc = false;
+  const char *e = getenv("KHG_STATS_KERNEL");
+  if (e && !strcmp(e, "simt")) return KHG_OK;
+  KHG_TRY(stats_tc_build(m));
+  *use_tc = m->stk.ready;
+  return KHG_OK;
+}
+
+khg_status khg_model_stats_kernel(khg_model *m, int32_t *kernel) {
+  KHG_REQUIRE(m && kernel && m->uploaded, "model not uploaded");
+  bool use_tc = false;
+  KHG_TRY(stats_use_tc(m, &use_tc));
+  *kernel = use_tc ? KHG_KERNEL_TCGEN05_F16 : KHG_KERNEL_SIMT;
   return KHG_OK;
 }
 
@@ -633,13 +651,7 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
   KHG_CUDA_TRY(cudaFuncSetAttribute(stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));  // (per device)
   // pdfs of <= 32 Gaussians, dim <= 56, operands inside fp16's range: the tensor-core kernel (khg_stats_tc.cu)
   bool use_tc = false;
-  {
-    const char *e = getenv("KHG_STATS_KERNEL");  // "simt" / "tc" (default: tc when the model fits)
-    if (!(e && !strcmp(e, "simt"))) {
-      KHG_TRY(stats_tc_build(m));
-      use_tc = m->stk.ready;
-    }
-  }
+  KHG_TRY(stats_use_tc(m, &use_tc));
   for (int64_t t0 = 0; t0 < T; t0 += slab) {
     const int64_t n = std::min(slab, T - t0);
     KHG_TRY(m->w_keys.reserve(sizeof(int32_t) * n));

@@ -35,6 +35,7 @@ SYMBOLS = [
     ("khg_model_get_gconsts", _i32, [_vp, _vp]),
     ("khg_model_info", _i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     ("khg_model_dense_kernel", _i32, [_vp, C.POINTER(_i32)]),
+    ("khg_model_stats_kernel", _i32, [_vp, C.POINTER(_i32)]),
     ("khg_model_set_kernel", _i32, [_vp, _i32]),
     ("khg_model_set_stream", _i32, [_vp, _vp]),
     ("khg_model_sync", _i32, [_vp]),

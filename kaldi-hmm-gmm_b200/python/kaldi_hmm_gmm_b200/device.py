@@ -93,6 +93,12 @@ class DeviceModel:
         A.check(A.lib().khg_model_dense_kernel(self._h, C.byref(k)))
         return k.value
 
+    def stats_kernel(self) -> int:
+        """1 = fp32 kernel, 3 = tcgen05 kernel (fp16 hi/lo split tile): what the bucketed statistics pass runs."""
+        k = C.c_int32()
+        A.check(A.lib().khg_model_stats_kernel(self._h, C.byref(k)))
+        return k.value
+
     def set_kernel(self, kernel: int):
         A.check(A.lib().khg_model_set_kernel(self._h, kernel))
 

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/khg_b200.h but not exported"
     assert sorted(n for n, _, _ in _cabi.SYMBOLS) == declared
-    assert L.khg_abi_version() == 3
+    assert L.khg_abi_version() == 4
 
 
 def test_flag_augmentation_matches_reference():
