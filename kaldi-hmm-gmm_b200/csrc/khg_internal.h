@@ -133,6 +133,7 @@ struct StatsTcPack {
   uint8_t *img = nullptr;
   int32_t *img_off = nullptr;  // P+1, 1024-byte units
   float *ascale = nullptr;     // 64 floats: 2^-k_d
+  float h_ascale[40] = {};     // host copy (passed to the kernel by value)
   float *unscale = nullptr;    // 128 floats: multiplier of each row of the statistics tile
   int *fb_count = nullptr;     // [0]: items left to the fp32 kernel by the current launch; [1]: pack flag
 };
@@ -146,6 +147,7 @@ struct StatsTcArgs {
   const uint8_t *img;         // per-pdf model images
   const int32_t *img_off;     // P+1, in 1024-byte units
   const float *ascale;        // DP floats: 2^-k_d
+  float asc_c[40];            // the same by value (0 beyond dim): constant-bank operands
   const float *unscale;       // 128 floats: what a row of S is multiplied by
   const float *miv, *iv, *gconsts;  // the fp32 parameters (exact re-evaluation of the Gaussians that matter)
   int np_max;                 // 16 or 32: operand rows of the model's largest pdf

@@ -171,7 +171,7 @@ __host__ __device__ inline int stk_pt_bytes(int np) { return 2 * 2 * np * 128; }
 constexpr int kStkDescStage = 128;  // item descriptors staged in shared memory at a time (+ 2 of look-ahead)
 // shared-memory bytes: X tile | posterior tile | model image | tables, staged descriptors, barriers
 __host__ __device__ inline int stk_smem_bytes(int np_max, int dp) {
-  return kStkXBytes + 1024 + stk_pt_bytes(np_max) + stk_img_bytes(np_max, dp) + 64 * 4 + 128 * 4 + (kStkDescStage + 8) * 16 + 64 + 64;
+  return kStkXBytes + 1024 + stk_pt_bytes(np_max) + stk_img_bytes(np_max, dp) + 128 * 4 + (kStkDescStage + 8) * 16 + 64 + 64;
 }
 
 // NU = DP / 8, DP = D rounded up to 8: columns [0, DP) = x, [DP, 2 DP) = x^2, 2 DP and 2 DP + 1 = 1;
@@ -188,12 +188,12 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
   const int pitch = stk_pitch(DP);
   // (1 KB of slack after X: the second statistics MMA reads one chunk past the lo' columns; those rows are never used)
   uint8_t *X = bp, *Pt = X + kStkXBytes + 1024, *Bm = Pt + stk_pt_bytes(a.np_max);
-  float *asc = reinterpret_cast<float *>(Bm + stk_img_bytes(a.np_max, DP));  // 64 floats: 2^-k
-  float *uns = asc + 64;                                        // 128 floats
+  float *uns = reinterpret_cast<float *>(Bm + stk_img_bytes(a.np_max, DP));  // 128 floats
   int4 *s_desc = reinterpret_cast<int4 *>(uns + 128);           // kStkDescStage + 8 item descriptors
   double *s_red = reinterpret_cast<double *>(s_desc + kStkDescStage + 8);  // 8 doubles
   const uint32_t sX = base, sPt = sX + kStkXBytes + 1024, sBm = sPt + stk_pt_bytes(a.np_max);
   const uint32_t sBarA = smem_u32(s_red + 8), sBarB = sBarA + 8, sBarM = sBarB + 8, sSlot = sBarM + 8;
+  volatile int *s_flag = reinterpret_cast<volatile int *>(s_red + 8) + 7;  // set by a thread whose row does not fit fp16
   const int tid = threadIdx.x, D = a.D;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
@@ -206,9 +206,9 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
     *reinterpret_cast<__half *>(X + x_unit_off(c0 >> 3, tid) + ((c0 & 7) << 1)) = __float2half(1.f);
     *reinterpret_cast<__half *>(X + x_unit_off(c1 >> 3, tid) + ((c1 & 7) << 1)) = __float2half(1.f);
   }
-  if (tid < 64) asc[tid] = tid < D ? a.ascale[tid] : 0.f;
   uns[tid] = a.unscale[tid];
   if (tid == 0) {
+    *s_flag = 0;
     mbar_init(sBarA, 1);
     mbar_init(sBarB, 1);
     mbar_init(sBarM, 1);
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
       vf = mf + NP * pitch;
       gcf = vf + NP * pitch;
     }
-    // ---- this item's rows (prefetched), scaled; x^2 doubles as the range check (NaN and Inf fail it too)
+    // ---- this item's rows (prefetched), scaled; range check (NaN and Inf fail it too)
     const bool live = tid < n;
     if (!kStkRegPrefetch) load_rows(idx1);  // (an L2 hit: the row was prefetched about four tiles ago)
     const float w = w1;
@@ -387,8 +387,8 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
     bool bad = false;
 #pragma unroll
     for (int d2 = 0; d2 < DP; ++d2) {
-      xs[d2] = xr[d2] * asc[d2];
-      bad |= !(xs[d2] * xs[d2] <= kF16FeatLimit * kF16FeatLimit);
+      xs[d2] = xr[d2] * a.asc_c[d2];  // (a kernel parameter: a constant-bank operand of the FMUL, no load)
+      bad |= !(fabsf(xs[d2]) <= kF16FeatLimit);
     }
     bad = live && (bad || !(fabsf(w) <= kStkWeightLimit));
     // next item's rows (index loaded one item ago), the index after that, L2 prefetch further ahead
@@ -397,12 +397,11 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
     idx2 = load_index(it + 2);
     l2_pipeline(pf_pos);
     pf_pos += n;
-    if (__syncthreads_or(bad)) {
-      if (tid == 0) a.fb_items[atomicAdd(a.fb_count, 1)] = it;
-      continue;
-    }
     wait_b();  // phase B of the previous item has read X and Pt
-    if (live) {
+    if (bad) *s_flag = 1;  // (the item is declined as a whole, below; an out-of-range row is never written to the tile)
+    if (live && !bad) {
+      uint8_t *xrow = X + tid * 128;
+      const uint32_t t7s = (uint32_t)(tid & 7) << 4;
 #pragma unroll
       for (int u = 0; u < NU; ++u) {
         float v[8], q[8];
@@ -411,13 +410,15 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
           v[j] = xs[8 * u + j];
           q[j] = v[j] * v[j];  // data.array().square(), csrc/diag-gmm.cc:175 (the scaling is a power of two: exact)
         }
+        // unit index -> chunk (u >> 3) and swizzled 16-byte slot ((u & 7) << 4) ^ t7s of the thread's row
+        constexpr int ul = kStkLoCol0 / 8;
         uint4 hi, lo;
         split8(v, hi, lo);
-        *reinterpret_cast<uint4 *>(X + x_unit_off(u, tid)) = hi;                        // x: virtual columns 8u..
-        *reinterpret_cast<uint4 *>(X + x_unit_off(kStkLoCol0 / 8 + u, tid)) = lo;
+        *reinterpret_cast<uint4 *>(xrow + (u >> 3) * kAChunkBytes + ((((u) & 7) << 4) ^ t7s)) = hi;                  // x: virtual columns 8u..
+        *reinterpret_cast<uint4 *>(xrow + ((ul + u) >> 3) * kAChunkBytes + ((((ul + u) & 7) << 4) ^ t7s)) = lo;
         split8(q, hi, lo);
-        *reinterpret_cast<uint4 *>(X + x_unit_off(NU + u, tid)) = hi;                   // x^2: virtual columns DP + 8u..
-        *reinterpret_cast<uint4 *>(X + x_unit_off(kStkLoCol0 / 8 + NU + u, tid)) = lo;
+        *reinterpret_cast<uint4 *>(xrow + ((NU + u) >> 3) * kAChunkBytes + ((((NU + u) & 7) << 4) ^ t7s)) = hi;      // x^2: virtual columns DP + 8u..
+        *reinterpret_cast<uint4 *>(xrow + ((ul + NU + u) >> 3) * kAChunkBytes + ((((ul + NU + u) & 7) << 4) ^ t7s)) = lo;
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -428,6 +429,15 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
     }
     tc_fence_before();
     __syncthreads();
+    if (*s_flag != 0) {  // some row of the item is outside fp16's range: the whole item goes to the fp32 kernel
+      __syncthreads();   // (every thread has read the flag)
+      if (tid == 0) {
+        *s_flag = 0;
+        a.fb_items[atomicAdd(a.fb_count, 1)] = it;
+      }
+      __syncthreads();
+      continue;
+    }
     // ---- phase A (screening): L = X_hi . B_hi^T, N = NP
     if (warp_u == 0) {
       tc_fence_after();
@@ -624,6 +634,7 @@ khg_status stats_tc_build(khg_model *m) {
   KHG_CUDA_TRY(cudaGetLastError());
   int flag = 0;
   KHG_CUDA_TRY(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  KHG_CUDA_TRY(cudaMemcpyAsync(t.h_ascale, t.ascale, sizeof(float) * kStkMaxDP, cudaMemcpyDeviceToHost, st));
   KHG_CUDA_TRY(cudaStreamSynchronize(st));  // (pageable `off` and `flag` are done with)
   t.ready = flag == 0;
   return KHG_OK;
@@ -657,6 +668,7 @@ khg_status stats_tc_launch(khg_model *m, StatsTcArgs a, cudaStream_t st) {
   a.ascale = t.ascale;
   a.unscale = t.unscale;
   a.fb_count = t.fb_count;
+  for (int d = 0; d < kStkMaxDP; ++d) a.asc_c[d] = t.h_ascale[d];
   a.miv = m->d_miv;
   a.iv = m->d_iv;
   a.gconsts = m->d_gconsts;
