@@ -175,7 +175,11 @@ khg_status khg_pdf_posteriors(khg_model *m, int32_t pdf, const float *feats,
  * Replaces AccumDiagGmm storage (csrc/mle-diag-gmm.h:174-181) for all pdfs and
  * the totals of AccumAmDiagGmm (csrc/mle-am-diag-gmm.h:93-96).  One packed fp64
  * device buffer: [occ G | mean G*D (if m) | var G*D (if v) | tot_like |
- * tot_frames].  flags are augmented v=>m=>w (csrc/model-common.cc:72-84). */
+ * tot_frames].  flags are augmented v=>m=>w (csrc/model-common.cc:72-84).
+ * Lifetime: a khg_stats refers to its khg_model (stream, shapes) for as long as it lives — destroy the statistics
+ * before the model they were created for (khg_mle_update returns a NEW model: the old model and its statistics
+ * stay valid until the caller destroys them, statistics first).  Device views of the buffer
+ * (khg_stats_device_buffer) die with the handle. */
 khg_status khg_stats_create(khg_model *m, uint16_t flags, khg_stats **out);
 khg_status khg_stats_zero(khg_stats *s);
 khg_status khg_stats_flags(const khg_stats *s, uint16_t *flags);
