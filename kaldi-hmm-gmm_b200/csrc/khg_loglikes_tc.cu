@@ -438,9 +438,16 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
 #ifdef KHG_EXPERIMENTS
       // (timing only: 10 = every tile stores into the block's first 128 frames — an L2-resident window, no DRAM
       // write stream; 11 = every store goes to the scratch word)
+      // 12 = tile-major addressing out[t / 128][p][128] inside the same block: every CTA's stores of an item fall into ONE
+      // contiguous P x 512-byte region instead of P pieces 4 * ld bytes apart (address-translation locality of the store stream)
       const bool to_scratch = !valid || a.debug_mode == 11;
       char *out_t = to_scratch ? reinterpret_cast<char *>(a.scratch) : reinterpret_cast<char *>(a.out + (a.debug_mode == 10 ? (int64_t)row : t));
-      const uint32_t ld_bytes = to_scratch ? 0u : (uint32_t)(a.ld * 4);
+      uint32_t ld_bytes = to_scratch ? 0u : (uint32_t)(a.ld * 4);
+      if (a.debug_mode == 12 && valid) {
+        const int64_t P = __ldg(a.tile_p0 + a.n_tiles);
+        out_t = reinterpret_cast<char *>(a.out + (item / a.n_splits) * P * kTileM + row);
+        ld_bytes = (uint32_t)(kTileM * 4);
+      }
 #else
       // rows beyond T store into a scratch word (ld_bytes = 0): no predicate in the hot loop
       char *out_t = valid ? reinterpret_cast<char *>(a.out + t) : reinterpret_cast<char *>(a.scratch);
