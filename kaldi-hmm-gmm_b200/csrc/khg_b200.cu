@@ -261,7 +261,7 @@ khg_status khg_model_stats_kernel(khg_model *m, int32_t *kernel) {
 khg_status khg_model_set_kernel(khg_model *m, int32_t kernel) {
   KHG_REQUIRE(m && kernel >= KHG_KERNEL_AUTO && kernel <= KHG_KERNEL_TCGEN05_F16_GS, "bad kernel id");
   if (kernel >= KHG_KERNEL_TCGEN05 && !tc_supported(m)) {
-    set_error("tcgen05 kernel does not support this model shape (needs 2*dim+2 <= 160 for the tf32 split / <= 320 for the fp16 split, and every pdf <= 240 Gaussians)");
+    set_error("tcgen05 kernel does not support this model shape (needs 2*dim+2 <= 160 for the tf32 split / <= 320 for the fp16 split; pdfs of more than 240 Gaussians need the tf32 shape)");
     return KHG_ERR_UNSUPPORTED;
   }
   m->kernel = kernel;
@@ -358,23 +358,45 @@ static khg_status dense_device(khg_model *m, const float *d_feats, int64_t T, fl
     return KHG_ERR_UNSUPPORTED;
   }
   if (use_tc) {
-    // the tensor-core kernel writes pdf-major; frame-major goes through scratch + transpose
-    float *dst = d_out;
-    int64_t ldt = ld;
-    if (layout != KHG_PDF_MAJOR) {
-      ldt = (T + 3) & ~(int64_t)3;
-      KHG_TRY(m->w_out.reserve(sizeof(float) * (size_t)m->P * ldt));
-      dst = m->w_out.as<float>();
-    }
+    // The tensor-core kernel writes pdf-major rows of its (virtual) pdfs.  Directly into d_out when that is the layout
+    // asked for and no pdf is split; otherwise through a bounded scratch block, a chunk of frames at a time:
+    // transposed (frame-major) or merged (pdfs of more than 240 Gaussians run as virtual pdfs of unscaled
+    // log-sum-exps, merge_virtual_kernel combines and scales them into either layout).
+    const int Pv = m->tc.Pv;
+    const bool split = Pv != m->P;
     const unsigned *gate = nullptr;
     float gate_limit = 0.f;
-    KHG_TRY(tc_loglikes(m, d_feats, T, scale, dst, ldt, prec, &gate, &gate_limit));
-    // shapes the tf32 split cannot take (2*dim+1 > 160): the fp16 split's out-of-range
-    // fall-back is the fp32 SIMT kernel, gated on the same device word
-    if (gate != nullptr) KHG_TRY(simt_launch(m, d_feats, T, scale, dst, ldt, 1, gate, gate_limit));
-    if (layout != KHG_PDF_MAJOR) {
-      dim3 grid(grid_for(T, 32), grid_for(m->P, 32)), block(32, 8);
-      transpose_kernel<<<grid, block, 0, m->stream>>>(dst, m->P, T, ldt, d_out, ld);
+    if (layout == KHG_PDF_MAJOR && !split) {
+      KHG_TRY(tc_loglikes(m, d_feats, T, scale, d_out, ld, prec, &gate, &gate_limit));
+      // shapes the tf32 split cannot take (2*dim+1 > 160): the fp16 split's out-of-range
+      // fall-back is the fp32 SIMT kernel, gated on the same device word
+      if (gate != nullptr) KHG_TRY(simt_launch(m, d_feats, T, scale, d_out, ld, 1, gate, gate_limit));
+      return KHG_OK;
+    }
+    int64_t cap = std::max<int64_t>(1024, ((int64_t)(512e6 / (4.0 * Pv))) & ~(int64_t)1023);  // frames per scratch block (~512 MB)
+    if (const char *e = getenv("KHG_DENSE_SCRATCH_FRAMES")) cap = std::max<int64_t>(128, atoll(e) & ~(int64_t)127);  // (tests: several blocks)
+    const int64_t chunk = std::min<int64_t>(cap, (T + 3) & ~(int64_t)3);
+    KHG_TRY(m->w_out.reserve(sizeof(float) * (size_t)Pv * chunk));
+    float *scr = m->w_out.as<float>();
+    for (int64_t t0 = 0; t0 < T; t0 += chunk) {
+      const int64_t n = std::min(chunk, T - t0);
+      KHG_TRY(tc_loglikes(m, d_feats + t0 * m->dim, n, split ? 1.0f : scale, scr, chunk, prec, &gate, &gate_limit));
+      if (gate != nullptr) {
+        if (split) {
+          set_error("internal: virtual pdfs with a gated fp32 fall-back");
+          return KHG_ERR_UNSUPPORTED;
+        }
+        KHG_TRY(simt_launch(m, d_feats + t0 * m->dim, n, scale, scr, chunk, 1, gate, gate_limit));
+      }
+      float *dst = layout == KHG_PDF_MAJOR ? d_out + t0 : d_out + t0 * ld;
+      if (split) {
+        dim3 grid(grid_for(n, 32), grid_for(m->P, 32)), block(32, 8);
+        merge_virtual_kernel<<<grid, block, 0, m->stream>>>(scr, chunk, m->tc.d_vfirst, m->P, n, scale, dst, layout == KHG_PDF_MAJOR ? ld : 1,
+                                                            layout == KHG_PDF_MAJOR ? 1 : ld, m->d_err);
+      } else {
+        dim3 grid(grid_for(n, 32), grid_for(m->P, 32)), block(32, 8);
+        transpose_kernel<<<grid, block, 0, m->stream>>>(scr, m->P, n, chunk, dst, ld);
+      }
       ++g_launch_count;
       KHG_CUDA_TRY(cudaGetLastError());
     }

@@ -115,6 +115,12 @@ struct TcPack {
   bool grouped_segs = false;     // some tile has a group of short pdfs read by one load (epi_run_multi)
   bool two_chunk_segs = false;   // some pdf has 17..32 Gaussians: the epilogue's two-load segment form is in use
   bool dead_pdf = false;         // some pdf has only -inf gconsts: every call must fail like the reference
+  // pdfs of more than 240 Gaussians are split into virtual pdfs of <= 240 (the kernels' pdf ids are virtual ids);
+  // Pv == P when no pdf is split.  The kernels then write Pv rows of unscaled log-sum-exps and merge_virtual_kernel
+  // combines them (khg_b200.cu dense_device)
+  int Pv = 0;
+  std::vector<int32_t> v_off;    // Pv+1 Gaussian offsets of the virtual pdfs
+  int32_t *d_vfirst = nullptr;   // device, P+1: first virtual pdf of every pdf
   // Gaussian-stationary kernel (khg_loglikes_gs.cu): the split feature operand A' of the current block
   // of frames, a_rows x KPB16 fp16, and its TMA map (box 64 columns x 128 rows)
   Buf a_scr;

@@ -238,6 +238,43 @@ __global__ void transpose_kernel(const float *__restrict__ src, int64_t rows, in
   }
 }
 
+// pdfs of more than 240 Gaussians run on the tensor-core kernel as several VIRTUAL pdfs (<= 240 Gaussians each, see
+// tc_pack_build); src holds the unscaled log-sum-exp of every virtual pdf, row v = src + v * ld_src (frames
+// contiguous).  dst[p * sp + t * st] = scale * LogSumExp over the virtual rows [vfirst[p], vfirst[p + 1]) of pdf p
+// (csrc/eigen.cc:14-18 applied to the partial sums: log sum exp is associative).  A 32 x 32 tile goes through shared
+// memory so that both layouts of dst are written coalesced.
+__global__ void merge_virtual_kernel(const float *__restrict__ src, int64_t ld_src, const int32_t *__restrict__ vfirst, int P, int64_t T,
+                                     float scale, float *__restrict__ dst, int64_t sp, int64_t st, int *__restrict__ err) {
+  __shared__ float tile[32][33];
+  const int64_t t0 = (int64_t)blockIdx.x * 32;
+  const int p0 = blockIdx.y * 32;
+  const int64_t t = t0 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i;
+    if (p < P && t < T) {
+      const int v0 = vfirst[p], v1 = vfirst[p + 1];
+      float r = src[(int64_t)v0 * ld_src + t];
+      if (v1 - v0 > 1) {
+        float mx = r;
+        for (int v = v0 + 1; v < v1; ++v) mx = fmaxf(mx, src[(int64_t)v * ld_src + t]);
+        float sum = 0.f;
+        for (int v = v0; v < v1; ++v) sum += expf(src[(int64_t)v * ld_src + t] - mx);
+        r = mx + logf(sum);
+      }
+      if (!finite_f(r)) atomicOr(err, ERR_NONFINITE);
+      tile[i][threadIdx.x] = scale * r;
+    }
+  }
+  __syncthreads();
+  if (st == 1) {  // pdf-major: rows of dst are pdfs, frames contiguous
+    for (int i = threadIdx.y; i < 32; i += blockDim.y)
+      if (p0 + i < P && t < T) dst[(int64_t)(p0 + i) * sp + t] = tile[i][threadIdx.x];
+  } else {        // frame-major: pdfs contiguous
+    for (int i = threadIdx.y; i < 32; i += blockDim.y)
+      if (t0 + i < T && p0 + (int)threadIdx.x < P) dst[(t0 + i) * st + (int64_t)(p0 + threadIdx.x) * sp] = tile[threadIdx.x][i];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Per-pdf, per-Gaussian log-likelihoods: DiagGmm::LogLikelihoods /
 // LogLikelihoodsMatrix (csrc/diag-gmm.cc:167-189).  One thread per (t, g);

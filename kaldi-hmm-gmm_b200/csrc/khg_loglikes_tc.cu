@@ -550,16 +550,21 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
 static bool tc_shape_ok(const khg_model *m, bool f16) {
   const int K = 2 * m->dim + 2;  // feature columns + gconst + its residual
   const int ck = f16 ? Elem<true>::kChunkK : Elem<false>::kChunkK;
-  return (K + ck - 1) / ck <= kMaxChunks && m->max_gp <= kTileN;
+  return (K + ck - 1) / ck <= kMaxChunks;
 }
-bool tc_supported(const khg_model *m) { return tc_shape_ok(m, false) || tc_shape_ok(m, true); }
+// pdfs of more than 240 Gaussians run as virtual sub-pdfs; that form has no gated fp32 fall-back, so it needs the
+// tf32 split as the out-of-range path of the fp16 split
+bool tc_supported(const khg_model *m) {
+  return (tc_shape_ok(m, false) || tc_shape_ok(m, true)) && (m->max_gp <= kTileN || tc_shape_ok(m, false));
+}
 
 void tc_pack_free(khg_model *m) {
   TcPack &t = m->tc;
   gs_free(m);
   cudaFree(t.bhi); cudaFree(t.blo); cudaFree(t.tile_g0); cudaFree(t.tile_p0);
   cudaFree(t.hhi); cudaFree(t.hlo); cudaFree(t.ascale); cudaFree(t.gate);
-  cudaFree(t.epi_hdr); cudaFree(t.runs); cudaFree(t.seg);
+  cudaFree(t.epi_hdr); cudaFree(t.runs); cudaFree(t.seg); cudaFree(t.d_vfirst);
+  t.d_vfirst = nullptr;
   t.epi_hdr = nullptr;
   t.runs = nullptr;
   t.seg = nullptr;
@@ -670,7 +675,7 @@ static khg_status tc_pack_build_f16(khg_model *m) {
 khg_status tc_pack_build(khg_model *m) {
   TcPack &t = m->tc;
   tc_pack_free(m);
-  const int D = m->dim, G = m->G, P = m->P;
+  const int D = m->dim, G = m->G;
   t.K = 2 * D + 1;
   t.K8 = (t.K + 1 + 7) / 8 * 8;
   t.KP = (t.K8 + 31) / 32 * 32;      // A_hi / A_lo row width in smem
@@ -678,18 +683,34 @@ khg_status tc_pack_build(khg_model *m) {
   t.tab8 = make_stage_tab(t.K8, Kc8, 32, 8, false);
   t.KPB = t.tab8.n * 32;
   t.rows = (G + kTileN + 15) / 16 * 16;
+  // virtual pdfs: a pdf of more than 240 Gaussians becomes ceil(len / 240) pieces of (almost) equal size
+  std::vector<int32_t> vfirst(m->P + 1);
+  t.v_off.assign(1, 0);
+  for (int q = 0; q < m->P; ++q) {
+    vfirst[q] = (int32_t)t.v_off.size() - 1;
+    const int len = m->h_offsets[q + 1] - m->h_offsets[q], k = std::max(1, (len + kTileN - 1) / kTileN);
+    for (int i = 1; i <= k; ++i) t.v_off.push_back(m->h_offsets[q] + (int32_t)((int64_t)len * i / k));
+  }
+  t.Pv = (int)t.v_off.size() - 1;
+  vfirst[m->P] = t.Pv;
+  const int P = t.Pv;                         // from here on "pdf" means virtual pdf
+  const std::vector<int32_t> &off = t.v_off;
+  if (t.Pv != m->P) {
+    KHG_CUDA_TRY(cudaMalloc(&t.d_vfirst, sizeof(int32_t) * (m->P + 1)));
+    KHG_CUDA_TRY(cudaMemcpy(t.d_vfirst, vfirst.data(), sizeof(int32_t) * (m->P + 1), cudaMemcpyHostToDevice));
+  }
   // pdf-aligned N tiles (greedy)
   t.h_tile_g0.clear();
   t.h_tile_p0.clear();
   int p = 0;
   while (p < P) {
-    int g0 = m->h_offsets[p];
+    int g0 = off[p];
     t.h_tile_g0.push_back(g0);
     t.h_tile_p0.push_back(p);
     int q = p;
-    while (q < P && m->h_offsets[q + 1] - g0 <= kTileN) ++q;
+    while (q < P && off[q + 1] - g0 <= kTileN) ++q;
     if (q == p) {
-      set_error("a pdf has more than 240 Gaussians: not supported by the tcgen05 kernel");
+      set_error("internal: a virtual pdf has more than 240 Gaussians");
       return KHG_ERR_UNSUPPORTED;
     }
     p = q;
@@ -709,10 +730,10 @@ khg_status tc_pack_build(khg_model *m) {
       // TMEM load per group), single pdfs otherwise; key = grouped << 8 | len
       std::vector<std::pair<int, int>> by_len;  // (key, first pdf)
       for (int q = pa; q < pb;) {
-        const int len = m->h_offsets[q + 1] - m->h_offsets[q];
+        const int len = off[q + 1] - off[q];
         const int ns = len <= 8 ? 16 / len : 1;
         bool grp = ns > 1 && q + ns <= pb;
-        for (int k = 1; grp && k < ns; ++k) grp = m->h_offsets[q + k + 1] - m->h_offsets[q + k] == len;
+        for (int k = 1; grp && k < ns; ++k) grp = off[q + k + 1] - off[q + k] == len;
         if (grp) t.grouped_segs = true;
         by_len.emplace_back((grp ? 256 : 0) | len, q);
         q += grp ? ns : 1;
@@ -733,7 +754,7 @@ khg_status tc_pack_build(khg_model *m) {
           else
             runs.push_back(tag | 1u << 8);
           if (len > 16 && len <= 32) t.two_chunk_segs = true;
-          seg.push_back((uint32_t)(m->h_offsets[q] - g0) | (len > 16 && len <= 32 ? kSegTwoChunks : 0u) | (uint32_t)q << kSegPdfShift);
+          seg.push_back((uint32_t)(off[q] - g0) | (len > 16 && len <= 32 ? kSegTwoChunks : 0u) | (uint32_t)q << kSegPdfShift);
         }
         seg.push_back(0);  // two sentinels: the epilogue prefetches two descriptors ahead
         seg.push_back(0);
@@ -757,7 +778,7 @@ khg_status tc_pack_build(khg_model *m) {
     std::vector<float> gc(G);
     KHG_CUDA_TRY(cudaMemcpy(gc.data(), m->d_gconsts, sizeof(float) * G, cudaMemcpyDeviceToHost));
     t.dead_pdf = false;
-    for (int q = 0; q < P && !t.dead_pdf; ++q) {
+    for (int q = 0; q < m->P && !t.dead_pdf; ++q) {
       bool all_dead = true;
       for (int g = m->h_offsets[q]; g < m->h_offsets[q + 1]; ++g) all_dead = all_dead && std::isinf(gc[g]) && gc[g] < 0;
       t.dead_pdf = all_dead;

@@ -286,14 +286,21 @@ def test_tc_length_classes_and_kernel_query(oracle):
         dm = _one(model, kernel)
         assert dm.dense_kernel() == expect
         _check(dm.loglikes_all_pdfs(feats), ref)
-    # a pdf with 241 Gaussians does not fit an accumulator tile: AUTO falls back to the SIMT kernel
-    sizes2 = np.array([241, 3], np.int32)
+    # a pdf with 241 Gaussians does not fit an accumulator tile: it runs as two virtual pdfs (121 + 120) on the
+    # tensor cores; with features too wide for the tf32 split (no device-side fall-back for that form) it is fp32
     off2 = np.array([0, 241, 244], np.int32)
     dm = DeviceModel(D, off2)
     dm.upload(np.full(244, 1 / 122, np.float32), miv[:244], iv[:244])
-    assert dm.dense_kernel() == 1
+    assert dm.dense_kernel() == 3
+    dm.set_kernel(TC)
+    assert dm.dense_kernel() == 2
+    Dw = 100
+    rng2 = np.random.default_rng(2)
+    dmw = DeviceModel(Dw, off2)
+    dmw.upload(np.full(244, 1 / 122, np.float32), rng2.standard_normal((244, Dw)).astype(np.float32), np.ones((244, Dw), np.float32))
+    assert dmw.dense_kernel() == 1
     with pytest.raises(RuntimeError, match="does not support"):
-        dm.set_kernel(TC)
+        dmw.set_kernel(TC)
 
 
 @pytest.mark.parametrize("sizes", [
@@ -434,3 +441,67 @@ def test_gaussian_stationary_rejects_wide_features_and_raises_on_nonfinite(oracl
     feats[5, 2] = np.nan
     with pytest.raises(RuntimeError, match="Invalid answer"):
         _one(model, TC_F16_GS).loglikes_all_pdfs(feats)
+
+
+def _ragged(oracle, D, sizes, seed=11):
+    rng = np.random.default_rng(seed)
+    sizes = np.asarray(sizes, np.int32)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    G = int(offsets[-1])
+    means = (2.0 * rng.standard_normal((G, D))).astype(np.float32)
+    vars_ = rng.uniform(0.5, 2, (G, D)).astype(np.float32)
+    w = np.concatenate([rng.dirichlet(np.ones(s)) for s in sizes]).astype(np.float32)
+    iv = (1 / vars_).astype(np.float32)
+    miv = (means * iv).astype(np.float32)
+    gc = np.concatenate([oracle.compute_gconsts(w[a:b], miv[a:b], iv[a:b])[0] for a, b in zip(offsets[:-1], offsets[1:])])
+    return ko.PackedModel(offsets, w, miv, iv, gc), means, vars_
+
+
+@pytest.mark.parametrize("kernel", [AUTO, TC, TC_F16])
+def test_pdfs_of_more_than_240_gaussians_on_the_tensor_cores(oracle, kernel):
+    """DiagGmm-sized mixtures (csrc/diag-gmm.cc:241-317 builds UBMs of up to 2048 components): a pdf of more than 240
+    Gaussians runs as virtual sub-pdfs whose log-sum-exps merge_virtual_kernel combines — both layouts, device and
+    host buffers, next to small pdfs; the kernel that ran is asserted."""
+    import torch
+
+    model, means, vars_ = _ragged(oracle, 20, [1, 300, 2, 17, 64, 9, 1, 33, 700, 241, 240])
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, 1500)
+    dm = _one(model, kernel)
+    assert dm.dense_kernel() == (TC if kernel == TC else TC_F16)
+    ref, bad = oracle.loglikes_all_pdfs(model, feats)
+    assert bad == 0
+    _check(dm.loglikes_all_pdfs(feats), ref)
+    _check(dm.loglikes_all_pdfs(feats, scale=0.1, layout=1).T, 0.1 * ref.astype(np.float64))
+    dfeats = torch.from_numpy(feats).cuda()
+    _check(dm.loglikes_all_pdfs(dfeats).cpu().numpy(), ref)
+    _check(dm.loglikes_all_pdfs(dfeats, layout=1).cpu().numpy().T, ref)
+
+
+def test_ubm_sized_single_pdf_on_the_tensor_cores(oracle):
+    model, means, vars_ = _ragged(oracle, 40, [2048], seed=5)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, 700)
+    dm = _one(model, AUTO)
+    assert dm.dense_kernel() == TC_F16
+    ref, bad = oracle.loglikes_all_pdfs(model, feats)
+    assert bad == 0
+    _check(dm.loglikes_all_pdfs(feats), ref)
+
+
+def test_frame_major_device_output_in_bounded_scratch_blocks(oracle, monkeypatch):
+    """Frame-major output of device-resident frames goes through a bounded scratch block, a chunk of frames at a time
+    (KHG_DENSE_SCRATCH_FRAMES shrinks the block so that a small batch takes several)."""
+    import torch
+
+    monkeypatch.setenv("KHG_DENSE_SCRATCH_FRAMES", "256")
+    model, means, vars_ = ko.make_synthetic_model(40, 37, 350, oracle=oracle)
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, 1111)
+    dm = _one(model, AUTO)
+    ref, _ = oracle.loglikes_all_pdfs(model, feats)
+    got = dm.loglikes_all_pdfs(torch.from_numpy(feats).cuda())
+    _check(got.cpu().numpy(), ref)
+    big, mu, va = _ragged(oracle, 20, [300, 5, 260])
+    f2, _ = ko.make_synthetic_frames(big, mu, va, 900)
+    d2 = _one(big, AUTO)
+    r2, _ = oracle.loglikes_all_pdfs(big, f2)
+    _check(d2.loglikes_all_pdfs(torch.from_numpy(f2).cuda(), layout=1).cpu().numpy().T, r2)
+    _check(d2.loglikes_all_pdfs(torch.from_numpy(f2).cuda()).cpu().numpy(), r2)
