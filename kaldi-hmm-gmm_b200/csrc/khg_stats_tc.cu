@@ -41,6 +41,11 @@ constexpr float kStkWeightLimit = 8.f;           // |w| * 4096 must stay inside 
 #ifndef KHG_STK_CTAS
 #define KHG_STK_CTAS 3
 #endif
+#ifdef KHG_STK_TIMING  // per-phase cycle counters of thread 0, printed by one CTA (tools/ab_variant.sh x -DKHG_STK_TIMING)
+#define STK_T(i) do { const long long _t = clock64(); if (tid == 0) tacc[i] += _t - tlast; tlast = _t; } while (0)
+#else
+#define STK_T(i) do { } while (0)
+#endif
 constexpr bool kStkRegPrefetch = KHG_STK_REG_PREFETCH != 0;  // 1: the next item's rows wait in registers (40 more of them)
 constexpr float kStkScreen = 16.f;               // Gaussians within this of the frame's best (screened) log-like are re-evaluated in fp32
 
@@ -349,7 +354,11 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
   if (kStkRegPrefetch) load_rows(idx1);
   idx2 = load_index(i0 + 1);
   int pf_pos = i0 < i1 ? s_desc[0].y + 3 * 128 + tid : 0;
+#ifdef KHG_STK_TIMING
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
   for (int it = i0; it < i1; ++it) {
+    STK_T(7);
     if (it - stage0 == kStkDescStage) {
       __syncthreads();  // (every thread has read its descriptors of the previous stage)
       stage_descs(it);
@@ -378,6 +387,7 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
       vf = mf + NP * pitch;
       gcf = vf + NP * pitch;
     }
+    STK_T(0);  // pdf change: flush, image load
     // ---- this item's rows (prefetched), scaled; range check (NaN and Inf fail it too)
     const bool live = tid < n;
     if (!kStkRegPrefetch) load_rows(idx1);  // (an L2 hit: the row was prefetched about four tiles ago)
@@ -397,7 +407,9 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
     idx2 = load_index(it + 2);
     l2_pipeline(pf_pos);
     pf_pos += n;
+    STK_T(1);  // scale, check, next loads issued
     wait_b();  // phase B of the previous item has read X and Pt
+    STK_T(2);  // wait for phase B of the previous item
     if (bad) *s_flag = 1;  // (the item is declined as a whole, below; an out-of-range row is never written to the tile)
     if (live && !bad) {
       uint8_t *xrow = X + tid * 128;
@@ -429,6 +441,7 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
     }
     tc_fence_before();
     __syncthreads();
+    STK_T(3);  // build + barrier
     if (*s_flag != 0) {  // some row of the item is outside fp16's range: the whole item goes to the fp32 kernel
       __syncthreads();   // (every thread has read the flag)
       if (tid == 0) {
@@ -455,6 +468,7 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
     mbar_wait(sBarA, ph_a);
     ph_a ^= 1;
     tc_fence_after();
+    STK_T(4);  // phase A: issue + wait
     float lse;
     if (NPM == 16 || NP == 16) lse = stk_softmax_store<16, DP>(trow, ng, w, live, Pt, tid, xs, mf, vf, gcf, pitch);
     else lse = stk_softmax_store<32, DP>(trow, ng, w, live, Pt, tid, xs, mf, vf, gcf, pitch);
@@ -467,6 +481,7 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
     tc_fence_before();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    STK_T(5);  // softmax, exact re-evaluation, posterior tile + barrier
     // ---- phase B: S_a (+)= X[chunks 0, 1]^T . [P_hi ; P_lo] (N = 2 NP), S_c (+)= X[chunk 2, ...]^T . P_hi (N = NP); X read
     // MN-major: 16 frames = 2048 bytes per K step, LBO = one chunk (the next 64 virtual columns)
     if (warp_u == 0) {
@@ -488,6 +503,7 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
       }
       __syncwarp();
     }
+    STK_T(6);  // phase B issue (the issuing thread stalls behind the tensor pipe's queue: 16 MMAs x ~66 cycles)
     b_pending = true;
     if (++acc_tiles == kStkMaxTilesPerFlush) {
       flush();
@@ -497,6 +513,12 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
   if (acc_tiles > 0) flush();
   wait_b();
   if (m_pending) mbar_wait(sBarM, ph_m);
+#ifdef KHG_STK_TIMING
+  if (tid == 0 && blockIdx.x == 7 && i1 > i0)
+    printf("K3t CTA 7: %d items; cycles per item: pdf-change %lld | scale+issue %lld | wait B %lld | build+bar %lld | phase A %lld | softmax+bar %lld | issue B %lld | loop %lld\n",
+           i1 - i0, tacc[0] / (i1 - i0), tacc[1] / (i1 - i0), tacc[2] / (i1 - i0), tacc[3] / (i1 - i0), tacc[4] / (i1 - i0), tacc[5] / (i1 - i0),
+           tacc[6] / (i1 - i0), tacc[7] / (i1 - i0));
+#endif
 
   for (int off = 16; off > 0; off >>= 1) {
     my_like += __shfl_xor_sync(0xffffffffu, my_like, off);
