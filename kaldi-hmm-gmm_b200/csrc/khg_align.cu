@@ -730,8 +730,7 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
       break;
     }
   const size_t smem = (use_gcost ? 0 : cost_bytes) + 4 * (size_t)FC * n_pdf_max + 16;
-  static std::once_flag once;
-  std::call_once(once, [] { cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
+  KHG_CUDA_TRY(cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));  // (per device: set on every call)
   const int NT = S_max <= 256 ? 128 : (S_max <= 2048 ? 256 : 512);
   double *d_gcost = nullptr;
   if (use_gcost) {

@@ -328,10 +328,7 @@ static khg_status simt_launch(khg_model *m, const float *d_feats, int64_t T, flo
     set_error("feature dimension too large for the dense SIMT kernel");
     return KHG_ERR_UNSUPPORTED;
   }
-  static std::once_flag once;
-  std::call_once(once, [] {
-    cudaFuncSetAttribute(loglikes_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  });
+  KHG_CUDA_TRY(cudaFuncSetAttribute(loglikes_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));  // (per device: set on every call)
   int64_t n_ft = (T + kDenseFrames - 1) / kDenseFrames;
   // enough CTAs for >= 2 waves when T is small: split the pdf range
   int groups = (int)std::min<int64_t>(std::max<int64_t>(1, (4LL * m->sm_count + n_ft - 1) / n_ft), std::max(1, m->P / 4));

@@ -153,8 +153,7 @@ extern "C" khg_status khg_gaussian_selection(khg_model *m, int32_t pdf, const fl
     set_error("too many candidates for the selection kernel");
     return KHG_ERR_UNSUPPORTED;
   }
-  static std::once_flag once;
-  std::call_once(once, [] { cudaFuncSetAttribute(gselect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+  KHG_CUDA_TRY(cudaFuncSetAttribute(gselect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));  // (per device: set on every call)
   const int32_t *d_pre = nullptr;
   if (n_preselect > 0) {
     KHG_TRY(m->w_sub.reserve(sizeof(int32_t) * n_preselect));
