@@ -85,7 +85,7 @@ typedef struct khg_model khg_model; /* device-resident packed AmDiagGmm      */
 typedef struct khg_stats khg_stats; /* device-resident packed AccumAmDiagGmm */
 
 const char *khg_last_error(void);
-int32_t khg_abi_version(void); /* 4 (3 + khg_model_stats_kernel) */
+int32_t khg_abi_version(void); /* 4 (3 + khg_model_stats_kernel, khg_align_last_tile_fraction) */
 
 khg_status khg_device_count(int32_t *count);
 khg_status khg_set_device(int32_t device);
@@ -349,6 +349,11 @@ khg_status khg_align_batch(khg_model *m, const khg_graph_batch *graphs, const fl
 /* Utterances of the most recent khg_align_batch call (this process) that were re-aligned by the exact
  * host decoder below because the device search could not certify its result (diagnostics). */
 int64_t khg_align_last_exact_count(void);
+/* Fraction of the (128-frame tile, 240-Gaussian model tile) units of the all-pdf likelihood block that the most recent
+ * khg_align_batch call computed: the dense kernel skips model tiles that hold no pdf of the graphs of the frames'
+ * utterances (the batched form of the reference's lazy per-pdf evaluation, csrc/decodable-am-diag-gmm.cc:29-71);
+ * 1.0 when everything was computed (small batches, KHG_ALIGN_TILE_SUBSET=0, kernels without that mode). */
+double khg_align_last_tile_fraction(void);
 
 /* The reference's FasterDecoder + AlignUtteranceWrapper on the HOST for ONE utterance of a graph batch,
  * consuming a block of log-likelihoods computed elsewhere (the GPU): csrc/faster-decoder.cc:36-425 with

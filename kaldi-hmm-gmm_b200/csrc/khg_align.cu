@@ -81,6 +81,7 @@ struct UttOut {
   int32_t pad2[3];
 };
 
+double g_align_tile_fraction = 1.0;        // (tile, frame tile) units the last call's dense kernel computed / all of them
 int64_t g_align_exact_utts = 0;           // utterances of the last khg_align_batch call that took the exact host pass
 constexpr int kAlignMinActive = 20;       // faster-decoder.h:42
 constexpr float kAlignBeamDelta = 0.5f;   // faster-decoder.h:43
@@ -557,26 +558,95 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   const int64_t ld = (chunk_frames_max + 3) & ~(int64_t)3;
   KHG_TRY(m->w_al_block.reserve(sizeof(float) * (size_t)P * std::max<int64_t>(ld, 4)));
   float *d_block = m->w_al_block.as<float>();
-  auto launch_dense = [&](int u0, int u1) -> khg_status {
+  // Dense kernel of a chunk of utterances.  Only the model tiles (240-Gaussian blocks of pdfs) that hold a pdf of some
+  // graph of the frames' utterances are computed — the batched form of what the reference's decodable does lazily
+  // (DecodableAmDiagGmmUnmapped::LogLikelihoodZeroBased, csrc/decodable-am-diag-gmm.cc:29-71, evaluates a pdf when
+  // the decoder asks for it): per pair of 128-frame tiles the union of the tiles of the utterances it overlaps
+  // (KHG_ALIGN_TILE_SUBSET=0: everything).  The search reads the rows of its utterance's pdfs only.
+  const bool want_subset = !(getenv("KHG_ALIGN_TILE_SUBSET") && atoi(getenv("KHG_ALIGN_TILE_SUBSET")) == 0) && m->tc.ready &&
+                           m->kernel != KHG_KERNEL_SIMT;
+  std::vector<std::vector<int32_t>> updf(U);  // distinct pdfs of every graph (filled by the first host pass)
+  int64_t units_done = 0, units_all = 0;
+  auto stage_feats = [&](int u0, int u1, const float **d_f) -> khg_status {
     const int64_t f0 = gb->frame_offsets[u0] - gb->frame_offsets[0], nfr = gb->frame_offsets[u1] - gb->frame_offsets[u0];
-    if (nfr <= 0) return KHG_OK;
-    const float *d_f = feats + (gb->frame_offsets[0] + f0) * D;
-    if (feats_loc == KHG_HOST) {
+    *d_f = feats + (gb->frame_offsets[0] + f0) * D;
+    if (nfr > 0 && feats_loc == KHG_HOST) {
       KHG_TRY(m->w_feats.reserve(sizeof(float) * (size_t)nfr * D));
-      KHG_CUDA_TRY(cudaMemcpyAsync(m->w_feats.p, d_f, sizeof(float) * (size_t)nfr * D, cudaMemcpyHostToDevice, st));
-      d_f = m->w_feats.as<float>();
+      KHG_CUDA_TRY(cudaMemcpyAsync(m->w_feats.p, *d_f, sizeof(float) * (size_t)nfr * D, cudaMemcpyHostToDevice, st));
+      *d_f = m->w_feats.as<float>();
     }
+    return KHG_OK;
+  };
+  auto run_dense = [&](int u0, int u1, const float *d_f, bool subset) -> khg_status {
+    const int64_t nfr = gb->frame_offsets[u1] - gb->frame_offsets[u0];
+    if (nfr <= 0) return KHG_OK;
+    TileSubset sub;
+    const int n_tiles = m->tc.ready ? tc_num_tiles(m) : 0;
+    const int64_t n_pairs = (nfr + 255) / 256;
+    if (subset && n_tiles > 1) {
+      // tiles of every utterance (bitmap), then per frame-tile pair the union over the utterances it overlaps
+      const int words = (n_tiles + 63) / 64;
+      std::vector<uint64_t> ubits((size_t)(u1 - u0) * words, 0);
+      parallel_for(u1 - u0, [&](int i, int) {
+        uint64_t *b = ubits.data() + (size_t)i * words;
+        for (int32_t pdf : updf[u0 + i]) {
+          int ja, jb;
+          tc_pdf_tile_range(m, pdf, &ja, &jb);
+          for (int j = ja; j <= jb; ++j) b[j >> 6] |= 1ull << (j & 63);
+        }
+      });
+      std::vector<int32_t> off((size_t)n_pairs + 1, 0), tiles;
+      tiles.reserve((size_t)n_pairs * 64);
+      std::vector<uint64_t> acc(words);
+      int u = u0;
+      const int64_t base = gb->frame_offsets[u0];
+      for (int64_t q = 0; q < n_pairs; ++q) {
+        const int64_t fa = base + q * 256, fb = std::min<int64_t>(fa + 256, base + nfr);
+        while (u + 1 < u1 && gb->frame_offsets[u + 1] <= fa) ++u;
+        std::fill(acc.begin(), acc.end(), 0);
+        for (int v = u; v < u1 && gb->frame_offsets[v] < fb; ++v)
+          if (gb->frame_offsets[v + 1] > fa)
+            for (int w2 = 0; w2 < words; ++w2) acc[w2] |= ubits[(size_t)(v - u0) * words + w2];
+        for (int w2 = 0; w2 < words; ++w2)
+          for (uint64_t x = acc[w2]; x; x &= x - 1) tiles.push_back(w2 * 64 + __builtin_ctzll(x));
+        off[q + 1] = (int32_t)tiles.size();
+      }
+      KHG_TRY(m->w_al_tiles.reserve(4 * (off.size() + std::max<size_t>(tiles.size(), 1))));
+      int32_t *d_off = m->w_al_tiles.as<int32_t>(), *d_tiles = d_off + off.size();
+      KHG_CUDA_TRY(cudaMemcpyAsync(d_off, off.data(), 4 * off.size(), cudaMemcpyHostToDevice, st));
+      KHG_CUDA_TRY(cudaMemcpyAsync(d_tiles, tiles.data(), 4 * tiles.size(), cudaMemcpyHostToDevice, st));
+      KHG_CUDA_TRY(cudaStreamSynchronize(st));  // (the host vectors go out of scope)
+      sub.off = d_off;
+      sub.tiles = d_tiles;
+      bool used = false;
+      KHG_TRY(dense_block(m, d_f, nfr, acoustic_scale, KHG_PDF_MAJOR, d_block, ld, &sub, &used));
+      units_all += n_pairs * n_tiles;
+      units_done += used ? (int64_t)tiles.size() : n_pairs * n_tiles;
+      return KHG_OK;
+    }
+    units_all += n_pairs * std::max(1, n_tiles);
+    units_done += n_pairs * std::max(1, n_tiles);
     return dense_block(m, d_f, nfr, acoustic_scale, KHG_PDF_MAJOR, d_block, ld);
   };
+  auto launch_dense = [&](int u0, int u1, bool subset) -> khg_status {
+    const float *d_f = nullptr;
+    KHG_TRY(stage_feats(u0, u1, &d_f));
+    return run_dense(u0, u1, d_f, subset);
+  };
+  // with the subset the kernel of the first chunk needs the graphs' pdf lists (first host pass below); without it, it is
+  // launched right away and runs under the whole host preparation
+  const float *d_f0 = nullptr;
   if (timing) cudaEventRecord(ev[0], st);
-  KHG_TRY(launch_dense(chunk_start[0], chunk_start[1]));
-  if (timing) cudaEventRecord(ev[1], st);
+  KHG_TRY(stage_feats(chunk_start[0], chunk_start[1], &d_f0));
+  if (!want_subset) {
+    KHG_TRY(run_dense(chunk_start[0], chunk_start[1], d_f0, false));
+    if (timing) cudaEventRecord(ev[1], st);
+  }
 
   // ---------------- host: transpose every graph (incoming emitting arcs per state, incoming
   // epsilon arcs per state), local pdf lists
   std::vector<UttDesc> desc(U);
   std::vector<int32_t> n_emit(U, 0), n_eps(U, 0), bad(U, 0), neg_eps(U, 0);
-  std::vector<std::vector<int32_t>> updf(U);
   std::vector<int32_t> in_off((size_t)S_all + 1, 0), arc_src(A_all), arc_lp(A_all);
   std::vector<int32_t> eps_deg((size_t)S_all, 0);
   const int n_workers = 16;
@@ -621,6 +691,10 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
       cudaStreamSynchronize(st);  // the first chunk's dense kernel is already running
       KHG_REQUIRE(false, "graph of utterance " + std::to_string(u) + ": state / label / offset out of range");
     }
+  if (want_subset) {
+    KHG_TRY(run_dense(chunk_start[0], chunk_start[1], d_f0, true));
+    if (timing) cudaEventRecord(ev[1], st);
+  }
   // prefix sums: in-arc CSR over all states; epsilon-destination lists
   for (size_t s = 0; s < (size_t)S_all; ++s) in_off[s + 1] += in_off[s];
   std::vector<int32_t> ed_state, ed_off(1, 0), utt_pdfs;
@@ -755,7 +829,7 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     const int u0 = chunk_start[c], u1 = chunk_start[c + 1];
     if (c > 0) {
       if (timing) cudaEventRecord(ev[0], st);
-      KHG_TRY(launch_dense(u0, u1));
+      KHG_TRY(launch_dense(u0, u1, want_subset));
       if (timing) cudaEventRecord(ev[1], st);
     }
     if (timing) cudaEventRecord(ev[3], st);  // (chunk 0: ev[0] / ev[1] were recorded around the early launch)
@@ -855,12 +929,13 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   KHG_CUDA_TRY(cudaStreamSynchronize(st));
   if (timing) {
     fprintf(stderr, "khg_align_batch: utts %d frames %lld states %d arcs %d | S_max %d n_pdf_max %d FC %d NT %d smem %zu chunks %zu | "
-            "host prep %.2f ms, dense %.2f ms, search %.2f ms, exact host pass %.2f ms (%d utterances), total %.2f ms\n", U,
+            "host prep %.2f ms, dense %.2f ms (%.1f %% of the tile units), search %.2f ms, exact host pass %.2f ms (%d utterances), total %.2f ms\n", U,
             (long long)T_all, S_all, A_all, S_max, n_pdf_max, FC, NT, smem, chunk_start.size() - 1, t_prep - t_begin, ms_dense,
-            ms_search, ms_exact, n_redo_total, now() - t_begin);
+            units_all > 0 ? 100.0 * units_done / units_all : 100.0, ms_search, ms_exact, n_redo_total, now() - t_begin);
     for (auto &e : ev) cudaEventDestroy(e);
   }
   g_align_exact_utts = n_redo_total;
+  g_align_tile_fraction = units_all > 0 ? (double)units_done / (double)units_all : 1.0;
   for (int u = 0; u < U; ++u) {
     if (utt_status) utt_status[u] = h_outs[u].status;
     // decoder-wrappers.cc:91: like = -(graph + acoustic) / acoustic_scale
@@ -871,3 +946,4 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
 }
 
 extern "C" int64_t khg_align_last_exact_count(void) { return g_align_exact_utts; }
+extern "C" double khg_align_last_tile_fraction(void) { return g_align_tile_fraction; }

@@ -291,7 +291,7 @@ void khg_model_destroy(khg_model *m) {
   for (Buf *b : {&m->w_feats, &m->w_ids, &m->w_wts, &m->w_out, &m->w_pf, &m->w_keys, &m->w_vals_in,
                  &m->w_vals_out, &m->w_cub, &m->w_starts, &m->w_item_start, &m->w_tot, &m->w_tid,
                  &m->w_tid2pdf, &m->w_trans, &m->w_keys_out, &m->w_sub, &m->w_full, &m->w_al_graph,
-                 &m->w_al_block, &m->w_al_bp, &m->w_al_cost, &m->w_al_ali, &m->w_al_path, &m->w_al_xlist, &m->w_al_xll, &m->w_item_desc, &m->w_fb_items})
+                 &m->w_al_block, &m->w_al_bp, &m->w_al_cost, &m->w_al_ali, &m->w_al_path, &m->w_al_xlist, &m->w_al_xll, &m->w_item_desc, &m->w_fb_items, &m->w_al_tiles})
     b->release();
   for (int i = 0; i < 2; ++i) {
     m->pin_feats[i].release(); m->pin_ids[i].release(); m->pin_wts[i].release();
@@ -346,8 +346,10 @@ static khg_status simt_launch(khg_model *m, const float *d_feats, int64_t T, flo
   return KHG_OK;
 }
 
+constexpr int kSubsetMinTilesPerSm = 1;  // the tile subset needs n_splits == 1 in tc_launch: at least 2 frame tiles per SM
 static khg_status dense_device(khg_model *m, const float *d_feats, int64_t T, float scale,
-                               int layout, float *d_out, int64_t ld) {
+                               int layout, float *d_out, int64_t ld, const TileSubset *subset = nullptr, bool *subset_used = nullptr) {
+  if (subset_used) *subset_used = false;
   const bool use_tc = m->kernel != KHG_KERNEL_SIMT && m->tc.ready;
   const int prec = m->kernel == KHG_KERNEL_TCGEN05 ? 1 : (m->kernel == KHG_KERNEL_TCGEN05_F16 ? 2 : (m->kernel == KHG_KERNEL_TCGEN05_F16_GS ? 3 : 0));
   if (m->kernel >= KHG_KERNEL_TCGEN05 && !m->tc.ready) {
@@ -364,7 +366,11 @@ static khg_status dense_device(khg_model *m, const float *d_feats, int64_t T, fl
     const unsigned *gate = nullptr;
     float gate_limit = 0.f;
     if (layout == KHG_PDF_MAJOR && !split) {
-      KHG_TRY(tc_loglikes(m, d_feats, T, scale, d_out, ld, prec, &gate, &gate_limit));
+      // (the tile subset of the batched aligner: honoured by the frame-stationary kernels with whole tiles per CTA,
+      // and only when no gated fp32 fall-back is involved; otherwise everything is computed)
+      const bool sub = subset && subset->off && prec != 3 && (m->tc.tf32_ready || prec == 2) && T >= 2LL * kSubsetMinTilesPerSm * m->sm_count * 128;
+      KHG_TRY(tc_loglikes(m, d_feats, T, scale, d_out, ld, prec, &gate, &gate_limit, sub ? subset : nullptr));
+      if (subset_used) *subset_used = sub;
       // shapes the tf32 split cannot take (2*dim+1 > 160): the fp16 split's out-of-range
       // fall-back is the fp32 SIMT kernel, gated on the same device word
       if (gate != nullptr) KHG_TRY(simt_launch(m, d_feats, T, scale, d_out, ld, 1, gate, gate_limit));
@@ -1096,8 +1102,9 @@ khg_status finish_model_from_device(khg_model *nm, int32_t *num_bad) {
   return KHG_OK;
 }
 
-khg_status dense_block(khg_model *m, const float *d_feats, int64_t T, float scale, int layout, float *d_out, int64_t ld) {
-  return dense_device(m, d_feats, T, scale, layout, d_out, ld);
+khg_status dense_block(khg_model *m, const float *d_feats, int64_t T, float scale, int layout, float *d_out, int64_t ld,
+                       const TileSubset *subset, bool *subset_used) {
+  return dense_device(m, d_feats, T, scale, layout, d_out, ld, subset, subset_used);
 }
 khg_status sync_and_check(khg_model *m) { return sync_check(m); }
 }  // namespace khg

@@ -121,6 +121,7 @@ struct TcPack {
   int Pv = 0;
   std::vector<int32_t> v_off;    // Pv+1 Gaussian offsets of the virtual pdfs
   int32_t *d_vfirst = nullptr;   // device, P+1: first virtual pdf of every pdf
+  std::vector<int32_t> h_vfirst; // host copy
   // Gaussian-stationary kernel (khg_loglikes_gs.cu): the split feature operand A' of the current block
   // of frames, a_rows x KPB16 fp16, and its TMA map (box 64 columns x 128 rows)
   Buf a_scr;
@@ -201,6 +202,7 @@ struct khg_model {
   khg::Buf w_tid, w_tid2pdf, w_trans;                  // tid path
   khg::Buf w_sub, w_full;                              // pdf-subset gather
   khg::Buf w_al_graph, w_al_block, w_al_bp, w_al_cost, w_al_ali, w_al_path;  // khg_align_batch (khg_align.cu)
+  khg::Buf w_al_tiles;                                                       // ... tile subset lists of the dense kernel
   khg::Buf w_al_xlist, w_al_xll;                                             // ... its exact host pass: flagged list, likelihood rows
   khg::Buf pin_feats[2], pin_ids[2], pin_wts[2];       // pinned staging for estep(HOST)
   khg::Buf w_efeats[2], w_eids[2], w_ewts[2];
@@ -219,12 +221,21 @@ namespace khg {
 khg_status tc_pack_build(khg_model *m);
 void tc_pack_free(khg_model *m);
 bool tc_supported(const khg_model *m);
+// Optional restriction of the dense kernel to the model tiles somebody will read (device arrays): frame tiles 2q and
+// 2q + 1 compute the tiles tiles[off[q] .. off[q + 1]) only; rows of pdfs in other tiles are left untouched.
+struct TileSubset {
+  const int32_t *off = nullptr;
+  const int32_t *tiles = nullptr;
+};
+// model tiles [*ja, *jb] that hold Gaussians of pdf p (host tables of the pack), and the number of model tiles
+void tc_pdf_tile_range(const khg_model *m, int p, int *ja, int *jb);
+int tc_num_tiles(const khg_model *m);
 // out is pdf-major: out[p*ld + t]
 // *simt_gate (out): non-NULL when the caller must also launch the fp32 SIMT kernel gated on
 // that device word (fp16-only shapes whose features may be out of range).
 khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale,
                        float *d_out, int64_t ld_out, int precision, const unsigned **simt_gate,
-                       float *gate_limit);
+                       float *gate_limit, const TileSubset *subset = nullptr);
 // khg_stats_tc.cu: posteriors + statistics of bucketed frames on the tensor cores (lazy pack; launch fills the pack fields of `a`)
 khg_status stats_tc_build(khg_model *m);
 void stats_tc_free(khg_model *m);
@@ -240,7 +251,9 @@ khg_status align_exact_host(const khg_graph_batch *gb, int32_t utt, const float 
                             float *cost, std::vector<int32_t> *path);
 // khg_b200.cu: the dense all-pdf block of device-resident frames (kernel choice of the model),
 // and the synchronising read of the latched device error flag
-khg_status dense_block(khg_model *m, const float *d_feats, int64_t T, float scale, int layout, float *d_out, int64_t ld);
+// (*subset_used, if given, tells whether the tile subset was honoured; when it was not, everything was computed)
+khg_status dense_block(khg_model *m, const float *d_feats, int64_t T, float scale, int layout, float *d_out, int64_t ld,
+                       const TileSubset *subset = nullptr, bool *subset_used = nullptr);
 khg_status sync_and_check(khg_model *m);
 khg_status finish_model_from_device(khg_model *nm, int32_t *num_bad);
 }  // namespace khg

@@ -152,6 +152,10 @@ struct TcArgs {
   const uint32_t *runs;      // per run of equal-length segments: length | count << 8
   const uint32_t *seg;       // per segment: column | pdf << 8; per (tile, group) in run order, + 2 sentinels
   int n_tiles, n_splits, tiles_per_split;
+  // optional tile subset (the batched aligner: only the model tiles that hold a pdf of the frames' utterances): frame
+  // tiles 2q and 2q + 1 run the tiles sub_tiles[sub_off[q] .. sub_off[q + 1]) instead of all of them (n_splits == 1)
+  const int32_t *sub_off;
+  const int32_t *sub_tiles;
   int64_t n_items;
   float scale;
   float *out;              // pdf-major, out[p*ld + t]
@@ -253,8 +257,13 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
       for (int64_t k = k_first; k < k_end; k += k_stride) {
         const int64_t item = item_of(k);
         const int split = (int)(item % a.n_splits);
-        const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
-        for (int j = j0; j < j1; ++j) {
+        int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
+        if (a.sub_off) {
+          j0 = __shfl_sync(0xffffffffu, __ldg(a.sub_off + (item >> 1)), 0);
+          j1 = __shfl_sync(0xffffffffu, __ldg(a.sub_off + (item >> 1) + 1), 0);
+        }
+        for (int jj = j0; jj < j1; ++jj) {
+          const int j = a.sub_off ? __shfl_sync(0xffffffffu, __ldg(a.sub_tiles + jj), 0) : jj;
           const int g0 = __shfl_sync(0xffffffffu, __ldg(a.tile_g0 + j), 0);
           for (int c = 0; c < a.tab.n; ++c) {
             mbar_wait(b_empty(st), ph);
@@ -301,7 +310,11 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
       for (int64_t k = k_first; k < k_end; k += k_stride, ++a_it) {
         const int64_t item = item_of(k);
         const int split = (int)(item % a.n_splits);
-        const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
+        int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
+        if (a.sub_off) {  // (only the number of tiles matters here)
+          j0 = __shfl_sync(0xffffffffu, __ldg(a.sub_off + (item >> 1)), 0);
+          j1 = __shfl_sync(0xffffffffu, __ldg(a.sub_off + (item >> 1) + 1), 0);
+        }
         const uint32_t asl = a_it & a_two, aph = (a_two ? a_it >> 1 : a_it) & 1;
         const uint32_t a_hi0 = a_hi_base + asl * a_slot_desc, a_lo0 = a_lo_base + asl * a_slot_desc;
         mbar_wait(a_full(asl), aph);
@@ -431,7 +444,11 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
     for (int64_t k = k_first; k < k_end; k += k_stride) {
       const int64_t item = item_of(k);
       const int split = (int)(item % a.n_splits);
-      const int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
+      int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
+      if (a.sub_off) {
+        j0 = __ldg(a.sub_off + (item >> 1));
+        j1 = __ldg(a.sub_off + (item >> 1) + 1);
+      }
       const int64_t t = (item / a.n_splits) * kTileM + row;
       const bool valid = t < a.T;
       // rows beyond T store into a scratch word (ld_bytes = 0): no predicate in the hot loop
@@ -458,10 +475,10 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
       e.nan_acc = 0.f;
       e.ld_bytes = ld_bytes;
       e.out_t = out_t;
-      const int2 *hdr = a.epi_hdr + (size_t)kEpiGroups * j0 + eg;
-      for (int j = j0; j < j1; ++j, ++acc_it, hdr += kEpiGroups) {
+      for (int jj = j0; jj < j1; ++jj, ++acc_it) {
         const int buf = acc_it & 1;
-        const int2 h = __ldg(hdr);
+        const int j = a.sub_off ? __ldg(a.sub_tiles + jj) : jj;
+        const int2 h = __ldg(a.epi_hdr + (size_t)kEpiGroups * j + eg);
         const uint32_t *rp = a.runs + (h.y & 0xffffff);
         int nr = (int)((uint32_t)h.y >> 24);
         e.sp = a.seg + h.x;
@@ -693,6 +710,7 @@ khg_status tc_pack_build(khg_model *m) {
   }
   t.Pv = (int)t.v_off.size() - 1;
   vfirst[m->P] = t.Pv;
+  t.h_vfirst = vfirst;
   const int P = t.Pv;                         // from here on "pdf" means virtual pdf
   const std::vector<int32_t> &off = t.v_off;
   if (t.Pv != m->P) {
@@ -804,9 +822,17 @@ khg_status tc_pack_build(khg_model *m) {
   return KHG_OK;
 }
 
+void tc_pdf_tile_range(const khg_model *m, int p, int *ja, int *jb) {
+  const TcPack &t = m->tc;
+  const int v0 = t.h_vfirst[p], v1 = t.h_vfirst[p + 1] - 1;  // virtual pdfs of p; tile j owns virtual pdfs [h_tile_p0[j], h_tile_p0[j + 1])
+  *ja = (int)(std::upper_bound(t.h_tile_p0.begin(), t.h_tile_p0.end(), v0) - t.h_tile_p0.begin()) - 1;
+  *jb = (int)(std::upper_bound(t.h_tile_p0.begin(), t.h_tile_p0.end(), v1) - t.h_tile_p0.begin()) - 1;
+}
+int tc_num_tiles(const khg_model *m) { return m->tc.n_tiles; }
+
 template <bool F16>
 static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t ld_out,
-                            const unsigned *gate, int gate_run_if_above) {
+                            const unsigned *gate, int gate_run_if_above, const TileSubset *subset = nullptr) {
   TcPack &t = m->tc;
   TcArgs a;
   a.feats = d_feats;
@@ -847,6 +873,9 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   a.tiles_per_split = (int)((t.n_tiles + splits - 1) / splits);
   a.n_splits = (t.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
   a.n_items = n_m * a.n_splits;
+  const bool sub = subset && subset->off && a.n_splits == 1;
+  a.sub_off = sub ? subset->off : nullptr;
+  a.sub_tiles = sub ? subset->tiles : nullptr;
   a.scale = scale;
   a.out = d_out;
   a.ld = ld_out;
@@ -905,7 +934,7 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
 // call, the features fit; tf32 split otherwise), 1 = force the tf32 split, 2 = force fp16,
 // 3 = force fp16 in the Gaussian-stationary form.
 khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t ld_out,
-                       int precision, const unsigned **simt_gate, float *gate_limit) {
+                       int precision, const unsigned **simt_gate, float *gate_limit, const TileSubset *subset) {
   TcPack &t = m->tc;
   *simt_gate = nullptr;
   *gate_limit = kF16FeatLimit;
@@ -925,7 +954,7 @@ khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scal
     set_error("the tf32-split tensor-core path does not fit this model (2*dim+2 > 160)");
     return KHG_ERR_UNSUPPORTED;
   }
-  if (precision == 1 || !t.f16_ready) return tc_launch<false>(m, d_feats, T, scale, d_out, ld_out, nullptr, 0);
+  if (precision == 1 || !t.f16_ready) return tc_launch<false>(m, d_feats, T, scale, d_out, ld_out, nullptr, 0, subset);
   if (precision == 3) {  // the Gaussian-stationary form of the fp16 split (khg_loglikes_gs.cu), forced
     if (!gs_supported(m)) {
       set_error("the Gaussian-stationary fp16 kernel does not fit this model (fp16 range, or 2*dim+2 > 128)");
@@ -933,7 +962,7 @@ khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scal
     }
     return gs_loglikes(m, d_feats, T, scale, d_out, ld_out);
   }
-  if (precision == 2) return tc_launch<true>(m, d_feats, T, scale, d_out, ld_out, nullptr, 0);
+  if (precision == 2) return tc_launch<true>(m, d_feats, T, scale, d_out, ld_out, nullptr, 0, subset);
   // automatic: one pass over the features finds max |x * 2^-k|; both kernels are launched and
   // exactly one of them runs, chosen on the device (no host round trip, stays asynchronous)
   KHG_CUDA_TRY(cudaMemsetAsync(t.gate, 0, sizeof(unsigned), m->stream));
@@ -941,8 +970,8 @@ khg_status tc_loglikes(khg_model *m, const float *d_feats, int64_t T, float scal
   feat_absmax_kernel<<<(unsigned)std::min<int64_t>(4 * m->sm_count, (n + 255) / 256), 256, 0, m->stream>>>(
       d_feats, n, m->dim, t.ascale, t.gate);
   ++g_launch_count;
-  KHG_TRY(tc_launch<true>(m, d_feats, T, scale, d_out, ld_out, t.gate, 0));
-  if (t.tf32_ready) return tc_launch<false>(m, d_feats, T, scale, d_out, ld_out, t.gate, 1);
+  KHG_TRY(tc_launch<true>(m, d_feats, T, scale, d_out, ld_out, t.gate, 0, subset));
+  if (t.tf32_ready) return tc_launch<false>(m, d_feats, T, scale, d_out, ld_out, t.gate, 1, subset);
   *simt_gate = t.gate;  // no tf32 operands for this shape: the caller launches the gated SIMT kernel
   return KHG_OK;
 }

@@ -321,3 +321,42 @@ def test_script_gmm_align_compiled_contract():
     rc = khg.gmm_align_compiled_batch(am, t2p, ["a", "b"], tgs[:2], feats[:2], careful)
     plain = khg.gmm_align_compiled_batch(am, t2p, ["a", "b"], tgs[:2], feats[:2], khg.AlignConfig())
     assert rc["alignment"] == plain["alignment"] and rc["num_done"] == 2
+
+
+def test_align_batch_computes_only_the_tiles_the_graphs_need(monkeypatch):
+    """A batch large enough for the dense kernel's tile-subset mode (>= 2 frame tiles per SM) on a model of many
+    240-Gaussian tiles, every utterance touching a few of them: the likelihood block is computed only where some graph
+    of the frames' utterances has a pdf (khg_align_last_tile_fraction < 1), the results equal the full computation's
+    bit for bit, and a sample of utterances equals the oracle on the full likelihood block."""
+    from kaldi_hmm_gmm_b200 import _cabi as A
+
+    rng = np.random.default_rng(41)
+    P, D, G = 3000, 20, 15000
+    model, means, vars_ = ko.make_synthetic_model(D, P, G)
+    graphs, feats, n_tids = [], [], 1
+    for _ in range(190):
+        phones = [int(x) for x in rng.integers(0, P // 3, int(rng.integers(18, 30)))]
+        g, nt = ao.make_training_graph(rng, phones, alt_prob=0.2)
+        graphs.append(g)
+        n_tids = max(n_tids, nt)
+    t2p = ao.make_tid2pdf(n_tids, P)
+    for g in graphs:
+        f, _ = ao.sample_utterance(rng, g, t2p, model, means, vars_, noise=1.0)
+        feats.append(f)
+    assert sum(f.shape[0] for f in feats) >= 2 * 148 * 128
+    dm = _device_model(model)
+    out, ll, gb, pdf_ids = _run(dm, graphs, feats, t2p, 1.0, 10.0, 40.0, device_feats=True)
+    frac = A.lib().khg_align_last_tile_fraction()
+    assert 0.0 < frac < 0.8, frac
+    monkeypatch.setenv("KHG_ALIGN_TILE_SUBSET", "0")
+    out_full, _, _, pdf_full = _run(dm, graphs, feats, t2p, 1.0, 10.0, 40.0, device_feats=True)
+    assert A.lib().khg_align_last_tile_fraction() == 1.0
+    assert np.array_equal(out["alignment"], out_full["alignment"]) and np.array_equal(out["status"], out_full["status"])
+    assert np.array_equal(out["path_arcs"], out_full["path_arcs"]) and np.array_equal(pdf_ids, pdf_full)
+    np.testing.assert_array_equal(out["like"], out_full["like"])
+    fo = gb.frame_offsets
+    for u in range(0, len(graphs), 12):
+        ref = ao.align_utterance(graphs[u], np.ascontiguousarray(ll[:, fo[u]:fo[u + 1]]), t2p, 1.0, beam=10.0, retry_beam=40.0, tight=_tight())
+        assert out["status"][u] == ref["status"]
+        if ref["status"] != 2:
+            assert out["alignment"][fo[u]:fo[u + 1]].tolist() == ref["alignment"], u
