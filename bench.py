@@ -452,6 +452,7 @@ def align_workload(torch, dev, local, peaks, tf32_peak, rank, world, n_utts=2000
     hf.copy_(f)
     t_host = wall(hf.numpy())
     exact_utts = int(_cabi.lib().khg_align_last_exact_count())
+    tile_frac = float(_cabi.lib().khg_align_last_tile_fraction())
     correct = float((res["out"]["alignment"] == tids).mean())
     status = np.bincount(res["out"]["status"], minlength=3).tolist()
     out = {}
@@ -459,8 +460,10 @@ def align_workload(torch, dev, local, peaks, tf32_peak, rank, world, n_utts=2000
     out[key] = {"value": T_total / t_dev, "unit": "frames/s", "ms_per_call": t_dev * 1e3, "utterances": n_utts, "frames": T_total,
                 "e2e_host_feats": {"value": T_total / t_host, "unit": "frames/s", "h2d_bytes_per_call": T_total * 4 * D,
                                    "d2h_bytes_per_call": T_total * 4 + n_utts * 8},
-                "frames_equal_to_generating_path": correct, "exact_host_pass_utterances_rank0": exact_utts, "status_counts_rank0": status, "beam": [10.0, 40.0], "clocks": ck,
-                "what": "khg_align_batch: all-pdf likelihood block (K1) + device Viterbi (+ exact host FasterDecoder re-run of "
+                "frames_equal_to_generating_path": correct, "exact_host_pass_utterances_rank0": exact_utts,
+                "dense_tile_units_computed_rank0": tile_frac, "status_counts_rank0": status, "beam": [10.0, 40.0], "clocks": ck,
+                "what": "khg_align_batch: likelihood block (K1, only the 240-Gaussian model tiles that hold a pdf of the graphs of the "
+                        "frames' utterances: dense_tile_units_computed) + device Viterbi (+ exact host FasterDecoder re-run of "
                         "flagged utterances); wall clock, max over ranks, utterances sharded with no exchange"}
     if world == 1:
         nd = min(T, 148 * 128 * 8)

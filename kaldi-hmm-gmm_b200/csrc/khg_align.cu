@@ -577,9 +577,12 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     }
     return KHG_OK;
   };
-  auto run_dense = [&](int u0, int u1, const float *d_f, bool subset) -> khg_status {
+  std::vector<std::vector<int32_t>> list_keep;  // host copies of the uploaded lists (alive until the call returns)
+  size_t list_used = 0;                          // int32 words of w_al_tiles handed out so far
+  auto run_dense = [&](int u0, int u1, const float *d_f, bool subset, int64_t col = 0) -> khg_status {
     const int64_t nfr = gb->frame_offsets[u1] - gb->frame_offsets[u0];
     if (nfr <= 0) return KHG_OK;
+    float *d_dst = d_block + col;
     TileSubset sub;
     const int n_tiles = m->tc.ready ? tc_num_tiles(m) : 0;
     const int64_t n_pairs = (nfr + 255) / 256;
@@ -611,28 +614,39 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
           for (uint64_t x = acc[w2]; x; x &= x - 1) tiles.push_back(w2 * 64 + __builtin_ctzll(x));
         off[q + 1] = (int32_t)tiles.size();
       }
-      KHG_TRY(m->w_al_tiles.reserve(4 * (off.size() + std::max<size_t>(tiles.size(), 1))));
-      int32_t *d_off = m->w_al_tiles.as<int32_t>(), *d_tiles = d_off + off.size();
+      // (w_al_tiles was sized for the whole call up front: launches of one call must not move it)
+      if (4 * (list_used + off.size() + tiles.size() + 2) > m->w_al_tiles.cap) {
+        units_all += n_pairs * n_tiles;
+        units_done += n_pairs * n_tiles;
+        return dense_block(m, d_f, nfr, acoustic_scale, KHG_PDF_MAJOR, d_dst, ld);
+      }
+      int32_t *d_off = m->w_al_tiles.as<int32_t>() + list_used, *d_tiles = d_off + off.size();
+      list_used += off.size() + tiles.size();
       KHG_CUDA_TRY(cudaMemcpyAsync(d_off, off.data(), 4 * off.size(), cudaMemcpyHostToDevice, st));
       KHG_CUDA_TRY(cudaMemcpyAsync(d_tiles, tiles.data(), 4 * tiles.size(), cudaMemcpyHostToDevice, st));
-      KHG_CUDA_TRY(cudaStreamSynchronize(st));  // (the host vectors go out of scope)
+      const int64_t n_list = (int64_t)tiles.size();
+      list_keep.push_back(std::move(off));
+      list_keep.push_back(std::move(tiles));
       sub.off = d_off;
       sub.tiles = d_tiles;
       bool used = false;
-      KHG_TRY(dense_block(m, d_f, nfr, acoustic_scale, KHG_PDF_MAJOR, d_block, ld, &sub, &used));
+      KHG_TRY(dense_block(m, d_f, nfr, acoustic_scale, KHG_PDF_MAJOR, d_dst, ld, &sub, &used));
       units_all += n_pairs * n_tiles;
-      units_done += used ? (int64_t)tiles.size() : n_pairs * n_tiles;
+      units_done += used ? n_list : n_pairs * n_tiles;
       return KHG_OK;
     }
     units_all += n_pairs * std::max(1, n_tiles);
     units_done += n_pairs * std::max(1, n_tiles);
-    return dense_block(m, d_f, nfr, acoustic_scale, KHG_PDF_MAJOR, d_block, ld);
+    return dense_block(m, d_f, nfr, acoustic_scale, KHG_PDF_MAJOR, d_dst, ld);
   };
   auto launch_dense = [&](int u0, int u1, bool subset) -> khg_status {
+    list_used = 0;  // (the previous chunk's kernel has finished: the host synchronised on its search)
     const float *d_f = nullptr;
     KHG_TRY(stage_feats(u0, u1, &d_f));
     return run_dense(u0, u1, d_f, subset);
   };
+  if (want_subset && m->tc.ready)  // worst case: every pair of frame tiles lists every model tile (+ the offsets, per launch)
+    KHG_TRY(m->w_al_tiles.reserve(4 * ((size_t)((chunk_frames_max + 255) / 256 + 16) * (size_t)(tc_num_tiles(m) + 1) + 64)));
   // with the subset the kernel of the first chunk needs the graphs' pdf lists (first host pass below); without it, it is
   // launched right away and runs under the whole host preparation
   const float *d_f0 = nullptr;
@@ -651,7 +665,7 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   std::vector<int32_t> eps_deg((size_t)S_all, 0);
   const int n_workers = 16;
   std::vector<std::vector<int32_t>> stamp(n_workers, std::vector<int32_t>(P, -1)), lidx(n_workers, std::vector<int32_t>(P, 0));
-  parallel_for(U, [&](int u, int w) {
+  auto first_pass = [&](int u, int w) {
     const int32_t s0 = gb->state_offsets[u], s1 = gb->state_offsets[u + 1], S = s1 - s0;
     UttDesc &d = desc[u];
     memset(&d, 0, sizeof(d));
@@ -685,16 +699,35 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
       }
     }
     d.n_pdf = (int32_t)updf[u].size();
-  });
+  };
+  if (want_subset) {
+    // the first chunk in groups of utterances: the dense kernel of a group is launched as soon as the group's pdf
+    // lists exist and runs under the host pass of the next groups (a group keeps >= 2 frame tiles per SM, what the
+    // kernel's subset mode needs)
+    const int c0 = chunk_start[0], c1 = chunk_start[1];
+    const int64_t fr0 = gb->frame_offsets[c0], frc = gb->frame_offsets[c1] - fr0;
+    const int n_groups = (int)std::max<int64_t>(1, std::min<int64_t>(4, frc / (4LL * m->sm_count * 128)));
+    int ga = c0;
+    for (int gidx = 0; gidx < n_groups; ++gidx) {
+      int gb_ = c1;
+      if (gidx + 1 < n_groups) {
+        gb_ = ga;
+        while (gb_ < c1 && gb->frame_offsets[gb_] - fr0 < frc * (gidx + 1) / n_groups) ++gb_;
+      }
+      parallel_for(gb_ - ga, [&](int i, int w) { first_pass(ga + i, w); });
+      KHG_TRY(run_dense(ga, gb_, d_f0 + (gb->frame_offsets[ga] - fr0) * D, true, gb->frame_offsets[ga] - fr0));
+      ga = gb_;
+    }
+    if (timing) cudaEventRecord(ev[1], st);
+    parallel_for(U - c1, [&](int i, int w) { first_pass(c1 + i, w); });
+  } else {
+    parallel_for(U, first_pass);
+  }
   for (int u = 0; u < U; ++u)
     if (bad[u]) {
       cudaStreamSynchronize(st);  // the first chunk's dense kernel is already running
       KHG_REQUIRE(false, "graph of utterance " + std::to_string(u) + ": state / label / offset out of range");
     }
-  if (want_subset) {
-    KHG_TRY(run_dense(chunk_start[0], chunk_start[1], d_f0, true));
-    if (timing) cudaEventRecord(ev[1], st);
-  }
   // prefix sums: in-arc CSR over all states; epsilon-destination lists
   for (size_t s = 0; s < (size_t)S_all; ++s) in_off[s + 1] += in_off[s];
   std::vector<int32_t> ed_state, ed_off(1, 0), utt_pdfs;
