@@ -31,13 +31,18 @@
 // competing predecessors / final states (the reference then keeps whichever its list order met first), or
 // a negative epsilon weight — is FLAGGED and re-aligned by the exact host restatement of the reference
 // (khg_align_exact.cu) on the same likelihood block.  Everything else is provably the reference's result.
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 
@@ -458,21 +463,90 @@ __global__ void gather_ll_kernel(AlignDev g, const int2 *__restrict__ list, cons
   }
 }
 
+// A small persistent pool for the host passes over the graphs (a call makes ~10 of them; creating 16 threads each
+// time costs more than the passes themselves at C5 sizes).  One job at a time (callers are serialised by a mutex).
+class HostPool {
+ public:
+  static HostPool &get() {
+    static HostPool p;
+    return p;
+  }
+  int workers() const { return (int)th_.size() + 1; }
+  // runs job(w) for w = 0 .. n_workers-1 (the caller is worker 0) and returns when all are done
+  void run(int n_workers, const std::function<void(int)> &job) {
+    std::lock_guard<std::mutex> one(call_mu_);
+    n_workers = std::max(1, std::min(n_workers, workers()));
+    if (getpid() != pid_) n_workers = 1;  // (a forked child has no worker threads: the caller does everything)
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = &job;
+      active_ = n_workers - 1;
+      pending_ = n_workers - 1;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    job(0);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  HostPool() {
+    const int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    for (int w = 1; w < nt; ++w) th_.emplace_back([this, w] { loop(w); });
+    pid_ = getpid();
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    for (auto &t : th_) t.join();
+  }
+  void loop(int w) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int)> *job = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (stop_) return;
+        if (w <= active_) job = job_;
+      }
+      if (job) {
+        (*job)(w);
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_, call_mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)> *job_ = nullptr;
+  int active_ = 0, pending_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+  pid_t pid_ = 0;
+};
+
 template <class F>
 static void parallel_for(int n, F f, int min_parallel = 64) {
-  int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
-  nt = std::min(nt, std::max(1, n));
+  int nt = std::min(HostPool::get().workers(), std::max(1, n));
   if (n < min_parallel) nt = 1;
   if (nt == 1) {
     for (int i = 0; i < n; ++i) f(i, 0);
     return;
   }
-  std::vector<std::thread> th;
-  for (int w = 0; w < nt; ++w)
-    th.emplace_back([=] {
-      for (int i = w; i < n; i += nt) f(i, w);
-    });
-  for (auto &t : th) t.join();
+  // (items are handed out dynamically: in a forked child the caller alone runs, and takes them all)
+  std::atomic<int> next{0};
+  HostPool::get().run(nt, [&](int w) {
+    for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) f(i, w);
+  });
 }
 
 }  // namespace khg
@@ -657,6 +731,8 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     if (timing) cudaEventRecord(ev[1], st);
   }
 
+  double t_mark[6] = {0, 0, 0, 0, 0, 0};
+  t_mark[0] = now();
   // ---------------- host: transpose every graph (incoming emitting arcs per state, incoming
   // epsilon arcs per state), local pdf lists
   std::vector<UttDesc> desc(U);
@@ -723,6 +799,7 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   } else {
     parallel_for(U, first_pass);
   }
+  t_mark[1] = now();
   for (int u = 0; u < U; ++u)
     if (bad[u]) {
       cudaStreamSynchronize(st);  // the first chunk's dense kernel is already running
@@ -748,6 +825,7 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     S_max = std::max(S_max, d.S);
     n_pdf_max = std::max(n_pdf_max, d.n_pdf);
   }
+  t_mark[2] = now();
   const int64_t n_in = in_off[S_all];
   std::vector<int4> in_arcs((size_t)n_in), e_arcs((size_t)eps_total);
   parallel_for(U, [&](int u, int) {
@@ -770,6 +848,7 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   });
 
   const double t_prep = now();
+  t_mark[3] = t_prep;
   // ---------------- device copy of the graphs
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   size_t o_desc = 0, o_inoff = o_desc + al(sizeof(UttDesc) * U), o_in = o_inoff + al(4 * ((size_t)S_all + 1)),
@@ -807,6 +886,7 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   KHG_CUDA_TRY(up(o_pdf, utt_pdfs.data(), 4 * utt_pdfs.size()));
   KHG_CUDA_TRY(up(o_t2p, tid2pdf, 4 * (size_t)n_tids));
   KHG_CUDA_TRY(up(o_ord, order.data(), 4 * (size_t)U));
+  t_mark[4] = now();
   AlignDev g;
   g.utts = reinterpret_cast<const UttDesc *>(gbase + o_desc);
   g.in_off = reinterpret_cast<const int32_t *>(gbase + o_inoff);
@@ -965,6 +1045,8 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
             "host prep %.2f ms, dense %.2f ms (%.1f %% of the tile units), search %.2f ms, exact host pass %.2f ms (%d utterances), total %.2f ms\n", U,
             (long long)T_all, S_all, A_all, S_max, n_pdf_max, FC, NT, smem, chunk_start.size() - 1, t_prep - t_begin, ms_dense,
             units_all > 0 ? 100.0 * units_done / units_all : 100.0, ms_search, ms_exact, n_redo_total, now() - t_begin);
+    fprintf(stderr, "khg_align_batch host: setup %.2f | pass 1 (+ dense launches) %.2f | serial %.2f | pass 2 %.2f | upload %.2f ms\n",
+            t_mark[0] - t_begin, t_mark[1] - t_mark[0], t_mark[2] - t_mark[1], t_mark[3] - t_mark[2], t_mark[4] - t_mark[3]);
     for (auto &e : ev) cudaEventDestroy(e);
   }
   g_align_exact_utts = n_redo_total;
