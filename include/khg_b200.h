@@ -85,7 +85,7 @@ typedef struct khg_model khg_model; /* device-resident packed AmDiagGmm      */
 typedef struct khg_stats khg_stats; /* device-resident packed AccumAmDiagGmm */
 
 const char *khg_last_error(void);
-int32_t khg_abi_version(void); /* 4 (3 + khg_model_stats_kernel, khg_align_last_tile_fraction) */
+int32_t khg_abi_version(void); /* 4 (3 + khg_model_stats_kernel, khg_align_last_tile_fraction, khg_align_last_prep_cached) */
 
 khg_status khg_device_count(int32_t *count);
 khg_status khg_set_device(int32_t device);
@@ -354,6 +354,11 @@ int64_t khg_align_last_exact_count(void);
  * utterances (the batched form of the reference's lazy per-pdf evaluation, csrc/decodable-am-diag-gmm.cc:29-71);
  * 1.0 when everything was computed (small batches, KHG_ALIGN_TILE_SUBSET=0, kernels without that mode). */
 double khg_align_last_tile_fraction(void);
+/* 1 when the most recent khg_align_batch call reused the graph preparation (transposed graphs, their device copy) of
+ * the previous call on the same model: graphs, frame offsets and tid2pdf are compared by a 128-bit content hash — the
+ * realignment passes of an EM recipe align the same graphs every time (egs/yesno/train.py:165-206).
+ * KHG_ALIGN_PREP_CACHE=0 (environment) disables the reuse. */
+int32_t khg_align_last_prep_cached(void);
 
 /* The reference's FasterDecoder + AlignUtteranceWrapper on the HOST for ONE utterance of a graph batch,
  * consuming a block of log-likelihoods computed elsewhere (the GPU): csrc/faster-decoder.cc:36-425 with

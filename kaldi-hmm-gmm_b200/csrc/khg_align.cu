@@ -86,6 +86,7 @@ struct UttOut {
   int32_t pad2[3];
 };
 
+int g_align_prep_hit = 0;                  // the last call reused the previous call's graph preparation
 double g_align_tile_fraction = 1.0;        // (tile, frame tile) units the last call's dense kernel computed / all of them
 int64_t g_align_exact_utts = 0;           // utterances of the last khg_align_batch call that took the exact host pass
 constexpr int kAlignMinActive = 20;       // faster-decoder.h:42
@@ -549,6 +550,56 @@ static void parallel_for(int n, F f, int min_parallel = 64) {
   });
 }
 
+
+// What the host preparation of khg_align_batch produces and later phases need, kept on the model between calls: the
+// realignment passes of an EM recipe align the SAME graphs again and again (egs/yesno/train.py:165-206), and the
+// preparation — transposing 2000 graphs — is the longest host phase of a call.  A call whose graphs, frame offsets,
+// tid2pdf and chunking hash to the key of the previous call reuses the device copy of the graphs (w_al_graph) and
+// these host tables.  KHG_ALIGN_PREP_CACHE=0 disables it.
+struct AlignPrepCache {
+  bool valid = false;
+  uint64_t key[2] = {0, 0};
+  std::vector<UttDesc> desc;
+  std::vector<int32_t> neg_eps, arc_lp;
+  std::vector<std::vector<int32_t>> updf;
+  int S_max = 1, n_pdf_max = 1;
+  size_t n_in = 0, n_eds = 0, n_edo = 0, eps_total = 0, n_updf = 0;
+};
+void align_cache_free(khg_model *m) {
+  delete static_cast<AlignPrepCache *>(m->al_cache);
+  m->al_cache = nullptr;
+}
+// 2 x 64-bit content hash of a byte range (multiply-xorshift over 8-byte words, blocks hashed by the pool's workers)
+static void hash_bytes(const void *ptr, size_t bytes, uint64_t (&key)[2]) {
+  if (!ptr || !bytes) return;
+  const size_t kBlock = 1 << 16, nb = (bytes + kBlock - 1) / kBlock;
+  std::vector<uint64_t> h0(nb), h1(nb);
+  parallel_for((int)nb, [&](int b, int) {
+    const unsigned char *q = static_cast<const unsigned char *>(ptr) + (size_t)b * kBlock;
+    const size_t n = std::min(kBlock, bytes - (size_t)b * kBlock);
+    uint64_t a = 0x9E3779B97F4A7C15ull ^ (uint64_t)b, c = 0xC2B2AE3D27D4EB4Full + (uint64_t)b;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+      uint64_t w;
+      memcpy(&w, q + i, 8);
+      a = (a ^ w) * 0xFF51AFD7ED558CCDull;
+      a ^= a >> 32;
+      c = (c + w) * 0x9FB21C651E98DF25ull;
+      c ^= c >> 29;
+    }
+    uint64_t w = 0;
+    if (i < n) memcpy(&w, q + i, n - i);
+    a = (a ^ w ^ (uint64_t)n) * 0xFF51AFD7ED558CCDull;
+    c = (c + w + (uint64_t)n) * 0x9FB21C651E98DF25ull;
+    h0[b] = a ^ (a >> 31);
+    h1[b] = c ^ (c >> 33);
+  }, 8);
+  for (size_t b = 0; b < nb; ++b) {
+    key[0] = (key[0] ^ h0[b]) * 0xD6E8FEB86659FD93ull + 0x2545F4914F6CDD1Dull;
+    key[1] = (key[1] + h1[b]) * 0xA0761D6478BD642Full ^ (key[1] >> 27);
+  }
+}
+
 }  // namespace khg
 
 using namespace khg;
@@ -639,7 +690,31 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   // (KHG_ALIGN_TILE_SUBSET=0: everything).  The search reads the rows of its utterance's pdfs only.
   const bool want_subset = !(getenv("KHG_ALIGN_TILE_SUBSET") && atoi(getenv("KHG_ALIGN_TILE_SUBSET")) == 0) && m->tc.ready &&
                            m->kernel != KHG_KERNEL_SIMT;
-  std::vector<std::vector<int32_t>> updf(U);  // distinct pdfs of every graph (filled by the first host pass)
+  // ---- preparation cache (see AlignPrepCache): key over everything the preparation reads
+  if (!m->al_cache) m->al_cache = new AlignPrepCache();
+  AlignPrepCache &pc = *static_cast<AlignPrepCache *>(m->al_cache);
+  bool prep_hit = false;
+  {
+    uint64_t key[2] = {0x1234567ull + (uint64_t)U * 1315423911ull + (uint64_t)P, 0x89abcdefull + (uint64_t)n_tids + ((uint64_t)want_subset << 40)};
+    hash_bytes(gb->frame_offsets, 8 * ((size_t)U + 1), key);
+    hash_bytes(gb->state_offsets, 4 * ((size_t)U + 1), key);
+    hash_bytes(gb->arc_offsets, 4 * ((size_t)S_all + 1), key);
+    hash_bytes(gb->arc_ilabel, 4 * (size_t)A_all, key);
+    hash_bytes(gb->arc_nextstate, 4 * (size_t)A_all, key);
+    hash_bytes(gb->arc_weight, 4 * (size_t)A_all, key);
+    hash_bytes(gb->start_state, 4 * (size_t)U, key);
+    hash_bytes(gb->final_cost, 4 * (size_t)S_all, key);
+    hash_bytes(tid2pdf, 4 * (size_t)n_tids, key);
+    hash_bytes(chunk_start.data(), sizeof(int) * chunk_start.size(), key);
+    const char *e = getenv("KHG_ALIGN_PREP_CACHE");
+    prep_hit = !(e && atoi(e) == 0) && pc.valid && pc.key[0] == key[0] && pc.key[1] == key[1] && (int)pc.desc.size() == U;
+    pc.valid = false;  // (set again once this call's tables and device copy are complete)
+    pc.key[0] = key[0];
+    pc.key[1] = key[1];
+  }
+  g_align_prep_hit = prep_hit ? 1 : 0;
+  std::vector<std::vector<int32_t>> &updf = pc.updf;  // distinct pdfs of every graph (filled by the first host pass)
+  if (!prep_hit) updf.assign(U, std::vector<int32_t>());
   int64_t units_done = 0, units_all = 0;
   auto stage_feats = [&](int u0, int u1, const float **d_f) -> khg_status {
     const int64_t f0 = gb->frame_offsets[u0] - gb->frame_offsets[0], nfr = gb->frame_offsets[u1] - gb->frame_offsets[u0];
@@ -735,10 +810,21 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   t_mark[0] = now();
   // ---------------- host: transpose every graph (incoming emitting arcs per state, incoming
   // epsilon arcs per state), local pdf lists
-  std::vector<UttDesc> desc(U);
-  std::vector<int32_t> n_emit(U, 0), n_eps(U, 0), bad(U, 0), neg_eps(U, 0);
-  std::vector<int32_t> in_off((size_t)S_all + 1, 0), arc_src(A_all), arc_lp(A_all);
-  std::vector<int32_t> eps_deg((size_t)S_all, 0);
+  std::vector<UttDesc> &desc = pc.desc;
+  std::vector<int32_t> &neg_eps = pc.neg_eps, &arc_lp = pc.arc_lp;
+  int &S_max = pc.S_max, &n_pdf_max = pc.n_pdf_max;
+  std::vector<int32_t> n_emit, n_eps, bad, in_off, arc_src, eps_deg;
+  if (!prep_hit) {
+    desc.assign(U, UttDesc());
+    neg_eps.assign(U, 0);
+    arc_lp.assign(A_all, 0);
+    n_emit.assign(U, 0);
+    n_eps.assign(U, 0);
+    bad.assign(U, 0);
+    in_off.assign((size_t)S_all + 1, 0);
+    arc_src.assign(A_all, 0);
+    eps_deg.assign((size_t)S_all, 0);
+  }
   const int n_workers = 16;
   std::vector<std::vector<int32_t>> stamp(n_workers, std::vector<int32_t>(P, -1)), lidx(n_workers, std::vector<int32_t>(P, 0));
   auto first_pass = [&](int u, int w) {
@@ -790,16 +876,20 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
         gb_ = ga;
         while (gb_ < c1 && gb->frame_offsets[gb_] - fr0 < frc * (gidx + 1) / n_groups) ++gb_;
       }
-      parallel_for(gb_ - ga, [&](int i, int w) { first_pass(ga + i, w); });
+      if (!prep_hit) parallel_for(gb_ - ga, [&](int i, int w) { first_pass(ga + i, w); });
       KHG_TRY(run_dense(ga, gb_, d_f0 + (gb->frame_offsets[ga] - fr0) * D, true, gb->frame_offsets[ga] - fr0));
       ga = gb_;
     }
     if (timing) cudaEventRecord(ev[1], st);
-    parallel_for(U - c1, [&](int i, int w) { first_pass(c1 + i, w); });
-  } else {
+    if (!prep_hit) parallel_for(U - c1, [&](int i, int w) { first_pass(c1 + i, w); });
+  } else if (!prep_hit) {
     parallel_for(U, first_pass);
   }
   t_mark[1] = now();
+  std::vector<int32_t> ed_state, ed_off, utt_pdfs;
+  std::vector<int4> in_arcs, e_arcs;
+  int64_t eps_total = 0, n_in = 0;
+  if (!prep_hit) {
   for (int u = 0; u < U; ++u)
     if (bad[u]) {
       cudaStreamSynchronize(st);  // the first chunk's dense kernel is already running
@@ -807,9 +897,9 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     }
   // prefix sums: in-arc CSR over all states; epsilon-destination lists
   for (size_t s = 0; s < (size_t)S_all; ++s) in_off[s + 1] += in_off[s];
-  std::vector<int32_t> ed_state, ed_off(1, 0), utt_pdfs;
-  int64_t eps_total = 0;
-  int S_max = 1, n_pdf_max = 1;
+  ed_off.assign(1, 0);
+  S_max = 1;
+  n_pdf_max = 1;
   for (int u = 0; u < U; ++u) {
     UttDesc &d = desc[u];
     d.ed0 = (int32_t)ed_state.size();
@@ -826,8 +916,9 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     n_pdf_max = std::max(n_pdf_max, d.n_pdf);
   }
   t_mark[2] = now();
-  const int64_t n_in = in_off[S_all];
-  std::vector<int4> in_arcs((size_t)n_in), e_arcs((size_t)eps_total);
+  n_in = in_off[S_all];
+  in_arcs.assign((size_t)n_in, make_int4(0, 0, 0, 0));
+  e_arcs.assign((size_t)eps_total, make_int4(0, 0, 0, 0));
   parallel_for(U, [&](int u, int) {
     const UttDesc &d = desc[u];
     const int32_t s0 = d.state0;
@@ -847,15 +938,21 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
       }
   });
 
+  pc.n_in = (size_t)n_in;
+  pc.n_eds = ed_state.size();
+  pc.n_edo = ed_off.size();
+  pc.eps_total = (size_t)eps_total;
+  pc.n_updf = utt_pdfs.size();
+  }  // !prep_hit
   const double t_prep = now();
   t_mark[3] = t_prep;
   // ---------------- device copy of the graphs
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   size_t o_desc = 0, o_inoff = o_desc + al(sizeof(UttDesc) * U), o_in = o_inoff + al(4 * ((size_t)S_all + 1)),
-         o_eds = o_in + al(16 * (size_t)n_in), o_edo = o_eds + al(4 * ed_state.size()),
-         o_ea = o_edo + al(4 * ed_off.size()), o_fin = o_ea + al(16 * (size_t)eps_total),
+         o_eds = o_in + al(16 * pc.n_in), o_edo = o_eds + al(4 * pc.n_eds),
+         o_ea = o_edo + al(4 * pc.n_edo), o_fin = o_ea + al(16 * pc.eps_total),
          o_src = o_fin + al(4 * (size_t)S_all), o_il = o_src + al(4 * (size_t)A_all), o_w = o_il + al(4 * (size_t)A_all),
-         o_pdf = o_w + al(4 * (size_t)A_all), o_t2p = o_pdf + al(4 * utt_pdfs.size()),
+         o_pdf = o_w + al(4 * (size_t)A_all), o_t2p = o_pdf + al(4 * pc.n_updf),
          o_ord = o_t2p + al(4 * (size_t)n_tids), o_out = o_ord + al(4 * (size_t)U),
          o_poff = o_out + al(sizeof(UttOut) * U), o_end = o_poff + al(8 * ((size_t)U + 1));
   KHG_TRY(m->w_al_graph.reserve(o_end));
@@ -864,6 +961,7 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     return bytes ? cudaMemcpyAsync(gbase + off, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
   };
 
+  if (!prep_hit) {
   // launch order inside each chunk: longest search first
   std::vector<int32_t> order(U);
   for (size_t c = 0; c + 1 < chunk_start.size(); ++c) {
@@ -886,6 +984,8 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   KHG_CUDA_TRY(up(o_pdf, utt_pdfs.data(), 4 * utt_pdfs.size()));
   KHG_CUDA_TRY(up(o_t2p, tid2pdf, 4 * (size_t)n_tids));
   KHG_CUDA_TRY(up(o_ord, order.data(), 4 * (size_t)U));
+  }  // !prep_hit: the device copy of an identical batch is still in w_al_graph
+  pc.valid = true;
   t_mark[4] = now();
   AlignDev g;
   g.utts = reinterpret_cast<const UttDesc *>(gbase + o_desc);
@@ -1062,3 +1162,4 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
 
 extern "C" int64_t khg_align_last_exact_count(void) { return g_align_exact_utts; }
 extern "C" double khg_align_last_tile_fraction(void) { return g_align_tile_fraction; }
+extern "C" int32_t khg_align_last_prep_cached(void) { return g_align_prep_hit; }

@@ -285,6 +285,7 @@ void khg_model_destroy(khg_model *m) {
   if (m->gsel_shadow) khg_model_destroy(m->gsel_shadow);
   tc_pack_free(m);
   stats_tc_free(m);
+  align_cache_free(m);
   cudaFree(m->d_offsets); cudaFree(m->d_weights); cudaFree(m->d_miv); cudaFree(m->d_iv);
   cudaFree(m->d_gconsts); cudaFree(m->d_packT); cudaFree(m->d_err); cudaFree(m->d_scratch_int);
   cudaFree(m->d_grp_start); cudaFree(m->d_pack8); cudaFree(m->d_gc8);

@@ -202,6 +202,7 @@ struct khg_model {
   khg::Buf w_tid, w_tid2pdf, w_trans;                  // tid path
   khg::Buf w_sub, w_full;                              // pdf-subset gather
   khg::Buf w_al_graph, w_al_block, w_al_bp, w_al_cost, w_al_ali, w_al_path;  // khg_align_batch (khg_align.cu)
+  void *al_cache = nullptr;                                                   // AlignPrepCache (khg_align.cu)
   khg::Buf w_al_tiles;                                                       // ... tile subset lists of the dense kernel
   khg::Buf w_al_xlist, w_al_xll;                                             // ... its exact host pass: flagged list, likelihood rows
   khg::Buf pin_feats[2], pin_ids[2], pin_wts[2];       // pinned staging for estep(HOST)
@@ -245,6 +246,8 @@ khg_status stats_tc_launch(khg_model *m, StatsTcArgs a, cudaStream_t st);
 bool gs_supported(const khg_model *m);
 void gs_free(khg_model *m);
 khg_status gs_loglikes(khg_model *m, const float *d_feats, int64_t T, float scale, float *d_out, int64_t ld_out);
+// khg_align.cu: frees the model's cached graph preparation
+void align_cache_free(khg_model *m);
 // khg_align_exact.cu: the reference's FasterDecoder on the host for one utterance of a graph batch
 khg_status align_exact_host(const khg_graph_batch *gb, int32_t utt, const float *ll, int64_t ld, const int32_t *row_of_tid,
                             const int32_t *row_of_arc, float beam, float retry_beam, int32_t *alignment, int32_t *status,

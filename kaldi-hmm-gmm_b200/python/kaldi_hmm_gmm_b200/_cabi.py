@@ -63,6 +63,7 @@ SYMBOLS = [
     ("khg_align_batch", _i32, [_vp, _vp, _vp, _i32, _vp, _i32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     ("khg_align_last_exact_count", _i64, []),
     ("khg_align_last_tile_fraction", C.c_double, []),
+    ("khg_align_last_prep_cached", _i32, []),
     ("khg_align_utterance_host", _i32, [_vp, _i32, _vp, _i64, _vp, _i32, _f32, _f32, _f32, _vp, C.POINTER(_i32), C.POINTER(_f32), _vp, _i32, C.POINTER(_i32)]),
     ("khg_gaussian_selection", _i32, [_vp, _i32, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, C.POINTER(C.c_double)]),
     ("khg_model_split_by_count", _i32, [_vp, _vp, _i32, _f32, _f32, _f32, _vp, _i64, C.c_uint64, C.POINTER(_vp), C.POINTER(_i32)]),

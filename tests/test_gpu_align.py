@@ -360,3 +360,43 @@ def test_align_batch_computes_only_the_tiles_the_graphs_need(monkeypatch):
         assert out["status"][u] == ref["status"]
         if ref["status"] != 2:
             assert out["alignment"][fo[u]:fo[u + 1]].tolist() == ref["alignment"], u
+
+
+def test_align_batch_reuses_the_graph_preparation_of_an_identical_batch(monkeypatch):
+    """Realignment passes align the same graphs again: the second call reuses the transposed graphs and their device copy
+    (content hash), gives the same results, and any change of the graphs or of tid2pdf is a miss."""
+    import copy
+
+    from kaldi_hmm_gmm_b200 import _cabi as A
+
+    model, graphs, feats, t2p = _batch(53, 40)
+    dm = _device_model(model)
+    out1, ll, gb, pdf1 = _run(dm, graphs, feats, t2p, 1.0, 8.0, 40.0)
+    assert A.lib().khg_align_last_prep_cached() == 0
+    _check(out1, ll, gb, graphs, t2p, 1.0, 8.0, 40.0, pdf1)
+    out2, _, _, pdf2 = _run(dm, graphs, feats, t2p, 1.0, 8.0, 40.0)
+    assert A.lib().khg_align_last_prep_cached() == 1
+    for k in ("alignment", "status", "path_arcs", "path_offsets"):
+        assert np.array_equal(out1[k], out2[k]), k
+    np.testing.assert_array_equal(out1["like"], out2["like"])
+    assert np.array_equal(pdf1, pdf2)
+    # other beams on the same graphs: still a hit, results per the oracle
+    out3, ll3, gb3, pdf3 = _run(dm, graphs, feats, t2p, 1.0, 3.0, 30.0)
+    assert A.lib().khg_align_last_prep_cached() == 1
+    _check(out3, ll3, gb3, graphs, t2p, 1.0, 3.0, 30.0, pdf3)
+    # a changed arc weight: miss, and the result follows the new graph
+    graphs2 = copy.deepcopy(graphs)
+    graphs2[3].weight = graphs2[3].weight.copy()
+    graphs2[3].weight[0] += 0.25
+    out4, ll4, gb4, pdf4 = _run(dm, graphs2, feats, t2p, 1.0, 8.0, 40.0)
+    assert A.lib().khg_align_last_prep_cached() == 0
+    _check(out4, ll4, gb4, graphs2, t2p, 1.0, 8.0, 40.0, pdf4)
+    # a changed tid2pdf: miss
+    t2p2 = t2p.copy()
+    t2p2[1:] = (t2p[1:] + 1) % model.num_pdfs
+    out5, ll5, gb5, pdf5 = _run(dm, graphs2, feats, t2p2, 1.0, 8.0, 40.0)
+    assert A.lib().khg_align_last_prep_cached() == 0
+    _check(out5, ll5, gb5, graphs2, t2p2, 1.0, 8.0, 40.0, pdf5)
+    monkeypatch.setenv("KHG_ALIGN_PREP_CACHE", "0")
+    _run(dm, graphs2, feats, t2p2, 1.0, 8.0, 40.0)
+    assert A.lib().khg_align_last_prep_cached() == 0
