@@ -178,3 +178,27 @@ def test_tc_stats_nonfinite_features_raise_like_the_reference(oracle):
     with pytest.raises(Exception):
         st.acc_stats_ali(feats, pdf)
         st.download()
+
+
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_tc_stats_random_shapes(oracle, seed):
+    """Random model shapes inside the tensor-core kernel's range (dim 1..40, ragged pdf sizes 1..32, empty pdfs, batches
+    just above the bucketing threshold, single-frame items): statistics, totals and per-frame values against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    D = int(rng.choice([1, 2, 3, 7, 8, 9, 13, 16, 20, 24, 31, 32, 33, 39, 40]))
+    P = int(rng.integers(1, 60))
+    sizes = rng.integers(1, 33, P)
+    if seed % 2 == 0:
+        sizes = np.minimum(sizes, 16)  # the 16-row instantiation
+    model, means, vars_ = _ragged_model(oracle, D, sizes, 7 + seed)
+    T = int(rng.choice([2049, 2100, 4097, 9000, 20000]))
+    feats, pdf = ko.make_synthetic_frames(model, means, vars_, T, seed=seed)
+    if P > 3:  # some pdfs get no frames, one gets exactly one
+        pdf[pdf == 1] = 0
+        pdf[pdf == 2] = 0
+        pdf[0] = 2
+    weights = None if seed % 3 else (rng.random(T) * 3).astype(np.float32)
+    got, tot, pf = _run(model, feats, pdf, weights)
+    ref = oracle.acc_stats_ali(model, feats, pdf, weights)
+    _assert_ll(pf, ref["per_frame"])
+    _assert_stats(got, ref)
