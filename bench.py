@@ -65,7 +65,7 @@ def parse():
     ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
     ap.add_argument("--frames", type=int, default=0, help="override total frames (debug)")
     ap.add_argument("--kernel", default="auto", choices=sorted(KERNELS))
-    ap.add_argument("--chunk", type=int, default=148 * 128 * 16, help="frames per dense block")
+    ap.add_argument("--chunk", type=int, default=148 * 128 * 32, help="frames per dense block (10 GB at C4; twice that measures the same, half of it 1 % less: profiles/r3l_estep_chunk_size.txt)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-workloads", action="store_true")
