@@ -53,6 +53,19 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// tcgen05.mma kind::f16 with the high words of the two shared-memory descriptors given separately (the posterior
+// operand is MN-major with a 32-byte swizzle: other stride / layout fields than the X tile's)
+__device__ __forceinline__ void stk_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kDescHi), "r"(b_hi)
+      : "memory");
+}
+constexpr uint32_t kStkPtDescHi = (uint32_t)(256 >> 4) | (1u << 14) | (6u << 29);  // SBO = 256 B (8 frames), version 1, SWIZZLE_32B
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -152,16 +165,27 @@ __device__ __forceinline__ float stk_softmax_store(uint32_t trow, int ng, float 
   }
   const float lse = fmaf(fast_log2(s), kLn2, mx);
   const float f = live ? (w * kStkPostScale) * __frcp_rn(s) : 0.f;
-  // element (row, frame t) of a K-major tile over frames: chunk t / 64, 16-byte unit (t % 64) / 8 swizzled with the row
-  uint8_t *col = pt + (t >> 6) * (2 * NP * 128) + ((t & 7) << 1);
-  const int u = (t & 63) >> 3;
+  // The posterior tile is an MN-major operand of the statistics GEMM (frames = K rows, 16 Gaussians = 32 contiguous
+  // bytes per row, 32-byte swizzle: the canonical layout ((2,n),(8,k)):((1,LBO),(2,SBO)) of 16-byte units under
+  // Swizzle<1,4,3>; tools/umma_mn_check.cu): atom r (Gaussians 16r..16r+15) at r * 4096 bytes, frame t at t * 32, the
+  // two 16-byte units of a row swapped when bit 2 of t is set.  Atoms [0, NP/16) = P_hi, [NP/16, NP/8) = P_lo: the
+  // frame's column is 2 (4) 128-bit stores per part instead of 16 (32) 16-bit ones.
+  uint8_t *row = pt + t * 32;
+  const uint32_t sw = (uint32_t)((t >> 2) & 1) << 4;
 #pragma unroll
-  for (int g = 0; g < NP; ++g) {
-    const float ps = live ? ll[g] * f : 0.f;   // (dead rows may hold anything: never NaN into the tile)
-    const __half hi = __float2half_rn(ps);
-    const __half lo = __float2half_rn(ps - __half2float(hi));
-    *reinterpret_cast<__half *>(col + g * 128 + ((u ^ (g & 7)) << 4)) = hi;
-    *reinterpret_cast<__half *>(col + (NP + g) * 128 + ((u ^ (g & 7)) << 4)) = lo;   // ((NP + g) & 7 == g & 7)
+  for (int r = 0; r < NP / 16; ++r) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = ll[16 * r + 2 * j] * f, p1 = ll[16 * r + 2 * j + 1] * f;  // (dead rows: f = 0 and the exponentials are <= 1)
+      h[j] = pack_h2(p0, p1);
+      const float2 hf = unpack_h2(h[j]);
+      l[j] = pack_h2(p0 - hf.x, p1 - hf.y);
+    }
+    *reinterpret_cast<uint4 *>(row + r * 4096 + (0u ^ sw)) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(row + r * 4096 + (16u ^ sw)) = make_uint4(h[4], h[5], h[6], h[7]);
+    *reinterpret_cast<uint4 *>(row + (NP / 16 + r) * 4096 + (0u ^ sw)) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4 *>(row + (NP / 16 + r) * 4096 + (16u ^ sw)) = make_uint4(l[4], l[5], l[6], l[7]);
   }
   return lse;
 }
@@ -482,23 +506,23 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     STK_T(5);  // softmax, exact re-evaluation, posterior tile + barrier
-    // ---- phase B: S_a (+)= X[chunks 0, 1]^T . [P_hi ; P_lo] (N = 2 NP), S_c (+)= X[chunk 2, ...]^T . P_hi (N = NP); X read
-    // MN-major: 16 frames = 2048 bytes per K step, LBO = one chunk (the next 64 virtual columns)
+    // ---- phase B: S_a (+)= X[chunks 0, 1]^T . [P_hi | P_lo] (N = 2 NP), S_c (+)= X[chunk 2, ...]^T . P_hi (N = NP); both
+    // operands MN-major: X 16 frames = 2048 bytes per K step, LBO = one chunk (the next 64 virtual columns)
     if (warp_u == 0) {
       tc_fence_after();
       if (elect_one()) {
         const uint32_t lbo = (uint32_t)(kAChunkBytes >> 4) << 16;
-        const uint32_t xa = umma_desc_lo(sX) | lbo, xc = umma_desc_lo(sX + 2 * kAChunkBytes) | lbo, pt = umma_desc_lo(sPt);
-        const uint32_t pchunk = (uint32_t)(2 * NP * 128) >> 4;
-        const uint32_t id2 = (1u << 4) | (1u << 15) | ((uint32_t)(2 * NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t id1 = (1u << 4) | (1u << 15) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t xa = umma_desc_lo(sX) | lbo, xc = umma_desc_lo(sX + 2 * kAChunkBytes) | lbo;
+        const uint32_t pt = umma_desc_lo(sPt) | ((uint32_t)(4096 >> 4) << 16);  // LBO = 4096 B: the next 16 Gaussians
+        const uint32_t id2 = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(2 * NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t id1 = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t acc0 = acc_tiles > 0 ? 1u : 0u;
 #pragma unroll
-        for (int s = 0; s < 8; ++s)
-          tc_mma<true>(tmem + 32, xa + s * (2048 >> 4), pt + (s >> 2) * pchunk + (s & 3) * 2, id2, s ? 1u : acc0);
+        for (int s = 0; s < 8; ++s)  // 16 frames per K step: 2048 bytes of X, 512 bytes of the posterior tile
+          stk_mma(tmem + 32, xa + s * (2048 >> 4), pt + s * (512 >> 4), kStkPtDescHi, id2, s ? 1u : acc0);
 #pragma unroll
         for (int s = 0; s < 8; ++s)
-          tc_mma<true>(tmem + 96, xc + s * (2048 >> 4), pt + (s >> 2) * pchunk + (s & 3) * 2, id1, s ? 1u : acc0);
+          stk_mma(tmem + 96, xc + s * (2048 >> 4), pt + s * (512 >> 4), kStkPtDescHi, id1, s ? 1u : acc0);
         tc_commit(sBarB);
       }
       __syncwarp();

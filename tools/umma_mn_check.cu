@@ -33,6 +33,11 @@ __device__ __forceinline__ void mma_f16(uint32_t d, uint32_t a_lo, uint32_t b_lo
                "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
                ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kDescHi) : "memory");
 }
+__device__ __forceinline__ void mma_f16_desc(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -49,14 +54,14 @@ __host__ __device__ inline uint32_t sw_off(int rows, int row, int col) {
 }
 
 // X: 128 x 128 fp16 (row-major, plain), B: N x 128, P: N x 128 (row g, column t).  out_a[t][g], out_b[k][g].
-__global__ void __launch_bounds__(128, 1) check_kernel(const __half *X, const __half *B, const __half *P, int N, float *out_a, float *out_b,
+__global__ void __launch_bounds__(128, 1) check_kernel(const __half *X, const __half *B, const __half *P, int N, float *out_a, float *out_b, float *out_c,
                                                        int reps, unsigned *cyc) {
   extern __shared__ uint8_t raw_[];
   const uint32_t raw = smem_u32(raw_);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *bp = raw_ + (base - raw);
   // X: 2 chunks x 16 KB | B: 2 chunks x N*128 | P: 2 chunks x N*128 | barrier, slot
-  const uint32_t oX = 0, oB = 32768, oP = oB + 2 * 32 * 128, oBar = oP + 2 * 32 * 128, oSlot = oBar + 8;
+  const uint32_t oX = 0, oB = 32768, oP = oB + 2 * 32 * 128, oP2 = oP + 2 * 32 * 128, oBar = oP2 + 2 * 4096, oSlot = oBar + 8;
   for (int i = threadIdx.x; i < 128 * 128; i += 128) {
     const int r = i >> 7, c = i & 127;
     *reinterpret_cast<__half *>(bp + oX + sw_off(128, r, c)) = X[i];
@@ -65,13 +70,15 @@ __global__ void __launch_bounds__(128, 1) check_kernel(const __half *X, const __
     const int r = i >> 7, c = i & 127;
     *reinterpret_cast<__half *>(bp + oB + sw_off(N, r, c)) = B[i];
     *reinterpret_cast<__half *>(bp + oP + sw_off(N, r, c)) = P[i];
+    // the same posterior matrix, frames as rows: P2[t = c][g = r], MN-major (g contiguous), 32-byte swizzle
+    *reinterpret_cast<__half *>(bp + oP2 + (r >> 4) * 4096 + c * 32 + (((((r & 15) >> 3) ^ ((c >> 2) & 1))) << 4) + ((r & 7) << 1)) = P[i];
   }
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(base + oBar), "r"(1) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 32) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + oSlot), "r"(64) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + oSlot), "r"(128) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -99,6 +106,18 @@ __global__ void __launch_bounds__(128, 1) check_kernel(const __half *X, const __
       const uint32_t bo = (uint32_t)((s >> 2) * ((N * 128) >> 4) + (s & 3) * 2);
       if (leader) mma_f16(tmem + 32, xa + ao, pa + bo, idesc_mn, s ? 1u : 0u);
     }
+    // phase B': the same product with P as an MN-major operand (frames x Gaussians, 16 Gaussians = 32 bytes per row,
+    // 32-byte swizzle: 8 frames x 32 B atoms, SBO = 256 B to the next 8 frames, LBO = 4096 B to the next 16 Gaussians)
+    {
+      const uint64_t hiA = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      const uint64_t hiB = ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+      const uint32_t idesc_mn2 = idesc_mn | (1u << 16);
+      for (int s = 0; s < 8; ++s) {
+        const uint64_t da = hiA | (uint64_t)(((base + oX + s * 2048) >> 4) & 0x3FFF) | ((uint64_t)(16384 >> 4) << 16);
+        const uint64_t db = hiB | (uint64_t)(((base + oP2 + s * 512) >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16);
+        if (leader) mma_f16_desc(tmem + 64, da, db, idesc_mn2, s ? 1u : 0u);
+      }
+    }
     if (leader) commit(base + oBar);
   }
   mbar_wait(base + oBar, phase);
@@ -112,6 +131,8 @@ __global__ void __launch_bounds__(128, 1) check_kernel(const __half *X, const __
       for (int i = 0; i < 16; ++i) out_a[row * N + c0 + i] = __uint_as_float(r[i]);
       ld16(tmem + ((uint32_t)(w * 32) << 16) + 32 + c0, r);
       for (int i = 0; i < 16; ++i) out_b[row * N + c0 + i] = __uint_as_float(r[i]);
+      ld16(tmem + ((uint32_t)(w * 32) << 16) + 64 + c0, r);
+      for (int i = 0; i < 16; ++i) out_c[row * N + c0 + i] = __uint_as_float(r[i]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -146,7 +167,7 @@ __global__ void __launch_bounds__(128, 1) check_kernel(const __half *X, const __
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64) : "memory");
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128) : "memory");
 }
 
 int main() {
@@ -158,24 +179,25 @@ int main() {
     for (auto &v : B) v = __float2half(rnd());
     for (auto &v : P) v = __float2half(fabsf(rnd()));
     __half *dX, *dB, *dP;
-    float *da, *db;
+    float *da, *db, *dcc;
     unsigned *dc;
     cudaMalloc(&dX, X.size() * 2); cudaMalloc(&dB, B.size() * 2); cudaMalloc(&dP, P.size() * 2);
-    cudaMalloc(&da, 128 * N * 4); cudaMalloc(&db, 128 * N * 4); cudaMalloc(&dc, 8);
+    cudaMalloc(&da, 128 * N * 4); cudaMalloc(&db, 128 * N * 4); cudaMalloc(&dcc, 128 * N * 4); cudaMalloc(&dc, 8);
     cudaMemcpy(dX, X.data(), X.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(dP, P.data(), P.size() * 2, cudaMemcpyHostToDevice);
-    const size_t smem = 32768 + 4 * 32 * 128 + 64 + 1024;
+    const size_t smem = 32768 + 4 * 32 * 128 + 2 * 4096 + 64 + 1024;
     cudaFuncSetAttribute(check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    check_kernel<<<1, 128, smem>>>(dX, dB, dP, N, da, db, 2000, dc);
+    check_kernel<<<1, 128, smem>>>(dX, dB, dP, N, da, db, dcc, 2000, dc);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("N=%d: ERROR %s\n", N, cudaGetErrorString(e)); return 1; }
-    std::vector<float> ha(128 * N), hb(128 * N);
+    std::vector<float> ha(128 * N), hb(128 * N), hcc(128 * N);
     unsigned hc[2];
     cudaMemcpy(ha.data(), da, ha.size() * 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(hb.data(), db, hb.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hcc.data(), dcc, hcc.size() * 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(hc, dc, 8, cudaMemcpyDeviceToHost);
-    double ea = 0, eb = 0;
+    double ea = 0, eb = 0, ec = 0;
     for (int t = 0; t < 128; ++t)
       for (int g = 0; g < N; ++g) {
         double ra = 0, rb = 0;
@@ -183,9 +205,11 @@ int main() {
         for (int u = 0; u < 128; ++u) rb += (double)__half2float(X[u * 128 + t]) * __half2float(P[g * 128 + u]);  // row index t plays k
         ea = fmax(ea, fabs(ra - ha[t * N + g]));
         eb = fmax(eb, fabs(rb - hb[t * N + g]));
+        ec = fmax(ec, fabs(rb - hcc[t * N + g]));
       }
     printf("N=%d: phase A (K-major X) max abs err %.3g; phase B (same tile as MN-major A) max abs err %.3g  -> %s\n", N, ea, eb,
            (ea < 1e-3 && eb < 1e-3) ? "OK" : "MISMATCH");
+    printf("N=%d: phase B with P as an MN-major 32B-swizzle operand: max abs err %.3g -> %s\n", N, ec, ec < 1e-3 ? "OK" : "MISMATCH");
     printf("N=%d: %.1f cycles per K-major MMA, %.1f cycles per MN-major-A MMA (M=128, K=16, one CTA)\n", N, hc[0] / 100.0, hc[1] / 100.0);
   }
   return 0;
