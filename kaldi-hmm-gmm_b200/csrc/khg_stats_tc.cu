@@ -135,10 +135,7 @@ __device__ __forceinline__ float stk_softmax_store(uint32_t trow, int ng, float 
   }
   float mx = -CUDART_INF_F;
 #pragma unroll
-  for (int g = 0; g < NP; ++g) {
-    if (g >= ng) ll[g] = -CUDART_INF_F;
-    mx = fmaxf(mx, ll[g]);
-  }
+  for (int g = 0; g < NP; ++g) mx = fmaxf(mx, ll[g]);  // (rows beyond the pdf's Gaussians are -inf: see stk_pack_kernel)
   if (live) {
     uint32_t todo = 0;
 #pragma unroll
@@ -617,8 +614,11 @@ __global__ void __launch_bounds__(128) stk_pack_kernel(int P, int D, int DP, con
       else if (k == 2 * DP + 1) { v = gconsts[g0 + g]; gc_lo = true; }
     }
     if (!(fabsf(v) <= 3.0e4f)) bad = true;  // also -inf gconsts and NaN: such models stay on the fp32 kernel
-    const __half hi = __float2half_rn(v);
+    __half hi = __float2half_rn(v);
     const __half lo = __float2half_rn(v - __half2float(hi));
+    // rows beyond the pdf's Gaussians: gconst = -inf, so that their screened log-like is -inf (x 1 in the tile's
+    // 1-column; every other entry of the row is 0) and the softmax needs no index mask
+    if (g >= ng && k == 2 * DP) hi = __float2half_rn(-CUDART_INF_F);
     const uint32_t off = (uint32_t)((k >> 6) * (NP * 128) + g * 128 + ((((k & 63) >> 3) ^ (g & 7)) << 4) + ((k & 7) << 1));
     *reinterpret_cast<__half *>(o + off) = gc_lo ? lo : hi;
   }
