@@ -38,6 +38,9 @@ constexpr float kStkWeightLimit = 8.f;           // |w| * 4096 must stay inside 
 #ifndef KHG_STK_REG_PREFETCH
 #define KHG_STK_REG_PREFETCH 1
 #endif
+#ifndef KHG_STK_L2PF
+#define KHG_STK_L2PF 1  // rows about four tiles ahead go to L2: 0 = no (-14 % at C4), 1 = prefetch.global.L2 per line, 2 = one bulk prefetch per row (-1 % at C4, -8 % at C5: profiles/r3q)
+#endif
 #ifndef KHG_STK_CTAS
 #define KHG_STK_CTAS 3
 #endif
@@ -324,10 +327,16 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
   };
   int pf_idx = -1;  // index whose row goes to L2 next
   auto l2_pipeline = [&](int pos) {
-    if (pf_idx >= 0) {
+    if (KHG_STK_L2PF != 0 && pf_idx >= 0) {
       const char *r = reinterpret_cast<const char *>(a.feats + (size_t)pf_idx * D);
-      prefetch_l2(r);
-      prefetch_l2(r + 4 * D - 4);
+      if (KHG_STK_L2PF == 2 && vec) {
+        // one bulk prefetch of the whole row (the TMA unit's path: no tag lookups in L1TEX, where the 32 rows of a warp's
+        // prefetch instruction cost 32 each)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(r), "r"(4 * D) : "memory");
+      } else {
+        prefetch_l2(r);
+        prefetch_l2(r + 4 * D - 4);
+      }
       if (a.weights) prefetch_l2(a.weights + pf_idx);
     }
     pf_idx = pos < a.n_frames ? __ldg(a.order + pos) : -1;
