@@ -267,13 +267,15 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
   const int i0 = (int)((int64_t)blockIdx.x * n_items / gridDim.x), i1 = (int)((int64_t)(blockIdx.x + 1) * n_items / gridDim.x);
   const bool vec = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.feats) & 15) == 0);
   const bool vec256 = (D & 7) == 0 && ((reinterpret_cast<uintptr_t>(a.feats) & 31) == 0);
+  const bool chunked = !vec && ((reinterpret_cast<uintptr_t>(a.feats) & 15) == 0);  // 4-byte aligned rows, 16-byte aligned buffer
 
   // Gather pipeline.  While item `it` is computed: the ROWS of item it+1 are in flight into xr[] (their index was
   // loaded one item earlier: the address depends on a loaded value and a thread cannot issue past a dependent
   // instruction), the INDEX of item it+2 is in flight into idx2, and the rows about four tiles ahead in the sorted
   // order are being pulled into L2 (prefetch: position-based, item boundaries do not matter for it), so that the
   // register loads are L2 hits.
-  float xr[DP];
+  float xr[DP + 4];  // (rows that are only 4-byte aligned arrive as aligned 16-byte chunks: up to 3 leading words)
+  int xoff1 = 0;     // word offset of the row inside its first chunk (0 on the aligned paths)
   float w1 = 0.f;
   int idx1 = -1, idx2 = -1;
   // item descriptors of [stage0, stage0 + kStkDescStage + 2) wait in shared memory: a descriptor read never
@@ -320,7 +322,25 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
           xr[4 * q] = xr[4 * q + 1] = xr[4 * q + 2] = xr[4 * q + 3] = 0.f;
         }
       }
+    } else if (chunked && idx != a.n_frames - 1) {
+      // rows of dim 39 (13 x 3) and the like start on any 4-byte boundary: 39 scalar loads per row cost 39 x 32 tag
+      // lookups per warp.  The ALIGNED 16-byte chunks that cover the row are loaded instead (11 at dim 39), the row's
+      // word offset inside the first chunk is kept, and the words are picked by two levels of selects when the row is
+      // consumed.  (The buffer's last row keeps the scalar loads: its last chunk would end past the buffer.)
+      const int o = (int)(((size_t)idx * D) & 3);
+      xoff1 = o;
+      const float4 *c4 = reinterpret_cast<const float4 *>(src - o);
+#pragma unroll
+      for (int q = 0; q < DP / 4 + 1; ++q) {
+        if (4 * q < o + D) {
+          const float4 v = __ldg(c4 + q);
+          xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w;
+        } else {
+          xr[4 * q] = xr[4 * q + 1] = xr[4 * q + 2] = xr[4 * q + 3] = 0.f;
+        }
+      }
     } else {
+      xoff1 = 0;
 #pragma unroll
       for (int d2 = 0; d2 < DP; ++d2) xr[d2] = d2 < D ? __ldg(src + d2) : 0.f;
     }
@@ -342,7 +362,7 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
     pf_idx = pos < a.n_frames ? __ldg(a.order + pos) : -1;
   };
 #pragma unroll
-  for (int d2 = 0; d2 < DP; ++d2) xr[d2] = 0.f;
+  for (int d2 = 0; d2 < DP + 4; ++d2) xr[d2] = 0.f;
 
   const float *mf = nullptr, *vf = nullptr, *gcf = nullptr;  // fp32 parameters of the current pdf inside its image
   int cur_p = -1, g0 = 0, ng = 0, NP = 16, acc_tiles = 0;  // (NP stays 16 when NPM == 16: the compiler folds it)
@@ -441,11 +461,22 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
     const int idx = idx1;
     float xs[DP];
     bool bad = false;
+    if (chunked) {  // word d of the row is word d + offset of the loaded chunks: two levels of selects (offset bit 0, bit 1)
+      const bool o1 = (xoff1 & 1) != 0, o2 = (xoff1 & 2) != 0;
+      float u1[DP + 2];
 #pragma unroll
-    for (int d2 = 0; d2 < DP; ++d2) {
-      xs[d2] = xr[d2] * a.asc_c[d2];  // (a kernel parameter: a constant-bank operand of the FMUL, no load)
-      bad |= !(fabsf(xs[d2]) <= kF16FeatLimit);
+      for (int d2 = 0; d2 < DP + 2; ++d2) u1[d2] = o1 ? xr[d2 + 1] : xr[d2];
+#pragma unroll
+      for (int d2 = 0; d2 < DP; ++d2) {
+        const float v = o2 ? u1[d2 + 2] : u1[d2];
+        xs[d2] = (d2 < D ? v : 0.f) * a.asc_c[d2];
+      }
+    } else {
+#pragma unroll
+      for (int d2 = 0; d2 < DP; ++d2) xs[d2] = xr[d2] * a.asc_c[d2];  // (a kernel parameter: a constant-bank operand of the FMUL, no load)
     }
+#pragma unroll
+    for (int d2 = 0; d2 < DP; ++d2) bad |= !(fabsf(xs[d2]) <= kF16FeatLimit);
     bad = live && (bad || !(fabsf(w) <= kStkWeightLimit));
     // next item's rows (index loaded one item ago), the index after that, L2 prefetch further ahead
     idx1 = idx2;
