@@ -356,12 +356,34 @@ def run_workloads(torch, args, dev, local, peaks, tf32_peak, dm4, feats4, pdf4, 
     # -- W-aligned at C4: K2 + K3 only (what gmm-acc-stats-ali computes), HBM-bound
     n = min(feats4.shape[0], 20_000_000)
     st = DeviceStats(dm4)
-    ms, ck, reps = timed(torch, lambda: st.acc_stats_ali(feats4[:n], pdf4[:n], want_total=False), 5, local)
+    ms, ck, reps = timed(torch, lambda: st.acc_stats_ali(feats4[:n], pdf4[:n], want_total=False), 5, local, 1.0)
     fps = n / (ms * 1e-3)
     out["w_aligned_c4"] = {"value": fps, "unit": "frames/s", "ms_per_call": ms, "frames_per_call": n, "reps": reps, "clocks": ck,
+                           "stats_kernel": int(dm4.stats_kernel()) if hasattr(dm4, "stats_kernel") else None,
                            "roofline": {"bound": "hbm", "achieved": fps * (4 * D4 + 4) / 1e9, "peak": hbm, "unit": "GB/s",
                                         "frac": fps * (4 * D4 + 4) / 1e9 / hbm, "algorithmic_bytes_per_frame": 4 * D4 + 4}}
-    del st
+    # the same call as the reference's script makes it (scripts/gmm_acc_stats_ali.py:46-56): HOST features and pdf ids
+    # (pinned), H2D inside the call, the statistics read back to the host — wall clock, PCIe-bound
+    ne = min(n, 8_000_000)
+    hf = torch.empty((ne, D4), dtype=torch.float32, pin_memory=True)
+    hp = torch.empty(ne, dtype=torch.int32, pin_memory=True)
+    hf.copy_(feats4[:ne])
+    hp.copy_(pdf4[:ne])
+    hfn, hpn = hf.numpy(), hp.numpy()
+    st.acc_stats_ali(hfn, hpn, want_total=True)  # sizes the staging buffers
+    e_reps = 3
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e_reps):
+        st.zero()
+        st.acc_stats_ali(hfn, hpn, want_total=True)
+        got = st.download()
+    dt = (time.perf_counter() - t0) / e_reps
+    assert abs(got["tot_frames"] - ne) < 0.5, (got["tot_frames"], ne)
+    out["w_aligned_c4"]["e2e_host_feats"] = {"value": ne / dt, "unit": "frames/s", "frames_per_call": ne, "ms_per_call": dt * 1e3,
+                                             "h2d_bytes_per_call": int(ne * (4 * D4 + 4)), "d2h_bytes_per_call": int(st.as_torch().numel() * 8),
+                                             "h2d_GBps": ne * (4 * D4 + 4) / dt / 1e9}
+    del st, hf, hp, hfn, hpn
 
     # -- the north star's literal 3xTF32 kernel at C4 (dense block only)
     if dm4.dense_kernel() != 2:
@@ -587,7 +609,8 @@ def run_b200(args):
         st2 = DeviceStats(dm)
         sv2 = st2.as_torch()
         e2e_steps = max(1, min(args.steps, 3))
-        st2.estep(hfn[: chunk * 2], hpn[: chunk * 2], block, chunk_frames=chunk)  # warms the staging buffers
+        n_warm = min(T, (16 << 20) + 2 * chunk)  # sizes the staging buffers (two device halves of one statistics group each)
+        st2.estep(hfn[:n_warm], hpn[:n_warm], block, chunk_frames=chunk)
         barrier()
         t0 = time.perf_counter()
         res = None

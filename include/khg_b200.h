@@ -252,7 +252,9 @@ khg_status khg_acc_from_posteriors(khg_model *m, khg_stats *s, int32_t pdf,
  * ld_out >= chunk_frames; it is reused chunk by chunk (the consumer is on the
  * device side of the boundary).  feats/pdf_ids/frame_weights per `loc`; with
  * KHG_HOST the call streams chunks through pinned staging buffers, copy
- * overlapped with compute.  chunk_frames<=0 picks a default. */
+ * overlapped with compute.  chunk_frames<=0 picks a default.  The statistics
+ * pass runs once per group of chunks (up to 16 M frames; with KHG_HOST the
+ * frames of two groups are staged on the device: <= 2 x 2.7 GB at dim 40). */
 khg_status khg_estep(khg_model *m, khg_stats *s, const float *feats, int64_t T,
                      int32_t loc, const int32_t *pdf_ids,
                      const float *frame_weights, float *loglikes_out,

@@ -1000,15 +1000,28 @@ khg_status khg_estep(khg_model *m, khg_stats *s, const float *feats, int64_t T, 
     d_call = m->w_tot.as<double>();
     KHG_CUDA_TRY(cudaMemsetAsync(d_call, 0, sizeof(double), m->stream));
   }
+  // The statistics pass (K2 + K3 / K3t) does not read the dense block, so it runs once per GROUP of chunks: a chunk of
+  // 606 208 frames holds ~144 frames per pdf at C4 (303 at C3) — partly filled 128-frame work items and a dozen small
+  // launches per chunk (1.1-2.4 G frames/s inside the E-step against 7-8 G for a whole batch).  A group is up to 16 M
+  // frames (KHG_ESTEP_STATS_GROUP_FRAMES), a multiple of the chunk.
+  int64_t group_frames = 16LL << 20;
+  if (const char *e = getenv("KHG_ESTEP_STATS_GROUP_FRAMES")) group_frames = std::max<int64_t>(1, atoll(e));
+  const int64_t cpg = std::max<int64_t>(1, group_frames / chunk_frames);  // chunks per group
   if (loc == KHG_DEVICE) {
-    for (int64_t t0 = 0; t0 < T; t0 += chunk_frames) {
+    int64_t g0 = 0;
+    for (int64_t t0 = 0, c = 0; t0 < T; t0 += chunk_frames, ++c) {
       int64_t n = std::min(chunk_frames, T - t0);
       KHG_TRY(dense_device(m, feats + t0 * D, n, 1.0f, KHG_PDF_MAJOR, loglikes_out, ld_out));
-      KHG_TRY(acc_device(m, s, feats + t0 * D, n, pdf_ids + t0, frame_weights ? frame_weights + t0 : nullptr, nullptr, d_call));
+      if ((c + 1) % cpg == 0 || t0 + n == T) {
+        KHG_TRY(acc_device(m, s, feats + g0 * D, t0 + n - g0, pdf_ids + g0, frame_weights ? frame_weights + g0 : nullptr, nullptr, d_call));
+        g0 = t0 + n;
+      }
     }
   } else {
-    // Host inputs: double-buffered pinned staging; the H2D copy of chunk i+1 runs on
-    // copy_stream while chunk i computes on the model stream.
+    // Host inputs: pinned staging (two chunk slots) -> device staging (two HALVES of one group of chunks each); the
+    // H2D copies run on copy_stream ahead of the compute on the model stream: the dense kernel of a chunk starts when
+    // its copy has landed, the statistics pass of a group after the group's last dense kernel, and a half is
+    // refilled (group g + 2) once the statistics of group g have read it.
     KHG_TRY(estep_init_streams(m));
     // Caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory)
     // are copied from directly: no staging memcpy on the calling thread, which is what limits several
@@ -1022,42 +1035,48 @@ khg_status khg_estep(khg_model *m, khg_stats *s, const float *feats, int64_t T, 
       return at.type == cudaMemoryTypeHost;
     };
     const bool direct_f = is_pinned(feats), direct_i = is_pinned(pdf_ids), direct_w = frame_weights && is_pinned(frame_weights);
+    const int64_t n_chunks = (T + chunk_frames - 1) / chunk_frames;
+    const int64_t half_frames = std::min(cpg, n_chunks) * chunk_frames;
     for (int i = 0; i < 2; ++i) {
       if (!direct_f) KHG_TRY(m->pin_feats[i].reserve(sizeof(float) * chunk_frames * D));
       if (!direct_i) KHG_TRY(m->pin_ids[i].reserve(sizeof(int32_t) * chunk_frames));
-      KHG_TRY(m->w_efeats[i].reserve(sizeof(float) * chunk_frames * D));
-      KHG_TRY(m->w_eids[i].reserve(sizeof(int32_t) * chunk_frames));
-      if (frame_weights) {
-        if (!direct_w) KHG_TRY(m->pin_wts[i].reserve(sizeof(float) * chunk_frames));
-        KHG_TRY(m->w_ewts[i].reserve(sizeof(float) * chunk_frames));
-      }
+      if (frame_weights && !direct_w) KHG_TRY(m->pin_wts[i].reserve(sizeof(float) * chunk_frames));
+      if (i == 1 && n_chunks <= cpg) break;  // a single group: one half
+      KHG_TRY(m->w_efeats[i].reserve(sizeof(float) * half_frames * D));
+      KHG_TRY(m->w_eids[i].reserve(sizeof(int32_t) * half_frames));
+      if (frame_weights) KHG_TRY(m->w_ewts[i].reserve(sizeof(float) * half_frames));
     }
-    int64_t n_chunks = (T + chunk_frames - 1) / chunk_frames;
-    std::vector<bool> used(2, false);
+    bool pin_used[2] = {false, false};
     for (int64_t c = 0; c < n_chunks; ++c) {
-      int b = (int)(c & 1);
-      int64_t t0 = c * chunk_frames, n = std::min(chunk_frames, T - t0);
-      // the device buffers of slot b are free once the compute that read them is done
-      if (used[b]) KHG_CUDA_TRY(cudaStreamWaitEvent(m->copy_stream, m->ev_done[b], 0));
-      // pinned slot b is free once its previous H2D finished
-      if (used[b]) KHG_CUDA_TRY(cudaEventSynchronize(m->ev_copy[b]));
+      const int b = (int)(c & 1);                      // pinned staging slot
+      const int64_t g = c / cpg, k = c % cpg;          // group, chunk inside the group
+      const int h = (int)(g & 1);                      // device half
+      const int64_t t0 = c * chunk_frames, n = std::min(chunk_frames, T - t0);
+      // half h is free once the statistics pass of group g - 2 (recorded on ev_done[h]) has read it
+      if (k == 0 && g >= 2) KHG_CUDA_TRY(cudaStreamWaitEvent(m->copy_stream, m->ev_done[h], 0));
+      // pinned slot b is free once its previous H2D finished (also bounds how far the host runs ahead)
+      if (pin_used[b]) KHG_CUDA_TRY(cudaEventSynchronize(m->ev_copy[b]));
+      float *d_f = m->w_efeats[h].as<float>() + k * chunk_frames * D;
+      int32_t *d_i = m->w_eids[h].as<int32_t>() + k * chunk_frames;
       const void *src_f = feats + t0 * D, *src_i = pdf_ids + t0;
       if (!direct_f) src_f = std::memcpy(m->pin_feats[b].p, src_f, sizeof(float) * n * D);
       if (!direct_i) src_i = std::memcpy(m->pin_ids[b].p, src_i, sizeof(int32_t) * n);
-      KHG_CUDA_TRY(cudaMemcpyAsync(m->w_efeats[b].p, src_f, sizeof(float) * n * D, cudaMemcpyHostToDevice, m->copy_stream));
-      KHG_CUDA_TRY(cudaMemcpyAsync(m->w_eids[b].p, src_i, sizeof(int32_t) * n, cudaMemcpyHostToDevice, m->copy_stream));
+      KHG_CUDA_TRY(cudaMemcpyAsync(d_f, src_f, sizeof(float) * n * D, cudaMemcpyHostToDevice, m->copy_stream));
+      KHG_CUDA_TRY(cudaMemcpyAsync(d_i, src_i, sizeof(int32_t) * n, cudaMemcpyHostToDevice, m->copy_stream));
       if (frame_weights) {
         const void *src_w = frame_weights + t0;
         if (!direct_w) src_w = std::memcpy(m->pin_wts[b].p, src_w, sizeof(float) * n);
-        KHG_CUDA_TRY(cudaMemcpyAsync(m->w_ewts[b].p, src_w, sizeof(float) * n, cudaMemcpyHostToDevice, m->copy_stream));
+        KHG_CUDA_TRY(cudaMemcpyAsync(m->w_ewts[h].as<float>() + k * chunk_frames, src_w, sizeof(float) * n, cudaMemcpyHostToDevice, m->copy_stream));
       }
       KHG_CUDA_TRY(cudaEventRecord(m->ev_copy[b], m->copy_stream));
+      pin_used[b] = true;
       KHG_CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_copy[b], 0));
-      KHG_TRY(dense_device(m, m->w_efeats[b].as<float>(), n, 1.0f, KHG_PDF_MAJOR, loglikes_out, ld_out));
-      KHG_TRY(acc_device(m, s, m->w_efeats[b].as<float>(), n, m->w_eids[b].as<int32_t>(),
-                         frame_weights ? m->w_ewts[b].as<float>() : nullptr, nullptr, d_call));
-      KHG_CUDA_TRY(cudaEventRecord(m->ev_done[b], m->stream));
-      used[b] = true;
+      KHG_TRY(dense_device(m, d_f, n, 1.0f, KHG_PDF_MAJOR, loglikes_out, ld_out));
+      if (k == cpg - 1 || c == n_chunks - 1) {
+        KHG_TRY(acc_device(m, s, m->w_efeats[h].as<float>(), k * chunk_frames + n, m->w_eids[h].as<int32_t>(),
+                           frame_weights ? m->w_ewts[h].as<float>() : nullptr, nullptr, d_call));
+        KHG_CUDA_TRY(cudaEventRecord(m->ev_done[h], m->stream));
+      }
     }
   }
   if (tot_loglike) {

@@ -319,6 +319,34 @@ def test_estep_device_and_host_paths(oracle):
     assert abs(tot2 - ref["tot_like"]) <= STATS_RTOL * abs(ref["tot_like"])
 
 
+def test_estep_statistics_groups(oracle, monkeypatch):
+    """khg_estep runs the statistics pass once per GROUP of chunks (two device halves, refilled while the other one
+    computes): several groups with a ragged tail, device / pageable / pinned inputs, frame weights; the answer is the
+    oracle's and does not depend on the grouping."""
+    import torch
+    from kaldi_hmm_gmm_b200 import DeviceStats
+
+    model, means, vars_ = ko.make_synthetic_model(40, 50, 400, oracle=oracle)
+    T = 23_000
+    feats, pdf = ko.make_synthetic_frames(model, means, vars_, T)
+    w = np.random.default_rng(3).uniform(0.25, 2.0, T).astype(np.float32)
+    dm, _ = _device_model(model)
+    ref = oracle.acc_stats_ali(model, feats, pdf, frame_weights=w)
+    block = torch.empty((model.num_pdfs, 1024), device="cuda")
+    hf, hp, hw = (torch.from_numpy(a).pin_memory() for a in (feats, pdf, w))
+    dfe, dpd, dw = (torch.from_numpy(a).cuda() for a in (feats, pdf, w))
+    for group in ("1", "3000", "5000", "100000"):  # 1, 2, 4 chunks per group (7 groups, the last one ragged); one group
+        monkeypatch.setenv("KHG_ESTEP_STATS_GROUP_FRAMES", group)
+        for args in ((dfe, dpd, dw), (feats, pdf, w), (hf.numpy(), hp.numpy(), hw.numpy())):
+            st = DeviceStats(dm)
+            tot = st.estep(args[0], args[1], block, chunk_frames=1024, frame_weights=args[2], want_total=True)
+            got = st.download()
+            for k in ("occ", "mean", "var"):
+                np.testing.assert_allclose(got[k], ref[k], rtol=STATS_RTOL, atol=STATS_RTOL * np.abs(ref[k]).max())
+            assert abs(got["tot_frames"] - float(w.astype(np.float64).sum())) < 1e-3
+            assert abs(tot - ref["tot_like"]) <= STATS_RTOL * abs(ref["tot_like"])
+
+
 def test_large_properties(oracle):
     """Size-independent properties at a size the oracle cannot check frame by frame:
     (1) sum of occupancies == number of frames, per pdf, exactly the bucket sizes;
