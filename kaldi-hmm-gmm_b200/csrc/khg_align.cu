@@ -1009,16 +1009,52 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   // KHG_ALIGN_FORCE_GCOST / KHG_ALIGN_FORCE_FC: tests force the large-graph paths (costs in global
   // scratch; likelihood tile of 16 / 8 / 0 frames) on small inputs
   const bool use_gcost = cost_bytes > 160 * 1024 || getenv("KHG_ALIGN_FORCE_GCOST") != nullptr;
-  int FC = 0;
+  // Launch shape.  The search is latency-bound per utterance (one CTA walks its frames in sequence), so its time is
+  // (waves of CTAs) x (latency of one utterance): fewer threads per utterance and a shorter likelihood tile are slower
+  // per utterance (measured at C5, 205 states: 128 / 64 / 32 threads = 1 : 1.65 : 2.2; 8 instead of 32 frames per tile
+  // +5 %) but more utterances are resident per SM.  The shape with the lowest estimate wins (C5, 2000 utterances: 64
+  // threads x 8 frames, one wave, 5.4 ms against 6.5 ms for two waves of 128 x 32: profiles/r4f_align_search.txt).
+  // KHG_ALIGN_FORCE_FC caps the tile (tests: the large-graph paths), KHG_ALIGN_NT fixes the threads.
   const char *force_fc = getenv("KHG_ALIGN_FORCE_FC");
-  for (int fc : {32, 16, 8})
-    if ((use_gcost ? 0 : cost_bytes) + 4 * (size_t)fc * n_pdf_max <= smem_budget && (!force_fc || fc <= atoi(force_fc))) {
-      FC = fc;
-      break;
-    }
-  const size_t smem = (use_gcost ? 0 : cost_bytes) + 4 * (size_t)FC * n_pdf_max + 16;
+  const int nt_base = S_max <= 256 ? 128 : (S_max <= 2048 ? 256 : 512);
   KHG_CUDA_TRY(cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));  // (per device: set on every call)
-  const int NT = S_max <= 256 ? 128 : (S_max <= 2048 ? 256 : 512);
+  int FC = 0, NT = nt_base;
+  size_t smem = (use_gcost ? 0 : cost_bytes) + 16;
+  {
+    double best_est = 0.0;
+    bool have = false;
+    int nt_forced = 0;
+    if (const char *e = getenv("KHG_ALIGN_NT")) nt_forced = std::max(32, std::min(512, atoi(e) & ~31));
+    for (int nt : {nt_base, nt_base / 2, nt_base / 4}) {
+      if (nt_forced) nt = nt_forced;
+      if (nt < 32) continue;
+      for (int fc : {32, 16, 8}) {
+        const size_t sm = (use_gcost ? 0 : cost_bytes) + 4 * (size_t)fc * n_pdf_max + 16;
+        if (sm - 16 > smem_budget || (force_fc && fc > atoi(force_fc))) continue;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, viterbi_kernel, nt, sm) != cudaSuccess || per_sm < 1) {
+          (void)cudaGetLastError();
+          continue;
+        }
+        const int64_t slots = (int64_t)per_sm * m->sm_count;
+        const double waves = (double)((max_chunk_utts + slots - 1) / slots);
+        const double lat = (nt >= nt_base ? 1.0 : (nt >= nt_base / 2 ? 1.65 : 2.2)) * (fc == 32 ? 1.0 : (fc == 16 ? 1.03 : 1.05));
+        const double est = waves * lat;
+        if (!have || est < best_est - 1e-9) {
+          have = true;
+          best_est = est;
+          NT = nt;
+          FC = fc;
+          smem = sm;
+        }
+      }
+    }
+    if (!have) {  // no tile fits: the likelihoods are read from the block directly
+      FC = 0;
+      NT = nt_base;
+      smem = (use_gcost ? 0 : cost_bytes) + 16;
+    }
+  }
   double *d_gcost = nullptr;
   if (use_gcost) {
     KHG_TRY(m->w_al_cost.reserve(sizeof(double) * 3 * (size_t)S_max * max_chunk_utts));
