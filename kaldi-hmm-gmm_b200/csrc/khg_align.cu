@@ -747,7 +747,13 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     float *d_dst = d_block + col;
     TileSubset sub;
     const int n_tiles = m->tc.ready ? tc_num_tiles(m) : 0;
-    const int64_t n_pairs = (nfr + 255) / 256;
+    // one tile list per frame tile (128 frames; the kernel then runs without CTA pairs: -1 % of operand sharing, but a tile
+    // overlaps fewer utterances than a pair of tiles: 16.8 % instead of 18.6 % of the tile units at C5), or per pair of
+    // tiles (KHG_ALIGN_SUBSET_SHIFT=1)
+    int sub_shift = 0;
+    if (const char *e = getenv("KHG_ALIGN_SUBSET_SHIFT")) sub_shift = atoi(e) != 0 ? 1 : 0;
+    const int64_t unit_frames = 128LL << sub_shift;
+    const int64_t n_pairs = (nfr + unit_frames - 1) / unit_frames;  // (lists: per pair of tiles or per tile)
     if (subset && n_tiles > 1) {
       // tiles of every utterance (bitmap), then per frame-tile pair the union over the utterances it overlaps
       const int words = (n_tiles + 63) / 64;
@@ -766,7 +772,7 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
       int u = u0;
       const int64_t base = gb->frame_offsets[u0];
       for (int64_t q = 0; q < n_pairs; ++q) {
-        const int64_t fa = base + q * 256, fb = std::min<int64_t>(fa + 256, base + nfr);
+        const int64_t fa = base + q * unit_frames, fb = std::min<int64_t>(fa + unit_frames, base + nfr);
         while (u + 1 < u1 && gb->frame_offsets[u + 1] <= fa) ++u;
         std::fill(acc.begin(), acc.end(), 0);
         for (int v = u; v < u1 && gb->frame_offsets[v] < fb; ++v)
@@ -791,6 +797,7 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
       list_keep.push_back(std::move(tiles));
       sub.off = d_off;
       sub.tiles = d_tiles;
+      sub.shift = sub_shift;
       bool used = false;
       KHG_TRY(dense_block(m, d_f, nfr, acoustic_scale, KHG_PDF_MAJOR, d_dst, ld, &sub, &used));
       units_all += n_pairs * n_tiles;
@@ -808,7 +815,7 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     return run_dense(u0, u1, d_f, subset);
   };
   if (want_subset && m->tc.ready)  // worst case: every pair of frame tiles lists every model tile (+ the offsets, per launch)
-    KHG_TRY(m->w_al_tiles.reserve(4 * ((size_t)((chunk_frames_max + 255) / 256 + 16) * (size_t)(tc_num_tiles(m) + 1) + 64)));
+    KHG_TRY(m->w_al_tiles.reserve(4 * ((size_t)((chunk_frames_max + 127) / 128 + 16) * (size_t)(tc_num_tiles(m) + 1) + 64)));
   // with the subset the kernel of the first chunk needs the graphs' pdf lists (first host pass below); without it, it is
   // launched right away and runs under the whole host preparation
   const float *d_f0 = nullptr;

@@ -227,6 +227,7 @@ bool tc_supported(const khg_model *m);
 struct TileSubset {
   const int32_t *off = nullptr;
   const int32_t *tiles = nullptr;
+  int shift = 1;  // list q serves the frame tiles [q << shift, (q + 1) << shift): 1 = per pair of tiles (CTA pairs share the operand stream), 0 = per tile (plain launch)
 };
 // model tiles [*ja, *jb] that hold Gaussians of pdf p (host tables of the pack), and the number of model tiles
 void tc_pdf_tile_range(const khg_model *m, int p, int *ja, int *jb);

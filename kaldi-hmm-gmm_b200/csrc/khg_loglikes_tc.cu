@@ -156,6 +156,7 @@ struct TcArgs {
   // tiles 2q and 2q + 1 run the tiles sub_tiles[sub_off[q] .. sub_off[q + 1]) instead of all of them (n_splits == 1)
   const int32_t *sub_off;
   const int32_t *sub_tiles;
+  int sub_shift;  // 1: one list per pair of frame tiles, 0: one per tile (no CTA pairs)
   int64_t n_items;
   float scale;
   float *out;              // pdf-major, out[p*ld + t]
@@ -259,8 +260,8 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
         const int split = (int)(item % a.n_splits);
         int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
         if (a.sub_off) {
-          j0 = __shfl_sync(0xffffffffu, __ldg(a.sub_off + (item >> 1)), 0);
-          j1 = __shfl_sync(0xffffffffu, __ldg(a.sub_off + (item >> 1) + 1), 0);
+          j0 = __shfl_sync(0xffffffffu, __ldg(a.sub_off + (item >> a.sub_shift)), 0);
+          j1 = __shfl_sync(0xffffffffu, __ldg(a.sub_off + (item >> a.sub_shift) + 1), 0);
         }
         for (int jj = j0; jj < j1; ++jj) {
           const int j = a.sub_off ? __shfl_sync(0xffffffffu, __ldg(a.sub_tiles + jj), 0) : jj;
@@ -312,8 +313,8 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
         const int split = (int)(item % a.n_splits);
         int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
         if (a.sub_off) {  // (only the number of tiles matters here)
-          j0 = __shfl_sync(0xffffffffu, __ldg(a.sub_off + (item >> 1)), 0);
-          j1 = __shfl_sync(0xffffffffu, __ldg(a.sub_off + (item >> 1) + 1), 0);
+          j0 = __shfl_sync(0xffffffffu, __ldg(a.sub_off + (item >> a.sub_shift)), 0);
+          j1 = __shfl_sync(0xffffffffu, __ldg(a.sub_off + (item >> a.sub_shift) + 1), 0);
         }
         const uint32_t asl = a_it & a_two, aph = (a_two ? a_it >> 1 : a_it) & 1;
         const uint32_t a_hi0 = a_hi_base + asl * a_slot_desc, a_lo0 = a_lo_base + asl * a_slot_desc;
@@ -446,8 +447,8 @@ loglikes_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_const
       const int split = (int)(item % a.n_splits);
       int j0 = split * a.tiles_per_split, j1 = min(a.n_tiles, j0 + a.tiles_per_split);
       if (a.sub_off) {
-        j0 = __ldg(a.sub_off + (item >> 1));
-        j1 = __ldg(a.sub_off + (item >> 1) + 1);
+        j0 = __ldg(a.sub_off + (item >> a.sub_shift));
+        j1 = __ldg(a.sub_off + (item >> a.sub_shift) + 1);
       }
       const int64_t t = (item / a.n_splits) * kTileM + row;
       const bool valid = t < a.T;
@@ -876,6 +877,7 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   const bool sub = subset && subset->off && a.n_splits == 1;
   a.sub_off = sub ? subset->off : nullptr;
   a.sub_tiles = sub ? subset->tiles : nullptr;
+  a.sub_shift = sub ? subset->shift : 1;
   a.scale = scale;
   a.out = d_out;
   a.ld = ld_out;
@@ -899,7 +901,7 @@ static khg_status tc_launch(khg_model *m, const float *d_feats, int64_t T, float
   // CTA pairs (clusters of 2) share the streamed operand through TMA multicast when every CTA has
   // whole frame tiles to itself and there are enough of them (KHG_TC_CLUSTER=0 forces the plain form)
   const char *cl = getenv("KHG_TC_CLUSTER");
-  a.cluster = (a.n_splits == 1 && n_m >= 2LL * m->sm_count && grid >= 2 && !(cl && atoi(cl) == 0)) ? 2 : 1;
+  a.cluster = (a.n_splits == 1 && n_m >= 2LL * m->sm_count && grid >= 2 && !(cl && atoi(cl) == 0) && !(sub && a.sub_shift == 0)) ? 2 : 1;
 #ifdef KHG_EXPERIMENTS
   if (a.debug_mode == 6 || a.debug_mode == 7) a.cluster = 1;
 #endif
