@@ -577,6 +577,10 @@ struct AlignPrepCache {
   std::vector<std::vector<int32_t>> updf;
   int S_max = 1, n_pdf_max = 1;
   size_t n_in = 0, n_eds = 0, n_edo = 0, eps_total = 0, n_updf = 0;
+  // tile lists of the dense launches (they depend on the graphs' pdfs, the frame offsets and the pack only): the device
+  // copies in w_al_tiles stay valid for an identical batch
+  struct TileLists { int u0, u1, shift; size_t first_word, n_off, n_list; const void *base; };
+  std::vector<TileLists> lists;
 };
 void align_cache_free(khg_model *m) {
   delete static_cast<AlignPrepCache *>(m->al_cache);
@@ -726,6 +730,8 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     pc.key[1] = key[1];
   }
   g_align_prep_hit = prep_hit ? 1 : 0;
+  const bool lists_cacheable = chunk_start.size() == 2;  // (the lists of a later chunk overwrite those of the previous one)
+  if (!prep_hit || !lists_cacheable) pc.lists.clear();
   std::vector<std::vector<int32_t>> &updf = pc.updf;  // distinct pdfs of every graph (filled by the first host pass)
   if (!prep_hit) updf.assign(U, std::vector<int32_t>());
   int64_t units_done = 0, units_all = 0;
@@ -755,6 +761,18 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     const int64_t unit_frames = 128LL << sub_shift;
     const int64_t n_pairs = (nfr + unit_frames - 1) / unit_frames;  // (lists: per pair of tiles or per tile)
     if (subset && n_tiles > 1) {
+      for (const AlignPrepCache::TileLists &L : pc.lists)  // identical batch: the lists of this launch are still on the device
+        if (prep_hit && lists_cacheable && L.u0 == u0 && L.u1 == u1 && L.shift == sub_shift && L.first_word == list_used && L.base == m->w_al_tiles.p) {
+          sub.off = m->w_al_tiles.as<int32_t>() + L.first_word;
+          sub.tiles = sub.off + L.n_off;
+          sub.shift = sub_shift;
+          list_used += L.n_off + L.n_list;
+          bool used = false;
+          KHG_TRY(dense_block(m, d_f, nfr, acoustic_scale, KHG_PDF_MAJOR, d_dst, ld, &sub, &used));
+          units_all += n_pairs * n_tiles;
+          units_done += used ? (int64_t)L.n_list : n_pairs * n_tiles;
+          return KHG_OK;
+        }
       // tiles of every utterance (bitmap), then per frame-tile pair the union over the utterances it overlaps
       const int words = (n_tiles + 63) / 64;
       std::vector<uint64_t> ubits((size_t)(u1 - u0) * words, 0);
@@ -789,6 +807,13 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
         return dense_block(m, d_f, nfr, acoustic_scale, KHG_PDF_MAJOR, d_dst, ld);
       }
       int32_t *d_off = m->w_al_tiles.as<int32_t>() + list_used, *d_tiles = d_off + off.size();
+      {  // what these words held before is gone (lists of another form, or of a buffer that has moved)
+        const size_t w0 = list_used, w1 = list_used + off.size() + tiles.size();
+        pc.lists.erase(std::remove_if(pc.lists.begin(), pc.lists.end(), [&](const AlignPrepCache::TileLists &L) {
+          return L.base != m->w_al_tiles.p || (L.first_word < w1 && w0 < L.first_word + L.n_off + L.n_list);
+        }), pc.lists.end());
+      }
+      if (lists_cacheable) pc.lists.push_back({u0, u1, sub_shift, list_used, off.size(), tiles.size(), m->w_al_tiles.p});
       list_used += off.size() + tiles.size();
       KHG_CUDA_TRY(cudaMemcpyAsync(d_off, off.data(), 4 * off.size(), cudaMemcpyHostToDevice, st));
       KHG_CUDA_TRY(cudaMemcpyAsync(d_tiles, tiles.data(), 4 * tiles.size(), cudaMemcpyHostToDevice, st));

@@ -348,6 +348,18 @@ def test_align_batch_computes_only_the_tiles_the_graphs_need(monkeypatch):
     out, ll, gb, pdf_ids = _run(dm, graphs, feats, t2p, 1.0, 10.0, 40.0, device_feats=True)
     frac = A.lib().khg_align_last_tile_fraction()
     assert 0.0 < frac < 0.8, frac
+    # the same batch again: the graph preparation AND the tile lists of the dense launches are reused from the device
+    out_again, _, _, pdf_again = _run(dm, graphs, feats, t2p, 1.0, 10.0, 40.0, device_feats=True)
+    assert A.lib().khg_align_last_prep_cached() == 1 and A.lib().khg_align_last_tile_fraction() == frac
+    assert np.array_equal(out["alignment"], out_again["alignment"]) and np.array_equal(pdf_ids, pdf_again)
+    np.testing.assert_array_equal(out["like"], out_again["like"])
+    # tile lists per pair of frame tiles (CTA pairs sharing the operand stream) instead of per tile: more units, same answer
+    monkeypatch.setenv("KHG_ALIGN_SUBSET_SHIFT", "1")
+    out_pair, _, _, pdf_pair = _run(dm, graphs, feats, t2p, 1.0, 10.0, 40.0, device_feats=True)
+    assert frac <= A.lib().khg_align_last_tile_fraction() < 1.0
+    assert np.array_equal(out["alignment"], out_pair["alignment"]) and np.array_equal(pdf_ids, pdf_pair)
+    np.testing.assert_array_equal(out["like"], out_pair["like"])
+    monkeypatch.delenv("KHG_ALIGN_SUBSET_SHIFT")
     monkeypatch.setenv("KHG_ALIGN_TILE_SUBSET", "0")
     out_full, _, _, pdf_full = _run(dm, graphs, feats, t2p, 1.0, 10.0, 40.0, device_feats=True)
     assert A.lib().khg_align_last_tile_fraction() == 1.0
