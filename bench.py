@@ -380,6 +380,19 @@ def run_workloads(torch, args, dev, local, peaks, tf32_peak, dm4, feats4, pdf4, 
         got = st.download()
     dt = (time.perf_counter() - t0) / e_reps
     assert abs(got["tot_frames"] - ne) < 0.5, (got["tot_frames"], ne)
+    # and from PAGEABLE host memory (a numpy array): the library stages it through pinned slots with several host threads
+    pf, pp = hfn.copy(), hpn.copy()
+    st.acc_stats_ali(pf, pp, want_total=True)
+    t0 = time.perf_counter()
+    for _ in range(e_reps):
+        st.zero()
+        st.acc_stats_ali(pf, pp, want_total=True)
+        got_p = st.download()
+    dt_p = (time.perf_counter() - t0) / e_reps
+    assert abs(got_p["tot_frames"] - ne) < 0.5
+    out["w_aligned_c4"]["e2e_pageable_host_feats"] = {"value": ne / dt_p, "unit": "frames/s", "ms_per_call": dt_p * 1e3,
+                                                      "h2d_GBps": ne * (4 * D4 + 4) / dt_p / 1e9}
+    del pf, pp
     out["w_aligned_c4"]["e2e_host_feats"] = {"value": ne / dt, "unit": "frames/s", "frames_per_call": ne, "ms_per_call": dt * 1e3,
                                              "h2d_bytes_per_call": int(ne * (4 * D4 + 4)), "d2h_bytes_per_call": int(st.as_torch().numel() * 8),
                                              "h2d_GBps": ne * (4 * D4 + 4) / dt / 1e9}

@@ -48,6 +48,7 @@
 
 #include <math_constants.h>
 
+#include "khg_host_pool.h"
 #include "khg_internal.h"
 
 namespace khg {
@@ -477,91 +478,6 @@ __global__ void gather_ll_kernel(AlignDev g, const int2 *__restrict__ list, cons
   }
 }
 
-// A small persistent pool for the host passes over the graphs (a call makes ~10 of them; creating 16 threads each
-// time costs more than the passes themselves at C5 sizes).  One job at a time (callers are serialised by a mutex).
-class HostPool {
- public:
-  static HostPool &get() {
-    static HostPool p;
-    return p;
-  }
-  int workers() const { return (int)th_.size() + 1; }
-  // runs job(w) for w = 0 .. n_workers-1 (the caller is worker 0) and returns when all are done
-  void run(int n_workers, const std::function<void(int)> &job) {
-    std::lock_guard<std::mutex> one(call_mu_);
-    n_workers = std::max(1, std::min(n_workers, workers()));
-    if (getpid() != pid_) n_workers = 1;  // (a forked child has no worker threads: the caller does everything)
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      job_ = &job;
-      active_ = n_workers - 1;
-      pending_ = n_workers - 1;
-      ++epoch_;
-    }
-    cv_.notify_all();
-    job(0);
-    std::unique_lock<std::mutex> lk(mu_);
-    done_.wait(lk, [&] { return pending_ == 0; });
-    job_ = nullptr;
-  }
-
- private:
-  HostPool() {
-    const int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
-    for (int w = 1; w < nt; ++w) th_.emplace_back([this, w] { loop(w); });
-    pid_ = getpid();
-  }
-  ~HostPool() {
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      stop_ = true;
-      ++epoch_;
-    }
-    cv_.notify_all();
-    for (auto &t : th_) t.join();
-  }
-  void loop(int w) {
-    uint64_t seen = 0;
-    for (;;) {
-      const std::function<void(int)> *job = nullptr;
-      {
-        std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return epoch_ != seen; });
-        seen = epoch_;
-        if (stop_) return;
-        if (w <= active_) job = job_;
-      }
-      if (job) {
-        (*job)(w);
-        std::lock_guard<std::mutex> lk(mu_);
-        if (--pending_ == 0) done_.notify_one();
-      }
-    }
-  }
-  std::vector<std::thread> th_;
-  std::mutex mu_, call_mu_;
-  std::condition_variable cv_, done_;
-  const std::function<void(int)> *job_ = nullptr;
-  int active_ = 0, pending_ = 0;
-  uint64_t epoch_ = 0;
-  bool stop_ = false;
-  pid_t pid_ = 0;
-};
-
-template <class F>
-static void parallel_for(int n, F f, int min_parallel = 64) {
-  int nt = std::min(HostPool::get().workers(), std::max(1, n));
-  if (n < min_parallel) nt = 1;
-  if (nt == 1) {
-    for (int i = 0; i < n; ++i) f(i, 0);
-    return;
-  }
-  // (items are handed out dynamically: in a forked child the caller alone runs, and takes them all)
-  std::atomic<int> next{0};
-  HostPool::get().run(nt, [&](int w) {
-    for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) f(i, w);
-  });
-}
 
 
 // What the host preparation of khg_align_batch produces and later phases need, kept on the model between calls: the
@@ -740,7 +656,7 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     *d_f = feats + (gb->frame_offsets[0] + f0) * D;
     if (nfr > 0 && feats_loc == KHG_HOST) {
       KHG_TRY(m->w_feats.reserve(sizeof(float) * (size_t)nfr * D));
-      KHG_CUDA_TRY(cudaMemcpyAsync(m->w_feats.p, *d_f, sizeof(float) * (size_t)nfr * D, cudaMemcpyHostToDevice, st));
+      KHG_TRY(h2d_copy(m, m->w_feats.p, *d_f, sizeof(float) * (size_t)nfr * D));  // (pageable features: staged by several threads)
       *d_f = m->w_feats.as<float>();
     }
     return KHG_OK;
@@ -871,7 +787,11 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     eps_deg.assign((size_t)S_all, 0);
   }
   const int n_workers = 16;
-  std::vector<std::vector<int32_t>> stamp(n_workers, std::vector<int32_t>(P, -1)), lidx(n_workers, std::vector<int32_t>(P, 0));
+  std::vector<std::vector<int32_t>> stamp, lidx;  // per worker: which utterance saw a pdf last, and its local index there
+  if (!prep_hit) {
+    stamp.assign(n_workers, std::vector<int32_t>(P, -1));
+    lidx.assign(n_workers, std::vector<int32_t>(P, 0));
+  }
   auto first_pass = [&](int u, int w) {
     const int32_t s0 = gb->state_offsets[u], s1 = gb->state_offsets[u + 1], S = s1 - s0;
     UttDesc &d = desc[u];

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "khg_host_pool.h"
 #include "khg_internal.h"
 #include "khg_kernels.cuh"
 
@@ -65,12 +66,57 @@ static khg_status sync_check(khg_model *m) {
 
 // Returns a device pointer for a caller buffer: the buffer itself (KHG_DEVICE) or
 // a staged copy (KHG_HOST).
+// Host -> device copy on the model's stream.  A large PAGEABLE source (a numpy array: what a Python caller hands in)
+// goes through two pinned slots filled by the pool's threads — the driver's own staging of pageable memory is one
+// thread at 6-12 GB/s — the copy of slice i + 1 into its slot running under the DMA of slice i.  Pinned sources and
+// small buffers are one cudaMemcpyAsync.  KHG_STAGE_THREADS=1 keeps the plain copy.
+khg_status h2d_copy(khg_model *m, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return KHG_OK;
+  constexpr size_t kSlice = 16u << 20;
+  int threads = std::min(8, HostPool::get().workers());
+  if (const char *e = getenv("KHG_STAGE_THREADS")) threads = std::max(1, std::min(threads, atoi(e)));
+  bool pageable = false;
+  if (bytes >= 2 * kSlice && threads > 1) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, src) != cudaSuccess) {
+      (void)cudaGetLastError();
+      pageable = true;
+    } else {
+      pageable = at.type == cudaMemoryTypeUnregistered;
+    }
+  }
+  if (!pageable) {
+    KHG_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, m->stream));
+    return KHG_OK;
+  }
+  for (int i = 0; i < 2; ++i) {
+    m->pin_stage[i].pinned = true;
+    KHG_TRY(m->pin_stage[i].reserve(kSlice));
+    if (!m->ev_stage[i]) KHG_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_stage[i], cudaEventDisableTiming));
+  }
+  const size_t n_slices = (bytes + kSlice - 1) / kSlice;
+  for (size_t i = 0; i < n_slices; ++i) {
+    const int b = (int)(i & 1);
+    const size_t off = i * kSlice, n = std::min(kSlice, bytes - off);
+    if (i >= 2) KHG_CUDA_TRY(cudaEventSynchronize(m->ev_stage[b]));  // the DMA out of slot b (slice i - 2) has finished
+    const char *s0 = static_cast<const char *>(src) + off;
+    char *p0 = m->pin_stage[b].as<char>();
+    parallel_memcpy(p0, s0, n, threads);
+    KHG_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(dst) + off, p0, n, cudaMemcpyHostToDevice, m->stream));
+    KHG_CUDA_TRY(cudaEventRecord(m->ev_stage[b], m->stream));
+  }
+  // the slots are reused by the next call: wait for the last two DMAs (the data is then on the device; later work on
+  // the stream is ordered behind it anyway)
+  for (int b = 0; b < 2; ++b) KHG_CUDA_TRY(cudaEventSynchronize(m->ev_stage[b]));
+  return KHG_OK;
+}
+
 template <class T>
 static khg_status stage_in(khg_model *m, Buf &buf, const T *src, size_t count, int loc, const T **dev) {
   if (src == nullptr) { *dev = nullptr; return KHG_OK; }
   if (loc == KHG_DEVICE) { *dev = src; return KHG_OK; }
   KHG_TRY(buf.reserve(count * sizeof(T)));
-  KHG_CUDA_TRY(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, m->stream));
+  KHG_TRY(h2d_copy(m, buf.p, src, count * sizeof(T)));
   *dev = buf.as<T>();
   return KHG_OK;
 }
@@ -297,6 +343,8 @@ void khg_model_destroy(khg_model *m) {
   for (int i = 0; i < 2; ++i) {
     m->pin_feats[i].release(); m->pin_ids[i].release(); m->pin_wts[i].release();
     m->w_efeats[i].release(); m->w_eids[i].release(); m->w_ewts[i].release();
+    m->pin_stage[i].release();
+    if (m->ev_stage[i]) cudaEventDestroy(m->ev_stage[i]);
     if (m->ev_copy[i]) cudaEventDestroy(m->ev_copy[i]);
     if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
   }
@@ -1059,7 +1107,7 @@ khg_status khg_estep(khg_model *m, khg_stats *s, const float *feats, int64_t T, 
       float *d_f = m->w_efeats[h].as<float>() + k * chunk_frames * D;
       int32_t *d_i = m->w_eids[h].as<int32_t>() + k * chunk_frames;
       const void *src_f = feats + t0 * D, *src_i = pdf_ids + t0;
-      if (!direct_f) src_f = std::memcpy(m->pin_feats[b].p, src_f, sizeof(float) * n * D);
+      if (!direct_f) src_f = parallel_memcpy(m->pin_feats[b].p, src_f, sizeof(float) * n * D, 4);
       if (!direct_i) src_i = std::memcpy(m->pin_ids[b].p, src_i, sizeof(int32_t) * n);
       KHG_CUDA_TRY(cudaMemcpyAsync(d_f, src_f, sizeof(float) * n * D, cudaMemcpyHostToDevice, m->copy_stream));
       KHG_CUDA_TRY(cudaMemcpyAsync(d_i, src_i, sizeof(int32_t) * n, cudaMemcpyHostToDevice, m->copy_stream));

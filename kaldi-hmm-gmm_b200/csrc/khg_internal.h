@@ -207,6 +207,9 @@ struct khg_model {
   khg::Buf w_al_xlist, w_al_xll;                                             // ... its exact host pass: flagged list, likelihood rows
   khg::Buf pin_feats[2], pin_ids[2], pin_wts[2];       // pinned staging for estep(HOST)
   khg::Buf w_efeats[2], w_eids[2], w_ewts[2];
+  // pinned staging of large pageable host buffers (stage_in): two slots, one event each
+  khg::Buf pin_stage[2];
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
 };
 
 struct khg_stats {
@@ -259,6 +262,8 @@ khg_status align_exact_host(const khg_graph_batch *gb, int32_t utt, const float 
 khg_status dense_block(khg_model *m, const float *d_feats, int64_t T, float scale, int layout, float *d_out, int64_t ld,
                        const TileSubset *subset = nullptr, bool *subset_used = nullptr);
 khg_status sync_and_check(khg_model *m);
+// host -> device copy on the model's stream; large pageable sources are staged through pinned slots by several threads
+khg_status h2d_copy(khg_model *m, void *dst, const void *src, size_t bytes);
 khg_status finish_model_from_device(khg_model *nm, int32_t *num_bad);
 }  // namespace khg
 

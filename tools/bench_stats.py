@@ -40,3 +40,22 @@ gbs = n * (4 * D + 4) / best / 1e9
 print(json.dumps({"workload": f"W-aligned {cfg}: D={D} P={P} G={G}, {n} frames resident in HBM", "frames_per_s": n / best,
                   "ms": best * 1e3, "algorithmic_GBps": gbs, "hbm_peak_GBps": peak, "frac_of_hbm_roof": gbs / peak,
                   "lib": os.environ.get("KHG_B200_LIB", "in-tree")}))
+
+if os.environ.get("KHG_BENCH_HOST"):
+    # the same call with HOST inputs: pageable numpy arrays (what a Python caller hands in) and pinned ones
+    import time
+
+    ne = min(n, 8_000_000)
+    hf_pin = torch.empty((ne, D), dtype=torch.float32, pin_memory=True)
+    hp_pin = torch.empty(ne, dtype=torch.int32, pin_memory=True)
+    hf_pin.copy_(feats[:ne])
+    hp_pin.copy_(pdf[:ne])
+    hf_page, hp_page = hf_pin.numpy().copy(), hp_pin.numpy().copy()
+    for name, (f, p) in (("pageable", (hf_page, hp_page)), ("pinned", (hf_pin.numpy(), hp_pin.numpy()))):
+        st.acc_stats_ali(f, p, want_total=True)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            st.acc_stats_ali(f, p, want_total=True)
+        dt = (time.perf_counter() - t0) / 3
+        print(json.dumps({"host_inputs": name, "frames_per_s": ne / dt, "ms": dt * 1e3, "h2d_GBps": ne * (4 * D + 4) / dt / 1e9,
+                          "stage_threads": os.environ.get("KHG_STAGE_THREADS", "default")}))
