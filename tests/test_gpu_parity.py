@@ -347,6 +347,38 @@ def test_estep_statistics_groups(oracle, monkeypatch):
             assert abs(tot - ref["tot_like"]) <= STATS_RTOL * abs(ref["tot_like"])
 
 
+def test_large_pageable_host_buffers_are_staged_by_the_pool(oracle, monkeypatch):
+    """A pageable host buffer of 32 MB or more (a numpy array) reaches the device through two pinned slots filled by
+    several host threads (h2d_copy); a ragged last slice, the driver's own pageable copy (KHG_STAGE_THREADS=1) and
+    device-resident inputs give the same statistics."""
+    import torch
+    from kaldi_hmm_gmm_b200 import DeviceStats
+
+    model, means, vars_ = ko.make_synthetic_model(40, 30, 240, oracle=oracle)
+    T = 330_001  # 52.8 MB of features: three full slices and a ragged one
+    feats, pdf = ko.make_synthetic_frames(model, means, vars_, T)
+    dm, _ = _device_model(model)
+    ref_st = DeviceStats(dm)
+    ref_tot = ref_st.acc_stats_ali(torch.from_numpy(feats).cuda(), torch.from_numpy(pdf).cuda(), want_total=True)
+    ref = ref_st.download()
+    for threads in (None, "1", "3"):
+        if threads is None:
+            monkeypatch.delenv("KHG_STAGE_THREADS", raising=False)
+        else:
+            monkeypatch.setenv("KHG_STAGE_THREADS", threads)
+        st = DeviceStats(dm)
+        pf = np.empty(T, np.float32)
+        tot = st.acc_stats_ali(feats, pdf, per_frame=pf, want_total=True)
+        got = st.download()
+        for k in ("occ", "mean", "var"):
+            np.testing.assert_allclose(got[k], ref[k], rtol=1e-9, atol=1e-9 * np.abs(ref[k]).max())
+        assert got["tot_frames"] == T and abs(tot - ref_tot) <= 1e-9 * abs(ref_tot)
+        assert np.isfinite(pf).all()
+    sample = slice(T - 3000, T)  # the tail of the last slice against the oracle
+    o = oracle.acc_stats_ali(model, feats[sample], pdf[sample])
+    np.testing.assert_allclose(pf[sample], o["per_frame"], rtol=LL_RTOL, atol=LL_ATOL)
+
+
 def test_large_properties(oracle):
     """Size-independent properties at a size the oracle cannot check frame by frame:
     (1) sum of occupancies == number of frames, per pdf, exactly the bucket sizes;
