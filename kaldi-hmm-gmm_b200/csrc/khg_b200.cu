@@ -111,6 +111,71 @@ khg_status h2d_copy(khg_model *m, void *dst, const void *src, size_t bytes) {
   return KHG_OK;
 }
 
+// Device -> host copy of `rows` rows of `width` bytes (pitches in bytes) on the model's stream, complete on return.
+// A large PAGEABLE destination (a fresh numpy array: every page of it still to be faulted in) is filled from two pinned
+// slots by the pool's threads while the DMA of the next band of rows runs; pinned destinations and small blocks are one
+// cudaMemcpy2DAsync + synchronize.
+khg_status d2h_copy_2d(khg_model *m, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width, size_t rows) {
+  if (width == 0 || rows == 0) return KHG_OK;
+  constexpr size_t kSlice = 16u << 20, kPiece = 1u << 20;
+  int threads = std::min(8, HostPool::get().workers());
+  if (const char *e = getenv("KHG_STAGE_THREADS")) threads = std::max(1, std::min(threads, atoi(e)));
+  bool staged = width * rows >= kSlice / 2 && width <= kSlice && threads > 1;
+  if (staged) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, dst) != cudaSuccess) (void)cudaGetLastError();
+    else staged = at.type == cudaMemoryTypeUnregistered;
+  }
+  if (!staged) {
+    KHG_CUDA_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width, rows, cudaMemcpyDeviceToHost, m->stream));
+    KHG_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return KHG_OK;
+  }
+  for (int i = 0; i < 2; ++i) {
+    m->pin_stage[i].pinned = true;
+    KHG_TRY(m->pin_stage[i].reserve(kSlice));
+    if (!m->ev_stage[i]) KHG_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_stage[i], cudaEventDisableTiming));
+  }
+  const size_t band = std::max<size_t>(1, kSlice / width), n_bands = (rows + band - 1) / band;
+  // rows r0 .. r0 + nr of a band wait densely packed in slot b: out to the destination, one piece per job
+  auto drain = [&](int b, size_t r0, size_t nr) {
+    const char *p0 = m->pin_stage[b].as<char>();
+    char *d0 = static_cast<char *>(dst) + r0 * dst_pitch;
+    const size_t per_row = (width + kPiece - 1) / kPiece;            // pieces of a long row
+    const size_t rows_per_job = std::max<size_t>(1, kPiece / width);  // short rows: several per job
+    const int n_jobs = (int)(per_row > 1 ? nr * per_row : (nr + rows_per_job - 1) / rows_per_job);
+    std::atomic<int> next{0};
+    HostPool::get().run(std::min(threads, std::max(1, n_jobs)), [&](int) {
+      for (int q = next.fetch_add(1); q < n_jobs; q = next.fetch_add(1)) {
+        if (per_row > 1) {
+          const size_t r = (size_t)q / per_row, c0 = ((size_t)q % per_row) * kPiece;
+          std::memcpy(d0 + r * dst_pitch + c0, p0 + r * width + c0, std::min(kPiece, width - c0));
+        } else {
+          const size_t ra = (size_t)q * rows_per_job, rb = std::min(nr, ra + rows_per_job);
+          if (dst_pitch == width) std::memcpy(d0 + ra * width, p0 + ra * width, (rb - ra) * width);
+          else for (size_t r = ra; r < rb; ++r) std::memcpy(d0 + r * dst_pitch, p0 + r * width, width);
+        }
+      }
+    });
+  };
+  for (size_t i = 0; i < n_bands; ++i) {
+    const int b = (int)(i & 1);
+    const size_t r0 = i * band, nr = std::min(band, rows - r0);
+    // (slot b was drained two bands ago, by this thread)
+    KHG_CUDA_TRY(cudaMemcpy2DAsync(m->pin_stage[b].p, width, static_cast<const char *>(src) + r0 * src_pitch, src_pitch, width, nr,
+                                   cudaMemcpyDeviceToHost, m->stream));
+    KHG_CUDA_TRY(cudaEventRecord(m->ev_stage[b], m->stream));
+    if (i > 0) {
+      KHG_CUDA_TRY(cudaEventSynchronize(m->ev_stage[b ^ 1]));
+      drain(b ^ 1, (i - 1) * band, band);
+    }
+  }
+  const size_t last = n_bands - 1;
+  KHG_CUDA_TRY(cudaEventSynchronize(m->ev_stage[last & 1]));
+  drain((int)(last & 1), last * band, rows - last * band);
+  return KHG_OK;
+}
+
 template <class T>
 static khg_status stage_in(khg_model *m, Buf &buf, const T *src, size_t count, int loc, const T **dev) {
   if (src == nullptr) { *dev = nullptr; return KHG_OK; }
@@ -489,9 +554,9 @@ khg_status khg_loglikes_all_pdfs(khg_model *m, const float *feats, int64_t T, in
     KHG_TRY(dense_device(m, d_f, n, scale, layout, d_o, ldd));
     if (out_loc == KHG_HOST) {
       if (layout == KHG_PDF_MAJOR)
-        KHG_CUDA_TRY(cudaMemcpy2DAsync(out + t0, sizeof(float) * ld_out, d_o, sizeof(float) * ldd, sizeof(float) * n, m->P, cudaMemcpyDeviceToHost, m->stream));
+        KHG_TRY(d2h_copy_2d(m, out + t0, sizeof(float) * ld_out, d_o, sizeof(float) * ldd, sizeof(float) * n, m->P));
       else
-        KHG_CUDA_TRY(cudaMemcpy2DAsync(out + t0 * ld_out, sizeof(float) * ld_out, d_o, sizeof(float) * ldd, sizeof(float) * m->P, n, cudaMemcpyDeviceToHost, m->stream));
+        KHG_TRY(d2h_copy_2d(m, out + t0 * ld_out, sizeof(float) * ld_out, d_o, sizeof(float) * ldd, sizeof(float) * m->P, n));
     }
     KHG_TRY(sync_check(m));
   }

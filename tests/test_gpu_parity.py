@@ -379,6 +379,40 @@ def test_large_pageable_host_buffers_are_staged_by_the_pool(oracle, monkeypatch)
     np.testing.assert_allclose(pf[sample], o["per_frame"], rtol=LL_RTOL, atol=LL_ATOL)
 
 
+def test_dense_block_to_large_pageable_host_outputs(oracle, monkeypatch):
+    """khg_loglikes_all_pdfs into a pageable host array of several staging bands (d2h_copy_2d: DMA into two pinned slots,
+    the pool's threads move the rows out): both layouts, an output wider than the block (ld_out > row length), against
+    the device-resident output of the same call bit for bit; the driver's own copy (KHG_STAGE_THREADS=1) as well."""
+    import torch
+    from kaldi_hmm_gmm_b200 import _cabi as A
+
+    model, means, vars_ = ko.make_synthetic_model(24, 600, 3000, oracle=oracle)
+    T = 21_003
+    feats, _ = ko.make_synthetic_frames(model, means, vars_, T)
+    dm, _ = _device_model(model)
+    dfe = torch.from_numpy(feats).cuda()
+    ref_fm = dm.loglikes_all_pdfs(dfe, layout=A.KHG_FRAME_MAJOR).cpu().numpy()
+    ref_pm = dm.loglikes_all_pdfs(dfe, layout=A.KHG_PDF_MAJOR).cpu().numpy()
+    assert np.array_equal(ref_fm, ref_pm.T)
+    P = model.num_pdfs
+    for threads in (None, "1"):
+        if threads is None:
+            monkeypatch.delenv("KHG_STAGE_THREADS", raising=False)
+        else:
+            monkeypatch.setenv("KHG_STAGE_THREADS", threads)
+        assert np.array_equal(dm.loglikes_all_pdfs(feats, layout=A.KHG_FRAME_MAJOR), ref_fm)
+        assert np.array_equal(dm.loglikes_all_pdfs(feats, layout=A.KHG_PDF_MAJOR), ref_pm)
+        wide = np.full((T, P + 5), -7.0, np.float32)
+        dm.loglikes_all_pdfs(feats, layout=A.KHG_FRAME_MAJOR, out=wide)
+        assert np.array_equal(wide[:, :P], ref_fm) and (wide[:, P:] == -7.0).all()
+        wide = np.full((P, T + 9), -7.0, np.float32)
+        dm.loglikes_all_pdfs(feats, layout=A.KHG_PDF_MAJOR, out=wide)
+        assert np.array_equal(wide[:, :T], ref_pm) and (wide[:, T:] == -7.0).all()
+    sample = slice(T - 500, T)
+    o, _ = oracle.loglikes_all_pdfs(model, feats[sample])
+    _assert_ll(ref_fm[sample], o)
+
+
 def test_large_properties(oracle):
     """Size-independent properties at a size the oracle cannot check frame by frame:
     (1) sum of occupancies == number of frames, per pdf, exactly the bucket sizes;
