@@ -761,7 +761,17 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
   // launched right away and runs under the whole host preparation
   const float *d_f0 = nullptr;
   if (timing) cudaEventRecord(ev[0], st);
-  KHG_TRY(stage_feats(chunk_start[0], chunk_start[1], &d_f0));
+  // host features of the first chunk in subset mode go to the device group by group on the copy stream (below): the
+  // copy of a group runs under the dense kernel of the previous one
+  const bool grouped_copy = want_subset && feats_loc == KHG_HOST && T_all > 0;
+  if (grouped_copy) {
+    const int64_t nfr0 = gb->frame_offsets[chunk_start[1]] - gb->frame_offsets[chunk_start[0]];
+    KHG_TRY(m->w_feats.reserve(sizeof(float) * (size_t)std::max<int64_t>(nfr0, 1) * D));
+    KHG_TRY(ensure_copy_stream(m));
+    d_f0 = m->w_feats.as<float>();
+  } else {
+    KHG_TRY(stage_feats(chunk_start[0], chunk_start[1], &d_f0));
+  }
   if (!want_subset) {
     KHG_TRY(run_dense(chunk_start[0], chunk_start[1], d_f0, false));
     if (timing) cudaEventRecord(ev[1], st);
@@ -840,6 +850,16 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
       if (gidx + 1 < n_groups) {
         gb_ = ga;
         while (gb_ < c1 && gb->frame_offsets[gb_] - fr0 < frc * (gidx + 1) / n_groups) ++gb_;
+      }
+      if (grouped_copy && gb_ > ga) {
+        const int64_t f_a = gb->frame_offsets[ga] - fr0, n_g = gb->frame_offsets[gb_] - gb->frame_offsets[ga];
+        if (gidx == 0) {  // w_feats may still be read by an earlier call's kernels on the model stream
+          KHG_CUDA_TRY(cudaEventRecord(m->ev_done[0], st));
+          KHG_CUDA_TRY(cudaStreamWaitEvent(m->copy_stream, m->ev_done[0], 0));
+        }
+        KHG_TRY(h2d_copy(m, m->w_feats.as<float>() + f_a * D, feats + gb->frame_offsets[ga] * D, sizeof(float) * (size_t)n_g * D, m->copy_stream));
+        KHG_CUDA_TRY(cudaEventRecord(m->ev_copy[gidx & 1], m->copy_stream));
+        KHG_CUDA_TRY(cudaStreamWaitEvent(st, m->ev_copy[gidx & 1], 0));
       }
       if (!prep_hit) parallel_for(gb_ - ga, [&](int i, int w) { first_pass(ga + i, w); });
       KHG_TRY(run_dense(ga, gb_, d_f0 + (gb->frame_offsets[ga] - fr0) * D, true, gb->frame_offsets[ga] - fr0));

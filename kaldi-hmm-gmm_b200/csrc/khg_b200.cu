@@ -70,8 +70,9 @@ static khg_status sync_check(khg_model *m) {
 // goes through two pinned slots filled by the pool's threads — the driver's own staging of pageable memory is one
 // thread at 6-12 GB/s — the copy of slice i + 1 into its slot running under the DMA of slice i.  Pinned sources and
 // small buffers are one cudaMemcpyAsync.  KHG_STAGE_THREADS=1 keeps the plain copy.
-khg_status h2d_copy(khg_model *m, void *dst, const void *src, size_t bytes) {
+khg_status h2d_copy(khg_model *m, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
   if (bytes == 0) return KHG_OK;
+  if (!stream) stream = m->stream;
   constexpr size_t kSlice = 16u << 20;
   int threads = std::min(8, HostPool::get().workers());
   if (const char *e = getenv("KHG_STAGE_THREADS")) threads = std::max(1, std::min(threads, atoi(e)));
@@ -86,7 +87,7 @@ khg_status h2d_copy(khg_model *m, void *dst, const void *src, size_t bytes) {
     }
   }
   if (!pageable) {
-    KHG_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, m->stream));
+    KHG_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
     return KHG_OK;
   }
   for (int i = 0; i < 2; ++i) {
@@ -102,8 +103,8 @@ khg_status h2d_copy(khg_model *m, void *dst, const void *src, size_t bytes) {
     const char *s0 = static_cast<const char *>(src) + off;
     char *p0 = m->pin_stage[b].as<char>();
     parallel_memcpy(p0, s0, n, threads);
-    KHG_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(dst) + off, p0, n, cudaMemcpyHostToDevice, m->stream));
-    KHG_CUDA_TRY(cudaEventRecord(m->ev_stage[b], m->stream));
+    KHG_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(dst) + off, p0, n, cudaMemcpyHostToDevice, stream));
+    KHG_CUDA_TRY(cudaEventRecord(m->ev_stage[b], stream));
   }
   // the slots are reused by the next call: wait for the last two DMAs (the data is then on the device; later work on
   // the stream is ordered behind it anyway)
@@ -594,7 +595,7 @@ khg_status khg_loglikes_pdf_subset(khg_model *m, const float *feats, int64_t T, 
     ++g_launch_count;
     KHG_CUDA_TRY(cudaGetLastError());
     if (out_loc == KHG_HOST)
-      KHG_CUDA_TRY(cudaMemcpy2DAsync(out + t0, sizeof(float) * ld_out, d_o, sizeof(float) * ldo, sizeof(float) * n, n_subset, cudaMemcpyDeviceToHost, st));
+      KHG_TRY(d2h_copy_2d(m, out + t0, sizeof(float) * ld_out, d_o, sizeof(float) * ldo, sizeof(float) * n, n_subset));
     KHG_TRY(sync_check(m));
   }
   return KHG_OK;
@@ -1083,16 +1084,7 @@ khg_status khg_mle_update(khg_model *m, const khg_stats *s, const khg_mle_option
 }
 
 // ------------------------------------------------------------------ E-step --
-static khg_status estep_init_streams(khg_model *m) {
-  if (m->copy_stream) return KHG_OK;
-  KHG_CUDA_TRY(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
-    KHG_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_copy[i], cudaEventDisableTiming));
-    KHG_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
-    m->pin_feats[i].pinned = m->pin_ids[i].pinned = m->pin_wts[i].pinned = true;
-  }
-  return KHG_OK;
-}
+static khg_status estep_init_streams(khg_model *m) { return khg::ensure_copy_stream(m); }
 
 khg_status khg_estep(khg_model *m, khg_stats *s, const float *feats, int64_t T, int32_t loc,
                      const int32_t *pdf_ids, const float *frame_weights, float *loglikes_out,
@@ -1240,4 +1232,14 @@ khg_status dense_block(khg_model *m, const float *d_feats, int64_t T, float scal
   return dense_device(m, d_feats, T, scale, layout, d_out, ld, subset, subset_used);
 }
 khg_status sync_and_check(khg_model *m) { return sync_check(m); }
+khg_status ensure_copy_stream(khg_model *m) {
+  if (m->copy_stream) return KHG_OK;
+  KHG_CUDA_TRY(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    KHG_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_copy[i], cudaEventDisableTiming));
+    KHG_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
+    m->pin_feats[i].pinned = m->pin_ids[i].pinned = m->pin_wts[i].pinned = true;
+  }
+  return KHG_OK;
+}
 }  // namespace khg

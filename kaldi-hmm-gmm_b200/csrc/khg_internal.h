@@ -263,7 +263,9 @@ khg_status dense_block(khg_model *m, const float *d_feats, int64_t T, float scal
                        const TileSubset *subset = nullptr, bool *subset_used = nullptr);
 khg_status sync_and_check(khg_model *m);
 // host -> device copy on the model's stream; large pageable sources are staged through pinned slots by several threads
-khg_status h2d_copy(khg_model *m, void *dst, const void *src, size_t bytes);
+khg_status h2d_copy(khg_model *m, void *dst, const void *src, size_t bytes, cudaStream_t stream = nullptr);  // (nullptr: the model's stream)
+// the model's second stream (H2D copies that run under compute) and its events
+khg_status ensure_copy_stream(khg_model *m);
 khg_status finish_model_from_device(khg_model *nm, int32_t *num_bad);
 }  // namespace khg
 
