@@ -661,7 +661,6 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     }
     return KHG_OK;
   };
-  std::vector<std::vector<int32_t>> list_keep;  // host copies of the uploaded lists (alive until the call returns)
   size_t list_used = 0;                          // int32 words of w_al_tiles handed out so far
   auto run_dense = [&](int u0, int u1, const float *d_f, bool subset, int64_t col = 0) -> khg_status {
     const int64_t nfr = gb->frame_offsets[u1] - gb->frame_offsets[u0];
@@ -731,11 +730,14 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
       }
       if (lists_cacheable) pc.lists.push_back({u0, u1, sub_shift, list_used, off.size(), tiles.size(), m->w_al_tiles.p});
       list_used += off.size() + tiles.size();
-      KHG_CUDA_TRY(cudaMemcpyAsync(d_off, off.data(), 4 * off.size(), cudaMemcpyHostToDevice, st));
-      KHG_CUDA_TRY(cudaMemcpyAsync(d_tiles, tiles.data(), 4 * tiles.size(), cudaMemcpyHostToDevice, st));
+      {  // through the pinned image: a copy from pageable memory would block the host until the dense kernel of the
+         // previous group, running on this stream, has finished — and with it the host pass that should run under it
+        int32_t *h = m->pin_al_tiles.as<int32_t>() + (d_off - m->w_al_tiles.as<int32_t>());
+        std::memcpy(h, off.data(), 4 * off.size());
+        std::memcpy(h + off.size(), tiles.data(), 4 * tiles.size());
+        KHG_CUDA_TRY(cudaMemcpyAsync(d_off, h, 4 * (off.size() + tiles.size()), cudaMemcpyHostToDevice, st));
+      }
       const int64_t n_list = (int64_t)tiles.size();
-      list_keep.push_back(std::move(off));
-      list_keep.push_back(std::move(tiles));
       sub.off = d_off;
       sub.tiles = d_tiles;
       sub.shift = sub_shift;
@@ -756,7 +758,11 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     return run_dense(u0, u1, d_f, subset);
   };
   if (want_subset && m->tc.ready)  // worst case: every pair of frame tiles lists every model tile (+ the offsets, per launch)
+  {
     KHG_TRY(m->w_al_tiles.reserve(4 * ((size_t)((chunk_frames_max + 127) / 128 + 16) * (size_t)(tc_num_tiles(m) + 1) + 64)));
+    m->pin_al_tiles.pinned = true;
+    KHG_TRY(m->pin_al_tiles.reserve(m->w_al_tiles.cap));
+  }
   // with the subset the kernel of the first chunk needs the graphs' pdf lists (first host pass below); without it, it is
   // launched right away and runs under the whole host preparation
   const float *d_f0 = nullptr;
@@ -816,6 +822,12 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
     if (d.T < 0 || S < 0 || d.start >= S) { bad[u] = 1; return; }
     auto &st_ = stamp[w];
     auto &li = lidx[w];
+    // (per-utterance counters stay local until the end: neighbouring utterances are other threads' work, and a counter
+    // bumped per arc in a shared array bounces its cache line between them)
+    int32_t ne = 0, nep = 0, neg = 0;
+    std::vector<int32_t> &up_ = updf[u];
+    up_.clear();
+    up_.reserve((size_t)S);
     for (int32_t s = s0; s < s1; ++s) {
       if (gb->arc_offsets[s + 1] < gb->arc_offsets[s]) { bad[u] = 1; return; }
       for (int32_t a = gb->arc_offsets[s]; a < gb->arc_offsets[s + 1]; ++a) {
@@ -823,19 +835,22 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
         if (ns < 0 || ns >= S || il < 0 || il >= n_tids) { bad[u] = 1; return; }
         arc_src[a] = s - s0;
         if (il == 0) {
-          if (gb->arc_weight[a] < 0.f) neg_eps[u] = 1;  // the exactness certificate assumes epsilon costs >= 0
-          ++n_eps[u];
+          if (gb->arc_weight[a] < 0.f) neg = 1;  // the exactness certificate assumes epsilon costs >= 0
+          ++nep;
           ++eps_deg[s0 + ns];
         } else {
-          ++n_emit[u];
+          ++ne;
           ++in_off[(size_t)s0 + ns + 1];
           const int32_t pdf = tid2pdf[il];
-          if (st_[pdf] != u) { st_[pdf] = u; li[pdf] = (int32_t)updf[u].size(); updf[u].push_back(pdf); }
+          if (st_[pdf] != u) { st_[pdf] = u; li[pdf] = (int32_t)up_.size(); up_.push_back(pdf); }
           arc_lp[a] = li[pdf];
         }
       }
     }
-    d.n_pdf = (int32_t)updf[u].size();
+    n_emit[u] = ne;
+    n_eps[u] = nep;
+    neg_eps[u] = neg;
+    d.n_pdf = (int32_t)up_.size();
   };
   if (want_subset) {
     // the first chunk in groups of utterances: the dense kernel of a group is launched as soon as the group's pdf
@@ -861,8 +876,11 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
         KHG_CUDA_TRY(cudaEventRecord(m->ev_copy[gidx & 1], m->copy_stream));
         KHG_CUDA_TRY(cudaStreamWaitEvent(st, m->ev_copy[gidx & 1], 0));
       }
+      const double tg0 = now();
       if (!prep_hit) parallel_for(gb_ - ga, [&](int i, int w) { first_pass(ga + i, w); });
+      const double tg1 = now();
       KHG_TRY(run_dense(ga, gb_, d_f0 + (gb->frame_offsets[ga] - fr0) * D, true, gb->frame_offsets[ga] - fr0));
+      if (timing) fprintf(stderr, "  group %d: first pass %.2f ms, lists + launch %.2f ms\n", gidx, tg1 - tg0, now() - tg1);
       ga = gb_;
     }
     if (timing) cudaEventRecord(ev[1], st);
@@ -942,8 +960,12 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
          o_poff = o_out + al(sizeof(UttOut) * U), o_end = o_poff + al(8 * ((size_t)U + 1));
   KHG_TRY(m->w_al_graph.reserve(o_end));
   unsigned char *gbase = m->w_al_graph.as<unsigned char>();
-  auto up = [&](size_t off, const void *src, size_t bytes) -> cudaError_t {
-    return bytes ? cudaMemcpyAsync(gbase + off, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+  // (on the copy stream: queued on the model's stream the copies — from pageable vectors — would wait behind the dense
+  // kernel of the first chunk, and the host with them; the search waits for ev_copy[0] below)
+  KHG_TRY(ensure_copy_stream(m));
+  cudaStream_t up_st = m->copy_stream;
+  auto up = [&](size_t off, const void *src, size_t bytes) -> khg_status {
+    return h2d_copy(m, gbase + off, src, bytes, up_st);  // (the arc arrays are a few MB each: staged by the pool's threads)
   };
 
   if (!prep_hit) {
@@ -956,19 +978,21 @@ extern "C" khg_status khg_align_batch(khg_model *m, const khg_graph_batch *gb, c
       return (int64_t)desc[u0 + a].T * desc[u0 + a].S > (int64_t)desc[u0 + b].T * desc[u0 + b].S;
     });
   }
-  KHG_CUDA_TRY(up(o_desc, desc.data(), sizeof(UttDesc) * U));
-  KHG_CUDA_TRY(up(o_inoff, in_off.data(), 4 * in_off.size()));
-  KHG_CUDA_TRY(up(o_in, in_arcs.data(), 16 * in_arcs.size()));
-  KHG_CUDA_TRY(up(o_eds, ed_state.data(), 4 * ed_state.size()));
-  KHG_CUDA_TRY(up(o_edo, ed_off.data(), 4 * ed_off.size()));
-  KHG_CUDA_TRY(up(o_ea, e_arcs.data(), 16 * e_arcs.size()));
-  KHG_CUDA_TRY(up(o_fin, gb->final_cost, 4 * (size_t)S_all));
-  KHG_CUDA_TRY(up(o_src, arc_src.data(), 4 * (size_t)A_all));
-  KHG_CUDA_TRY(up(o_il, gb->arc_ilabel, 4 * (size_t)A_all));
-  KHG_CUDA_TRY(up(o_w, gb->arc_weight, 4 * (size_t)A_all));
-  KHG_CUDA_TRY(up(o_pdf, utt_pdfs.data(), 4 * utt_pdfs.size()));
-  KHG_CUDA_TRY(up(o_t2p, tid2pdf, 4 * (size_t)n_tids));
-  KHG_CUDA_TRY(up(o_ord, order.data(), 4 * (size_t)U));
+  KHG_TRY(up(o_desc, desc.data(), sizeof(UttDesc) * U));
+  KHG_TRY(up(o_inoff, in_off.data(), 4 * in_off.size()));
+  KHG_TRY(up(o_in, in_arcs.data(), 16 * in_arcs.size()));
+  KHG_TRY(up(o_eds, ed_state.data(), 4 * ed_state.size()));
+  KHG_TRY(up(o_edo, ed_off.data(), 4 * ed_off.size()));
+  KHG_TRY(up(o_ea, e_arcs.data(), 16 * e_arcs.size()));
+  KHG_TRY(up(o_fin, gb->final_cost, 4 * (size_t)S_all));
+  KHG_TRY(up(o_src, arc_src.data(), 4 * (size_t)A_all));
+  KHG_TRY(up(o_il, gb->arc_ilabel, 4 * (size_t)A_all));
+  KHG_TRY(up(o_w, gb->arc_weight, 4 * (size_t)A_all));
+  KHG_TRY(up(o_pdf, utt_pdfs.data(), 4 * utt_pdfs.size()));
+  KHG_TRY(up(o_t2p, tid2pdf, 4 * (size_t)n_tids));
+  KHG_TRY(up(o_ord, order.data(), 4 * (size_t)U));
+  KHG_CUDA_TRY(cudaEventRecord(m->ev_copy[0], up_st));
+  KHG_CUDA_TRY(cudaStreamWaitEvent(st, m->ev_copy[0], 0));
   }  // !prep_hit: the device copy of an identical batch is still in w_al_graph
   pc.valid = true;
   t_mark[4] = now();

@@ -77,7 +77,7 @@ khg_status h2d_copy(khg_model *m, void *dst, const void *src, size_t bytes, cuda
   int threads = std::min(8, HostPool::get().workers());
   if (const char *e = getenv("KHG_STAGE_THREADS")) threads = std::max(1, std::min(threads, atoi(e)));
   bool pageable = false;
-  if (bytes >= 2 * kSlice && threads > 1) {
+  if (bytes >= kSlice / 4 && threads > 1) {  // (4 MB: below that the driver's own staging is as fast)
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, src) != cudaSuccess) {
       (void)cudaGetLastError();
@@ -404,7 +404,7 @@ void khg_model_destroy(khg_model *m) {
   for (Buf *b : {&m->w_feats, &m->w_ids, &m->w_wts, &m->w_out, &m->w_pf, &m->w_keys, &m->w_vals_in,
                  &m->w_vals_out, &m->w_cub, &m->w_starts, &m->w_item_start, &m->w_tot, &m->w_tid,
                  &m->w_tid2pdf, &m->w_trans, &m->w_keys_out, &m->w_sub, &m->w_full, &m->w_al_graph,
-                 &m->w_al_block, &m->w_al_bp, &m->w_al_cost, &m->w_al_ali, &m->w_al_path, &m->w_al_xlist, &m->w_al_xll, &m->w_item_desc, &m->w_fb_items, &m->w_al_tiles})
+                 &m->w_al_block, &m->w_al_bp, &m->w_al_cost, &m->w_al_ali, &m->w_al_path, &m->w_al_xlist, &m->w_al_xll, &m->w_item_desc, &m->w_fb_items, &m->w_al_tiles, &m->pin_al_tiles})
     b->release();
   for (int i = 0; i < 2; ++i) {
     m->pin_feats[i].release(); m->pin_ids[i].release(); m->pin_wts[i].release();

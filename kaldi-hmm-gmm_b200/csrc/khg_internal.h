@@ -203,6 +203,7 @@ struct khg_model {
   khg::Buf w_sub, w_full;                              // pdf-subset gather
   khg::Buf w_al_graph, w_al_block, w_al_bp, w_al_cost, w_al_ali, w_al_path;  // khg_align_batch (khg_align.cu)
   void *al_cache = nullptr;                                                   // AlignPrepCache (khg_align.cu)
+  khg::Buf pin_al_tiles;  // pinned host image of the tile lists (an upload from pageable memory would wait for the dense kernel running on the stream)
   khg::Buf w_al_tiles;                                                       // ... tile subset lists of the dense kernel
   khg::Buf w_al_xlist, w_al_xll;                                             // ... its exact host pass: flagged list, likelihood rows
   khg::Buf pin_feats[2], pin_ids[2], pin_wts[2];       // pinned staging for estep(HOST)
