@@ -116,7 +116,7 @@ khg_status khg_model_info(const khg_model *m, int32_t *dim, int32_t *num_pdfs,
 khg_status khg_model_dense_kernel(const khg_model *m, int32_t *kernel);
 /* Which kernel the bucketed statistics pass of khg_acc_stats_ali / khg_acc_stats_ali_tids / khg_estep (the per-frame
  * AccumAmDiagGmm::AccumulateForGmm, csrc/mle-am-diag-gmm.cc:41-52, of more than 2048 frames) runs for this model:
- * KHG_KERNEL_TCGEN05_F16 = the tensor-core kernel (dim <= 40, every pdf <= 32 Gaussians, parameters inside fp16's
+ * KHG_KERNEL_TCGEN05_F16 = the tensor-core kernel (dim <= 40, at least half of the Gaussians in pdfs of <= 32 — the items of larger pdfs run on the fp32 kernel —, parameters inside fp16's
  * range after a per-dimension power-of-two scaling; work items whose features or frame weights leave that range
  * are handed, on the device, to the fp32 kernel), KHG_KERNEL_SIMT = the fp32 kernel for everything.  Same
  * statistics either way (tests/test_gpu_stats_tc.py).  Builds the tensor-core operand pack on first use. */

@@ -851,7 +851,8 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
       KHG_TRY(stats_tc_launch(m, ta, st));
       a.item_list = m->w_fb_items.as<int32_t>();
       a.item_list_n = m->stk.fb_count;
-      stats_kernel<<<(unsigned)std::min<int64_t>(max_items, 2 * (int64_t)m->sm_count), 128, smem, st>>>(a);
+      // (a model with pdfs of more than 32 Gaussians hands their items over here: more CTAs than for the normally empty list)
+      stats_kernel<<<(unsigned)std::min<int64_t>(max_items, (m->stk.partial ? 12 : 2) * (int64_t)m->sm_count), 128, smem, st>>>(a);
     } else {
       stats_kernel<<<(unsigned)max_items, 128, smem, st>>>(a);
     }

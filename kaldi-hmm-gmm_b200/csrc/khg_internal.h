@@ -135,10 +135,12 @@ struct TcPack {
 // one bulk copy into shared memory) and the per-dimension power-of-two scaling they were built with.
 struct StatsTcPack {
   bool tried = false;      // build attempted for the current parameters
-  bool ready = false;      // shape and value range fit (dim <= 40, pdfs <= 32 Gaussians, |operand| <= 3e4)
+  bool ready = false;      // shape and value range fit (dim <= 40, at least half of the Gaussians in pdfs of <= 32, |operand| <= 3e4)
   int DP = 0;              // dim rounded up to 8
+  int np_max = 16;         // operand rows of the largest pdf that has an image (16 or 32)
+  bool partial = false;    // some pdfs have more than 32 Gaussians: no image (img_off < 0), their items go to the fp32 kernel
   uint8_t *img = nullptr;
-  int32_t *img_off = nullptr;  // P+1, 1024-byte units
+  int32_t *img_off = nullptr;  // P+1, 1024-byte units; -1: the pdf has no image
   float *ascale = nullptr;     // 64 floats: 2^-k_d
   float h_ascale[40] = {};     // host copy (passed to the kernel by value)
   float *unscale = nullptr;    // 128 floats: multiplier of each row of the statistics tile

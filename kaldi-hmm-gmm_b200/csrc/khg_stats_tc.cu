@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
   const float *mf = nullptr, *vf = nullptr, *gcf = nullptr;  // fp32 parameters of the current pdf inside its image
   int cur_p = -1, g0 = 0, ng = 0, NP = 16, acc_tiles = 0;  // (NP stays 16 when NPM == 16: the compiler folds it)
   uint32_t ph_a = 0, ph_b = 0, ph_m = 0;
-  bool b_pending = false, m_pending = false;
+  bool b_pending = false, m_pending = false, big_pdf = false;
   double my_like = 0.0, my_w = 0.0;
 
   auto wait_b = [&]() {
@@ -443,12 +443,16 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
       ng = a.offsets[p + 1] - g0;
       NP = (NPM == 16 || ng <= 16) ? 16 : 32;
       __syncthreads();  // every thread is past the previous pdf's phase A, softmax and flush: the image and Pt are free
-      if (tid == 0) {
-        const uint32_t bytes = (uint32_t)stk_img_bytes(NP, DP);
-        mbar_expect_tx(sBarM, bytes);
-        bulk_load(sBm, a.img + (size_t)a.img_off[p] * 1024, bytes, sBarM);
+      const int ioff = __ldg(a.img_off + p);
+      big_pdf = ioff < 0;  // more than 32 Gaussians: no image; the pdf's items are declined (fp32 kernel), like out-of-range rows
+      if (!big_pdf) {
+        if (tid == 0) {
+          const uint32_t bytes = (uint32_t)stk_img_bytes(NP, DP);
+          mbar_expect_tx(sBarM, bytes);
+          bulk_load(sBm, a.img + (size_t)ioff * 1024, bytes, sBarM);
+        }
+        m_pending = true;
       }
-      m_pending = true;
       mf = reinterpret_cast<const float *>(Bm + stk_f16_bytes(NP));  // (the fp32 part follows the operand rows)
       vf = mf + NP * pitch;
       gcf = vf + NP * pitch;
@@ -477,7 +481,7 @@ __global__ void __launch_bounds__(128, NPM == 16 ? KHG_STK_CTAS : 2) stats_tc_ke
     }
 #pragma unroll
     for (int d2 = 0; d2 < DP; ++d2) bad |= !(fabsf(xs[d2]) <= kF16FeatLimit);
-    bad = live && (bad || !(fabsf(w) <= kStkWeightLimit));
+    bad = live && (bad || big_pdf || !(fabsf(w) <= kStkWeightLimit));
     // next item's rows (index loaded one item ago), the index after that, L2 prefetch further ahead
     idx1 = idx2;
     if (kStkRegPrefetch) load_rows(idx1);
@@ -656,6 +660,7 @@ __global__ void __launch_bounds__(128) stk_pack_kernel(int P, int D, int DP, con
                                                        const float *__restrict__ ascale, uint8_t *__restrict__ img, int *__restrict__ flag) {
   const int p = blockIdx.x;
   const int g0 = offsets[p], ng = offsets[p + 1] - g0, NP = ng <= 16 ? 16 : 32;
+  if (img_off[p] < 0) return;  // (more than 32 Gaussians: the fp32 kernel's pdf)
   uint8_t *o = img + (size_t)img_off[p] * 1024;
   bool bad = false;
   for (int e = threadIdx.x; e < NP * 128; e += 128) {
@@ -700,7 +705,17 @@ void stats_tc_free(khg_model *m) {
   t = StatsTcPack();
 }
 
-bool stats_tc_shape_ok(const khg_model *m) { return m->dim >= 1 && m->dim <= kStkMaxDP && m->max_gp <= 32; }
+// dim <= 40 and at least half of the Gaussians in pdfs of at most 32 (larger pdfs keep the fp32 kernel, item by item)
+bool stats_tc_shape_ok(const khg_model *m) {
+  if (m->dim < 1 || m->dim > kStkMaxDP) return false;
+  if (m->max_gp <= 32) return true;
+  int64_t small = 0;
+  for (int p = 0; p < m->P; ++p) {
+    const int ng = m->h_offsets[p + 1] - m->h_offsets[p];
+    if (ng <= 32) small += ng;
+  }
+  return 2 * small >= (int64_t)m->G;
+}
 
 khg_status stats_tc_build(khg_model *m) {
   StatsTcPack &t = m->stk;
@@ -711,12 +726,21 @@ khg_status stats_tc_build(khg_model *m) {
   t.DP = (D + 7) / 8 * 8;
   std::vector<int32_t> off(P + 1);
   int64_t run = 0;
+  t.np_max = 16;
+  t.partial = false;
   for (int p = 0; p < P; ++p) {
-    off[p] = (int32_t)run;
     const int ng = m->h_offsets[p + 1] - m->h_offsets[p];
+    if (ng > 32) {
+      off[p] = -1;
+      t.partial = true;
+      continue;
+    }
+    off[p] = (int32_t)run;
+    if (ng > 16) t.np_max = 32;
     run += stk_img_units(ng <= 16 ? 16 : 32, t.DP);
   }
   off[P] = (int32_t)run;
+  if (run == 0) return KHG_OK;
   if (run > (int64_t)1 << 30) return KHG_OK;
   int *d_flag = nullptr;
   cudaStream_t st = m->stream;
@@ -774,7 +798,7 @@ khg_status stats_tc_launch(khg_model *m, StatsTcArgs a, cudaStream_t st) {
   a.miv = m->d_miv;
   a.iv = m->d_iv;
   a.gconsts = m->d_gconsts;
-  a.np_max = m->max_gp <= 16 ? 16 : 32;
+  a.np_max = t.np_max;
   KHG_CUDA_TRY(cudaMemsetAsync(t.fb_count, 0, sizeof(int), st));
   switch (t.DP / 8) {
     case 1: return a.np_max == 16 ? stk_launch_nu<1, 16>(m, a, st) : stk_launch_nu<1, 32>(m, a, st);

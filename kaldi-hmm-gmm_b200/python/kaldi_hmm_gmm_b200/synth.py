@@ -10,12 +10,17 @@ from typing import List, Sequence, Tuple
 import numpy as np
 
 
-def host_model(D: int, P: int, G: int, seed: int = 20230414) -> dict:
-    """g_p = G//P (+1 for the first G%P pdfs); mean ~ 3*N(0,1), var ~ U(0.5,2), weights =
+def host_model(D: int, P: int, G: int, seed: int = 20230414, size_range=None) -> dict:
+    """g_p = G//P (+1 for the first G%P pdfs), or uniform in size_range = (lo, hi) — a model after mix-up has pdfs of
+    very different sizes; G is then what the sizes sum to; mean ~ 3*N(0,1), var ~ U(0.5,2), weights =
     softmax(N(0,1)) within each pdf."""
     rng = np.random.default_rng(seed)
-    gp = np.full(P, G // P, np.int32)
-    gp[: G % P] += 1
+    if size_range is None:
+        gp = np.full(P, G // P, np.int32)
+        gp[: G % P] += 1
+    else:
+        gp = rng.integers(size_range[0], size_range[1] + 1, P).astype(np.int32)
+        G = int(gp.sum())
     offsets = np.zeros(P + 1, np.int32)
     np.cumsum(gp, out=offsets[1:])
     means = (3.0 * rng.standard_normal((G, D))).astype(np.float32)

@@ -163,6 +163,24 @@ def test_tc_and_fp32_kernels_agree_and_shapes_outside_fall_back(oracle):
         _assert_stats(got, oracle.acc_stats_ali(m2, f2, p2))
 
 
+def test_tc_stats_models_with_some_large_pdfs(oracle):
+    """A model after mix-up has pdfs of very different sizes.  Pdfs of more than 32 Gaussians have no tensor-core image:
+    their work items are declined one by one and go to the fp32 kernel through the device list, the others stay on the
+    tensor-core kernel (at least half of the Gaussians must be in pdfs of at most 32 for the model to take this path)."""
+    sizes = [40, 8, 12, 33, 5, 16, 20, 64, 9, 30, 7, 11, 3, 25]
+    for D, T, seed in ((40, 50000, 5), (39, 30000, 6), (13, 20000, 7)):
+        model, means, vars_ = _ragged_model(oracle, D, sizes, seed)
+        feats, pdf = ko.make_synthetic_frames(model, means, vars_, T)
+        w = np.random.default_rng(seed).uniform(0.5, 1.5, T).astype(np.float32)
+        got, tot, pf = _run(model, feats, pdf, w)
+        ref = oracle.acc_stats_ali(model, feats, pdf, frame_weights=w)
+        _assert_ll(pf, ref["per_frame"])
+        _assert_stats(got, ref)
+        for p_ in range(model.num_pdfs):  # every pdf, large or small, received its frames
+            sel = pdf == p_
+            assert abs(got["occ"][model.offsets[p_]:model.offsets[p_ + 1]].sum() - float(w[sel].astype(np.float64).sum())) <= 1e-4 * max(1.0, sel.sum())
+
+
 def test_tc_stats_nonfinite_features_raise_like_the_reference(oracle):
     """A NaN feature: the item goes to the fp32 kernel, which latches the reference's "Invalid answer"
     (csrc/diag-gmm.cc:158-163) — reported by the synchronising call."""

@@ -15,7 +15,11 @@ from kaldi_hmm_gmm_b200 import DeviceModel, DeviceStats  # noqa: E402
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c4"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 8_000_000
 D, P, G, _ = bench.CONFIGS[cfg]
-hm = bench.host_model(D, P, G)
+# KHG_BENCH_SIZES=lo,hi: pdf sizes uniform in [lo, hi] instead of G / P each (a model after mix-up)
+sizes = tuple(int(x) for x in os.environ["KHG_BENCH_SIZES"].split(",")) if os.environ.get("KHG_BENCH_SIZES") else None
+hm = bench.host_model(D, P, G, size_range=sizes)
+if sizes:
+    G = int(hm["gp"].sum())
 dm = DeviceModel(D, hm["offsets"])
 dm.upload(hm["weights"], hm["miv"], hm["iv"])
 feats, pdf = bench.device_frames(hm, n, 1, torch.device("cuda"))
@@ -39,7 +43,8 @@ except Exception:
 gbs = n * (4 * D + 4) / best / 1e9
 print(json.dumps({"workload": f"W-aligned {cfg}: D={D} P={P} G={G}, {n} frames resident in HBM", "frames_per_s": n / best,
                   "ms": best * 1e3, "algorithmic_GBps": gbs, "hbm_peak_GBps": peak, "frac_of_hbm_roof": gbs / peak,
-                  "lib": os.environ.get("KHG_B200_LIB", "in-tree")}))
+                  "lib": os.environ.get("KHG_B200_LIB", "in-tree"), "stats_kernel": int(dm.stats_kernel()),
+                  "pdf_sizes": "uniform %d..%d, %.0f %% of the Gaussians in pdfs of more than 32" % (sizes[0], sizes[1], 100.0 * hm["gp"][hm["gp"] > 32].sum() / G) if sizes else "G / P"}))
 
 if os.environ.get("KHG_BENCH_HOST"):
     # the same call with HOST inputs: pageable numpy arrays (what a Python caller hands in) and pinned ones
