@@ -92,7 +92,11 @@ khg_status h2d_copy(khg_model *m, void *dst, const void *src, size_t bytes, cuda
   }
   for (int i = 0; i < 2; ++i) {
     m->pin_stage[i].pinned = true;
-    KHG_TRY(m->pin_stage[i].reserve(kSlice));
+    if (m->pin_stage[i].reserve(kSlice) != KHG_OK) {  // no page-locked memory to be had: the driver's own copy
+      (void)cudaGetLastError();
+      KHG_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+      return KHG_OK;
+    }
     if (!m->ev_stage[i]) KHG_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_stage[i], cudaEventDisableTiming));
   }
   const size_t n_slices = (bytes + kSlice - 1) / kSlice;
@@ -134,7 +138,12 @@ khg_status d2h_copy_2d(khg_model *m, void *dst, size_t dst_pitch, const void *sr
   }
   for (int i = 0; i < 2; ++i) {
     m->pin_stage[i].pinned = true;
-    KHG_TRY(m->pin_stage[i].reserve(kSlice));
+    if (m->pin_stage[i].reserve(kSlice) != KHG_OK) {  // no page-locked memory to be had: the driver's own copy
+      (void)cudaGetLastError();
+      KHG_CUDA_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width, rows, cudaMemcpyDeviceToHost, m->stream));
+      KHG_CUDA_TRY(cudaStreamSynchronize(m->stream));
+      return KHG_OK;
+    }
     if (!m->ev_stage[i]) KHG_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_stage[i], cudaEventDisableTiming));
   }
   const size_t band = std::max<size_t>(1, kSlice / width), n_bands = (rows + band - 1) / band;
