@@ -861,7 +861,9 @@ static khg_status acc_device(khg_model *m, khg_stats *s, const float *d_feats, i
       a.item_list = m->w_fb_items.as<int32_t>();
       a.item_list_n = m->stk.fb_count;
       // (a model with pdfs of more than 32 Gaussians hands their items over here: more CTAs than for the normally empty list)
-      stats_kernel<<<(unsigned)std::min<int64_t>(max_items, (m->stk.partial ? 12 : 2) * (int64_t)m->sm_count), 128, smem, st>>>(a);
+      int list_ctas = m->stk.partial ? 12 : 2;
+      if (const char *e = getenv("KHG_STATS_LIST_CTAS_PER_SM")) list_ctas = std::max(1, atoi(e));  // experiments
+      stats_kernel<<<(unsigned)std::min<int64_t>(max_items, list_ctas * (int64_t)m->sm_count), 128, smem, st>>>(a);
     } else {
       stats_kernel<<<(unsigned)max_items, 128, smem, st>>>(a);
     }
