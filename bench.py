@@ -481,8 +481,8 @@ def align_workload(torch, dev, local, peaks, tf32_peak, rank, world, n_utts=2000
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    sampler = ClockSampler(local, 100).start()
-    t_dev = wall(f)
+    sampler = ClockSampler(local, 500).start()  # (a call is ~10 ms: NVML queries every 100 ms on every rank perturb it)
+    t_dev = wall(f, reps=6)
     ck = sampler.stop()
     prep_cached = int(_cabi.lib().khg_align_last_prep_cached())
     os.environ["KHG_ALIGN_PREP_CACHE"] = "0"  # the same with the graph preparation redone by every call (a first alignment)
